@@ -1,0 +1,1290 @@
+/*
+ * srrg2b_oracle.c -- CPU ORACLE (test infrastructure, NOT product code; see srrg2b_oracle.h).
+ *
+ * Restates, in plain C:
+ *   - the MultiAligner control flow        R/registration/aligners/multi_aligner_impl.cpp:46-263
+ *   - the slice glue                       R/registration/aligners/aligner_slice_processor_impl.cpp:19-93
+ *   - prior slices                         R/registration/aligners/aligner_slice_odometry_prior.cpp:6-37
+ *   - the termination criterion            R/registration/aligners/aligner_termination_criteria_impl.cpp:10-65
+ *   - the finder contract                  R/registration/correspondence_finder.h:41-124
+ * and the arithmetic those call in srrg2_solver / srrg2_core / srrg2_laser_slam_2d (absent from
+ * /root/reference, unpinned HEAD per srrg2_slam_interfaces/README.md:20-23): exact nearest
+ * neighbour inside max_distance + normal gate, point-to-point and point+normal ("plane") error
+ * factors with right-multiplicative SE(d) perturbation, Saturated/Cauchy/Clamp/Huber robustifiers,
+ * one Gauss-Newton step H dx = -b by Cholesky, X <- X * v2t(dx).  PARITY UNPINNED for that part.
+ *
+ * Numerics contract (shared with the CUDA product so results can be compared bit for bit):
+ *   * per-term arithmetic is fp32 with an explicitly written operation order; every fused
+ *     multiply-add is spelled fmaf(); compile with -ffp-contract=off so nothing else fuses;
+ *   * every per-correspondence contribution to H, b, chi is converted to 64-bit fixed point
+ *     (llrint(term * 2^k), k from orc_scales) and summed as integers: the sums are exact, hence
+ *     independent of summation order, thread count and GPU count;
+ *   * the 6x6 / 3x3 solve, pose update and prior factors are fp64 with plain (unfused) operations
+ *     and in-house sin/cos/atan2/log so that host libm differences cannot leak in.
+ */
+#include "srrg2b_oracle.h"
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <limits.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* ------------------------------------------------------------------------------------------ */
+/* deterministic elementary functions (fp64, only + - * / sqrt fma)                            */
+/* ------------------------------------------------------------------------------------------ */
+void orc_sincos(double x, double* s, double* c) {
+  const double two_over_pi = 6.36619772367581382433e-01;
+  const double pio2_1 = 1.57079632673412561417e+00; /* first 33 bits of pi/2 */
+  const double pio2_2 = 6.07710050650619224932e-11; /* pi/2 - pio2_1 */
+  double k = nearbyint(x * two_over_pi);
+  double r = fma(-k, pio2_1, x);
+  r = fma(-k, pio2_2, r);
+  double z = r * r;
+  /* Taylor/minimax kernels on |r| <= pi/4 (fdlibm __kernel_sin/__kernel_cos coefficients) */
+  double ps = 1.58969099521155010221e-10;
+  ps = fma(ps, z, -2.50507602534068634195e-08);
+  ps = fma(ps, z, 2.75573137070700676789e-06);
+  ps = fma(ps, z, -1.98412698298579493134e-04);
+  ps = fma(ps, z, 8.33333333332248946124e-03);
+  ps = fma(ps, z, -1.66666666666666324348e-01);
+  double sr = fma(r * z, ps, r);
+  double pc = -1.13596475577881948265e-11;
+  pc = fma(pc, z, 2.08757232129817482790e-09);
+  pc = fma(pc, z, -2.75573143513906633035e-07);
+  pc = fma(pc, z, 2.48015872894767294178e-05);
+  pc = fma(pc, z, -1.38888888888741095749e-03);
+  pc = fma(pc, z, 4.16666666666666019037e-02);
+  double cr = fma(z * z, pc, fma(-0.5, z, 1.0));
+  long long q = (long long) k;
+  switch ((int) (q & 3)) {
+    case 0: *s = sr; *c = cr; break;
+    case 1: *s = cr; *c = -sr; break;
+    case 2: *s = -sr; *c = -cr; break;
+    default: *s = -cr; *c = sr; break;
+  }
+}
+
+static double orc_atan_unit(double z) { /* 0 <= z <= 1 */
+  /* three half-angle reductions: atan z = 2 atan( z / (1 + sqrt(1+z^2)) ) */
+  for (int i = 0; i < 3; ++i) {
+    z = z / (1.0 + sqrt(1.0 + z * z));
+  }
+  double z2 = z * z;
+  double p = 1.0 / 19.0;
+  p = fma(-p, z2, 1.0 / 17.0);
+  p = fma(-p, z2, 1.0 / 15.0);
+  p = fma(-p, z2, 1.0 / 13.0);
+  p = fma(-p, z2, 1.0 / 11.0);
+  p = fma(-p, z2, 1.0 / 9.0);
+  p = fma(-p, z2, 1.0 / 7.0);
+  p = fma(-p, z2, 1.0 / 5.0);
+  p = fma(-p, z2, 1.0 / 3.0);
+  p = fma(-p, z2, 1.0);
+  return 8.0 * (z * p);
+}
+
+double orc_atan2(double y, double x) {
+  const double pi = 3.14159265358979311600e+00;
+  const double pio2 = 1.57079632679489655800e+00;
+  double ax = fabs(x), ay = fabs(y);
+  double a;
+  if (ax == 0.0 && ay == 0.0) {
+    return 0.0;
+  }
+  if (ay <= ax) {
+    a = orc_atan_unit(ay / ax);
+  } else {
+    a = pio2 - orc_atan_unit(ax / ay);
+  }
+  if (x < 0.0) {
+    a = pi - a;
+  }
+  return (y < 0.0) ? -a : a;
+}
+
+double orc_log(double x) { /* x > 0, finite */
+  const double ln2 = 6.93147180559945286227e-01;
+  int e;
+  double m = frexp(x, &e); /* m in [0.5,1) */
+  if (m < 7.07106781186547572737e-01) {
+    m = m * 2.0;
+    e -= 1;
+  }
+  double z = (m - 1.0) / (m + 1.0);
+  double z2 = z * z;
+  double p = 1.0 / 25.0;
+  for (int d = 23; d >= 1; d -= 2) {
+    p = fma(p, z2, 1.0 / (double) d);
+  }
+  return fma((double) e, ln2, 2.0 * (z * p));
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* small SE(d) helpers; matrices are row-major (dim+1)x(dim+1) floats                          */
+/* ------------------------------------------------------------------------------------------ */
+static void embed4(int dim, const float* M, float* M4) {
+  if (dim == 3) {
+    memcpy(M4, M, 16 * sizeof(float));
+    return;
+  }
+  memset(M4, 0, 16 * sizeof(float));
+  M4[0] = M[0]; M4[1] = M[1]; M4[3] = M[2];
+  M4[4] = M[3]; M4[5] = M[4]; M4[7] = M[5];
+  M4[10] = 1.f; M4[15] = 1.f;
+}
+
+static void unembed4(int dim, const float* M4, float* M) {
+  if (dim == 3) {
+    memcpy(M, M4, 16 * sizeof(float));
+    return;
+  }
+  M[0] = M4[0]; M[1] = M4[1]; M[2] = M4[3];
+  M[3] = M4[4]; M[4] = M4[5]; M[5] = M4[7];
+  M[6] = 0.f; M[7] = 0.f; M[8] = 1.f;
+}
+
+/* C = A*B for isometries embedded in 4x4; fp64 plain ops, rounded to float */
+static void mul4(const float* A, const float* B, float* C) {
+  float out[16];
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 4; ++j) {
+      double c = (double) A[i * 4 + 0] * (double) B[0 * 4 + j];
+      c = c + (double) A[i * 4 + 1] * (double) B[1 * 4 + j];
+      c = c + (double) A[i * 4 + 2] * (double) B[2 * 4 + j];
+      if (j == 3) {
+        c = c + (double) A[i * 4 + 3];
+      }
+      out[i * 4 + j] = (float) c;
+    }
+  }
+  out[12] = 0.f; out[13] = 0.f; out[14] = 0.f; out[15] = 1.f;
+  memcpy(C, out, sizeof(out));
+}
+
+/* inverse of an isometry: [R t]^-1 = [R^T, -R^T t] */
+static void inv4(const float* A, float* Ai) {
+  float out[16];
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) {
+      out[i * 4 + j] = A[j * 4 + i];
+    }
+  }
+  for (int i = 0; i < 3; ++i) {
+    double c = (double) A[0 * 4 + i] * (double) A[0 * 4 + 3];
+    c = c + (double) A[1 * 4 + i] * (double) A[1 * 4 + 3];
+    c = c + (double) A[2 * 4 + i] * (double) A[2 * 4 + 3];
+    out[i * 4 + 3] = (float) (-c);
+  }
+  out[12] = 0.f; out[13] = 0.f; out[14] = 0.f; out[15] = 1.f;
+  memcpy(Ai, out, sizeof(out));
+}
+
+void orc_mul(int dim, const float* A, const float* B, float* C) {
+  float A4[16], B4[16], C4[16];
+  embed4(dim, A, A4); embed4(dim, B, B4);
+  mul4(A4, B4, C4);
+  unembed4(dim, C4, C);
+}
+
+void orc_inverse(int dim, const float* A, float* Ai) {
+  float A4[16], I4[16];
+  embed4(dim, A, A4);
+  inv4(A4, I4);
+  unembed4(dim, I4, Ai);
+}
+
+static void quat_from_R(const double R[9], double q[4] /* x y z w */) {
+  double tr = R[0] + R[4] + R[8];
+  double x, y, z, w, s;
+  if (tr > 0.0) {
+    s = sqrt(tr + 1.0) * 2.0;
+    w = 0.25 * s; x = (R[7] - R[5]) / s; y = (R[2] - R[6]) / s; z = (R[3] - R[1]) / s;
+  } else if (R[0] > R[4] && R[0] > R[8]) {
+    s = sqrt(1.0 + R[0] - R[4] - R[8]) * 2.0;
+    w = (R[7] - R[5]) / s; x = 0.25 * s; y = (R[1] + R[3]) / s; z = (R[2] + R[6]) / s;
+  } else if (R[4] > R[8]) {
+    s = sqrt(1.0 + R[4] - R[0] - R[8]) * 2.0;
+    w = (R[2] - R[6]) / s; x = (R[1] + R[3]) / s; y = 0.25 * s; z = (R[5] + R[7]) / s;
+  } else {
+    s = sqrt(1.0 + R[8] - R[0] - R[4]) * 2.0;
+    w = (R[3] - R[1]) / s; x = (R[2] + R[6]) / s; y = (R[5] + R[7]) / s; z = 0.25 * s;
+  }
+  double n = sqrt(x * x + y * y + z * z + w * w);
+  x = x / n; y = y / n; z = z / n; w = w / n;
+  if (w < 0.0) {
+    x = -x; y = -y; z = -z; w = -w;
+  }
+  q[0] = x; q[1] = y; q[2] = z; q[3] = w;
+}
+
+static void R_from_quat(const double q[4], double R[9]) {
+  double x = q[0], y = q[1], z = q[2], w = q[3];
+  double xx = x * x, yy = y * y, zz = z * z;
+  double xy = x * y, xz = x * z, yz = y * z;
+  double wx = w * x, wy = w * y, wz = w * z;
+  R[0] = 1.0 - 2.0 * (yy + zz); R[1] = 2.0 * (xy - wz); R[2] = 2.0 * (xz + wy);
+  R[3] = 2.0 * (xy + wz); R[4] = 1.0 - 2.0 * (xx + zz); R[5] = 2.0 * (yz - wx);
+  R[6] = 2.0 * (xz - wy); R[7] = 2.0 * (yz + wx); R[8] = 1.0 - 2.0 * (xx + yy);
+}
+
+/* srrg2_core fixTransform (called at R/registration/aligners/multi_aligner_impl.cpp:92):
+ * re-orthonormalise the rotation. Upstream body is not in /root/reference; restated as
+ * R -> unit quaternion -> R (3D) and (c,s)/hypot (2D). */
+void orc_fix_transform(int dim, float* T) {
+  if (dim == 3) {
+    double R[9], q[4];
+    for (int i = 0; i < 3; ++i) {
+      for (int j = 0; j < 3; ++j) {
+        R[i * 3 + j] = (double) T[i * 4 + j];
+      }
+    }
+    quat_from_R(R, q);
+    R_from_quat(q, R);
+    for (int i = 0; i < 3; ++i) {
+      for (int j = 0; j < 3; ++j) {
+        T[i * 4 + j] = (float) R[i * 3 + j];
+      }
+    }
+    T[12] = 0.f; T[13] = 0.f; T[14] = 0.f; T[15] = 1.f;
+  } else {
+    double c = 0.5 * ((double) T[0] + (double) T[4]);
+    double s = 0.5 * ((double) T[3] - (double) T[1]);
+    double n = sqrt(c * c + s * s);
+    c = c / n; s = s / n;
+    T[0] = (float) c; T[1] = (float) (-s);
+    T[3] = (float) s; T[4] = (float) c;
+    T[6] = 0.f; T[7] = 0.f; T[8] = 1.f;
+  }
+}
+
+/* geometry{2,3}d::t2v : 3D -> [t ; unit-quaternion vector part, w >= 0], 2D -> [t ; theta] */
+void orc_t2v(int dim, const float* T, float* v) {
+  if (dim == 3) {
+    double R[9], q[4];
+    for (int i = 0; i < 3; ++i) {
+      for (int j = 0; j < 3; ++j) {
+        R[i * 3 + j] = (double) T[i * 4 + j];
+      }
+    }
+    quat_from_R(R, q);
+    v[0] = T[3]; v[1] = T[7]; v[2] = T[11];
+    v[3] = (float) q[0]; v[4] = (float) q[1]; v[5] = (float) q[2];
+  } else {
+    v[0] = T[2]; v[1] = T[5];
+    v[2] = (float) orc_atan2((double) T[3], (double) T[0]);
+  }
+}
+
+/* perturbation -> isometry (fp64), D = [Rd td] 3x4 row-major (4x4 embedding rows 0..2) */
+static void v2t_d(int dim, int variable, const double* dx, double D[12]) {
+  memset(D, 0, 12 * sizeof(double));
+  if (dim == 2) {
+    double s, c;
+    orc_sincos(dx[2], &s, &c);
+    D[0] = c; D[1] = -s; D[3] = dx[0];
+    D[4] = s; D[5] = c; D[7] = dx[1];
+    D[10] = 1.0;
+    return;
+  }
+  double R[9];
+  if (variable == ORC_VAR_SE3_QUAT_RIGHT) {
+    double q[4];
+    double x = dx[3], y = dx[4], z = dx[5];
+    double n2 = x * x + y * y + z * z;
+    if (n2 < 1.0) {
+      q[3] = sqrt(1.0 - n2);
+      q[0] = x; q[1] = y; q[2] = z;
+    } else {
+      double n = sqrt(n2);
+      q[3] = 0.0;
+      q[0] = x / n; q[1] = y / n; q[2] = z / n;
+    }
+    R_from_quat(q, R);
+  } else { /* Euler: R = Rx * Ry * Rz */
+    double sx, cx, sy, cy, sz, cz;
+    orc_sincos(dx[3], &sx, &cx);
+    orc_sincos(dx[4], &sy, &cy);
+    orc_sincos(dx[5], &sz, &cz);
+    R[0] = cy * cz;                R[1] = -cy * sz;               R[2] = sy;
+    R[3] = cx * sz + sx * sy * cz; R[4] = cx * cz - sx * sy * sz; R[5] = -sx * cy;
+    R[6] = sx * sz - cx * sy * cz; R[7] = sx * cz + cx * sy * sz; R[8] = cx * cy;
+  }
+  for (int i = 0; i < 3; ++i) {
+    D[i * 4 + 0] = R[i * 3 + 0]; D[i * 4 + 1] = R[i * 3 + 1]; D[i * 4 + 2] = R[i * 3 + 2];
+    D[i * 4 + 3] = dx[i];
+  }
+}
+
+void orc_v2t(int dim, int variable, const float* v, float* T) {
+  double dx[6] = {0, 0, 0, 0, 0, 0}, D[12];
+  int P = (dim == 3) ? 6 : 3;
+  for (int i = 0; i < P; ++i) {
+    dx[i] = (double) v[i];
+  }
+  v2t_d(dim, variable, dx, D);
+  float T4[16];
+  for (int i = 0; i < 12; ++i) {
+    T4[i] = (float) D[i];
+  }
+  T4[12] = 0.f; T4[13] = 0.f; T4[14] = 0.f; T4[15] = 1.f;
+  unembed4(dim, T4, T);
+}
+
+/* X <- X * v2t(dx)  (Variable*Right::applyPerturbation), X embedded 4x4 float */
+static void apply_perturbation(int dim, int variable, const double* dx, float* X4) {
+  double D[12];
+  float dxf[6];
+  double dxr[6] = {0, 0, 0, 0, 0, 0};
+  int P = (dim == 3) ? 6 : 3;
+  for (int i = 0; i < P; ++i) { /* upstream perturbation vectors are float */
+    dxf[i] = (float) dx[i];
+    dxr[i] = (double) dxf[i];
+  }
+  v2t_d(dim, variable, dxr, D);
+  float out[16];
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 4; ++j) {
+      double c = (double) X4[i * 4 + 0] * D[0 * 4 + j];
+      c = c + (double) X4[i * 4 + 1] * D[1 * 4 + j];
+      c = c + (double) X4[i * 4 + 2] * D[2 * 4 + j];
+      if (j == 3) {
+        c = c + (double) X4[i * 4 + 3];
+      }
+      out[i * 4 + j] = (float) c;
+    }
+  }
+  out[12] = 0.f; out[13] = 0.f; out[14] = 0.f; out[15] = 1.f;
+  memcpy(X4, out, sizeof(out));
+}
+
+/* Cholesky solve of H dx = -b (H full row-major PxP). returns 1 on success */
+static int chol_solve(int P, const double* H, const double* b, double* dx) {
+  double L[36];
+  memset(L, 0, sizeof(L));
+  for (int j = 0; j < P; ++j) {
+    double d = H[j * P + j];
+    for (int k = 0; k < j; ++k) {
+      d = d - L[j * P + k] * L[j * P + k];
+    }
+    if (!(d > 0.0) || !(d < 1e300)) {
+      return 0;
+    }
+    double ljj = sqrt(d);
+    L[j * P + j] = ljj;
+    for (int i = j + 1; i < P; ++i) {
+      double s = H[i * P + j];
+      for (int k = 0; k < j; ++k) {
+        s = s - L[i * P + k] * L[j * P + k];
+      }
+      L[i * P + j] = s / ljj;
+    }
+  }
+  double y[6];
+  for (int i = 0; i < P; ++i) {
+    double s = -b[i];
+    for (int k = 0; k < i; ++k) {
+      s = s - L[i * P + k] * y[k];
+    }
+    y[i] = s / L[i * P + i];
+  }
+  for (int i = P - 1; i >= 0; --i) {
+    double s = y[i];
+    for (int k = i + 1; k < P; ++k) {
+      s = s - L[k * P + i] * dx[k];
+    }
+    dx[i] = s / L[i * P + i];
+  }
+  for (int i = 0; i < P; ++i) {
+    if (!(dx[i] == dx[i]) || fabs(dx[i]) > 1e300) {
+      return 0;
+    }
+  }
+  return 1;
+}
+
+int orc_solve_update(int dim, int variable, const double* H, const double* b, float* T) {
+  int P = (dim == 3) ? 6 : 3;
+  double dx[6];
+  if (!chol_solve(P, H, b, dx)) {
+    return 0;
+  }
+  float T4[16];
+  embed4(dim, T, T4);
+  apply_perturbation(dim, variable, dx, T4);
+  unembed4(dim, T4, T);
+  return 1;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* point access + fp32 transform with pinned operation order                                   */
+/* ------------------------------------------------------------------------------------------ */
+static inline void get3(const float* a, int dim, int64_t i, float* o) {
+  if (dim == 3) {
+    o[0] = a[3 * i]; o[1] = a[3 * i + 1]; o[2] = a[3 * i + 2];
+  } else {
+    o[0] = a[2 * i]; o[1] = a[2 * i + 1]; o[2] = 0.f;
+  }
+}
+
+static inline void xf_point(const float* S4, const float* m, float* q) {
+  for (int r = 0; r < 3; ++r) {
+    float t = S4[r * 4 + 0] * m[0];
+    t = fmaf(S4[r * 4 + 1], m[1], t);
+    t = fmaf(S4[r * 4 + 2], m[2], t);
+    q[r] = t + S4[r * 4 + 3];
+  }
+}
+
+static inline void xf_dir(const float* S4, const float* n, float* o) {
+  for (int r = 0; r < 3; ++r) {
+    float t = S4[r * 4 + 0] * n[0];
+    t = fmaf(S4[r * 4 + 1], n[1], t);
+    t = fmaf(S4[r * 4 + 2], n[2], t);
+    o[r] = t;
+  }
+}
+
+static inline float dist2(const float* q, const float* f) {
+  float dx = q[0] - f[0], dy = q[1] - f[1], dz = q[2] - f[2];
+  return fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+}
+
+static inline float dot3(const float* a, const float* b) {
+  return fmaf(a[2], b[2], fmaf(a[1], b[1], a[0] * b[0]));
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* exact NN index: kd-tree with full backtracking, lexicographic (d2, index) minimum            */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int32_t lo, hi, left, right, axis;
+  float split;
+} kdnode;
+
+struct orc_index {
+  int dim, method;
+  int64_t n;        /* fixed cloud size */
+  float* pts;       /* n x 3 padded */
+  int32_t* perm;    /* valid point indices, kd order */
+  float* lpts;      /* points in perm order (x3) */
+  int64_t nvalid;
+  kdnode* nodes;
+  int32_t nnodes, cap;
+};
+
+#define KD_LEAF 8
+
+static void kd_select(const float* pts, int32_t* perm, int64_t lo, int64_t hi, int64_t k, int axis) {
+  /* quickselect: afterwards perm[k] holds the k-th smallest along axis in [lo,hi) */
+  while (hi - lo > 1) {
+    float pv = pts[3 * (int64_t) perm[lo + (hi - lo) / 2] + axis];
+    int64_t i = lo, j = hi - 1;
+    while (i <= j) {
+      while (pts[3 * (int64_t) perm[i] + axis] < pv) ++i;
+      while (pts[3 * (int64_t) perm[j] + axis] > pv) --j;
+      if (i <= j) {
+        int32_t t = perm[i]; perm[i] = perm[j]; perm[j] = t;
+        ++i; --j;
+      }
+    }
+    if (k <= j) {
+      hi = j + 1;
+    } else if (k >= i) {
+      lo = i;
+    } else {
+      return;
+    }
+  }
+}
+
+static int32_t kd_build(orc_index* ix, int64_t lo, int64_t hi) {
+  if (ix->nnodes == ix->cap) {
+    ix->cap = ix->cap ? ix->cap * 2 : 1024;
+    ix->nodes = (kdnode*) realloc(ix->nodes, sizeof(kdnode) * (size_t) ix->cap);
+  }
+  int32_t id = ix->nnodes++;
+  kdnode nd;
+  nd.lo = (int32_t) lo; nd.hi = (int32_t) hi; nd.left = -1; nd.right = -1; nd.axis = 0; nd.split = 0.f;
+  if (hi - lo > KD_LEAF) {
+    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int64_t i = lo; i < hi; ++i) {
+      const float* p = ix->pts + 3 * (int64_t) ix->perm[i];
+      for (int a = 0; a < 3; ++a) {
+        if (p[a] < mn[a]) mn[a] = p[a];
+        if (p[a] > mx[a]) mx[a] = p[a];
+      }
+    }
+    int axis = 0;
+    float ext = mx[0] - mn[0];
+    for (int a = 1; a < 3; ++a) {
+      if (mx[a] - mn[a] > ext) {
+        ext = mx[a] - mn[a];
+        axis = a;
+      }
+    }
+    if (ext > 0.f) {
+      int64_t mid = lo + (hi - lo) / 2;
+      kd_select(ix->pts, ix->perm, lo, hi, mid, axis);
+      nd.axis = axis;
+      nd.split = ix->pts[3 * (int64_t) ix->perm[mid] + axis];
+      ix->nodes[id] = nd;
+      int32_t l = kd_build(ix, lo, mid);
+      int32_t r = kd_build(ix, mid, hi);
+      nd.left = l; nd.right = r;
+    }
+  }
+  ix->nodes[id] = nd;
+  return id;
+}
+
+orc_index* orc_index_create(int dim, const orc_cloud* fixed, int method) {
+  orc_index* ix = (orc_index*) calloc(1, sizeof(orc_index));
+  ix->dim = dim; ix->method = method; ix->n = fixed->n;
+  ix->pts = (float*) malloc(sizeof(float) * 3 * (size_t) (fixed->n + 1));
+  ix->perm = (int32_t*) malloc(sizeof(int32_t) * (size_t) (fixed->n + 1));
+  int64_t nv = 0;
+  for (int64_t i = 0; i < fixed->n; ++i) {
+    get3(fixed->coords, dim, i, ix->pts + 3 * i);
+    if (!fixed->valid || fixed->valid[i]) {
+      ix->perm[nv++] = (int32_t) i;
+    }
+  }
+  ix->nvalid = nv;
+  if (method == ORC_NN_KDTREE && nv > 0) {
+    kd_build(ix, 0, nv);
+  }
+  ix->lpts = (float*) malloc(sizeof(float) * 3 * (size_t) (nv + 1));
+  for (int64_t i = 0; i < nv; ++i) {
+    memcpy(ix->lpts + 3 * i, ix->pts + 3 * (int64_t) ix->perm[i], 3 * sizeof(float));
+  }
+  return ix;
+}
+
+void orc_index_free(orc_index* ix) {
+  if (!ix) return;
+  free(ix->pts); free(ix->perm); free(ix->lpts); free(ix->nodes); free(ix);
+}
+
+static void kd_search(const orc_index* ix, int32_t node, const float* q, float* best_d2, int32_t* best_i) {
+  const kdnode* nd = &ix->nodes[node];
+  if (nd->left < 0) {
+    for (int32_t i = nd->lo; i < nd->hi; ++i) {
+      float d2 = dist2(q, ix->lpts + 3 * (int64_t) i);
+      int32_t id = ix->perm[i];
+      if (d2 < *best_d2 || (d2 == *best_d2 && id < *best_i)) {
+        *best_d2 = d2; *best_i = id;
+      }
+    }
+    return;
+  }
+  float diff = q[nd->axis] - nd->split;
+  int32_t near = diff < 0.f ? nd->left : nd->right;
+  int32_t far = diff < 0.f ? nd->right : nd->left;
+  kd_search(ix, near, q, best_d2, best_i);
+  if (diff * diff <= *best_d2) {
+    kd_search(ix, far, q, best_d2, best_i);
+  }
+}
+
+static int32_t nn_query(const orc_index* ix, const float* q, float md2, float* d2_out) {
+  float best = md2;
+  int32_t bi = INT32_MAX;
+  if (ix->method == ORC_NN_KDTREE) {
+    if (ix->nvalid > 0) {
+      kd_search(ix, 0, q, &best, &bi);
+    }
+  } else {
+    for (int64_t i = 0; i < ix->nvalid; ++i) {
+      float d2 = dist2(q, ix->lpts + 3 * i);
+      int32_t id = ix->perm[i];
+      if (d2 < best || (d2 == best && id < bi)) {
+        best = d2; bi = id;
+      }
+    }
+  }
+  if (bi == INT32_MAX) {
+    return -1;
+  }
+  *d2_out = best;
+  return bi;
+}
+
+/* projective association: index image of the fixed cloud (nearest depth wins, then lowest index) */
+static int proj_pixel(const orc_finder_params* fp, const float* p, int* col, int* row) {
+  float z = p[2];
+  if (!(z > fp->min_depth) || !(z < fp->max_depth)) {
+    return 0;
+  }
+  float u = fmaf(fp->fx, p[0] / z, fp->cx);
+  float v = fmaf(fp->fy, p[1] / z, fp->cy);
+  float uf = floorf(u + 0.5f), vf = floorf(v + 0.5f);
+  if (!(uf >= 0.f) || !(vf >= 0.f) || !(uf < (float) fp->width) || !(vf < (float) fp->height)) {
+    return 0;
+  }
+  *col = (int) uf; *row = (int) vf;
+  return 1;
+}
+
+int orc_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+  return omp_get_max_threads();
+#else
+  (void) n;
+  return 1;
+#endif
+}
+
+/* a3 -- CorrespondenceFinder_::compute() (interface R/registration/correspondence_finder.h:56,
+ * called from R/registration/aligners/aligner_slice_processor_impl.cpp:43).  For every valid moving
+ * point j: q = S m_j; nearest valid fixed point (lowest index on ties) with |q-f|^2 <= max_d^2;
+ * rejected if n_f . (R_S n_m) < normal_cos; response = |q - f|. */
+int orc_find(const orc_index* index, int dim, const orc_cloud* fixed, const orc_cloud* moving,
+             const float* S, const orc_finder_params* fp, int32_t* fidx, float* resp) {
+  float S4[16];
+  embed4(dim, S, S4);
+  const float md2 = fp->max_distance * fp->max_distance;
+  const int use_normals = (fixed->normals && moving->normals && fp->normal_cos > -1.f);
+  int64_t* image = NULL;
+  if (fp->kind == ORC_FINDER_PROJECTIVE) {
+    if (dim != 3) return 1;
+    int64_t npx = (int64_t) fp->width * fp->height;
+    image = (int64_t*) malloc(sizeof(int64_t) * (size_t) npx);
+    for (int64_t i = 0; i < npx; ++i) image[i] = INT64_MAX;
+    for (int64_t i = 0; i < fixed->n; ++i) {
+      if (fixed->valid && !fixed->valid[i]) continue;
+      float f[3];
+      int c, r;
+      get3(fixed->coords, dim, i, f);
+      if (!proj_pixel(fp, f, &c, &r)) continue;
+      uint32_t zb;
+      memcpy(&zb, &f[2], 4);
+      int64_t key = ((int64_t) zb << 32) | (int64_t) (uint32_t) i;
+      int64_t* px = &image[(int64_t) r * fp->width + c];
+      if (key < *px) *px = key;
+    }
+  }
+#pragma omp parallel for schedule(static)
+  for (int64_t j = 0; j < moving->n; ++j) {
+    fidx[j] = -1;
+    resp[j] = 0.f;
+    if (moving->valid && !moving->valid[j]) continue;
+    float m[3], q[3];
+    get3(moving->coords, dim, j, m);
+    xf_point(S4, m, q);
+    float d2 = 0.f;
+    int32_t bi = -1;
+    if (fp->kind == ORC_FINDER_PROJECTIVE) {
+      int c, r;
+      if (!proj_pixel(fp, q, &c, &r)) continue;
+      int64_t key = image[(int64_t) r * fp->width + c];
+      if (key == INT64_MAX) continue;
+      bi = (int32_t) (key & 0xffffffffLL);
+      float f[3];
+      get3(fixed->coords, dim, bi, f);
+      d2 = dist2(q, f);
+      if (!(d2 <= md2)) continue;
+    } else {
+      bi = nn_query(index, q, md2, &d2);
+      if (bi < 0) continue;
+    }
+    if (use_normals) {
+      float nm[3], nq[3], nf[3];
+      get3(moving->normals, dim, j, nm);
+      xf_dir(S4, nm, nq);
+      get3(fixed->normals, dim, bi, nf);
+      if (dot3(nf, nq) < fp->normal_cos) continue;
+    }
+    fidx[j] = bi;
+    resp[j] = sqrtf(d2);
+  }
+  free(image);
+  return 0;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* fixed-point scales                                                                          */
+/* ------------------------------------------------------------------------------------------ */
+static int ceil_log2f_(float x) { /* smallest e with x <= 2^e (x > 0) */
+  int e;
+  if (!(x > 0.f)) return 0;
+  (void) frexpf(x, &e);
+  return e;
+}
+
+float orc_coord_bound(int dim, const orc_cloud* moving) {
+  float b = 0.f;
+  for (int64_t i = 0; i < moving->n * dim; ++i) {
+    float a = fabsf(moving->coords[i]);
+    if (a > b) b = a;
+  }
+  return b;
+}
+
+int orc_scales(int dim, int64_t n_global, float coord_bound, const orc_finder_params* fp,
+               const orc_factor_params* fa, orc_scales_t* out) {
+  (void) dim;
+  int nb = 0;
+  while (((int64_t) 1 << nb) < n_global) ++nb;
+  float jm = 4.f * coord_bound;
+  if (jm < 2.f) jm = 2.f;
+  int Jb = ceil_log2f_(jm);
+  float wm = fa->info_point > fa->info_normal ? fa->info_point : fa->info_normal;
+  if (!(wm > 1.f)) wm = 1.f;
+  int wb = ceil_log2f_(wm);
+  float em = fp->max_distance > 2.f ? fp->max_distance : 2.f;
+  int eb = ceil_log2f_(em);
+  int kH = 62 - nb - 2 - wb - 2 * Jb;
+  int kb = 62 - nb - 2 - wb - Jb - eb;
+  int kc = 62 - nb - 2 - wb - 2 * eb;
+  if (kH > 60) kH = 60;
+  if (kb > 60) kb = 60;
+  if (kc > 60) kc = 60;
+  out->kH = kH; out->kb = kb; out->kchi = kc;
+  return 0;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* a5 -- per-correspondence linearisation (FactorCorrespondenceDriven_<F,...> inside            */
+/* Solver::compute(), reached from R/registration/aligners/multi_aligner_impl.cpp:112)          */
+/* ------------------------------------------------------------------------------------------ */
+static inline int64_t to_fix(float v, int k) {
+  return llrint(ldexp((double) v, k));
+}
+
+/* robustifier on chi with threshold tau -> weight w, robustified rho; returns 1 if kernelized.
+ * RobustifierBase::param_chi_threshold is the in-tree evidence (multi_aligner_impl.cpp:194-196);
+ * bodies restated from srrg2_solver conventions (unpinned). */
+static int robustify(int kind, float tau, float chi, float* w, float* rho) {
+  *w = 1.f; *rho = chi;
+  if (kind == ORC_ROB_NONE) return 0;
+  if (!(chi > tau)) return 0;
+  switch (kind) {
+    case ORC_ROB_SATURATED:
+    case ORC_ROB_CLAMP:
+      *w = 0.f; *rho = tau;
+      return 1;
+    case ORC_ROB_CAUCHY: {
+      float r = chi / tau;
+      *w = 1.f / (1.f + r);
+      *rho = (float) ((double) tau * orc_log(1.0 + (double) r));
+      return 1;
+    }
+    case ORC_ROB_HUBER: {
+      float delta = sqrtf(tau);
+      float sc = sqrtf(chi);
+      *w = delta / sc;
+      *rho = fmaf(2.f * delta, sc, -tau);
+      return 1;
+    }
+    default: return 0;
+  }
+}
+
+/* builds error rows e[E], info w[E], Jacobian J[E][P]; returns E */
+static int build_rows(int dim, int variable, int factor, const float* S4, const float* m, const float* nm,
+                      const float* f, const float* nf, const float* q, const float* nq,
+                      float ip, float in_, float* e, float* om, float J[4][6]) {
+  const float rs = (dim == 3 && variable == ORC_VAR_SE3_QUAT_RIGHT) ? 2.f : 1.f;
+  float d[3] = {q[0] - f[0], q[1] - f[1], q[2] - f[2]};
+  if (dim == 3) {
+    if (factor == ORC_FACTOR_P2P) {
+      for (int r = 0; r < 3; ++r) {
+        const float* R = S4 + r * 4;
+        J[r][0] = R[0]; J[r][1] = R[1]; J[r][2] = R[2];
+        float t;
+        t = R[2] * m[1]; J[r][3] = -rs * fmaf(R[1], m[2], -t);
+        t = R[0] * m[2]; J[r][4] = -rs * fmaf(R[2], m[0], -t);
+        t = R[1] * m[0]; J[r][5] = -rs * fmaf(R[0], m[1], -t);
+        e[r] = d[r]; om[r] = ip;
+      }
+      return 3;
+    }
+    float a[3];
+    for (int c = 0; c < 3; ++c) {
+      float t = S4[0 * 4 + c] * nf[0];
+      t = fmaf(S4[1 * 4 + c], nf[1], t);
+      t = fmaf(S4[2 * 4 + c], nf[2], t);
+      a[c] = t;
+    }
+    float t;
+    J[0][0] = a[0]; J[0][1] = a[1]; J[0][2] = a[2];
+    t = m[2] * a[1]; J[0][3] = rs * fmaf(m[1], a[2], -t);
+    t = m[0] * a[2]; J[0][4] = rs * fmaf(m[2], a[0], -t);
+    t = m[1] * a[0]; J[0][5] = rs * fmaf(m[0], a[1], -t);
+    e[0] = dot3(nf, d); om[0] = ip;
+    for (int r = 0; r < 3; ++r) {
+      const float* R = S4 + r * 4;
+      J[r + 1][0] = 0.f; J[r + 1][1] = 0.f; J[r + 1][2] = 0.f;
+      t = R[2] * nm[1]; J[r + 1][3] = -rs * fmaf(R[1], nm[2], -t);
+      t = R[0] * nm[2]; J[r + 1][4] = -rs * fmaf(R[2], nm[0], -t);
+      t = R[1] * nm[0]; J[r + 1][5] = -rs * fmaf(R[0], nm[1], -t);
+      e[r + 1] = nq[r] - nf[r]; om[r + 1] = in_;
+    }
+    return 4;
+  }
+  /* dim == 2 */
+  if (factor == ORC_FACTOR_P2P) {
+    for (int r = 0; r < 2; ++r) {
+      const float* R = S4 + r * 4;
+      J[r][0] = R[0]; J[r][1] = R[1];
+      float t = R[0] * m[1];
+      J[r][2] = fmaf(R[1], m[0], -t);
+      e[r] = d[r]; om[r] = ip;
+    }
+    return 2;
+  }
+  float a[2];
+  for (int c = 0; c < 2; ++c) {
+    a[c] = fmaf(S4[1 * 4 + c], nf[1], S4[0 * 4 + c] * nf[0]);
+  }
+  float t = a[0] * m[1];
+  J[0][0] = a[0]; J[0][1] = a[1]; J[0][2] = fmaf(a[1], m[0], -t);
+  e[0] = fmaf(nf[1], d[1], nf[0] * d[0]); om[0] = ip;
+  for (int r = 0; r < 2; ++r) {
+    const float* R = S4 + r * 4;
+    J[r + 1][0] = 0.f; J[r + 1][1] = 0.f;
+    t = R[0] * nm[1];
+    J[r + 1][2] = fmaf(R[1], nm[0], -t);
+    e[r + 1] = nq[r] - nf[r]; om[r + 1] = in_;
+  }
+  return 3;
+}
+
+/* slots of the 32-entry accumulator */
+#define ACC_B 21
+#define ACC_CHI_IN 27
+#define ACC_CHI_OUT 28
+#define ACC_N_IN 29
+#define ACC_N_OUT 30
+#define ACC_N_SUP 31
+
+static void lin_one(int dim, int variable, const orc_factor_params* fa, const orc_scales_t* sc,
+                    const float* S4, const float* m, const float* nm, const float* f, const float* nf,
+                    int64_t* acc, uint8_t* status, float* chi_out) {
+  const int P = (dim == 3) ? 6 : 3;
+  float q[3], nq[3] = {0, 0, 0}, e[4], om[4], J[4][6];
+  xf_point(S4, m, q);
+  xf_dir(S4, nm, nq);
+  int E = build_rows(dim, variable, fa->factor, S4, m, nm, f, nf, q, nq, fa->info_point, fa->info_normal, e, om, J);
+  float chi = (om[0] * e[0]) * e[0];
+  for (int r = 1; r < E; ++r) {
+    chi = fmaf(om[r] * e[r], e[r], chi);
+  }
+  if (!(chi == chi) || isinf(chi)) {
+    acc[ACC_N_SUP] += 1;
+    if (status) *status = ORC_STAT_SUPPRESSED;
+    if (chi_out) *chi_out = chi;
+    return;
+  }
+  float w, rho;
+  int kern = robustify(fa->robustifier, fa->chi_threshold, chi, &w, &rho);
+  if (kern) {
+    acc[ACC_N_OUT] += 1;
+    acc[ACC_CHI_OUT] += to_fix(rho, sc->kchi);
+  } else {
+    acc[ACC_N_IN] += 1;
+    acc[ACC_CHI_IN] += to_fix(chi, sc->kchi);
+  }
+  if (status) *status = kern ? ORC_STAT_KERNELIZED : ORC_STAT_INLIER;
+  if (chi_out) *chi_out = chi;
+  float u[4][6];
+  for (int r = 0; r < E; ++r) {
+    float s = w * om[r];
+    for (int i = 0; i < P; ++i) {
+      u[r][i] = s * J[r][i];
+    }
+  }
+  int slot = 0;
+  for (int i = 0; i < P; ++i) {
+    for (int j = i; j < P; ++j) {
+      float h = u[0][i] * J[0][j];
+      for (int r = 1; r < E; ++r) {
+        h = fmaf(u[r][i], J[r][j], h);
+      }
+      acc[slot++] += to_fix(h, sc->kH);
+    }
+  }
+  for (int i = 0; i < P; ++i) {
+    float g = u[0][i] * e[0];
+    for (int r = 1; r < E; ++r) {
+      g = fmaf(u[r][i], e[r], g);
+    }
+    acc[ACC_B + i] += to_fix(g, sc->kb);
+  }
+}
+
+static void acc_to_Hb(int dim, const int64_t* acc, const orc_scales_t* sc, double* H, double* b) {
+  const int P = (dim == 3) ? 6 : 3;
+  int slot = 0;
+  for (int i = 0; i < P; ++i) {
+    for (int j = i; j < P; ++j) {
+      double v = ldexp((double) acc[slot++], -sc->kH);
+      H[i * P + j] = v;
+      H[j * P + i] = v;
+    }
+  }
+  for (int i = 0; i < P; ++i) {
+    b[i] = ldexp((double) acc[ACC_B + i], -sc->kb);
+  }
+}
+
+int orc_linearize(int dim, int variable, const orc_cloud* fixed, const orc_cloud* moving,
+                  const int32_t* fidx, const float* S, const orc_finder_params* fp,
+                  const orc_factor_params* fa, int64_t n_global, int64_t* acc_out, double* H, double* b,
+                  orc_iter_stats* stats, uint8_t* status_dense, float* chi_dense) {
+  float S4[16];
+  embed4(dim, S, S4);
+  orc_scales_t sc;
+  orc_scales(dim, n_global > 0 ? n_global : moving->n, orc_coord_bound(dim, moving), fp, fa, &sc);
+  int64_t acc[32];
+  memset(acc, 0, sizeof(acc));
+  const int have_n = (fixed->normals && moving->normals);
+  if (fa->factor == ORC_FACTOR_PLANE && !have_n) return 1;
+#pragma omp parallel
+  {
+    int64_t loc[32];
+    memset(loc, 0, sizeof(loc));
+#pragma omp for schedule(static)
+    for (int64_t j = 0; j < moving->n; ++j) {
+      if (status_dense) status_dense[j] = ORC_STAT_NONE;
+      if (chi_dense) chi_dense[j] = 0.f;
+      int32_t i = fidx[j];
+      if (i < 0) continue;
+      if (i >= fixed->n || (fixed->valid && !fixed->valid[i]) || (moving->valid && !moving->valid[j])) {
+        loc[ACC_N_SUP] += 1;
+        if (status_dense) status_dense[j] = ORC_STAT_SUPPRESSED;
+        continue;
+      }
+      float m[3], nm[3] = {0, 0, 0}, f[3], nf[3] = {0, 0, 0};
+      get3(moving->coords, dim, j, m);
+      get3(fixed->coords, dim, i, f);
+      if (have_n) {
+        get3(moving->normals, dim, j, nm);
+        get3(fixed->normals, dim, i, nf);
+      }
+      lin_one(dim, variable, fa, &sc, S4, m, nm, f, nf, loc, status_dense ? status_dense + j : NULL,
+              chi_dense ? chi_dense + j : NULL);
+    }
+#pragma omp critical
+    for (int k = 0; k < 32; ++k) acc[k] += loc[k];
+  }
+  if (acc_out) memcpy(acc_out, acc, sizeof(acc));
+  if (H && b) acc_to_Hb(dim, acc, &sc, H, b);
+  if (stats) {
+    stats->num_inliers = acc[ACC_N_IN];
+    stats->num_outliers = acc[ACC_N_OUT];
+    stats->num_suppressed = acc[ACC_N_SUP];
+    stats->num_correspondences = acc[ACC_N_IN] + acc[ACC_N_OUT] + acc[ACC_N_SUP];
+    stats->chi_inliers = ldexp((double) acc[ACC_CHI_IN], -sc.kchi);
+    stats->chi_outliers = ldexp((double) acc[ACC_CHI_OUT], -sc.kchi);
+  }
+  return 0;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* a9 -- SE(d) prior factor e = t2v(Z^-1 X) with diagonal information (fp64)                    */
+/* (factor types: R/registration/aligners/aligner_slice_odometry_prior.h:9,33)                  */
+/* ------------------------------------------------------------------------------------------ */
+static int prior_terms(int dim, int variable, const float* Z4, const float* X4, const float* info,
+                       double* H, double* b, double* chi) {
+  const int P = (dim == 3) ? 6 : 3;
+  float Zi[16];
+  inv4(Z4, Zi);
+  double E[12];
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 4; ++j) {
+      double c = (double) Zi[i * 4 + 0] * (double) X4[0 * 4 + j];
+      c = c + (double) Zi[i * 4 + 1] * (double) X4[1 * 4 + j];
+      c = c + (double) Zi[i * 4 + 2] * (double) X4[2 * 4 + j];
+      if (j == 3) c = c + (double) Zi[i * 4 + 3];
+      E[i * 4 + j] = c;
+    }
+  }
+  double e[6], J[36];
+  memset(J, 0, sizeof(J));
+  if (dim == 3) {
+    if (variable != ORC_VAR_SE3_QUAT_RIGHT) return 0;
+    double R[9], q[4];
+    for (int i = 0; i < 3; ++i) {
+      for (int j = 0; j < 3; ++j) R[i * 3 + j] = E[i * 4 + j];
+    }
+    quat_from_R(R, q);
+    e[0] = E[3]; e[1] = E[7]; e[2] = E[11];
+    e[3] = q[0]; e[4] = q[1]; e[5] = q[2];
+    for (int i = 0; i < 3; ++i) {
+      for (int j = 0; j < 3; ++j) J[i * 6 + j] = R[i * 3 + j];
+    }
+    /* d vec(q_e * (1,dq)) / d dq = w I + [v]x */
+    J[3 * 6 + 3] = q[3];  J[3 * 6 + 4] = -q[2]; J[3 * 6 + 5] = q[1];
+    J[4 * 6 + 3] = q[2];  J[4 * 6 + 4] = q[3];  J[4 * 6 + 5] = -q[0];
+    J[5 * 6 + 3] = -q[1]; J[5 * 6 + 4] = q[0];  J[5 * 6 + 5] = q[3];
+  } else {
+    e[0] = E[3]; e[1] = E[7];
+    e[2] = orc_atan2(E[4], E[0]);
+    J[0 * 3 + 0] = E[0]; J[0 * 3 + 1] = E[1];
+    J[1 * 3 + 0] = E[4]; J[1 * 3 + 1] = E[5];
+    J[2 * 3 + 2] = 1.0;
+  }
+  double c = 0.0;
+  for (int r = 0; r < P; ++r) {
+    c = c + ((double) info[r] * e[r]) * e[r];
+  }
+  *chi = c;
+  for (int i = 0; i < P; ++i) {
+    for (int j = 0; j < P; ++j) {
+      double h = 0.0;
+      for (int r = 0; r < P; ++r) {
+        h = h + (J[r * P + i] * (double) info[r]) * J[r * P + j];
+      }
+      H[i * P + j] = H[i * P + j] + h;
+    }
+    double g = 0.0;
+    for (int r = 0; r < P; ++r) {
+      g = g + (J[r * P + i] * (double) info[r]) * e[r];
+    }
+    b[i] = b[i] + g;
+  }
+  return 1;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* a6 -- AlignerTerminationCriteriaStandard_ (aligner_termination_criteria_impl.cpp:10-65)      */
+/* ------------------------------------------------------------------------------------------ */
+#define TC_MAXW 64
+typedef struct {
+  int window, count, head;
+  double v[TC_MAXW];
+} tc_ring;
+
+static void ring_reset(tc_ring* r, int w) {
+  r->window = w > TC_MAXW ? TC_MAXW : (w < 1 ? 1 : w);
+  r->count = 0; r->head = 0;
+}
+static void ring_add(tc_ring* r, double x) {
+  r->v[r->head] = x;
+  r->head = (r->head + 1) % r->window;
+  if (r->count < r->window) r->count++;
+}
+static double ring_max(const tc_ring* r) {
+  double m = r->v[0];
+  for (int i = 1; i < r->count; ++i) if (r->v[i] > m) m = r->v[i];
+  return m;
+}
+static double ring_min(const tc_ring* r) {
+  double m = r->v[0];
+  for (int i = 1; i < r->count; ++i) if (r->v[i] < m) m = r->v[i];
+  return m;
+}
+
+typedef struct {
+  tc_ring ncorr, ninl, nout, chi;
+  int num_iteration;
+} term_crit;
+
+static void tc_init(term_crit* tc, const orc_aligner_params* ap) { /* :10-21 */
+  tc->num_iteration = 0;
+  ring_reset(&tc->ncorr, ap->window_size);
+  ring_reset(&tc->ninl, ap->window_size);
+  ring_reset(&tc->nout, ap->window_size);
+  ring_reset(&tc->chi, ap->window_size);
+}
+
+static int tc_has_to_stop(term_crit* tc, const orc_aligner_params* ap, const orc_iter_stats* st,
+                          int64_t ncorr) { /* :24-65, quirks kept */
+  ++tc->num_iteration;
+  int ninl = (int) st->num_inliers;
+  int nout = (int) st->num_outliers;
+  float chi = (float) st->chi_inliers / (float) ninl;
+  if (!ninl) return 0;
+  ring_add(&tc->ncorr, (double) ncorr);
+  ring_add(&tc->ninl, (double) ninl);
+  ring_add(&tc->nout, (double) nout);
+  ring_add(&tc->chi, (double) chi);
+  if (tc->ncorr.count < ap->window_size) return 0;
+  if (ring_max(&tc->nout) - ring_min(&tc->nout) > (double) ap->num_correspondences_range) return 0; /* :46 */
+  if (ring_max(&tc->ninl) - ring_min(&tc->ninl) > (double) ap->num_inliers_range) return 0;
+  float crange = (float) ring_max(&tc->chi) - (float) ring_min(&tc->chi);
+  float cmax = (float) ring_max(&tc->chi);
+  if (crange > (float) ap->num_outliers_range) return 0; /* :53 */
+  if (crange / cmax > ap->chi_epsilon) return 0;
+  return 1;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* a1/a2/a7/a8 -- MultiAlignerBase_::compute / _runSolver / _postCompute / _pruneCorrespondences */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int dim, n_slices, nn_method;
+  const orc_slice* slices;
+  const orc_aligner_params* ap;
+  orc_index** index;
+  int32_t** fidx;   /* dense per slice */
+  float** resp;
+  uint8_t** fstat;
+  int64_t* ncorr;
+  float X4[16];     /* variable 0 estimate (moving in fixed) */
+  term_crit tc;
+  orc_iter_stats* stats;
+  int n_stats, cap_stats;
+  int status;
+} run_state;
+
+/* _runSolver, multi_aligner_impl.cpp:97-128 */
+static void run_solver(run_state* rs, int iterations, int use_tc, int clamp) {
+  const int dim = rs->dim, P = (dim == 3) ? 6 : 3;
+  float backup[16];
+  memcpy(backup, rs->X4, sizeof(backup)); /* :102 */
+  for (int it = 0; it < iterations; ++it) {
+    int good = 0;
+    /* _computeCorrespondencesPerSlices, multi_aligner.h:126-138 */
+    for (int s = 0; s < rs->n_slices; ++s) {
+      const orc_slice* sl = &rs->slices[s];
+      if (sl->kind == ORC_SLICE_PRIOR) {
+        rs->ncorr[s] = 1;  /* aligner_slice_processor_prior.h:75-77 */
+        good |= 1;         /* :65-67 */
+        continue;
+      }
+      float ris4[16], S4[16], S[16];
+      embed4(dim, sl->robot_in_sensor, ris4);
+      mul4(ris4, backup, S4); /* aligner_slice_processor_impl.cpp:35 */
+      unembed4(dim, S4, S);
+      orc_find(rs->index[s], dim, &sl->fixed, &sl->moving, S, &sl->finder, rs->fidx[s], rs->resp[s]);
+      int64_t n = 0;
+      for (int64_t j = 0; j < sl->moving.n; ++j) n += (rs->fidx[s][j] >= 0);
+      rs->ncorr[s] = n;
+      good |= ((int) n > sl->min_num_correspondences); /* :77-79, strict > */
+    }
+    if (!good) { /* :107-111 */
+      rs->status = ORC_ALIGNER_NOT_ENOUGH_CORR;
+      memcpy(rs->X4, backup, sizeof(backup));
+      break;
+    }
+    /* solver->compute(): one GN iteration (multi_aligner.h:61-62) */
+    double H[36], b[6];
+    memset(H, 0, sizeof(H)); memset(b, 0, sizeof(b));
+    orc_iter_stats st;
+    memset(&st, 0, sizeof(st));
+    st.iteration = rs->n_stats;
+    for (int s = 0; s < rs->n_slices; ++s) {
+      const orc_slice* sl = &rs->slices[s];
+      if (sl->kind == ORC_SLICE_PRIOR) {
+        float Z4[16];
+        double chi = 0.0;
+        embed4(dim, sl->prior_measurement, Z4);
+        prior_terms(dim, rs->ap->variable, Z4, rs->X4, sl->prior_info_diag, H, b, &chi);
+        st.num_inliers += 1; st.num_correspondences += 1; st.chi_inliers += chi;
+        continue;
+      }
+      float ris4[16], S4[16], S[16];
+      embed4(dim, sl->robot_in_sensor, ris4);
+      mul4(ris4, rs->X4, S4);
+      unembed4(dim, S4, S);
+      orc_factor_params fa = sl->factor;
+      if (clamp && fa.robustifier != ORC_ROB_NONE) fa.robustifier = ORC_ROB_CLAMP; /* :193-199 */
+      double Hs[36], bs[6];
+      orc_iter_stats ss;
+      orc_linearize(dim, rs->ap->variable, &sl->fixed, &sl->moving, rs->fidx[s], S, &sl->finder, &fa, 0,
+                    NULL, Hs, bs, &ss, rs->fstat[s], NULL);
+      for (int k = 0; k < P * P; ++k) H[k] = H[k] + Hs[k];
+      for (int k = 0; k < P; ++k) b[k] = b[k] + bs[k];
+      st.num_inliers += ss.num_inliers; st.num_outliers += ss.num_outliers;
+      st.num_suppressed += ss.num_suppressed; st.num_correspondences += ss.num_correspondences;
+      st.chi_inliers += ss.chi_inliers; st.chi_outliers += ss.chi_outliers;
+    }
+    float Xn[16], Xu[16];
+    memcpy(Xn, rs->X4, sizeof(Xn));
+    unembed4(dim, Xn, Xu);
+    st.solver_status = orc_solve_update(dim, rs->ap->variable, H, b, Xu);
+    if (st.solver_status) embed4(dim, Xu, rs->X4);
+    if (rs->n_stats < rs->cap_stats) rs->stats[rs->n_stats] = st; /* :113-115 */
+    rs->n_stats++;
+    if (st.solver_status) memcpy(backup, rs->X4, sizeof(backup)); /* :118-121 */
+    int64_t total = 0;
+    for (int s = 0; s < rs->n_slices; ++s) total += rs->ncorr[s];
+    if (use_tc && tc_has_to_stop(&rs->tc, rs->ap, &st, total)) break; /* :124-126 */
+  }
+}
+
+int orc_icp_run(int dim, int n_slices, const orc_slice* slices, const orc_aligner_params* ap,
+                float* T, orc_iter_stats* stats_out, int32_t* n_stats, int32_t* status_out,
+                orc_corr_out* corr_out, int nn_method) {
+  run_state rs;
+  memset(&rs, 0, sizeof(rs));
+  rs.dim = dim; rs.n_slices = n_slices; rs.slices = slices; rs.ap = ap; rs.nn_method = nn_method;
+  rs.index = (orc_index**) calloc((size_t) n_slices, sizeof(void*));
+  rs.fidx = (int32_t**) calloc((size_t) n_slices, sizeof(void*));
+  rs.resp = (float**) calloc((size_t) n_slices, sizeof(void*));
+  rs.fstat = (uint8_t**) calloc((size_t) n_slices, sizeof(void*));
+  rs.ncorr = (int64_t*) calloc((size_t) n_slices, sizeof(int64_t));
+  rs.stats = stats_out; rs.cap_stats = *n_stats; rs.n_stats = 0;
+  rs.status = ORC_ALIGNER_FAIL;
+  embed4(dim, T, rs.X4);
+  for (int s = 0; s < n_slices; ++s) {
+    if (slices[s].kind != ORC_SLICE_POINTS) continue;
+    if (slices[s].finder.kind == ORC_FINDER_NN) {
+      rs.index[s] = orc_index_create(dim, &slices[s].fixed, nn_method);
+    }
+    rs.fidx[s] = (int32_t*) malloc(sizeof(int32_t) * (size_t) (slices[s].moving.n + 1));
+    rs.resp[s] = (float*) malloc(sizeof(float) * (size_t) (slices[s].moving.n + 1));
+    rs.fstat[s] = (uint8_t*) malloc((size_t) (slices[s].moving.n + 1));
+    for (int64_t j = 0; j < slices[s].moving.n; ++j) rs.fidx[s][j] = -1;
+  }
+  if (ap->use_termination_criteria) tc_init(&rs.tc, ap); /* compute() :52-57 */
+  /* _preCompute :130-141 -- prior slices overwrite the guess in slice order
+   * (aligner_slice_odometry_prior.cpp:19,34; aligner_slice_motion_model.hpp:70) */
+  for (int s = 0; s < n_slices; ++s) {
+    if (slices[s].kind == ORC_SLICE_PRIOR) embed4(dim, slices[s].prior_measurement, rs.X4);
+  }
+  run_solver(&rs, ap->max_iterations, ap->use_termination_criteria, 0); /* :72 */
+  int done = 0;
+  if (rs.n_stats == 0) { /* :75-78 */
+    rs.status = ORC_ALIGNER_FAIL;
+    done = 1;
+  }
+  if (!done) {
+    int last = rs.n_stats <= rs.cap_stats ? rs.n_stats - 1 : rs.cap_stats - 1;
+    if (rs.stats[last].num_inliers < ap->min_num_inliers) { /* :81-85 */
+      rs.status = ORC_ALIGNER_NOT_ENOUGH_INLIERS;
+      done = 1;
+    }
+  }
+  if (!done) {
+    if (ap->enable_inlier_only_runs) { /* _postCompute :162-175 */
+      run_solver(&rs, ap->max_iterations, ap->use_termination_criteria, 1);
+    }
+    float Tf[16];
+    unembed4(dim, rs.X4, Tf);
+    orc_fix_transform(dim, Tf); /* :90-93 */
+    embed4(dim, Tf, rs.X4);
+    rs.status = ORC_ALIGNER_SUCCESS;
+  }
+  unembed4(dim, rs.X4, T);
+  *n_stats = rs.n_stats;
+  *status_out = rs.status;
+  if (corr_out) {
+    for (int s = 0; s < n_slices; ++s) {
+      corr_out[s].n = 0;
+      if (slices[s].kind != ORC_SLICE_POINTS || !corr_out[s].fixed_idx) continue;
+      const int prune = (!done && ap->keep_only_inlier_correspondences); /* :177-180, :213-263 */
+      int64_t k = 0;
+      for (int64_t j = 0; j < slices[s].moving.n; ++j) {
+        if (rs.fidx[s][j] < 0) continue;
+        if (prune && rs.fstat[s][j] != ORC_STAT_INLIER) continue;
+        corr_out[s].fixed_idx[k] = rs.fidx[s][j];
+        corr_out[s].moving_idx[k] = (int32_t) j;
+        corr_out[s].response[k] = rs.resp[s][j];
+        ++k;
+      }
+      corr_out[s].n = k;
+    }
+  }
+  for (int s = 0; s < n_slices; ++s) {
+    orc_index_free(rs.index[s]);
+    free(rs.fidx[s]); free(rs.resp[s]); free(rs.fstat[s]);
+  }
+  free(rs.index); free(rs.fidx); free(rs.resp); free(rs.fstat); free(rs.ncorr);
+  return 0;
+}

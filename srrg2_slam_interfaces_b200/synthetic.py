@@ -1,0 +1,172 @@
+"""Seeded synthetic clouds / graphs for the BASELINE.json configurations.
+
+Pure numpy, PCG64 streams: the same seed gives bit-identical inputs in the tests, in bench.py, for
+the CPU oracle and for the CUDA path.  Nothing here touches the GPU.
+"""
+import numpy as np
+
+
+def rot3(rpy):
+    r, p, y = [float(v) for v in rpy]
+    cr, sr, cp, sp, cy, sy = np.cos(r), np.sin(r), np.cos(p), np.sin(p), np.cos(y), np.sin(y)
+    Rx = np.array([[1, 0, 0], [0, cr, -sr], [0, sr, cr]])
+    Ry = np.array([[cp, 0, sp], [0, 1, 0], [-sp, 0, cp]])
+    Rz = np.array([[cy, -sy, 0], [sy, cy, 0], [0, 0, 1]])
+    return Rz @ Ry @ Rx
+
+
+def iso3(t, rpy):
+    T = np.eye(4)
+    T[:3, :3] = rot3(rpy)
+    T[:3, 3] = t
+    return T
+
+
+def iso2(x, y, th):
+    c, s = np.cos(th), np.sin(th)
+    return np.array([[c, -s, x], [s, c, y], [0, 0, 1.0]])
+
+
+def inv_iso(T):
+    d = T.shape[0] - 1
+    Ti = np.eye(d + 1)
+    Ti[:d, :d] = T[:d, :d].T
+    Ti[:d, d] = -T[:d, :d].T @ T[:d, d]
+    return Ti
+
+
+def transform_cloud(T, pts, nrm=None):
+    d = T.shape[0] - 1
+    p = pts.astype(np.float64) @ T[:d, :d].T + T[:d, d]
+    n = None if nrm is None else nrm.astype(np.float64) @ T[:d, :d].T
+    return p.astype(np.float32), (None if n is None else n.astype(np.float32))
+
+
+# ----------------------------------------------------------------------------------------------
+# 3D scene: planar patches + spheres inside a cube
+# ----------------------------------------------------------------------------------------------
+class Scene3D:
+    def __init__(self, seed, n_planes=64, n_spheres=16, cube=20.0):
+        rng = np.random.default_rng([seed, 0xA11])
+        self.cube = float(cube)
+        h = cube / 2
+        self.pl_c = rng.uniform(-0.7 * h, 0.7 * h, size=(n_planes, 3))
+        nrm = rng.normal(size=(n_planes, 3))
+        self.pl_n = nrm / np.linalg.norm(nrm, axis=1, keepdims=True)
+        a = np.cross(self.pl_n, rng.normal(size=(n_planes, 3)))
+        self.pl_u = a / np.linalg.norm(a, axis=1, keepdims=True)
+        self.pl_v = np.cross(self.pl_n, self.pl_u)
+        self.pl_l = rng.uniform(0.3 * cube, 0.7 * cube, size=(n_planes, 2))
+        self.sp_c = rng.uniform(-0.6 * h, 0.6 * h, size=(n_spheres, 3))
+        self.sp_r = rng.uniform(0.05 * cube, 0.15 * cube, size=n_spheres)
+        area = np.concatenate([self.pl_l[:, 0] * self.pl_l[:, 1], 4 * np.pi * self.sp_r ** 2])
+        self.prob = area / area.sum()
+        self.n_planes = n_planes
+
+    def sample(self, n, rng, jitter=0.0):
+        which = rng.choice(len(self.prob), size=n, p=self.prob)
+        pts = np.empty((n, 3))
+        nrm = np.empty((n, 3))
+        isp = which < self.n_planes
+        k = which[isp]
+        uv = rng.uniform(-0.5, 0.5, size=(k.size, 2)) * self.pl_l[k]
+        pts[isp] = self.pl_c[k] + uv[:, :1] * self.pl_u[k] + uv[:, 1:] * self.pl_v[k]
+        nrm[isp] = self.pl_n[k]
+        k = which[~isp] - self.n_planes
+        d = rng.normal(size=(k.size, 3))
+        d /= np.linalg.norm(d, axis=1, keepdims=True)
+        pts[~isp] = self.sp_c[k] + self.sp_r[k, None] * d
+        nrm[~isp] = d
+        if jitter > 0:
+            pts += rng.uniform(-jitter, jitter, size=pts.shape)
+        return pts, nrm
+
+
+C2_T_STAR = iso3([0.10, -0.05, 0.08], np.deg2rad([1.5, -1.0, 2.0]))
+
+
+def make_icp3d(n_fixed, n_moving, seed=2, T_star=None, noise=0.002, outlier_frac=0.05, cube=20.0,
+               jitter=0.0005, n_planes=64, n_spheres=16):
+    """Config C2 generator: fixed and moving are INDEPENDENT samples of the same
+    surfaces; moving = T*^-1 (sample + N(0,noise)), a fraction replaced by uniform outliers.
+    The aligner estimate (moving in fixed) should converge to T*."""
+    T_star = C2_T_STAR if T_star is None else T_star
+    scene = Scene3D(seed, n_planes, n_spheres, cube)
+    rf = np.random.default_rng([seed, 1])
+    rm = np.random.default_rng([seed, 2])
+    fp, fn = scene.sample(n_fixed, rf, jitter)
+    mp, mn = scene.sample(n_moving, rm, 0.0)
+    mp = mp + rm.normal(scale=noise, size=mp.shape)
+    n_out = int(outlier_frac * n_moving)
+    if n_out:
+        idx = rm.choice(n_moving, size=n_out, replace=False)
+        mp[idx] = rm.uniform(-cube / 2, cube / 2, size=(n_out, 3))
+        d = rm.normal(size=(n_out, 3))
+        mn[idx] = d / np.linalg.norm(d, axis=1, keepdims=True)
+    Ti = inv_iso(T_star)
+    mp32, mn32 = transform_cloud(Ti, mp, mn)
+    return dict(fixed=fp.astype(np.float32), fixed_normals=fn.astype(np.float32), moving=mp32,
+                moving_normals=mn32, T_star=T_star.astype(np.float64))
+
+
+# ----------------------------------------------------------------------------------------------
+# 2D scene: wall segments
+# ----------------------------------------------------------------------------------------------
+C1_T_STAR = iso2(0.05, -0.03, np.deg2rad(2.0))
+
+
+def walls2d(seed, n_walls=8, half=10.0):
+    rng = np.random.default_rng([seed, 0xB22])
+    a = rng.uniform(-half, half, size=(n_walls, 2))
+    ang = rng.uniform(0, np.pi, size=n_walls)
+    length = rng.uniform(0.4 * half, 1.2 * half, size=n_walls)
+    d = np.stack([np.cos(ang), np.sin(ang)], axis=1)
+    return a, d, length
+
+
+def sample_walls2d(walls, n, rng, jitter=0.0):
+    a, d, length = walls
+    p = length / length.sum()
+    which = rng.choice(len(p), size=n, p=p)
+    s = rng.uniform(-0.5, 0.5, size=n) * length[which]
+    pts = a[which] + s[:, None] * d[which]
+    nrm = np.stack([-d[which, 1], d[which, 0]], axis=1)
+    if jitter > 0:
+        pts += rng.uniform(-jitter, jitter, size=pts.shape)
+    return pts, nrm
+
+
+def make_icp2d(n_fixed, n_moving=None, seed=1, T_star=None, noise=0.005, paired=True, n_walls=8, half=10.0):
+    """Config C1 generator: fixed on wall segments; moving = T*^-1 (fixed + N(0,noise)) when
+    paired, else independent samples of the same walls."""
+    T_star = C1_T_STAR if T_star is None else T_star
+    walls = walls2d(seed, n_walls, half)
+    rf = np.random.default_rng([seed, 1])
+    rm = np.random.default_rng([seed, 2])
+    fp, fn = sample_walls2d(walls, n_fixed, rf, 0.001)
+    if paired:
+        mp, mn = fp.copy(), fn.copy()
+        if n_moving is not None and n_moving != n_fixed:
+            sel = rm.choice(n_fixed, size=n_moving, replace=n_moving > n_fixed)
+            mp, mn = mp[sel], mn[sel]
+    else:
+        mp, mn = sample_walls2d(walls, n_moving or n_fixed, rm, 0.0)
+    mp = mp + rm.normal(scale=noise, size=mp.shape)
+    mp32, mn32 = transform_cloud(inv_iso(T_star), mp, mn)
+    return dict(fixed=fp.astype(np.float32), fixed_normals=fn.astype(np.float32), moving=mp32,
+                moving_normals=mn32, T_star=T_star.astype(np.float64))
+
+
+def pose_error(T, T_ref):
+    """(rotation error [rad], translation error [m]) between two isometries."""
+    d = T.shape[0] - 1
+    E = inv_iso(np.asarray(T_ref, dtype=np.float64)) @ np.asarray(T, dtype=np.float64)
+    if d == 3:
+        c = np.clip((np.trace(E[:3, :3]) - 1) / 2, -1, 1)
+        ang = float(np.arccos(c))
+        if ang < 1e-3:  # arccos loses precision near 0: use the skew part
+            w = np.array([E[2, 1] - E[1, 2], E[0, 2] - E[2, 0], E[1, 0] - E[0, 1]]) / 2
+            ang = float(np.linalg.norm(w))
+    else:
+        ang = float(abs(np.arctan2(E[1, 0], E[0, 0])))
+    return ang, float(np.linalg.norm(E[:d, d]))
