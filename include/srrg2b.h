@@ -1,0 +1,169 @@
+/*
+ * srrg2b.h -- C ABI of libsrrg2b.so: B200 (sm_100a) implementation of the two data-parallel hot
+ * paths of srrg2_slam_interfaces (the MultiAligner ICP loop and the pose-graph Gauss-Newton step).
+ *
+ * Every entry point is extern "C", takes plain pointers and sizes, returns an int error code
+ * (0 = ok) and has finished (results visible on the host) when it returns, matching the
+ * single-threaded, synchronous calling convention of the reference.
+ * Configuration errors map to SRRG2B_ERR_INVALID (the reference throws std::runtime_error, e.g.
+ * R/registration/aligners/aligner_slice_processor_impl.cpp:13-16); numeric outcomes are reported
+ * through status enums (R/registration/aligners/aligner.h:23-28), never as errors.
+ *
+ * R/ = srrg2_slam_interfaces/src/srrg2_slam_interfaces/ of the reference tree.
+ * Matrices are row-major (dim+1)x(dim+1) float (Isometry2f / Isometry3f .matrix()).
+ * There is NO CPU fallback: every compute entry point fails with SRRG2B_ERR_CUDA without a GPU.
+ */
+#ifndef SRRG2B_H
+#define SRRG2B_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SRRG2B_VERSION 100
+#define SRRG2B_MAX_SLICES 8
+
+enum { SRRG2B_OK = 0, SRRG2B_ERR_INVALID = 1, SRRG2B_ERR_CUDA = 2, SRRG2B_ERR_STATE = 3, SRRG2B_ERR_NCCL = 4 };
+enum { SRRG2B_FIXED = 0, SRRG2B_MOVING = 1 };
+/* factor types instantiated by the reference: R/instances.h:27-30,70-73 (Point2Point) and the
+ * point+normal factor the laser/proslam pipelines plug into AlignerSliceProcessor_ */
+enum { SRRG2B_FACTOR_P2P = 0, SRRG2B_FACTOR_PLANE = 1 };
+/* RobustifierBase subclasses (R/registration/aligners/aligner_slice_processor_base.h:34-38,
+ * RobustifierClamp at R/registration/aligners/multi_aligner_impl.cpp:194) */
+enum { SRRG2B_ROB_NONE = 0, SRRG2B_ROB_SATURATED = 1, SRRG2B_ROB_CAUCHY = 2, SRRG2B_ROB_CLAMP = 3, SRRG2B_ROB_HUBER = 4 };
+/* VariableSE3QuaternionRightAD (MultiAligner3DQR) / VariableSE3EulerRightAD (MultiAligner3D):
+ * R/registration/aligners/multi_aligner.h:152-158; dim 2 is always VariableSE2RightAD */
+enum { SRRG2B_VAR_SE3_QUAT_RIGHT = 0, SRRG2B_VAR_SE3_EULER_RIGHT = 1 };
+enum { SRRG2B_FINDER_NN = 0, SRRG2B_FINDER_PROJECTIVE = 1 };
+enum { SRRG2B_SLICE_POINTS = 0, SRRG2B_SLICE_PRIOR = 1 };
+/* AlignerBase::Status, R/registration/aligners/aligner.h:23-28 */
+enum { SRRG2B_ALIGNER_SUCCESS = 0, SRRG2B_ALIGNER_NOT_ENOUGH_CORRESPONDENCES = 1, SRRG2B_ALIGNER_NOT_ENOUGH_INLIERS = 2, SRRG2B_ALIGNER_FAIL = 3 };
+/* srrg2_solver FactorStats::Status as consumed at R/registration/aligners/multi_aligner_impl.cpp:244 */
+enum { SRRG2B_STAT_INLIER = 0, SRRG2B_STAT_KERNELIZED = 1, SRRG2B_STAT_SUPPRESSED = 2, SRRG2B_STAT_NONE = 3 };
+
+typedef struct srrg2b_ctx srrg2b_ctx;
+
+/* A point(+normal) cloud slice: PointNormal{2,3}fVectorCloud flattened to packed fp32 arrays. */
+typedef struct {
+  const float* coords;    /* n x dim */
+  const float* normals;   /* n x dim or NULL */
+  const uint8_t* valid;   /* n (point.status == Valid) or NULL = all valid */
+  int64_t n;
+  int64_t index_offset;   /* global moving index of element 0 when the moving cloud is sharded */
+  int64_t n_global;       /* size of the whole (unsharded) cloud; 0 = n */
+  int32_t on_device;      /* 1: the pointers are device pointers on the context's GPU */
+  int32_t reserved;
+} srrg2b_cloud;
+
+/* CorrespondenceFinder_ parameters (kd-tree NN finder of srrg2_laser_slam_2d, projective finder of
+ * srrg2_proslam; interface R/registration/correspondence_finder.h:66-125) */
+typedef struct {
+  int32_t kind;
+  float max_distance;
+  float normal_cos;       /* <= -1 disables the normal gate */
+  float fx, fy, cx, cy;   /* projective only */
+  int32_t width, height;
+  float min_depth, max_depth;
+} srrg2b_finder_params;
+
+typedef struct {
+  int32_t factor;
+  int32_t robustifier;
+  float chi_threshold;    /* RobustifierBase::param_chi_threshold */
+  float info_point;       /* information of the point rows (isotropic for P2P) */
+  float info_normal;      /* information of the normal rows (PLANE factor) */
+} srrg2b_factor_params;
+
+/* One entry of MultiAlignerBase_::param_slice_processors (R/registration/aligners/multi_aligner.h:34-37):
+ * an AlignerSliceProcessor_ (points) or an AlignerSliceProcessorPrior_ (odometry / motion model). */
+typedef struct {
+  int32_t kind;
+  int32_t slice_id;                 /* cloud slot set with srrg2b_set_cloud */
+  int32_t min_num_correspondences;  /* aligner_slice_processor.h:61-66, strict > */
+  int32_t reserved;
+  float robot_in_sensor[16];        /* aligner_slice_processor.h:142-150 */
+  srrg2b_finder_params finder;
+  srrg2b_factor_params factor;
+  float prior_measurement[16];      /* prior: factor measurement AND initial guess (odometry_prior.cpp:19,34) */
+  float prior_info_diag[6];         /* param_diagonal_info_matrix */
+} srrg2b_slice;
+
+/* srrg2_solver::IterationStats fields the reference reads (aligner_termination_criteria_impl.cpp:30-32) */
+typedef struct {
+  int32_t iteration;
+  int32_t solver_status;            /* 1 = SolverBase::Success */
+  int64_t num_inliers, num_outliers, num_suppressed, num_correspondences;
+  double chi_inliers, chi_outliers;
+} srrg2b_iter_stats;
+
+/* AlignerBase / MultiAlignerBase_ / AlignerTerminationCriteriaStandard_ parameters, same names and
+ * defaults: aligner.h:30-35, multi_aligner.h:45-57, aligner_termination_criteria.h:40-56 */
+typedef struct {
+  int32_t variable;
+  int32_t max_iterations;
+  int32_t min_num_inliers;
+  int32_t enable_inlier_only_runs;
+  int32_t keep_only_inlier_correspondences;
+  int32_t use_termination_criteria;
+  int32_t window_size, num_correspondences_range, num_inliers_range, num_outliers_range;
+  float chi_epsilon;
+} srrg2b_aligner_params;
+
+/* ---- context ---- */
+int srrg2b_version(void);
+int srrg2b_ctx_create(int dim, int device, srrg2b_ctx** out);
+int srrg2b_ctx_destroy(srrg2b_ctx* ctx);
+const char* srrg2b_last_error(const srrg2b_ctx* ctx);
+/* CUDA stream the context launches on (cudaStream_t), for callers that time with events */
+void* srrg2b_stream(srrg2b_ctx* ctx);
+/* number of kernels this context has launched so far */
+int64_t srrg2b_launch_count(const srrg2b_ctx* ctx);
+
+/* ---- multi-GPU: one context per rank; only the reduced H/b/stats cross NVLink ---- */
+int srrg2b_comm_unique_id(void* id_128_bytes);
+int srrg2b_comm_init(srrg2b_ctx* ctx, const void* id_128_bytes, int rank, int world_size);
+
+/* ---- data: CorrespondenceFinder_::setFixed / setMoving (correspondence_finder.h:80-91) ---- */
+int srrg2b_set_cloud(srrg2b_ctx* ctx, int slot, int slice_id, const srrg2b_cloud* cloud);
+
+/* ---- a3: CorrespondenceFinder_::compute() (correspondence_finder.h:56). S = local_map_in_sensor
+ * (:111-114). Output: ascending moving_idx, at most one entry per moving point; buffers must hold
+ * n_moving entries; any of them may be NULL. */
+int srrg2b_find_correspondences(srrg2b_ctx* ctx, int slice_id, const float* S, const srrg2b_finder_params* fp,
+                                int32_t* fixed_idx, int32_t* moving_idx, float* response, int64_t* n_out);
+/* HBST path (R/registration/loop_detector/multi_loop_detector_hbst_impl.cpp:331-352): externally
+ * matched correspondences, then srrg2b_linearize / srrg2b_icp_iterate with fixed associations */
+int srrg2b_set_correspondences(srrg2b_ctx* ctx, int slice_id, const int32_t* fixed_idx, const int32_t* moving_idx, int64_t n);
+
+/* ---- a5 (linearise): FactorCorrespondenceDriven_ accumulation over the slice's current
+ * correspondences at S. H is PxP row-major (P = 6 | 3), b is P; acc (optional) receives the 32
+ * exact fixed-point sums; status/chi (optional) are per correspondence in ascending moving_idx. */
+int srrg2b_linearize(srrg2b_ctx* ctx, int slice_id, const float* S, int variable, const srrg2b_finder_params* fp,
+                     const srrg2b_factor_params* fa, double* H, double* b, int64_t* acc,
+                     srrg2b_iter_stats* stats, uint8_t* status, float* chi);
+
+/* ---- a1..a9: MultiAlignerBase_::compute() (multi_aligner_impl.cpp:46-95) entirely on the device:
+ * all iterations are enqueued back to back, termination is decided on the GPU, one sync at the end.
+ * stats_out holds *n_stats entries on input (capacity) and receives the appended IterationStats. */
+int srrg2b_icp_run(srrg2b_ctx* ctx, int n_slices, const srrg2b_slice* slices, const srrg2b_aligner_params* ap,
+                   float* T_inout, srrg2b_iter_stats* stats_out, int32_t* n_stats, int32_t* aligner_status);
+/* one _runSolver iteration (multi_aligner_impl.cpp:103-126 body): correspondences + one GN step */
+int srrg2b_icp_iterate(srrg2b_ctx* ctx, int n_slices, const srrg2b_slice* slices, int variable,
+                       float* T_inout, srrg2b_iter_stats* stats, int32_t* association_good);
+/* correspondences of the last iteration (pruned to inliers if keep_only_inlier_correspondences),
+ * Aligner_::storeCorrespondences() (aligner_slice_processor_impl.cpp:50-74) */
+int srrg2b_get_correspondences(srrg2b_ctx* ctx, int slice_id, int32_t* fixed_idx, int32_t* moving_idx,
+                               float* response, int64_t* n_out);
+
+/* ---- benchmarking support: device time of the last srrg2b_icp_run between its first and last
+ * kernel (CUDA events on the context stream), and how many _runSolver iterations it executed ---- */
+int srrg2b_last_run_timing(srrg2b_ctx* ctx, float* device_ms, int32_t* iterations);
+/* when enabled, every launch of the fused per-slice ICP kernel is bracketed by CUDA events on the
+ * context stream; the sum and count for the last run are returned (roofline measurement) */
+int srrg2b_set_kernel_timing(srrg2b_ctx* ctx, int enable);
+int srrg2b_last_kernel_timing(srrg2b_ctx* ctx, float* slice_kernel_ms, int32_t* slice_kernel_launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

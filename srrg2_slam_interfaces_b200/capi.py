@@ -1,0 +1,305 @@
+"""ctypes binding of libsrrg2b.so (include/srrg2b.h).  This is the product path: it fails loudly
+when the CUDA library is missing or no GPU is present -- there is no CPU fallback."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsrrg2b.so")
+
+OK, ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_NCCL = 0, 1, 2, 3, 4
+FIXED, MOVING = 0, 1
+FACTOR_P2P, FACTOR_PLANE = 0, 1
+ROB_NONE, ROB_SATURATED, ROB_CAUCHY, ROB_CLAMP, ROB_HUBER = 0, 1, 2, 3, 4
+VAR_SE3_QUAT_RIGHT, VAR_SE3_EULER_RIGHT = 0, 1
+FINDER_NN, FINDER_PROJECTIVE = 0, 1
+SLICE_POINTS, SLICE_PRIOR = 0, 1
+ALIGNER_SUCCESS, ALIGNER_NOT_ENOUGH_CORRESPONDENCES, ALIGNER_NOT_ENOUGH_INLIERS, ALIGNER_FAIL = 0, 1, 2, 3
+STAT_INLIER, STAT_KERNELIZED, STAT_SUPPRESSED, STAT_NONE = 0, 1, 2, 3
+MAX_SLICES = 8
+
+EXPORTED_SYMBOLS = [
+    "srrg2b_version", "srrg2b_ctx_create", "srrg2b_ctx_destroy", "srrg2b_last_error", "srrg2b_stream",
+    "srrg2b_launch_count", "srrg2b_comm_unique_id", "srrg2b_comm_init", "srrg2b_set_cloud",
+    "srrg2b_find_correspondences", "srrg2b_set_correspondences", "srrg2b_linearize", "srrg2b_icp_run",
+    "srrg2b_icp_iterate", "srrg2b_get_correspondences", "srrg2b_last_run_timing",
+    "srrg2b_set_kernel_timing", "srrg2b_last_kernel_timing",
+]
+
+
+class Srrg2bError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("srrg2b error %d: %s" % (code, msg))
+        self.code = code
+
+
+class Cloud(C.Structure):
+    _fields_ = [("coords", C.c_void_p), ("normals", C.c_void_p), ("valid", C.c_void_p), ("n", C.c_int64),
+                ("index_offset", C.c_int64), ("n_global", C.c_int64), ("on_device", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+class FinderParams(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("max_distance", C.c_float), ("normal_cos", C.c_float),
+                ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float),
+                ("width", C.c_int32), ("height", C.c_int32), ("min_depth", C.c_float), ("max_depth", C.c_float)]
+
+
+class FactorParams(C.Structure):
+    _fields_ = [("factor", C.c_int32), ("robustifier", C.c_int32), ("chi_threshold", C.c_float),
+                ("info_point", C.c_float), ("info_normal", C.c_float)]
+
+
+class Slice(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("slice_id", C.c_int32), ("min_num_correspondences", C.c_int32),
+                ("reserved", C.c_int32), ("robot_in_sensor", C.c_float * 16), ("finder", FinderParams),
+                ("factor", FactorParams), ("prior_measurement", C.c_float * 16),
+                ("prior_info_diag", C.c_float * 6)]
+
+
+class IterStats(C.Structure):
+    _fields_ = [("iteration", C.c_int32), ("solver_status", C.c_int32), ("num_inliers", C.c_int64),
+                ("num_outliers", C.c_int64), ("num_suppressed", C.c_int64), ("num_correspondences", C.c_int64),
+                ("chi_inliers", C.c_double), ("chi_outliers", C.c_double)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class AlignerParams(C.Structure):
+    _fields_ = [("variable", C.c_int32), ("max_iterations", C.c_int32), ("min_num_inliers", C.c_int32),
+                ("enable_inlier_only_runs", C.c_int32), ("keep_only_inlier_correspondences", C.c_int32),
+                ("use_termination_criteria", C.c_int32), ("window_size", C.c_int32),
+                ("num_correspondences_range", C.c_int32), ("num_inliers_range", C.c_int32),
+                ("num_outliers_range", C.c_int32), ("chi_epsilon", C.c_float)]
+
+
+_lib = None
+
+
+def load_library():
+    """Loads libsrrg2b.so; raises if it has not been built (python __graft_entry__.py build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise Srrg2bError(ERR_CUDA, "libsrrg2b.so is not built (%s); run __graft_entry__.build()" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    vp, i32p, i64p = C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int64)
+    lib.srrg2b_version.restype = C.c_int
+    lib.srrg2b_ctx_create.argtypes = [C.c_int, C.c_int, C.POINTER(vp)]
+    lib.srrg2b_ctx_destroy.argtypes = [vp]
+    lib.srrg2b_last_error.restype = C.c_char_p
+    lib.srrg2b_last_error.argtypes = [vp]
+    lib.srrg2b_stream.restype = vp
+    lib.srrg2b_stream.argtypes = [vp]
+    lib.srrg2b_launch_count.restype = C.c_int64
+    lib.srrg2b_launch_count.argtypes = [vp]
+    lib.srrg2b_comm_unique_id.argtypes = [vp]
+    lib.srrg2b_comm_init.argtypes = [vp, vp, C.c_int, C.c_int]
+    lib.srrg2b_set_cloud.argtypes = [vp, C.c_int, C.c_int, C.POINTER(Cloud)]
+    lib.srrg2b_find_correspondences.argtypes = [vp, C.c_int, vp, C.POINTER(FinderParams), vp, vp, vp, i64p]
+    lib.srrg2b_set_correspondences.argtypes = [vp, C.c_int, vp, vp, C.c_int64]
+    lib.srrg2b_linearize.argtypes = [vp, C.c_int, vp, C.c_int, C.POINTER(FinderParams), C.POINTER(FactorParams),
+                                     vp, vp, vp, C.POINTER(IterStats), vp, vp]
+    lib.srrg2b_icp_run.argtypes = [vp, C.c_int, C.POINTER(Slice), C.POINTER(AlignerParams), vp,
+                                   C.POINTER(IterStats), i32p, i32p]
+    lib.srrg2b_icp_iterate.argtypes = [vp, C.c_int, C.POINTER(Slice), C.c_int, vp, C.POINTER(IterStats), i32p]
+    lib.srrg2b_get_correspondences.argtypes = [vp, C.c_int, vp, vp, vp, i64p]
+    lib.srrg2b_last_run_timing.argtypes = [vp, C.POINTER(C.c_float), i32p]
+    lib.srrg2b_set_kernel_timing.argtypes = [vp, C.c_int]
+    lib.srrg2b_last_kernel_timing.argtypes = [vp, C.POINTER(C.c_float), i32p]
+    _lib = lib
+    return lib
+
+
+def finder_params(max_distance=0.5, normal_cos=0.8, kind=FINDER_NN, fx=0, fy=0, cx=0, cy=0, width=0, height=0,
+                  min_depth=0.0, max_depth=1e9):
+    return FinderParams(kind, max_distance, normal_cos, fx, fy, cx, cy, width, height, min_depth, max_depth)
+
+
+def factor_params(factor=FACTOR_PLANE, robustifier=ROB_NONE, chi_threshold=1.0, info_point=1.0, info_normal=1.0):
+    return FactorParams(factor, robustifier, chi_threshold, info_point, info_normal)
+
+
+def aligner_params(variable=VAR_SE3_QUAT_RIGHT, max_iterations=10, min_num_inliers=10,
+                   enable_inlier_only_runs=False, keep_only_inlier_correspondences=False,
+                   use_termination_criteria=False, window_size=5, num_correspondences_range=20,
+                   num_inliers_range=20, num_outliers_range=20, chi_epsilon=0.2):
+    return AlignerParams(variable, max_iterations, min_num_inliers, int(enable_inlier_only_runs),
+                         int(keep_only_inlier_correspondences), int(use_termination_criteria), window_size,
+                         num_correspondences_range, num_inliers_range, num_outliers_range, chi_epsilon)
+
+
+def make_slice(dim, slice_id=0, robot_in_sensor=None, fp=None, fa=None, min_num_correspondences=0,
+               prior_measurement=None, prior_info_diag=None):
+    s = Slice()
+    D1 = dim + 1
+    eye = np.eye(D1, dtype=np.float32).reshape(-1)
+    r = eye if robot_in_sensor is None else np.asarray(robot_in_sensor, dtype=np.float32).reshape(-1)
+    for i in range(D1 * D1):
+        s.robot_in_sensor[i] = r[i]
+    if prior_measurement is not None:
+        s.kind = SLICE_PRIOR
+        z = np.asarray(prior_measurement, dtype=np.float32).reshape(-1)
+        for i in range(D1 * D1):
+            s.prior_measurement[i] = z[i]
+        info = np.asarray(prior_info_diag, dtype=np.float32).reshape(-1)
+        for i in range(len(info)):
+            s.prior_info_diag[i] = info[i]
+        return s
+    s.kind = SLICE_POINTS
+    s.slice_id = slice_id
+    s.min_num_correspondences = min_num_correspondences
+    s.finder = fp
+    s.factor = fa
+    return s
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+class Context:
+    """One srrg2b_ctx: one GPU, one CUDA stream, device-resident clouds."""
+
+    def __init__(self, dim, device=0):
+        self.lib = load_library()
+        self.dim = dim
+        h = C.c_void_p()
+        rc = self.lib.srrg2b_ctx_create(dim, device, C.byref(h))
+        if rc != OK:
+            raise Srrg2bError(rc, "srrg2b_ctx_create failed (no CUDA device? dim=%d device=%d)" % (dim, device))
+        self.h = h
+        self._keep = {}
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.srrg2b_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != OK:
+            raise Srrg2bError(rc, self.lib.srrg2b_last_error(self.h).decode())
+
+    @property
+    def stream(self):
+        return self.lib.srrg2b_stream(self.h)
+
+    @property
+    def launch_count(self):
+        return self.lib.srrg2b_launch_count(self.h)
+
+    # ---- multi GPU ----
+    def unique_id(self):
+        buf = (C.c_char * 128)()
+        rc = self.lib.srrg2b_comm_unique_id(buf)
+        if rc != OK:
+            raise Srrg2bError(rc, "ncclGetUniqueId failed")
+        return bytes(buf)
+
+    def comm_init(self, uid, rank, world):
+        buf = (C.c_char * 128).from_buffer_copy(uid)
+        self._check(self.lib.srrg2b_comm_init(self.h, buf, rank, world))
+
+    # ---- data ----
+    def set_cloud(self, slot, slice_id, coords, normals=None, valid=None, index_offset=0, n_global=0):
+        coords = np.ascontiguousarray(coords, dtype=np.float32)
+        if coords.ndim != 2 or coords.shape[1] != self.dim:
+            raise Srrg2bError(ERR_INVALID, "coords must be n x %d" % self.dim)
+        normals = None if normals is None else np.ascontiguousarray(normals, dtype=np.float32)
+        valid = None if valid is None else np.ascontiguousarray(valid, dtype=np.uint8)
+        cl = Cloud(_ptr(coords), _ptr(normals), _ptr(valid), coords.shape[0], index_offset, n_global, 0, 0)
+        self._check(self.lib.srrg2b_set_cloud(self.h, slot, slice_id, C.byref(cl)))
+
+    def set_cloud_device(self, slot, slice_id, coords_ptr, normals_ptr, valid_ptr, n, index_offset=0, n_global=0):
+        cl = Cloud(coords_ptr, normals_ptr, valid_ptr, n, index_offset, n_global, 1, 0)
+        self._check(self.lib.srrg2b_set_cloud(self.h, slot, slice_id, C.byref(cl)))
+
+    # ---- a3 ----
+    def find_correspondences(self, slice_id, S, fp, n_moving):
+        S = np.ascontiguousarray(np.asarray(S, dtype=np.float32).reshape(-1))
+        fi = np.empty(n_moving, dtype=np.int32)
+        mi = np.empty(n_moving, dtype=np.int32)
+        rs = np.empty(n_moving, dtype=np.float32)
+        n = C.c_int64(0)
+        self._check(self.lib.srrg2b_find_correspondences(self.h, slice_id, S.ctypes.data, C.byref(fp), fi.ctypes.data,
+                                                         mi.ctypes.data, rs.ctypes.data, C.byref(n)))
+        return fi[:n.value], mi[:n.value], rs[:n.value]
+
+    def set_correspondences(self, slice_id, fixed_idx, moving_idx):
+        fi = np.ascontiguousarray(fixed_idx, dtype=np.int32)
+        mi = np.ascontiguousarray(moving_idx, dtype=np.int32)
+        self._check(self.lib.srrg2b_set_correspondences(self.h, slice_id, fi.ctypes.data, mi.ctypes.data, fi.size))
+
+    # ---- a5 ----
+    def linearize(self, slice_id, S, fp, fa, variable=VAR_SE3_QUAT_RIGHT, n_moving=0, want_status=True):
+        P = 6 if self.dim == 3 else 3
+        S = np.ascontiguousarray(np.asarray(S, dtype=np.float32).reshape(-1))
+        H = np.zeros((P, P), dtype=np.float64)
+        b = np.zeros(P, dtype=np.float64)
+        acc = np.zeros(32, dtype=np.int64)
+        st = IterStats()
+        status = np.empty(n_moving, dtype=np.uint8) if want_status else None
+        chi = np.empty(n_moving, dtype=np.float32) if want_status else None
+        self._check(self.lib.srrg2b_linearize(self.h, slice_id, S.ctypes.data, variable, C.byref(fp), C.byref(fa),
+                                              H.ctypes.data, b.ctypes.data, acc.ctypes.data, C.byref(st),
+                                              _ptr(status), _ptr(chi)))
+        n = st.num_correspondences
+        return dict(H=H, b=b, acc=acc, stats=st.as_dict(), status=None if status is None else status[:n],
+                    chi=None if chi is None else chi[:n])
+
+    # ---- a1 ----
+    def icp_run(self, slices, ap, T0):
+        D1 = self.dim + 1
+        n = len(slices)
+        arr = (Slice * n)(*slices)
+        T = np.ascontiguousarray(np.asarray(T0, dtype=np.float32).reshape(D1, D1)).copy()
+        cap = 256
+        stats = (IterStats * cap)()
+        n_stats = C.c_int32(cap)
+        status = C.c_int32(-1)
+        self._check(self.lib.srrg2b_icp_run(self.h, n, arr, C.byref(ap), T.ctypes.data, stats, C.byref(n_stats),
+                                            C.byref(status)))
+        return dict(T=T, status=status.value, stats=[stats[i].as_dict() for i in range(min(n_stats.value, cap))])
+
+    def icp_iterate(self, slices, variable, T):
+        D1 = self.dim + 1
+        n = len(slices)
+        arr = (Slice * n)(*slices)
+        T = np.ascontiguousarray(np.asarray(T, dtype=np.float32).reshape(D1, D1)).copy()
+        st = IterStats()
+        good = C.c_int32(0)
+        self._check(self.lib.srrg2b_icp_iterate(self.h, n, arr, variable, T.ctypes.data, C.byref(st), C.byref(good)))
+        return dict(T=T, stats=st.as_dict(), association_good=bool(good.value))
+
+    def get_correspondences(self, slice_id, n_moving):
+        fi = np.empty(n_moving, dtype=np.int32)
+        mi = np.empty(n_moving, dtype=np.int32)
+        rs = np.empty(n_moving, dtype=np.float32)
+        n = C.c_int64(0)
+        self._check(self.lib.srrg2b_get_correspondences(self.h, slice_id, fi.ctypes.data, mi.ctypes.data,
+                                                        rs.ctypes.data, C.byref(n)))
+        return fi[:n.value], mi[:n.value], rs[:n.value]
+
+    def set_kernel_timing(self, enable):
+        self._check(self.lib.srrg2b_set_kernel_timing(self.h, int(enable)))
+
+    def last_kernel_timing(self):
+        ms = C.c_float(0)
+        n = C.c_int32(0)
+        self._check(self.lib.srrg2b_last_kernel_timing(self.h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def last_run_timing(self):
+        ms = C.c_float(0)
+        it = C.c_int32(0)
+        self._check(self.lib.srrg2b_last_run_timing(self.h, C.byref(ms), C.byref(it)))
+        return ms.value, it.value

@@ -1,0 +1,945 @@
+// s2b_api.cu -- host side of libsrrg2b.so: context, cloud residency, index builds, launch
+// sequencing of the device-driven ICP loop, NCCL plumbing, and the extern "C" boundary declared in
+// include/srrg2b.h.  No CPU fallback: without a CUDA device every compute call returns
+// SRRG2B_ERR_CUDA.
+#include "s2b_icp.cuh"
+
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+#include <dlfcn.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+using namespace s2b;
+
+namespace {
+
+// ---- minimal NCCL binding (resolved at run time from the NCCL already loaded in the process) ----
+struct NcclId { char internal[128]; };
+typedef void* ncclComm_t;
+struct NcclApi {
+  void* handle = nullptr;
+  int (*GetUniqueId)(NcclId*) = nullptr;
+  int (*CommInitRank)(ncclComm_t*, int, NcclId, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool load() {
+    if (handle) return true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so", nullptr};
+    const char* env = getenv("SRRG2B_NCCL_LIB");
+    if (env) handle = dlopen(env, RTLD_NOW | RTLD_GLOBAL);
+    for (int i = 0; !handle && names[i]; ++i) handle = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
+    if (!handle) return false;
+    GetUniqueId = (int (*)(NcclId*)) dlsym(handle, "ncclGetUniqueId");
+    CommInitRank = (int (*)(ncclComm_t*, int, NcclId, int)) dlsym(handle, "ncclCommInitRank");
+    AllReduce = (int (*)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t)) dlsym(handle, "ncclAllReduce");
+    CommDestroy = (int (*)(ncclComm_t)) dlsym(handle, "ncclCommDestroy");
+    GetErrorString = (const char* (*) (int) ) dlsym(handle, "ncclGetErrorString");
+    return GetUniqueId && CommInitRank && AllReduce && CommDestroy;
+  }
+};
+NcclApi g_nccl;
+constexpr int kNcclUint64 = 5, kNcclFloat32 = 7, kNcclSum = 0, kNcclMax = 2;
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMalloc((void**) &p, sizeof(T) * (n ? n : 1));
+    if (e == cudaSuccess) cap = n;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+struct RawCloud {
+  DevBuf<float> xyz, nrm;
+  DevBuf<unsigned char> valid;
+  int64_t n = 0, n_global = 0, index_offset = 0;
+  bool has_normals = false, has_valid = false, present = false;
+};
+
+struct SliceData {
+  RawCloud fixed_raw, moving_raw;
+  // fixed index (lazy, keyed by the cell size it was built for)
+  DevBuf<float4> f_pts, f_nrm;
+  DevBuf<int> f_inverse, cell_start;
+  int nf_valid = 0;
+  float built_for_max_distance = -1.f;
+  float ox = 0, oy = 0, oz = 0, inv_cell = 1;
+  int nx = 1, ny = 1, nz = 1;
+  // moving, Morton order
+  DevBuf<float4> m_pts, m_nrm;
+  DevBuf<int> m_inverse;
+  int nm_valid = 0;
+  float coord_bound = 0.f;
+  bool coord_bound_global = false;
+  // correspondences in moving-sorted order
+  DevBuf<int> c_fidx, c_fpos;
+  DevBuf<float> c_resp, c_chi;
+  DevBuf<unsigned char> c_stat;
+  bool corr_valid = false, stat_valid = false;
+  int prune_on_export = 0;
+};
+
+}  // namespace
+
+struct srrg2b_ctx {
+  int dim = 3, device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::string err;
+  int64_t launches = 0;
+  std::map<int, SliceData> slices;
+  DevState* d_state = nullptr;
+  DevState* h_state = nullptr;  // pinned mirror (header part is copied back)
+  // scratch
+  DevBuf<unsigned> keys_a, keys_b;
+  DevBuf<int> vals_a, vals_b, flags, positions, bounds;
+  DevBuf<unsigned char> cub_tmp;
+  DevBuf<int> o_fidx, o_midx, d_fidx;
+  DevBuf<float> o_resp, d_resp, o_chi, d_chi;
+  DevBuf<unsigned char> o_stat, d_stat;
+  DevBuf<int> imp_f, imp_m, imp_bad;
+  int* h_bounds = nullptr;  // pinned 8 ints
+  // comm
+  ncclComm_t comm = nullptr;
+  int rank = 0, world = 1;
+  float last_ms = 0.f;
+  int last_iterations = 0;
+  int sm_count = 148;
+  // optional per-launch timing of the slice kernel (roofline measurement)
+  bool time_kernels = false;
+  std::vector<cudaEvent_t> kev;
+  size_t kev_used = 0;
+  float last_kernel_ms = 0.f;
+  int last_kernel_launches = 0;
+};
+
+namespace {
+
+#define CK(ctx, call)                                                                         \
+  do {                                                                                        \
+    cudaError_t e__ = (call);                                                                 \
+    if (e__ != cudaSuccess) {                                                                 \
+      (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e__);                       \
+      return SRRG2B_ERR_CUDA;                                                                 \
+    }                                                                                         \
+  } while (0)
+
+#define FAIL(ctx, code, msg) \
+  do {                       \
+    (ctx)->err = (msg);      \
+    return (code);           \
+  } while (0)
+
+inline int blocks_for(int64_t n, int threads) { return (int) ((n + threads - 1) / threads); }
+
+int cub_sort_pairs(srrg2b_ctx* c, int n, int end_bit) {
+  size_t bytes = 0;
+  CK(c, cub::DeviceRadixSort::SortPairs(nullptr, bytes, c->keys_a.p, c->keys_b.p, c->vals_a.p, c->vals_b.p, n, 0,
+                                        end_bit, c->stream));
+  CK(c, c->cub_tmp.ensure(bytes));
+  CK(c, cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, bytes, c->keys_a.p, c->keys_b.p, c->vals_a.p, c->vals_b.p, n, 0,
+                                        end_bit, c->stream));
+  return SRRG2B_OK;
+}
+
+int compute_bounds(srrg2b_ctx* c, const RawCloud& rc) {
+  CK(c, c->bounds.ensure(8));
+  const int init[8] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN, 0, 0};
+  CK(c, cudaMemcpyAsync(c->bounds.p, init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
+  if (rc.n > 0) {
+    const int blocks = std::min(blocks_for(rc.n, 256), c->sm_count * 8);
+    bounds_kernel<<<blocks, 256, 0, c->stream>>>(rc.xyz.p, rc.has_valid ? rc.valid.p : nullptr, (int) rc.n, c->dim,
+                                                 c->bounds.p);
+    c->launches++;
+  }
+  CK(c, cudaMemcpyAsync(c->h_bounds, c->bounds.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CK(c, cudaStreamSynchronize(c->stream));
+  return SRRG2B_OK;
+}
+
+int upload_raw(srrg2b_ctx* c, RawCloud& rc, const srrg2b_cloud* cl) {
+  const int dim = c->dim;
+  const cudaMemcpyKind kind = cl->on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  rc.n = cl->n;
+  rc.n_global = cl->n_global > 0 ? cl->n_global : cl->n;
+  rc.index_offset = cl->index_offset;
+  rc.has_normals = cl->normals != nullptr;
+  rc.has_valid = cl->valid != nullptr;
+  CK(c, rc.xyz.ensure((size_t) cl->n * dim));
+  if (cl->n) CK(c, cudaMemcpyAsync(rc.xyz.p, cl->coords, sizeof(float) * cl->n * dim, kind, c->stream));
+  if (rc.has_normals) {
+    CK(c, rc.nrm.ensure((size_t) cl->n * dim));
+    if (cl->n) CK(c, cudaMemcpyAsync(rc.nrm.p, cl->normals, sizeof(float) * cl->n * dim, kind, c->stream));
+  }
+  if (rc.has_valid) {
+    CK(c, rc.valid.ensure((size_t) cl->n));
+    if (cl->n) CK(c, cudaMemcpyAsync(rc.valid.p, cl->valid, cl->n, kind, c->stream));
+  }
+  rc.present = true;
+  return SRRG2B_OK;
+}
+
+// moving cloud: Morton order over its own bounding box, float4 SoA, inverse permutation
+int build_moving(srrg2b_ctx* c, SliceData& sd) {
+  RawCloud& rc = sd.moving_raw;
+  const int n = (int) rc.n, dim = c->dim;
+  int rcode = compute_bounds(c, rc);
+  if (rcode) return rcode;
+  sd.nm_valid = c->h_bounds[7];
+  memcpy(&sd.coord_bound, &c->h_bounds[6], 4);
+  sd.coord_bound_global = false;
+  CK(c, sd.m_pts.ensure((size_t) n));
+  CK(c, sd.m_nrm.ensure((size_t) n));
+  CK(c, sd.m_inverse.ensure((size_t) n));
+  CK(c, sd.c_fidx.ensure((size_t) n));
+  CK(c, sd.c_fpos.ensure((size_t) n));
+  CK(c, sd.c_resp.ensure((size_t) n));
+  CK(c, sd.c_chi.ensure((size_t) n));
+  CK(c, sd.c_stat.ensure((size_t) n));
+  sd.corr_valid = false;
+  sd.stat_valid = false;
+  if (n == 0) return SRRG2B_OK;
+  float mn[3] = {0, 0, 0}, mx[3] = {0, 0, 0};
+  for (int a = 0; a < dim; ++a) {
+    mn[a] = ord2f(c->h_bounds[a]);
+    mx[a] = ord2f(c->h_bounds[3 + a]);
+  }
+  const float q = dim == 3 ? 1023.f : 32767.f;
+  float sc[3];
+  for (int a = 0; a < 3; ++a) {
+    const float ext = mx[a] - mn[a];
+    sc[a] = (sd.nm_valid > 0 && ext > 0.f) ? q / ext : 0.f;
+  }
+  CK(c, c->keys_a.ensure(n));
+  CK(c, c->keys_b.ensure(n));
+  CK(c, c->vals_a.ensure(n));
+  CK(c, c->vals_b.ensure(n));
+  morton_key_kernel<<<blocks_for(n, 256), 256, 0, c->stream>>>(rc.xyz.p, rc.has_valid ? rc.valid.p : nullptr, n, dim,
+                                                               mn[0], mn[1], mn[2], sc[0], sc[1], sc[2], c->keys_a.p,
+                                                               c->vals_a.p);
+  c->launches++;
+  rcode = cub_sort_pairs(c, n, 32);
+  if (rcode) return rcode;
+  fill_int_kernel<<<blocks_for(n, 256), 256, 0, c->stream>>>(sd.m_inverse.p, n, -1);
+  c->launches++;
+  if (sd.nm_valid > 0) {
+    gather_kernel<<<blocks_for(sd.nm_valid, 256), 256, 0, c->stream>>>(
+      rc.xyz.p, rc.has_normals ? rc.nrm.p : nullptr, c->vals_b.p, sd.nm_valid, dim, sd.m_pts.p, sd.m_nrm.p,
+      sd.m_inverse.p);
+    c->launches++;
+    fill_int_kernel<<<blocks_for(sd.nm_valid, 256), 256, 0, c->stream>>>(sd.c_fidx.p, sd.nm_valid, -1);
+    fill_int_kernel<<<blocks_for(sd.nm_valid, 256), 256, 0, c->stream>>>(sd.c_fpos.p, sd.nm_valid, -1);
+    c->launches += 2;
+  }
+  CK(c, cudaGetLastError());
+  return SRRG2B_OK;
+}
+
+// k0: uniform grid over the fixed cloud with cell edge >= max_distance (so the 3^dim
+// neighbourhood of a query's cell contains every point within max_distance), cell-sorted float4 SoA
+int ensure_index(srrg2b_ctx* c, SliceData& sd, float max_distance) {
+  RawCloud& rc = sd.fixed_raw;
+  if (!rc.present) FAIL(c, SRRG2B_ERR_STATE, "fixed cloud not set for slice");
+  if (!(max_distance > 0.f)) FAIL(c, SRRG2B_ERR_INVALID, "max_distance must be > 0");
+  if (sd.built_for_max_distance == max_distance) return SRRG2B_OK;
+  const int n = (int) rc.n, dim = c->dim;
+  int rcode = compute_bounds(c, rc);
+  if (rcode) return rcode;
+  sd.nf_valid = c->h_bounds[7];
+  float mn[3] = {0, 0, 0}, mx[3] = {0, 0, 0};
+  if (sd.nf_valid > 0) {
+    for (int a = 0; a < dim; ++a) {
+      mn[a] = ord2f(c->h_bounds[a]);
+      mx[a] = ord2f(c->h_bounds[3 + a]);
+    }
+  }
+  // 0.1% slack on the cell edge absorbs the fp32 rounding of the cell coordinate
+  float cell = max_distance * 1.001f;
+  int dims[3] = {1, 1, 1};
+  for (;;) {
+    double total = 1.0;
+    bool ok = true;
+    for (int a = 0; a < dim; ++a) {
+      const double cnt = floor((double) (mx[a] - mn[a]) / (double) cell) + 1.0;
+      if (cnt > 1024.0) ok = false;
+      dims[a] = (int) (cnt > 1024.0 ? 1024 : cnt);
+      total *= cnt;
+    }
+    if (ok && total <= 16.0 * 1024 * 1024) break;
+    cell *= 2.f;
+  }
+  sd.ox = mn[0]; sd.oy = mn[1]; sd.oz = mn[2];
+  sd.inv_cell = 1.f / cell;
+  sd.nx = dims[0]; sd.ny = dims[1]; sd.nz = dims[2];
+  const int ncells = sd.nx * sd.ny * sd.nz;
+  CK(c, sd.f_pts.ensure((size_t) n + 1));
+  CK(c, sd.f_nrm.ensure((size_t) n + 1));
+  CK(c, sd.f_inverse.ensure((size_t) n + 1));
+  CK(c, sd.cell_start.ensure((size_t) ncells + 1));
+  if (n > 0) {
+    CK(c, c->keys_a.ensure(n));
+    CK(c, c->keys_b.ensure(n));
+    CK(c, c->vals_a.ensure(n));
+    CK(c, c->vals_b.ensure(n));
+    cell_key_kernel<<<blocks_for(n, 256), 256, 0, c->stream>>>(rc.xyz.p, rc.has_valid ? rc.valid.p : nullptr, n, dim,
+                                                               sd.ox, sd.oy, sd.oz, sd.inv_cell, sd.nx, sd.ny, sd.nz,
+                                                               c->keys_a.p, c->vals_a.p);
+    c->launches++;
+    rcode = cub_sort_pairs(c, n, 32);
+    if (rcode) return rcode;
+    fill_int_kernel<<<blocks_for(n, 256), 256, 0, c->stream>>>(sd.f_inverse.p, n, -1);
+    c->launches++;
+    if (sd.nf_valid > 0) {
+      gather_kernel<<<blocks_for(sd.nf_valid, 256), 256, 0, c->stream>>>(
+        rc.xyz.p, rc.has_normals ? rc.nrm.p : nullptr, c->vals_b.p, sd.nf_valid, dim, sd.f_pts.p, sd.f_nrm.p,
+        sd.f_inverse.p);
+      c->launches++;
+    }
+  }
+  cell_start_kernel<<<blocks_for(ncells + 1, 256), 256, 0, c->stream>>>(c->keys_b.p, sd.nf_valid, ncells,
+                                                                        sd.cell_start.p);
+  c->launches++;
+  CK(c, cudaGetLastError());
+  sd.built_for_max_distance = max_distance;
+  return SRRG2B_OK;
+}
+
+int ensure_global_bound(srrg2b_ctx* c, SliceData& sd) {
+  if (c->world <= 1 || sd.coord_bound_global) return SRRG2B_OK;
+  CK(c, c->bounds.ensure(8));
+  CK(c, cudaMemcpyAsync(c->bounds.p, &sd.coord_bound, 4, cudaMemcpyHostToDevice, c->stream));
+  if (g_nccl.AllReduce(c->bounds.p, c->bounds.p, 1, kNcclFloat32, kNcclMax, c->comm, c->stream) != 0)
+    FAIL(c, SRRG2B_ERR_NCCL, "ncclAllReduce(max) failed");
+  CK(c, cudaMemcpyAsync(&sd.coord_bound, c->bounds.p, 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(c, cudaStreamSynchronize(c->stream));
+  sd.coord_bound_global = true;
+  return SRRG2B_OK;
+}
+
+int fill_slice_args(srrg2b_ctx* c, SliceData& sd, int state_slot, const srrg2b_finder_params& fp,
+                    const srrg2b_factor_params& fa, int variable, bool want_status, SliceArgs& a, Scales* sc_out) {
+  if (!sd.moving_raw.present) FAIL(c, SRRG2B_ERR_STATE, "moving cloud not set for slice");
+  if (fp.kind != SRRG2B_FINDER_NN) FAIL(c, SRRG2B_ERR_INVALID, "finder kind not supported by this entry point");
+  int rcode = ensure_index(c, sd, fp.max_distance);
+  if (rcode) return rcode;
+  rcode = ensure_global_bound(c, sd);
+  if (rcode) return rcode;
+  const bool normals = sd.fixed_raw.has_normals && sd.moving_raw.has_normals;
+  if (fa.factor == SRRG2B_FACTOR_PLANE && !normals)
+    FAIL(c, SRRG2B_ERR_INVALID, "PLANE factor needs normals on both clouds");
+  const Scales sc = choose_scales(sd.moving_raw.n_global, sd.coord_bound, fp.max_distance, fa.info_point, fa.info_normal);
+  if (sc_out) *sc_out = sc;
+  a.mp = sd.m_pts.p; a.mn = sd.m_nrm.p; a.nm = sd.nm_valid;
+  a.fp = sd.f_pts.p; a.fn = sd.f_nrm.p; a.cell_start = sd.cell_start.p;
+  a.ox = sd.ox; a.oy = sd.oy; a.oz = sd.oz; a.inv_cell = sd.inv_cell;
+  a.nx = sd.nx; a.ny = sd.ny; a.nz = sd.nz;
+  a.md2 = fp.max_distance * fp.max_distance;
+  a.normal_cos = fp.normal_cos;
+  a.gate = (normals && fp.normal_cos > -1.f) ? 1 : 0;
+  a.rob = fa.robustifier; a.tau = fa.chi_threshold; a.ip = fa.info_point; a.in_ = fa.info_normal;
+  a.rs = (c->dim == 3 && variable == SRRG2B_VAR_SE3_QUAT_RIGHT) ? 2.f : 1.f;
+  a.sH = ldexp(1.0, sc.kH); a.sb = ldexp(1.0, sc.kb); a.sc = ldexp(1.0, sc.kchi);
+  a.S = c->d_state->S[state_slot].m;
+  a.c_fidx = sd.c_fidx.p; a.c_fpos = sd.c_fpos.p; a.c_resp = sd.c_resp.p;
+  a.c_stat = want_status ? sd.c_stat.p : nullptr;
+  a.c_chi = want_status ? sd.c_chi.p : nullptr;
+  a.acc = c->d_state->acc[state_slot];
+  a.stop = &c->d_state->stop;
+  return SRRG2B_OK;
+}
+
+template <int MODE>
+int launch_slice(srrg2b_ctx* c, const SliceArgs& a, int factor) {
+  if (a.nm <= 0) return SRRG2B_OK;
+  const int threads = 256;
+  const int blocks = std::max(1, std::min(blocks_for(a.nm, threads), c->sm_count * 4));
+  if (c->dim == 3) {
+    if (factor == SRRG2B_FACTOR_P2P) icp_slice_kernel<3, SRRG2B_FACTOR_P2P, MODE><<<blocks, threads, 0, c->stream>>>(a);
+    else icp_slice_kernel<3, SRRG2B_FACTOR_PLANE, MODE><<<blocks, threads, 0, c->stream>>>(a);
+  } else {
+    if (factor == SRRG2B_FACTOR_P2P) icp_slice_kernel<2, SRRG2B_FACTOR_P2P, MODE><<<blocks, threads, 0, c->stream>>>(a);
+    else icp_slice_kernel<2, SRRG2B_FACTOR_PLANE, MODE><<<blocks, threads, 0, c->stream>>>(a);
+  }
+  c->launches++;
+  return SRRG2B_OK;
+}
+
+int validate_slices(srrg2b_ctx* c, int n_slices, const srrg2b_slice* slices, int variable) {
+  if (n_slices < 1 || n_slices > SRRG2B_MAX_SLICES || !slices)
+    FAIL(c, SRRG2B_ERR_INVALID, "n_slices must be in [1, SRRG2B_MAX_SLICES]");
+  for (int s = 0; s < n_slices; ++s) {
+    const srrg2b_slice& sl = slices[s];
+    if (sl.kind == SRRG2B_SLICE_PRIOR) {
+      if (c->dim == 3 && variable != SRRG2B_VAR_SE3_QUAT_RIGHT)
+        FAIL(c, SRRG2B_ERR_INVALID, "prior slices need the quaternion SE(3) variable (SE3PriorErrorFactorAD)");
+      continue;
+    }
+    if (sl.kind != SRRG2B_SLICE_POINTS) FAIL(c, SRRG2B_ERR_INVALID, "unknown slice kind");
+    if (!c->slices.count(sl.slice_id)) FAIL(c, SRRG2B_ERR_STATE, "slice has no clouds (no fixed / no moving)");
+    if (sl.factor.factor != SRRG2B_FACTOR_P2P && sl.factor.factor != SRRG2B_FACTOR_PLANE)
+      FAIL(c, SRRG2B_ERR_INVALID, "unknown factor kind");
+    if (sl.factor.robustifier < 0 || sl.factor.robustifier > SRRG2B_ROB_HUBER)
+      FAIL(c, SRRG2B_ERR_INVALID, "unknown robustifier");
+  }
+  return SRRG2B_OK;
+}
+
+struct Plan {
+  SolveArgs solve;
+  SliceArgs sargs[SRRG2B_MAX_SLICES];
+  int factor[SRRG2B_MAX_SLICES];
+  bool is_points[SRRG2B_MAX_SLICES];
+};
+
+int make_plan(srrg2b_ctx* c, int n_slices, const srrg2b_slice* slices, const srrg2b_aligner_params& ap, bool clamp,
+              bool want_status, Plan& plan) {
+  memset(&plan.solve, 0, sizeof(plan.solve));
+  plan.solve.dim = c->dim;
+  plan.solve.variable = ap.variable;
+  plan.solve.n_slices = n_slices;
+  plan.solve.use_tc = ap.use_termination_criteria;
+  plan.solve.window = ap.window_size;
+  plan.solve.range_corr = ap.num_correspondences_range;
+  plan.solve.range_inl = ap.num_inliers_range;
+  plan.solve.range_out = ap.num_outliers_range;
+  plan.solve.chi_eps = ap.chi_epsilon;
+  for (int s = 0; s < n_slices; ++s) {
+    const srrg2b_slice& sl = slices[s];
+    SolveSlice& ss = plan.solve.sl[s];
+    ss.kind = sl.kind;
+    ss.min_corr = sl.min_num_correspondences;
+    embed(c->dim, sl.robot_in_sensor, ss.ris);
+    plan.is_points[s] = sl.kind == SRRG2B_SLICE_POINTS;
+    if (sl.kind == SRRG2B_SLICE_PRIOR) {
+      embed(c->dim, sl.prior_measurement, ss.Z);
+      set_identity(ss.ris);
+      for (int k = 0; k < 6; ++k) ss.info[k] = sl.prior_info_diag[k];
+      continue;
+    }
+    set_identity(ss.Z);
+    srrg2b_factor_params fa = sl.factor;
+    if (clamp && fa.robustifier != SRRG2B_ROB_NONE) fa.robustifier = SRRG2B_ROB_CLAMP;  // multi_aligner_impl.cpp:193-199
+    Scales sc;
+    int rcode = fill_slice_args(c, c->slices[sl.slice_id], s, sl.finder, fa, ap.variable, want_status, plan.sargs[s], &sc);
+    if (rcode) return rcode;
+    plan.factor[s] = fa.factor;
+    ss.invH = ldexp(1.0, -sc.kH);
+    ss.invb = ldexp(1.0, -sc.kb);
+    ss.invchi = ldexp(1.0, -sc.kchi);
+  }
+  return SRRG2B_OK;
+}
+
+int allreduce_acc(srrg2b_ctx* c, int n_slices) {
+  if (c->world <= 1) return SRRG2B_OK;
+  if (g_nccl.AllReduce(c->d_state->acc, c->d_state->acc, (size_t) n_slices * kAcc, kNcclUint64, kNcclSum, c->comm,
+                       c->stream) != 0)
+    FAIL(c, SRRG2B_ERR_NCCL, "ncclAllReduce(sum) of H/b/stats failed");
+  return SRRG2B_OK;
+}
+
+// enqueue `iterations` _runSolver iterations (multi_aligner_impl.cpp:103-126); no host sync inside
+int enqueue_iterations(srrg2b_ctx* c, const Plan& plan, int iterations) {
+  for (int it = 0; it < iterations; ++it) {
+    for (int s = 0; s < plan.solve.n_slices; ++s) {
+      if (!plan.is_points[s]) continue;
+      if (c->time_kernels) {
+        while (c->kev.size() < c->kev_used + 2) {
+          cudaEvent_t e;
+          CK(c, cudaEventCreate(&e));
+          c->kev.push_back(e);
+        }
+        CK(c, cudaEventRecord(c->kev[c->kev_used], c->stream));
+      }
+      int rcode = launch_slice<MODE_FUSED>(c, plan.sargs[s], plan.factor[s]);
+      if (rcode) return rcode;
+      if (c->time_kernels) {
+        CK(c, cudaEventRecord(c->kev[c->kev_used + 1], c->stream));
+        c->kev_used += 2;
+      }
+    }
+    int rcode = allreduce_acc(c, plan.solve.n_slices);
+    if (rcode) return rcode;
+    icp_solve_kernel<<<1, 32, 0, c->stream>>>(plan.solve, c->d_state);
+    c->launches++;
+  }
+  CK(c, cudaGetLastError());
+  return SRRG2B_OK;
+}
+
+int fetch_state(srrg2b_ctx* c) {
+  CK(c, cudaMemcpyAsync(c->h_state, c->d_state, sizeof(DevState), cudaMemcpyDeviceToHost, c->stream));
+  CK(c, cudaStreamSynchronize(c->stream));
+  if (c->time_kernels) {
+    c->last_kernel_ms = 0.f;
+    c->last_kernel_launches = 0;
+    for (size_t i = 0; i + 1 < c->kev_used; i += 2) {
+      float ms = 0.f;
+      CK(c, cudaEventElapsedTime(&ms, c->kev[i], c->kev[i + 1]));
+      c->last_kernel_ms += ms;
+      c->last_kernel_launches++;
+    }
+    c->kev_used = 0;
+  }
+  return SRRG2B_OK;
+}
+
+int export_corr(srrg2b_ctx* c, SliceData& sd, int prune, bool want_stat, int32_t* fixed_idx, int32_t* moving_idx,
+                float* response, uint8_t* status, float* chi, int64_t* n_out) {
+  const int n = (int) sd.moving_raw.n;
+  *n_out = 0;
+  if (n == 0 || !sd.corr_valid) return SRRG2B_OK;
+  CK(c, c->flags.ensure(n));
+  CK(c, c->positions.ensure(n));
+  CK(c, c->d_fidx.ensure(n));
+  CK(c, c->d_resp.ensure(n));
+  CK(c, c->o_fidx.ensure(n));
+  CK(c, c->o_midx.ensure(n));
+  CK(c, c->o_resp.ensure(n));
+  if (want_stat) {
+    CK(c, c->d_stat.ensure(n));
+    CK(c, c->d_chi.ensure(n));
+    CK(c, c->o_stat.ensure(n));
+    CK(c, c->o_chi.ensure(n));
+  }
+  CK(c, cudaMemsetAsync(c->flags.p, 0, sizeof(int) * n, c->stream));
+  if (sd.nm_valid > 0) {
+    export_dense_kernel<<<blocks_for(sd.nm_valid, 256), 256, 0, c->stream>>>(
+      sd.m_pts.p, sd.c_fidx.p, sd.c_resp.p, sd.stat_valid ? sd.c_stat.p : nullptr, sd.stat_valid ? sd.c_chi.p : nullptr,
+      sd.nm_valid, prune, c->d_fidx.p, c->d_resp.p, want_stat ? c->d_stat.p : nullptr, want_stat ? c->d_chi.p : nullptr,
+      c->flags.p);
+    c->launches++;
+  }
+  size_t bytes = 0;
+  CK(c, cub::DeviceScan::ExclusiveSum(nullptr, bytes, c->flags.p, c->positions.p, n, c->stream));
+  CK(c, c->cub_tmp.ensure(bytes));
+  CK(c, cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, bytes, c->flags.p, c->positions.p, n, c->stream));
+  compact_kernel<<<blocks_for(n, 256), 256, 0, c->stream>>>(
+    c->flags.p, c->positions.p, n, (int) sd.moving_raw.index_offset, c->d_fidx.p, c->d_resp.p,
+    want_stat ? c->d_stat.p : nullptr, want_stat ? c->d_chi.p : nullptr, c->o_fidx.p, c->o_midx.p, c->o_resp.p,
+    want_stat ? c->o_stat.p : nullptr, want_stat ? c->o_chi.p : nullptr);
+  c->launches++;
+  int last_flag = 0, last_pos = 0;
+  CK(c, cudaMemcpyAsync(&last_flag, c->flags.p + (n - 1), 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(c, cudaMemcpyAsync(&last_pos, c->positions.p + (n - 1), 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(c, cudaStreamSynchronize(c->stream));
+  const int m = last_flag + last_pos;
+  if (m > 0) {
+    if (fixed_idx) CK(c, cudaMemcpyAsync(fixed_idx, c->o_fidx.p, 4 * (size_t) m, cudaMemcpyDeviceToHost, c->stream));
+    if (moving_idx) CK(c, cudaMemcpyAsync(moving_idx, c->o_midx.p, 4 * (size_t) m, cudaMemcpyDeviceToHost, c->stream));
+    if (response) CK(c, cudaMemcpyAsync(response, c->o_resp.p, 4 * (size_t) m, cudaMemcpyDeviceToHost, c->stream));
+    if (status && want_stat) CK(c, cudaMemcpyAsync(status, c->o_stat.p, (size_t) m, cudaMemcpyDeviceToHost, c->stream));
+    if (chi && want_stat) CK(c, cudaMemcpyAsync(chi, c->o_chi.p, 4 * (size_t) m, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+  }
+  *n_out = m;
+  return SRRG2B_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+// extern "C" boundary
+// =================================================================================================
+extern "C" {
+
+int srrg2b_version(void) { return SRRG2B_VERSION; }
+
+int srrg2b_ctx_create(int dim, int device, srrg2b_ctx** out) {
+  if (!out || (dim != 2 && dim != 3)) return SRRG2B_ERR_INVALID;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0 || device < 0 || device >= count) return SRRG2B_ERR_CUDA;
+  if (cudaSetDevice(device) != cudaSuccess) return SRRG2B_ERR_CUDA;
+  srrg2b_ctx* c = new srrg2b_ctx();
+  c->dim = dim;
+  c->device = device;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
+  bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
+  ok = ok && cudaEventCreate(&c->ev0) == cudaSuccess && cudaEventCreate(&c->ev1) == cudaSuccess;
+  ok = ok && cudaMalloc((void**) &c->d_state, sizeof(DevState)) == cudaSuccess;
+  ok = ok && cudaMallocHost((void**) &c->h_state, sizeof(DevState)) == cudaSuccess;
+  ok = ok && cudaMallocHost((void**) &c->h_bounds, 8 * sizeof(int)) == cudaSuccess;
+  ok = ok && cudaMemsetAsync(c->d_state, 0, sizeof(DevState), c->stream) == cudaSuccess;
+  ok = ok && cudaStreamSynchronize(c->stream) == cudaSuccess;
+  if (!ok) {
+    srrg2b_ctx_destroy(c);
+    return SRRG2B_ERR_CUDA;
+  }
+  *out = c;
+  return SRRG2B_OK;
+}
+
+int srrg2b_ctx_destroy(srrg2b_ctx* c) {
+  if (!c) return SRRG2B_OK;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+  for (auto& kv : c->slices) {
+    SliceData& s = kv.second;
+    s.fixed_raw.xyz.release(); s.fixed_raw.nrm.release(); s.fixed_raw.valid.release();
+    s.moving_raw.xyz.release(); s.moving_raw.nrm.release(); s.moving_raw.valid.release();
+    s.f_pts.release(); s.f_nrm.release(); s.f_inverse.release(); s.cell_start.release();
+    s.m_pts.release(); s.m_nrm.release(); s.m_inverse.release();
+    s.c_fidx.release(); s.c_fpos.release(); s.c_resp.release(); s.c_chi.release(); s.c_stat.release();
+  }
+  c->keys_a.release(); c->keys_b.release(); c->vals_a.release(); c->vals_b.release();
+  c->flags.release(); c->positions.release(); c->bounds.release(); c->cub_tmp.release();
+  c->o_fidx.release(); c->o_midx.release(); c->d_fidx.release(); c->o_resp.release(); c->d_resp.release();
+  c->o_chi.release(); c->d_chi.release(); c->o_stat.release(); c->d_stat.release();
+  c->imp_f.release(); c->imp_m.release(); c->imp_bad.release();
+  if (c->d_state) cudaFree(c->d_state);
+  if (c->h_state) cudaFreeHost(c->h_state);
+  if (c->h_bounds) cudaFreeHost(c->h_bounds);
+  for (cudaEvent_t e : c->kev) cudaEventDestroy(e);
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+  return SRRG2B_OK;
+}
+
+const char* srrg2b_last_error(const srrg2b_ctx* c) { return c ? c->err.c_str() : "null context"; }
+void* srrg2b_stream(srrg2b_ctx* c) { return c ? (void*) c->stream : nullptr; }
+int64_t srrg2b_launch_count(const srrg2b_ctx* c) { return c ? c->launches : 0; }
+
+int srrg2b_comm_unique_id(void* id) {
+  if (!id) return SRRG2B_ERR_INVALID;
+  if (!g_nccl.load()) return SRRG2B_ERR_NCCL;
+  NcclId nid;
+  if (g_nccl.GetUniqueId(&nid) != 0) return SRRG2B_ERR_NCCL;
+  memcpy(id, &nid, sizeof(nid));
+  return SRRG2B_OK;
+}
+
+int srrg2b_comm_init(srrg2b_ctx* c, const void* id, int rank, int world) {
+  if (!c || !id || world < 1 || rank < 0 || rank >= world) return SRRG2B_ERR_INVALID;
+  if (world == 1) {
+    c->rank = 0;
+    c->world = 1;
+    return SRRG2B_OK;
+  }
+  if (!g_nccl.load()) FAIL(c, SRRG2B_ERR_NCCL, "libnccl.so.2 not found");
+  CK(c, cudaSetDevice(c->device));
+  NcclId nid;
+  memcpy(&nid, id, sizeof(nid));
+  const int r = g_nccl.CommInitRank(&c->comm, world, nid, rank);
+  if (r != 0) FAIL(c, SRRG2B_ERR_NCCL, std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
+  c->rank = rank;
+  c->world = world;
+  return SRRG2B_OK;
+}
+
+int srrg2b_set_cloud(srrg2b_ctx* c, int slot, int slice_id, const srrg2b_cloud* cl) {
+  if (!c) return SRRG2B_ERR_INVALID;
+  if (!cl || cl->n < 0 || (cl->n > 0 && !cl->coords) || cl->n > 0x7fffffff00ll / 16)
+    FAIL(c, SRRG2B_ERR_INVALID, "bad cloud descriptor");
+  if (slot != SRRG2B_FIXED && slot != SRRG2B_MOVING) FAIL(c, SRRG2B_ERR_INVALID, "slot must be FIXED or MOVING");
+  CK(c, cudaSetDevice(c->device));
+  SliceData& sd = c->slices[slice_id];
+  if (slot == SRRG2B_FIXED) {
+    int rcode = upload_raw(c, sd.fixed_raw, cl);
+    if (rcode) return rcode;
+    sd.built_for_max_distance = -1.f;  // _fixed_changed_flag: rebuild the index on next use
+    sd.corr_valid = false;
+    CK(c, cudaStreamSynchronize(c->stream));
+    return SRRG2B_OK;
+  }
+  int rcode = upload_raw(c, sd.moving_raw, cl);
+  if (rcode) return rcode;
+  rcode = build_moving(c, sd);
+  if (rcode) return rcode;
+  CK(c, cudaStreamSynchronize(c->stream));
+  return SRRG2B_OK;
+}
+
+int srrg2b_find_correspondences(srrg2b_ctx* c, int slice_id, const float* S, const srrg2b_finder_params* fp,
+                                int32_t* fixed_idx, int32_t* moving_idx, float* response, int64_t* n_out) {
+  if (!c) return SRRG2B_ERR_INVALID;
+  if (!S || !fp || !n_out) FAIL(c, SRRG2B_ERR_INVALID, "null argument");
+  if (!c->slices.count(slice_id)) FAIL(c, SRRG2B_ERR_STATE, "unknown slice");
+  CK(c, cudaSetDevice(c->device));
+  SliceData& sd = c->slices[slice_id];
+  srrg2b_factor_params fa = {SRRG2B_FACTOR_P2P, SRRG2B_ROB_NONE, 1.f, 1.f, 1.f};
+  SliceArgs a;
+  int rcode = fill_slice_args(c, sd, 0, *fp, fa, SRRG2B_VAR_SE3_QUAT_RIGHT, false, a, nullptr);
+  if (rcode) return rcode;
+  Mat4f S4;
+  embed(c->dim, S, S4);
+  set_S_kernel<<<1, 32, 0, c->stream>>>(c->d_state, 0, S4);
+  c->launches++;
+  rcode = launch_slice<MODE_FIND>(c, a, SRRG2B_FACTOR_P2P);
+  if (rcode) return rcode;
+  CK(c, cudaGetLastError());
+  sd.corr_valid = true;
+  sd.stat_valid = false;
+  return export_corr(c, sd, 0, false, fixed_idx, moving_idx, response, nullptr, nullptr, n_out);
+}
+
+int srrg2b_set_correspondences(srrg2b_ctx* c, int slice_id, const int32_t* fixed_idx, const int32_t* moving_idx,
+                               int64_t n) {
+  if (!c) return SRRG2B_ERR_INVALID;
+  if (n < 0 || (n > 0 && (!fixed_idx || !moving_idx))) FAIL(c, SRRG2B_ERR_INVALID, "bad correspondence list");
+  if (!c->slices.count(slice_id)) FAIL(c, SRRG2B_ERR_STATE, "unknown slice");
+  CK(c, cudaSetDevice(c->device));
+  SliceData& sd = c->slices[slice_id];
+  if (!sd.moving_raw.present || !sd.fixed_raw.present) FAIL(c, SRRG2B_ERR_STATE, "slice needs both clouds");
+  if (sd.built_for_max_distance <= 0.f) {  // any cell size will do: only the sorted SoA is needed
+    int rcode = ensure_index(c, sd, 1.0f);
+    if (rcode) return rcode;
+  }
+  if (sd.nm_valid > 0) {
+    fill_int_kernel<<<blocks_for(sd.nm_valid, 256), 256, 0, c->stream>>>(sd.c_fidx.p, sd.nm_valid, -1);
+    fill_int_kernel<<<blocks_for(sd.nm_valid, 256), 256, 0, c->stream>>>(sd.c_fpos.p, sd.nm_valid, -1);
+    c->launches += 2;
+  }
+  if (n > 0) {
+    CK(c, c->imp_f.ensure(n));
+    CK(c, c->imp_m.ensure(n));
+    CK(c, c->imp_bad.ensure(1));
+    CK(c, cudaMemcpyAsync(c->imp_f.p, fixed_idx, 4 * (size_t) n, cudaMemcpyHostToDevice, c->stream));
+    CK(c, cudaMemcpyAsync(c->imp_m.p, moving_idx, 4 * (size_t) n, cudaMemcpyHostToDevice, c->stream));
+    CK(c, cudaMemsetAsync(c->imp_bad.p, 0, 4, c->stream));
+    import_corr_kernel<<<blocks_for(n, 256), 256, 0, c->stream>>>(
+      c->imp_f.p, c->imp_m.p, (int) n, sd.m_inverse.p, sd.f_inverse.p, (int) sd.moving_raw.n, (int) sd.fixed_raw.n,
+      (int) sd.moving_raw.index_offset, sd.c_fidx.p, sd.c_fpos.p, sd.c_resp.p, c->imp_bad.p);
+    c->launches++;
+  }
+  CK(c, cudaGetLastError());
+  CK(c, cudaStreamSynchronize(c->stream));
+  sd.corr_valid = true;
+  sd.stat_valid = false;
+  return SRRG2B_OK;
+}
+
+int srrg2b_linearize(srrg2b_ctx* c, int slice_id, const float* S, int variable, const srrg2b_finder_params* fp,
+                     const srrg2b_factor_params* fa, double* H, double* b, int64_t* acc, srrg2b_iter_stats* stats,
+                     uint8_t* status, float* chi) {
+  if (!c) return SRRG2B_ERR_INVALID;
+  if (!S || !fa || !fp) FAIL(c, SRRG2B_ERR_INVALID, "null argument");
+  if (!c->slices.count(slice_id)) FAIL(c, SRRG2B_ERR_STATE, "unknown slice");
+  CK(c, cudaSetDevice(c->device));
+  SliceData& sd = c->slices[slice_id];
+  if (!sd.corr_valid) FAIL(c, SRRG2B_ERR_STATE, "slice has no correspondences (call find / set_correspondences)");
+  SliceArgs a;
+  Scales sc;
+  srrg2b_finder_params fpl = *fp;
+  if (sd.built_for_max_distance > 0.f && fpl.kind == SRRG2B_FINDER_NN) {
+    // the index is only used for its sorted SoA here: do not rebuild it for a different gate
+    const float keep = sd.built_for_max_distance;
+    fpl.max_distance = keep;
+  }
+  int rcode = fill_slice_args(c, sd, 0, fpl, *fa, variable, true, a, nullptr);
+  if (rcode) return rcode;
+  sc = choose_scales(sd.moving_raw.n_global, sd.coord_bound, fp->max_distance, fa->info_point, fa->info_normal);
+  a.sH = ldexp(1.0, sc.kH); a.sb = ldexp(1.0, sc.kb); a.sc = ldexp(1.0, sc.kchi);
+  Mat4f S4;
+  embed(c->dim, S, S4);
+  set_S_kernel<<<1, 32, 0, c->stream>>>(c->d_state, 0, S4);
+  c->launches++;
+  rcode = launch_slice<MODE_LINEARIZE>(c, a, fa->factor);
+  if (rcode) return rcode;
+  CK(c, cudaGetLastError());
+  rcode = allreduce_acc(c, 1);
+  if (rcode) return rcode;
+  rcode = fetch_state(c);
+  if (rcode) return rcode;
+  sd.stat_valid = true;
+  const int P = c->dim == 3 ? 6 : 3;
+  const unsigned long long* A = c->h_state->acc[0];
+  if (acc) memcpy(acc, A, sizeof(int64_t) * kAcc);
+  if (H && b) {
+    int slot = 0;
+    for (int i = 0; i < P; ++i)
+      for (int j = i; j < P; ++j) {
+        const double v = ldexp((double) (long long) A[slot++], -sc.kH);
+        H[i * P + j] = v;
+        H[j * P + i] = v;
+      }
+    for (int i = 0; i < P; ++i) b[i] = ldexp((double) (long long) A[kAccB + i], -sc.kb);
+  }
+  if (stats) {
+    stats->iteration = 0;
+    stats->solver_status = 0;
+    stats->num_inliers = (int64_t) A[kAccNIn];
+    stats->num_outliers = (int64_t) A[kAccNOut];
+    stats->num_suppressed = (int64_t) A[kAccNSup];
+    stats->num_correspondences = stats->num_inliers + stats->num_outliers + stats->num_suppressed;
+    stats->chi_inliers = ldexp((double) (long long) A[kAccChiIn], -sc.kchi);
+    stats->chi_outliers = ldexp((double) (long long) A[kAccChiOut], -sc.kchi);
+  }
+  if (status || chi) {
+    int64_t m = 0;
+    return export_corr(c, sd, 0, true, nullptr, nullptr, nullptr, status, chi, &m);
+  }
+  return SRRG2B_OK;
+}
+
+int srrg2b_icp_run(srrg2b_ctx* c, int n_slices, const srrg2b_slice* slices, const srrg2b_aligner_params* ap,
+                   float* T, srrg2b_iter_stats* stats_out, int32_t* n_stats, int32_t* aligner_status) {
+  if (!c) return SRRG2B_ERR_INVALID;
+  if (!ap || !T || !aligner_status) FAIL(c, SRRG2B_ERR_INVALID, "null argument");
+  if (ap->max_iterations < 0) FAIL(c, SRRG2B_ERR_INVALID, "max_iterations < 0");
+  int rcode = validate_slices(c, n_slices, slices, ap->variable);
+  if (rcode) return rcode;
+  CK(c, cudaSetDevice(c->device));
+  const bool want_status = ap->keep_only_inlier_correspondences != 0;
+  Plan plan;
+  rcode = make_plan(c, n_slices, slices, *ap, false, want_status, plan);
+  if (rcode) return rcode;
+  Mat4f T0;
+  embed(c->dim, T, T0);
+  CK(c, cudaEventRecord(c->ev0, c->stream));
+  icp_init_kernel<<<1, 32, 0, c->stream>>>(plan.solve, c->d_state, T0, 1, 1, 0);
+  c->launches++;
+  rcode = enqueue_iterations(c, plan, ap->max_iterations);  // multi_aligner_impl.cpp:72
+  if (rcode) return rcode;
+  CK(c, cudaEventRecord(c->ev1, c->stream));
+  rcode = fetch_state(c);
+  if (rcode) return rcode;
+  float ms = 0.f;
+  CK(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+  c->last_ms = ms;
+  c->last_iterations = c->h_state->iterations_run;
+  int status = SRRG2B_ALIGNER_FAIL;
+  bool done = false;
+  const DevState* hs = c->h_state;
+  if (hs->n_stats == 0) {  // :75-78
+    status = SRRG2B_ALIGNER_FAIL;
+    done = true;
+  } else {
+    const int last = std::min(hs->n_stats, kMaxStats) - 1;
+    if (hs->stats[last].num_inliers < ap->min_num_inliers) {  // :81-85
+      status = SRRG2B_ALIGNER_NOT_ENOUGH_INLIERS;
+      done = true;
+    }
+  }
+  if (!done && ap->enable_inlier_only_runs) {  // _postCompute, :162-175
+    Plan plan2;
+    rcode = make_plan(c, n_slices, slices, *ap, true, want_status, plan2);
+    if (rcode) return rcode;
+    CK(c, cudaEventRecord(c->ev0, c->stream));
+    icp_init_kernel<<<1, 32, 0, c->stream>>>(plan2.solve, c->d_state, T0, 0, 0, 1);
+    c->launches++;
+    rcode = enqueue_iterations(c, plan2, ap->max_iterations);
+    if (rcode) return rcode;
+    CK(c, cudaEventRecord(c->ev1, c->stream));
+    rcode = fetch_state(c);
+    if (rcode) return rcode;
+    CK(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    c->last_ms += ms;
+    c->last_iterations = c->h_state->iterations_run;
+  }
+  Mat4f X = c->h_state->X;
+  if (!done) {
+    fix_transform(c->dim, X);  // :90-93
+    status = SRRG2B_ALIGNER_SUCCESS;
+  }
+  unembed(c->dim, X, T);
+  const int have = std::min(c->h_state->n_stats, kMaxStats);
+  if (stats_out && n_stats) {
+    const int cap = *n_stats;
+    for (int i = 0; i < have && i < cap; ++i) stats_out[i] = c->h_state->stats[i];
+  }
+  if (n_stats) *n_stats = c->h_state->n_stats;
+  *aligner_status = status;
+  for (int s = 0; s < n_slices; ++s) {
+    if (slices[s].kind != SRRG2B_SLICE_POINTS) continue;
+    SliceData& sd = c->slices[slices[s].slice_id];
+    sd.corr_valid = c->h_state->iterations_run > 0;
+    sd.stat_valid = want_status && sd.corr_valid;
+    sd.prune_on_export = (!done && want_status) ? 1 : 0;  // :177-180
+  }
+  return SRRG2B_OK;
+}
+
+int srrg2b_icp_iterate(srrg2b_ctx* c, int n_slices, const srrg2b_slice* slices, int variable, float* T,
+                       srrg2b_iter_stats* stats, int32_t* association_good) {
+  if (!c) return SRRG2B_ERR_INVALID;
+  if (!T) FAIL(c, SRRG2B_ERR_INVALID, "null argument");
+  int rcode = validate_slices(c, n_slices, slices, variable);
+  if (rcode) return rcode;
+  CK(c, cudaSetDevice(c->device));
+  srrg2b_aligner_params ap;
+  memset(&ap, 0, sizeof(ap));
+  ap.variable = variable;
+  ap.max_iterations = 1;
+  ap.window_size = 5;
+  Plan plan;
+  rcode = make_plan(c, n_slices, slices, ap, false, true, plan);
+  if (rcode) return rcode;
+  Mat4f T0;
+  embed(c->dim, T, T0);
+  icp_init_kernel<<<1, 32, 0, c->stream>>>(plan.solve, c->d_state, T0, 0, 1, 0);
+  c->launches++;
+  rcode = enqueue_iterations(c, plan, 1);
+  if (rcode) return rcode;
+  rcode = fetch_state(c);
+  if (rcode) return rcode;
+  unembed(c->dim, c->h_state->X, T);
+  if (association_good) *association_good = c->h_state->not_enough_corr ? 0 : 1;
+  if (stats) {
+    if (c->h_state->n_stats > 0) *stats = c->h_state->stats[0];
+    else memset(stats, 0, sizeof(*stats));
+  }
+  for (int s = 0; s < n_slices; ++s) {
+    if (slices[s].kind != SRRG2B_SLICE_POINTS) continue;
+    SliceData& sd = c->slices[slices[s].slice_id];
+    sd.corr_valid = true;
+    sd.stat_valid = true;
+    sd.prune_on_export = 0;
+  }
+  return SRRG2B_OK;
+}
+
+int srrg2b_get_correspondences(srrg2b_ctx* c, int slice_id, int32_t* fixed_idx, int32_t* moving_idx, float* response,
+                               int64_t* n_out) {
+  if (!c) return SRRG2B_ERR_INVALID;
+  if (!n_out) FAIL(c, SRRG2B_ERR_INVALID, "null argument");
+  if (!c->slices.count(slice_id)) FAIL(c, SRRG2B_ERR_STATE, "unknown slice");
+  CK(c, cudaSetDevice(c->device));
+  SliceData& sd = c->slices[slice_id];
+  return export_corr(c, sd, sd.prune_on_export, false, fixed_idx, moving_idx, response, nullptr, nullptr, n_out);
+}
+
+int srrg2b_last_run_timing(srrg2b_ctx* c, float* device_ms, int32_t* iterations) {
+  if (!c) return SRRG2B_ERR_INVALID;
+  if (device_ms) *device_ms = c->last_ms;
+  if (iterations) *iterations = c->last_iterations;
+  return SRRG2B_OK;
+}
+
+int srrg2b_set_kernel_timing(srrg2b_ctx* c, int enable) {
+  if (!c) return SRRG2B_ERR_INVALID;
+  c->time_kernels = enable != 0;
+  c->kev_used = 0;
+  return SRRG2B_OK;
+}
+
+int srrg2b_last_kernel_timing(srrg2b_ctx* c, float* slice_kernel_ms, int32_t* slice_kernel_launches) {
+  if (!c) return SRRG2B_ERR_INVALID;
+  if (slice_kernel_ms) *slice_kernel_ms = c->last_kernel_ms;
+  if (slice_kernel_launches) *slice_kernel_launches = c->last_kernel_launches;
+  return SRRG2B_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,727 @@
+// s2b_icp.cuh -- device code of the aligner hot path:
+//   k0  index build helpers (bounds, cell ids, Morton keys, gathers, cell table)
+//   k1  icp_slice_kernel: fused  transform -> exact grid NN -> gates -> error/Jacobian ->
+//       robust weight -> exact fixed-point accumulation of H, b, chi, counters
+//   k1s icp_solve_kernel: slice-ordered assembly, prior factors, 6x6/3x3 LL^T, X <- X [+] dx,
+//       IterationStats append, termination criterion, next-iteration finder transforms
+//   k2b export kernels (sorted order -> ascending moving_idx, optional inlier pruning)
+// Everything is fp32 per term with an explicit operation order (fmaf spelled out, TU compiled with
+// -fmad=false); sums are 64-bit integers, so results do not depend on grid shape or GPU count.
+#pragma once
+#include "s2b_math.cuh"
+#include "../../include/srrg2b.h"
+
+namespace s2b {
+
+constexpr int kAcc = 32;  // accumulator slots per slice
+constexpr int kAccB = 21, kAccChiIn = 27, kAccChiOut = 28, kAccNIn = 29, kAccNOut = 30, kAccNSup = 31;
+constexpr int kMaxStats = 256;
+constexpr int kMaxWindow = 64;
+
+struct Ring {
+  int window, count, head;
+  double v[kMaxWindow];
+};
+
+struct DevState {
+  Mat4f X;                                   // variable 0 estimate (moving in fixed)
+  Mat4f S[SRRG2B_MAX_SLICES];                // robot_in_sensor * X per slice (finder transform)
+  unsigned long long acc[SRRG2B_MAX_SLICES][kAcc];
+  long long ncorr[SRRG2B_MAX_SLICES];
+  int stop;                                  // set on termination / bad association
+  int n_stats;
+  int not_enough_corr;
+  int iterations_run;
+  srrg2b_iter_stats stats[kMaxStats];
+  Ring r_ncorr, r_ninl, r_nout, r_chi;
+  int tc_iterations;
+};
+
+struct SolveSlice {
+  int kind, min_corr;
+  Mat4f ris, Z;
+  float info[6];
+  double invH, invb, invchi;  // 2^-k of the slice's fixed-point scales
+};
+
+struct SolveArgs {
+  int dim, variable, n_slices;
+  int use_tc, window, range_corr, range_inl, range_out;
+  float chi_eps;
+  SolveSlice sl[SRRG2B_MAX_SLICES];
+};
+
+struct SliceArgs {
+  const float4* __restrict__ mp;   // moving points, Morton order: x y z | local index bits
+  const float4* __restrict__ mn;   // moving normals
+  int nm;
+  const float4* __restrict__ fp;   // fixed points, cell order: x y z | original index bits
+  const float4* __restrict__ fn;
+  const int* __restrict__ cell_start;
+  float ox, oy, oz, inv_cell;
+  int nx, ny, nz;
+  float md2, normal_cos;
+  int gate;
+  int rob;
+  float tau, ip, in_, rs;
+  double sH, sb, sc;
+  const float* S;
+  int* c_fidx;
+  int* c_fpos;
+  float* c_resp;
+  unsigned char* c_stat;  // may be null
+  float* c_chi;           // may be null
+  unsigned long long* acc;
+  const int* stop;
+};
+
+// ---------------------------------------------------------------------------------------------
+// ordered-int encoding so float min/max can use integer atomics
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int f2ord(float f) {
+  const int i = __float_as_int(f);
+  return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__host__ __device__ __forceinline__ float ord2f(int i) {
+  const int j = i >= 0 ? i : i ^ 0x7fffffff;
+#ifdef __CUDA_ARCH__
+  return __int_as_float(j);
+#else
+  float f;
+  memcpy(&f, &j, 4);
+  return f;
+#endif
+}
+
+// out[0..2] = min, out[3..5] = max (ordered ints), out[6] = max |coord| (float bits, >= 0),
+// out[7] = number of valid points
+__global__ void bounds_kernel(const float* __restrict__ xyz, const unsigned char* __restrict__ valid, int n,
+                              int dim, int* __restrict__ out) {
+  int mn[3] = {INT_MAX, INT_MAX, INT_MAX}, mx[3] = {INT_MIN, INT_MIN, INT_MIN};
+  int amax = 0, cnt = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if (valid && !valid[i]) continue;
+    ++cnt;
+    for (int a = 0; a < dim; ++a) {
+      const float v = xyz[(size_t) i * dim + a];
+      const int o = f2ord(v);
+      mn[a] = min(mn[a], o);
+      mx[a] = max(mx[a], o);
+      amax = max(amax, __float_as_int(fabsf(v)));
+    }
+  }
+  for (int off = 16; off; off >>= 1) {
+    for (int a = 0; a < 3; ++a) {
+      mn[a] = min(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], off));
+      mx[a] = max(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], off));
+    }
+    amax = max(amax, __shfl_xor_sync(0xffffffffu, amax, off));
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    for (int a = 0; a < 3; ++a) {
+      atomicMin(&out[a], mn[a]);
+      atomicMax(&out[3 + a], mx[a]);
+    }
+    atomicMax(&out[6], amax);
+    atomicAdd(&out[7], cnt);
+  }
+}
+
+__device__ __forceinline__ int cell_coord(float v, float o, float inv, int n) {
+  float c = (v - o) * inv;
+  c = fminf(fmaxf(c, -2.f), (float) n + 1.f);
+  return (int) floorf(c);
+}
+
+// fixed cloud: key = linear cell id (x fastest), invalid points -> 0xffffffff
+__global__ void cell_key_kernel(const float* __restrict__ xyz, const unsigned char* __restrict__ valid, int n,
+                                int dim, float ox, float oy, float oz, float inv, int nx, int ny, int nz,
+                                unsigned* __restrict__ keys, int* __restrict__ vals) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  vals[i] = i;
+  if (valid && !valid[i]) {
+    keys[i] = 0xffffffffu;
+    return;
+  }
+  const float x = xyz[(size_t) i * dim], y = xyz[(size_t) i * dim + 1];
+  const float z = dim == 3 ? xyz[(size_t) i * dim + 2] : 0.f;
+  int cx = min(max(cell_coord(x, ox, inv, nx), 0), nx - 1);
+  int cy = min(max(cell_coord(y, oy, inv, ny), 0), ny - 1);
+  int cz = min(max(cell_coord(z, oz, inv, nz), 0), nz - 1);
+  keys[i] = (unsigned) ((cz * ny + cy) * nx + cx);
+}
+
+__device__ __forceinline__ unsigned spread3(unsigned v) {  // 10 bits -> every third bit
+  v &= 0x3ffu;
+  v = (v | (v << 16)) & 0x030000ffu;
+  v = (v | (v << 8)) & 0x0300f00fu;
+  v = (v | (v << 4)) & 0x030c30c3u;
+  v = (v | (v << 2)) & 0x09249249u;
+  return v;
+}
+__device__ __forceinline__ unsigned spread2(unsigned v) {  // 15 bits -> every second bit
+  v &= 0x7fffu;
+  v = (v | (v << 8)) & 0x00ff00ffu;
+  v = (v | (v << 4)) & 0x0f0f0f0fu;
+  v = (v | (v << 2)) & 0x33333333u;
+  v = (v | (v << 1)) & 0x55555555u;
+  return v;
+}
+
+// moving cloud: Morton key over its own bounding box (pose independent, so the spatial coherence
+// of a warp's queries survives every rigid transform the aligner applies)
+__global__ void morton_key_kernel(const float* __restrict__ xyz, const unsigned char* __restrict__ valid, int n,
+                                  int dim, float ox, float oy, float oz, float sx, float sy, float sz,
+                                  unsigned* __restrict__ keys, int* __restrict__ vals) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  vals[i] = i;
+  if (valid && !valid[i]) {
+    keys[i] = 0xffffffffu;
+    return;
+  }
+  const float x = xyz[(size_t) i * dim], y = xyz[(size_t) i * dim + 1];
+  if (dim == 3) {
+    const float z = xyz[(size_t) i * dim + 2];
+    const unsigned qx = (unsigned) fminf(fmaxf((x - ox) * sx, 0.f), 1023.f);
+    const unsigned qy = (unsigned) fminf(fmaxf((y - oy) * sy, 0.f), 1023.f);
+    const unsigned qz = (unsigned) fminf(fmaxf((z - oz) * sz, 0.f), 1023.f);
+    keys[i] = spread3(qx) | (spread3(qy) << 1) | (spread3(qz) << 2);
+  } else {
+    const unsigned qx = (unsigned) fminf(fmaxf((x - ox) * sx, 0.f), 32767.f);
+    const unsigned qy = (unsigned) fminf(fmaxf((y - oy) * sy, 0.f), 32767.f);
+    keys[i] = spread2(qx) | (spread2(qy) << 1);
+  }
+}
+
+// sorted float4 SoA: points carry the original index in .w
+__global__ void gather_kernel(const float* __restrict__ xyz, const float* __restrict__ nrm,
+                              const int* __restrict__ order, int n_valid, int dim, float4* __restrict__ op,
+                              float4* __restrict__ on, int* __restrict__ inverse) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_valid) return;
+  const int src = order[i];
+  float4 p;
+  p.x = xyz[(size_t) src * dim];
+  p.y = xyz[(size_t) src * dim + 1];
+  p.z = dim == 3 ? xyz[(size_t) src * dim + 2] : 0.f;
+  p.w = __int_as_float(src);
+  op[i] = p;
+  float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (nrm) {
+    q.x = nrm[(size_t) src * dim];
+    q.y = nrm[(size_t) src * dim + 1];
+    q.z = dim == 3 ? nrm[(size_t) src * dim + 2] : 0.f;
+  }
+  on[i] = q;
+  if (inverse) inverse[src] = i;
+}
+
+// cell_start[c] = first sorted position whose key >= c (lower bound), c in [0, ncells]
+__global__ void cell_start_kernel(const unsigned* __restrict__ keys, int n_valid, int ncells,
+                                  int* __restrict__ cell_start) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c > ncells) return;
+  int lo = 0, hi = n_valid;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (keys[mid] < (unsigned) c) lo = mid + 1; else hi = mid;
+  }
+  cell_start[c] = lo;
+}
+
+__global__ void fill_int_kernel(int* p, int n, int v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// k1: fused ICP iteration over one slice
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ long long to_fixed(float v, double scale) {
+  return __double2ll_rn((double) v * scale);
+}
+
+// robustifier on chi (threshold tau): weight, robustified chi, kernelized flag
+__device__ __forceinline__ bool robustify(int kind, float tau, float chi, float& w, float& rho) {
+  w = 1.f;
+  rho = chi;
+  if (kind == SRRG2B_ROB_NONE || !(chi > tau)) return false;
+  if (kind == SRRG2B_ROB_HUBER) {
+    const float delta = __fsqrt_rn(tau);
+    const float sc = __fsqrt_rn(chi);
+    w = __fdiv_rn(delta, sc);
+    rho = fmaf(2.f * delta, sc, -tau);
+  } else if (kind == SRRG2B_ROB_CAUCHY) {
+    const float r = __fdiv_rn(chi, tau);
+    w = __fdiv_rn(1.f, 1.f + r);
+    rho = (float) ((double) tau * log_det(1.0 + (double) r));
+  } else {  // Saturated / Clamp
+    w = 0.f;
+    rho = tau;
+  }
+  return true;
+}
+
+enum { MODE_FUSED = 0, MODE_FIND = 1, MODE_LINEARIZE = 2 };
+
+template <int DIM, int FACTOR, int MODE>
+__global__ void __launch_bounds__(256) icp_slice_kernel(const SliceArgs a) {
+  if (*a.stop) return;
+  constexpr int P = (DIM == 3) ? 6 : 3;
+  constexpr int NH = P * (P + 1) / 2;
+  __shared__ float Ss[16];
+  __shared__ unsigned long long sacc[kAcc];
+  if (threadIdx.x < 16) Ss[threadIdx.x] = a.S[threadIdx.x];
+  if (threadIdx.x < kAcc) sacc[threadIdx.x] = 0ull;
+  __syncthreads();
+  const float s00 = Ss[0], s01 = Ss[1], s02 = Ss[2], s03 = Ss[3];
+  const float s10 = Ss[4], s11 = Ss[5], s12 = Ss[6], s13 = Ss[7];
+  const float s20 = Ss[8], s21 = Ss[9], s22 = Ss[10], s23 = Ss[11];
+
+  long long aH[NH], ab[P];
+  long long achi_in = 0, achi_out = 0;
+  int n_in = 0, n_out = 0, n_sup = 0;
+#pragma unroll
+  for (int k = 0; k < NH; ++k) aH[k] = 0;
+#pragma unroll
+  for (int k = 0; k < P; ++k) ab[k] = 0;
+
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.nm; i += gridDim.x * blockDim.x) {
+    const float4 m = a.mp[i];
+    const float4 nm = a.mn[i];
+    // q = S m, nq = R_S n_m  (operation order is part of the numerics contract)
+    float t;
+    t = s00 * m.x; t = fmaf(s01, m.y, t); if (DIM == 3) t = fmaf(s02, m.z, t); const float qx = t + s03;
+    t = s10 * m.x; t = fmaf(s11, m.y, t); if (DIM == 3) t = fmaf(s12, m.z, t); const float qy = t + s13;
+    float qz = 0.f;
+    if (DIM == 3) { t = s20 * m.x; t = fmaf(s21, m.y, t); t = fmaf(s22, m.z, t); qz = t + s23; }
+    t = s00 * nm.x; t = fmaf(s01, nm.y, t); if (DIM == 3) t = fmaf(s02, nm.z, t); const float nqx = t;
+    t = s10 * nm.x; t = fmaf(s11, nm.y, t); if (DIM == 3) t = fmaf(s12, nm.z, t); const float nqy = t;
+    float nqz = 0.f;
+    if (DIM == 3) { t = s20 * nm.x; t = fmaf(s21, nm.y, t); t = fmaf(s22, nm.z, t); nqz = t; }
+
+    int bpos = -1;
+    float4 f, nf;
+    if (MODE != MODE_LINEARIZE) {
+      // ---- exact NN inside max_distance over the 3^DIM neighbourhood of q's cell ----
+      float bd2 = a.md2;
+      int bidx = INT_MAX;
+      const int cx = cell_coord(qx, a.ox, a.inv_cell, a.nx);
+      const int cy = cell_coord(qy, a.oy, a.inv_cell, a.ny);
+      const int cz = (DIM == 3) ? cell_coord(qz, a.oz, a.inv_cell, a.nz) : 0;
+      const int x0 = max(cx - 1, 0), x1 = min(cx + 1, a.nx - 1);
+      if (x0 <= x1) {
+        const int z0 = (DIM == 3) ? cz - 1 : 0, z1 = (DIM == 3) ? cz + 1 : 0;
+        for (int z = z0; z <= z1; ++z) {
+          if (z < 0 || z >= a.nz) continue;
+          for (int y = cy - 1; y <= cy + 1; ++y) {
+            if (y < 0 || y >= a.ny) continue;
+            const int row = (z * a.ny + y) * a.nx;
+            const int ps = __ldg(a.cell_start + row + x0);
+            const int pe = __ldg(a.cell_start + row + x1 + 1);
+            for (int p = ps; p < pe; ++p) {
+              const float4 c = __ldg(a.fp + p);
+              const float dx = qx - c.x, dy = qy - c.y, dz = qz - c.z;
+              float d2 = fmaf(dy, dy, dx * dx);
+              if (DIM == 3) d2 = fmaf(dz, dz, d2);
+              const int id = __float_as_int(c.w);
+              if (d2 < bd2 || (d2 == bd2 && id < bidx)) {
+                bd2 = d2; bidx = id; bpos = p;
+              }
+            }
+          }
+        }
+      }
+      int out_idx = -1;
+      float out_resp = 0.f;
+      if (bpos >= 0) {
+        f = __ldg(a.fp + bpos);
+        nf = __ldg(a.fn + bpos);
+        bool ok = true;
+        if (a.gate) {
+          float dot = fmaf(nf.y, nqy, nf.x * nqx);
+          if (DIM == 3) dot = fmaf(nf.z, nqz, dot);
+          ok = !(dot < a.normal_cos);
+        }
+        if (ok) { out_idx = bidx; out_resp = __fsqrt_rn(bd2); } else { bpos = -1; }
+      }
+      a.c_fidx[i] = out_idx;
+      a.c_fpos[i] = bpos;
+      a.c_resp[i] = out_resp;
+    } else {
+      bpos = a.c_fpos[i];
+      if (bpos >= 0) {
+        f = __ldg(a.fp + bpos);
+        nf = __ldg(a.fn + bpos);
+      } else if (bpos == -2) {  // externally supplied correspondence that cannot be evaluated
+        ++n_sup;
+        if (a.c_stat) a.c_stat[i] = SRRG2B_STAT_SUPPRESSED;
+        continue;
+      }
+    }
+    if (MODE == MODE_FIND) continue;
+    if (bpos < 0) {
+      if (a.c_stat) a.c_stat[i] = SRRG2B_STAT_NONE;
+      continue;
+    }
+
+    // ---- error rows e, information om, Jacobian rows J (right perturbation of X) ----
+    constexpr int E = (FACTOR == SRRG2B_FACTOR_P2P) ? DIM : DIM + 1;
+    float e[E], om[E], J[E][P];
+    const float dx = qx - f.x, dy = qy - f.y, dz = qz - f.z;
+    const float rs = a.rs;
+    if (DIM == 3) {
+      const float R[3][3] = {{s00, s01, s02}, {s10, s11, s12}, {s20, s21, s22}};
+      if (FACTOR == SRRG2B_FACTOR_P2P) {
+        const float d[3] = {dx, dy, dz};
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          J[r][0] = R[r][0]; J[r][1] = R[r][1]; J[r][2] = R[r][2];
+          t = R[r][2] * m.y; J[r][3] = -rs * fmaf(R[r][1], m.z, -t);
+          t = R[r][0] * m.z; J[r][4] = -rs * fmaf(R[r][2], m.x, -t);
+          t = R[r][1] * m.x; J[r][5] = -rs * fmaf(R[r][0], m.y, -t);
+          e[r] = d[r]; om[r] = a.ip;
+        }
+      } else {
+        float av[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          t = R[0][c] * nf.x; t = fmaf(R[1][c], nf.y, t); t = fmaf(R[2][c], nf.z, t);
+          av[c] = t;
+        }
+        J[0][0] = av[0]; J[0][1] = av[1]; J[0][2] = av[2];
+        t = m.z * av[1]; J[0][3] = rs * fmaf(m.y, av[2], -t);
+        t = m.x * av[2]; J[0][4] = rs * fmaf(m.z, av[0], -t);
+        t = m.y * av[0]; J[0][5] = rs * fmaf(m.x, av[1], -t);
+        e[0] = fmaf(nf.z, dz, fmaf(nf.y, dy, nf.x * dx)); om[0] = a.ip;
+        const float nqv[3] = {nqx, nqy, nqz}, nfv[3] = {nf.x, nf.y, nf.z};
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          J[r + 1][0] = 0.f; J[r + 1][1] = 0.f; J[r + 1][2] = 0.f;
+          t = R[r][2] * nm.y; J[r + 1][3] = -rs * fmaf(R[r][1], nm.z, -t);
+          t = R[r][0] * nm.z; J[r + 1][4] = -rs * fmaf(R[r][2], nm.x, -t);
+          t = R[r][1] * nm.x; J[r + 1][5] = -rs * fmaf(R[r][0], nm.y, -t);
+          e[r + 1] = nqv[r] - nfv[r]; om[r + 1] = a.in_;
+        }
+      }
+    } else {
+      const float R[2][2] = {{s00, s01}, {s10, s11}};
+      if (FACTOR == SRRG2B_FACTOR_P2P) {
+        const float d[2] = {dx, dy};
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          J[r][0] = R[r][0]; J[r][1] = R[r][1];
+          t = R[r][0] * m.y; J[r][2] = fmaf(R[r][1], m.x, -t);
+          e[r] = d[r]; om[r] = a.ip;
+        }
+      } else {
+        float av[2];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) av[c] = fmaf(R[1][c], nf.y, R[0][c] * nf.x);
+        t = av[0] * m.y;
+        J[0][0] = av[0]; J[0][1] = av[1]; J[0][2] = fmaf(av[1], m.x, -t);
+        e[0] = fmaf(nf.y, dy, nf.x * dx); om[0] = a.ip;
+        const float nqv[2] = {nqx, nqy}, nfv[2] = {nf.x, nf.y};
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          J[r + 1][0] = 0.f; J[r + 1][1] = 0.f;
+          t = R[r][0] * nm.y; J[r + 1][2] = fmaf(R[r][1], nm.x, -t);
+          e[r + 1] = nqv[r] - nfv[r]; om[r + 1] = a.in_;
+        }
+      }
+    }
+    float chi = (om[0] * e[0]) * e[0];
+#pragma unroll
+    for (int r = 1; r < E; ++r) chi = fmaf(om[r] * e[r], e[r], chi);
+    if (a.c_chi) a.c_chi[i] = chi;
+    if (!(chi == chi) || isinf(chi)) {
+      ++n_sup;
+      if (a.c_stat) a.c_stat[i] = SRRG2B_STAT_SUPPRESSED;
+      continue;
+    }
+    float w, rho;
+    const bool kern = robustify(a.rob, a.tau, chi, w, rho);
+    if (kern) { ++n_out; achi_out += to_fixed(rho, a.sc); } else { ++n_in; achi_in += to_fixed(chi, a.sc); }
+    if (a.c_stat) a.c_stat[i] = kern ? SRRG2B_STAT_KERNELIZED : SRRG2B_STAT_INLIER;
+    // ---- H += J^T (w Om) J, b += J^T (w Om) e; structural zeros of the normal rows skipped ----
+    constexpr int TR = (FACTOR == SRRG2B_FACTOR_P2P) ? 0 : DIM;  // columns < TR are zero in rows >= 1
+    float u[E][P];
+#pragma unroll
+    for (int r = 0; r < E; ++r) {
+      const float s = w * om[r];
+#pragma unroll
+      for (int c = 0; c < P; ++c) u[r][c] = s * J[r][c];
+    }
+    int slot = 0;
+#pragma unroll
+    for (int ii = 0; ii < P; ++ii) {
+#pragma unroll
+      for (int jj = ii; jj < P; ++jj) {
+        float h = u[0][ii] * J[0][jj];
+        if (ii >= TR && jj >= TR) {
+#pragma unroll
+          for (int r = 1; r < E; ++r) h = fmaf(u[r][ii], J[r][jj], h);
+        }
+        aH[slot++] += to_fixed(h, a.sH);
+      }
+    }
+#pragma unroll
+    for (int ii = 0; ii < P; ++ii) {
+      float g = u[0][ii] * e[0];
+      if (ii >= TR) {
+#pragma unroll
+        for (int r = 1; r < E; ++r) g = fmaf(u[r][ii], e[r], g);
+      }
+      ab[ii] += to_fixed(g, a.sb);
+    }
+  }
+
+  if (MODE == MODE_FIND) return;
+  // ---- exact integer block reduction: warp shuffles -> shared atomics -> one global atomic per slot
+  auto wsum = [](long long v) {
+#pragma unroll
+    for (int off = 16; off; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+  };
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 0; k < NH; ++k) {
+    const long long v = wsum(aH[k]);
+    if (lane == 0 && v) atomicAdd(&sacc[k], (unsigned long long) v);
+  }
+#pragma unroll
+  for (int k = 0; k < P; ++k) {
+    const long long v = wsum(ab[k]);
+    if (lane == 0 && v) atomicAdd(&sacc[kAccB + k], (unsigned long long) v);
+  }
+  {
+    long long v = wsum(achi_in);
+    if (lane == 0 && v) atomicAdd(&sacc[kAccChiIn], (unsigned long long) v);
+    v = wsum(achi_out);
+    if (lane == 0 && v) atomicAdd(&sacc[kAccChiOut], (unsigned long long) v);
+    const int ni = __reduce_add_sync(0xffffffffu, n_in);
+    const int no = __reduce_add_sync(0xffffffffu, n_out);
+    const int ns = __reduce_add_sync(0xffffffffu, n_sup);
+    if (lane == 0) {
+      if (ni) atomicAdd(&sacc[kAccNIn], (unsigned long long) ni);
+      if (no) atomicAdd(&sacc[kAccNOut], (unsigned long long) no);
+      if (ns) atomicAdd(&sacc[kAccNSup], (unsigned long long) ns);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < kAcc) {
+    const unsigned long long v = sacc[threadIdx.x];
+    if (v) atomicAdd(&a.acc[threadIdx.x], v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k1s: per-iteration solve / update / statistics / termination (one thread; O(#slices) work)
+// ---------------------------------------------------------------------------------------------
+__device__ inline void ring_reset(Ring& r, int w) {
+  r.window = w > kMaxWindow ? kMaxWindow : (w < 1 ? 1 : w);
+  r.count = 0;
+  r.head = 0;
+}
+__device__ inline void ring_add(Ring& r, double x) {
+  r.v[r.head] = x;
+  r.head = (r.head + 1) % r.window;
+  if (r.count < r.window) r.count++;
+}
+__device__ inline double ring_max(const Ring& r) {
+  double m = r.v[0];
+  for (int i = 1; i < r.count; ++i) m = r.v[i] > m ? r.v[i] : m;
+  return m;
+}
+__device__ inline double ring_min(const Ring& r) {
+  double m = r.v[0];
+  for (int i = 1; i < r.count; ++i) m = r.v[i] < m ? r.v[i] : m;
+  return m;
+}
+
+// AlignerTerminationCriteriaStandard_::hasToStop,
+// R/registration/aligners/aligner_termination_criteria_impl.cpp:24-65 (quirks at :32-33,:46,:53 kept)
+__device__ inline bool has_to_stop(DevState* st, const SolveArgs& a, const srrg2b_iter_stats& s, long long ncorr) {
+  ++st->tc_iterations;
+  const int ninl = (int) s.num_inliers, nout = (int) s.num_outliers;
+  const float chi = __fdiv_rn((float) s.chi_inliers, (float) ninl);
+  if (!ninl) return false;
+  ring_add(st->r_ncorr, (double) ncorr);
+  ring_add(st->r_ninl, (double) ninl);
+  ring_add(st->r_nout, (double) nout);
+  ring_add(st->r_chi, (double) chi);
+  if (st->r_ncorr.count < a.window) return false;
+  if (ring_max(st->r_nout) - ring_min(st->r_nout) > (double) a.range_corr) return false;
+  if (ring_max(st->r_ninl) - ring_min(st->r_ninl) > (double) a.range_inl) return false;
+  const float crange = (float) ring_max(st->r_chi) - (float) ring_min(st->r_chi);
+  const float cmax = (float) ring_max(st->r_chi);
+  if (crange > (float) a.range_out) return false;
+  if (__fdiv_rn(crange, cmax) > a.chi_eps) return false;
+  return true;
+}
+
+// compute() prologue: variable <- guess, prior slices overwrite it in slice order
+// (multi_aligner_impl.cpp:130-141), finder transforms, counters
+__global__ void icp_init_kernel(const SolveArgs a, DevState* st, Mat4f T0, int apply_prior_guess, int reset_tc,
+                                int keep_stats) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (!keep_stats) {
+    Mat4f X = T0;
+    if (apply_prior_guess) {
+      for (int s = 0; s < a.n_slices; ++s)
+        if (a.sl[s].kind == SRRG2B_SLICE_PRIOR) X = a.sl[s].Z;
+    }
+    st->X = X;
+    st->n_stats = 0;
+    st->iterations_run = 0;
+  }
+  for (int s = 0; s < a.n_slices; ++s) {
+    compose(a.sl[s].ris, st->X, st->S[s]);
+    for (int k = 0; k < kAcc; ++k) st->acc[s][k] = 0ull;
+    st->ncorr[s] = 0;
+  }
+  st->stop = 0;
+  st->not_enough_corr = 0;
+  if (reset_tc) {
+    ring_reset(st->r_ncorr, a.window);
+    ring_reset(st->r_ninl, a.window);
+    ring_reset(st->r_nout, a.window);
+    ring_reset(st->r_chi, a.window);
+    st->tc_iterations = 0;
+  }
+}
+
+// set only the finder transform of one slice (stand-alone find / linearise entry points)
+__global__ void set_S_kernel(DevState* st, int slice, Mat4f S) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    st->S[slice] = S;
+    for (int k = 0; k < kAcc; ++k) st->acc[slice][k] = 0ull;
+    st->stop = 0;
+  }
+}
+
+// body of one _runSolver iteration after the per-slice kernels
+// (R/registration/aligners/multi_aligner_impl.cpp:106-126)
+__global__ void icp_solve_kernel(const SolveArgs a, DevState* st) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (st->stop) return;
+  const int P = (a.dim == 3) ? 6 : 3;
+  double H[36], b[6];
+  for (int i = 0; i < 36; ++i) H[i] = 0.0;
+  for (int i = 0; i < 6; ++i) b[i] = 0.0;
+  srrg2b_iter_stats s;
+  s.iteration = st->n_stats;
+  s.solver_status = 0;
+  s.num_inliers = 0; s.num_outliers = 0; s.num_suppressed = 0; s.num_correspondences = 0;
+  s.chi_inliers = 0.0; s.chi_outliers = 0.0;
+  bool good = false;
+  long long total = 0;
+  for (int k = 0; k < a.n_slices; ++k) {
+    const SolveSlice& sl = a.sl[k];
+    if (sl.kind == SRRG2B_SLICE_PRIOR) {
+      double chi = 0.0;
+      prior_accumulate(a.dim, a.variable, sl.Z, st->X, sl.info, H, b, chi);
+      s.num_inliers += 1; s.num_correspondences += 1; s.chi_inliers += chi;
+      good = true;  // aligner_slice_processor_prior.h:65-67
+      total += 1;   // :75-77
+      st->ncorr[k] = 1;
+      continue;
+    }
+    const unsigned long long* acc = st->acc[k];
+    double Hs[36], bs[6];
+    int slot = 0;
+    for (int i = 0; i < P; ++i) {
+      for (int j = i; j < P; ++j) {
+        const double v = __ll2double_rn((long long) acc[slot++]) * sl.invH;
+        Hs[i * P + j] = v;
+        Hs[j * P + i] = v;
+      }
+    }
+    for (int i = 0; i < P; ++i) bs[i] = __ll2double_rn((long long) acc[kAccB + i]) * sl.invb;
+    for (int i = 0; i < P * P; ++i) H[i] = H[i] + Hs[i];
+    for (int i = 0; i < P; ++i) b[i] = b[i] + bs[i];
+    const long long ni = (long long) acc[kAccNIn], no = (long long) acc[kAccNOut], ns = (long long) acc[kAccNSup];
+    s.num_inliers += ni; s.num_outliers += no; s.num_suppressed += ns; s.num_correspondences += ni + no + ns;
+    s.chi_inliers += __ll2double_rn((long long) acc[kAccChiIn]) * sl.invchi;
+    s.chi_outliers += __ll2double_rn((long long) acc[kAccChiOut]) * sl.invchi;
+    const long long n = ni + no + ns;
+    st->ncorr[k] = n;
+    total += n;
+    good = good || (n > (long long) sl.min_corr);  // aligner_slice_processor_impl.cpp:77-79
+    for (int q = 0; q < kAcc; ++q) st->acc[k][q] = 0ull;
+  }
+  st->iterations_run += 1;
+  if (!good) {  // multi_aligner_impl.cpp:107-111 (estimate already equals the backup)
+    st->not_enough_corr = 1;
+    st->stop = 1;
+    return;
+  }
+  double dx[6];
+  Mat4f X = st->X;
+  if (spd_solve(P, H, b, dx)) {
+    box_plus(a.dim, a.variable, dx, X);
+    st->X = X;
+    s.solver_status = 1;
+  }
+  if (st->n_stats < kMaxStats) st->stats[st->n_stats] = s;
+  st->n_stats += 1;
+  for (int k = 0; k < a.n_slices; ++k) compose(a.sl[k].ris, st->X, st->S[k]);
+  if (a.use_tc && has_to_stop(st, a, s, total)) st->stop = 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// k2b: export (sorted order -> dense by local moving index), then compaction
+// ---------------------------------------------------------------------------------------------
+__global__ void export_dense_kernel(const float4* __restrict__ mp, const int* __restrict__ c_fidx,
+                                    const float* __restrict__ c_resp, const unsigned char* __restrict__ c_stat,
+                                    const float* __restrict__ c_chi, int nm, int prune, int* __restrict__ d_fidx,
+                                    float* __restrict__ d_resp, unsigned char* __restrict__ d_stat,
+                                    float* __restrict__ d_chi, int* __restrict__ d_flag) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nm) return;
+  const int src = __float_as_int(mp[i].w);
+  const int fi = c_fidx[i];
+  const bool keep = fi >= 0 && (!prune || (c_stat && c_stat[i] == SRRG2B_STAT_INLIER));
+  d_flag[src] = keep ? 1 : 0;
+  d_fidx[src] = fi;
+  d_resp[src] = c_resp[i];
+  if (d_stat) d_stat[src] = c_stat ? c_stat[i] : (unsigned char) SRRG2B_STAT_NONE;
+  if (d_chi) d_chi[src] = c_chi ? c_chi[i] : 0.f;
+}
+
+__global__ void compact_kernel(const int* __restrict__ flag, const int* __restrict__ pos, int n, int index_offset,
+                               const int* __restrict__ d_fidx, const float* __restrict__ d_resp,
+                               const unsigned char* __restrict__ d_stat, const float* __restrict__ d_chi,
+                               int* __restrict__ o_fidx, int* __restrict__ o_midx, float* __restrict__ o_resp,
+                               unsigned char* __restrict__ o_stat, float* __restrict__ o_chi) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || !flag[i]) return;
+  const int k = pos[i];
+  o_fidx[k] = d_fidx[i];
+  o_midx[k] = i + index_offset;
+  o_resp[k] = d_resp[i];
+  if (o_stat) o_stat[k] = d_stat[i];
+  if (o_chi) o_chi[k] = d_chi[i];
+}
+
+// external correspondences (HBST path): list -> sorted-order slots; -2 marks "cannot evaluate"
+__global__ void import_corr_kernel(const int* __restrict__ fixed_idx, const int* __restrict__ moving_idx, int n,
+                                   const int* __restrict__ m_inverse, const int* __restrict__ f_inverse, int nm_raw,
+                                   int nf_raw, int index_offset, int* __restrict__ c_fidx, int* __restrict__ c_fpos,
+                                   float* __restrict__ c_resp, int* __restrict__ n_bad) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int mi = moving_idx[k] - index_offset, fi = fixed_idx[k];
+  if (mi < 0 || mi >= nm_raw) return;  // not in this shard
+  const int mpos = m_inverse[mi];
+  if (mpos < 0) { atomicAdd(n_bad, 1); return; }
+  const int fpos = (fi >= 0 && fi < nf_raw) ? f_inverse[fi] : -1;
+  c_fidx[mpos] = fi;
+  c_fpos[mpos] = fpos >= 0 ? fpos : -2;
+  c_resp[mpos] = 0.f;
+}
+
+}  // namespace s2b

@@ -1,0 +1,150 @@
+"""GPU parity: CUDA path through the C ABI vs the CPU oracle on the same seeded inputs.
+Bars (BASELINE.json north_star): correspondence indices bit-exact; H/b/chi exact (integer sums);
+pose / chi^2 far inside 1e-5 rad / 1e-4 m / 1e-6 relative (they are in fact bit-identical)."""
+import numpy as np
+import pytest
+
+from srrg2_slam_interfaces_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+
+def _dense_from_compact(n, fi, mi, rs):
+    d = np.full(n, -1, dtype=np.int32)
+    r = np.zeros(n, dtype=np.float32)
+    d[mi] = fi
+    r[mi] = rs
+    return d, r
+
+
+def _setup3d(oracle, capi, nf, nm, seed=2, valid_frac=None):
+    d = syn.make_icp3d(nf, nm, seed=seed)
+    fv = mv = None
+    if valid_frac is not None:
+        rng = np.random.default_rng(seed + 100)
+        fv = (rng.uniform(size=nf) < valid_frac).astype(np.uint8)
+        mv = (rng.uniform(size=nm) < valid_frac).astype(np.uint8)
+    F = oracle.CloudRef(d["fixed"], d["fixed_normals"], fv)
+    M = oracle.CloudRef(d["moving"], d["moving_normals"], mv)
+    ctx = capi.Context(3)
+    ctx.set_cloud(capi.FIXED, 0, d["fixed"], d["fixed_normals"], fv)
+    ctx.set_cloud(capi.MOVING, 0, d["moving"], d["moving_normals"], mv)
+    return d, F, M, ctx
+
+
+@pytest.mark.parametrize("nf,nm,valid", [(5000, 4000, None), (20000, 30000, 0.9), (1, 10, None), (300, 1, None)])
+def test_find_bit_exact_3d(oracle, capi, nf, nm, valid):
+    d, F, M, ctx = _setup3d(oracle, capi, nf, nm, valid_frac=valid)
+    ix = oracle.Index(F, oracle.NN_KDTREE)
+    for S in (np.eye(4), syn.iso3([0.3, -0.2, 0.1], [0.02, -0.03, 0.05]), d["T_star"]):
+        for md, nc in ((0.3, 0.8), (1.5, -2.0), (0.05, 0.95)):
+            ofi, ors = oracle.find(ix, F, M, S, oracle.finder_params(md, nc))
+            fi, mi, rs = ctx.find_correspondences(0, S, capi.finder_params(md, nc), nm)
+            assert np.all(np.diff(mi) > 0)
+            gfi, grs = _dense_from_compact(nm, fi, mi, rs)
+            assert np.array_equal(gfi, ofi)
+            assert np.array_equal(grs, ors)
+    ctx.close()
+
+
+@pytest.mark.parametrize("factor", ["P2P", "PLANE"])
+@pytest.mark.parametrize("rob", ["NONE", "HUBER", "CAUCHY", "CLAMP", "SATURATED"])
+@pytest.mark.parametrize("variable", [0, 1])
+def test_linearize_exact_3d(oracle, capi, factor, rob, variable):
+    nf, nm = 20000, 20000
+    d, F, M, ctx = _setup3d(oracle, capi, nf, nm, valid_frac=0.95)
+    S = syn.iso3([0.02, -0.01, 0.03], [0.004, -0.003, 0.005])
+    ofp = oracle.finder_params(0.3, 0.8)
+    gfp = capi.finder_params(0.3, 0.8)
+    ofa = oracle.factor_params(getattr(oracle, "FACTOR_" + factor), getattr(oracle, "ROB_" + rob), 0.01, 2.0, 0.5)
+    gfa = capi.factor_params(getattr(capi, "FACTOR_" + factor), getattr(capi, "ROB_" + rob), 0.01, 2.0, 0.5)
+    ix = oracle.Index(F, oracle.NN_KDTREE)
+    ofi, _ = oracle.find(ix, F, M, S, ofp)
+    o = oracle.linearize(F, M, ofi, S, ofp, ofa, variable=variable)
+    ctx.find_correspondences(0, S, gfp, nm)
+    g = ctx.linearize(0, S, gfp, gfa, variable=variable, n_moving=nm)
+    assert np.array_equal(g["acc"], o["acc"])
+    assert np.array_equal(g["H"], o["H"]) and np.array_equal(g["b"], o["b"])
+    assert g["stats"]["num_inliers"] == o["stats"]["num_inliers"]
+    assert g["stats"]["num_outliers"] == o["stats"]["num_outliers"]
+    assert g["stats"]["chi_inliers"] == o["stats"]["chi_inliers"]
+    assert g["stats"]["chi_outliers"] == o["stats"]["chi_outliers"]
+    sel = ofi >= 0
+    assert np.array_equal(g["status"], o["status"][sel])
+    assert np.array_equal(g["chi"], o["chi"][sel])
+    ctx.close()
+
+
+def _run_both(oracle, capi, dim, d, oap, gap, ofp, gfp, ofa, gfa, T0):
+    F = oracle.CloudRef(d["fixed"], d["fixed_normals"])
+    M = oracle.CloudRef(d["moving"], d["moving_normals"])
+    o = oracle.icp_run(dim, [oracle.make_slice(F, M, None, ofp, ofa, dim=dim)], oap, T0)
+    ctx = capi.Context(dim)
+    ctx.set_cloud(capi.FIXED, 0, d["fixed"], d["fixed_normals"])
+    ctx.set_cloud(capi.MOVING, 0, d["moving"], d["moving_normals"])
+    g = ctx.icp_run([capi.make_slice(dim, 0, None, gfp, gfa)], gap, T0)
+    corr = ctx.get_correspondences(0, d["moving"].shape[0])
+    ctx.close()
+    return o, g, corr
+
+
+def _assert_same_run(o, g, corr):
+    assert g["status"] == o["status"]
+    assert len(g["stats"]) == len(o["stats"])
+    for a, b in zip(g["stats"], o["stats"]):
+        assert a == b
+    assert np.array_equal(g["T"], o["T"])
+    ofi, omi, ors = o["correspondences"][0]
+    assert np.array_equal(corr[0], ofi) and np.array_equal(corr[1], omi) and np.array_equal(corr[2], ors)
+
+
+def test_icp_run_c2_small(oracle, capi):
+    """Config C2 at 1/20 scale: 20 iterations, Huber, point+normal factor."""
+    d = syn.make_icp3d(50000, 50000, seed=2)
+    kw = dict(max_iterations=20, min_num_inliers=10)
+    o, g, corr = _run_both(oracle, capi, 3, d, oracle.aligner_params(**kw), capi.aligner_params(**kw),
+                           oracle.finder_params(0.3, 0.8), capi.finder_params(0.3, 0.8),
+                           oracle.factor_params(oracle.FACTOR_PLANE, oracle.ROB_HUBER, 0.01),
+                           capi.factor_params(capi.FACTOR_PLANE, capi.ROB_HUBER, 0.01), np.eye(4))
+    _assert_same_run(o, g, corr)
+    assert g["status"] == capi.ALIGNER_SUCCESS and len(g["stats"]) == 20
+    rot, trans = syn.pose_error(g["T"], d["T_star"])
+    assert rot < 2e-3 and trans < 2e-2
+
+
+def test_icp_run_c1_2d(oracle, capi):
+    """Config C1: 2D SE(2), 10k vs 10k, 1 iteration, no robustifier (plumbing config)."""
+    d = syn.make_icp2d(10000, seed=1)
+    for iters in (1, 10):
+        kw = dict(max_iterations=iters, min_num_inliers=10)
+        o, g, corr = _run_both(oracle, capi, 2, d, oracle.aligner_params(**kw), capi.aligner_params(**kw),
+                               oracle.finder_params(0.5, 0.8), capi.finder_params(0.5, 0.8),
+                               oracle.factor_params(oracle.FACTOR_PLANE, oracle.ROB_NONE),
+                               capi.factor_params(capi.FACTOR_PLANE, capi.ROB_NONE), np.eye(3))
+        _assert_same_run(o, g, corr)
+    rot, trans = syn.pose_error(g["T"], d["T_star"])
+    assert rot < 1e-3 and trans < 5e-3
+
+
+def test_icp_run_termination_and_inlier_runs(oracle, capi):
+    d = syn.make_icp3d(30000, 30000, seed=7)
+    kw = dict(max_iterations=30, min_num_inliers=10, use_termination_criteria=True, enable_inlier_only_runs=True,
+              keep_only_inlier_correspondences=True, num_correspondences_range=200, num_inliers_range=200,
+              num_outliers_range=200)
+    o, g, corr = _run_both(oracle, capi, 3, d, oracle.aligner_params(**kw), capi.aligner_params(**kw),
+                           oracle.finder_params(0.3, 0.8), capi.finder_params(0.3, 0.8),
+                           oracle.factor_params(oracle.FACTOR_P2P, oracle.ROB_CAUCHY, 0.01),
+                           capi.factor_params(capi.FACTOR_P2P, capi.ROB_CAUCHY, 0.01), np.eye(4))
+    _assert_same_run(o, g, corr)
+
+
+def test_not_enough_correspondences(oracle, capi):
+    d = syn.make_icp3d(2000, 2000, seed=3)
+    far = syn.iso3([500.0, 0, 0], [0, 0, 0])
+    kw = dict(max_iterations=5, min_num_inliers=10)
+    o, g, corr = _run_both(oracle, capi, 3, d, oracle.aligner_params(**kw), capi.aligner_params(**kw),
+                           oracle.finder_params(0.3, 0.8), capi.finder_params(0.3, 0.8),
+                           oracle.factor_params(), capi.factor_params(), far)
+    assert g["status"] == capi.ALIGNER_FAIL == o["status"]
+    assert len(g["stats"]) == 0
+    assert np.array_equal(g["T"], o["T"])
