@@ -160,6 +160,9 @@ int srrg2b_get_correspondences(srrg2b_ctx* ctx, int slice_id, int32_t* fixed_idx
 int srrg2b_last_run_timing(srrg2b_ctx* ctx, float* device_ms, int32_t* iterations);
 /* when enabled, every launch of the fused per-slice ICP kernel is bracketed by CUDA events on the
  * context stream; the sum and count for the last run are returned (roofline measurement) */
+/* diagnostics of a slice's NN index: out16 = {R, nx, ny, nz, n_fixed_valid, n_moving_valid,
+ * size of the last phase-2 worklist, cell edge (float bits), 0...} */
+int srrg2b_debug_info(srrg2b_ctx* ctx, int slice_id, int32_t* out16);
 int srrg2b_set_kernel_timing(srrg2b_ctx* ctx, int enable);
 int srrg2b_last_kernel_timing(srrg2b_ctx* ctx, float* slice_kernel_ms, int32_t* slice_kernel_launches);
 

@@ -24,7 +24,7 @@ EXPORTED_SYMBOLS = [
     "srrg2b_launch_count", "srrg2b_comm_unique_id", "srrg2b_comm_init", "srrg2b_set_cloud",
     "srrg2b_find_correspondences", "srrg2b_set_correspondences", "srrg2b_linearize", "srrg2b_icp_run",
     "srrg2b_icp_iterate", "srrg2b_get_correspondences", "srrg2b_last_run_timing",
-    "srrg2b_set_kernel_timing", "srrg2b_last_kernel_timing",
+    "srrg2b_set_kernel_timing", "srrg2b_last_kernel_timing", "srrg2b_debug_info",
 ]
 
 
@@ -108,6 +108,7 @@ def load_library():
     lib.srrg2b_icp_iterate.argtypes = [vp, C.c_int, C.POINTER(Slice), C.c_int, vp, C.POINTER(IterStats), i32p]
     lib.srrg2b_get_correspondences.argtypes = [vp, C.c_int, vp, vp, vp, i64p]
     lib.srrg2b_last_run_timing.argtypes = [vp, C.POINTER(C.c_float), i32p]
+    lib.srrg2b_debug_info.argtypes = [vp, C.c_int, vp]
     lib.srrg2b_set_kernel_timing.argtypes = [vp, C.c_int]
     lib.srrg2b_last_kernel_timing.argtypes = [vp, C.POINTER(C.c_float), i32p]
     _lib = lib
@@ -288,6 +289,13 @@ class Context:
         self._check(self.lib.srrg2b_get_correspondences(self.h, slice_id, fi.ctypes.data, mi.ctypes.data,
                                                         rs.ctypes.data, C.byref(n)))
         return fi[:n.value], mi[:n.value], rs[:n.value]
+
+    def debug_info(self, slice_id):
+        out = np.zeros(16, dtype=np.int32)
+        self._check(self.lib.srrg2b_debug_info(self.h, slice_id, out.ctypes.data))
+        return dict(R=int(out[0]), dims=(int(out[1]), int(out[2]), int(out[3])), n_fixed_valid=int(out[4]),
+                    n_moving_valid=int(out[5]), last_far_count=int(out[6]),
+                    cell=float(out[7:8].view(np.float32)[0]))
 
     def set_kernel_timing(self, enable):
         self._check(self.lib.srrg2b_set_kernel_timing(self.h, int(enable)))

@@ -83,6 +83,7 @@ struct SliceData {
   float built_for_max_distance = -1.f;
   float ox = 0, oy = 0, oz = 0, inv_cell = 1;
   int nx = 1, ny = 1, nz = 1;
+  int R = 1;  // cells per max_distance
   // moving, Morton order
   DevBuf<float4> m_pts, m_nrm;
   DevBuf<int> m_inverse;
@@ -90,7 +91,7 @@ struct SliceData {
   float coord_bound = 0.f;
   bool coord_bound_global = false;
   // correspondences in moving-sorted order
-  DevBuf<int> c_fidx, c_fpos;
+  DevBuf<int> c_fidx, c_fpos, far_list, far_count;
   DevBuf<float> c_resp, c_chi;
   DevBuf<unsigned char> c_stat;
   bool corr_valid = false, stat_valid = false;
@@ -211,6 +212,8 @@ int build_moving(srrg2b_ctx* c, SliceData& sd) {
   CK(c, sd.m_inverse.ensure((size_t) n));
   CK(c, sd.c_fidx.ensure((size_t) n));
   CK(c, sd.c_fpos.ensure((size_t) n));
+  CK(c, sd.far_list.ensure((size_t) n));
+  CK(c, sd.far_count.ensure(1));
   CK(c, sd.c_resp.ensure((size_t) n));
   CK(c, sd.c_chi.ensure((size_t) n));
   CK(c, sd.c_stat.ensure((size_t) n));
@@ -271,40 +274,75 @@ int ensure_index(srrg2b_ctx* c, SliceData& sd, float max_distance) {
       mx[a] = ord2f(c->h_bounds[3 + a]);
     }
   }
-  // 0.1% slack on the cell edge absorbs the fp32 rounding of the cell coordinate
-  float cell = max_distance * 1.001f;
-  int dims[3] = {1, 1, 1};
-  for (;;) {
-    double total = 1.0;
-    bool ok = true;
-    for (int a = 0; a < dim; ++a) {
-      const double cnt = floor((double) (mx[a] - mn[a]) / (double) cell) + 1.0;
-      if (cnt > 1024.0) ok = false;
-      dims[a] = (int) (cnt > 1024.0 ? 1024 : cnt);
-      total *= cnt;
-    }
-    if (ok && total <= 16.0 * 1024 * 1024) break;
-    cell *= 2.f;
-  }
-  sd.ox = mn[0]; sd.oy = mn[1]; sd.oz = mn[2];
-  sd.inv_cell = 1.f / cell;
-  sd.nx = dims[0]; sd.ny = dims[1]; sd.nz = dims[2];
-  const int ncells = sd.nx * sd.ny * sd.nz;
   CK(c, sd.f_pts.ensure((size_t) n + 1));
   CK(c, sd.f_nrm.ensure((size_t) n + 1));
   CK(c, sd.f_inverse.ensure((size_t) n + 1));
-  CK(c, sd.cell_start.ensure((size_t) ncells + 1));
   if (n > 0) {
     CK(c, c->keys_a.ensure(n));
     CK(c, c->keys_b.ensure(n));
     CK(c, c->vals_a.ensure(n));
     CK(c, c->vals_b.ensure(n));
-    cell_key_kernel<<<blocks_for(n, 256), 256, 0, c->stream>>>(rc.xyz.p, rc.has_valid ? rc.valid.p : nullptr, n, dim,
-                                                               sd.ox, sd.oy, sd.oz, sd.inv_cell, sd.nx, sd.ny, sd.nz,
-                                                               c->keys_a.p, c->vals_a.p);
+  }
+  // Cell edge = 1.001 * max_distance / R: the 0.1% slack absorbs the fp32 rounding of the cell
+  // coordinate, and the (2R+1)^dim neighbourhood of a query's cell holds every point within
+  // max_distance.  R is the finest of 4..1 that fits the table budget and keeps about two or more
+  // points per occupied cell (finer cells = fewer candidates examined per query).
+  int R = kMaxR;
+  if (const char* env = getenv("SRRG2B_GRID_R")) R = std::max(1, std::min(kMaxR, atoi(env)));
+  const bool forced = getenv("SRRG2B_GRID_R") != nullptr;
+  int dims[3] = {1, 1, 1};
+  float cell = max_distance;
+  for (;; --R) {
+    cell = max_distance * 1.001f / (float) R;
+    double total = 1.0;
+    bool fits = true;
+    for (int a = 0; a < dim; ++a) {
+      const double cnt = floor((double) (mx[a] - mn[a]) / (double) cell) + 1.0;
+      if (cnt > 1024.0) fits = false;
+      dims[a] = (int) (cnt > 1024.0 ? 1024 : cnt);
+      total *= cnt;
+    }
+    if (!fits || total > 8.0 * 1024 * 1024) {
+      if (R > 1) continue;
+      // even R = 1 does not fit: grow the cell (the search then covers more than it needs to)
+      while (true) {
+        cell *= 2.f;
+        total = 1.0;
+        fits = true;
+        for (int a = 0; a < dim; ++a) {
+          const double cnt = floor((double) (mx[a] - mn[a]) / (double) cell) + 1.0;
+          if (cnt > 1024.0) fits = false;
+          dims[a] = (int) (cnt > 1024.0 ? 1024 : cnt);
+          total *= cnt;
+        }
+        if (fits && total <= 8.0 * 1024 * 1024) break;
+      }
+    }
+    sd.ox = mn[0]; sd.oy = mn[1]; sd.oz = mn[2];
+    sd.inv_cell = 1.f / cell;
+    sd.nx = dims[0]; sd.ny = dims[1]; sd.nz = dims[2];
+    sd.R = R;
+    if (n > 0) {
+      cell_key_kernel<<<blocks_for(n, 256), 256, 0, c->stream>>>(rc.xyz.p, rc.has_valid ? rc.valid.p : nullptr, n,
+                                                                 dim, sd.ox, sd.oy, sd.oz, sd.inv_cell, sd.nx, sd.ny,
+                                                                 sd.nz, c->keys_a.p, c->vals_a.p);
+      c->launches++;
+      rcode = cub_sort_pairs(c, n, 32);
+      if (rcode) return rcode;
+    }
+    if (R == 1 || forced || sd.nf_valid == 0) break;
+    CK(c, cudaMemsetAsync(c->bounds.p, 0, 4, c->stream));
+    count_distinct_kernel<<<std::min(blocks_for(sd.nf_valid, 256), c->sm_count * 8), 256, 0, c->stream>>>(
+      c->keys_b.p, sd.nf_valid, c->bounds.p);
     c->launches++;
-    rcode = cub_sort_pairs(c, n, 32);
-    if (rcode) return rcode;
+    CK(c, cudaMemcpyAsync(c->h_bounds, c->bounds.p, 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    const double occupancy = (double) sd.nf_valid / (double) std::max(1, c->h_bounds[0]);
+    if (occupancy >= 2.0) break;
+  }
+  const int ncells = sd.nx * sd.ny * sd.nz;
+  CK(c, sd.cell_start.ensure((size_t) ncells + 1));
+  if (n > 0) {
     fill_int_kernel<<<blocks_for(n, 256), 256, 0, c->stream>>>(sd.f_inverse.p, n, -1);
     c->launches++;
     if (sd.nf_valid > 0) {
@@ -317,6 +355,13 @@ int ensure_index(srrg2b_ctx* c, SliceData& sd, float max_distance) {
   cell_start_kernel<<<blocks_for(ncells + 1, 256), 256, 0, c->stream>>>(c->keys_b.p, sd.nf_valid, ncells,
                                                                         sd.cell_start.p);
   c->launches++;
+  // positions into the old ordering are meaningless now: drop the warm-start candidates
+  if (sd.moving_raw.present && sd.nm_valid > 0) {
+    fill_int_kernel<<<blocks_for(sd.nm_valid, 256), 256, 0, c->stream>>>(sd.c_fpos.p, sd.nm_valid, -1);
+    fill_int_kernel<<<blocks_for(sd.nm_valid, 256), 256, 0, c->stream>>>(sd.c_fidx.p, sd.nm_valid, -1);
+    c->launches += 2;
+    sd.corr_valid = false;
+  }
   CK(c, cudaGetLastError());
   sd.built_for_max_distance = max_distance;
   return SRRG2B_OK;
@@ -351,6 +396,8 @@ int fill_slice_args(srrg2b_ctx* c, SliceData& sd, int state_slot, const srrg2b_f
   a.fp = sd.f_pts.p; a.fn = sd.f_nrm.p; a.cell_start = sd.cell_start.p;
   a.ox = sd.ox; a.oy = sd.oy; a.oz = sd.oz; a.inv_cell = sd.inv_cell;
   a.nx = sd.nx; a.ny = sd.ny; a.nz = sd.nz;
+  a.R = sd.R;
+  a.warm = 1;
   a.md2 = fp.max_distance * fp.max_distance;
   a.normal_cos = fp.normal_cos;
   a.gate = (normals && fp.normal_cos > -1.f) ? 1 : 0;
@@ -358,7 +405,8 @@ int fill_slice_args(srrg2b_ctx* c, SliceData& sd, int state_slot, const srrg2b_f
   a.rs = (c->dim == 3 && variable == SRRG2B_VAR_SE3_QUAT_RIGHT) ? 2.f : 1.f;
   a.sH = ldexp(1.0, sc.kH); a.sb = ldexp(1.0, sc.kb); a.sc = ldexp(1.0, sc.kchi);
   a.S = c->d_state->S[state_slot].m;
-  a.c_fidx = sd.c_fidx.p; a.c_fpos = sd.c_fpos.p; a.c_resp = sd.c_resp.p;
+  a.c_fpos = sd.c_fpos.p; a.c_resp = sd.c_resp.p;
+  a.far_list = sd.far_list.p; a.far_count = sd.far_count.p;
   a.c_stat = want_status ? sd.c_stat.p : nullptr;
   a.c_chi = want_status ? sd.c_chi.p : nullptr;
   a.acc = c->d_state->acc[state_slot];
@@ -366,19 +414,58 @@ int fill_slice_args(srrg2b_ctx* c, SliceData& sd, int state_slot, const srrg2b_f
   return SRRG2B_OK;
 }
 
-template <int MODE>
-int launch_slice(srrg2b_ctx* c, const SliceArgs& a, int factor) {
+int launch_find(srrg2b_ctx* c, const SliceArgs& a) {
   if (a.nm <= 0) return SRRG2B_OK;
   const int threads = 256;
-  const int blocks = std::max(1, std::min(blocks_for(a.nm, threads), c->sm_count * 4));
+  const int blocks = std::max(1, std::min(blocks_for(a.nm, threads), c->sm_count * 8));
+  CK(c, cudaMemsetAsync(a.far_count, 0, sizeof(int), c->stream));
+  if (c->dim == 3) nn_kernel<3><<<blocks, threads, 0, c->stream>>>(a);
+  else nn_kernel<2><<<blocks, threads, 0, c->stream>>>(a);
+  c->launches++;
+  if (a.R >= 2) {
+    const int fblocks = std::max(1, std::min(blocks_for((int64_t) a.nm * 32, threads), c->sm_count * 8));
+    if (c->dim == 3) nn_far_kernel<3><<<fblocks, threads, 0, c->stream>>>(a);
+    else nn_far_kernel<2><<<fblocks, threads, 0, c->stream>>>(a);
+    c->launches++;
+  }
+  return SRRG2B_OK;
+}
+
+int launch_linearize(srrg2b_ctx* c, const SliceArgs& a, int factor) {
+  if (a.nm <= 0) return SRRG2B_OK;
+  const int threads = 256;
+  const int blocks = std::max(1, std::min(blocks_for(a.nm, threads), c->sm_count * 2));
   if (c->dim == 3) {
-    if (factor == SRRG2B_FACTOR_P2P) icp_slice_kernel<3, SRRG2B_FACTOR_P2P, MODE><<<blocks, threads, 0, c->stream>>>(a);
-    else icp_slice_kernel<3, SRRG2B_FACTOR_PLANE, MODE><<<blocks, threads, 0, c->stream>>>(a);
+    if (factor == SRRG2B_FACTOR_P2P) linearize_kernel<3, SRRG2B_FACTOR_P2P><<<blocks, threads, 0, c->stream>>>(a);
+    else linearize_kernel<3, SRRG2B_FACTOR_PLANE><<<blocks, threads, 0, c->stream>>>(a);
   } else {
-    if (factor == SRRG2B_FACTOR_P2P) icp_slice_kernel<2, SRRG2B_FACTOR_P2P, MODE><<<blocks, threads, 0, c->stream>>>(a);
-    else icp_slice_kernel<2, SRRG2B_FACTOR_PLANE, MODE><<<blocks, threads, 0, c->stream>>>(a);
+    if (factor == SRRG2B_FACTOR_P2P) linearize_kernel<2, SRRG2B_FACTOR_P2P><<<blocks, threads, 0, c->stream>>>(a);
+    else linearize_kernel<2, SRRG2B_FACTOR_PLANE><<<blocks, threads, 0, c->stream>>>(a);
   }
   c->launches++;
+  return SRRG2B_OK;
+}
+
+// ring-ordered (dy, dz) row offsets of the NN search neighbourhood -> __constant__ tables
+int upload_row_tables() {
+  signed char t3[kRowTable][4];
+  int n = 0;
+  for (int ring = 0; ring <= kMaxR; ++ring)
+    for (int dz = -ring; dz <= ring; ++dz)
+      for (int dy = -ring; dy <= ring; ++dy) {
+        if (std::max(std::abs(dy), std::abs(dz)) != ring) continue;
+        t3[n][0] = (signed char) dy; t3[n][1] = (signed char) dz; t3[n][2] = (signed char) ring; t3[n][3] = 0;
+        ++n;
+      }
+  signed char t2[2 * kMaxR + 1][4];
+  n = 0;
+  for (int ring = 0; ring <= kMaxR; ++ring)
+    for (int dy = -ring; dy <= ring; dy += (ring ? 2 * ring : 1)) {
+      t2[n][0] = (signed char) dy; t2[n][1] = 0; t2[n][2] = (signed char) ring; t2[n][3] = 0;
+      ++n;
+    }
+  if (cudaMemcpyToSymbol(c_rows3, t3, sizeof(t3)) != cudaSuccess) return SRRG2B_ERR_CUDA;
+  if (cudaMemcpyToSymbol(c_rows2, t2, sizeof(t2)) != cudaSuccess) return SRRG2B_ERR_CUDA;
   return SRRG2B_OK;
 }
 
@@ -469,7 +556,9 @@ int enqueue_iterations(srrg2b_ctx* c, const Plan& plan, int iterations) {
         }
         CK(c, cudaEventRecord(c->kev[c->kev_used], c->stream));
       }
-      int rcode = launch_slice<MODE_FUSED>(c, plan.sargs[s], plan.factor[s]);
+      int rcode = launch_find(c, plan.sargs[s]);
+      if (rcode) return rcode;
+      rcode = launch_linearize(c, plan.sargs[s], plan.factor[s]);
       if (rcode) return rcode;
       if (c->time_kernels) {
         CK(c, cudaEventRecord(c->kev[c->kev_used + 1], c->stream));
@@ -478,7 +567,8 @@ int enqueue_iterations(srrg2b_ctx* c, const Plan& plan, int iterations) {
     }
     int rcode = allreduce_acc(c, plan.solve.n_slices);
     if (rcode) return rcode;
-    icp_solve_kernel<<<1, 32, 0, c->stream>>>(plan.solve, c->d_state);
+    if (c->dim == 3) icp_solve_kernel<3><<<1, 32, 0, c->stream>>>(plan.solve, c->d_state);
+    else icp_solve_kernel<2><<<1, 32, 0, c->stream>>>(plan.solve, c->d_state);
     c->launches++;
   }
   CK(c, cudaGetLastError());
@@ -523,7 +613,7 @@ int export_corr(srrg2b_ctx* c, SliceData& sd, int prune, bool want_stat, int32_t
   CK(c, cudaMemsetAsync(c->flags.p, 0, sizeof(int) * n, c->stream));
   if (sd.nm_valid > 0) {
     export_dense_kernel<<<blocks_for(sd.nm_valid, 256), 256, 0, c->stream>>>(
-      sd.m_pts.p, sd.c_fidx.p, sd.c_resp.p, sd.stat_valid ? sd.c_stat.p : nullptr, sd.stat_valid ? sd.c_chi.p : nullptr,
+      sd.m_pts.p, sd.f_pts.p, sd.c_fpos.p, sd.c_fidx.p, sd.c_resp.p, sd.stat_valid ? sd.c_stat.p : nullptr, sd.stat_valid ? sd.c_chi.p : nullptr,
       sd.nm_valid, prune, c->d_fidx.p, c->d_resp.p, want_stat ? c->d_stat.p : nullptr, want_stat ? c->d_chi.p : nullptr,
       c->flags.p);
     c->launches++;
@@ -581,6 +671,7 @@ int srrg2b_ctx_create(int dim, int device, srrg2b_ctx** out) {
   ok = ok && cudaMallocHost((void**) &c->h_bounds, 8 * sizeof(int)) == cudaSuccess;
   ok = ok && cudaMemsetAsync(c->d_state, 0, sizeof(DevState), c->stream) == cudaSuccess;
   ok = ok && cudaStreamSynchronize(c->stream) == cudaSuccess;
+  ok = ok && upload_row_tables() == SRRG2B_OK;
   if (!ok) {
     srrg2b_ctx_destroy(c);
     return SRRG2B_ERR_CUDA;
@@ -600,7 +691,7 @@ int srrg2b_ctx_destroy(srrg2b_ctx* c) {
     s.moving_raw.xyz.release(); s.moving_raw.nrm.release(); s.moving_raw.valid.release();
     s.f_pts.release(); s.f_nrm.release(); s.f_inverse.release(); s.cell_start.release();
     s.m_pts.release(); s.m_nrm.release(); s.m_inverse.release();
-    s.c_fidx.release(); s.c_fpos.release(); s.c_resp.release(); s.c_chi.release(); s.c_stat.release();
+    s.c_fidx.release(); s.c_fpos.release(); s.far_list.release(); s.far_count.release(); s.c_resp.release(); s.c_chi.release(); s.c_stat.release();
   }
   c->keys_a.release(); c->keys_b.release(); c->vals_a.release(); c->vals_b.release();
   c->flags.release(); c->positions.release(); c->bounds.release(); c->cub_tmp.release();
@@ -687,7 +778,7 @@ int srrg2b_find_correspondences(srrg2b_ctx* c, int slice_id, const float* S, con
   embed(c->dim, S, S4);
   set_S_kernel<<<1, 32, 0, c->stream>>>(c->d_state, 0, S4);
   c->launches++;
-  rcode = launch_slice<MODE_FIND>(c, a, SRRG2B_FACTOR_P2P);
+  rcode = launch_find(c, a);
   if (rcode) return rcode;
   CK(c, cudaGetLastError());
   sd.corr_valid = true;
@@ -756,7 +847,7 @@ int srrg2b_linearize(srrg2b_ctx* c, int slice_id, const float* S, int variable, 
   embed(c->dim, S, S4);
   set_S_kernel<<<1, 32, 0, c->stream>>>(c->d_state, 0, S4);
   c->launches++;
-  rcode = launch_slice<MODE_LINEARIZE>(c, a, fa->factor);
+  rcode = launch_linearize(c, a, fa->factor);
   if (rcode) return rcode;
   CK(c, cudaGetLastError());
   rcode = allreduce_acc(c, 1);
@@ -925,6 +1016,23 @@ int srrg2b_last_run_timing(srrg2b_ctx* c, float* device_ms, int32_t* iterations)
   if (!c) return SRRG2B_ERR_INVALID;
   if (device_ms) *device_ms = c->last_ms;
   if (iterations) *iterations = c->last_iterations;
+  return SRRG2B_OK;
+}
+
+int srrg2b_debug_info(srrg2b_ctx* c, int slice_id, int32_t* out16) {
+  if (!c || !out16) return SRRG2B_ERR_INVALID;
+  if (!c->slices.count(slice_id)) FAIL(c, SRRG2B_ERR_STATE, "unknown slice");
+  CK(c, cudaSetDevice(c->device));
+  SliceData& sd = c->slices[slice_id];
+  memset(out16, 0, 16 * sizeof(int32_t));
+  out16[0] = sd.R; out16[1] = sd.nx; out16[2] = sd.ny; out16[3] = sd.nz;
+  out16[4] = sd.nf_valid; out16[5] = sd.nm_valid;
+  if (sd.far_count.p) {
+    CK(c, cudaMemcpyAsync(&out16[6], sd.far_count.p, 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+  }
+  float cell = 1.f / sd.inv_cell;
+  memcpy(&out16[7], &cell, 4);
   return SRRG2B_OK;
 }
 

@@ -1,7 +1,8 @@
 // s2b_icp.cuh -- device code of the aligner hot path:
 //   k0  index build helpers (bounds, cell ids, Morton keys, gathers, cell table)
-//   k1  icp_slice_kernel: fused  transform -> exact grid NN -> gates -> error/Jacobian ->
-//       robust weight -> exact fixed-point accumulation of H, b, chi, counters
+//   k1a nn_kernel: transform -> exact pruned grid NN (warm-started) -> normal gate
+//   k1b linearize_kernel: error/Jacobian -> robust weight -> exact fixed-point accumulation of
+//       H, b, chi, counters
 //   k1s icp_solve_kernel: slice-ordered assembly, prior factors, 6x6/3x3 LL^T, X <- X [+] dx,
 //       IterationStats append, termination criterion, next-iteration finder transforms
 //   k2b export kernels (sorted order -> ascending moving_idx, optional inlier pruning)
@@ -60,15 +61,18 @@ struct SliceArgs {
   const int* __restrict__ cell_start;
   float ox, oy, oz, inv_cell;
   int nx, ny, nz;
+  int R;      // search radius in cells (cell edge = 1.001 * max_distance / R)
+  int warm;   // c_fpos holds a valid candidate position per query (previous iteration's NN)
   float md2, normal_cos;
   int gate;
   int rob;
   float tau, ip, in_, rs;
   double sH, sb, sc;
   const float* S;
-  int* c_fidx;
   int* c_fpos;
   float* c_resp;
+  int* far_list;   // phase-2 worklist of the NN search (query positions) and its counter
+  int* far_count;
   unsigned char* c_stat;  // may be null
   float* c_chi;           // may be null
   unsigned long long* acc;
@@ -132,6 +136,19 @@ __device__ __forceinline__ int cell_coord(float v, float o, float inv, int n) {
   float c = (v - o) * inv;
   c = fminf(fmaxf(c, -2.f), (float) n + 1.f);
   return (int) floorf(c);
+}
+
+__device__ __forceinline__ float cell_coord_f(float v, float o, float inv, int n) {
+  const float c = (v - o) * inv;
+  return fminf(fmaxf(c, -2.f), (float) n + 1.f);
+}
+
+// conservative lower bound (in cells) of the distance along one axis between a query at in-cell
+// fraction fr and any point of the cell at integer offset d; 2e-3 cells of slack cover the fp32
+// rounding of the cell coordinate (grids are capped at 1024 cells per axis)
+__device__ __forceinline__ float axis_gap(int d, float fr) {
+  const float g = d > 0 ? (float) d - fr : (d < 0 ? fr - (float) (d + 1) : 0.f);
+  return fmaxf(g - 2e-3f, 0.f);
 }
 
 // fixed cloud: key = linear cell id (x fastest), invalid points -> 0xffffffff
@@ -232,13 +249,241 @@ __global__ void cell_start_kernel(const unsigned* __restrict__ keys, int n_valid
   cell_start[c] = lo;
 }
 
+// number of distinct keys among the first n sorted keys (= occupied cells)
+__global__ void count_distinct_kernel(const unsigned* __restrict__ keys, int n, int* __restrict__ out) {
+  int c = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    c += (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
+  c = __reduce_add_sync(0xffffffffu, c);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+
 __global__ void fill_int_kernel(int* p, int n, int v) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
 }
 
 // ---------------------------------------------------------------------------------------------
-// k1: fused ICP iteration over one slice
+// k1a: exact nearest neighbour (a3).  One query per thread, queries in Morton order.
+// ---------------------------------------------------------------------------------------------
+// Correspondence slot encoding (c_fpos, per moving point in Morton order):
+//   >= 0            accepted correspondence, value = position of the fixed point in cell order
+//   -1              no fixed point within max_distance
+//   <= -2           neighbour at position -(v+2) exists but the normal gate rejected it (kept only
+//                   as the warm-start candidate of the next iteration)
+//   kSlotSuppressed externally supplied correspondence that cannot be evaluated
+constexpr int kSlotSuppressed = INT_MIN;
+constexpr int kMaxR = 4;
+constexpr int kRowTable = (2 * kMaxR + 1) * (2 * kMaxR + 1);
+
+// rows (dy, dz) of the search neighbourhood ordered by Chebyshev ring; filled by the host
+__constant__ signed char c_rows3[kRowTable][4];  // dy, dz, ring, 0   (3D)
+__constant__ signed char c_rows2[2 * kMaxR + 1][4];  // dy, 0, ring, 0 (2D)
+
+// shared pieces of the two NN kernels -----------------------------------------------------------
+struct NNQuery {
+  float qx, qy, qz;      // transformed query
+  float cfx;             // float cell coordinate along x
+  int cx, cy, cz;        // integer cell
+  float fry, frz;        // in-cell fractions along y, z
+  float bd2;             // best squared distance so far (starts at max_distance^2)
+  int bidx, bpos;        // best original index / position in cell order
+};
+
+template <int DIM>
+__device__ __forceinline__ void nn_consider(const SliceArgs& a, NNQuery& q, int p) {
+  const float4 c = __ldg(a.fp + p);
+  const float ddx = q.qx - c.x, ddy = q.qy - c.y, ddz = q.qz - c.z;
+  float d2 = fmaf(ddy, ddy, ddx * ddx);
+  if (DIM == 3) d2 = fmaf(ddz, ddz, d2);
+  const int id = __float_as_int(c.w);
+  if (d2 < q.bd2 || (d2 == q.bd2 && id < q.bidx)) {
+    q.bd2 = d2; q.bidx = id; q.bpos = p;
+  }
+}
+
+// scan the part of cell row (y, z) that can still hold a point with d2 <= bd2, given the
+// conservative squared distance lb2 between the query and the row's y/z slab
+template <int DIM>
+__device__ __forceinline__ void nn_scan_row(const SliceArgs& a, NNQuery& q, int y, int z, float lb2) {
+  const float rr = __fsqrt_rn(fmaxf(q.bd2 - lb2, 0.f)) * a.inv_cell + 2e-3f;
+  const int xa = max(max((int) floorf(q.cfx - rr), q.cx - a.R), 0);
+  const int xb = min(min((int) floorf(q.cfx + rr), q.cx + a.R), a.nx - 1);
+  if (xa > xb) return;
+  const int row = (z * a.ny + y) * a.nx;
+  const int ps = __ldg(a.cell_start + row + xa);
+  const int pe = __ldg(a.cell_start + row + xb + 1);
+#pragma unroll 1
+  for (int p = ps; p < pe; ++p) nn_consider<DIM>(a, q, p);
+}
+
+template <int DIM>
+__device__ __forceinline__ void nn_setup(const SliceArgs& a, const float* S, const float4 m, NNQuery& q) {
+  float t;  // q = S m  (operation order is part of the numerics contract)
+  t = S[0] * m.x; t = fmaf(S[1], m.y, t); if (DIM == 3) t = fmaf(S[2], m.z, t); q.qx = t + S[3];
+  t = S[4] * m.x; t = fmaf(S[5], m.y, t); if (DIM == 3) t = fmaf(S[6], m.z, t); q.qy = t + S[7];
+  q.qz = 0.f;
+  if (DIM == 3) { t = S[8] * m.x; t = fmaf(S[9], m.y, t); t = fmaf(S[10], m.z, t); q.qz = t + S[11]; }
+  q.cfx = cell_coord_f(q.qx, a.ox, a.inv_cell, a.nx);
+  const float cfy = cell_coord_f(q.qy, a.oy, a.inv_cell, a.ny);
+  const float cfz = (DIM == 3) ? cell_coord_f(q.qz, a.oz, a.inv_cell, a.nz) : 0.f;
+  q.cx = (int) floorf(q.cfx); q.cy = (int) floorf(cfy); q.cz = (DIM == 3) ? (int) floorf(cfz) : 0;
+  q.fry = cfy - (float) q.cy; q.frz = cfz - (float) q.cz;
+  q.bd2 = a.md2; q.bidx = INT_MAX; q.bpos = -1;
+}
+
+// normal gate + slot/response of a finished query
+template <int DIM>
+__device__ __forceinline__ void nn_finish(const SliceArgs& a, const float* S, const NNQuery& q, int i) {
+  int slot = -1;
+  float resp = 0.f;
+  if (q.bpos >= 0) {
+    bool ok = true;
+    if (a.gate) {
+      const float4 nm = a.mn[i];
+      const float4 nf = __ldg(a.fn + q.bpos);
+      float t;
+      t = S[0] * nm.x; t = fmaf(S[1], nm.y, t); if (DIM == 3) t = fmaf(S[2], nm.z, t); const float nqx = t;
+      t = S[4] * nm.x; t = fmaf(S[5], nm.y, t); if (DIM == 3) t = fmaf(S[6], nm.z, t); const float nqy = t;
+      float dot = fmaf(nf.y, nqy, nf.x * nqx);
+      if (DIM == 3) {
+        t = S[8] * nm.x; t = fmaf(S[9], nm.y, t); t = fmaf(S[10], nm.z, t);
+        dot = fmaf(nf.z, t, dot);
+      }
+      ok = !(dot < a.normal_cos);
+    }
+    slot = ok ? q.bpos : -(q.bpos + 2);
+    resp = ok ? __fsqrt_rn(q.bd2) : 0.f;
+  }
+  a.c_fpos[i] = slot;
+  a.c_resp[i] = resp;
+}
+
+// Phase 1: warm start + the 3^(DIM-1) rows of rings 0 and 1, fully unrolled (row offsets are
+// compile-time constants, so the slab gaps are three registers per axis).  A query whose best
+// distance is still larger than the distance to ring 2 is handed to phase 2 through a worklist,
+// so that the rare expensive queries (outliers, large initial misalignment) do not serialise
+// the warps of the cheap ones.
+template <int DIM>
+__global__ void __launch_bounds__(256) nn_kernel(const SliceArgs a) {
+  if (*a.stop) return;
+  __shared__ float S[16];
+  if (threadIdx.x < 16) S[threadIdx.x] = a.S[threadIdx.x];
+  __syncthreads();
+  const float cell = __fdiv_rn(1.f, a.inv_cell);
+  const float ring2 = (a.R >= 2) ? (1.f - 2e-3f) * cell : 3.0e38f;
+  const float ring2_sq = (a.R >= 2) ? ring2 * ring2 : 3.0e38f;
+
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.nm; i += gridDim.x * blockDim.x) {
+    NNQuery q;
+    nn_setup<DIM>(a, S, a.mp[i], q);
+    if (a.warm) {  // previous iteration's neighbour: a real candidate, so exactness is untouched
+      int p0 = a.c_fpos[i];
+      if (p0 <= -2 && p0 != kSlotSuppressed) p0 = -(p0 + 2);
+      if (p0 >= 0) nn_consider<DIM>(a, q, p0);
+    }
+    // squared slab gaps for offsets -1 and +1 along y and z (offset 0 has gap 0)
+    const float gym = fmaxf(q.fry - 2e-3f, 0.f) * cell, gyp = fmaxf(1.f - q.fry - 2e-3f, 0.f) * cell;
+    const float gy2m = gym * gym, gy2p = gyp * gyp;
+    float gz2m = 0.f, gz2p = 0.f;
+    if (DIM == 3) {
+      const float gzm = fmaxf(q.frz - 2e-3f, 0.f) * cell, gzp = fmaxf(1.f - q.frz - 2e-3f, 0.f) * cell;
+      gz2m = gzm * gzm; gz2p = gzp * gzp;
+    }
+    // centre row first: it usually tightens bd2 enough to prune most of ring 1
+    if (q.cy >= 0 && q.cy < a.ny && q.cz >= 0 && q.cz < a.nz) nn_scan_row<DIM>(a, q, q.cy, q.cz, 0.f);
+    // ring 1: each lane walks only ITS OWN surviving rows (bit b = jz * 3 + jy), so a warp spends
+    // max-over-lanes(#surviving rows) iterations instead of all eight
+    unsigned mask = 0;
+#pragma unroll
+    for (int jz = (DIM == 3 ? 0 : 1); jz < (DIM == 3 ? 3 : 2); ++jz) {
+      const int z = q.cz + jz - 1;
+      const bool zin = (z >= 0 && z < a.nz);
+#pragma unroll
+      for (int jy = 0; jy < 3; ++jy) {
+        if (jy == 1 && jz == 1) continue;
+        const int y = q.cy + jy - 1;
+        const float lb2 = (jy == 0 ? gy2m : (jy == 2 ? gy2p : 0.f)) + (jz == 0 ? gz2m : (jz == 2 ? gz2p : 0.f));
+        if (zin && y >= 0 && y < a.ny && !(lb2 > q.bd2)) mask |= 1u << (jz * 3 + jy);
+      }
+    }
+    while (mask) {
+      const int b = __ffs(mask) - 1;
+      mask &= mask - 1;
+      const int jz = (b * 11) >> 5, jy = b - 3 * jz;
+      const float lb2 = (jy == 0 ? gy2m : (jy == 2 ? gy2p : 0.f)) + (jz == 0 ? gz2m : (jz == 2 ? gz2p : 0.f));
+      if (lb2 > q.bd2) continue;
+      nn_scan_row<DIM>(a, q, q.cy + jy - 1, q.cz + jz - 1, lb2);
+    }
+    if (q.bd2 > ring2_sq) {
+      // not settled by rings 0-1: keep the provisional best as phase 2's warm start
+      a.c_fpos[i] = (q.bpos >= 0) ? -(q.bpos + 2) : -1;
+      const int w = atomicAdd(a.far_count, 1);
+      a.far_list[w] = i;
+      continue;
+    }
+    nn_finish<DIM>(a, S, q, i);
+  }
+}
+
+// Phase 2: rings 2..R for the queries phase 1 could not settle (worklist).  These are few but
+// expensive (typically no neighbour at all, so nothing prunes), so one WARP takes one query: lane l
+// scans row K0 + l (+32, ...) against the provisional best, then a lexicographic (d2, index)
+// shuffle-min picks the winner and lane 0 applies the gate and writes the slot.
+template <int DIM>
+__global__ void __launch_bounds__(256) nn_far_kernel(const SliceArgs a) {
+  if (*a.stop) return;
+  __shared__ float S[16];
+  __shared__ int rows[kRowTable];
+  if (threadIdx.x < 16) S[threadIdx.x] = a.S[threadIdx.x];
+  const int R = a.R;
+  const int K = (DIM == 3) ? (2 * R + 1) * (2 * R + 1) : (2 * R + 1);
+  const int K0 = (DIM == 3) ? 9 : 3;  // rows of rings 0-1, done by phase 1
+  for (int k = threadIdx.x; k < K; k += blockDim.x)
+    rows[k] = (DIM == 3) ? *reinterpret_cast<const int*>(c_rows3[k]) : *reinterpret_cast<const int*>(c_rows2[k]);
+  __syncthreads();
+  const float cell = __fdiv_rn(1.f, a.inv_cell);
+  const int n_far = *a.far_count;
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  for (int w = blockIdx.x * warps_per_block + (threadIdx.x >> 5); w < n_far; w += gridDim.x * warps_per_block) {
+    const int i = a.far_list[w];
+    NNQuery q;
+    nn_setup<DIM>(a, S, a.mp[i], q);
+    {
+      int p0 = a.c_fpos[i];
+      if (p0 <= -2 && p0 != kSlotSuppressed) p0 = -(p0 + 2);
+      if (p0 >= 0) nn_consider<DIM>(a, q, p0);
+    }
+    for (int k = K0 + lane; k < K; k += 32) {
+      const int e = rows[k];
+      const int dy = (int) (signed char) (e & 0xff), dz = (int) (signed char) ((e >> 8) & 0xff);
+      const int y = q.cy + dy, z = q.cz + dz;
+      if (y < 0 || y >= a.ny || z < 0 || z >= a.nz) continue;
+      const float gy = axis_gap(dy, q.fry) * cell;
+      float lb2 = gy * gy;
+      if (DIM == 3) {
+        const float gz = axis_gap(dz, q.frz) * cell;
+        lb2 = fmaf(gz, gz, lb2);
+      }
+      if (lb2 > q.bd2) continue;
+      nn_scan_row<DIM>(a, q, y, z, lb2);
+    }
+#pragma unroll
+    for (int off = 16; off; off >>= 1) {
+      const float od2 = __shfl_xor_sync(0xffffffffu, q.bd2, off);
+      const int oidx = __shfl_xor_sync(0xffffffffu, q.bidx, off);
+      const int opos = __shfl_xor_sync(0xffffffffu, q.bpos, off);
+      if (od2 < q.bd2 || (od2 == q.bd2 && oidx < q.bidx)) {
+        q.bd2 = od2; q.bidx = oidx; q.bpos = opos;
+      }
+    }
+    if (lane == 0) nn_finish<DIM>(a, S, q, i);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k1b: per-correspondence linearisation + exact accumulation (a5)
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ long long to_fixed(float v, double scale) {
   return __double2ll_rn((double) v * scale);
@@ -265,10 +510,8 @@ __device__ __forceinline__ bool robustify(int kind, float tau, float chi, float&
   return true;
 }
 
-enum { MODE_FUSED = 0, MODE_FIND = 1, MODE_LINEARIZE = 2 };
-
-template <int DIM, int FACTOR, int MODE>
-__global__ void __launch_bounds__(256) icp_slice_kernel(const SliceArgs a) {
+template <int DIM, int FACTOR>
+__global__ void __launch_bounds__(256) linearize_kernel(const SliceArgs a) {
   if (*a.stop) return;
   constexpr int P = (DIM == 3) ? 6 : 3;
   constexpr int NH = P * (P + 1) / 2;
@@ -289,10 +532,37 @@ __global__ void __launch_bounds__(256) icp_slice_kernel(const SliceArgs a) {
 #pragma unroll
   for (int k = 0; k < P; ++k) ab[k] = 0;
 
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.nm; i += gridDim.x * blockDim.x) {
-    const float4 m = a.mp[i];
-    const float4 nm = a.mn[i];
-    // q = S m, nq = R_S n_m  (operation order is part of the numerics contract)
+  // software pipeline: the loads of the next query (slot -> gathered fixed point/normal) are in
+  // flight while the current one is linearised; the kernel is latency bound otherwise
+  const int stride = gridDim.x * blockDim.x;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  int slot_n = (i < a.nm) ? a.c_fpos[i] : -1;
+  float4 m_n = zero4, nm_n = zero4, f_n = zero4, nf_n = zero4;
+  if (slot_n >= 0) {
+    m_n = a.mp[i]; nm_n = a.mn[i];
+    f_n = __ldg(a.fp + slot_n); nf_n = __ldg(a.fn + slot_n);
+  }
+  int slot_nn = (i + stride < a.nm) ? a.c_fpos[i + stride] : -1;
+  for (; i < a.nm; i += stride) {
+    const int bpos = slot_n;
+    const float4 m = m_n, nm = nm_n, f = f_n, nf = nf_n;
+    // advance the pipeline
+    slot_n = slot_nn;
+    if (slot_n >= 0) {
+      m_n = a.mp[i + stride]; nm_n = a.mn[i + stride];
+      f_n = __ldg(a.fp + slot_n); nf_n = __ldg(a.fn + slot_n);
+    }
+    slot_nn = (i + 2 * stride < a.nm) ? a.c_fpos[i + 2 * stride] : -1;
+    if (bpos < 0) {
+      if (bpos == kSlotSuppressed) {
+        ++n_sup;
+        if (a.c_stat) a.c_stat[i] = SRRG2B_STAT_SUPPRESSED;
+      } else if (a.c_stat) {
+        a.c_stat[i] = SRRG2B_STAT_NONE;
+      }
+      continue;
+    }
     float t;
     t = s00 * m.x; t = fmaf(s01, m.y, t); if (DIM == 3) t = fmaf(s02, m.z, t); const float qx = t + s03;
     t = s10 * m.x; t = fmaf(s11, m.y, t); if (DIM == 3) t = fmaf(s12, m.z, t); const float qy = t + s13;
@@ -302,71 +572,6 @@ __global__ void __launch_bounds__(256) icp_slice_kernel(const SliceArgs a) {
     t = s10 * nm.x; t = fmaf(s11, nm.y, t); if (DIM == 3) t = fmaf(s12, nm.z, t); const float nqy = t;
     float nqz = 0.f;
     if (DIM == 3) { t = s20 * nm.x; t = fmaf(s21, nm.y, t); t = fmaf(s22, nm.z, t); nqz = t; }
-
-    int bpos = -1;
-    float4 f, nf;
-    if (MODE != MODE_LINEARIZE) {
-      // ---- exact NN inside max_distance over the 3^DIM neighbourhood of q's cell ----
-      float bd2 = a.md2;
-      int bidx = INT_MAX;
-      const int cx = cell_coord(qx, a.ox, a.inv_cell, a.nx);
-      const int cy = cell_coord(qy, a.oy, a.inv_cell, a.ny);
-      const int cz = (DIM == 3) ? cell_coord(qz, a.oz, a.inv_cell, a.nz) : 0;
-      const int x0 = max(cx - 1, 0), x1 = min(cx + 1, a.nx - 1);
-      if (x0 <= x1) {
-        const int z0 = (DIM == 3) ? cz - 1 : 0, z1 = (DIM == 3) ? cz + 1 : 0;
-        for (int z = z0; z <= z1; ++z) {
-          if (z < 0 || z >= a.nz) continue;
-          for (int y = cy - 1; y <= cy + 1; ++y) {
-            if (y < 0 || y >= a.ny) continue;
-            const int row = (z * a.ny + y) * a.nx;
-            const int ps = __ldg(a.cell_start + row + x0);
-            const int pe = __ldg(a.cell_start + row + x1 + 1);
-            for (int p = ps; p < pe; ++p) {
-              const float4 c = __ldg(a.fp + p);
-              const float dx = qx - c.x, dy = qy - c.y, dz = qz - c.z;
-              float d2 = fmaf(dy, dy, dx * dx);
-              if (DIM == 3) d2 = fmaf(dz, dz, d2);
-              const int id = __float_as_int(c.w);
-              if (d2 < bd2 || (d2 == bd2 && id < bidx)) {
-                bd2 = d2; bidx = id; bpos = p;
-              }
-            }
-          }
-        }
-      }
-      int out_idx = -1;
-      float out_resp = 0.f;
-      if (bpos >= 0) {
-        f = __ldg(a.fp + bpos);
-        nf = __ldg(a.fn + bpos);
-        bool ok = true;
-        if (a.gate) {
-          float dot = fmaf(nf.y, nqy, nf.x * nqx);
-          if (DIM == 3) dot = fmaf(nf.z, nqz, dot);
-          ok = !(dot < a.normal_cos);
-        }
-        if (ok) { out_idx = bidx; out_resp = __fsqrt_rn(bd2); } else { bpos = -1; }
-      }
-      a.c_fidx[i] = out_idx;
-      a.c_fpos[i] = bpos;
-      a.c_resp[i] = out_resp;
-    } else {
-      bpos = a.c_fpos[i];
-      if (bpos >= 0) {
-        f = __ldg(a.fp + bpos);
-        nf = __ldg(a.fn + bpos);
-      } else if (bpos == -2) {  // externally supplied correspondence that cannot be evaluated
-        ++n_sup;
-        if (a.c_stat) a.c_stat[i] = SRRG2B_STAT_SUPPRESSED;
-        continue;
-      }
-    }
-    if (MODE == MODE_FIND) continue;
-    if (bpos < 0) {
-      if (a.c_stat) a.c_stat[i] = SRRG2B_STAT_NONE;
-      continue;
-    }
 
     // ---- error rows e, information om, Jacobian rows J (right perturbation of X) ----
     constexpr int E = (FACTOR == SRRG2B_FACTOR_P2P) ? DIM : DIM + 1;
@@ -479,7 +684,6 @@ __global__ void __launch_bounds__(256) icp_slice_kernel(const SliceArgs a) {
     }
   }
 
-  if (MODE == MODE_FIND) return;
   // ---- exact integer block reduction: warp shuffles -> shared atomics -> one global atomic per slot
   auto wsum = [](long long v) {
 #pragma unroll
@@ -605,13 +809,27 @@ __global__ void set_S_kernel(DevState* st, int slice, Mat4f S) {
 
 // body of one _runSolver iteration after the per-slice kernels
 // (R/registration/aligners/multi_aligner_impl.cpp:106-126)
+template <int DIM>
 __global__ void icp_solve_kernel(const SolveArgs a, DevState* st) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  if (st->stop) return;
-  const int P = (a.dim == 3) ? 6 : 3;
-  double H[36], b[6];
-  for (int i = 0; i < 36; ++i) H[i] = 0.0;
-  for (int i = 0; i < 6; ++i) b[i] = 0.0;
+  constexpr int P = (DIM == 3) ? 6 : 3;
+  // the accumulators of all slices are fetched by the whole warp in one go (and zeroed for the
+  // next iteration); the O(#slices) serial part then runs on lane 0 out of shared memory
+  __shared__ unsigned long long sacc[SRRG2B_MAX_SLICES][kAcc];
+  __shared__ int s_stop;
+  if (threadIdx.x == 0) s_stop = st->stop;
+  __syncthreads();
+  if (s_stop) return;
+  for (int k = threadIdx.x; k < a.n_slices * kAcc; k += blockDim.x) {
+    sacc[k / kAcc][k % kAcc] = st->acc[k / kAcc][k % kAcc];
+    st->acc[k / kAcc][k % kAcc] = 0ull;
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  double H[P * P], b[P];
+#pragma unroll
+  for (int i = 0; i < P * P; ++i) H[i] = 0.0;
+#pragma unroll
+  for (int i = 0; i < P; ++i) b[i] = 0.0;
   srrg2b_iter_stats s;
   s.iteration = st->n_stats;
   s.solver_status = 0;
@@ -619,30 +837,37 @@ __global__ void icp_solve_kernel(const SolveArgs a, DevState* st) {
   s.chi_inliers = 0.0; s.chi_outliers = 0.0;
   bool good = false;
   long long total = 0;
+  Mat4f X = st->X;
   for (int k = 0; k < a.n_slices; ++k) {
     const SolveSlice& sl = a.sl[k];
     if (sl.kind == SRRG2B_SLICE_PRIOR) {
       double chi = 0.0;
-      prior_accumulate(a.dim, a.variable, sl.Z, st->X, sl.info, H, b, chi);
+      double Hf[36], bf[6];  // prior_accumulate is written for run-time P
+      for (int i = 0; i < P * P; ++i) Hf[i] = H[i];
+      for (int i = 0; i < P; ++i) bf[i] = b[i];
+      prior_accumulate(DIM, a.variable, sl.Z, X, sl.info, Hf, bf, chi);
+      for (int i = 0; i < P * P; ++i) H[i] = Hf[i];
+      for (int i = 0; i < P; ++i) b[i] = bf[i];
       s.num_inliers += 1; s.num_correspondences += 1; s.chi_inliers += chi;
       good = true;  // aligner_slice_processor_prior.h:65-67
       total += 1;   // :75-77
       st->ncorr[k] = 1;
       continue;
     }
-    const unsigned long long* acc = st->acc[k];
-    double Hs[36], bs[6];
+    const unsigned long long* acc = sacc[k];
+    // the slice's H (both triangles) and b are added entry by entry in slice order
     int slot = 0;
+#pragma unroll
     for (int i = 0; i < P; ++i) {
+#pragma unroll
       for (int j = i; j < P; ++j) {
         const double v = __ll2double_rn((long long) acc[slot++]) * sl.invH;
-        Hs[i * P + j] = v;
-        Hs[j * P + i] = v;
+        H[i * P + j] = H[i * P + j] + v;
+        if (j != i) H[j * P + i] = H[j * P + i] + v;
       }
     }
-    for (int i = 0; i < P; ++i) bs[i] = __ll2double_rn((long long) acc[kAccB + i]) * sl.invb;
-    for (int i = 0; i < P * P; ++i) H[i] = H[i] + Hs[i];
-    for (int i = 0; i < P; ++i) b[i] = b[i] + bs[i];
+#pragma unroll
+    for (int i = 0; i < P; ++i) b[i] = b[i] + __ll2double_rn((long long) acc[kAccB + i]) * sl.invb;
     const long long ni = (long long) acc[kAccNIn], no = (long long) acc[kAccNOut], ns = (long long) acc[kAccNSup];
     s.num_inliers += ni; s.num_outliers += no; s.num_suppressed += ns; s.num_correspondences += ni + no + ns;
     s.chi_inliers += __ll2double_rn((long long) acc[kAccChiIn]) * sl.invchi;
@@ -651,7 +876,6 @@ __global__ void icp_solve_kernel(const SolveArgs a, DevState* st) {
     st->ncorr[k] = n;
     total += n;
     good = good || (n > (long long) sl.min_corr);  // aligner_slice_processor_impl.cpp:77-79
-    for (int q = 0; q < kAcc; ++q) st->acc[k][q] = 0ull;
   }
   st->iterations_run += 1;
   if (!good) {  // multi_aligner_impl.cpp:107-111 (estimate already equals the backup)
@@ -659,23 +883,23 @@ __global__ void icp_solve_kernel(const SolveArgs a, DevState* st) {
     st->stop = 1;
     return;
   }
-  double dx[6];
-  Mat4f X = st->X;
-  if (spd_solve(P, H, b, dx)) {
-    box_plus(a.dim, a.variable, dx, X);
+  double dx[6] = {0, 0, 0, 0, 0, 0};
+  if (spd_solve_t<P>(H, b, dx)) {
+    box_plus(DIM, a.variable, dx, X);
     st->X = X;
     s.solver_status = 1;
   }
   if (st->n_stats < kMaxStats) st->stats[st->n_stats] = s;
   st->n_stats += 1;
-  for (int k = 0; k < a.n_slices; ++k) compose(a.sl[k].ris, st->X, st->S[k]);
+  for (int k = 0; k < a.n_slices; ++k) compose(a.sl[k].ris, X, st->S[k]);
   if (a.use_tc && has_to_stop(st, a, s, total)) st->stop = 1;
 }
 
 // ---------------------------------------------------------------------------------------------
 // k2b: export (sorted order -> dense by local moving index), then compaction
 // ---------------------------------------------------------------------------------------------
-__global__ void export_dense_kernel(const float4* __restrict__ mp, const int* __restrict__ c_fidx,
+__global__ void export_dense_kernel(const float4* __restrict__ mp, const float4* __restrict__ fp,
+                                    const int* __restrict__ c_fpos, const int* __restrict__ c_fidx,
                                     const float* __restrict__ c_resp, const unsigned char* __restrict__ c_stat,
                                     const float* __restrict__ c_chi, int nm, int prune, int* __restrict__ d_fidx,
                                     float* __restrict__ d_resp, unsigned char* __restrict__ d_stat,
@@ -683,8 +907,11 @@ __global__ void export_dense_kernel(const float4* __restrict__ mp, const int* __
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nm) return;
   const int src = __float_as_int(mp[i].w);
-  const int fi = c_fidx[i];
-  const bool keep = fi >= 0 && (!prune || (c_stat && c_stat[i] == SRRG2B_STAT_INLIER));
+  const int slot = c_fpos[i];
+  int fi = -1;
+  if (slot >= 0) fi = __float_as_int(fp[slot].w);
+  else if (slot == kSlotSuppressed) fi = c_fidx[i];  // externally supplied, kept as given
+  const bool keep = (slot >= 0 || slot == kSlotSuppressed) && (!prune || (c_stat && c_stat[i] == SRRG2B_STAT_INLIER));
   d_flag[src] = keep ? 1 : 0;
   d_fidx[src] = fi;
   d_resp[src] = c_resp[i];
@@ -720,7 +947,7 @@ __global__ void import_corr_kernel(const int* __restrict__ fixed_idx, const int*
   if (mpos < 0) { atomicAdd(n_bad, 1); return; }
   const int fpos = (fi >= 0 && fi < nf_raw) ? f_inverse[fi] : -1;
   c_fidx[mpos] = fi;
-  c_fpos[mpos] = fpos >= 0 ? fpos : -2;
+  c_fpos[mpos] = fpos >= 0 ? fpos : kSlotSuppressed;
   c_resp[mpos] = 0.f;
 }
 

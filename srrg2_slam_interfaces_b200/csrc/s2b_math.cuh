@@ -258,36 +258,52 @@ S2B_HD void fix_transform(int dim, Mat4f& X) {
   }
 }
 
-// dense SPD solve H dx = -b via LL^T; false when H is not positive definite / not finite
-S2B_HD bool spd_solve(int P, const double* H, const double* b, double* dx) {
-  double L[36];
-  for (int i = 0; i < 36; ++i) L[i] = 0.0;
+// dense SPD solve H dx = -b via LL^T; false when H is not positive definite / not finite.
+// Compile-time P and full unrolling keep L, y in registers on the device.
+template <int P>
+S2B_HD bool spd_solve_t(const double* H, const double* b, double* dx) {
+  double L[P * P];
+#pragma unroll
+  for (int i = 0; i < P * P; ++i) L[i] = 0.0;
+#pragma unroll
   for (int j = 0; j < P; ++j) {
     double d = H[j * P + j];
+#pragma unroll
     for (int k = 0; k < j; ++k) d = d - L[j * P + k] * L[j * P + k];
     if (!(d > 0.0) || !(d < 1e300)) return false;
     const double ljj = sqrt(d);
     L[j * P + j] = ljj;
+#pragma unroll
     for (int i = j + 1; i < P; ++i) {
       double s = H[i * P + j];
+#pragma unroll
       for (int k = 0; k < j; ++k) s = s - L[i * P + k] * L[j * P + k];
       L[i * P + j] = s / ljj;
     }
   }
-  double y[6];
+  double y[P];
+#pragma unroll
   for (int i = 0; i < P; ++i) {
     double s = -b[i];
+#pragma unroll
     for (int k = 0; k < i; ++k) s = s - L[i * P + k] * y[k];
     y[i] = s / L[i * P + i];
   }
+#pragma unroll
   for (int i = P - 1; i >= 0; --i) {
     double s = y[i];
+#pragma unroll
     for (int k = i + 1; k < P; ++k) s = s - L[k * P + i] * dx[k];
     dx[i] = s / L[i * P + i];
   }
+#pragma unroll
   for (int i = 0; i < P; ++i)
     if (!(dx[i] == dx[i]) || fabs(dx[i]) > 1e300) return false;
   return true;
+}
+
+S2B_HD bool spd_solve(int P, const double* H, const double* b, double* dx) {
+  return P == 6 ? spd_solve_t<6>(H, b, dx) : spd_solve_t<3>(H, b, dx);
 }
 
 // SE(d) prior factor e = t2v(Z^-1 X), diagonal information; adds J^T W J / J^T W e, returns chi.

@@ -86,14 +86,14 @@ C2_T_STAR = iso3([0.10, -0.05, 0.08], np.deg2rad([1.5, -1.0, 2.0]))
 
 
 def make_icp3d(n_fixed, n_moving, seed=2, T_star=None, noise=0.002, outlier_frac=0.05, cube=20.0,
-               jitter=0.0005, n_planes=64, n_spheres=16):
+               jitter=0.0005, n_planes=64, n_spheres=16, moving_stream=0):
     """Config C2 generator: fixed and moving are INDEPENDENT samples of the same
     surfaces; moving = T*^-1 (sample + N(0,noise)), a fraction replaced by uniform outliers.
     The aligner estimate (moving in fixed) should converge to T*."""
     T_star = C2_T_STAR if T_star is None else T_star
     scene = Scene3D(seed, n_planes, n_spheres, cube)
     rf = np.random.default_rng([seed, 1])
-    rm = np.random.default_rng([seed, 2])
+    rm = np.random.default_rng([seed, 2] if moving_stream == 0 else [seed, 2, moving_stream])
     fp, fn = scene.sample(n_fixed, rf, jitter)
     mp, mn = scene.sample(n_moving, rm, 0.0)
     mp = mp + rm.normal(scale=noise, size=mp.shape)
