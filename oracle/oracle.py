@@ -94,7 +94,7 @@ def lib():
                                   C.POINTER(FinderParams), C.c_void_p, C.c_void_p]
         _lib.orc_linearize.argtypes = [C.c_int, C.c_int, C.POINTER(Cloud), C.POINTER(Cloud), C.c_void_p,
                                        C.c_void_p, C.POINTER(FinderParams), C.POINTER(FactorParams),
-                                       C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_int64, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.POINTER(IterStats), C.c_void_p, C.c_void_p]
         _lib.orc_icp_run.argtypes = [C.c_int, C.c_int, C.POINTER(Slice), C.POINTER(AlignerParams),
                                      C.c_void_p, C.POINTER(IterStats), C.POINTER(C.c_int32),
@@ -177,7 +177,8 @@ def find(index, fixed, moving, S, fp):
     return fidx, resp
 
 
-def linearize(fixed, moving, fidx, S, fp, fa, variable=VAR_SE3_QUAT_RIGHT, n_global=0, want_status=True):
+def linearize(fixed, moving, fidx, S, fp, fa, variable=VAR_SE3_QUAT_RIGHT, n_global=0, want_status=True,
+              coord_bound=0.0):
     dim = fixed.dim
     P = 6 if dim == 3 else 3
     S = _f32(S).reshape(-1)
@@ -189,7 +190,7 @@ def linearize(fixed, moving, fidx, S, fp, fa, variable=VAR_SE3_QUAT_RIGHT, n_glo
     status = np.empty(moving.n, dtype=np.uint8) if want_status else None
     chi = np.empty(moving.n, dtype=np.float32) if want_status else None
     rc = lib().orc_linearize(dim, variable, C.byref(fixed.c), C.byref(moving.c), fidx.ctypes.data,
-                             S.ctypes.data, C.byref(fp), C.byref(fa), n_global, acc.ctypes.data,
+                             S.ctypes.data, C.byref(fp), C.byref(fa), n_global, coord_bound, acc.ctypes.data,
                              H.ctypes.data, b.ctypes.data, C.byref(st), _ptr(status), _ptr(chi))
     assert rc == 0
     return dict(acc=acc, H=H, b=b, stats=st.as_dict(), status=status, chi=chi)

@@ -933,12 +933,14 @@ static void acc_to_Hb(int dim, const int64_t* acc, const orc_scales_t* sc, doubl
 
 int orc_linearize(int dim, int variable, const orc_cloud* fixed, const orc_cloud* moving,
                   const int32_t* fidx, const float* S, const orc_finder_params* fp,
-                  const orc_factor_params* fa, int64_t n_global, int64_t* acc_out, double* H, double* b,
-                  orc_iter_stats* stats, uint8_t* status_dense, float* chi_dense) {
+                  const orc_factor_params* fa, int64_t n_global, float coord_bound, int64_t* acc_out, double* H,
+                  double* b, orc_iter_stats* stats, uint8_t* status_dense, float* chi_dense) {
   float S4[16];
   embed4(dim, S, S4);
   orc_scales_t sc;
-  orc_scales(dim, n_global > 0 ? n_global : moving->n, orc_coord_bound(dim, moving), fp, fa, &sc);
+  /* n_global / coord_bound describe the WHOLE moving cloud when `moving` is one shard of it */
+  orc_scales(dim, n_global > 0 ? n_global : moving->n, coord_bound > 0.f ? coord_bound : orc_coord_bound(dim, moving),
+             fp, fa, &sc);
   int64_t acc[32];
   memset(acc, 0, sizeof(acc));
   const int have_n = (fixed->normals && moving->normals);
@@ -1186,7 +1188,7 @@ static void run_solver(run_state* rs, int iterations, int use_tc, int clamp) {
       if (clamp && fa.robustifier != ORC_ROB_NONE) fa.robustifier = ORC_ROB_CLAMP; /* :193-199 */
       double Hs[36], bs[6];
       orc_iter_stats ss;
-      orc_linearize(dim, rs->ap->variable, &sl->fixed, &sl->moving, rs->fidx[s], S, &sl->finder, &fa, 0,
+      orc_linearize(dim, rs->ap->variable, &sl->fixed, &sl->moving, rs->fidx[s], S, &sl->finder, &fa, 0, 0.f,
                     NULL, Hs, bs, &ss, rs->fstat[s], NULL);
       for (int k = 0; k < P * P; ++k) H[k] = H[k] + Hs[k];
       for (int k = 0; k < P; ++k) b[k] = b[k] + bs[k];

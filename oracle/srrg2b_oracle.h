@@ -114,7 +114,7 @@ int orc_scales(int dim, int64_t n_moving_global, float coord_bound, const orc_fi
 float orc_coord_bound(int dim, const orc_cloud* moving);
 int orc_linearize(int dim, int variable, const orc_cloud* fixed, const orc_cloud* moving,
                   const int32_t* fixed_idx_dense, const float* S, const orc_finder_params* fp,
-                  const orc_factor_params* fa, int64_t n_moving_global,
+                  const orc_factor_params* fa, int64_t n_moving_global, float coord_bound_global /* <=0: from moving */,
                   int64_t* acc /*[32] fixed point*/, double* H /*36 or 9 full row-major*/, double* b,
                   orc_iter_stats* stats, uint8_t* status_dense, float* chi_dense);
 

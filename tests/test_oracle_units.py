@@ -1,0 +1,212 @@
+"""CPU tests of the oracle itself (no GPU): exact NN vs independent implementations, analytic
+Jacobians vs finite differences, robustifiers, deterministic math, order independence of the
+fixed-point sums, termination criterion restated in Python, sharded sums over gloo."""
+import math
+
+import numpy as np
+import pytest
+
+from srrg2_slam_interfaces_b200 import synthetic as syn
+
+
+def test_deterministic_math(oracle):
+    import ctypes as C
+    L = oracle.lib()
+    s, c = C.c_double(), C.c_double()
+    for x in np.concatenate([np.linspace(-20, 20, 2001), [1e-9, -1e-9, 1e3, -777.7]]):
+        L.orc_sincos(float(x), C.byref(s), C.byref(c))
+        assert abs(s.value - math.sin(x)) < 4e-16 * max(1, abs(x)) and abs(c.value - math.cos(x)) < 4e-16 * max(1, abs(x))
+    rng = np.random.default_rng(1)
+    for y, x in rng.normal(size=(500, 2)):
+        assert abs(L.orc_atan2(float(y), float(x)) - math.atan2(y, x)) < 2e-15
+    for x in np.exp(rng.uniform(-30, 30, size=500)):
+        assert abs(L.orc_log(float(x)) - math.log(x)) < 1e-14 * max(1, abs(math.log(x)))
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_nn_bruteforce_kdtree_scipy_agree(oracle, dim):
+    from scipy.spatial import cKDTree
+    rng = np.random.default_rng(5)
+    nf, nm = 3000, 2500
+    f = rng.uniform(-2, 2, size=(nf, dim)).astype(np.float32)
+    m = rng.uniform(-2.2, 2.2, size=(nm, dim)).astype(np.float32)
+    f[100:110] = f[50:60]  # exact duplicates: the tie must go to the lowest index
+    fv = (rng.uniform(size=nf) < 0.9).astype(np.uint8)
+    mv = (rng.uniform(size=nm) < 0.9).astype(np.uint8)
+    F, M = oracle.CloudRef(f, None, fv), oracle.CloudRef(m, None, mv)
+    S = syn.iso3([0.1, 0.05, -0.02], [0.01, 0.02, 0.03]) if dim == 3 else syn.iso2(0.1, 0.05, 0.03)
+    fp = oracle.finder_params(0.25, -2.0)
+    a = oracle.find(oracle.Index(F, oracle.NN_BRUTE), F, M, S, fp)
+    b = oracle.find(oracle.Index(F, oracle.NN_KDTREE), F, M, S, fp)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    assert np.all(a[0][mv == 0] == -1)
+    assert not np.any(np.isin(a[0][a[0] >= 0], np.arange(100, 110)[fv[50:60] == 1]))  # duplicates lose the tie
+    # independent check: scipy on the valid subset, in float64, away from ties / the radius edge
+    valid_idx = np.nonzero(fv)[0]
+    tree = cKDTree(f[valid_idx].astype(np.float64))
+    q = (m.astype(np.float64) @ S[:dim, :dim].T + S[:dim, dim])
+    dd, ii = tree.query(q, k=2)
+    clear = (mv == 1) & (dd[:, 0] < 0.249) & (dd[:, 1] - dd[:, 0] > 1e-5)
+    assert np.array_equal(valid_idx[ii[clear, 0]], a[0][clear])
+    assert np.allclose(dd[clear, 0], a[1][clear], rtol=0, atol=1e-5)
+    far = (mv == 1) & (dd[:, 0] > 0.251)
+    assert np.all(a[0][far] == -1)
+
+
+def test_nn_edge_cases(oracle):
+    fp = oracle.finder_params(0.5, -2.0)
+    F = oracle.CloudRef(np.zeros((0, 3), np.float32))
+    M = oracle.CloudRef(np.zeros((4, 3), np.float32))
+    fi, rs = oracle.find(oracle.Index(F), F, M, np.eye(4), fp)
+    assert np.all(fi == -1)
+    F = oracle.CloudRef(np.array([[0, 0, 0.4]], np.float32))
+    fi, rs = oracle.find(oracle.Index(F), F, M, np.eye(4), fp)
+    assert np.all(fi == 0) and np.allclose(rs, 0.4)
+    M0 = oracle.CloudRef(np.zeros((0, 3), np.float32))
+    fi, rs = oracle.find(oracle.Index(F), F, M0, np.eye(4), fp)
+    assert fi.size == 0
+
+
+def _chi_at(oracle, F, M, fidx, S, fp, fa, variable):
+    r = oracle.linearize(F, M, fidx, S, fp, fa, variable=variable, want_status=False)
+    return r["stats"]["chi_inliers"] + r["stats"]["chi_outliers"], r
+
+
+@pytest.mark.parametrize("dim,variable", [(3, 0), (3, 1), (2, 0)])
+@pytest.mark.parametrize("factor", ["P2P", "PLANE"])
+def test_jacobians_against_finite_differences(oracle, dim, variable, factor):
+    """b must be half the gradient of chi^2 and H its Gauss-Newton Hessian under X <- X * v2t(dx)."""
+    import ctypes as C
+    d = syn.make_icp3d(400, 400, seed=11, outlier_frac=0.0, cube=4.0, n_planes=6, n_spheres=2) if dim == 3 \
+        else syn.make_icp2d(400, seed=12, half=3.0)
+    F = oracle.CloudRef(d["fixed"], d["fixed_normals"])
+    M = oracle.CloudRef(d["moving"], d["moving_normals"])
+    fp = oracle.finder_params(1.0, -2.0)
+    fa = oracle.factor_params(getattr(oracle, "FACTOR_" + factor), oracle.ROB_NONE, 1.0, 3.0, 0.7)
+    S = d["T_star"].astype(np.float32)
+    fidx, _ = oracle.find(oracle.Index(F), F, M, S, fp)
+    chi0, r0 = _chi_at(oracle, F, M, fidx, S, fp, fa, variable)
+    P = 6 if dim == 3 else 3
+    L = oracle.lib()
+    L.orc_v2t.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    eps = 2e-3
+    grad = np.zeros(P)
+    for i in range(P):
+        vals = []
+        for sgn in (+1, -1):
+            v = np.zeros(6, dtype=np.float32)
+            v[i] = sgn * eps
+            D = np.zeros((dim + 1, dim + 1), dtype=np.float32)
+            L.orc_v2t(dim, variable, v.ctypes.data, D.ctypes.data)
+            Sp = (S.astype(np.float64) @ D.astype(np.float64)).astype(np.float32)
+            vals.append(_chi_at(oracle, F, M, fidx, Sp, fp, fa, variable)[0])
+        grad[i] = (vals[0] - vals[1]) / (2 * eps)
+    scale = np.sqrt(np.diag(r0["H"]) * max(chi0, 1e-9))
+    assert np.all(np.abs(grad - 2 * r0["b"]) < 2e-2 * scale + 1e-3), (grad, 2 * r0["b"])
+    assert np.allclose(r0["H"], r0["H"].T) and np.all(np.linalg.eigvalsh(r0["H"]) > 0)
+
+
+def test_robustifier_known_answers(oracle):
+    """One correspondence, P2P, e = (0.3, 0, 0) => chi = w*0.09 with info 1."""
+    F = oracle.CloudRef(np.array([[0, 0, 0]], np.float32), np.array([[0, 0, 1]], np.float32))
+    M = oracle.CloudRef(np.array([[0.3, 0, 0]], np.float32), np.array([[0, 0, 1]], np.float32))
+    fp = oracle.finder_params(1.0, -2.0)
+    fidx = np.array([0], np.int32)
+    chi, tau = 0.3 ** 2, 0.01
+    base = oracle.linearize(F, M, fidx, np.eye(4), fp, oracle.factor_params(oracle.FACTOR_P2P, oracle.ROB_NONE, tau))
+    assert base["stats"]["num_inliers"] == 1 and abs(base["stats"]["chi_inliers"] - chi) < 1e-7
+    h00 = base["H"][0, 0]
+    expect = {oracle.ROB_HUBER: (math.sqrt(tau / chi), 2 * math.sqrt(tau * chi) - tau),
+              oracle.ROB_CAUCHY: (1 / (1 + chi / tau), tau * math.log(1 + chi / tau)),
+              oracle.ROB_CLAMP: (0.0, tau), oracle.ROB_SATURATED: (0.0, tau)}
+    for rob, (w, rho) in expect.items():
+        r = oracle.linearize(F, M, fidx, np.eye(4), fp, oracle.factor_params(oracle.FACTOR_P2P, rob, tau))
+        assert r["stats"]["num_outliers"] == 1 and r["stats"]["num_inliers"] == 0
+        assert r["status"][0] == oracle.STAT_KERNELIZED
+        assert abs(r["stats"]["chi_outliers"] - rho) < 1e-6, (rob, r["stats"]["chi_outliers"], rho)
+        assert abs(r["H"][0, 0] - w * h00) < 1e-5 * max(1.0, h00)
+    # below the threshold every robustifier leaves the factor untouched (status Inlier)
+    r = oracle.linearize(F, M, fidx, np.eye(4), fp, oracle.factor_params(oracle.FACTOR_P2P, oracle.ROB_HUBER, 1.0))
+    assert r["stats"]["num_inliers"] == 1 and np.array_equal(r["H"], base["H"])
+
+
+def test_sums_are_order_independent(oracle):
+    d = syn.make_icp3d(30000, 30000, seed=4)
+    F = oracle.CloudRef(d["fixed"], d["fixed_normals"])
+    M = oracle.CloudRef(d["moving"], d["moving_normals"])
+    fp = oracle.finder_params(0.3, 0.8)
+    fa = oracle.factor_params(oracle.FACTOR_PLANE, oracle.ROB_HUBER, 0.01)
+    fidx, _ = oracle.find(oracle.Index(F), F, M, np.eye(4), fp)
+    accs = []
+    for t in (1, 3, 8):
+        oracle.set_threads(t)
+        accs.append(oracle.linearize(F, M, fidx, np.eye(4), fp, fa)["acc"])
+    oracle.set_threads(8)
+    assert np.array_equal(accs[0], accs[1]) and np.array_equal(accs[0], accs[2])
+    # permuting the moving cloud permutes the terms but not the integer sums
+    perm = np.random.default_rng(0).permutation(M.n)
+    Mp = oracle.CloudRef(d["moving"][perm], d["moving_normals"][perm])
+    fidx_p, _ = oracle.find(oracle.Index(F), F, Mp, np.eye(4), fp)
+    assert np.array_equal(fidx_p, fidx[perm])
+    assert np.array_equal(oracle.linearize(F, Mp, fidx_p, np.eye(4), fp, fa)["acc"], accs[0])
+
+
+def _has_to_stop_py(history, ncorr_hist, ap):
+    """aligner_termination_criteria_impl.cpp:24-65 restated on the full history (window = last w samples)."""
+    w = ap.window_size
+    samples = [(nc, s["num_inliers"], s["num_outliers"], np.float32(s["chi_inliers"]) / np.float32(s["num_inliers"]))
+               for nc, s in zip(ncorr_hist, history) if s["num_inliers"]]
+    if not history[-1]["num_inliers"] or len(samples) < w:
+        return False
+    win = samples[-w:]
+    rng = lambda k: max(x[k] for x in win) - min(x[k] for x in win)
+    if rng(2) > ap.num_correspondences_range:  # quirk :46
+        return False
+    if rng(1) > ap.num_inliers_range:
+        return False
+    chi_rng = np.float32(max(x[3] for x in win)) - np.float32(min(x[3] for x in win))
+    if chi_rng > ap.num_outliers_range:  # quirk :53
+        return False
+    return not (chi_rng / np.float32(max(x[3] for x in win)) > np.float32(ap.chi_epsilon))
+
+
+def test_termination_criterion_matches_python_restatement(oracle):
+    d = syn.make_icp3d(8000, 8000, seed=9)
+    F = oracle.CloudRef(d["fixed"], d["fixed_normals"])
+    M = oracle.CloudRef(d["moving"], d["moving_normals"])
+    sl = [oracle.make_slice(F, M, None, oracle.finder_params(0.5, 0.8),
+                            oracle.factor_params(oracle.FACTOR_PLANE, oracle.ROB_HUBER, 0.02))]
+    kw = dict(max_iterations=40, min_num_inliers=10, window_size=4, num_correspondences_range=60,
+              num_inliers_range=60, num_outliers_range=60, chi_epsilon=0.05)
+    free = oracle.icp_run(3, sl, oracle.aligner_params(**kw), np.eye(4))
+    ap = oracle.aligner_params(use_termination_criteria=True, **kw)
+    stopped = oracle.icp_run(3, sl, ap, np.eye(4))
+    assert len(free["stats"]) == 40
+    expected = 40
+    for k in range(1, 41):
+        hist = free["stats"][:k]
+        if _has_to_stop_py(hist, [s["num_correspondences"] for s in hist], ap):
+            expected = k
+            break
+    assert 4 <= expected < 40, expected
+    assert len(stopped["stats"]) == expected
+    assert stopped["stats"] == free["stats"][:expected]
+
+
+def test_status_paths(oracle):
+    d = syn.make_icp3d(3000, 3000, seed=3)
+    F = oracle.CloudRef(d["fixed"], d["fixed_normals"])
+    M = oracle.CloudRef(d["moving"], d["moving_normals"])
+    fp, fa = oracle.finder_params(0.3, 0.8), oracle.factor_params()
+    far = syn.iso3([300.0, 0, 0], [0, 0, 0])
+    r = oracle.icp_run(3, [oracle.make_slice(F, M, None, fp, fa)], oracle.aligner_params(max_iterations=4), far)
+    assert r["status"] == 3 and len(r["stats"]) == 0 and np.array_equal(r["T"], far.astype(np.float32))  # Fail
+    r = oracle.icp_run(3, [oracle.make_slice(F, M, None, fp, fa)],
+                       oracle.aligner_params(max_iterations=4, min_num_inliers=10 ** 7), np.eye(4))
+    assert r["status"] == 2 and len(r["stats"]) == 4  # NotEnoughInliers
+    # a prior slice keeps the association "good" even with zero point correspondences
+    # (aligner_slice_processor_prior.h:65-67): the loop runs and ends in Success
+    pr = oracle.make_slice(prior_measurement=far, prior_info_diag=np.ones(6), dim=3)
+    r = oracle.icp_run(3, [oracle.make_slice(F, M, None, fp, fa), pr],
+                       oracle.aligner_params(max_iterations=3, min_num_inliers=0), np.eye(4))
+    assert r["status"] == 0 and len(r["stats"]) == 3 and r["stats"][0]["num_correspondences"] == 1
