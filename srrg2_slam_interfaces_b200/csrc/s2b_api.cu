@@ -92,7 +92,7 @@ struct SliceData {
   bool coord_bound_global = false;
   // correspondences in moving-sorted order
   DevBuf<int> c_fidx, c_fpos, far_list, far_count;
-  DevBuf<float> c_resp, c_chi;
+  DevBuf<float> c_resp, c_chi, c_lb, S_lb;
   DevBuf<unsigned char> c_stat;
   bool corr_valid = false, stat_valid = false;
   int prune_on_export = 0;
@@ -125,6 +125,7 @@ struct srrg2b_ctx {
   int last_iterations = 0;
   int sm_count = 148;
   // optional per-launch timing of the slice kernel (roofline measurement)
+  int track2_mode = 2;  // 0 never, 1 always, 2 automatic; env SRRG2B_TRACK2 overrides
   bool time_kernels = false;
   std::vector<cudaEvent_t> kev;
   size_t kev_used = 0;
@@ -214,6 +215,10 @@ int build_moving(srrg2b_ctx* c, SliceData& sd) {
   CK(c, sd.c_fpos.ensure((size_t) n));
   CK(c, sd.far_list.ensure((size_t) n));
   CK(c, sd.far_count.ensure(1));
+  CK(c, sd.c_lb.ensure((size_t) n));
+  CK(c, sd.S_lb.ensure(16));
+  if (n) CK(c, cudaMemsetAsync(sd.c_lb.p, 0, sizeof(float) * (size_t) n, c->stream));
+  CK(c, cudaMemsetAsync(sd.S_lb.p, 0, sizeof(float) * 16, c->stream));
   CK(c, sd.c_resp.ensure((size_t) n));
   CK(c, sd.c_chi.ensure((size_t) n));
   CK(c, sd.c_stat.ensure((size_t) n));
@@ -256,6 +261,12 @@ int build_moving(srrg2b_ctx* c, SliceData& sd) {
   return SRRG2B_OK;
 }
 
+// The cell edge is kCellSlack * max_distance / R: the (2R+1)^dim neighbourhood of a query's cell is
+// then guaranteed to cover a radius rho_s ~ 1.046 * max_distance, a little MORE than the accept
+// radius, so a search that finds nothing certifies 'no point within rho_s' and the verdict survives
+// small motions (temporal coherence, see s2b_icp.cuh).
+constexpr float kCellSlack = 1.05f;
+
 // k0: uniform grid over the fixed cloud with cell edge >= max_distance (so the 3^dim
 // neighbourhood of a query's cell contains every point within max_distance), cell-sorted float4 SoA
 int ensure_index(srrg2b_ctx* c, SliceData& sd, float max_distance) {
@@ -293,7 +304,7 @@ int ensure_index(srrg2b_ctx* c, SliceData& sd, float max_distance) {
   int dims[3] = {1, 1, 1};
   float cell = max_distance;
   for (;; --R) {
-    cell = max_distance * 1.001f / (float) R;
+    cell = max_distance * kCellSlack / (float) R;
     double total = 1.0;
     bool fits = true;
     for (int a = 0; a < dim; ++a) {
@@ -360,6 +371,7 @@ int ensure_index(srrg2b_ctx* c, SliceData& sd, float max_distance) {
     fill_int_kernel<<<blocks_for(sd.nm_valid, 256), 256, 0, c->stream>>>(sd.c_fpos.p, sd.nm_valid, -1);
     fill_int_kernel<<<blocks_for(sd.nm_valid, 256), 256, 0, c->stream>>>(sd.c_fidx.p, sd.nm_valid, -1);
     c->launches += 2;
+    CK(c, cudaMemsetAsync(sd.c_lb.p, 0, sizeof(float) * (size_t) sd.nm_valid, c->stream));
     sd.corr_valid = false;
   }
   CK(c, cudaGetLastError());
@@ -407,6 +419,13 @@ int fill_slice_args(srrg2b_ctx* c, SliceData& sd, int state_slot, const srrg2b_f
   a.S = c->d_state->S[state_slot].m;
   a.c_fpos = sd.c_fpos.p; a.c_resp = sd.c_resp.p;
   a.far_list = sd.far_list.p; a.far_count = sd.far_count.p;
+  a.c_lb = sd.c_lb.p; a.S_lb = sd.S_lb.p;
+  a.track2 = &c->d_state->track2[state_slot];
+  {
+    const float rho = ((float) sd.R - 4e-3f) / sd.inv_cell;
+    a.rho_s2 = rho * rho;
+    if (a.rho_s2 < a.md2) a.rho_s2 = a.md2;
+  }
   a.c_stat = want_status ? sd.c_stat.p : nullptr;
   a.c_chi = want_status ? sd.c_chi.p : nullptr;
   a.acc = c->d_state->acc[state_slot];
@@ -528,6 +547,13 @@ int make_plan(srrg2b_ctx* c, int n_slices, const srrg2b_slice* slices, const srr
     int rcode = fill_slice_args(c, c->slices[sl.slice_id], s, sl.finder, fa, ap.variable, want_status, plan.sargs[s], &sc);
     if (rcode) return rcode;
     plan.factor[s] = fa.factor;
+    {
+      SliceData& sdd = c->slices[sl.slice_id];
+      ss.S_lb = sdd.S_lb.p;
+      ss.cell = 1.f / sdd.inv_cell;
+      ss.coord_bound = sdd.coord_bound;
+      ss.track2_mode = c->track2_mode;
+    }
     ss.invH = ldexp(1.0, -sc.kH);
     ss.invb = ldexp(1.0, -sc.kb);
     ss.invchi = ldexp(1.0, -sc.kchi);
@@ -662,6 +688,7 @@ int srrg2b_ctx_create(int dim, int device, srrg2b_ctx** out) {
   srrg2b_ctx* c = new srrg2b_ctx();
   c->dim = dim;
   c->device = device;
+  if (const char* env = getenv("SRRG2B_TRACK2")) c->track2_mode = std::max(0, std::min(2, atoi(env)));
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
   bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
@@ -691,7 +718,7 @@ int srrg2b_ctx_destroy(srrg2b_ctx* c) {
     s.moving_raw.xyz.release(); s.moving_raw.nrm.release(); s.moving_raw.valid.release();
     s.f_pts.release(); s.f_nrm.release(); s.f_inverse.release(); s.cell_start.release();
     s.m_pts.release(); s.m_nrm.release(); s.m_inverse.release();
-    s.c_fidx.release(); s.c_fpos.release(); s.far_list.release(); s.far_count.release(); s.c_resp.release(); s.c_chi.release(); s.c_stat.release();
+    s.c_lb.release(); s.S_lb.release(); s.c_fidx.release(); s.c_fpos.release(); s.far_list.release(); s.far_count.release(); s.c_resp.release(); s.c_chi.release(); s.c_stat.release();
   }
   c->keys_a.release(); c->keys_b.release(); c->vals_a.release(); c->vals_b.release();
   c->flags.release(); c->positions.release(); c->bounds.release(); c->cub_tmp.release();
@@ -776,10 +803,12 @@ int srrg2b_find_correspondences(srrg2b_ctx* c, int slice_id, const float* S, con
   if (rcode) return rcode;
   Mat4f S4;
   embed(c->dim, S, S4);
-  set_S_kernel<<<1, 32, 0, c->stream>>>(c->d_state, 0, S4);
+  set_S_kernel<<<1, 32, 0, c->stream>>>(c->d_state, 0, S4, c->track2_mode == 1 ? 1 : 0);
   c->launches++;
   rcode = launch_find(c, a);
   if (rcode) return rcode;
+  commit_S_kernel<<<1, 32, 0, c->stream>>>(a.S, sd.S_lb.p);
+  c->launches++;
   CK(c, cudaGetLastError());
   sd.corr_valid = true;
   sd.stat_valid = false;
@@ -802,6 +831,7 @@ int srrg2b_set_correspondences(srrg2b_ctx* c, int slice_id, const int32_t* fixed
     fill_int_kernel<<<blocks_for(sd.nm_valid, 256), 256, 0, c->stream>>>(sd.c_fidx.p, sd.nm_valid, -1);
     fill_int_kernel<<<blocks_for(sd.nm_valid, 256), 256, 0, c->stream>>>(sd.c_fpos.p, sd.nm_valid, -1);
     c->launches += 2;
+    CK(c, cudaMemsetAsync(sd.c_lb.p, 0, sizeof(float) * (size_t) sd.nm_valid, c->stream));
   }
   if (n > 0) {
     CK(c, c->imp_f.ensure(n));
@@ -845,7 +875,7 @@ int srrg2b_linearize(srrg2b_ctx* c, int slice_id, const float* S, int variable, 
   a.sH = ldexp(1.0, sc.kH); a.sb = ldexp(1.0, sc.kb); a.sc = ldexp(1.0, sc.kchi);
   Mat4f S4;
   embed(c->dim, S, S4);
-  set_S_kernel<<<1, 32, 0, c->stream>>>(c->d_state, 0, S4);
+  set_S_kernel<<<1, 32, 0, c->stream>>>(c->d_state, 0, S4, 0);
   c->launches++;
   rcode = launch_linearize(c, a, fa->factor);
   if (rcode) return rcode;

@@ -29,6 +29,7 @@ struct DevState {
   Mat4f S[SRRG2B_MAX_SLICES];                // robot_in_sensor * X per slice (finder transform)
   unsigned long long acc[SRRG2B_MAX_SLICES][kAcc];
   long long ncorr[SRRG2B_MAX_SLICES];
+  int track2[SRRG2B_MAX_SLICES];             // NN searches of the next iteration certify bounds
   int stop;                                  // set on termination / bad association
   int n_stats;
   int not_enough_corr;
@@ -43,6 +44,9 @@ struct SolveSlice {
   Mat4f ris, Z;
   float info[6];
   double invH, invb, invchi;  // 2^-k of the slice's fixed-point scales
+  float* S_lb;                // slice's bound-validity transform (committed every iteration)
+  float cell, coord_bound;    // NN cell edge / max |coordinate| of the moving cloud
+  int track2_mode;            // 0 never, 1 always, 2 automatic (small motion)
 };
 
 struct SolveArgs {
@@ -73,6 +77,10 @@ struct SliceArgs {
   float* c_resp;
   int* far_list;   // phase-2 worklist of the NN search (query positions) and its counter
   int* far_count;
+  float* c_lb;         // certified lower bound per query (see nn kernels)
+  const float* S_lb;   // transform the bounds are valid for
+  const int* track2;   // device flag: searches track the second neighbour (certify bounds)
+  float rho_s2;        // squared radius the (2R+1) cell neighbourhood is guaranteed to cover
   unsigned char* c_stat;  // may be null
   float* c_chi;           // may be null
   unsigned long long* acc;
@@ -281,32 +289,49 @@ __constant__ signed char c_rows3[kRowTable][4];  // dy, dz, ring, 0   (3D)
 __constant__ signed char c_rows2[2 * kMaxR + 1][4];  // dy, 0, ring, 0 (2D)
 
 // shared pieces of the two NN kernels -----------------------------------------------------------
+//
+// Exact temporal coherence.  Besides its slot every query keeps a certified lower bound `lb`:
+//   slot holds a neighbour p0 : every OTHER fixed point is at least lb away from the query
+//   slot == -1 (none)         : EVERY fixed point is at least lb away
+// valid for the transform S_lb the bound was computed (or last refreshed) at.  At a new transform
+// the query moved by delta = |S m - S_lb m|, so by the triangle inequality the bound lb - delta still
+// holds; if d(q, p0) is strictly below it, p0 is the unique nearest neighbour and the search is
+// skipped -- same result as the full search, bit for bit (1e-5 relative slack covers the fp32
+// rounding of the distances).  Bounds come from searches that track the SECOND nearest point
+// (track2); the solve step switches that on once the per-iteration motion is small.
 struct NNQuery {
   float qx, qy, qz;      // transformed query
   float cfx;             // float cell coordinate along x
   int cx, cy, cz;        // integer cell
   float fry, frz;        // in-cell fractions along y, z
-  float bd2;             // best squared distance so far (starts at max_distance^2)
+  float bd2;             // best squared distance so far (starts at max_distance^2, accept radius)
+  float sd2;             // smallest squared distance of any OTHER examined point (starts at rho_s^2)
   int bidx, bpos;        // best original index / position in cell order
 };
 
-template <int DIM>
+template <int DIM, bool TRACK2>
 __device__ __forceinline__ void nn_consider(const SliceArgs& a, NNQuery& q, int p) {
+  if (TRACK2 && p == q.bpos) return;  // the warm-start candidate met again during the walk
   const float4 c = __ldg(a.fp + p);
   const float ddx = q.qx - c.x, ddy = q.qy - c.y, ddz = q.qz - c.z;
   float d2 = fmaf(ddy, ddy, ddx * ddx);
   if (DIM == 3) d2 = fmaf(ddz, ddz, d2);
   const int id = __float_as_int(c.w);
   if (d2 < q.bd2 || (d2 == q.bd2 && id < q.bidx)) {
+    if (TRACK2 && q.bpos >= 0) q.sd2 = fminf(q.sd2, q.bd2);
     q.bd2 = d2; q.bidx = id; q.bpos = p;
+  } else if (TRACK2) {
+    q.sd2 = fminf(q.sd2, d2);
   }
 }
 
-// scan the part of cell row (y, z) that can still hold a point with d2 <= bd2, given the
-// conservative squared distance lb2 between the query and the row's y/z slab
-template <int DIM>
+// scan the part of cell row (y, z) that can still matter, given the conservative squared distance
+// lb2 between the query and the row's y/z slab.  Pruning radius: bd2 (nearest only) or sd2 (two
+// nearest, needed to certify a bound).
+template <int DIM, bool TRACK2>
 __device__ __forceinline__ void nn_scan_row(const SliceArgs& a, NNQuery& q, int y, int z, float lb2) {
-  const float rr = __fsqrt_rn(fmaxf(q.bd2 - lb2, 0.f)) * a.inv_cell + 2e-3f;
+  const float pr2 = TRACK2 ? q.sd2 : q.bd2;
+  const float rr = __fsqrt_rn(fmaxf(pr2 - lb2, 0.f)) * a.inv_cell + 2e-3f;
   const int xa = max(max((int) floorf(q.cfx - rr), q.cx - a.R), 0);
   const int xb = min(min((int) floorf(q.cfx + rr), q.cx + a.R), a.nx - 1);
   if (xa > xb) return;
@@ -314,27 +339,38 @@ __device__ __forceinline__ void nn_scan_row(const SliceArgs& a, NNQuery& q, int 
   const int ps = __ldg(a.cell_start + row + xa);
   const int pe = __ldg(a.cell_start + row + xb + 1);
 #pragma unroll 1
-  for (int p = ps; p < pe; ++p) nn_consider<DIM>(a, q, p);
+  for (int p = ps; p < pe; ++p) nn_consider<DIM, TRACK2>(a, q, p);
+}
+
+template <int DIM>
+__device__ __forceinline__ void nn_transform(const float* S, const float4 m, float& x, float& y, float& z) {
+  float t;  // q = S m  (operation order is part of the numerics contract)
+  t = S[0] * m.x; t = fmaf(S[1], m.y, t); if (DIM == 3) t = fmaf(S[2], m.z, t); x = t + S[3];
+  t = S[4] * m.x; t = fmaf(S[5], m.y, t); if (DIM == 3) t = fmaf(S[6], m.z, t); y = t + S[7];
+  z = 0.f;
+  if (DIM == 3) { t = S[8] * m.x; t = fmaf(S[9], m.y, t); t = fmaf(S[10], m.z, t); z = t + S[11]; }
 }
 
 template <int DIM>
 __device__ __forceinline__ void nn_setup(const SliceArgs& a, const float* S, const float4 m, NNQuery& q) {
-  float t;  // q = S m  (operation order is part of the numerics contract)
-  t = S[0] * m.x; t = fmaf(S[1], m.y, t); if (DIM == 3) t = fmaf(S[2], m.z, t); q.qx = t + S[3];
-  t = S[4] * m.x; t = fmaf(S[5], m.y, t); if (DIM == 3) t = fmaf(S[6], m.z, t); q.qy = t + S[7];
-  q.qz = 0.f;
-  if (DIM == 3) { t = S[8] * m.x; t = fmaf(S[9], m.y, t); t = fmaf(S[10], m.z, t); q.qz = t + S[11]; }
+  nn_transform<DIM>(S, m, q.qx, q.qy, q.qz);
   q.cfx = cell_coord_f(q.qx, a.ox, a.inv_cell, a.nx);
   const float cfy = cell_coord_f(q.qy, a.oy, a.inv_cell, a.ny);
   const float cfz = (DIM == 3) ? cell_coord_f(q.qz, a.oz, a.inv_cell, a.nz) : 0.f;
   q.cx = (int) floorf(q.cfx); q.cy = (int) floorf(cfy); q.cz = (DIM == 3) ? (int) floorf(cfz) : 0;
   q.fry = cfy - (float) q.cy; q.frz = cfz - (float) q.cz;
-  q.bd2 = a.md2; q.bidx = INT_MAX; q.bpos = -1;
+  q.bd2 = a.md2; q.sd2 = a.rho_s2; q.bidx = INT_MAX; q.bpos = -1;
 }
 
-// normal gate + slot/response of a finished query
+__device__ __forceinline__ int slot_candidate(int slot) {
+  if (slot >= 0) return slot;
+  if (slot <= -2 && slot != kSlotSuppressed) return -(slot + 2);
+  return -1;
+}
+
+// normal gate + slot / response / bound of a finished query
 template <int DIM>
-__device__ __forceinline__ void nn_finish(const SliceArgs& a, const float* S, const NNQuery& q, int i) {
+__device__ __forceinline__ void nn_finish(const SliceArgs& a, const float* S, const NNQuery& q, int i, float lb) {
   int slot = -1;
   float resp = 0.f;
   if (q.bpos >= 0) {
@@ -357,31 +393,43 @@ __device__ __forceinline__ void nn_finish(const SliceArgs& a, const float* S, co
   }
   a.c_fpos[i] = slot;
   a.c_resp[i] = resp;
+  a.c_lb[i] = lb;
 }
 
-// Phase 1: warm start + the 3^(DIM-1) rows of rings 0 and 1, fully unrolled (row offsets are
-// compile-time constants, so the slab gaps are three registers per axis).  A query whose best
-// distance is still larger than the distance to ring 2 is handed to phase 2 through a worklist,
-// so that the rare expensive queries (outliers, large initial misalignment) do not serialise
-// the warps of the cheap ones.
-template <int DIM>
-__global__ void __launch_bounds__(256) nn_kernel(const SliceArgs a) {
-  if (*a.stop) return;
-  __shared__ float S[16];
-  if (threadIdx.x < 16) S[threadIdx.x] = a.S[threadIdx.x];
-  __syncthreads();
-  const float cell = __fdiv_rn(1.f, a.inv_cell);
-  const float ring2 = (a.R >= 2) ? (1.f - 2e-3f) * cell : 3.0e38f;
-  const float ring2_sq = (a.R >= 2) ? ring2 * ring2 : 3.0e38f;
-
+// Phase 1: temporal-coherence check, else warm start + the 3^(DIM-1) rows of rings 0 and 1 (each
+// lane walks only its own surviving rows).  A query whose best distance is still larger than the
+// distance to ring 2 is handed to phase 2 through a worklist, so that the rare expensive queries
+// (outliers, large initial misalignment) do not serialise the warps of the cheap ones.
+template <int DIM, bool TRACK2>
+__device__ __forceinline__ void nn_phase1_body(const SliceArgs& a, const float* S, const float* Slb, float cell,
+                                               float ring2, float ring2_sq) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.nm; i += gridDim.x * blockDim.x) {
     NNQuery q;
-    nn_setup<DIM>(a, S, a.mp[i], q);
-    if (a.warm) {  // previous iteration's neighbour: a real candidate, so exactness is untouched
-      int p0 = a.c_fpos[i];
-      if (p0 <= -2 && p0 != kSlotSuppressed) p0 = -(p0 + 2);
-      if (p0 >= 0) nn_consider<DIM>(a, q, p0);
+    const float4 m = a.mp[i];
+    nn_setup<DIM>(a, S, m, q);
+    const int p0 = slot_candidate(a.c_fpos[i]);
+    const float lb_old = a.c_lb[i];
+    if (lb_old > 0.f) {
+      float ox, oy, oz;
+      nn_transform<DIM>(Slb, m, ox, oy, oz);
+      const float ex = q.qx - ox, ey = q.qy - oy, ez = q.qz - oz;
+      const float delta = __fsqrt_rn(fmaf(ez, ez, fmaf(ey, ey, ex * ex)));
+      const float lbn = lb_old * (1.f - 1e-5f) - delta * (1.f + 1e-5f);
+      if (lbn > 0.f) {
+        if (p0 >= 0) {
+          nn_consider<DIM, false>(a, q, p0);
+          if (q.bpos >= 0 && q.bd2 * (1.f + 1e-5f) < lbn * lbn) {  // p0 is still the unique neighbour
+            nn_finish<DIM>(a, S, q, i, lbn);
+            continue;
+          }
+          q.bd2 = a.md2; q.bidx = INT_MAX; q.bpos = -1;
+        } else if (a.c_fpos[i] == -1 && lbn * lbn > a.md2 * (1.f + 1e-5f)) {  // still nothing in range
+          a.c_lb[i] = lbn;
+          continue;
+        }
+      }
     }
+    if (a.warm && p0 >= 0) nn_consider<DIM, TRACK2>(a, q, p0);  // a real candidate: exactness untouched
     // squared slab gaps for offsets -1 and +1 along y and z (offset 0 has gap 0)
     const float gym = fmaxf(q.fry - 2e-3f, 0.f) * cell, gyp = fmaxf(1.f - q.fry - 2e-3f, 0.f) * cell;
     const float gy2m = gym * gym, gy2p = gyp * gyp;
@@ -390,21 +438,23 @@ __global__ void __launch_bounds__(256) nn_kernel(const SliceArgs a) {
       const float gzm = fmaxf(q.frz - 2e-3f, 0.f) * cell, gzp = fmaxf(1.f - q.frz - 2e-3f, 0.f) * cell;
       gz2m = gzm * gzm; gz2p = gzp * gzp;
     }
-    // centre row first: it usually tightens bd2 enough to prune most of ring 1
-    if (q.cy >= 0 && q.cy < a.ny && q.cz >= 0 && q.cz < a.nz) nn_scan_row<DIM>(a, q, q.cy, q.cz, 0.f);
-    // ring 1: each lane walks only ITS OWN surviving rows (bit b = jz * 3 + jy), so a warp spends
-    // max-over-lanes(#surviving rows) iterations instead of all eight
+    // centre row first: it usually tightens the pruning radius enough to drop most of ring 1
+    if (q.cy >= 0 && q.cy < a.ny && q.cz >= 0 && q.cz < a.nz) nn_scan_row<DIM, TRACK2>(a, q, q.cy, q.cz, 0.f);
+    // ring 1: bit b = jz * 3 + jy marks a row this lane still has to visit
     unsigned mask = 0;
+    {
+      const float pr2 = TRACK2 ? q.sd2 : q.bd2;
 #pragma unroll
-    for (int jz = (DIM == 3 ? 0 : 1); jz < (DIM == 3 ? 3 : 2); ++jz) {
-      const int z = q.cz + jz - 1;
-      const bool zin = (z >= 0 && z < a.nz);
+      for (int jz = (DIM == 3 ? 0 : 1); jz < (DIM == 3 ? 3 : 2); ++jz) {
+        const int z = q.cz + jz - 1;
+        const bool zin = (z >= 0 && z < a.nz);
 #pragma unroll
-      for (int jy = 0; jy < 3; ++jy) {
-        if (jy == 1 && jz == 1) continue;
-        const int y = q.cy + jy - 1;
-        const float lb2 = (jy == 0 ? gy2m : (jy == 2 ? gy2p : 0.f)) + (jz == 0 ? gz2m : (jz == 2 ? gz2p : 0.f));
-        if (zin && y >= 0 && y < a.ny && !(lb2 > q.bd2)) mask |= 1u << (jz * 3 + jy);
+        for (int jy = 0; jy < 3; ++jy) {
+          if (jy == 1 && jz == 1) continue;
+          const int y = q.cy + jy - 1;
+          const float lb2 = (jy == 0 ? gy2m : (jy == 2 ? gy2p : 0.f)) + (jz == 0 ? gz2m : (jz == 2 ? gz2p : 0.f));
+          if (zin && y >= 0 && y < a.ny && !(lb2 > pr2)) mask |= 1u << (jz * 3 + jy);
+        }
       }
     }
     while (mask) {
@@ -412,37 +462,40 @@ __global__ void __launch_bounds__(256) nn_kernel(const SliceArgs a) {
       mask &= mask - 1;
       const int jz = (b * 11) >> 5, jy = b - 3 * jz;
       const float lb2 = (jy == 0 ? gy2m : (jy == 2 ? gy2p : 0.f)) + (jz == 0 ? gz2m : (jz == 2 ? gz2p : 0.f));
-      if (lb2 > q.bd2) continue;
-      nn_scan_row<DIM>(a, q, q.cy + jy - 1, q.cz + jz - 1, lb2);
+      if (lb2 > (TRACK2 ? q.sd2 : q.bd2)) continue;
+      nn_scan_row<DIM, TRACK2>(a, q, q.cy + jy - 1, q.cz + jz - 1, lb2);
     }
-    if (q.bd2 > ring2_sq) {
-      // not settled by rings 0-1: keep the provisional best as phase 2's warm start
-      a.c_fpos[i] = (q.bpos >= 0) ? -(q.bpos + 2) : -1;
+    if (q.bd2 > ring2_sq) {  // not settled by rings 0-1: phase 2 redoes this query with a whole warp
       const int w = atomicAdd(a.far_count, 1);
       a.far_list[w] = i;
       continue;
     }
-    nn_finish<DIM>(a, S, q, i);
+    // everything within min(sqrt(sd2), ring2) of the query has been examined
+    const float lb = TRACK2 ? fminf(__fsqrt_rn(q.sd2), ring2) * (1.f - 1e-5f) : 0.f;
+    nn_finish<DIM>(a, S, q, i, lb);
   }
 }
 
-// Phase 2: rings 2..R for the queries phase 1 could not settle (worklist).  These are few but
-// expensive (typically no neighbour at all, so nothing prunes), so one WARP takes one query: lane l
-// scans row K0 + l (+32, ...) against the provisional best, then a lexicographic (d2, index)
-// shuffle-min picks the winner and lane 0 applies the gate and writes the slot.
 template <int DIM>
-__global__ void __launch_bounds__(256) nn_far_kernel(const SliceArgs a) {
+__global__ void __launch_bounds__(256) nn_kernel(const SliceArgs a) {
   if (*a.stop) return;
-  __shared__ float S[16];
-  __shared__ int rows[kRowTable];
-  if (threadIdx.x < 16) S[threadIdx.x] = a.S[threadIdx.x];
-  const int R = a.R;
-  const int K = (DIM == 3) ? (2 * R + 1) * (2 * R + 1) : (2 * R + 1);
-  const int K0 = (DIM == 3) ? 9 : 3;  // rows of rings 0-1, done by phase 1
-  for (int k = threadIdx.x; k < K; k += blockDim.x)
-    rows[k] = (DIM == 3) ? *reinterpret_cast<const int*>(c_rows3[k]) : *reinterpret_cast<const int*>(c_rows2[k]);
+  __shared__ float S[16], Slb[16];
+  if (threadIdx.x < 16) { S[threadIdx.x] = a.S[threadIdx.x]; Slb[threadIdx.x] = a.S_lb[threadIdx.x]; }
   __syncthreads();
   const float cell = __fdiv_rn(1.f, a.inv_cell);
+  // distance below which a point cannot lie in ring 2 or beyond (for R == 1: the covered radius)
+  const float ring2 = (a.R >= 2) ? (1.f - 4e-3f) * cell : __fsqrt_rn(a.rho_s2);
+  const float ring2_sq = (a.R >= 2) ? ring2 * ring2 : 3.0e38f;
+  if (*a.track2) nn_phase1_body<DIM, true>(a, S, Slb, cell, ring2, ring2_sq);
+  else nn_phase1_body<DIM, false>(a, S, Slb, cell, ring2, ring2_sq);
+}
+
+// Phase 2: the queries phase 1 could not settle (worklist).  These are few but expensive
+// (typically no neighbour at all, so nothing prunes), so one WARP takes one query: lane l scans row
+// l (+32, ...) of the whole (2R+1)^(DIM-1) neighbourhood, then a shuffle reduction merges the
+// lanes' (nearest, second nearest) pairs and lane 0 applies the gate and writes slot and bound.
+template <int DIM, bool TRACK2>
+__device__ __forceinline__ void nn_far_body(const SliceArgs& a, const float* S, const int* rows, int K, float cell) {
   const int n_far = *a.far_count;
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
@@ -450,12 +503,9 @@ __global__ void __launch_bounds__(256) nn_far_kernel(const SliceArgs a) {
     const int i = a.far_list[w];
     NNQuery q;
     nn_setup<DIM>(a, S, a.mp[i], q);
-    {
-      int p0 = a.c_fpos[i];
-      if (p0 <= -2 && p0 != kSlotSuppressed) p0 = -(p0 + 2);
-      if (p0 >= 0) nn_consider<DIM>(a, q, p0);
-    }
-    for (int k = K0 + lane; k < K; k += 32) {
+    const int p0 = slot_candidate(a.c_fpos[i]);
+    if (a.warm && p0 >= 0) nn_consider<DIM, TRACK2>(a, q, p0);
+    for (int k = lane; k < K; k += 32) {
       const int e = rows[k];
       const int dy = (int) (signed char) (e & 0xff), dz = (int) (signed char) ((e >> 8) & 0xff);
       const int y = q.cy + dy, z = q.cz + dz;
@@ -466,20 +516,50 @@ __global__ void __launch_bounds__(256) nn_far_kernel(const SliceArgs a) {
         const float gz = axis_gap(dz, q.frz) * cell;
         lb2 = fmaf(gz, gz, lb2);
       }
-      if (lb2 > q.bd2) continue;
-      nn_scan_row<DIM>(a, q, y, z, lb2);
+      if (lb2 > (TRACK2 ? q.sd2 : q.bd2)) continue;
+      nn_scan_row<DIM, TRACK2>(a, q, y, z, lb2);
     }
 #pragma unroll
     for (int off = 16; off; off >>= 1) {
       const float od2 = __shfl_xor_sync(0xffffffffu, q.bd2, off);
+      const float os2 = __shfl_xor_sync(0xffffffffu, q.sd2, off);
       const int oidx = __shfl_xor_sync(0xffffffffu, q.bidx, off);
       const int opos = __shfl_xor_sync(0xffffffffu, q.bpos, off);
-      if (od2 < q.bd2 || (od2 == q.bd2 && oidx < q.bidx)) {
-        q.bd2 = od2; q.bidx = oidx; q.bpos = opos;
+      const bool other_wins = od2 < q.bd2 || (od2 == q.bd2 && oidx < q.bidx);
+      if (TRACK2) {
+        // the loser's best is a runner-up unless both lanes hold the same point (shared warm start)
+        float s = fminf(q.sd2, os2);
+        if (q.bpos >= 0 && opos >= 0 && q.bpos != opos) s = fminf(s, other_wins ? q.bd2 : od2);
+        q.sd2 = s;
       }
+      if (other_wins) { q.bd2 = od2; q.bidx = oidx; q.bpos = opos; }
     }
-    if (lane == 0) nn_finish<DIM>(a, S, q, i);
+    if (lane == 0) {
+      const float lb = TRACK2 ? __fsqrt_rn(q.sd2) * (1.f - 1e-5f) : 0.f;
+      nn_finish<DIM>(a, S, q, i, lb);
+    }
   }
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(256) nn_far_kernel(const SliceArgs a) {
+  if (*a.stop) return;
+  __shared__ float S[16];
+  __shared__ int rows[kRowTable];
+  if (threadIdx.x < 16) S[threadIdx.x] = a.S[threadIdx.x];
+  const int R = a.R;
+  const int K = (DIM == 3) ? (2 * R + 1) * (2 * R + 1) : (2 * R + 1);
+  for (int k = threadIdx.x; k < K; k += blockDim.x)
+    rows[k] = (DIM == 3) ? *reinterpret_cast<const int*>(c_rows3[k]) : *reinterpret_cast<const int*>(c_rows2[k]);
+  __syncthreads();
+  const float cell = __fdiv_rn(1.f, a.inv_cell);
+  if (*a.track2) nn_far_body<DIM, true>(a, S, rows, K, cell);
+  else nn_far_body<DIM, false>(a, S, rows, K, cell);
+}
+
+// S_lb <- S after a stand-alone find (inside the ICP loop the solve kernel does this)
+__global__ void commit_S_kernel(const float* S, float* S_lb) {
+  if (threadIdx.x < 16 && blockIdx.x == 0) S_lb[threadIdx.x] = S[threadIdx.x];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -786,6 +866,8 @@ __global__ void icp_init_kernel(const SolveArgs a, DevState* st, Mat4f T0, int a
     compose(a.sl[s].ris, st->X, st->S[s]);
     for (int k = 0; k < kAcc; ++k) st->acc[s][k] = 0ull;
     st->ncorr[s] = 0;
+    // the motion from the previous call's pose is unknown: certify bounds only when forced to
+    if (!keep_stats) st->track2[s] = (a.sl[s].track2_mode == 1) ? 1 : 0;
   }
   st->stop = 0;
   st->not_enough_corr = 0;
@@ -799,9 +881,10 @@ __global__ void icp_init_kernel(const SolveArgs a, DevState* st, Mat4f T0, int a
 }
 
 // set only the finder transform of one slice (stand-alone find / linearise entry points)
-__global__ void set_S_kernel(DevState* st, int slice, Mat4f S) {
+__global__ void set_S_kernel(DevState* st, int slice, Mat4f S, int track2) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     st->S[slice] = S;
+    st->track2[slice] = track2;
     for (int k = 0; k < kAcc; ++k) st->acc[slice][k] = 0ull;
     st->stop = 0;
   }
@@ -823,6 +906,10 @@ __global__ void icp_solve_kernel(const SolveArgs a, DevState* st) {
     sacc[k / kAcc][k % kAcc] = st->acc[k / kAcc][k % kAcc];
     st->acc[k / kAcc][k % kAcc] = 0ull;
   }
+  // the NN pass of this iteration certified its bounds at S: record that before anything can bail out
+  for (int k = 0; k < a.n_slices; ++k)
+    if (a.sl[k].kind == SRRG2B_SLICE_POINTS && a.sl[k].S_lb && threadIdx.x < 16)
+      a.sl[k].S_lb[threadIdx.x] = st->S[k].m[threadIdx.x];
   __syncthreads();
   if (threadIdx.x != 0) return;
   double H[P * P], b[P];
@@ -891,7 +978,28 @@ __global__ void icp_solve_kernel(const SolveArgs a, DevState* st) {
   }
   if (st->n_stats < kMaxStats) st->stats[st->n_stats] = s;
   st->n_stats += 1;
-  for (int k = 0; k < a.n_slices; ++k) compose(a.sl[k].ris, X, st->S[k]);
+  for (int k = 0; k < a.n_slices; ++k) {
+    Mat4f Sn;
+    compose(a.sl[k].ris, X, Sn);
+    if (a.sl[k].kind == SRRG2B_SLICE_POINTS) {
+      // upper bound of how far any query of the slice moves between this iteration and the next;
+      // when it is small against the cell edge the next NN pass certifies bounds (track2) so that
+      // later iterations can skip their searches
+      float dr = 0.f, dt = 0.f;
+      for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 3; ++c) {
+          const float d = Sn.m[r * 4 + c] - st->S[k].m[r * 4 + c];
+          dr += d * d;
+        }
+        const float d = Sn.m[r * 4 + 3] - st->S[k].m[r * 4 + 3];
+        dt += d * d;
+      }
+      const float motion = sqrtf(dr) * 1.7321f * a.sl[k].coord_bound + sqrtf(dt);
+      const int mode = a.sl[k].track2_mode;
+      st->track2[k] = (mode == 1) || (mode == 2 && motion < 0.125f * a.sl[k].cell) ? 1 : 0;
+    }
+    st->S[k] = Sn;
+  }
   if (a.use_tc && has_to_stop(st, a, s, total)) st->stop = 1;
 }
 

@@ -148,3 +148,39 @@ def test_not_enough_correspondences(oracle, capi):
     assert g["status"] == capi.ALIGNER_FAIL == o["status"]
     assert len(g["stats"]) == 0
     assert np.array_equal(g["T"], o["T"])
+
+
+@pytest.mark.parametrize("mode", ["0", "1", "2"])
+def test_temporal_coherence_modes_are_exact(oracle, capi, mode, monkeypatch):
+    """SRRG2B_TRACK2 = 0 (never certify bounds), 1 (always), 2 (automatic): the skip of the NN search
+    is an exact optimisation, so every mode must reproduce the oracle bit for bit -- including a
+    second compute() that starts from the previous run's bounds, and a 2D multi-iteration run."""
+    monkeypatch.setenv("SRRG2B_TRACK2", mode)
+    d = syn.make_icp3d(40000, 40000, seed=13)
+    kw = dict(max_iterations=14, min_num_inliers=10)
+    F = oracle.CloudRef(d["fixed"], d["fixed_normals"])
+    M = oracle.CloudRef(d["moving"], d["moving_normals"])
+    ofp, ofa = oracle.finder_params(0.3, 0.8), oracle.factor_params(oracle.FACTOR_PLANE, oracle.ROB_HUBER, 0.01)
+    ctx = capi.Context(3)
+    ctx.set_cloud(capi.FIXED, 0, d["fixed"], d["fixed_normals"])
+    ctx.set_cloud(capi.MOVING, 0, d["moving"], d["moving_normals"])
+    gsl = [capi.make_slice(3, 0, None, capi.finder_params(0.3, 0.8),
+                           capi.factor_params(capi.FACTOR_PLANE, capi.ROB_HUBER, 0.01))]
+    T0s = [np.eye(4), syn.iso3([0.09, -0.05, 0.08], np.deg2rad([1.4, -1.0, 1.9])), np.eye(4)]
+    for T0 in T0s:
+        o = oracle.icp_run(3, [oracle.make_slice(F, M, None, ofp, ofa)], oracle.aligner_params(**kw), T0)
+        g = ctx.icp_run(gsl, capi.aligner_params(**kw), T0)
+        _assert_same_run(o, g, ctx.get_correspondences(0, 40000))
+    # stand-alone finds interleaved with runs keep the bounds consistent
+    for S in (d["T_star"], d["T_star"] @ syn.iso3([1e-4, 0, 0], [0, 1e-5, 0]), np.eye(4)):
+        ofi, ors = oracle.find(oracle.Index(F), F, M, S, ofp)
+        fi, mi, rs = ctx.find_correspondences(0, S, capi.finder_params(0.3, 0.8), 40000)
+        gfi, grs = _dense_from_compact(40000, fi, mi, rs)
+        assert np.array_equal(gfi, ofi) and np.array_equal(grs, ors)
+    ctx.close()
+    d2 = syn.make_icp2d(20000, 15000, seed=3, paired=False)
+    o, g, corr = _run_both(oracle, capi, 2, d2, oracle.aligner_params(**kw), capi.aligner_params(**kw),
+                           oracle.finder_params(0.4, 0.8), capi.finder_params(0.4, 0.8),
+                           oracle.factor_params(oracle.FACTOR_P2P, oracle.ROB_SATURATED, 0.05),
+                           capi.factor_params(capi.FACTOR_P2P, capi.ROB_SATURATED, 0.05), np.eye(3))
+    _assert_same_run(o, g, corr)
