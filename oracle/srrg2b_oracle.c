@@ -361,7 +361,7 @@ static void apply_perturbation(int dim, int variable, const double* dx, float* X
 
 /* Cholesky solve of H dx = -b (H full row-major PxP). returns 1 on success */
 static int chol_solve(int P, const double* H, const double* b, double* dx) {
-  double L[36];
+  double L[36], inv[6]; /* inv[j] = 1 / L_jj: one division per column, the rest are products */
   memset(L, 0, sizeof(L));
   for (int j = 0; j < P; ++j) {
     double d = H[j * P + j];
@@ -373,12 +373,13 @@ static int chol_solve(int P, const double* H, const double* b, double* dx) {
     }
     double ljj = sqrt(d);
     L[j * P + j] = ljj;
+    inv[j] = 1.0 / ljj;
     for (int i = j + 1; i < P; ++i) {
       double s = H[i * P + j];
       for (int k = 0; k < j; ++k) {
         s = s - L[i * P + k] * L[j * P + k];
       }
-      L[i * P + j] = s / ljj;
+      L[i * P + j] = s * inv[j];
     }
   }
   double y[6];
@@ -387,14 +388,14 @@ static int chol_solve(int P, const double* H, const double* b, double* dx) {
     for (int k = 0; k < i; ++k) {
       s = s - L[i * P + k] * y[k];
     }
-    y[i] = s / L[i * P + i];
+    y[i] = s * inv[i];
   }
   for (int i = P - 1; i >= 0; --i) {
     double s = y[i];
     for (int k = i + 1; k < P; ++k) {
       s = s - L[k * P + i] * dx[k];
     }
-    dx[i] = s / L[i * P + i];
+    dx[i] = s * inv[i];
   }
   for (int i = 0; i < P; ++i) {
     if (!(dx[i] == dx[i]) || fabs(dx[i]) > 1e300) {

@@ -417,7 +417,8 @@ int fill_slice_args(srrg2b_ctx* c, SliceData& sd, int state_slot, const srrg2b_f
   a.rs = (c->dim == 3 && variable == SRRG2B_VAR_SE3_QUAT_RIGHT) ? 2.f : 1.f;
   a.sH = ldexp(1.0, sc.kH); a.sb = ldexp(1.0, sc.kb); a.sc = ldexp(1.0, sc.kchi);
   a.S = c->d_state->S[state_slot].m;
-  a.c_fpos = sd.c_fpos.p; a.c_resp = sd.c_resp.p;
+  a.c_fpos = sd.c_fpos.p;
+  a.gate_in_nn = 0;
   a.far_list = sd.far_list.p; a.far_count = sd.far_count.p;
   a.c_lb = sd.c_lb.p; a.S_lb = sd.S_lb.p;
   a.track2 = &c->d_state->track2[state_slot];
@@ -442,7 +443,7 @@ int launch_find(srrg2b_ctx* c, const SliceArgs& a) {
   else nn_kernel<2><<<blocks, threads, 0, c->stream>>>(a);
   c->launches++;
   if (a.R >= 2) {
-    const int fblocks = std::max(1, std::min(blocks_for((int64_t) a.nm * 32, threads), c->sm_count * 8));
+    const int fblocks = std::max(1, std::min(blocks_for((int64_t) a.nm * 32, threads), c->sm_count * 2));
     if (c->dim == 3) nn_far_kernel<3><<<fblocks, threads, 0, c->stream>>>(a);
     else nn_far_kernel<2><<<fblocks, threads, 0, c->stream>>>(a);
     c->launches++;
@@ -639,7 +640,7 @@ int export_corr(srrg2b_ctx* c, SliceData& sd, int prune, bool want_stat, int32_t
   CK(c, cudaMemsetAsync(c->flags.p, 0, sizeof(int) * n, c->stream));
   if (sd.nm_valid > 0) {
     export_dense_kernel<<<blocks_for(sd.nm_valid, 256), 256, 0, c->stream>>>(
-      sd.m_pts.p, sd.f_pts.p, sd.c_fpos.p, sd.c_fidx.p, sd.c_resp.p, sd.stat_valid ? sd.c_stat.p : nullptr, sd.stat_valid ? sd.c_chi.p : nullptr,
+      sd.m_pts.p, sd.f_pts.p, sd.c_fpos.p, sd.c_fidx.p, sd.S_lb.p, c->dim, sd.stat_valid ? sd.c_stat.p : nullptr, sd.stat_valid ? sd.c_chi.p : nullptr,
       sd.nm_valid, prune, c->d_fidx.p, c->d_resp.p, want_stat ? c->d_stat.p : nullptr, want_stat ? c->d_chi.p : nullptr,
       c->flags.p);
     c->launches++;
@@ -801,6 +802,7 @@ int srrg2b_find_correspondences(srrg2b_ctx* c, int slice_id, const float* S, con
   SliceArgs a;
   int rcode = fill_slice_args(c, sd, 0, *fp, fa, SRRG2B_VAR_SE3_QUAT_RIGHT, false, a, nullptr);
   if (rcode) return rcode;
+  a.gate_in_nn = 1;
   Mat4f S4;
   embed(c->dim, S, S4);
   set_S_kernel<<<1, 32, 0, c->stream>>>(c->d_state, 0, S4, c->track2_mode == 1 ? 1 : 0);
@@ -842,7 +844,7 @@ int srrg2b_set_correspondences(srrg2b_ctx* c, int slice_id, const int32_t* fixed
     CK(c, cudaMemsetAsync(c->imp_bad.p, 0, 4, c->stream));
     import_corr_kernel<<<blocks_for(n, 256), 256, 0, c->stream>>>(
       c->imp_f.p, c->imp_m.p, (int) n, sd.m_inverse.p, sd.f_inverse.p, (int) sd.moving_raw.n, (int) sd.fixed_raw.n,
-      (int) sd.moving_raw.index_offset, sd.c_fidx.p, sd.c_fpos.p, sd.c_resp.p, c->imp_bad.p);
+      (int) sd.moving_raw.index_offset, sd.c_fidx.p, sd.c_fpos.p, c->imp_bad.p);
     c->launches++;
   }
   CK(c, cudaGetLastError());
@@ -871,6 +873,7 @@ int srrg2b_linearize(srrg2b_ctx* c, int slice_id, const float* S, int variable, 
   }
   int rcode = fill_slice_args(c, sd, 0, fpl, *fa, variable, true, a, nullptr);
   if (rcode) return rcode;
+  a.gate = 0;  // the correspondences are taken as they are (gated by the finder or supplied by the caller)
   sc = choose_scales(sd.moving_raw.n_global, sd.coord_bound, fp->max_distance, fa->info_point, fa->info_normal);
   a.sH = ldexp(1.0, sc.kH); a.sb = ldexp(1.0, sc.kb); a.sc = ldexp(1.0, sc.kchi);
   Mat4f S4;

@@ -68,13 +68,13 @@ struct SliceArgs {
   int R;      // search radius in cells (cell edge = 1.001 * max_distance / R)
   int warm;   // c_fpos holds a valid candidate position per query (previous iteration's NN)
   float md2, normal_cos;
-  int gate;
+  int gate;        // apply the normal gate
+  int gate_in_nn;  // 1: the NN kernels gate and write responses (stand-alone find); 0: linearise gates
   int rob;
   float tau, ip, in_, rs;
   double sH, sb, sc;
   const float* S;
   int* c_fpos;
-  float* c_resp;
   int* far_list;   // phase-2 worklist of the NN search (query positions) and its counter
   int* far_count;
   float* c_lb;         // certified lower bound per query (see nn kernels)
@@ -368,31 +368,28 @@ __device__ __forceinline__ int slot_candidate(int slot) {
   return -1;
 }
 
-// normal gate + slot / response / bound of a finished query
+// slot / bound of a finished query.  Inside the ICP loop the normal gate is evaluated by the
+// lineariser (it has both normals in registers anyway); the stand-alone finder gates here.
 template <int DIM>
-__device__ __forceinline__ void nn_finish(const SliceArgs& a, const float* S, const NNQuery& q, int i, float lb) {
-  int slot = -1;
-  float resp = 0.f;
-  if (q.bpos >= 0) {
-    bool ok = true;
-    if (a.gate) {
-      const float4 nm = a.mn[i];
-      const float4 nf = __ldg(a.fn + q.bpos);
-      float t;
-      t = S[0] * nm.x; t = fmaf(S[1], nm.y, t); if (DIM == 3) t = fmaf(S[2], nm.z, t); const float nqx = t;
-      t = S[4] * nm.x; t = fmaf(S[5], nm.y, t); if (DIM == 3) t = fmaf(S[6], nm.z, t); const float nqy = t;
-      float dot = fmaf(nf.y, nqy, nf.x * nqx);
-      if (DIM == 3) {
-        t = S[8] * nm.x; t = fmaf(S[9], nm.y, t); t = fmaf(S[10], nm.z, t);
-        dot = fmaf(nf.z, t, dot);
-      }
-      ok = !(dot < a.normal_cos);
+__device__ __forceinline__ void nn_finish(const SliceArgs& a, const float* S, const NNQuery& q, int i, float lb,
+                                          int old_slot) {
+  int slot = q.bpos;
+  if (q.bpos >= 0 && a.gate && a.gate_in_nn) {
+    const float4 nm = a.mn[i];
+    const float4 nf = __ldg(a.fn + q.bpos);
+    float t;
+    t = S[0] * nm.x; t = fmaf(S[1], nm.y, t); if (DIM == 3) t = fmaf(S[2], nm.z, t); const float nqx = t;
+    t = S[4] * nm.x; t = fmaf(S[5], nm.y, t); if (DIM == 3) t = fmaf(S[6], nm.z, t); const float nqy = t;
+    float dot = fmaf(nf.y, nqy, nf.x * nqx);
+    if (DIM == 3) {
+      t = S[8] * nm.x; t = fmaf(S[9], nm.y, t); t = fmaf(S[10], nm.z, t);
+      dot = fmaf(nf.z, t, dot);
     }
-    slot = ok ? q.bpos : -(q.bpos + 2);
-    resp = ok ? __fsqrt_rn(q.bd2) : 0.f;
+    if (dot < a.normal_cos) slot = -(q.bpos + 2);
+  } else if (q.bpos >= 0 && a.gate && old_slot == -(q.bpos + 2)) {
+    slot = old_slot;  // same neighbour as before and it was gated out: the lineariser re-checks it
   }
-  a.c_fpos[i] = slot;
-  a.c_resp[i] = resp;
+  if (slot != old_slot) a.c_fpos[i] = slot;
   a.c_lb[i] = lb;
 }
 
@@ -407,7 +404,8 @@ __device__ __forceinline__ void nn_phase1_body(const SliceArgs& a, const float* 
     NNQuery q;
     const float4 m = a.mp[i];
     nn_setup<DIM>(a, S, m, q);
-    const int p0 = slot_candidate(a.c_fpos[i]);
+    const int old_slot = a.c_fpos[i];
+    const int p0 = slot_candidate(old_slot);
     const float lb_old = a.c_lb[i];
     if (lb_old > 0.f) {
       float ox, oy, oz;
@@ -419,11 +417,11 @@ __device__ __forceinline__ void nn_phase1_body(const SliceArgs& a, const float* 
         if (p0 >= 0) {
           nn_consider<DIM, false>(a, q, p0);
           if (q.bpos >= 0 && q.bd2 * (1.f + 1e-5f) < lbn * lbn) {  // p0 is still the unique neighbour
-            nn_finish<DIM>(a, S, q, i, lbn);
+            nn_finish<DIM>(a, S, q, i, lbn, old_slot);
             continue;
           }
           q.bd2 = a.md2; q.bidx = INT_MAX; q.bpos = -1;
-        } else if (a.c_fpos[i] == -1 && lbn * lbn > a.md2 * (1.f + 1e-5f)) {  // still nothing in range
+        } else if (old_slot == -1 && lbn * lbn > a.md2 * (1.f + 1e-5f)) {  // still nothing in range
           a.c_lb[i] = lbn;
           continue;
         }
@@ -472,7 +470,7 @@ __device__ __forceinline__ void nn_phase1_body(const SliceArgs& a, const float* 
     }
     // everything within min(sqrt(sd2), ring2) of the query has been examined
     const float lb = TRACK2 ? fminf(__fsqrt_rn(q.sd2), ring2) * (1.f - 1e-5f) : 0.f;
-    nn_finish<DIM>(a, S, q, i, lb);
+    nn_finish<DIM>(a, S, q, i, lb, old_slot);
   }
 }
 
@@ -495,15 +493,49 @@ __global__ void __launch_bounds__(256) nn_kernel(const SliceArgs a) {
 // l (+32, ...) of the whole (2R+1)^(DIM-1) neighbourhood, then a shuffle reduction merges the
 // lanes' (nearest, second nearest) pairs and lane 0 applies the gate and writes slot and bound.
 template <int DIM, bool TRACK2>
-__device__ __forceinline__ void nn_far_body(const SliceArgs& a, const float* S, const int* rows, int K, float cell) {
-  const int n_far = *a.far_count;
+__device__ __forceinline__ void nn_far_body(const SliceArgs& a, const float* S, const int* rows, int K, float cell,
+                                            int n_far) {
   const int lane = threadIdx.x & 31;
+  if (n_far > (a.nm >> 4)) {
+    // long worklist (large initial misalignment): one THREAD per query, rows nearest ring first
+    for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < n_far; w += gridDim.x * blockDim.x) {
+      const int i = a.far_list[w];
+      NNQuery q;
+      nn_setup<DIM>(a, S, a.mp[i], q);
+      const int old_slot = a.c_fpos[i];
+      const int p0 = slot_candidate(old_slot);
+      if (a.warm && p0 >= 0) nn_consider<DIM, TRACK2>(a, q, p0);
+      for (int k = 0; k < K; ++k) {
+        const int e = rows[k];
+        const int dy = (int) (signed char) (e & 0xff), dz = (int) (signed char) ((e >> 8) & 0xff);
+        const int ring = (e >> 16) & 0xff;
+        const float pr2 = TRACK2 ? q.sd2 : q.bd2;
+        if (ring >= 2) {  // every row of this and later rings is at least (ring - 1) cells away
+          const float g = ((float) (ring - 1) - 4e-3f) * cell;
+          if (g * g > pr2) break;
+        }
+        const int y = q.cy + dy, z = q.cz + dz;
+        if (y < 0 || y >= a.ny || z < 0 || z >= a.nz) continue;
+        const float gy = axis_gap(dy, q.fry) * cell;
+        float lb2 = gy * gy;
+        if (DIM == 3) {
+          const float gz = axis_gap(dz, q.frz) * cell;
+          lb2 = fmaf(gz, gz, lb2);
+        }
+        if (lb2 > pr2) continue;
+        nn_scan_row<DIM, TRACK2>(a, q, y, z, lb2);
+      }
+      nn_finish<DIM>(a, S, q, i, TRACK2 ? __fsqrt_rn(q.sd2) * (1.f - 1e-5f) : 0.f, old_slot);
+    }
+    return;
+  }
   const int warps_per_block = blockDim.x >> 5;
   for (int w = blockIdx.x * warps_per_block + (threadIdx.x >> 5); w < n_far; w += gridDim.x * warps_per_block) {
     const int i = a.far_list[w];
     NNQuery q;
     nn_setup<DIM>(a, S, a.mp[i], q);
-    const int p0 = slot_candidate(a.c_fpos[i]);
+    const int old_slot = a.c_fpos[i];
+    const int p0 = slot_candidate(old_slot);
     if (a.warm && p0 >= 0) nn_consider<DIM, TRACK2>(a, q, p0);
     for (int k = lane; k < K; k += 32) {
       const int e = rows[k];
@@ -534,16 +566,14 @@ __device__ __forceinline__ void nn_far_body(const SliceArgs& a, const float* S, 
       }
       if (other_wins) { q.bd2 = od2; q.bidx = oidx; q.bpos = opos; }
     }
-    if (lane == 0) {
-      const float lb = TRACK2 ? __fsqrt_rn(q.sd2) * (1.f - 1e-5f) : 0.f;
-      nn_finish<DIM>(a, S, q, i, lb);
-    }
+    if (lane == 0) nn_finish<DIM>(a, S, q, i, TRACK2 ? __fsqrt_rn(q.sd2) * (1.f - 1e-5f) : 0.f, old_slot);
   }
 }
 
 template <int DIM>
 __global__ void __launch_bounds__(256) nn_far_kernel(const SliceArgs a) {
-  if (*a.stop) return;
+  const int n_far = *a.far_count;
+  if (n_far == 0 || *a.stop) return;
   __shared__ float S[16];
   __shared__ int rows[kRowTable];
   if (threadIdx.x < 16) S[threadIdx.x] = a.S[threadIdx.x];
@@ -553,8 +583,8 @@ __global__ void __launch_bounds__(256) nn_far_kernel(const SliceArgs a) {
     rows[k] = (DIM == 3) ? *reinterpret_cast<const int*>(c_rows3[k]) : *reinterpret_cast<const int*>(c_rows2[k]);
   __syncthreads();
   const float cell = __fdiv_rn(1.f, a.inv_cell);
-  if (*a.track2) nn_far_body<DIM, true>(a, S, rows, K, cell);
-  else nn_far_body<DIM, false>(a, S, rows, K, cell);
+  if (*a.track2) nn_far_body<DIM, true>(a, S, rows, K, cell, n_far);
+  else nn_far_body<DIM, false>(a, S, rows, K, cell, n_far);
 }
 
 // S_lb <- S after a stand-alone find (inside the ICP loop the solve kernel does this)
@@ -619,23 +649,30 @@ __global__ void __launch_bounds__(256) linearize_kernel(const SliceArgs a) {
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
   int slot_n = (i < a.nm) ? a.c_fpos[i] : -1;
   float4 m_n = zero4, nm_n = zero4, f_n = zero4, nf_n = zero4;
-  if (slot_n >= 0) {
-    m_n = a.mp[i]; nm_n = a.mn[i];
-    f_n = __ldg(a.fp + slot_n); nf_n = __ldg(a.fn + slot_n);
+  {
+    const int pn = a.gate ? slot_candidate(slot_n) : slot_n;
+    if (pn >= 0) {
+      m_n = a.mp[i]; nm_n = a.mn[i];
+      f_n = __ldg(a.fp + pn); nf_n = __ldg(a.fn + pn);
+    }
   }
   int slot_nn = (i + stride < a.nm) ? a.c_fpos[i + stride] : -1;
   for (; i < a.nm; i += stride) {
-    const int bpos = slot_n;
+    const int slot = slot_n;
     const float4 m = m_n, nm = nm_n, f = f_n, nf = nf_n;
     // advance the pipeline
     slot_n = slot_nn;
-    if (slot_n >= 0) {
-      m_n = a.mp[i + stride]; nm_n = a.mn[i + stride];
-      f_n = __ldg(a.fp + slot_n); nf_n = __ldg(a.fn + slot_n);
+    {
+      const int pn = a.gate ? slot_candidate(slot_n) : slot_n;  // gated-out slots are re-checked
+      if (pn >= 0) {
+        m_n = a.mp[i + stride]; nm_n = a.mn[i + stride];
+        f_n = __ldg(a.fp + pn); nf_n = __ldg(a.fn + pn);
+      }
     }
     slot_nn = (i + 2 * stride < a.nm) ? a.c_fpos[i + 2 * stride] : -1;
+    const int bpos = a.gate ? slot_candidate(slot) : slot;
     if (bpos < 0) {
-      if (bpos == kSlotSuppressed) {
+      if (slot == kSlotSuppressed) {
         ++n_sup;
         if (a.c_stat) a.c_stat[i] = SRRG2B_STAT_SUPPRESSED;
       } else if (a.c_stat) {
@@ -653,6 +690,16 @@ __global__ void __launch_bounds__(256) linearize_kernel(const SliceArgs a) {
     float nqz = 0.f;
     if (DIM == 3) { t = s20 * nm.x; t = fmaf(s21, nm.y, t); t = fmaf(s22, nm.z, t); nqz = t; }
 
+    if (a.gate) {  // normal gate of the finder, n_f . (R_S n_m) >= normal_cos
+      float dot = fmaf(nf.y, nqy, nf.x * nqx);
+      if (DIM == 3) dot = fmaf(nf.z, nqz, dot);
+      const bool ok = !(dot < a.normal_cos);
+      if (ok != (slot >= 0)) a.c_fpos[i] = ok ? bpos : -(bpos + 2);
+      if (!ok) {
+        if (a.c_stat) a.c_stat[i] = SRRG2B_STAT_NONE;
+        continue;
+      }
+    }
     // ---- error rows e, information om, Jacobian rows J (right perturbation of X) ----
     constexpr int E = (FACTOR == SRRG2B_FACTOR_P2P) ? DIM : DIM + 1;
     float e[E], om[E], J[E][P];
@@ -740,7 +787,7 @@ __global__ void __launch_bounds__(256) linearize_kernel(const SliceArgs a) {
 #pragma unroll
       for (int c = 0; c < P; ++c) u[r][c] = s * J[r][c];
     }
-    int slot = 0;
+    int hslot = 0;
 #pragma unroll
     for (int ii = 0; ii < P; ++ii) {
 #pragma unroll
@@ -750,7 +797,7 @@ __global__ void __launch_bounds__(256) linearize_kernel(const SliceArgs a) {
 #pragma unroll
           for (int r = 1; r < E; ++r) h = fmaf(u[r][ii], J[r][jj], h);
         }
-        aH[slot++] += to_fixed(h, a.sH);
+        aH[hslot++] += to_fixed(h, a.sH);
       }
     }
 #pragma unroll
@@ -1008,7 +1055,7 @@ __global__ void icp_solve_kernel(const SolveArgs a, DevState* st) {
 // ---------------------------------------------------------------------------------------------
 __global__ void export_dense_kernel(const float4* __restrict__ mp, const float4* __restrict__ fp,
                                     const int* __restrict__ c_fpos, const int* __restrict__ c_fidx,
-                                    const float* __restrict__ c_resp, const unsigned char* __restrict__ c_stat,
+                                    const float* __restrict__ S_lb, int dim, const unsigned char* __restrict__ c_stat,
                                     const float* __restrict__ c_chi, int nm, int prune, int* __restrict__ d_fidx,
                                     float* __restrict__ d_resp, unsigned char* __restrict__ d_stat,
                                     float* __restrict__ d_chi, int* __restrict__ d_flag) {
@@ -1022,7 +1069,18 @@ __global__ void export_dense_kernel(const float4* __restrict__ mp, const float4*
   const bool keep = (slot >= 0 || slot == kSlotSuppressed) && (!prune || (c_stat && c_stat[i] == SRRG2B_STAT_INLIER));
   d_flag[src] = keep ? 1 : 0;
   d_fidx[src] = fi;
-  d_resp[src] = c_resp[i];
+  float resp = 0.f;
+  if (slot >= 0) {  // response = |S m - f| at the transform of the last NN pass (pinned arithmetic)
+    const float4 m = mp[i];
+    const float4 f = fp[slot];
+    float qx, qy, qz;
+    if (dim == 3) nn_transform<3>(S_lb, m, qx, qy, qz); else nn_transform<2>(S_lb, m, qx, qy, qz);
+    const float ddx = qx - f.x, ddy = qy - f.y, ddz = qz - f.z;
+    float d2 = fmaf(ddy, ddy, ddx * ddx);
+    if (dim == 3) d2 = fmaf(ddz, ddz, d2);
+    resp = __fsqrt_rn(d2);
+  }
+  d_resp[src] = resp;
   if (d_stat) d_stat[src] = c_stat ? c_stat[i] : (unsigned char) SRRG2B_STAT_NONE;
   if (d_chi) d_chi[src] = c_chi ? c_chi[i] : 0.f;
 }
@@ -1046,7 +1104,7 @@ __global__ void compact_kernel(const int* __restrict__ flag, const int* __restri
 __global__ void import_corr_kernel(const int* __restrict__ fixed_idx, const int* __restrict__ moving_idx, int n,
                                    const int* __restrict__ m_inverse, const int* __restrict__ f_inverse, int nm_raw,
                                    int nf_raw, int index_offset, int* __restrict__ c_fidx, int* __restrict__ c_fpos,
-                                   float* __restrict__ c_resp, int* __restrict__ n_bad) {
+                                   int* __restrict__ n_bad) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
   const int mi = moving_idx[k] - index_offset, fi = fixed_idx[k];
@@ -1056,7 +1114,6 @@ __global__ void import_corr_kernel(const int* __restrict__ fixed_idx, const int*
   const int fpos = (fi >= 0 && fi < nf_raw) ? f_inverse[fi] : -1;
   c_fidx[mpos] = fi;
   c_fpos[mpos] = fpos >= 0 ? fpos : kSlotSuppressed;
-  c_resp[mpos] = 0.f;
 }
 
 }  // namespace s2b

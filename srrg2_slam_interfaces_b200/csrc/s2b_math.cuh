@@ -262,7 +262,7 @@ S2B_HD void fix_transform(int dim, Mat4f& X) {
 // Compile-time P and full unrolling keep L, y in registers on the device.
 template <int P>
 S2B_HD bool spd_solve_t(const double* H, const double* b, double* dx) {
-  double L[P * P];
+  double L[P * P], inv[P];  // inv[j] = 1 / L_jj: one division per column, the rest are products
 #pragma unroll
   for (int i = 0; i < P * P; ++i) L[i] = 0.0;
 #pragma unroll
@@ -273,12 +273,13 @@ S2B_HD bool spd_solve_t(const double* H, const double* b, double* dx) {
     if (!(d > 0.0) || !(d < 1e300)) return false;
     const double ljj = sqrt(d);
     L[j * P + j] = ljj;
+    inv[j] = 1.0 / ljj;
 #pragma unroll
     for (int i = j + 1; i < P; ++i) {
       double s = H[i * P + j];
 #pragma unroll
       for (int k = 0; k < j; ++k) s = s - L[i * P + k] * L[j * P + k];
-      L[i * P + j] = s / ljj;
+      L[i * P + j] = s * inv[j];
     }
   }
   double y[P];
@@ -287,14 +288,14 @@ S2B_HD bool spd_solve_t(const double* H, const double* b, double* dx) {
     double s = -b[i];
 #pragma unroll
     for (int k = 0; k < i; ++k) s = s - L[i * P + k] * y[k];
-    y[i] = s / L[i * P + i];
+    y[i] = s * inv[i];
   }
 #pragma unroll
   for (int i = P - 1; i >= 0; --i) {
     double s = y[i];
 #pragma unroll
     for (int k = i + 1; k < P; ++k) s = s - L[k * P + i] * dx[k];
-    dx[i] = s / L[i * P + i];
+    dx[i] = s * inv[i];
   }
 #pragma unroll
   for (int i = 0; i < P; ++i)

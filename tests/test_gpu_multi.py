@@ -1,0 +1,74 @@
+"""Multi-GPU parity (needs >= 2 CUDA devices, skipped otherwise): the moving cloud is sharded by
+rank, one NCCL all-reduce of the integer accumulators per iteration; every rank must end with the
+oracle's single-process pose / IterationStats bit for bit, and the per-rank correspondence lists
+concatenate to the oracle's list."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.gpu
+
+N_FIXED, N_MOVING, SEED = 60000, 50001, 17
+KW = dict(max_iterations=12, min_num_inliers=10)
+
+
+def _worker(rank, world, uid_q, out_q):
+    sys.path.insert(0, ROOT)
+    from srrg2_slam_interfaces_b200 import capi as A
+    from srrg2_slam_interfaces_b200 import synthetic as syn
+    from srrg2_slam_interfaces_b200.sharding import shard_range
+    d = syn.make_icp3d(N_FIXED, N_MOVING, seed=SEED)
+    ctx = A.Context(3, rank)
+    if rank == 0:
+        uid = ctx.unique_id()
+        for _ in range(world - 1):
+            uid_q.put(uid)
+    else:
+        uid = uid_q.get(timeout=60)
+    ctx.comm_init(uid, rank, world)
+    b, e = shard_range(N_MOVING, rank, world)
+    ctx.set_cloud(A.FIXED, 0, d["fixed"], d["fixed_normals"])
+    ctx.set_cloud(A.MOVING, 0, d["moving"][b:e], d["moving_normals"][b:e], index_offset=b, n_global=N_MOVING)
+    sl = [A.make_slice(3, 0, None, A.finder_params(0.3, 0.8), A.factor_params(A.FACTOR_PLANE, A.ROB_HUBER, 0.01))]
+    res = None
+    for _ in range(2):
+        res = ctx.icp_run(sl, A.aligner_params(**KW), np.eye(4))
+    corr = ctx.get_correspondences(0, e - b)
+    out_q.put((rank, res["T"], res["status"], res["stats"], corr))
+    ctx.close()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("world", [2])
+def test_sharded_run_equals_oracle(oracle, world):
+    from srrg2_slam_interfaces_b200 import synthetic as syn
+    ctx = mp.get_context("spawn")
+    uid_q, out_q = ctx.Queue(), ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, uid_q, out_q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = sorted([out_q.get(timeout=300) for _ in range(world)], key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    d = syn.make_icp3d(N_FIXED, N_MOVING, seed=SEED)
+    F = oracle.CloudRef(d["fixed"], d["fixed_normals"])
+    M = oracle.CloudRef(d["moving"], d["moving_normals"])
+    o = oracle.icp_run(3, [oracle.make_slice(F, M, None, oracle.finder_params(0.3, 0.8),
+                                             oracle.factor_params(oracle.FACTOR_PLANE, oracle.ROB_HUBER, 0.01))],
+                       oracle.aligner_params(**KW), np.eye(4))
+    for rank, T, status, stats, corr in results:
+        assert status == o["status"]
+        assert np.array_equal(T, o["T"])
+        assert stats == o["stats"]
+    fi = np.concatenate([r[4][0] for r in results])
+    mi = np.concatenate([r[4][1] for r in results])
+    rs = np.concatenate([r[4][2] for r in results])
+    assert np.array_equal(fi, o["correspondences"][0][0])
+    assert np.array_equal(mi, o["correspondences"][0][1])
+    assert np.array_equal(rs, o["correspondences"][0][2])
