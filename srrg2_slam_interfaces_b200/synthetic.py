@@ -170,3 +170,45 @@ def pose_error(T, T_ref):
     else:
         ang = float(abs(np.arctan2(E[1, 0], E[0, 0])))
     return ang, float(np.linalg.norm(E[:d, d]))
+
+
+# ----------------------------------------------------------------------------------------------
+# Config C5: 2D multi-cue -- two 1080-beam scanners (fixed side) vs a large local map (moving side)
+# ----------------------------------------------------------------------------------------------
+def corridor2d(seed, length=60.0, width=4.0, n_doors=10):
+    """Wall segments of a corridor world with side rooms: (start points, unit directions, lengths)."""
+    rng = np.random.default_rng([seed, 0xC55])
+    a = [[-length / 2, -width / 2], [-length / 2, width / 2]]
+    d = [[1.0, 0.0], [1.0, 0.0]]
+    ln = [length, length]
+    for k in range(n_doors):
+        x = rng.uniform(-length / 2 + 2, length / 2 - 2)
+        side = 1.0 if k % 2 else -1.0
+        depth = rng.uniform(2.0, 6.0)
+        w = rng.uniform(1.5, 4.0)
+        y0 = side * width / 2
+        for (sx, sy, dx, dy, l) in ((x, y0, 0.0, side, depth), (x + w, y0, 0.0, side, depth), (x, y0 + side * depth, 1.0, 0.0, w)):
+            a.append([sx, sy]); d.append([dx, dy]); ln.append(l)
+    a, d, ln = np.array(a), np.array(d), np.array(ln)
+    return a + 0.5 * ln[:, None] * d, d, ln  # centre form used by sample_walls2d
+
+
+def make_multicue2d(n_map, n_beams=1080, seed=5, T_star=None, noise=0.004):
+    """Two laser scans (fixed, in their sensor frames) against one local map (moving, robot/map
+    frame) + the sensor mounting poses.  The aligner estimate (map in robot) converges to T*."""
+    T_star = iso2(0.08, -0.05, np.deg2rad(1.5)) if T_star is None else T_star
+    walls = corridor2d(seed)
+    rm = np.random.default_rng([seed, 2])
+    mp, mn = sample_walls2d(walls, n_map, rm, 0.0)
+    mp = mp + rm.normal(scale=noise, size=mp.shape)
+    map_pts, map_nrm = transform_cloud(inv_iso(T_star), mp, mn)  # map expressed so that T* aligns it
+    sensors = [iso2(0.2, 0.0, np.deg2rad(90.0)), iso2(-0.2, 0.0, np.deg2rad(-90.0))]  # sensor in robot
+    scans = []
+    for k, sir in enumerate(sensors):
+        rs = np.random.default_rng([seed, 10 + k])
+        sp, sn = sample_walls2d(walls, 8 * n_beams, rs, 0.002)
+        keep = np.nonzero(np.abs(sp[:, 0]) < 12.0)[0][:n_beams]  # the scanner sees the world near the robot
+        sp, sn = sp[keep], sn[keep]
+        p, n = transform_cloud(inv_iso(sir), sp, sn)  # world(robot) -> sensor frame
+        scans.append(dict(points=p, normals=n, sensor_in_robot=sir, robot_in_sensor=inv_iso(sir)))
+    return dict(map=map_pts, map_normals=map_nrm, scans=scans, T_star=T_star)

@@ -184,3 +184,56 @@ def test_temporal_coherence_modes_are_exact(oracle, capi, mode, monkeypatch):
                            oracle.factor_params(oracle.FACTOR_P2P, oracle.ROB_SATURATED, 0.05),
                            capi.factor_params(capi.FACTOR_P2P, capi.ROB_SATURATED, 0.05), np.eye(3))
     _assert_same_run(o, g, corr)
+
+
+def test_multicue_2d_two_scanners_plus_odom_prior(oracle, capi):
+    """Config C5 shape at reduced size: 2 laser slices (robot_in_sensor != I) + odometry prior
+    (Omega = diag(100,100,100), aligner_slice_odometry_prior.h:20), local map on the moving side."""
+    d = syn.make_multicue2d(200000, n_beams=1080, seed=5)
+    n_map = d["map"].shape[0]
+    odom = syn.iso2(0.07, -0.04, np.deg2rad(1.2))
+    kw = dict(max_iterations=10, min_num_inliers=10)
+    ofp, ofa = oracle.finder_params(0.5, 0.7), oracle.factor_params(oracle.FACTOR_PLANE, oracle.ROB_CAUCHY, 0.05)
+    gfp, gfa = capi.finder_params(0.5, 0.7), capi.factor_params(capi.FACTOR_PLANE, capi.ROB_CAUCHY, 0.05)
+    M = oracle.CloudRef(d["map"], d["map_normals"])
+    osl, gsl = [], []
+    ctx = capi.Context(2)
+    keep = []
+    for k, sc in enumerate(d["scans"]):
+        F = oracle.CloudRef(sc["points"], sc["normals"])
+        keep.append(F)
+        osl.append(oracle.make_slice(F, M, sc["robot_in_sensor"], ofp, ofa, dim=2))
+        ctx.set_cloud(capi.FIXED, k, sc["points"], sc["normals"])
+        ctx.set_cloud(capi.MOVING, k, d["map"], d["map_normals"])
+        gsl.append(capi.make_slice(2, k, sc["robot_in_sensor"], gfp, gfa))
+    osl.append(oracle.make_slice(prior_measurement=odom, prior_info_diag=np.full(3, 100.0), dim=2))
+    gsl.append(capi.make_slice(2, prior_measurement=odom, prior_info_diag=np.full(3, 100.0)))
+    o = oracle.icp_run(2, osl, oracle.aligner_params(**kw), np.eye(3))
+    g = ctx.icp_run(gsl, capi.aligner_params(**kw), np.eye(3))
+    assert g["status"] == o["status"] == capi.ALIGNER_SUCCESS
+    assert g["stats"] == o["stats"]
+    assert np.array_equal(g["T"], o["T"])
+    for k in range(2):
+        c = ctx.get_correspondences(k, n_map)
+        oc = o["correspondences"][k]
+        assert np.array_equal(c[0], oc[0]) and np.array_equal(c[1], oc[1]) and np.array_equal(c[2], oc[2])
+    rot, trans = syn.pose_error(g["T"], d["T_star"])
+    assert rot < 5e-3 and trans < 3e-2
+    ctx.close()
+
+
+def test_prior_only_reference_kat_on_gpu(oracle, capi):
+    """The reference's own solver-level test (tests/test_motion_model_slice.cpp:81-85) through the CUDA path."""
+    rng = np.random.default_rng(0)
+    ctx = capi.Context(3)
+    for _ in range(5):
+        motion_prev = syn.iso3(rng.uniform(-1, 1, 3), rng.uniform(0, 6, 3)).astype(np.float32)
+        inv = syn.inv_iso(motion_prev.astype(np.float64)).astype(np.float32)
+        g = ctx.icp_run([capi.make_slice(3, prior_measurement=inv, prior_info_diag=np.ones(6))],
+                        capi.aligner_params(max_iterations=10, min_num_inliers=0), np.eye(4))
+        o = oracle.icp_run(3, [oracle.make_slice(prior_measurement=inv, prior_info_diag=np.ones(6), dim=3)],
+                           oracle.aligner_params(max_iterations=10, min_num_inliers=0), np.eye(4))
+        assert g["status"] == 0 and np.array_equal(g["T"], o["T"]) and g["stats"] == o["stats"]
+        rot, trans = syn.pose_error(g["T"].astype(np.float64) @ motion_prev.astype(np.float64), np.eye(4))
+        assert rot < 1e-5 and trans < 1e-5
+    ctx.close()
