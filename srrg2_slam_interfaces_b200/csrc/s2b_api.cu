@@ -84,6 +84,10 @@ struct SliceData {
   float ox = 0, oy = 0, oz = 0, inv_cell = 1;
   int nx = 1, ny = 1, nz = 1;
   int R = 1;  // cells per max_distance
+  // projective index (alternative to the grid): index image + SoA in original order
+  bool index_is_projective = false;
+  srrg2b_finder_params proj_params = {};
+  DevBuf<unsigned long long> image;
   // moving, Morton order
   DevBuf<float4> m_pts, m_nrm;
   DevBuf<int> m_inverse;
@@ -379,6 +383,59 @@ int ensure_index(srrg2b_ctx* c, SliceData& sd, float max_distance) {
   return SRRG2B_OK;
 }
 
+// k0p: projective index = index image of the fixed cloud + float4 SoA in original order
+int ensure_proj_index(srrg2b_ctx* c, SliceData& sd, const srrg2b_finder_params& fp) {
+  RawCloud& rc = sd.fixed_raw;
+  if (!rc.present) FAIL(c, SRRG2B_ERR_STATE, "fixed cloud not set for slice");
+  if (c->dim != 3) FAIL(c, SRRG2B_ERR_INVALID, "the projective finder needs dim == 3");
+  if (fp.width <= 0 || fp.height <= 0 || !(fp.fx > 0.f) || !(fp.fy > 0.f) || !(fp.max_distance > 0.f))
+    FAIL(c, SRRG2B_ERR_INVALID, "bad projective finder parameters");
+  const srrg2b_finder_params& o = sd.proj_params;
+  if (sd.index_is_projective && sd.built_for_max_distance > 0.f && o.fx == fp.fx && o.fy == fp.fy && o.cx == fp.cx &&
+      o.cy == fp.cy && o.width == fp.width && o.height == fp.height && o.min_depth == fp.min_depth &&
+      o.max_depth == fp.max_depth)
+    return SRRG2B_OK;
+  const int n = (int) rc.n;
+  const size_t npx = (size_t) fp.width * fp.height;
+  CK(c, sd.f_pts.ensure((size_t) n + 1));
+  CK(c, sd.f_nrm.ensure((size_t) n + 1));
+  CK(c, sd.f_inverse.ensure((size_t) n + 1));
+  CK(c, sd.image.ensure(npx));
+  CK(c, cudaMemsetAsync(sd.image.p, 0xff, npx * sizeof(unsigned long long), c->stream));
+  if (n > 0) {
+    gather_identity_kernel<<<blocks_for(n, 256), 256, 0, c->stream>>>(rc.xyz.p, rc.has_normals ? rc.nrm.p : nullptr, n,
+                                                                      c->dim, sd.f_pts.p, sd.f_nrm.p, sd.f_inverse.p);
+    proj_image_kernel<<<blocks_for(n, 256), 256, 0, c->stream>>>(rc.xyz.p, rc.has_valid ? rc.valid.p : nullptr, n, fp.fx,
+                                                                 fp.fy, fp.cx, fp.cy, fp.min_depth, fp.max_depth,
+                                                                 fp.width, fp.height, sd.image.p);
+    c->launches += 2;
+  }
+  sd.nf_valid = n;
+  sd.R = 1; sd.nx = sd.ny = sd.nz = 1; sd.inv_cell = 1.f / fp.max_distance;
+  if (sd.moving_raw.present && sd.nm_valid > 0) {
+    fill_int_kernel<<<blocks_for(sd.nm_valid, 256), 256, 0, c->stream>>>(sd.c_fpos.p, sd.nm_valid, -1);
+    fill_int_kernel<<<blocks_for(sd.nm_valid, 256), 256, 0, c->stream>>>(sd.c_fidx.p, sd.nm_valid, -1);
+    c->launches += 2;
+    CK(c, cudaMemsetAsync(sd.c_lb.p, 0, sizeof(float) * (size_t) sd.nm_valid, c->stream));
+    sd.corr_valid = false;
+  }
+  CK(c, cudaGetLastError());
+  sd.index_is_projective = true;
+  sd.proj_params = fp;
+  sd.built_for_max_distance = fp.max_distance;
+  return SRRG2B_OK;
+}
+
+int ensure_any_index(srrg2b_ctx* c, SliceData& sd, const srrg2b_finder_params& fp) {
+  if (fp.kind == SRRG2B_FINDER_PROJECTIVE) return ensure_proj_index(c, sd, fp);
+  if (fp.kind != SRRG2B_FINDER_NN) FAIL(c, SRRG2B_ERR_INVALID, "unknown finder kind");
+  if (sd.index_is_projective) {  // switching back to the grid: force a rebuild
+    sd.index_is_projective = false;
+    sd.built_for_max_distance = -1.f;
+  }
+  return ensure_index(c, sd, fp.max_distance);
+}
+
 int ensure_global_bound(srrg2b_ctx* c, SliceData& sd) {
   if (c->world <= 1 || sd.coord_bound_global) return SRRG2B_OK;
   CK(c, c->bounds.ensure(8));
@@ -394,8 +451,7 @@ int ensure_global_bound(srrg2b_ctx* c, SliceData& sd) {
 int fill_slice_args(srrg2b_ctx* c, SliceData& sd, int state_slot, const srrg2b_finder_params& fp,
                     const srrg2b_factor_params& fa, int variable, bool want_status, SliceArgs& a, Scales* sc_out) {
   if (!sd.moving_raw.present) FAIL(c, SRRG2B_ERR_STATE, "moving cloud not set for slice");
-  if (fp.kind != SRRG2B_FINDER_NN) FAIL(c, SRRG2B_ERR_INVALID, "finder kind not supported by this entry point");
-  int rcode = ensure_index(c, sd, fp.max_distance);
+  int rcode = ensure_any_index(c, sd, fp);
   if (rcode) return rcode;
   rcode = ensure_global_bound(c, sd);
   if (rcode) return rcode;
@@ -420,6 +476,9 @@ int fill_slice_args(srrg2b_ctx* c, SliceData& sd, int state_slot, const srrg2b_f
   a.c_fpos = sd.c_fpos.p;
   a.gate_in_nn = 0;
   a.far_list = sd.far_list.p; a.far_count = sd.far_count.p;
+  a.projective = fp.kind == SRRG2B_FINDER_PROJECTIVE ? 1 : 0;
+  a.fx = fp.fx; a.fy = fp.fy; a.pcx = fp.cx; a.pcy = fp.cy; a.min_depth = fp.min_depth; a.max_depth = fp.max_depth;
+  a.width = fp.width; a.height = fp.height; a.image = sd.image.p;
   a.c_lb = sd.c_lb.p; a.S_lb = sd.S_lb.p;
   a.track2 = &c->d_state->track2[state_slot];
   {
@@ -438,6 +497,11 @@ int launch_find(srrg2b_ctx* c, const SliceArgs& a) {
   if (a.nm <= 0) return SRRG2B_OK;
   const int threads = 256;
   const int blocks = std::max(1, std::min(blocks_for(a.nm, threads), c->sm_count * 8));
+  if (a.projective) {
+    proj_find_kernel<<<blocks, threads, 0, c->stream>>>(a);
+    c->launches++;
+    return SRRG2B_OK;
+  }
   CK(c, cudaMemsetAsync(a.far_count, 0, sizeof(int), c->stream));
   if (c->dim == 3) nn_kernel<3><<<blocks, threads, 0, c->stream>>>(a);
   else nn_kernel<2><<<blocks, threads, 0, c->stream>>>(a);
@@ -719,7 +783,7 @@ int srrg2b_ctx_destroy(srrg2b_ctx* c) {
     s.moving_raw.xyz.release(); s.moving_raw.nrm.release(); s.moving_raw.valid.release();
     s.f_pts.release(); s.f_nrm.release(); s.f_inverse.release(); s.cell_start.release();
     s.m_pts.release(); s.m_nrm.release(); s.m_inverse.release();
-    s.c_lb.release(); s.S_lb.release(); s.c_fidx.release(); s.c_fpos.release(); s.far_list.release(); s.far_count.release(); s.c_resp.release(); s.c_chi.release(); s.c_stat.release();
+    s.image.release(); s.c_lb.release(); s.S_lb.release(); s.c_fidx.release(); s.c_fpos.release(); s.far_list.release(); s.far_count.release(); s.c_resp.release(); s.c_chi.release(); s.c_stat.release();
   }
   c->keys_a.release(); c->keys_b.release(); c->vals_a.release(); c->vals_b.release();
   c->flags.release(); c->positions.release(); c->bounds.release(); c->cub_tmp.release();
@@ -779,6 +843,7 @@ int srrg2b_set_cloud(srrg2b_ctx* c, int slot, int slice_id, const srrg2b_cloud* 
     int rcode = upload_raw(c, sd.fixed_raw, cl);
     if (rcode) return rcode;
     sd.built_for_max_distance = -1.f;  // _fixed_changed_flag: rebuild the index on next use
+    sd.index_is_projective = false;
     sd.corr_valid = false;
     CK(c, cudaStreamSynchronize(c->stream));
     return SRRG2B_OK;
@@ -866,10 +931,10 @@ int srrg2b_linearize(srrg2b_ctx* c, int slice_id, const float* S, int variable, 
   SliceArgs a;
   Scales sc;
   srrg2b_finder_params fpl = *fp;
-  if (sd.built_for_max_distance > 0.f && fpl.kind == SRRG2B_FINDER_NN) {
-    // the index is only used for its sorted SoA here: do not rebuild it for a different gate
-    const float keep = sd.built_for_max_distance;
-    fpl.max_distance = keep;
+  if (sd.built_for_max_distance > 0.f) {
+    // the index is only used for its SoA here: do not rebuild it for a different gate / finder
+    if (sd.index_is_projective) fpl = sd.proj_params;
+    else { fpl.kind = SRRG2B_FINDER_NN; fpl.max_distance = sd.built_for_max_distance; }
   }
   int rcode = fill_slice_args(c, sd, 0, fpl, *fa, variable, true, a, nullptr);
   if (rcode) return rcode;

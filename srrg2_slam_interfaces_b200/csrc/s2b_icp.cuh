@@ -81,6 +81,11 @@ struct SliceArgs {
   const float* S_lb;   // transform the bounds are valid for
   const int* track2;   // device flag: searches track the second neighbour (certify bounds)
   float rho_s2;        // squared radius the (2R+1) cell neighbourhood is guaranteed to cover
+  // projective finder (srrg2_proslam cue): pinhole + index image of the fixed cloud
+  int projective;
+  float fx, fy, pcx, pcy, min_depth, max_depth;
+  int width, height;
+  const unsigned long long* image;  // per pixel: (depth bits << 32) | fixed index, ~0 = empty
   unsigned char* c_stat;  // may be null
   float* c_chi;           // may be null
   unsigned long long* acc;
@@ -585,6 +590,80 @@ __global__ void __launch_bounds__(256) nn_far_kernel(const SliceArgs a) {
   const float cell = __fdiv_rn(1.f, a.inv_cell);
   if (*a.track2) nn_far_body<DIM, true>(a, S, rows, K, cell, n_far);
   else nn_far_body<DIM, false>(a, S, rows, K, cell, n_far);
+}
+
+// ---------------------------------------------------------------------------------------------
+// k1p: projective association (a3 for the RGB-D cue).  The fixed cloud (sensor/camera frame) is
+// rendered into an index image: per pixel the point of smallest depth wins, lowest index on ties.
+// A moving point is transformed, projected, and associated with the pixel's point if it lies
+// within max_distance (then the usual normal gate).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool project_pixel(float x, float y, float z, float fx, float fy, float cx, float cy,
+                                              float min_depth, float max_depth, int width, int height, int& pix) {
+  if (!(z > min_depth) || !(z < max_depth)) return false;
+  const float u = fmaf(fx, __fdiv_rn(x, z), cx);
+  const float v = fmaf(fy, __fdiv_rn(y, z), cy);
+  const float uf = floorf(u + 0.5f), vf = floorf(v + 0.5f);
+  if (!(uf >= 0.f) || !(vf >= 0.f) || !(uf < (float) width) || !(vf < (float) height)) return false;
+  pix = (int) vf * width + (int) uf;
+  return true;
+}
+
+__global__ void proj_image_kernel(const float* __restrict__ xyz, const unsigned char* __restrict__ valid, int n,
+                                  float fx, float fy, float cx, float cy, float min_depth, float max_depth, int width,
+                                  int height, unsigned long long* __restrict__ image) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || (valid && !valid[i])) return;
+  const float x = xyz[(size_t) i * 3], y = xyz[(size_t) i * 3 + 1], z = xyz[(size_t) i * 3 + 2];
+  int pix;
+  if (!project_pixel(x, y, z, fx, fy, cx, cy, min_depth, max_depth, width, height, pix)) return;
+  const unsigned long long key = ((unsigned long long) __float_as_uint(z) << 32) | (unsigned) i;
+  atomicMin(&image[pix], key);
+}
+
+// float4 SoA in ORIGINAL order (position == index) for the projective finder
+__global__ void gather_identity_kernel(const float* __restrict__ xyz, const float* __restrict__ nrm, int n, int dim,
+                                       float4* __restrict__ op, float4* __restrict__ on, int* __restrict__ inverse) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 p;
+  p.x = xyz[(size_t) i * dim];
+  p.y = xyz[(size_t) i * dim + 1];
+  p.z = dim == 3 ? xyz[(size_t) i * dim + 2] : 0.f;
+  p.w = __int_as_float(i);
+  op[i] = p;
+  float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (nrm) {
+    q.x = nrm[(size_t) i * dim];
+    q.y = nrm[(size_t) i * dim + 1];
+    q.z = dim == 3 ? nrm[(size_t) i * dim + 2] : 0.f;
+  }
+  on[i] = q;
+  if (inverse) inverse[i] = i;
+}
+
+__global__ void __launch_bounds__(256) proj_find_kernel(const SliceArgs a) {
+  if (*a.stop) return;
+  __shared__ float S[16];
+  if (threadIdx.x < 16) S[threadIdx.x] = a.S[threadIdx.x];
+  __syncthreads();
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.nm; i += gridDim.x * blockDim.x) {
+    NNQuery q;
+    nn_transform<3>(S, a.mp[i], q.qx, q.qy, q.qz);
+    q.bd2 = a.md2; q.sd2 = a.md2; q.bidx = INT_MAX; q.bpos = -1;
+    int pix;
+    if (project_pixel(q.qx, q.qy, q.qz, a.fx, a.fy, a.pcx, a.pcy, a.min_depth, a.max_depth, a.width, a.height, pix)) {
+      const unsigned long long key = __ldg(a.image + pix);
+      if (key != ~0ull) {
+        const int idx = (int) (key & 0xffffffffull);
+        const float4 c = __ldg(a.fp + idx);
+        const float ddx = q.qx - c.x, ddy = q.qy - c.y, ddz = q.qz - c.z;
+        const float d2 = fmaf(ddz, ddz, fmaf(ddy, ddy, ddx * ddx));
+        if (d2 <= a.md2) { q.bd2 = d2; q.bidx = idx; q.bpos = idx; }
+      }
+    }
+    nn_finish<3>(a, S, q, i, 0.f, a.c_fpos[i]);
+  }
 }
 
 // S_lb <- S after a stand-alone find (inside the ICP loop the solve kernel does this)

@@ -212,3 +212,66 @@ def make_multicue2d(n_map, n_beams=1080, seed=5, T_star=None, noise=0.004):
         p, n = transform_cloud(inv_iso(sir), sp, sn)  # world(robot) -> sensor frame
         scans.append(dict(points=p, normals=n, sensor_in_robot=sir, robot_in_sensor=inv_iso(sir)))
     return dict(map=map_pts, map_normals=map_nrm, scans=scans, T_star=T_star)
+
+
+# ----------------------------------------------------------------------------------------------
+# Config C3: synthetic RGB-D sequence (pinhole depth images of a box room with boxes inside)
+# ----------------------------------------------------------------------------------------------
+def _ray_aabb(o, d, lo, hi):
+    """Slab intersection of rays o + t d with the box [lo, hi]: (t_near, t_far, axis_near, axis_far)."""
+    with np.errstate(divide="ignore", invalid="ignore"):
+        t1 = (lo - o) / d
+        t2 = (hi - o) / d
+    tmin, tmax = np.minimum(t1, t2), np.maximum(t1, t2)
+    return tmin.max(axis=1), tmax.min(axis=1), tmin.argmax(axis=1), tmax.argmin(axis=1)
+
+
+def render_depth_cloud(cam_in_world, width=640, height=480, fx=525.0, fy=525.0, cx=319.5, cy=239.5, seed=3,
+                       noise=0.0):
+    """Point+normal cloud (camera frame) of one depth image: 6-plane room + 3 boxes."""
+    rng = np.random.default_rng([seed, 0xD33])
+    room_lo, room_hi = np.array([-2.0, -1.4, -3.0]), np.array([2.0, 1.4, 4.0])  # side walls, floor, ceiling in view
+    boxes = []
+    for _ in range(3):
+        c = rng.uniform([-1.2, 0.4, 1.8], [1.2, 1.0, 3.2])
+        h = rng.uniform(0.2, 0.4, size=3)
+        boxes.append((c - h, c + h))
+    v, u = np.mgrid[0:height, 0:width]
+    rays_c = np.stack([(u.ravel() - cx) / fx, (v.ravel() - cy) / fy, np.ones(u.size)], axis=1)
+    R, o = cam_in_world[:3, :3], cam_in_world[:3, 3]
+    d = rays_c @ R.T
+    oo = np.broadcast_to(o, d.shape)
+    _, tfar, _, afar = _ray_aabb(oo, d, room_lo, room_hi)
+    t = tfar.copy()
+    nw = np.zeros_like(d)
+    nw[np.arange(d.shape[0]), afar] = -np.sign(d[np.arange(d.shape[0]), afar])  # inward room normals
+    for lo, hi in boxes:
+        tn, tf, an, _ = _ray_aabb(oo, d, lo, hi)
+        hit = (tn > 0) & (tn < tf) & (tn < t)
+        t[hit] = tn[hit]
+        nb = np.zeros_like(d)
+        nb[np.arange(d.shape[0]), an] = -np.sign(d[np.arange(d.shape[0]), an])
+        nw[hit] = nb[hit]
+    if noise > 0:
+        t = t + np.random.default_rng([seed, 0xD34, int(abs(o).sum() * 1e6) % 100000]).normal(scale=noise, size=t.shape)
+    pts_c = rays_c * t[:, None]
+    nrm_c = nw @ R  # world normal -> camera frame (R^T n)
+    valid = (np.isfinite(t) & (t > 0.1) & (t < 20.0)).astype(np.uint8)
+    pts_c[valid == 0] = 0.0
+    return pts_c.astype(np.float32), nrm_c.astype(np.float32), valid
+
+
+def make_rgbd_sequence(n_frames=30, width=640, height=480, seed=3, noise=0.001):
+    """Camera on a smooth path (<= 2 cm / 0.5 deg per frame); frame k's cloud is the fixed side and
+    frame k-1's cloud the moving side of aligner call k; ground truth moving-in-fixed = cam_k^-1 cam_{k-1}."""
+    s = width / 640.0
+    K = dict(fx=525.0 * s, fy=525.0 * s, cx=319.5 * s + (s - 1) * 0.5, cy=239.5 * s + (s - 1) * 0.5,
+             width=width, height=height)
+    frames = []
+    for k in range(n_frames):
+        a = 0.05 * k  # path parameter: <= 2 cm and <= 0.5 deg between consecutive frames
+        pose = iso3([0.3 * np.sin(a) + 0.004 * k, -0.2 + 0.1 * np.cos(1.5 * a), 0.012 * k],
+                    np.deg2rad([4.0 * np.sin(2 * a), 0.4 * k, 3.0 * np.cos(a)]))
+        p, n, v = render_depth_cloud(pose, width, height, K["fx"], K["fy"], K["cx"], K["cy"], seed, noise)
+        frames.append(dict(points=p, normals=n, valid=v, pose=pose))
+    return frames, K
