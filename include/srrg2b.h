@@ -166,6 +166,25 @@ int srrg2b_debug_info(srrg2b_ctx* ctx, int slice_id, int32_t* out16);
 int srrg2b_set_kernel_timing(srrg2b_ctx* ctx, int enable);
 int srrg2b_last_kernel_timing(srrg2b_ctx* ctx, float* slice_kernel_ms, int32_t* slice_kernel_launches);
 
+/* ---- a10: pose-graph Gauss-Newton, MultiGraphSLAM_::optimize() -> Solver::compute()
+ * (R/system/multi_graph_slam_impl.cpp:299-317).  Variables are SE(3) poses (row-major 4x4 float each),
+ * factors are SE3PosePoseGeodesicErrorFactor (R/registration/loop_closure.h:110-111): pair (i, j),
+ * measurement Z (4x4) and 6x6 information.  With a communicator the factor list is sharded over the
+ * ranks (every rank uploads the whole graph) and only H / b are all-reduced. ---- */
+typedef struct {
+  double chi;                   /* sum of e^T Omega e at the linearisation point */
+  double dx_norm_inf;           /* largest perturbation component applied */
+  double cg_relative_residual;  /* |H dx + b| / |b| reached by the linear solve */
+  int32_t cg_iterations;
+  int32_t num_factors;
+  int32_t num_blocks;           /* 6x6 blocks of the block-CSR system matrix */
+  float linearize_ms, solve_ms; /* device times of the two phases */
+} srrg2b_pgo_stats;
+int srrg2b_pgo_upload(srrg2b_ctx* ctx, int64_t n_vars, const float* poses16, const uint8_t* fixed_mask,
+                      int64_t n_factors, const int32_t* ij, const float* Z16, const float* Omega36);
+int srrg2b_pgo_iterate(srrg2b_ctx* ctx, int max_cg_iterations, double cg_tolerance, srrg2b_pgo_stats* stats);
+int srrg2b_pgo_download(srrg2b_ctx* ctx, float* poses16);
+
 #ifdef __cplusplus
 }
 #endif

@@ -25,6 +25,7 @@ EXPORTED_SYMBOLS = [
     "srrg2b_find_correspondences", "srrg2b_set_correspondences", "srrg2b_linearize", "srrg2b_icp_run",
     "srrg2b_icp_iterate", "srrg2b_get_correspondences", "srrg2b_last_run_timing",
     "srrg2b_set_kernel_timing", "srrg2b_last_kernel_timing", "srrg2b_debug_info",
+    "srrg2b_pgo_upload", "srrg2b_pgo_iterate", "srrg2b_pgo_download",
 ]
 
 
@@ -62,6 +63,15 @@ class IterStats(C.Structure):
     _fields_ = [("iteration", C.c_int32), ("solver_status", C.c_int32), ("num_inliers", C.c_int64),
                 ("num_outliers", C.c_int64), ("num_suppressed", C.c_int64), ("num_correspondences", C.c_int64),
                 ("chi_inliers", C.c_double), ("chi_outliers", C.c_double)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class PgoStats(C.Structure):
+    _fields_ = [("chi", C.c_double), ("dx_norm_inf", C.c_double), ("cg_relative_residual", C.c_double),
+                ("cg_iterations", C.c_int32), ("num_factors", C.c_int32), ("num_blocks", C.c_int32),
+                ("linearize_ms", C.c_float), ("solve_ms", C.c_float)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -109,6 +119,9 @@ def load_library():
     lib.srrg2b_get_correspondences.argtypes = [vp, C.c_int, vp, vp, vp, i64p]
     lib.srrg2b_last_run_timing.argtypes = [vp, C.POINTER(C.c_float), i32p]
     lib.srrg2b_debug_info.argtypes = [vp, C.c_int, vp]
+    lib.srrg2b_pgo_upload.argtypes = [vp, C.c_int64, vp, vp, C.c_int64, vp, vp, vp]
+    lib.srrg2b_pgo_iterate.argtypes = [vp, C.c_int, C.c_double, C.POINTER(PgoStats)]
+    lib.srrg2b_pgo_download.argtypes = [vp, vp]
     lib.srrg2b_set_kernel_timing.argtypes = [vp, C.c_int]
     lib.srrg2b_last_kernel_timing.argtypes = [vp, C.POINTER(C.c_float), i32p]
     _lib = lib
@@ -305,6 +318,27 @@ class Context:
         n = C.c_int32(0)
         self._check(self.lib.srrg2b_last_kernel_timing(self.h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+    # ---- a10: pose graph ----
+    def pgo_upload(self, poses, fixed, ij, Z, Omega):
+        poses = np.ascontiguousarray(poses, dtype=np.float32).reshape(-1, 16)
+        fixed = np.ascontiguousarray(fixed, dtype=np.uint8)
+        ij = np.ascontiguousarray(ij, dtype=np.int32).reshape(-1, 2)
+        Z = np.ascontiguousarray(Z, dtype=np.float32).reshape(-1, 16)
+        Omega = np.ascontiguousarray(Omega, dtype=np.float32).reshape(-1, 36)
+        self._pgo_n = poses.shape[0]
+        self._check(self.lib.srrg2b_pgo_upload(self.h, poses.shape[0], poses.ctypes.data, fixed.ctypes.data,
+                                               ij.shape[0], ij.ctypes.data, Z.ctypes.data, Omega.ctypes.data))
+
+    def pgo_iterate(self, max_cg_iterations=2000, cg_tolerance=1e-10):
+        st = PgoStats()
+        self._check(self.lib.srrg2b_pgo_iterate(self.h, max_cg_iterations, cg_tolerance, C.byref(st)))
+        return st.as_dict()
+
+    def pgo_download(self):
+        out = np.empty((self._pgo_n, 4, 4), dtype=np.float32)
+        self._check(self.lib.srrg2b_pgo_download(self.h, out.ctypes.data))
+        return out
 
     def last_run_timing(self):
         ms = C.c_float(0)

@@ -772,8 +772,11 @@ int srrg2b_ctx_create(int dim, int device, srrg2b_ctx** out) {
   return SRRG2B_OK;
 }
 
+static void pgo_release(srrg2b_ctx* c);
+
 int srrg2b_ctx_destroy(srrg2b_ctx* c) {
   if (!c) return SRRG2B_OK;
+  pgo_release(c);
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
@@ -1149,3 +1152,5 @@ int srrg2b_last_kernel_timing(srrg2b_ctx* c, float* slice_kernel_ms, int32_t* sl
 }
 
 }  // extern "C"
+
+#include "s2b_pgo_host.inl"

@@ -275,3 +275,110 @@ def make_rgbd_sequence(n_frames=30, width=640, height=480, seed=3, noise=0.001):
         p, n, v = render_depth_cloud(pose, width, height, K["fx"], K["fy"], K["cx"], K["cy"], seed, noise)
         frames.append(dict(points=p, normals=n, valid=v, pose=pose))
     return frames, K
+
+
+# ----------------------------------------------------------------------------------------------
+# Config C4: Manhattan-3D pose graph (lattice walk confined to a box so that places are revisited)
+# ----------------------------------------------------------------------------------------------
+def make_pose_graph3d(n_poses, n_factors, seed=4, box=(40, 40, 4), sigma_t=0.02, sigma_r_deg=0.5, max_loop_dist=2.0):
+    """Axis-aligned 1 m steps / 90 deg turns inside a box (reflecting walls); n_poses-1 odometry
+    factors + loop factors between poses within max_loop_dist; measurements = truth (+) noise,
+    Omega = diag(1/sigma^2); initial guess = integrated noisy odometry; pose 0 is the gauge."""
+    rng = np.random.default_rng([seed, 0xE44])
+    box = np.asarray(box)
+    dirs = np.array([[1, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0], [0, 0, 1], [0, 0, -1]])
+    pos = np.zeros((n_poses, 3), dtype=np.int64)
+    pos[0] = box // 2
+    heading = np.zeros(n_poses, dtype=np.int64)
+    steps = rng.integers(0, 6, size=n_poses)
+    keep_dir = rng.uniform(size=n_poses) < 0.7
+    for k in range(1, n_poses):
+        h = heading[k - 1] if keep_dir[k] else steps[k]
+        p = pos[k - 1] + dirs[h]
+        if np.any(p < 0) or np.any(p >= box):
+            h = h ^ 1
+            p = pos[k - 1] + dirs[h]
+            if np.any(p < 0) or np.any(p >= box):
+                h = int(steps[k]) % 4
+                p = np.clip(pos[k - 1] + dirs[h], 0, box - 1)
+        pos[k], heading[k] = p, h
+    # orientation: x axis along the heading (yaw / pitch multiples of 90 deg)
+    truth = np.zeros((n_poses, 4, 4))
+    for h in range(6):
+        sel = heading == h
+        d = dirs[h].astype(float)
+        up = np.array([0.0, 0.0, 1.0]) if h < 4 else np.array([1.0, 0.0, 0.0])
+        y = np.cross(up, d)
+        R = np.stack([d, y, np.cross(d, y)], axis=1)
+        truth[sel, :3, :3] = R
+    truth[:, :3, 3] = pos
+    truth[:, 3, 3] = 1.0
+    # candidate loop pairs via a lattice hash (same or neighbouring site, non-consecutive)
+    key = (pos[:, 0] * box[1] + pos[:, 1]) * box[2] + pos[:, 2]
+    order = np.argsort(key, kind="stable")
+    n_loop = n_factors - (n_poses - 1)
+    pairs = []
+    if n_loop > 0:
+        ks = key[order]
+        starts = np.nonzero(np.r_[True, ks[1:] != ks[:-1]])[0]
+        ends = np.r_[starts[1:], ks.size]
+        site_of = {int(ks[s]): (s, e) for s, e in zip(starts, ends)}
+        got = 0
+        tries = 0
+        while got < n_loop and tries < 50:
+            tries += 1
+            a = rng.integers(0, n_poses, size=2 * (n_loop - got) + 16)
+            off = dirs[rng.integers(0, 6, size=a.size)] * (rng.uniform(size=(a.size, 1)) < 0.5)
+            q = pos[a] + off
+            ok = np.all((q >= 0) & (q < box), axis=1)
+            a, q = a[ok], q[ok]
+            kq = (q[:, 0] * box[1] + q[:, 1]) * box[2] + q[:, 2]
+            for ai, kk in zip(a, kq):
+                se = site_of.get(int(kk))
+                if se is None:
+                    continue
+                bi = int(order[rng.integers(se[0], se[1])])
+                if abs(bi - int(ai)) > 1 and np.linalg.norm(pos[bi] - pos[ai]) <= max_loop_dist:
+                    pairs.append((min(int(ai), bi), max(int(ai), bi)))
+                    got += 1
+                    if got >= n_loop:
+                        break
+    odo = np.stack([np.arange(n_poses - 1), np.arange(1, n_poses)], axis=1)
+    ij = np.concatenate([odo, np.array(pairs, dtype=np.int64).reshape(-1, 2)], axis=0).astype(np.int32)
+    F = ij.shape[0]
+    sr = np.deg2rad(sigma_r_deg)
+    noise = np.concatenate([rng.normal(scale=sigma_t, size=(F, 3)), rng.normal(scale=sr / 2, size=(F, 3))], axis=1)
+    Zt = _inv_iso_batch(truth[ij[:, 0]]) @ truth[ij[:, 1]]
+    Z = Zt @ _v2t_batch(noise)
+    omega = np.diag(np.r_[np.full(3, 1 / sigma_t ** 2), np.full(3, 1 / (sr / 2) ** 2)])
+    Omega = np.broadcast_to(omega, (F, 6, 6)).copy()
+    guess = np.empty_like(truth)
+    guess[0] = truth[0]
+    for k in range(1, n_poses):  # integrated noisy odometry
+        guess[k] = guess[k - 1] @ Z[k - 1]
+    fixed = np.zeros(n_poses, dtype=np.uint8)
+    fixed[0] = 1
+    return dict(truth=truth, guess=guess.astype(np.float32), ij=ij, Z=Z.astype(np.float32),
+                Omega=Omega.astype(np.float32), fixed=fixed)
+
+
+def _inv_iso_batch(T):
+    Ti = np.zeros_like(T)
+    Rt = np.swapaxes(T[..., :3, :3], -1, -2)
+    Ti[..., :3, :3] = Rt
+    Ti[..., :3, 3] = -np.einsum("...ij,...j->...i", Rt, T[..., :3, 3])
+    Ti[..., 3, 3] = 1.0
+    return Ti
+
+
+def _v2t_batch(dx):
+    dq = dx[..., 3:6]
+    w = np.sqrt(np.maximum(1.0 - np.sum(dq * dq, -1), 0.0))
+    x, y, z = dq[..., 0], dq[..., 1], dq[..., 2]
+    T = np.zeros(dx.shape[:-1] + (4, 4))
+    T[..., 0, 0] = 1 - 2 * (y * y + z * z); T[..., 0, 1] = 2 * (x * y - w * z); T[..., 0, 2] = 2 * (x * z + w * y)
+    T[..., 1, 0] = 2 * (x * y + w * z); T[..., 1, 1] = 1 - 2 * (x * x + z * z); T[..., 1, 2] = 2 * (y * z - w * x)
+    T[..., 2, 0] = 2 * (x * z - w * y); T[..., 2, 1] = 2 * (y * z + w * x); T[..., 2, 2] = 1 - 2 * (x * x + y * y)
+    T[..., :3, 3] = dx[..., :3]
+    T[..., 3, 3] = 1.0
+    return T
