@@ -136,8 +136,8 @@ int srrg2b_find_correspondences(srrg2b_ctx* ctx, int slice_id, const float* S, c
 int srrg2b_set_correspondences(srrg2b_ctx* ctx, int slice_id, const int32_t* fixed_idx, const int32_t* moving_idx, int64_t n);
 
 /* ---- a5 (linearise): FactorCorrespondenceDriven_ accumulation over the slice's current
- * correspondences at S. H is PxP row-major (P = 6 | 3), b is P; acc (optional) receives the 32
- * exact fixed-point sums; status/chi (optional) are per correspondence in ascending moving_idx. */
+ * correspondences at S. H is PxP row-major (P = 6 | 3), b is P; acc (optional) receives the 40
+ * exact fixed-point sums (21 H, 6 b, chi in/out as coarse+residual words, 3 counters, padding); status/chi (optional) are per correspondence in ascending moving_idx. */
 int srrg2b_linearize(srrg2b_ctx* ctx, int slice_id, const float* S, int variable, const srrg2b_finder_params* fp,
                      const srrg2b_factor_params* fa, double* H, double* b, int64_t* acc,
                      srrg2b_iter_stats* stats, uint8_t* status, float* chi);
@@ -161,7 +161,7 @@ int srrg2b_last_run_timing(srrg2b_ctx* ctx, float* device_ms, int32_t* iteration
 /* when enabled, every launch of the fused per-slice ICP kernel is bracketed by CUDA events on the
  * context stream; the sum and count for the last run are returned (roofline measurement) */
 /* diagnostics of a slice's NN index: out16 = {R, nx, ny, nz, n_fixed_valid, n_moving_valid,
- * size of the last phase-2 worklist, cell edge (float bits), 0...} */
+ * size of the last phase-2 worklist, cell edge (float bits), size of the last coherence worklist, 0...} */
 int srrg2b_debug_info(srrg2b_ctx* ctx, int slice_id, int32_t* out16);
 int srrg2b_set_kernel_timing(srrg2b_ctx* ctx, int enable);
 int srrg2b_last_kernel_timing(srrg2b_ctx* ctx, float* slice_kernel_ms, int32_t* slice_kernel_launches);

@@ -76,7 +76,10 @@ class CorrOut(C.Structure):
 
 
 class Scales(C.Structure):
-    _fields_ = [("kH", C.c_int32), ("kb", C.c_int32), ("kchi", C.c_int32)]
+    _fields_ = [("k", C.c_int32 * 7)]
+
+
+ACC_SLOTS = 40
 
 
 _lib = None
@@ -183,7 +186,7 @@ def linearize(fixed, moving, fidx, S, fp, fa, variable=VAR_SE3_QUAT_RIGHT, n_glo
     P = 6 if dim == 3 else 3
     S = _f32(S).reshape(-1)
     fidx = np.ascontiguousarray(fidx, dtype=np.int32)
-    acc = np.zeros(32, dtype=np.int64)
+    acc = np.zeros(ACC_SLOTS, dtype=np.int64)
     H = np.zeros((P, P), dtype=np.float64)
     b = np.zeros(P, dtype=np.float64)
     st = IterStats()
@@ -264,7 +267,7 @@ def icp_run(dim, slices, ap, T0, nn_method=NN_KDTREE, want_correspondences=True,
 def scales(dim, n_global, coord_bound, fp, fa):
     s = Scales()
     lib().orc_scales(dim, n_global, coord_bound, C.byref(fp), C.byref(fa), C.byref(s))
-    return s.kH, s.kb, s.kchi
+    return tuple(s.k)
 
 
 def solve_update(dim, variable, H, b, T):

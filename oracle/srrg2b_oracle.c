@@ -724,26 +724,31 @@ float orc_coord_bound(int dim, const orc_cloud* moving) {
   return b;
 }
 
+/* Per-TERM magnitude bounds (log2) of everything that is accumulated, from global quantities only:
+ *   translation columns of J : |entry| <= 2 (rotation-matrix entries / unit normals, one spare bit)
+ *   rotation columns of J    : |entry| <= max(2, 4 |coord|_max)      -> Jb bits
+ *   error rows               : |e| <= max(max_distance, 2)            -> eb bits
+ *   information              : <= max(info_point, info_normal, 1)     -> wb bits,  <= 4 rows -> 2 bits
+ * A term is stored as round(term * 2^k) with k = 21 - bound, so |term * 2^k| < 2^21 (terms are
+ * clamped to the bound before rounding).  chi gets a second, 2^20 times finer, residual word. */
 int orc_scales(int dim, int64_t n_global, float coord_bound, const orc_finder_params* fp,
                const orc_factor_params* fa, orc_scales_t* out) {
-  (void) dim;
-  int nb = 0;
-  while (((int64_t) 1 << nb) < n_global) ++nb;
+  (void) dim; (void) n_global;
   float jm = 4.f * coord_bound;
   if (jm < 2.f) jm = 2.f;
-  int Jb = ceil_log2f_(jm);
+  const int Jb = ceil_log2f_(jm);
   float wm = fa->info_point > fa->info_normal ? fa->info_point : fa->info_normal;
   if (!(wm > 1.f)) wm = 1.f;
-  int wb = ceil_log2f_(wm);
-  float em = fp->max_distance > 2.f ? fp->max_distance : 2.f;
-  int eb = ceil_log2f_(em);
-  int kH = 62 - nb - 2 - wb - 2 * Jb;
-  int kb = 62 - nb - 2 - wb - Jb - eb;
-  int kc = 62 - nb - 2 - wb - 2 * eb;
-  if (kH > 60) kH = 60;
-  if (kb > 60) kb = 60;
-  if (kc > 60) kc = 60;
-  out->kH = kH; out->kb = kb; out->kchi = kc;
+  const int wb = ceil_log2f_(wm);
+  const float em = fp->max_distance > 2.f ? fp->max_distance : 2.f;
+  const int eb = ceil_log2f_(em);
+  out->k[ORC_K_HTT] = 21 - (2 + wb + 2);
+  out->k[ORC_K_HTR] = 21 - (2 + wb + 1 + Jb);
+  out->k[ORC_K_HRR] = 21 - (2 + wb + 2 * Jb);
+  out->k[ORC_K_BT] = 21 - (2 + wb + 1 + eb);
+  out->k[ORC_K_BR] = 21 - (2 + wb + Jb + eb);
+  out->k[ORC_K_CHI] = 21 - (2 + wb + 2 * eb);
+  out->k[ORC_K_CHI_LO] = out->k[ORC_K_CHI] + 20;
   return 0;
 }
 
@@ -751,8 +756,29 @@ int orc_scales(int dim, int64_t n_global, float coord_bound, const orc_finder_pa
 /* a5 -- per-correspondence linearisation (FactorCorrespondenceDriven_<F,...> inside            */
 /* Solver::compute(), reached from R/registration/aligners/multi_aligner_impl.cpp:112)          */
 /* ------------------------------------------------------------------------------------------ */
-static inline int64_t to_fix(float v, int k) {
-  return llrint(ldexp((double) v, k));
+/* round(v * 2^k) for |v| <= 2^(21-k) (clamped), computed the way the GPU does it: adding the magic
+ * constant 1.5 * 2^(23-k) leaves the rounded integer (ties to even) in the low mantissa bits. */
+static inline int32_t to_fix(float v, int k) {
+  const float M = ldexpf(1.5f, 23 - k), B = ldexpf(1.f, 21 - k);
+  v = fminf(fmaxf(v, -B), B);
+  const float t = v + M;
+  int32_t ti, mi;
+  memcpy(&ti, &t, 4);
+  memcpy(&mi, &M, 4);
+  return ti - mi;
+}
+
+/* chi as a (coarse, residual) pair: the residual of the coarse rounding is exact in fp32 */
+static inline void to_fix2(float v, int k_hi, int k_lo, int64_t* hi, int64_t* lo) {
+  const float M = ldexpf(1.5f, 23 - k_hi), B = ldexpf(1.f, 21 - k_hi);
+  v = fminf(fmaxf(v, -B), B);
+  const float t = v + M;
+  int32_t ti, mi;
+  memcpy(&ti, &t, 4);
+  memcpy(&mi, &M, 4);
+  *hi += ti - mi;
+  const float rem = v - (t - M);
+  *lo += to_fix(rem, k_lo);
 }
 
 /* robustifier on chi with threshold tau -> weight w, robustified rho; returns 1 if kernelized.
@@ -856,11 +882,12 @@ static int build_rows(int dim, int variable, int factor, const float* S4, const 
 
 /* slots of the 32-entry accumulator */
 #define ACC_B 21
-#define ACC_CHI_IN 27
-#define ACC_CHI_OUT 28
-#define ACC_N_IN 29
-#define ACC_N_OUT 30
-#define ACC_N_SUP 31
+#define ACC_CHI_IN 27      /* coarse word; +1 = residual word */
+#define ACC_CHI_OUT 29     /* coarse word; +1 = residual word */
+#define ACC_N_IN 31
+#define ACC_N_OUT 32
+#define ACC_N_SUP 33
+#define ACC_SLOTS ORC_ACC_SLOTS
 
 static void lin_one(int dim, int variable, const orc_factor_params* fa, const orc_scales_t* sc,
                     const float* S4, const float* m, const float* nm, const float* f, const float* nf,
@@ -884,13 +911,14 @@ static void lin_one(int dim, int variable, const orc_factor_params* fa, const or
   int kern = robustify(fa->robustifier, fa->chi_threshold, chi, &w, &rho);
   if (kern) {
     acc[ACC_N_OUT] += 1;
-    acc[ACC_CHI_OUT] += to_fix(rho, sc->kchi);
+    to_fix2(rho, sc->k[ORC_K_CHI], sc->k[ORC_K_CHI_LO], &acc[ACC_CHI_OUT], &acc[ACC_CHI_OUT + 1]);
   } else {
     acc[ACC_N_IN] += 1;
-    acc[ACC_CHI_IN] += to_fix(chi, sc->kchi);
+    to_fix2(chi, sc->k[ORC_K_CHI], sc->k[ORC_K_CHI_LO], &acc[ACC_CHI_IN], &acc[ACC_CHI_IN + 1]);
   }
   if (status) *status = kern ? ORC_STAT_KERNELIZED : ORC_STAT_INLIER;
   if (chi_out) *chi_out = chi;
+  const int T = dim; /* columns < T are the translation part of the perturbation */
   float u[4][6];
   for (int r = 0; r < E; ++r) {
     float s = w * om[r];
@@ -905,7 +933,7 @@ static void lin_one(int dim, int variable, const orc_factor_params* fa, const or
       for (int r = 1; r < E; ++r) {
         h = fmaf(u[r][i], J[r][j], h);
       }
-      acc[slot++] += to_fix(h, sc->kH);
+      acc[slot++] += to_fix(h, sc->k[(j < T) ? ORC_K_HTT : ((i < T) ? ORC_K_HTR : ORC_K_HRR)]);
     }
   }
   for (int i = 0; i < P; ++i) {
@@ -913,7 +941,7 @@ static void lin_one(int dim, int variable, const orc_factor_params* fa, const or
     for (int r = 1; r < E; ++r) {
       g = fmaf(u[r][i], e[r], g);
     }
-    acc[ACC_B + i] += to_fix(g, sc->kb);
+    acc[ACC_B + i] += to_fix(g, sc->k[(i < T) ? ORC_K_BT : ORC_K_BR]);
   }
 }
 
@@ -922,13 +950,13 @@ static void acc_to_Hb(int dim, const int64_t* acc, const orc_scales_t* sc, doubl
   int slot = 0;
   for (int i = 0; i < P; ++i) {
     for (int j = i; j < P; ++j) {
-      double v = ldexp((double) acc[slot++], -sc->kH);
+      double v = ldexp((double) acc[slot++], -sc->k[(j < dim) ? ORC_K_HTT : ((i < dim) ? ORC_K_HTR : ORC_K_HRR)]);
       H[i * P + j] = v;
       H[j * P + i] = v;
     }
   }
   for (int i = 0; i < P; ++i) {
-    b[i] = ldexp((double) acc[ACC_B + i], -sc->kb);
+    b[i] = ldexp((double) acc[ACC_B + i], -sc->k[(i < dim) ? ORC_K_BT : ORC_K_BR]);
   }
 }
 
@@ -942,13 +970,13 @@ int orc_linearize(int dim, int variable, const orc_cloud* fixed, const orc_cloud
   /* n_global / coord_bound describe the WHOLE moving cloud when `moving` is one shard of it */
   orc_scales(dim, n_global > 0 ? n_global : moving->n, coord_bound > 0.f ? coord_bound : orc_coord_bound(dim, moving),
              fp, fa, &sc);
-  int64_t acc[32];
+  int64_t acc[ACC_SLOTS];
   memset(acc, 0, sizeof(acc));
   const int have_n = (fixed->normals && moving->normals);
   if (fa->factor == ORC_FACTOR_PLANE && !have_n) return 1;
 #pragma omp parallel
   {
-    int64_t loc[32];
+    int64_t loc[ACC_SLOTS];
     memset(loc, 0, sizeof(loc));
 #pragma omp for schedule(static)
     for (int64_t j = 0; j < moving->n; ++j) {
@@ -972,7 +1000,7 @@ int orc_linearize(int dim, int variable, const orc_cloud* fixed, const orc_cloud
               chi_dense ? chi_dense + j : NULL);
     }
 #pragma omp critical
-    for (int k = 0; k < 32; ++k) acc[k] += loc[k];
+    for (int k = 0; k < ACC_SLOTS; ++k) acc[k] += loc[k];
   }
   if (acc_out) memcpy(acc_out, acc, sizeof(acc));
   if (H && b) acc_to_Hb(dim, acc, &sc, H, b);
@@ -981,8 +1009,8 @@ int orc_linearize(int dim, int variable, const orc_cloud* fixed, const orc_cloud
     stats->num_outliers = acc[ACC_N_OUT];
     stats->num_suppressed = acc[ACC_N_SUP];
     stats->num_correspondences = acc[ACC_N_IN] + acc[ACC_N_OUT] + acc[ACC_N_SUP];
-    stats->chi_inliers = ldexp((double) acc[ACC_CHI_IN], -sc.kchi);
-    stats->chi_outliers = ldexp((double) acc[ACC_CHI_OUT], -sc.kchi);
+    stats->chi_inliers = ldexp((double) acc[ACC_CHI_IN], -sc.k[ORC_K_CHI]) + ldexp((double) acc[ACC_CHI_IN + 1], -sc.k[ORC_K_CHI_LO]);
+    stats->chi_outliers = ldexp((double) acc[ACC_CHI_OUT], -sc.k[ORC_K_CHI]) + ldexp((double) acc[ACC_CHI_OUT + 1], -sc.k[ORC_K_CHI_LO]);
   }
   return 0;
 }

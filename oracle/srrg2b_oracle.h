@@ -94,8 +94,10 @@ typedef struct {
   int64_t n;
 } orc_corr_out;
 
-/* fixed-point scale exponents (see oracle .c: orc_scales) */
-typedef struct { int32_t kH, kb, kchi; } orc_scales_t;
+/* fixed-point scale exponents per accumulated class (see oracle .c: orc_scales) */
+enum { ORC_K_HTT = 0, ORC_K_HTR = 1, ORC_K_HRR = 2, ORC_K_BT = 3, ORC_K_BR = 4, ORC_K_CHI = 5, ORC_K_CHI_LO = 6, ORC_K_COUNT = 7 };
+#define ORC_ACC_SLOTS 40
+typedef struct { int32_t k[ORC_K_COUNT]; } orc_scales_t;
 
 int orc_set_threads(int n);   /* OpenMP threads for the finder / lineariser loops; returns actual */
 
@@ -115,7 +117,7 @@ float orc_coord_bound(int dim, const orc_cloud* moving);
 int orc_linearize(int dim, int variable, const orc_cloud* fixed, const orc_cloud* moving,
                   const int32_t* fixed_idx_dense, const float* S, const orc_finder_params* fp,
                   const orc_factor_params* fa, int64_t n_moving_global, float coord_bound_global /* <=0: from moving */,
-                  int64_t* acc /*[32] fixed point*/, double* H /*36 or 9 full row-major*/, double* b,
+                  int64_t* acc /*[ORC_ACC_SLOTS] fixed point*/, double* H /*36 or 9 full row-major*/, double* b,
                   orc_iter_stats* stats, uint8_t* status_dense, float* chi_dense);
 
 /* a1..a9: MultiAlignerBase_::compute() */

@@ -259,7 +259,7 @@ class Context:
         S = np.ascontiguousarray(np.asarray(S, dtype=np.float32).reshape(-1))
         H = np.zeros((P, P), dtype=np.float64)
         b = np.zeros(P, dtype=np.float64)
-        acc = np.zeros(32, dtype=np.int64)
+        acc = np.zeros(40, dtype=np.int64)
         st = IterStats()
         status = np.empty(n_moving, dtype=np.uint8) if want_status else None
         chi = np.empty(n_moving, dtype=np.float32) if want_status else None
@@ -307,7 +307,7 @@ class Context:
         out = np.zeros(16, dtype=np.int32)
         self._check(self.lib.srrg2b_debug_info(self.h, slice_id, out.ctypes.data))
         return dict(R=int(out[0]), dims=(int(out[1]), int(out[2]), int(out[3])), n_fixed_valid=int(out[4]),
-                    n_moving_valid=int(out[5]), last_far_count=int(out[6]),
+                    n_moving_valid=int(out[5]), last_far_count=int(out[6]), last_work_count=int(out[8]),
                     cell=float(out[7:8].view(np.float32)[0]))
 
     def set_kernel_timing(self, enable):

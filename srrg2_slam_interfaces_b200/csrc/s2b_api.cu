@@ -95,7 +95,7 @@ struct SliceData {
   float coord_bound = 0.f;
   bool coord_bound_global = false;
   // correspondences in moving-sorted order
-  DevBuf<int> c_fidx, c_fpos, far_list, far_count;
+  DevBuf<int> c_fidx, c_fpos, far_list, far_count, work_list;
   DevBuf<float> c_resp, c_chi, c_lb, S_lb;
   DevBuf<unsigned char> c_stat;
   bool corr_valid = false, stat_valid = false;
@@ -218,7 +218,8 @@ int build_moving(srrg2b_ctx* c, SliceData& sd) {
   CK(c, sd.c_fidx.ensure((size_t) n));
   CK(c, sd.c_fpos.ensure((size_t) n));
   CK(c, sd.far_list.ensure((size_t) n));
-  CK(c, sd.far_count.ensure(1));
+  CK(c, sd.far_count.ensure(2));  // [0] far worklist size, [1] coherence worklist size
+  CK(c, sd.work_list.ensure((size_t) n));
   CK(c, sd.c_lb.ensure((size_t) n));
   CK(c, sd.S_lb.ensure(16));
   if (n) CK(c, cudaMemsetAsync(sd.c_lb.p, 0, sizeof(float) * (size_t) n, c->stream));
@@ -471,11 +472,17 @@ int fill_slice_args(srrg2b_ctx* c, SliceData& sd, int state_slot, const srrg2b_f
   a.gate = (normals && fp.normal_cos > -1.f) ? 1 : 0;
   a.rob = fa.robustifier; a.tau = fa.chi_threshold; a.ip = fa.info_point; a.in_ = fa.info_normal;
   a.rs = (c->dim == 3 && variable == SRRG2B_VAR_SE3_QUAT_RIGHT) ? 2.f : 1.f;
-  a.sH = ldexp(1.0, sc.kH); a.sb = ldexp(1.0, sc.kb); a.sc = ldexp(1.0, sc.kchi);
+  for (int k = 0; k < kKCount; ++k) {
+    a.fM[k] = ldexpf(1.5f, 23 - sc.k[k]);
+    a.fB[k] = ldexpf(1.f, 21 - sc.k[k]);
+  }
   a.S = c->d_state->S[state_slot].m;
   a.c_fpos = sd.c_fpos.p;
   a.gate_in_nn = 0;
   a.far_list = sd.far_list.p; a.far_count = sd.far_count.p;
+  a.work_list = sd.work_list.p; a.work_count = sd.far_count.p + 1;
+  a.list_all = &c->d_state->list_all[state_slot];
+  a.inline_check = 0; a.use_list = 0;
   a.projective = fp.kind == SRRG2B_FINDER_PROJECTIVE ? 1 : 0;
   a.fx = fp.fx; a.fy = fp.fy; a.pcx = fp.cx; a.pcy = fp.cy; a.min_depth = fp.min_depth; a.max_depth = fp.max_depth;
   a.width = fp.width; a.height = fp.height; a.image = sd.image.p;
@@ -493,6 +500,19 @@ int fill_slice_args(srrg2b_ctx* c, SliceData& sd, int state_slot, const srrg2b_f
   return SRRG2B_OK;
 }
 
+void launch_far(srrg2b_ctx* c, const SliceArgs& a, int factor) {
+  const int threads = 256;
+  const int fblocks = std::max(1, std::min(blocks_for((int64_t) a.nm * 32, threads), c->sm_count * 8));
+  if (c->dim == 3) {
+    if (factor == SRRG2B_FACTOR_P2P) nn_far_kernel<3, SRRG2B_FACTOR_P2P><<<fblocks, threads, 0, c->stream>>>(a);
+    else nn_far_kernel<3, SRRG2B_FACTOR_PLANE><<<fblocks, threads, 0, c->stream>>>(a);
+  } else {
+    if (factor == SRRG2B_FACTOR_P2P) nn_far_kernel<2, SRRG2B_FACTOR_P2P><<<fblocks, threads, 0, c->stream>>>(a);
+    else nn_far_kernel<2, SRRG2B_FACTOR_PLANE><<<fblocks, threads, 0, c->stream>>>(a);
+  }
+  c->launches++;
+}
+
 int launch_find(srrg2b_ctx* c, const SliceArgs& a) {
   if (a.nm <= 0) return SRRG2B_OK;
   const int threads = 256;
@@ -506,28 +526,51 @@ int launch_find(srrg2b_ctx* c, const SliceArgs& a) {
   if (c->dim == 3) nn_kernel<3><<<blocks, threads, 0, c->stream>>>(a);
   else nn_kernel<2><<<blocks, threads, 0, c->stream>>>(a);
   c->launches++;
-  if (a.R >= 2) {
-    const int fblocks = std::max(1, std::min(blocks_for((int64_t) a.nm * 32, threads), c->sm_count * 2));
-    if (c->dim == 3) nn_far_kernel<3><<<fblocks, threads, 0, c->stream>>>(a);
-    else nn_far_kernel<2><<<fblocks, threads, 0, c->stream>>>(a);
-    c->launches++;
-  }
+  if (a.R >= 2) launch_far(c, a, SRRG2B_FACTOR_P2P);
   return SRRG2B_OK;
 }
 
-int launch_linearize(srrg2b_ctx* c, const SliceArgs& a, int factor) {
+template <bool CHECK>
+int launch_linearize_t(srrg2b_ctx* c, const SliceArgs& a, int factor) {
   if (a.nm <= 0) return SRRG2B_OK;
   const int threads = 256;
-  const int blocks = std::max(1, std::min(blocks_for(a.nm, threads), c->sm_count * 2));
+  // 2 CTAs per SM, but never more than 512 correspondences per thread (32-bit partial sums)
+  const int blocks = std::max(1, std::min(blocks_for(a.nm, threads),
+                                          std::max(c->sm_count * 2, blocks_for(a.nm, threads * 512))));
   if (c->dim == 3) {
-    if (factor == SRRG2B_FACTOR_P2P) linearize_kernel<3, SRRG2B_FACTOR_P2P><<<blocks, threads, 0, c->stream>>>(a);
-    else linearize_kernel<3, SRRG2B_FACTOR_PLANE><<<blocks, threads, 0, c->stream>>>(a);
+    if (factor == SRRG2B_FACTOR_P2P) linearize_kernel<3, SRRG2B_FACTOR_P2P, CHECK><<<blocks, threads, 0, c->stream>>>(a);
+    else linearize_kernel<3, SRRG2B_FACTOR_PLANE, CHECK><<<blocks, threads, 0, c->stream>>>(a);
   } else {
-    if (factor == SRRG2B_FACTOR_P2P) linearize_kernel<2, SRRG2B_FACTOR_P2P><<<blocks, threads, 0, c->stream>>>(a);
-    else linearize_kernel<2, SRRG2B_FACTOR_PLANE><<<blocks, threads, 0, c->stream>>>(a);
+    if (factor == SRRG2B_FACTOR_P2P) linearize_kernel<2, SRRG2B_FACTOR_P2P, CHECK><<<blocks, threads, 0, c->stream>>>(a);
+    else linearize_kernel<2, SRRG2B_FACTOR_PLANE, CHECK><<<blocks, threads, 0, c->stream>>>(a);
   }
   c->launches++;
   return SRRG2B_OK;
+}
+
+int launch_linearize(srrg2b_ctx* c, const SliceArgs& a, int factor) { return launch_linearize_t<false>(c, a, factor); }
+
+// one pass over a slice inside the ICP loop: fused coherence check + linearise, then search and
+// linearise whatever failed the check (everything, while no bounds are certified)
+int launch_slice_iteration(srrg2b_ctx* c, const SliceArgs& a0, int factor) {
+  if (a0.nm <= 0) return SRRG2B_OK;
+  SliceArgs a = a0;
+  if (a.projective) {  // no coherence machinery for the index-image finder
+    int rcode = launch_find(c, a);
+    if (rcode) return rcode;
+    return launch_linearize(c, a, factor);
+  }
+  a.use_list = 1;
+  CK(c, cudaMemsetAsync(a.far_count, 0, 2 * sizeof(int), c->stream));
+  int rcode = launch_linearize_t<true>(c, a, factor);
+  if (rcode) return rcode;
+  const int threads = 256;
+  const int blocks = std::max(1, std::min(blocks_for(a.nm, threads), c->sm_count * 8));
+  if (c->dim == 3) nn_kernel<3><<<blocks, threads, 0, c->stream>>>(a);
+  else nn_kernel<2><<<blocks, threads, 0, c->stream>>>(a);
+  c->launches++;
+  launch_far(c, a, factor);  // phase 2 of long lists, or the whole job for short ones (any R)
+  return launch_linearize_t<false>(c, a, factor);
 }
 
 // ring-ordered (dy, dz) row offsets of the NN search neighbourhood -> __constant__ tables
@@ -619,9 +662,7 @@ int make_plan(srrg2b_ctx* c, int n_slices, const srrg2b_slice* slices, const srr
       ss.coord_bound = sdd.coord_bound;
       ss.track2_mode = c->track2_mode;
     }
-    ss.invH = ldexp(1.0, -sc.kH);
-    ss.invb = ldexp(1.0, -sc.kb);
-    ss.invchi = ldexp(1.0, -sc.kchi);
+    for (int k = 0; k < kKCount; ++k) ss.invk[k] = ldexp(1.0, -sc.k[k]);
   }
   return SRRG2B_OK;
 }
@@ -647,9 +688,7 @@ int enqueue_iterations(srrg2b_ctx* c, const Plan& plan, int iterations) {
         }
         CK(c, cudaEventRecord(c->kev[c->kev_used], c->stream));
       }
-      int rcode = launch_find(c, plan.sargs[s]);
-      if (rcode) return rcode;
-      rcode = launch_linearize(c, plan.sargs[s], plan.factor[s]);
+      int rcode = launch_slice_iteration(c, plan.sargs[s], plan.factor[s]);
       if (rcode) return rcode;
       if (c->time_kernels) {
         CK(c, cudaEventRecord(c->kev[c->kev_used + 1], c->stream));
@@ -786,7 +825,7 @@ int srrg2b_ctx_destroy(srrg2b_ctx* c) {
     s.moving_raw.xyz.release(); s.moving_raw.nrm.release(); s.moving_raw.valid.release();
     s.f_pts.release(); s.f_nrm.release(); s.f_inverse.release(); s.cell_start.release();
     s.m_pts.release(); s.m_nrm.release(); s.m_inverse.release();
-    s.image.release(); s.c_lb.release(); s.S_lb.release(); s.c_fidx.release(); s.c_fpos.release(); s.far_list.release(); s.far_count.release(); s.c_resp.release(); s.c_chi.release(); s.c_stat.release();
+    s.image.release(); s.c_lb.release(); s.S_lb.release(); s.c_fidx.release(); s.c_fpos.release(); s.far_list.release(); s.far_count.release(); s.work_list.release(); s.c_resp.release(); s.c_chi.release(); s.c_stat.release();
   }
   c->keys_a.release(); c->keys_b.release(); c->vals_a.release(); c->vals_b.release();
   c->flags.release(); c->positions.release(); c->bounds.release(); c->cub_tmp.release();
@@ -871,6 +910,7 @@ int srrg2b_find_correspondences(srrg2b_ctx* c, int slice_id, const float* S, con
   int rcode = fill_slice_args(c, sd, 0, *fp, fa, SRRG2B_VAR_SE3_QUAT_RIGHT, false, a, nullptr);
   if (rcode) return rcode;
   a.gate_in_nn = 1;
+  a.inline_check = 1;
   Mat4f S4;
   embed(c->dim, S, S4);
   set_S_kernel<<<1, 32, 0, c->stream>>>(c->d_state, 0, S4, c->track2_mode == 1 ? 1 : 0);
@@ -943,7 +983,10 @@ int srrg2b_linearize(srrg2b_ctx* c, int slice_id, const float* S, int variable, 
   if (rcode) return rcode;
   a.gate = 0;  // the correspondences are taken as they are (gated by the finder or supplied by the caller)
   sc = choose_scales(sd.moving_raw.n_global, sd.coord_bound, fp->max_distance, fa->info_point, fa->info_normal);
-  a.sH = ldexp(1.0, sc.kH); a.sb = ldexp(1.0, sc.kb); a.sc = ldexp(1.0, sc.kchi);
+  for (int k = 0; k < kKCount; ++k) {
+    a.fM[k] = ldexpf(1.5f, 23 - sc.k[k]);
+    a.fB[k] = ldexpf(1.f, 21 - sc.k[k]);
+  }
   Mat4f S4;
   embed(c->dim, S, S4);
   set_S_kernel<<<1, 32, 0, c->stream>>>(c->d_state, 0, S4, 0);
@@ -963,11 +1006,11 @@ int srrg2b_linearize(srrg2b_ctx* c, int slice_id, const float* S, int variable, 
     int slot = 0;
     for (int i = 0; i < P; ++i)
       for (int j = i; j < P; ++j) {
-        const double v = ldexp((double) (long long) A[slot++], -sc.kH);
+        const double v = ldexp((double) (long long) A[slot++], -sc.k[(j < c->dim) ? kKHtt : ((i < c->dim) ? kKHtr : kKHrr)]);
         H[i * P + j] = v;
         H[j * P + i] = v;
       }
-    for (int i = 0; i < P; ++i) b[i] = ldexp((double) (long long) A[kAccB + i], -sc.kb);
+    for (int i = 0; i < P; ++i) b[i] = ldexp((double) (long long) A[kAccB + i], -sc.k[(i < c->dim) ? kKBt : kKBr]);
   }
   if (stats) {
     stats->iteration = 0;
@@ -976,8 +1019,8 @@ int srrg2b_linearize(srrg2b_ctx* c, int slice_id, const float* S, int variable, 
     stats->num_outliers = (int64_t) A[kAccNOut];
     stats->num_suppressed = (int64_t) A[kAccNSup];
     stats->num_correspondences = stats->num_inliers + stats->num_outliers + stats->num_suppressed;
-    stats->chi_inliers = ldexp((double) (long long) A[kAccChiIn], -sc.kchi);
-    stats->chi_outliers = ldexp((double) (long long) A[kAccChiOut], -sc.kchi);
+    stats->chi_inliers = ldexp((double) (long long) A[kAccChiIn], -sc.k[kKChi]) + ldexp((double) (long long) A[kAccChiIn + 1], -sc.k[kKChiLo]);
+    stats->chi_outliers = ldexp((double) (long long) A[kAccChiOut], -sc.k[kKChi]) + ldexp((double) (long long) A[kAccChiOut + 1], -sc.k[kKChiLo]);
   }
   if (status || chi) {
     int64_t m = 0;
@@ -1129,8 +1172,11 @@ int srrg2b_debug_info(srrg2b_ctx* c, int slice_id, int32_t* out16) {
   out16[0] = sd.R; out16[1] = sd.nx; out16[2] = sd.ny; out16[3] = sd.nz;
   out16[4] = sd.nf_valid; out16[5] = sd.nm_valid;
   if (sd.far_count.p) {
-    CK(c, cudaMemcpyAsync(&out16[6], sd.far_count.p, 4, cudaMemcpyDeviceToHost, c->stream));
+    int two[2] = {0, 0};
+    CK(c, cudaMemcpyAsync(two, sd.far_count.p, 8, cudaMemcpyDeviceToHost, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
+    out16[6] = two[0];
+    out16[8] = two[1];
   }
   float cell = 1.f / sd.inv_cell;
   memcpy(&out16[7], &cell, 4);

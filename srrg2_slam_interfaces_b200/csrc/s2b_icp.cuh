@@ -11,11 +11,13 @@
 #pragma once
 #include "s2b_math.cuh"
 #include "../../include/srrg2b.h"
+#include <cooperative_groups.h>
 
 namespace s2b {
+namespace cg = cooperative_groups;
 
-constexpr int kAcc = 32;  // accumulator slots per slice
-constexpr int kAccB = 21, kAccChiIn = 27, kAccChiOut = 28, kAccNIn = 29, kAccNOut = 30, kAccNSup = 31;
+constexpr int kAcc = 40;  // accumulator slots per slice: 21 H, 6 b, chi in/out (coarse + residual), 3 counters
+constexpr int kAccB = 21, kAccChiIn = 27, kAccChiOut = 29, kAccNIn = 31, kAccNOut = 32, kAccNSup = 33;
 constexpr int kMaxStats = 256;
 constexpr int kMaxWindow = 64;
 
@@ -30,6 +32,7 @@ struct DevState {
   unsigned long long acc[SRRG2B_MAX_SLICES][kAcc];
   long long ncorr[SRRG2B_MAX_SLICES];
   int track2[SRRG2B_MAX_SLICES];             // NN searches of the next iteration certify bounds
+  int list_all[SRRG2B_MAX_SLICES];           // next iteration has no usable bounds: search everything
   int stop;                                  // set on termination / bad association
   int n_stats;
   int not_enough_corr;
@@ -43,7 +46,7 @@ struct SolveSlice {
   int kind, min_corr;
   Mat4f ris, Z;
   float info[6];
-  double invH, invb, invchi;  // 2^-k of the slice's fixed-point scales
+  double invk[kKCount];       // 2^-k of the slice's fixed-point scales, per accumulated class
   float* S_lb;                // slice's bound-validity transform (committed every iteration)
   float cell, coord_bound;    // NN cell edge / max |coordinate| of the moving cloud
   int track2_mode;            // 0 never, 1 always, 2 automatic (small motion)
@@ -72,11 +75,16 @@ struct SliceArgs {
   int gate_in_nn;  // 1: the NN kernels gate and write responses (stand-alone find); 0: linearise gates
   int rob;
   float tau, ip, in_, rs;
-  double sH, sb, sc;
+  float fM[kKCount], fB[kKCount];  // magic constant 1.5 * 2^(23-k) and clamp 2^(21-k) per class
   const float* S;
   int* c_fpos;
   int* far_list;   // phase-2 worklist of the NN search (query positions) and its counter
   int* far_count;
+  int* work_list;      // queries whose coherence check failed (need a search + a second linearise pass)
+  int* work_count;
+  const int* list_all; // device flag: no usable bounds -> the work list is implicitly [0, nm)
+  int inline_check;    // 1: nn_kernel does the coherence check itself (stand-alone finder)
+  int use_list;        // 1: nn / linearise kernels iterate over the work list
   float* c_lb;         // certified lower bound per query (see nn kernels)
   const float* S_lb;   // transform the bounds are valid for
   const int* track2;   // device flag: searches track the second neighbour (certify bounds)
@@ -367,6 +375,13 @@ __device__ __forceinline__ void nn_setup(const SliceArgs& a, const float* S, con
   q.bd2 = a.md2; q.sd2 = a.rho_s2; q.bidx = INT_MAX; q.bpos = -1;
 }
 
+// work lists shorter than this are handled by one warp per query inside nn_far_kernel (search +
+// linearise), where the chain of dependent loads of a search is short; the thread-per-query kernels
+// then return at once
+__device__ __forceinline__ bool small_work_list(const SliceArgs& a, bool all, int n_work) {
+  return a.use_list && !all && n_work < max(a.nm >> 6, 64);
+}
+
 __device__ __forceinline__ int slot_candidate(int slot) {
   if (slot >= 0) return slot;
   if (slot <= -2 && slot != kSlotSuppressed) return -(slot + 2);
@@ -376,8 +391,8 @@ __device__ __forceinline__ int slot_candidate(int slot) {
 // slot / bound of a finished query.  Inside the ICP loop the normal gate is evaluated by the
 // lineariser (it has both normals in registers anyway); the stand-alone finder gates here.
 template <int DIM>
-__device__ __forceinline__ void nn_finish(const SliceArgs& a, const float* S, const NNQuery& q, int i, float lb,
-                                          int old_slot) {
+__device__ __forceinline__ int nn_finish(const SliceArgs& a, const float* S, const NNQuery& q, int i, float lb,
+                                         int old_slot) {
   int slot = q.bpos;
   if (q.bpos >= 0 && a.gate && a.gate_in_nn) {
     const float4 nm = a.mn[i];
@@ -396,6 +411,7 @@ __device__ __forceinline__ void nn_finish(const SliceArgs& a, const float* S, co
   }
   if (slot != old_slot) a.c_fpos[i] = slot;
   a.c_lb[i] = lb;
+  return slot;
 }
 
 // Phase 1: temporal-coherence check, else warm start + the 3^(DIM-1) rows of rings 0 and 1 (each
@@ -405,13 +421,17 @@ __device__ __forceinline__ void nn_finish(const SliceArgs& a, const float* S, co
 template <int DIM, bool TRACK2>
 __device__ __forceinline__ void nn_phase1_body(const SliceArgs& a, const float* S, const float* Slb, float cell,
                                                float ring2, float ring2_sq) {
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.nm; i += gridDim.x * blockDim.x) {
+  const bool all = !a.use_list || *a.list_all;
+  const int n_work = all ? a.nm : *a.work_count;
+  if (small_work_list(a, all, n_work)) return;
+  for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < n_work; w += gridDim.x * blockDim.x) {
+    const int i = all ? w : a.work_list[w];
     NNQuery q;
     const float4 m = a.mp[i];
     nn_setup<DIM>(a, S, m, q);
     const int old_slot = a.c_fpos[i];
     const int p0 = slot_candidate(old_slot);
-    const float lb_old = a.c_lb[i];
+    const float lb_old = a.inline_check ? a.c_lb[i] : 0.f;
     if (lb_old > 0.f) {
       float ox, oy, oz;
       nn_transform<DIM>(Slb, m, ox, oy, oz);
@@ -497,14 +517,20 @@ __global__ void __launch_bounds__(256) nn_kernel(const SliceArgs a) {
 // (typically no neighbour at all, so nothing prunes), so one WARP takes one query: lane l scans row
 // l (+32, ...) of the whole (2R+1)^(DIM-1) neighbourhood, then a shuffle reduction merges the
 // lanes' (nearest, second nearest) pairs and lane 0 applies the gate and writes slot and bound.
-template <int DIM, bool TRACK2>
+template <int DIM>
+struct LinAcc;
+template <int DIM, int FACTOR>
+__device__ __forceinline__ void lin_one(const SliceArgs& a, const float* Ss, int i, int slot, int bpos, const float4 m,
+                                        const float4 nm, const float4 f, const float4 nf, LinAcc<DIM>& A);
+
+template <int DIM, bool TRACK2, int FACTOR = SRRG2B_FACTOR_P2P>
 __device__ __forceinline__ void nn_far_body(const SliceArgs& a, const float* S, const int* rows, int K, float cell,
-                                            int n_far) {
+                                            int n_far, const int* list, LinAcc<DIM>* lin) {
   const int lane = threadIdx.x & 31;
-  if (n_far > (a.nm >> 4)) {
+  if (!lin && n_far > (a.nm >> 4)) {
     // long worklist (large initial misalignment): one THREAD per query, rows nearest ring first
     for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < n_far; w += gridDim.x * blockDim.x) {
-      const int i = a.far_list[w];
+      const int i = list[w];
       NNQuery q;
       nn_setup<DIM>(a, S, a.mp[i], q);
       const int old_slot = a.c_fpos[i];
@@ -536,9 +562,10 @@ __device__ __forceinline__ void nn_far_body(const SliceArgs& a, const float* S, 
   }
   const int warps_per_block = blockDim.x >> 5;
   for (int w = blockIdx.x * warps_per_block + (threadIdx.x >> 5); w < n_far; w += gridDim.x * warps_per_block) {
-    const int i = a.far_list[w];
+    const int i = list[w];
     NNQuery q;
-    nn_setup<DIM>(a, S, a.mp[i], q);
+    const float4 m = a.mp[i];
+    nn_setup<DIM>(a, S, m, q);
     const int old_slot = a.c_fpos[i];
     const int p0 = slot_candidate(old_slot);
     if (a.warm && p0 >= 0) nn_consider<DIM, TRACK2>(a, q, p0);
@@ -571,25 +598,15 @@ __device__ __forceinline__ void nn_far_body(const SliceArgs& a, const float* S, 
       }
       if (other_wins) { q.bd2 = od2; q.bidx = oidx; q.bpos = opos; }
     }
-    if (lane == 0) nn_finish<DIM>(a, S, q, i, TRACK2 ? __fsqrt_rn(q.sd2) * (1.f - 1e-5f) : 0.f, old_slot);
+    if (lane == 0) {
+      const int slot = nn_finish<DIM>(a, S, q, i, TRACK2 ? __fsqrt_rn(q.sd2) * (1.f - 1e-5f) : 0.f, old_slot);
+      if (lin) {  // tail mode: linearise the query right away (the gate is re-evaluated there)
+        const int bpos = a.gate ? slot_candidate(slot) : slot;
+        if (bpos >= 0) lin_one<DIM, FACTOR>(a, S, i, slot, bpos, m, a.mn[i], __ldg(a.fp + bpos), __ldg(a.fn + bpos), *lin);
+        else if (a.c_stat) a.c_stat[i] = SRRG2B_STAT_NONE;
+      }
+    }
   }
-}
-
-template <int DIM>
-__global__ void __launch_bounds__(256) nn_far_kernel(const SliceArgs a) {
-  const int n_far = *a.far_count;
-  if (n_far == 0 || *a.stop) return;
-  __shared__ float S[16];
-  __shared__ int rows[kRowTable];
-  if (threadIdx.x < 16) S[threadIdx.x] = a.S[threadIdx.x];
-  const int R = a.R;
-  const int K = (DIM == 3) ? (2 * R + 1) * (2 * R + 1) : (2 * R + 1);
-  for (int k = threadIdx.x; k < K; k += blockDim.x)
-    rows[k] = (DIM == 3) ? *reinterpret_cast<const int*>(c_rows3[k]) : *reinterpret_cast<const int*>(c_rows2[k]);
-  __syncthreads();
-  const float cell = __fdiv_rn(1.f, a.inv_cell);
-  if (*a.track2) nn_far_body<DIM, true>(a, S, rows, K, cell, n_far);
-  else nn_far_body<DIM, false>(a, S, rows, K, cell, n_far);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -671,11 +688,18 @@ __global__ void commit_S_kernel(const float* S, float* S_lb) {
   if (threadIdx.x < 16 && blockIdx.x == 0) S_lb[threadIdx.x] = S[threadIdx.x];
 }
 
-// ---------------------------------------------------------------------------------------------
-// k1b: per-correspondence linearisation + exact accumulation (a5)
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ long long to_fixed(float v, double scale) {
-  return __double2ll_rn((double) v * scale);
+// round(v * 2^k) for |v| <= B = 2^(21-k) (clamped): adding M = 1.5 * 2^(23-k) leaves the rounded integer
+// (ties to even) in the low mantissa bits -- two full-rate instructions instead of fp64 conversions
+__device__ __forceinline__ int to_fixed(float v, float M, float B) {
+  v = fminf(fmaxf(v, -B), B);
+  return __float_as_int(v + M) - __float_as_int(M);
+}
+// chi as (coarse, residual): the residual of the coarse rounding is exact in fp32
+__device__ __forceinline__ void to_fixed2(float v, float M, float B, float Mlo, float Blo, int& hi, int& lo) {
+  v = fminf(fmaxf(v, -B), B);
+  const float t = v + M;
+  hi += __float_as_int(t) - __float_as_int(M);
+  lo += to_fixed(v - (t - M), Mlo, Blo);
 }
 
 // robustifier on chi (threshold tau): weight, robustified chi, kernelized flag
@@ -699,222 +723,201 @@ __device__ __forceinline__ bool robustify(int kind, float tau, float chi, float&
   return true;
 }
 
+// ---------------------------------------------------------------------------------------------
+// k1b: per-correspondence linearisation + exact accumulation (a5)
+// ---------------------------------------------------------------------------------------------
+template <int DIM>
+struct LinAcc {  // per-thread partial sums: |term| < 2^21 and a thread stays below 512 terms -> 32 bits
+  static constexpr int P = (DIM == 3) ? 6 : 3;
+  static constexpr int NH = P * (P + 1) / 2;
+  int aH[NH], ab[P];
+  int chi_in, chi_in_lo, chi_out, chi_out_lo;
+  int n_in, n_out, n_sup;
+  __device__ __forceinline__ void clear() {
+#pragma unroll
+    for (int k = 0; k < NH; ++k) aH[k] = 0;
+#pragma unroll
+    for (int k = 0; k < P; ++k) ab[k] = 0;
+    chi_in = chi_in_lo = chi_out = chi_out_lo = 0;
+    n_in = n_out = n_sup = 0;
+  }
+};
+
+// gate + error/Jacobian rows + robust weight + fixed-point accumulation of ONE correspondence
+// (moving point i with normal, fixed point at cell-order position bpos with normal)
 template <int DIM, int FACTOR>
-__global__ void __launch_bounds__(256) linearize_kernel(const SliceArgs a) {
-  if (*a.stop) return;
+__device__ __forceinline__ void lin_one(const SliceArgs& a, const float* Ss, int i, int slot, int bpos, const float4 m,
+                                        const float4 nm, const float4 f, const float4 nf, LinAcc<DIM>& A) {
   constexpr int P = (DIM == 3) ? 6 : 3;
-  constexpr int NH = P * (P + 1) / 2;
-  __shared__ float Ss[16];
-  __shared__ unsigned long long sacc[kAcc];
-  if (threadIdx.x < 16) Ss[threadIdx.x] = a.S[threadIdx.x];
-  if (threadIdx.x < kAcc) sacc[threadIdx.x] = 0ull;
-  __syncthreads();
   const float s00 = Ss[0], s01 = Ss[1], s02 = Ss[2], s03 = Ss[3];
   const float s10 = Ss[4], s11 = Ss[5], s12 = Ss[6], s13 = Ss[7];
   const float s20 = Ss[8], s21 = Ss[9], s22 = Ss[10], s23 = Ss[11];
+  float t;
+  t = s00 * m.x; t = fmaf(s01, m.y, t); if (DIM == 3) t = fmaf(s02, m.z, t); const float qx = t + s03;
+  t = s10 * m.x; t = fmaf(s11, m.y, t); if (DIM == 3) t = fmaf(s12, m.z, t); const float qy = t + s13;
+  float qz = 0.f;
+  if (DIM == 3) { t = s20 * m.x; t = fmaf(s21, m.y, t); t = fmaf(s22, m.z, t); qz = t + s23; }
+  t = s00 * nm.x; t = fmaf(s01, nm.y, t); if (DIM == 3) t = fmaf(s02, nm.z, t); const float nqx = t;
+  t = s10 * nm.x; t = fmaf(s11, nm.y, t); if (DIM == 3) t = fmaf(s12, nm.z, t); const float nqy = t;
+  float nqz = 0.f;
+  if (DIM == 3) { t = s20 * nm.x; t = fmaf(s21, nm.y, t); t = fmaf(s22, nm.z, t); nqz = t; }
 
-  long long aH[NH], ab[P];
-  long long achi_in = 0, achi_out = 0;
-  int n_in = 0, n_out = 0, n_sup = 0;
-#pragma unroll
-  for (int k = 0; k < NH; ++k) aH[k] = 0;
-#pragma unroll
-  for (int k = 0; k < P; ++k) ab[k] = 0;
-
-  // software pipeline: the loads of the next query (slot -> gathered fixed point/normal) are in
-  // flight while the current one is linearised; the kernel is latency bound otherwise
-  const int stride = gridDim.x * blockDim.x;
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  int slot_n = (i < a.nm) ? a.c_fpos[i] : -1;
-  float4 m_n = zero4, nm_n = zero4, f_n = zero4, nf_n = zero4;
-  {
-    const int pn = a.gate ? slot_candidate(slot_n) : slot_n;
-    if (pn >= 0) {
-      m_n = a.mp[i]; nm_n = a.mn[i];
-      f_n = __ldg(a.fp + pn); nf_n = __ldg(a.fn + pn);
+  if (a.gate) {  // normal gate of the finder, n_f . (R_S n_m) >= normal_cos
+    float dot = fmaf(nf.y, nqy, nf.x * nqx);
+    if (DIM == 3) dot = fmaf(nf.z, nqz, dot);
+    const bool ok = !(dot < a.normal_cos);
+    if (ok != (slot >= 0)) a.c_fpos[i] = ok ? bpos : -(bpos + 2);
+    if (!ok) {
+      if (a.c_stat) a.c_stat[i] = SRRG2B_STAT_NONE;
+      return;
     }
   }
-  int slot_nn = (i + stride < a.nm) ? a.c_fpos[i + stride] : -1;
-  for (; i < a.nm; i += stride) {
-    const int slot = slot_n;
-    const float4 m = m_n, nm = nm_n, f = f_n, nf = nf_n;
-    // advance the pipeline
-    slot_n = slot_nn;
-    {
-      const int pn = a.gate ? slot_candidate(slot_n) : slot_n;  // gated-out slots are re-checked
-      if (pn >= 0) {
-        m_n = a.mp[i + stride]; nm_n = a.mn[i + stride];
-        f_n = __ldg(a.fp + pn); nf_n = __ldg(a.fn + pn);
-      }
-    }
-    slot_nn = (i + 2 * stride < a.nm) ? a.c_fpos[i + 2 * stride] : -1;
-    const int bpos = a.gate ? slot_candidate(slot) : slot;
-    if (bpos < 0) {
-      if (slot == kSlotSuppressed) {
-        ++n_sup;
-        if (a.c_stat) a.c_stat[i] = SRRG2B_STAT_SUPPRESSED;
-      } else if (a.c_stat) {
-        a.c_stat[i] = SRRG2B_STAT_NONE;
-      }
-      continue;
-    }
-    float t;
-    t = s00 * m.x; t = fmaf(s01, m.y, t); if (DIM == 3) t = fmaf(s02, m.z, t); const float qx = t + s03;
-    t = s10 * m.x; t = fmaf(s11, m.y, t); if (DIM == 3) t = fmaf(s12, m.z, t); const float qy = t + s13;
-    float qz = 0.f;
-    if (DIM == 3) { t = s20 * m.x; t = fmaf(s21, m.y, t); t = fmaf(s22, m.z, t); qz = t + s23; }
-    t = s00 * nm.x; t = fmaf(s01, nm.y, t); if (DIM == 3) t = fmaf(s02, nm.z, t); const float nqx = t;
-    t = s10 * nm.x; t = fmaf(s11, nm.y, t); if (DIM == 3) t = fmaf(s12, nm.z, t); const float nqy = t;
-    float nqz = 0.f;
-    if (DIM == 3) { t = s20 * nm.x; t = fmaf(s21, nm.y, t); t = fmaf(s22, nm.z, t); nqz = t; }
-
-    if (a.gate) {  // normal gate of the finder, n_f . (R_S n_m) >= normal_cos
-      float dot = fmaf(nf.y, nqy, nf.x * nqx);
-      if (DIM == 3) dot = fmaf(nf.z, nqz, dot);
-      const bool ok = !(dot < a.normal_cos);
-      if (ok != (slot >= 0)) a.c_fpos[i] = ok ? bpos : -(bpos + 2);
-      if (!ok) {
-        if (a.c_stat) a.c_stat[i] = SRRG2B_STAT_NONE;
-        continue;
-      }
-    }
-    // ---- error rows e, information om, Jacobian rows J (right perturbation of X) ----
-    constexpr int E = (FACTOR == SRRG2B_FACTOR_P2P) ? DIM : DIM + 1;
-    float e[E], om[E], J[E][P];
-    const float dx = qx - f.x, dy = qy - f.y, dz = qz - f.z;
-    const float rs = a.rs;
-    if (DIM == 3) {
-      const float R[3][3] = {{s00, s01, s02}, {s10, s11, s12}, {s20, s21, s22}};
-      if (FACTOR == SRRG2B_FACTOR_P2P) {
-        const float d[3] = {dx, dy, dz};
+  // ---- error rows e, information om, Jacobian rows J (right perturbation of X) ----
+  constexpr int E = (FACTOR == SRRG2B_FACTOR_P2P) ? DIM : DIM + 1;
+  float e[E], om[E], J[E][P];
+  const float dx = qx - f.x, dy = qy - f.y, dz = qz - f.z;
+  const float rs = a.rs;
+  if (DIM == 3) {
+    const float R[3][3] = {{s00, s01, s02}, {s10, s11, s12}, {s20, s21, s22}};
+    if (FACTOR == SRRG2B_FACTOR_P2P) {
+      const float d[3] = {dx, dy, dz};
 #pragma unroll
-        for (int r = 0; r < 3; ++r) {
-          J[r][0] = R[r][0]; J[r][1] = R[r][1]; J[r][2] = R[r][2];
-          t = R[r][2] * m.y; J[r][3] = -rs * fmaf(R[r][1], m.z, -t);
-          t = R[r][0] * m.z; J[r][4] = -rs * fmaf(R[r][2], m.x, -t);
-          t = R[r][1] * m.x; J[r][5] = -rs * fmaf(R[r][0], m.y, -t);
-          e[r] = d[r]; om[r] = a.ip;
-        }
-      } else {
-        float av[3];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          t = R[0][c] * nf.x; t = fmaf(R[1][c], nf.y, t); t = fmaf(R[2][c], nf.z, t);
-          av[c] = t;
-        }
-        J[0][0] = av[0]; J[0][1] = av[1]; J[0][2] = av[2];
-        t = m.z * av[1]; J[0][3] = rs * fmaf(m.y, av[2], -t);
-        t = m.x * av[2]; J[0][4] = rs * fmaf(m.z, av[0], -t);
-        t = m.y * av[0]; J[0][5] = rs * fmaf(m.x, av[1], -t);
-        e[0] = fmaf(nf.z, dz, fmaf(nf.y, dy, nf.x * dx)); om[0] = a.ip;
-        const float nqv[3] = {nqx, nqy, nqz}, nfv[3] = {nf.x, nf.y, nf.z};
-#pragma unroll
-        for (int r = 0; r < 3; ++r) {
-          J[r + 1][0] = 0.f; J[r + 1][1] = 0.f; J[r + 1][2] = 0.f;
-          t = R[r][2] * nm.y; J[r + 1][3] = -rs * fmaf(R[r][1], nm.z, -t);
-          t = R[r][0] * nm.z; J[r + 1][4] = -rs * fmaf(R[r][2], nm.x, -t);
-          t = R[r][1] * nm.x; J[r + 1][5] = -rs * fmaf(R[r][0], nm.y, -t);
-          e[r + 1] = nqv[r] - nfv[r]; om[r + 1] = a.in_;
-        }
+      for (int r = 0; r < 3; ++r) {
+        J[r][0] = R[r][0]; J[r][1] = R[r][1]; J[r][2] = R[r][2];
+        t = R[r][2] * m.y; J[r][3] = -rs * fmaf(R[r][1], m.z, -t);
+        t = R[r][0] * m.z; J[r][4] = -rs * fmaf(R[r][2], m.x, -t);
+        t = R[r][1] * m.x; J[r][5] = -rs * fmaf(R[r][0], m.y, -t);
+        e[r] = d[r]; om[r] = a.ip;
       }
     } else {
-      const float R[2][2] = {{s00, s01}, {s10, s11}};
-      if (FACTOR == SRRG2B_FACTOR_P2P) {
-        const float d[2] = {dx, dy};
+      float av[3];
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
-          J[r][0] = R[r][0]; J[r][1] = R[r][1];
-          t = R[r][0] * m.y; J[r][2] = fmaf(R[r][1], m.x, -t);
-          e[r] = d[r]; om[r] = a.ip;
-        }
-      } else {
-        float av[2];
+      for (int c = 0; c < 3; ++c) {
+        t = R[0][c] * nf.x; t = fmaf(R[1][c], nf.y, t); t = fmaf(R[2][c], nf.z, t);
+        av[c] = t;
+      }
+      J[0][0] = av[0]; J[0][1] = av[1]; J[0][2] = av[2];
+      t = m.z * av[1]; J[0][3] = rs * fmaf(m.y, av[2], -t);
+      t = m.x * av[2]; J[0][4] = rs * fmaf(m.z, av[0], -t);
+      t = m.y * av[0]; J[0][5] = rs * fmaf(m.x, av[1], -t);
+      e[0] = fmaf(nf.z, dz, fmaf(nf.y, dy, nf.x * dx)); om[0] = a.ip;
+      const float nqv[3] = {nqx, nqy, nqz}, nfv[3] = {nf.x, nf.y, nf.z};
 #pragma unroll
-        for (int c = 0; c < 2; ++c) av[c] = fmaf(R[1][c], nf.y, R[0][c] * nf.x);
-        t = av[0] * m.y;
-        J[0][0] = av[0]; J[0][1] = av[1]; J[0][2] = fmaf(av[1], m.x, -t);
-        e[0] = fmaf(nf.y, dy, nf.x * dx); om[0] = a.ip;
-        const float nqv[2] = {nqx, nqy}, nfv[2] = {nf.x, nf.y};
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-          J[r + 1][0] = 0.f; J[r + 1][1] = 0.f;
-          t = R[r][0] * nm.y; J[r + 1][2] = fmaf(R[r][1], nm.x, -t);
-          e[r + 1] = nqv[r] - nfv[r]; om[r + 1] = a.in_;
-        }
+      for (int r = 0; r < 3; ++r) {
+        J[r + 1][0] = 0.f; J[r + 1][1] = 0.f; J[r + 1][2] = 0.f;
+        t = R[r][2] * nm.y; J[r + 1][3] = -rs * fmaf(R[r][1], nm.z, -t);
+        t = R[r][0] * nm.z; J[r + 1][4] = -rs * fmaf(R[r][2], nm.x, -t);
+        t = R[r][1] * nm.x; J[r + 1][5] = -rs * fmaf(R[r][0], nm.y, -t);
+        e[r + 1] = nqv[r] - nfv[r]; om[r + 1] = a.in_;
       }
     }
-    float chi = (om[0] * e[0]) * e[0];
+  } else {
+    const float R[2][2] = {{s00, s01}, {s10, s11}};
+    if (FACTOR == SRRG2B_FACTOR_P2P) {
+      const float d[2] = {dx, dy};
 #pragma unroll
-    for (int r = 1; r < E; ++r) chi = fmaf(om[r] * e[r], e[r], chi);
-    if (a.c_chi) a.c_chi[i] = chi;
-    if (!(chi == chi) || isinf(chi)) {
-      ++n_sup;
-      if (a.c_stat) a.c_stat[i] = SRRG2B_STAT_SUPPRESSED;
-      continue;
-    }
-    float w, rho;
-    const bool kern = robustify(a.rob, a.tau, chi, w, rho);
-    if (kern) { ++n_out; achi_out += to_fixed(rho, a.sc); } else { ++n_in; achi_in += to_fixed(chi, a.sc); }
-    if (a.c_stat) a.c_stat[i] = kern ? SRRG2B_STAT_KERNELIZED : SRRG2B_STAT_INLIER;
-    // ---- H += J^T (w Om) J, b += J^T (w Om) e; structural zeros of the normal rows skipped ----
-    constexpr int TR = (FACTOR == SRRG2B_FACTOR_P2P) ? 0 : DIM;  // columns < TR are zero in rows >= 1
-    float u[E][P];
-#pragma unroll
-    for (int r = 0; r < E; ++r) {
-      const float s = w * om[r];
-#pragma unroll
-      for (int c = 0; c < P; ++c) u[r][c] = s * J[r][c];
-    }
-    int hslot = 0;
-#pragma unroll
-    for (int ii = 0; ii < P; ++ii) {
-#pragma unroll
-      for (int jj = ii; jj < P; ++jj) {
-        float h = u[0][ii] * J[0][jj];
-        if (ii >= TR && jj >= TR) {
-#pragma unroll
-          for (int r = 1; r < E; ++r) h = fmaf(u[r][ii], J[r][jj], h);
-        }
-        aH[hslot++] += to_fixed(h, a.sH);
+      for (int r = 0; r < 2; ++r) {
+        J[r][0] = R[r][0]; J[r][1] = R[r][1];
+        t = R[r][0] * m.y; J[r][2] = fmaf(R[r][1], m.x, -t);
+        e[r] = d[r]; om[r] = a.ip;
       }
-    }
+    } else {
+      float av[2];
 #pragma unroll
-    for (int ii = 0; ii < P; ++ii) {
-      float g = u[0][ii] * e[0];
-      if (ii >= TR) {
+      for (int c = 0; c < 2; ++c) av[c] = fmaf(R[1][c], nf.y, R[0][c] * nf.x);
+      t = av[0] * m.y;
+      J[0][0] = av[0]; J[0][1] = av[1]; J[0][2] = fmaf(av[1], m.x, -t);
+      e[0] = fmaf(nf.y, dy, nf.x * dx); om[0] = a.ip;
+      const float nqv[2] = {nqx, nqy}, nfv[2] = {nf.x, nf.y};
 #pragma unroll
-        for (int r = 1; r < E; ++r) g = fmaf(u[r][ii], e[r], g);
+      for (int r = 0; r < 2; ++r) {
+        J[r + 1][0] = 0.f; J[r + 1][1] = 0.f;
+        t = R[r][0] * nm.y; J[r + 1][2] = fmaf(R[r][1], nm.x, -t);
+        e[r + 1] = nqv[r] - nfv[r]; om[r + 1] = a.in_;
       }
-      ab[ii] += to_fixed(g, a.sb);
     }
   }
-
-  // ---- exact integer block reduction: warp shuffles -> shared atomics -> one global atomic per slot
-  auto wsum = [](long long v) {
+  float chi = (om[0] * e[0]) * e[0];
 #pragma unroll
-    for (int off = 16; off; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-    return v;
+  for (int r = 1; r < E; ++r) chi = fmaf(om[r] * e[r], e[r], chi);
+  if (a.c_chi) a.c_chi[i] = chi;
+  if (!(chi == chi) || isinf(chi)) {
+    ++A.n_sup;
+    if (a.c_stat) a.c_stat[i] = SRRG2B_STAT_SUPPRESSED;
+    return;
+  }
+  float w, rho;
+  const bool kern = robustify(a.rob, a.tau, chi, w, rho);
+  if (kern) { ++A.n_out; to_fixed2(rho, a.fM[kKChi], a.fB[kKChi], a.fM[kKChiLo], a.fB[kKChiLo], A.chi_out, A.chi_out_lo); }
+  else { ++A.n_in; to_fixed2(chi, a.fM[kKChi], a.fB[kKChi], a.fM[kKChiLo], a.fB[kKChiLo], A.chi_in, A.chi_in_lo); }
+  if (a.c_stat) a.c_stat[i] = kern ? SRRG2B_STAT_KERNELIZED : SRRG2B_STAT_INLIER;
+  // ---- H += J^T (w Om) J, b += J^T (w Om) e; structural zeros of the normal rows skipped ----
+  constexpr int TR = (FACTOR == SRRG2B_FACTOR_P2P) ? 0 : DIM;  // columns < TR are zero in rows >= 1
+  float u[E][P];
+#pragma unroll
+  for (int r = 0; r < E; ++r) {
+    const float s = w * om[r];
+#pragma unroll
+    for (int c = 0; c < P; ++c) u[r][c] = s * J[r][c];
+  }
+  int hslot = 0;
+#pragma unroll
+  for (int ii = 0; ii < P; ++ii) {
+#pragma unroll
+    for (int jj = ii; jj < P; ++jj) {
+      float h = u[0][ii] * J[0][jj];
+      if (ii >= TR && jj >= TR) {
+#pragma unroll
+        for (int r = 1; r < E; ++r) h = fmaf(u[r][ii], J[r][jj], h);
+      }
+      constexpr int T = DIM;  // columns < T: translation part of the perturbation
+      const int cls = (jj < T) ? kKHtt : ((ii < T) ? kKHtr : kKHrr);
+      A.aH[hslot++] += to_fixed(h, a.fM[cls], a.fB[cls]);
+    }
+  }
+#pragma unroll
+  for (int ii = 0; ii < P; ++ii) {
+    float g = u[0][ii] * e[0];
+    if (ii >= TR) {
+#pragma unroll
+      for (int r = 1; r < E; ++r) g = fmaf(u[r][ii], e[r], g);
+    }
+    A.ab[ii] += to_fixed(g, a.fM[ii < DIM ? kKBt : kKBr], a.fB[ii < DIM ? kKBt : kKBr]);
+  }
+}
+
+// exact integer block reduction of the per-thread partial sums: two REDUX per slot (16-bit halves
+// cannot overflow the 32-bit warp sum) -> 64-bit shared atomics -> one global atomic per slot / CTA.
+// sacc must be zeroed (and the block synchronised) by the caller before any thread gets here.
+template <int DIM>
+__device__ __forceinline__ void lin_flush(const SliceArgs& a, const LinAcc<DIM>& A, unsigned long long* sacc) {
+  constexpr int P = LinAcc<DIM>::P, NH = LinAcc<DIM>::NH;
+  auto wsum = [](int v) -> long long {
+    const unsigned lo = __reduce_add_sync(0xffffffffu, (unsigned) v & 0xffffu);
+    const int hi = __reduce_add_sync(0xffffffffu, v >> 16);
+    return ((long long) hi << 16) + (long long) lo;
   };
   const int lane = threadIdx.x & 31;
 #pragma unroll
   for (int k = 0; k < NH; ++k) {
-    const long long v = wsum(aH[k]);
+    const long long v = wsum(A.aH[k]);
     if (lane == 0 && v) atomicAdd(&sacc[k], (unsigned long long) v);
   }
 #pragma unroll
   for (int k = 0; k < P; ++k) {
-    const long long v = wsum(ab[k]);
+    const long long v = wsum(A.ab[k]);
     if (lane == 0 && v) atomicAdd(&sacc[kAccB + k], (unsigned long long) v);
   }
   {
-    long long v = wsum(achi_in);
-    if (lane == 0 && v) atomicAdd(&sacc[kAccChiIn], (unsigned long long) v);
-    v = wsum(achi_out);
-    if (lane == 0 && v) atomicAdd(&sacc[kAccChiOut], (unsigned long long) v);
-    const int ni = __reduce_add_sync(0xffffffffu, n_in);
-    const int no = __reduce_add_sync(0xffffffffu, n_out);
-    const int ns = __reduce_add_sync(0xffffffffu, n_sup);
+    const int cv[4] = {A.chi_in, A.chi_in_lo, A.chi_out, A.chi_out_lo};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const long long v = wsum(cv[k]);
+      if (lane == 0 && v) atomicAdd(&sacc[kAccChiIn + k], (unsigned long long) v);
+    }
+    const int ni = __reduce_add_sync(0xffffffffu, A.n_in);
+    const int no = __reduce_add_sync(0xffffffffu, A.n_out);
+    const int ns = __reduce_add_sync(0xffffffffu, A.n_sup);
     if (lane == 0) {
       if (ni) atomicAdd(&sacc[kAccNIn], (unsigned long long) ni);
       if (no) atomicAdd(&sacc[kAccNOut], (unsigned long long) no);
@@ -926,6 +929,157 @@ __global__ void __launch_bounds__(256) linearize_kernel(const SliceArgs a) {
     const unsigned long long v = sacc[threadIdx.x];
     if (v) atomicAdd(&a.acc[threadIdx.x], v);
   }
+}
+
+// Phase 2 / tail kernel.  Large work lists: the far list of phase 1 (see nn_far_body).  Short work
+// lists (converged iterations: a few hundred queries fail the coherence check): one warp per query
+// does the whole job here -- search of all rows, slot + certified bound, and the linearisation of
+// that query -- because at this size the thread-per-query kernels would be pure load latency.
+template <int DIM, int FACTOR>
+__global__ void __launch_bounds__(256) nn_far_kernel(const SliceArgs a) {
+  if (*a.stop) return;
+  const bool all = !a.use_list || *a.list_all;
+  const int n_work = all ? a.nm : *a.work_count;
+  const bool tail = small_work_list(a, all, n_work);
+  const int n_far = tail ? n_work : *a.far_count;
+  if (n_far == 0) return;
+  __shared__ float S[16];
+  __shared__ int rows[kRowTable];
+  __shared__ unsigned long long sacc[kAcc];
+  if (threadIdx.x < 16) S[threadIdx.x] = a.S[threadIdx.x];
+  if (threadIdx.x < kAcc) sacc[threadIdx.x] = 0ull;
+  const int R = a.R;
+  const int K = (DIM == 3) ? (2 * R + 1) * (2 * R + 1) : (2 * R + 1);
+  for (int k = threadIdx.x; k < K; k += blockDim.x)
+    rows[k] = (DIM == 3) ? *reinterpret_cast<const int*>(c_rows3[k]) : *reinterpret_cast<const int*>(c_rows2[k]);
+  __syncthreads();
+  const float cell = __fdiv_rn(1.f, a.inv_cell);
+  const bool track2 = *a.track2 != 0;
+  if (!tail) {
+    if (track2) nn_far_body<DIM, true>(a, S, rows, K, cell, n_far, a.far_list, nullptr);
+    else nn_far_body<DIM, false>(a, S, rows, K, cell, n_far, a.far_list, nullptr);
+    return;
+  }
+  LinAcc<DIM> A;
+  A.clear();
+  if (track2) nn_far_body<DIM, true, FACTOR>(a, S, rows, K, cell, n_far, a.work_list, &A);
+  else nn_far_body<DIM, false, FACTOR>(a, S, rows, K, cell, n_far, a.work_list, &A);
+  lin_flush<DIM>(a, A, sacc);
+}
+
+// CHECK = true is the first pass of an iteration once bounds exist: the temporal-coherence test is
+// fused with the linearisation (one read of the query, its neighbour and both normals serves both);
+// queries that fail it are appended to the work list for nn_kernel / nn_far_kernel, and the
+// CHECK = false pass then linearises exactly those.
+template <int DIM, int FACTOR, bool CHECK>
+__global__ void __launch_bounds__(256) linearize_kernel(const SliceArgs a) {
+  if (*a.stop) return;
+  const bool all = !a.use_list || *a.list_all;
+  if (CHECK && all) return;  // nothing is certified: everything goes through the search path
+  __shared__ float Ss[16], Sl[16];
+  __shared__ unsigned long long sacc[kAcc];
+  if (threadIdx.x < 16) { Ss[threadIdx.x] = a.S[threadIdx.x]; Sl[threadIdx.x] = CHECK ? a.S_lb[threadIdx.x] : 0.f; }
+  if (threadIdx.x < kAcc) sacc[threadIdx.x] = 0ull;
+  __syncthreads();
+  LinAcc<DIM> A;
+  A.clear();
+
+  // software pipeline, three deep: index (w + 2 strides) -> slot / bound (w + 1 stride) -> point data
+  // (w); the loads of later queries are in flight while the current one is linearised
+  const int stride = gridDim.x * blockDim.x;
+  const int n_work = CHECK ? a.nm : (all ? a.nm : *a.work_count);
+  if (!CHECK && small_work_list(a, all, n_work)) return;  // nn_far_kernel linearises short lists itself
+  const bool direct = CHECK || all;
+  auto index_of = [&](int w) { return w < n_work ? (direct ? w : a.work_list[w]) : -1; };
+  const bool regate = a.gate != 0;  // gated-out slots are re-checked every iteration
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  int w = blockIdx.x * blockDim.x + threadIdx.x;
+  int i_n = index_of(w);
+  int slot_n = i_n >= 0 ? a.c_fpos[i_n] : -1;
+  float lb_n = (CHECK && i_n >= 0) ? a.c_lb[i_n] : 0.f;
+  float4 m_n = zero4, nm_n = zero4, f_n = zero4, nf_n = zero4;
+  {
+    const int pn = regate ? slot_candidate(slot_n) : slot_n;
+    if (i_n >= 0 && (pn >= 0 || CHECK)) m_n = a.mp[i_n];
+    if (pn >= 0) {
+      nm_n = a.mn[i_n];
+      f_n = __ldg(a.fp + pn); nf_n = __ldg(a.fn + pn);
+    }
+  }
+  int i_nn = index_of(w + stride);
+  int slot_nn = i_nn >= 0 ? a.c_fpos[i_nn] : -1;
+  float lb_nn = (CHECK && i_nn >= 0) ? a.c_lb[i_nn] : 0.f;
+  int i_nnn = index_of(w + 2 * stride);
+  for (; w < n_work; w += stride) {
+    const int i = i_n;
+    const int slot = slot_n;
+    const float lb_old = lb_n;
+    const float4 m = m_n, nm = nm_n, f = f_n, nf = nf_n;
+    // advance the pipeline
+    i_n = i_nn; slot_n = slot_nn; lb_n = lb_nn;
+    {
+      const int pn = regate ? slot_candidate(slot_n) : slot_n;
+      if (i_n >= 0 && (pn >= 0 || CHECK)) m_n = a.mp[i_n];
+      if (pn >= 0) {
+        nm_n = a.mn[i_n];
+        f_n = __ldg(a.fp + pn); nf_n = __ldg(a.fn + pn);
+      }
+    }
+    i_nn = i_nnn;
+    slot_nn = i_nn >= 0 ? a.c_fpos[i_nn] : -1;
+    lb_nn = (CHECK && i_nn >= 0) ? a.c_lb[i_nn] : 0.f;
+    i_nnn = index_of(w + 3 * stride);
+    const int bpos = regate ? slot_candidate(slot) : slot;
+    if (CHECK) {
+      // exact temporal coherence (see the NN kernels): keep the neighbour / the "none" verdict when
+      // the certified bound minus the query's motion still proves it; else hand over to the search
+      bool keep = false, none = false;
+      float lbn = 0.f;
+      if (lb_old > 0.f) {
+        float qx, qy, qz, ox, oy, oz;
+        nn_transform<DIM>(Ss, m, qx, qy, qz);
+        nn_transform<DIM>(Sl, m, ox, oy, oz);
+        const float ex = qx - ox, ey = qy - oy, ez = qz - oz;
+        const float delta = __fsqrt_rn(fmaf(ez, ez, fmaf(ey, ey, ex * ex)));
+        lbn = lb_old * (1.f - 1e-5f) - delta * (1.f + 1e-5f);
+        if (lbn > 0.f) {
+          if (bpos >= 0) {
+            const float ddx = qx - f.x, ddy = qy - f.y, ddz = qz - f.z;
+            float d2 = fmaf(ddy, ddy, ddx * ddx);
+            if (DIM == 3) d2 = fmaf(ddz, ddz, d2);
+            keep = d2 <= a.md2 && d2 * (1.f + 1e-5f) < lbn * lbn;
+          } else if (slot == -1) {
+            none = lbn * lbn > a.md2 * (1.f + 1e-5f);
+          }
+        }
+      }
+      if (keep || none) {
+        a.c_lb[i] = lbn;
+        if (none) {
+          if (a.c_stat) a.c_stat[i] = SRRG2B_STAT_NONE;
+          continue;
+        }
+      } else {
+        cg::coalesced_group g = cg::coalesced_threads();
+        int base = 0;
+        if (g.thread_rank() == 0) base = atomicAdd(a.work_count, (int) g.size());
+        base = g.shfl(base, 0);
+        a.work_list[base + g.thread_rank()] = i;
+        continue;
+      }
+    }
+    if (bpos < 0) {
+      if (slot == kSlotSuppressed) {
+        ++A.n_sup;
+        if (a.c_stat) a.c_stat[i] = SRRG2B_STAT_SUPPRESSED;
+      } else if (a.c_stat) {
+        a.c_stat[i] = SRRG2B_STAT_NONE;
+      }
+      continue;
+    }
+    lin_one<DIM, FACTOR>(a, Ss, i, slot, bpos, m, nm, f, nf, A);
+  }
+  lin_flush<DIM>(a, A, sacc);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -994,6 +1148,9 @@ __global__ void icp_init_kernel(const SolveArgs a, DevState* st, Mat4f T0, int a
     st->ncorr[s] = 0;
     // the motion from the previous call's pose is unknown: certify bounds only when forced to
     if (!keep_stats) st->track2[s] = (a.sl[s].track2_mode == 1) ? 1 : 0;
+    // a fresh compute() starts from an arbitrary guess: search everything; the inlier-only second
+    // run continues from certified bounds
+    if (!keep_stats) st->list_all[s] = 1;  // (the last solve step already set it for a continued run)
   }
   st->stop = 0;
   st->not_enough_corr = 0;
@@ -1011,6 +1168,7 @@ __global__ void set_S_kernel(DevState* st, int slice, Mat4f S, int track2) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     st->S[slice] = S;
     st->track2[slice] = track2;
+    st->list_all[slice] = 1;
     for (int k = 0; k < kAcc; ++k) st->acc[slice][k] = 0ull;
     st->stop = 0;
   }
@@ -1074,17 +1232,20 @@ __global__ void icp_solve_kernel(const SolveArgs a, DevState* st) {
     for (int i = 0; i < P; ++i) {
 #pragma unroll
       for (int j = i; j < P; ++j) {
-        const double v = __ll2double_rn((long long) acc[slot++]) * sl.invH;
+        const double v = __ll2double_rn((long long) acc[slot++]) * sl.invk[(j < DIM) ? kKHtt : ((i < DIM) ? kKHtr : kKHrr)];
         H[i * P + j] = H[i * P + j] + v;
         if (j != i) H[j * P + i] = H[j * P + i] + v;
       }
     }
 #pragma unroll
-    for (int i = 0; i < P; ++i) b[i] = b[i] + __ll2double_rn((long long) acc[kAccB + i]) * sl.invb;
+    for (int i = 0; i < P; ++i)
+      b[i] = b[i] + __ll2double_rn((long long) acc[kAccB + i]) * sl.invk[(i < DIM) ? kKBt : kKBr];
     const long long ni = (long long) acc[kAccNIn], no = (long long) acc[kAccNOut], ns = (long long) acc[kAccNSup];
     s.num_inliers += ni; s.num_outliers += no; s.num_suppressed += ns; s.num_correspondences += ni + no + ns;
-    s.chi_inliers += __ll2double_rn((long long) acc[kAccChiIn]) * sl.invchi;
-    s.chi_outliers += __ll2double_rn((long long) acc[kAccChiOut]) * sl.invchi;
+    s.chi_inliers += __ll2double_rn((long long) acc[kAccChiIn]) * sl.invk[kKChi] +
+                     __ll2double_rn((long long) acc[kAccChiIn + 1]) * sl.invk[kKChiLo];
+    s.chi_outliers += __ll2double_rn((long long) acc[kAccChiOut]) * sl.invk[kKChi] +
+                      __ll2double_rn((long long) acc[kAccChiOut + 1]) * sl.invk[kKChiLo];
     const long long n = ni + no + ns;
     st->ncorr[k] = n;
     total += n;
@@ -1122,6 +1283,7 @@ __global__ void icp_solve_kernel(const SolveArgs a, DevState* st) {
       }
       const float motion = sqrtf(dr) * 1.7321f * a.sl[k].coord_bound + sqrtf(dt);
       const int mode = a.sl[k].track2_mode;
+      st->list_all[k] = st->track2[k] ? 0 : 1;  // bounds exist only if the pass just done certified them
       st->track2[k] = (mode == 1) || (mode == 2 && motion < 0.125f * a.sl[k].cell) ? 1 : 0;
     }
     st->S[k] = Sn;

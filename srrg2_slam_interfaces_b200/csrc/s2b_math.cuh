@@ -360,8 +360,15 @@ S2B_HD bool prior_accumulate(int dim, int variable, const Mat4f& Z, const Mat4f&
 }
 
 // ---- fixed-point scale exponents for the exact integer accumulation ----------------------------
+// Per-TERM magnitude bounds (log2), from global quantities only:
+//   translation columns of J : |entry| <= 2            rotation columns: <= max(2, 4 |coord|_max) (Jb bits)
+//   error rows               : <= max(max_distance, 2) (eb bits)
+//   information              : <= max(info_point, info_normal, 1) (wb bits), <= 4 rows (2 bits)
+// A term is stored as round(term * 2^k), k = 21 - bound, so |term * 2^k| < 2^21 (terms are clamped to
+// the bound first).  chi gets a second, 2^20 times finer, residual word.
+enum { kKHtt = 0, kKHtr = 1, kKHrr = 2, kKBt = 3, kKBr = 4, kKChi = 5, kKChiLo = 6, kKCount = 7 };
 struct Scales {
-  int kH, kb, kchi;
+  int k[kKCount];
 };
 
 inline int ceil_log2_float(float x) {
@@ -373,8 +380,7 @@ inline int ceil_log2_float(float x) {
 
 inline Scales choose_scales(int64_t n_global, float coord_bound, float max_distance, float info_point,
                             float info_normal) {
-  int nb = 0;
-  while ((int64_t(1) << nb) < n_global) ++nb;
+  (void) n_global;
   float jm = 4.f * coord_bound;
   if (jm < 2.f) jm = 2.f;
   const int Jb = ceil_log2_float(jm);
@@ -384,12 +390,13 @@ inline Scales choose_scales(int64_t n_global, float coord_bound, float max_dista
   const float em = max_distance > 2.f ? max_distance : 2.f;
   const int eb = ceil_log2_float(em);
   Scales s;
-  s.kH = 62 - nb - 2 - wb - 2 * Jb;
-  s.kb = 62 - nb - 2 - wb - Jb - eb;
-  s.kchi = 62 - nb - 2 - wb - 2 * eb;
-  if (s.kH > 60) s.kH = 60;
-  if (s.kb > 60) s.kb = 60;
-  if (s.kchi > 60) s.kchi = 60;
+  s.k[kKHtt] = 21 - (2 + wb + 2);
+  s.k[kKHtr] = 21 - (2 + wb + 1 + Jb);
+  s.k[kKHrr] = 21 - (2 + wb + 2 * Jb);
+  s.k[kKBt] = 21 - (2 + wb + 1 + eb);
+  s.k[kKBr] = 21 - (2 + wb + Jb + eb);
+  s.k[kKChi] = 21 - (2 + wb + 2 * eb);
+  s.k[kKChiLo] = s.k[kKChi] + 20;
   return s;
 }
 
