@@ -50,6 +50,7 @@ struct SolveSlice {
   float* S_lb;                // slice's bound-validity transform (committed every iteration)
   float cell, coord_bound;    // NN cell edge / max |coordinate| of the moving cloud
   int track2_mode;            // 0 never, 1 always, 2 automatic (small motion)
+  float track2_frac;          // automatic: certify once the per-iteration motion bound is below this many cells
 };
 
 struct SolveArgs {
@@ -323,9 +324,8 @@ struct NNQuery {
 };
 
 template <int DIM, bool TRACK2>
-__device__ __forceinline__ void nn_consider(const SliceArgs& a, NNQuery& q, int p) {
+__device__ __forceinline__ void nn_consider_pt(NNQuery& q, int p, const float4 c) {
   if (TRACK2 && p == q.bpos) return;  // the warm-start candidate met again during the walk
-  const float4 c = __ldg(a.fp + p);
   const float ddx = q.qx - c.x, ddy = q.qy - c.y, ddz = q.qz - c.z;
   float d2 = fmaf(ddy, ddy, ddx * ddx);
   if (DIM == 3) d2 = fmaf(ddz, ddz, d2);
@@ -336,6 +336,10 @@ __device__ __forceinline__ void nn_consider(const SliceArgs& a, NNQuery& q, int 
   } else if (TRACK2) {
     q.sd2 = fminf(q.sd2, d2);
   }
+}
+template <int DIM, bool TRACK2>
+__device__ __forceinline__ void nn_consider(const SliceArgs& a, NNQuery& q, int p) {
+  nn_consider_pt<DIM, TRACK2>(q, p, __ldg(a.fp + p));
 }
 
 // scan the part of cell row (y, z) that can still matter, given the conservative squared distance
@@ -351,8 +355,20 @@ __device__ __forceinline__ void nn_scan_row(const SliceArgs& a, NNQuery& q, int 
   const int row = (z * a.ny + y) * a.nx;
   const int ps = __ldg(a.cell_start + row + xa);
   const int pe = __ldg(a.cell_start + row + xb + 1);
+  // candidates in ascending position, four loads in flight per step (the compare chain is serial,
+  // the loads are not): out-of-range slots re-read the last point and are not considered
+  const int last = pe - 1;
 #pragma unroll 1
-  for (int p = ps; p < pe; ++p) nn_consider<DIM, TRACK2>(a, q, p);
+  for (int p = ps; p < pe; p += 4) {
+    const float4 c0 = __ldg(a.fp + p);
+    const float4 c1 = __ldg(a.fp + min(p + 1, last));
+    const float4 c2 = __ldg(a.fp + min(p + 2, last));
+    const float4 c3 = __ldg(a.fp + min(p + 3, last));
+    nn_consider_pt<DIM, TRACK2>(q, p, c0);
+    if (p + 1 < pe) nn_consider_pt<DIM, TRACK2>(q, p + 1, c1);
+    if (p + 2 < pe) nn_consider_pt<DIM, TRACK2>(q, p + 2, c2);
+    if (p + 3 < pe) nn_consider_pt<DIM, TRACK2>(q, p + 3, c3);
+  }
 }
 
 template <int DIM>
@@ -514,9 +530,10 @@ __global__ void __launch_bounds__(256) nn_kernel(const SliceArgs a) {
 }
 
 // Phase 2: the queries phase 1 could not settle (worklist).  These are few but expensive
-// (typically no neighbour at all, so nothing prunes), so one WARP takes one query: lane l scans row
-// l (+32, ...) of the whole (2R+1)^(DIM-1) neighbourhood, then a shuffle reduction merges the
-// lanes' (nearest, second nearest) pairs and lane 0 applies the gate and writes slot and bound.
+// (typically no neighbour at all, so nothing prunes), so one WARP takes one query: the lanes fetch
+// the bounds of the (2R+1)^(DIM-1) rows, the points of all rows are dealt out to the lanes, then a
+// shuffle reduction merges the lanes' (nearest, second nearest) pairs and lane 0 applies the gate
+// and writes slot and bound.
 template <int DIM>
 struct LinAcc;
 template <int DIM, int FACTOR>
@@ -525,7 +542,7 @@ __device__ __forceinline__ void lin_one(const SliceArgs& a, const float* Ss, int
 
 template <int DIM, bool TRACK2, int FACTOR = SRRG2B_FACTOR_P2P>
 __device__ __forceinline__ void nn_far_body(const SliceArgs& a, const float* S, const int* rows, int K, float cell,
-                                            int n_far, const int* list, LinAcc<DIM>* lin) {
+                                            int n_far, const int* list, LinAcc<DIM>* lin, int w_first, int w_stride) {
   const int lane = threadIdx.x & 31;
   if (!lin && n_far > (a.nm >> 4)) {
     // long worklist (large initial misalignment): one THREAD per query, rows nearest ring first
@@ -560,8 +577,7 @@ __device__ __forceinline__ void nn_far_body(const SliceArgs& a, const float* S, 
     }
     return;
   }
-  const int warps_per_block = blockDim.x >> 5;
-  for (int w = blockIdx.x * warps_per_block + (threadIdx.x >> 5); w < n_far; w += gridDim.x * warps_per_block) {
+  for (int w = w_first; w < n_far; w += w_stride) {
     const int i = list[w];
     NNQuery q;
     const float4 m = a.mp[i];
@@ -569,34 +585,85 @@ __device__ __forceinline__ void nn_far_body(const SliceArgs& a, const float* S, 
     const int old_slot = a.c_fpos[i];
     const int p0 = slot_candidate(old_slot);
     if (a.warm && p0 >= 0) nn_consider<DIM, TRACK2>(a, q, p0);
-    for (int k = lane; k < K; k += 32) {
-      const int e = rows[k];
-      const int dy = (int) (signed char) (e & 0xff), dz = (int) (signed char) ((e >> 8) & 0xff);
-      const int y = q.cy + dy, z = q.cz + dz;
-      if (y < 0 || y >= a.ny || z < 0 || z >= a.nz) continue;
-      const float gy = axis_gap(dy, q.fry) * cell;
-      float lb2 = gy * gy;
-      if (DIM == 3) {
-        const float gz = axis_gap(dz, q.frz) * cell;
-        lb2 = fmaf(gz, gz, lb2);
+    // the warp takes the rows 32 at a time: lane -> bounds of one row, then the points of all 32 rows
+    // are dealt out to the lanes round robin (a handful of dependent loads per query instead of a
+    // serial walk per row); every lane keeps its own (nearest, second nearest) pair
+    // two stages: rings 0-1 first, merged across the warp, so that the outer rings are pruned with the
+    // radius the near rows established (nearly always to nothing)
+    const int K1 = min(K, (DIM == 3 ? 9 : 3));
+    for (int stage = 0; stage < 2; ++stage) {
+      const int kb = stage ? K1 : 0, ke = stage ? K : K1;
+      if (kb >= ke) break;
+      for (int k0 = kb; k0 < ke; k0 += 32) {
+        int ps = 0, cnt = 0;
+        const int k = k0 + lane;
+        if (k < ke) {
+          const int e = rows[k];
+          const int dy = (int) (signed char) (e & 0xff), dz = (int) (signed char) ((e >> 8) & 0xff);
+          const int y = q.cy + dy, z = q.cz + dz;
+          if (y >= 0 && y < a.ny && z >= 0 && z < a.nz) {
+            const float gy = axis_gap(dy, q.fry) * cell;
+            float lb2 = gy * gy;
+            if (DIM == 3) {
+              const float gz = axis_gap(dz, q.frz) * cell;
+              lb2 = fmaf(gz, gz, lb2);
+            }
+            const float pr2 = TRACK2 ? q.sd2 : q.bd2;
+            if (!(lb2 > pr2)) {
+              const float rr = __fsqrt_rn(fmaxf(pr2 - lb2, 0.f)) * a.inv_cell + 2e-3f;
+              const int xa = max(max((int) floorf(q.cfx - rr), q.cx - a.R), 0);
+              const int xb = min(min((int) floorf(q.cfx + rr), q.cx + a.R), a.nx - 1);
+              if (xa <= xb) {
+                const int row = (z * a.ny + y) * a.nx;
+                ps = __ldg(a.cell_start + row + xa);
+                cnt = __ldg(a.cell_start + row + xb + 1) - ps;
+              }
+            }
+          }
+        }
+        int incl = cnt;
+  #pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+          const int v = __shfl_up_sync(0xffffffffu, incl, off);
+          if (lane >= off) incl += v;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        const int excl = incl - cnt;
+        for (int t0 = 0; t0 < total; t0 += 64) {
+          // candidate t lives in the last row whose exclusive prefix is <= t (empty rows are skipped)
+          const int ta = t0 + lane, tb = t0 + 32 + lane;
+          int ra = 0, rb = 0;
+  #pragma unroll
+          for (int step = 16; step; step >>= 1) {
+            const int ea = __shfl_sync(0xffffffffu, excl, ra + step);
+            const int eb = __shfl_sync(0xffffffffu, excl, rb + step);
+            if (ea <= ta) ra += step;
+            if (eb <= tb) rb += step;
+          }
+          const int pa = __shfl_sync(0xffffffffu, ps, ra) + (ta - __shfl_sync(0xffffffffu, excl, ra));
+          const int pb = __shfl_sync(0xffffffffu, ps, rb) + (tb - __shfl_sync(0xffffffffu, excl, rb));
+          float4 ca, cb;
+          if (ta < total) ca = __ldg(a.fp + pa);
+          if (tb < total) cb = __ldg(a.fp + pb);
+          if (ta < total) nn_consider_pt<DIM, TRACK2>(q, pa, ca);
+          if (tb < total) nn_consider_pt<DIM, TRACK2>(q, pb, cb);
+        }
       }
-      if (lb2 > (TRACK2 ? q.sd2 : q.bd2)) continue;
-      nn_scan_row<DIM, TRACK2>(a, q, y, z, lb2);
-    }
-#pragma unroll
-    for (int off = 16; off; off >>= 1) {
-      const float od2 = __shfl_xor_sync(0xffffffffu, q.bd2, off);
-      const float os2 = __shfl_xor_sync(0xffffffffu, q.sd2, off);
-      const int oidx = __shfl_xor_sync(0xffffffffu, q.bidx, off);
-      const int opos = __shfl_xor_sync(0xffffffffu, q.bpos, off);
-      const bool other_wins = od2 < q.bd2 || (od2 == q.bd2 && oidx < q.bidx);
-      if (TRACK2) {
-        // the loser's best is a runner-up unless both lanes hold the same point (shared warm start)
-        float s = fminf(q.sd2, os2);
-        if (q.bpos >= 0 && opos >= 0 && q.bpos != opos) s = fminf(s, other_wins ? q.bd2 : od2);
-        q.sd2 = s;
+  #pragma unroll
+      for (int off = 16; off; off >>= 1) {
+        const float od2 = __shfl_xor_sync(0xffffffffu, q.bd2, off);
+        const float os2 = __shfl_xor_sync(0xffffffffu, q.sd2, off);
+        const int oidx = __shfl_xor_sync(0xffffffffu, q.bidx, off);
+        const int opos = __shfl_xor_sync(0xffffffffu, q.bpos, off);
+        const bool other_wins = od2 < q.bd2 || (od2 == q.bd2 && oidx < q.bidx);
+        if (TRACK2) {
+          // the loser's best is a runner-up unless both lanes hold the same point (shared warm start)
+          float s = fminf(q.sd2, os2);
+          if (q.bpos >= 0 && opos >= 0 && q.bpos != opos) s = fminf(s, other_wins ? q.bd2 : od2);
+          q.sd2 = s;
+        }
+        if (other_wins) { q.bd2 = od2; q.bidx = oidx; q.bpos = opos; }
       }
-      if (other_wins) { q.bd2 = od2; q.bidx = oidx; q.bpos = opos; }
     }
     if (lane == 0) {
       const int slot = nn_finish<DIM>(a, S, q, i, TRACK2 ? __fsqrt_rn(q.sd2) * (1.f - 1e-5f) : 0.f, old_slot);
@@ -955,15 +1022,16 @@ __global__ void __launch_bounds__(256) nn_far_kernel(const SliceArgs a) {
   __syncthreads();
   const float cell = __fdiv_rn(1.f, a.inv_cell);
   const bool track2 = *a.track2 != 0;
+  const int wpb = blockDim.x >> 5, w0 = blockIdx.x * wpb + (threadIdx.x >> 5), ws = gridDim.x * wpb;
   if (!tail) {
-    if (track2) nn_far_body<DIM, true>(a, S, rows, K, cell, n_far, a.far_list, nullptr);
-    else nn_far_body<DIM, false>(a, S, rows, K, cell, n_far, a.far_list, nullptr);
+    if (track2) nn_far_body<DIM, true>(a, S, rows, K, cell, n_far, a.far_list, nullptr, w0, ws);
+    else nn_far_body<DIM, false>(a, S, rows, K, cell, n_far, a.far_list, nullptr, w0, ws);
     return;
   }
   LinAcc<DIM> A;
   A.clear();
-  if (track2) nn_far_body<DIM, true, FACTOR>(a, S, rows, K, cell, n_far, a.work_list, &A);
-  else nn_far_body<DIM, false, FACTOR>(a, S, rows, K, cell, n_far, a.work_list, &A);
+  if (track2) nn_far_body<DIM, true, FACTOR>(a, S, rows, K, cell, n_far, a.work_list, &A, w0, ws);
+  else nn_far_body<DIM, false, FACTOR>(a, S, rows, K, cell, n_far, a.work_list, &A, w0, ws);
   lin_flush<DIM>(a, A, sacc);
 }
 
@@ -971,15 +1039,26 @@ __global__ void __launch_bounds__(256) nn_far_kernel(const SliceArgs a) {
 // fused with the linearisation (one read of the query, its neighbour and both normals serves both);
 // queries that fail it are appended to the work list for nn_kernel / nn_far_kernel, and the
 // CHECK = false pass then linearises exactly those.
+constexpr int kFailCap = 128;  // coherence-check failures a CTA of the fused kernel resolves in place
+
 template <int DIM, int FACTOR, bool CHECK>
-__global__ void __launch_bounds__(256) linearize_kernel(const SliceArgs a) {
+__global__ void __launch_bounds__(256, 2) linearize_kernel(const SliceArgs a) {
   if (*a.stop) return;
   const bool all = !a.use_list || *a.list_all;
   if (CHECK && all) return;  // nothing is certified: everything goes through the search path
   __shared__ float Ss[16], Sl[16];
   __shared__ unsigned long long sacc[kAcc];
+  __shared__ int s_fail[CHECK ? kFailCap : 1];
+  __shared__ int s_nfail;
+  __shared__ int s_rows[CHECK ? kRowTable : 1];
   if (threadIdx.x < 16) { Ss[threadIdx.x] = a.S[threadIdx.x]; Sl[threadIdx.x] = CHECK ? a.S_lb[threadIdx.x] : 0.f; }
   if (threadIdx.x < kAcc) sacc[threadIdx.x] = 0ull;
+  if (threadIdx.x == 0) s_nfail = 0;
+  constexpr int KMAX = (DIM == 3) ? kRowTable : (2 * kMaxR + 1);
+  if (CHECK) {
+    for (int k = threadIdx.x; k < KMAX; k += blockDim.x)
+      s_rows[k] = (DIM == 3) ? *reinterpret_cast<const int*>(c_rows3[k]) : *reinterpret_cast<const int*>(c_rows2[k]);
+  }
   __syncthreads();
   LinAcc<DIM> A;
   A.clear();
@@ -1060,11 +1139,18 @@ __global__ void __launch_bounds__(256) linearize_kernel(const SliceArgs a) {
           continue;
         }
       } else {
-        cg::coalesced_group g = cg::coalesced_threads();
-        int base = 0;
-        if (g.thread_rank() == 0) base = atomicAdd(a.work_count, (int) g.size());
-        base = g.shfl(base, 0);
-        a.work_list[base + g.thread_rank()] = i;
+        // the first kFailCap failures of the CTA are searched and linearised by its own warps after
+        // the loop (converged iterations: a handful per CTA); the rest go to the global work list
+        const int k = atomicAdd(&s_nfail, 1);
+        if (k < kFailCap) {
+          s_fail[k] = i;
+        } else {
+          cg::coalesced_group g = cg::coalesced_threads();
+          int base = 0;
+          if (g.thread_rank() == 0) base = atomicAdd(a.work_count, (int) g.size());
+          base = g.shfl(base, 0);
+          a.work_list[base + g.thread_rank()] = i;
+        }
         continue;
       }
     }
@@ -1078,6 +1164,16 @@ __global__ void __launch_bounds__(256) linearize_kernel(const SliceArgs a) {
       continue;
     }
     lin_one<DIM, FACTOR>(a, Ss, i, slot, bpos, m, nm, f, nf, A);
+  }
+  if (CHECK) {
+    __syncthreads();
+    const int n_local = min(s_nfail, kFailCap);
+    if (n_local > 0) {  // one warp per failed query: search, slot + bound, linearisation
+      const int K = (DIM == 3) ? (2 * a.R + 1) * (2 * a.R + 1) : (2 * a.R + 1);
+      const float cell = __fdiv_rn(1.f, a.inv_cell);
+      if (*a.track2) nn_far_body<DIM, true, FACTOR>(a, Ss, s_rows, K, cell, n_local, s_fail, &A, threadIdx.x >> 5, blockDim.x >> 5);
+      else nn_far_body<DIM, false, FACTOR>(a, Ss, s_rows, K, cell, n_local, s_fail, &A, threadIdx.x >> 5, blockDim.x >> 5);
+    }
   }
   lin_flush<DIM>(a, A, sacc);
 }
@@ -1129,11 +1225,22 @@ __device__ inline bool has_to_stop(DevState* st, const SolveArgs& a, const srrg2
 
 // compute() prologue: variable <- guess, prior slices overwrite it in slice order
 // (multi_aligner_impl.cpp:130-141), finder transforms, counters
-__global__ void icp_init_kernel(const SolveArgs a, DevState* st, Mat4f T0, int apply_prior_guess, int reset_tc,
+// SolveArgs live in device memory (refreshed before every run) so that per-call values such as a
+// prior's measurement do not change the launch sequence a cached CUDA graph replays
+__device__ __forceinline__ void load_solve_args(const SolveArgs* ap, SolveArgs* sh) {
+  const int* src = reinterpret_cast<const int*>(ap);
+  int* dst = reinterpret_cast<int*>(sh);
+  for (int k = threadIdx.x; k < (int) (sizeof(SolveArgs) / sizeof(int)); k += blockDim.x) dst[k] = src[k];
+  __syncthreads();
+}
+
+__global__ void icp_init_kernel(const SolveArgs* ap, DevState* st, const Mat4f* T0, int apply_prior_guess, int reset_tc,
                                 int keep_stats) {
+  __shared__ SolveArgs a;
+  load_solve_args(ap, &a);
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   if (!keep_stats) {
-    Mat4f X = T0;
+    Mat4f X = *T0;
     if (apply_prior_guess) {
       for (int s = 0; s < a.n_slices; ++s)
         if (a.sl[s].kind == SRRG2B_SLICE_PRIOR) X = a.sl[s].Z;
@@ -1177,8 +1284,10 @@ __global__ void set_S_kernel(DevState* st, int slice, Mat4f S, int track2) {
 // body of one _runSolver iteration after the per-slice kernels
 // (R/registration/aligners/multi_aligner_impl.cpp:106-126)
 template <int DIM>
-__global__ void icp_solve_kernel(const SolveArgs a, DevState* st) {
+__global__ void icp_solve_kernel(const SolveArgs* ap, DevState* st) {
   constexpr int P = (DIM == 3) ? 6 : 3;
+  __shared__ SolveArgs a;
+  load_solve_args(ap, &a);
   // the accumulators of all slices are fetched by the whole warp in one go (and zeroed for the
   // next iteration); the O(#slices) serial part then runs on lane 0 out of shared memory
   __shared__ unsigned long long sacc[SRRG2B_MAX_SLICES][kAcc];
@@ -1284,7 +1393,7 @@ __global__ void icp_solve_kernel(const SolveArgs a, DevState* st) {
       const float motion = sqrtf(dr) * 1.7321f * a.sl[k].coord_bound + sqrtf(dt);
       const int mode = a.sl[k].track2_mode;
       st->list_all[k] = st->track2[k] ? 0 : 1;  // bounds exist only if the pass just done certified them
-      st->track2[k] = (mode == 1) || (mode == 2 && motion < 0.125f * a.sl[k].cell) ? 1 : 0;
+      st->track2[k] = (mode == 1) || (mode == 2 && motion < a.sl[k].track2_frac * a.sl[k].cell) ? 1 : 0;
     }
     st->S[k] = Sn;
   }
