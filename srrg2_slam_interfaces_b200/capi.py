@@ -6,7 +6,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsrrg2b.so")
+# SRRG2B_LIB: an alternative build of the same library (tuning experiments); never a fallback
+LIB_PATH = os.environ.get("SRRG2B_LIB") or os.path.join(_HERE, "libsrrg2b.so")
 
 OK, ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_NCCL = 0, 1, 2, 3, 4
 FIXED, MOVING = 0, 1

@@ -79,6 +79,7 @@ struct SliceData {
   // fixed index (lazy, keyed by the cell size it was built for)
   DevBuf<float4> f_pts, f_nrm;
   DevBuf<int> f_inverse, cell_start;
+  DevBuf<unsigned> near_bits;
   int nf_valid = 0;
   float built_for_max_distance = -1.f;
   float ox = 0, oy = 0, oz = 0, inv_cell = 1;
@@ -385,6 +386,14 @@ int ensure_index(srrg2b_ctx* c, SliceData& sd, float max_distance) {
   cell_start_kernel<<<blocks_for(ncells + 1, 256), 256, 0, c->stream>>>(c->keys_b.p, sd.nf_valid, ncells,
                                                                         sd.cell_start.p);
   c->launches++;
+  {
+    const size_t words = ((size_t) ncells + 31) / 32;
+    CK(c, sd.near_bits.ensure(words));
+    CK(c, cudaMemsetAsync(sd.near_bits.p, 0, words * sizeof(unsigned), c->stream));
+    near_bits_kernel<<<blocks_for(ncells, 256), 256, 0, c->stream>>>(sd.cell_start.p, sd.nx, sd.ny, sd.nz, sd.R, dim,
+                                                                     sd.near_bits.p);
+    c->launches++;
+  }
   // positions into the old ordering are meaningless now: drop the warm-start candidates
   if (sd.moving_raw.present && sd.nm_valid > 0) {
     fill_int_kernel<<<blocks_for(sd.nm_valid, 256), 256, 0, c->stream>>>(sd.c_fpos.p, sd.nm_valid, -1);
@@ -476,7 +485,7 @@ int fill_slice_args(srrg2b_ctx* c, SliceData& sd, int state_slot, const srrg2b_f
   const Scales sc = choose_scales(sd.moving_raw.n_global, sd.coord_bound, fp.max_distance, fa.info_point, fa.info_normal);
   if (sc_out) *sc_out = sc;
   a.mp = sd.m_pts.p; a.mn = sd.m_nrm.p; a.nm = sd.nm_valid;
-  a.fp = sd.f_pts.p; a.fn = sd.f_nrm.p; a.cell_start = sd.cell_start.p;
+  a.fp = sd.f_pts.p; a.fn = sd.f_nrm.p; a.cell_start = sd.cell_start.p; a.near_bits = sd.near_bits.p;
   a.ox = sd.ox; a.oy = sd.oy; a.oz = sd.oz; a.inv_cell = sd.inv_cell;
   a.nx = sd.nx; a.ny = sd.ny; a.nz = sd.nz;
   a.R = sd.R;
@@ -514,9 +523,15 @@ int fill_slice_args(srrg2b_ctx* c, SliceData& sd, int state_slot, const srrg2b_f
   return SRRG2B_OK;
 }
 
-void launch_far(srrg2b_ctx* c, const SliceArgs& a, int factor) {
+void launch_far(srrg2b_ctx* c, const SliceArgs& a_in, int factor) {
   const int threads = 256;
+  SliceArgs a = a_in;
   const int fblocks = std::max(1, std::min(blocks_for((int64_t) a.nm * 32, threads), c->sm_count * 8));
+  {  // tail mode: lane 0 of a warp linearises its share of a short (< nm / 64 + 64) work list
+    const int64_t warps = (int64_t) fblocks * (threads / 32);
+    const int64_t per_lane = (((int64_t) a.nm >> 6) + 64 + warps - 1) / warps;
+    a.few_terms = per_lane <= 30 ? 1 : 0;
+  }
   if (c->dim == 3) {
     if (factor == SRRG2B_FACTOR_P2P) nn_far_kernel<3, SRRG2B_FACTOR_P2P><<<fblocks, threads, 0, c->stream>>>(a);
     else nn_far_kernel<3, SRRG2B_FACTOR_PLANE><<<fblocks, threads, 0, c->stream>>>(a);
@@ -545,12 +560,18 @@ int launch_find(srrg2b_ctx* c, const SliceArgs& a) {
 }
 
 template <bool CHECK>
-int launch_linearize_t(srrg2b_ctx* c, const SliceArgs& a, int factor) {
-  if (a.nm <= 0) return SRRG2B_OK;
-  const int threads = 256;
-  // 2 CTAs per SM, but never more than 512 correspondences per thread (32-bit partial sums)
-  const int blocks = std::max(1, std::min(blocks_for(a.nm, threads),
-                                          std::max(c->sm_count * 2, blocks_for(a.nm, threads * 512))));
+int launch_linearize_t(srrg2b_ctx* c, const SliceArgs& a_in, int factor) {
+  if (a_in.nm <= 0) return SRRG2B_OK;
+  const int threads = kLinThreads;
+  // one wave of resident CTAs, but never more than 512 correspondences per thread (32-bit partial sums)
+  const int blocks = std::max(1, std::min(blocks_for(a_in.nm, threads),
+                                          std::max(c->sm_count * kLinCtas, blocks_for(a_in.nm, threads * 512))));
+  SliceArgs a = a_in;
+  {  // terms a thread can add to one slot: its share of the slice plus, fused kernel, the CTA's in-place tail
+    const int64_t per_thread = ((int64_t) a.nm + (int64_t) blocks * threads - 1) / ((int64_t) blocks * threads) +
+                               (CHECK ? kFailCap / (threads / 32) : 0);
+    a.few_terms = per_thread <= 30 ? 1 : 0;
+  }
   if (c->dim == 3) {
     if (factor == SRRG2B_FACTOR_P2P) linearize_kernel<3, SRRG2B_FACTOR_P2P, CHECK><<<blocks, threads, 0, c->stream>>>(a);
     else linearize_kernel<3, SRRG2B_FACTOR_PLANE, CHECK><<<blocks, threads, 0, c->stream>>>(a);
@@ -902,7 +923,7 @@ int srrg2b_ctx_destroy(srrg2b_ctx* c) {
     SliceData& s = kv.second;
     s.fixed_raw.xyz.release(); s.fixed_raw.nrm.release(); s.fixed_raw.valid.release();
     s.moving_raw.xyz.release(); s.moving_raw.nrm.release(); s.moving_raw.valid.release();
-    s.f_pts.release(); s.f_nrm.release(); s.f_inverse.release(); s.cell_start.release();
+    s.f_pts.release(); s.f_nrm.release(); s.f_inverse.release(); s.cell_start.release(); s.near_bits.release();
     s.m_pts.release(); s.m_nrm.release(); s.m_inverse.release();
     s.image.release(); s.c_lb.release(); s.S_lb.release(); s.c_fidx.release(); s.c_fpos.release(); s.far_list.release(); s.far_count.release(); s.work_list.release(); s.c_resp.release(); s.c_chi.release(); s.c_stat.release();
   }

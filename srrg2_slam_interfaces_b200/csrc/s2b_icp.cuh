@@ -67,6 +67,7 @@ struct SliceArgs {
   const float4* __restrict__ fp;   // fixed points, cell order: x y z | original index bits
   const float4* __restrict__ fn;
   const int* __restrict__ cell_start;
+  const unsigned* __restrict__ near_bits;  // dilated occupancy (see near_bits_kernel)
   float ox, oy, oz, inv_cell;
   int nx, ny, nz;
   int R;      // search radius in cells (cell edge = 1.001 * max_distance / R)
@@ -86,6 +87,7 @@ struct SliceArgs {
   const int* list_all; // device flag: no usable bounds -> the work list is implicitly [0, nm)
   int inline_check;    // 1: nn_kernel does the coherence check itself (stand-alone finder)
   int use_list;        // 1: nn / linearise kernels iterate over the work list
+  int few_terms;       // every thread of the accumulating kernel adds at most 30 terms per slot
   float* c_lb;         // certified lower bound per query (see nn kernels)
   const float* S_lb;   // transform the bounds are valid for
   const int* track2;   // device flag: searches track the second neighbour (certify bounds)
@@ -280,6 +282,29 @@ __global__ void count_distinct_kernel(const unsigned* __restrict__ keys, int n, 
   if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
 }
 
+// near_bits: bit c is set iff some fixed point lies in a cell within Chebyshev distance R of cell c
+// (the occupancy grid dilated by the search radius).  A query whose own cell has the bit clear has
+// no fixed point within (R - slack) cells, i.e. nothing within max_distance: the finder can answer
+// "none" from one load instead of walking (2R+1)^(DIM-1) empty rows.
+__global__ void near_bits_kernel(const int* __restrict__ cell_start, int nx, int ny, int nz, int R, int dim,
+                                 unsigned* __restrict__ bits) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nx * ny * nz) return;
+  if (cell_start[c + 1] <= cell_start[c]) return;
+  const int cx = c % nx, cy = (c / nx) % ny, cz = c / (nx * ny);
+  const int rz = dim == 3 ? R : 0;
+  for (int z = max(cz - rz, 0); z <= min(cz + rz, nz - 1); ++z)
+    for (int y = max(cy - R, 0); y <= min(cy + R, ny - 1); ++y) {
+      const int row = (z * ny + y) * nx;
+      const int a = row + max(cx - R, 0), b = row + min(cx + R, nx - 1);  // bit range [a, b]
+      for (int w = a >> 5; w <= (b >> 5); ++w) {
+        const int lo = max(a - (w << 5), 0), hi = min(b - (w << 5), 31);
+        const unsigned m = (hi == 31 ? 0xffffffffu : ((1u << (hi + 1)) - 1u)) & ~((1u << lo) - 1u);
+        if ((bits[w] & m) != m) atomicOr(&bits[w], m);
+      }
+    }
+}
+
 __global__ void fill_int_kernel(int* p, int n, int v) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
@@ -399,9 +424,8 @@ __device__ __forceinline__ bool small_work_list(const SliceArgs& a, bool all, in
 }
 
 __device__ __forceinline__ int slot_candidate(int slot) {
-  if (slot >= 0) return slot;
-  if (slot <= -2 && slot != kSlotSuppressed) return -(slot + 2);
-  return -1;
+  const int c = slot >= 0 ? slot : -(slot + 2);  // -1 -> -1; kSlotSuppressed would wrap to a positive value
+  return slot == kSlotSuppressed ? -1 : c;
 }
 
 // slot / bound of a finished query.  Inside the ICP loop the normal gate is evaluated by the
@@ -466,6 +490,14 @@ __device__ __forceinline__ void nn_phase1_body(const SliceArgs& a, const float* 
           a.c_lb[i] = lbn;
           continue;
         }
+      }
+    }
+    if (p0 < 0 && q.cx >= 0 && q.cx < a.nx && q.cy >= 0 && q.cy < a.ny && q.cz >= 0 && q.cz < a.nz) {
+      // nothing occupied within R cells of the query's cell: no fixed point within the covered radius
+      const int c = (q.cz * a.ny + q.cy) * a.nx + q.cx;
+      if (!((__ldg(a.near_bits + (c >> 5)) >> (c & 31)) & 1u)) {
+        nn_finish<DIM>(a, S, q, i, TRACK2 ? __fsqrt_rn(a.rho_s2) * (1.f - 1e-5f) : 0.f, old_slot);
+        continue;
       }
     }
     if (a.warm && p0 >= 0) nn_consider<DIM, TRACK2>(a, q, p0);  // a real candidate: exactness untouched
@@ -953,48 +985,61 @@ __device__ __forceinline__ void lin_one(const SliceArgs& a, const float* Ss, int
   }
 }
 
-// exact integer block reduction of the per-thread partial sums: two REDUX per slot (16-bit halves
-// cannot overflow the 32-bit warp sum) -> 64-bit shared atomics -> one global atomic per slot / CTA.
-// sacc must be zeroed (and the block synchronised) by the caller before any thread gets here.
+// exact integer block reduction of the per-thread partial sums: REDUX per slot (one when the
+// per-thread sums are known to stay below 2^26, else two over 16-bit halves, which cannot overflow the
+// 32-bit warp sum), the warp's 40 sums parked in lanes, one plain shared store per lane, then 40
+// threads add the warps' rows and issue one global atomic per slot and CTA.
+constexpr int kMaxWarps = 8;  // CTAs of the accumulating kernels have at most 256 threads
+struct FlushSmem {
+  long long w[kMaxWarps][kAcc];
+};
+
 template <int DIM>
-__device__ __forceinline__ void lin_flush(const SliceArgs& a, const LinAcc<DIM>& A, unsigned long long* sacc) {
+__device__ __forceinline__ void lin_flush(const SliceArgs& a, const LinAcc<DIM>& A, FlushSmem& sm) {
   constexpr int P = LinAcc<DIM>::P, NH = LinAcc<DIM>::NH;
-  auto wsum = [](int v) -> long long {
+  const bool few = a.few_terms != 0;
+  auto wsum = [few](int v) -> long long {
+    if (few) return (long long) __reduce_add_sync(0xffffffffu, v);
     const unsigned lo = __reduce_add_sync(0xffffffffu, (unsigned) v & 0xffffu);
     const int hi = __reduce_add_sync(0xffffffffu, v >> 16);
     return ((long long) hi << 16) + (long long) lo;
   };
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  long long mine0 = 0, mine1 = 0;  // lane l keeps slot l and slot 32 + l
 #pragma unroll
   for (int k = 0; k < NH; ++k) {
     const long long v = wsum(A.aH[k]);
-    if (lane == 0 && v) atomicAdd(&sacc[k], (unsigned long long) v);
+    if (lane == k) mine0 = v;
   }
 #pragma unroll
   for (int k = 0; k < P; ++k) {
     const long long v = wsum(A.ab[k]);
-    if (lane == 0 && v) atomicAdd(&sacc[kAccB + k], (unsigned long long) v);
+    if (lane == kAccB + k) mine0 = v;
   }
   {
     const int cv[4] = {A.chi_in, A.chi_in_lo, A.chi_out, A.chi_out_lo};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const long long v = wsum(cv[k]);
-      if (lane == 0 && v) atomicAdd(&sacc[kAccChiIn + k], (unsigned long long) v);
+      if (kAccChiIn + k < 32) { if (lane == kAccChiIn + k) mine0 = v; }
+      else { if (lane == kAccChiIn + k - 32) mine1 = v; }
     }
-    const int ni = __reduce_add_sync(0xffffffffu, A.n_in);
-    const int no = __reduce_add_sync(0xffffffffu, A.n_out);
-    const int ns = __reduce_add_sync(0xffffffffu, A.n_sup);
-    if (lane == 0) {
-      if (ni) atomicAdd(&sacc[kAccNIn], (unsigned long long) ni);
-      if (no) atomicAdd(&sacc[kAccNOut], (unsigned long long) no);
-      if (ns) atomicAdd(&sacc[kAccNSup], (unsigned long long) ns);
+    const int cn[3] = {A.n_in, A.n_out, A.n_sup};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const long long v = (long long) __reduce_add_sync(0xffffffffu, cn[k]);
+      if (kAccNIn + k < 32) { if (lane == kAccNIn + k) mine0 = v; }
+      else { if (lane == kAccNIn + k - 32) mine1 = v; }
     }
   }
+  sm.w[warp][lane] = mine0;
+  if (lane < kAcc - 32) sm.w[warp][32 + lane] = mine1;
   __syncthreads();
   if (threadIdx.x < kAcc) {
-    const unsigned long long v = sacc[threadIdx.x];
-    if (v) atomicAdd(&a.acc[threadIdx.x], v);
+    long long v = 0;
+    const int nw = blockDim.x >> 5;
+    for (int w = 0; w < nw; ++w) v += sm.w[w][threadIdx.x];
+    if (v) atomicAdd(&a.acc[threadIdx.x], (unsigned long long) v);
   }
 }
 
@@ -1012,9 +1057,8 @@ __global__ void __launch_bounds__(256) nn_far_kernel(const SliceArgs a) {
   if (n_far == 0) return;
   __shared__ float S[16];
   __shared__ int rows[kRowTable];
-  __shared__ unsigned long long sacc[kAcc];
+  __shared__ FlushSmem fsm;
   if (threadIdx.x < 16) S[threadIdx.x] = a.S[threadIdx.x];
-  if (threadIdx.x < kAcc) sacc[threadIdx.x] = 0ull;
   const int R = a.R;
   const int K = (DIM == 3) ? (2 * R + 1) * (2 * R + 1) : (2 * R + 1);
   for (int k = threadIdx.x; k < K; k += blockDim.x)
@@ -1032,27 +1076,31 @@ __global__ void __launch_bounds__(256) nn_far_kernel(const SliceArgs a) {
   A.clear();
   if (track2) nn_far_body<DIM, true, FACTOR>(a, S, rows, K, cell, n_far, a.work_list, &A, w0, ws);
   else nn_far_body<DIM, false, FACTOR>(a, S, rows, K, cell, n_far, a.work_list, &A, w0, ws);
-  lin_flush<DIM>(a, A, sacc);
+  lin_flush<DIM>(a, A, fsm);
 }
 
 // CHECK = true is the first pass of an iteration once bounds exist: the temporal-coherence test is
 // fused with the linearisation (one read of the query, its neighbour and both normals serves both);
 // queries that fail it are appended to the work list for nn_kernel / nn_far_kernel, and the
 // CHECK = false pass then linearises exactly those.
+#ifndef S2B_LIN_THREADS
+#define S2B_LIN_THREADS 256  // CTA size / resident CTAs per SM of the linearise kernels (register budget)
+#define S2B_LIN_CTAS 2
+#endif
+constexpr int kLinThreads = S2B_LIN_THREADS, kLinCtas = S2B_LIN_CTAS;
 constexpr int kFailCap = 128;  // coherence-check failures a CTA of the fused kernel resolves in place
 
 template <int DIM, int FACTOR, bool CHECK>
-__global__ void __launch_bounds__(256, 2) linearize_kernel(const SliceArgs a) {
+__global__ void __launch_bounds__(kLinThreads, kLinCtas) linearize_kernel(const SliceArgs a) {
   if (*a.stop) return;
   const bool all = !a.use_list || *a.list_all;
   if (CHECK && all) return;  // nothing is certified: everything goes through the search path
   __shared__ float Ss[16], Sl[16];
-  __shared__ unsigned long long sacc[kAcc];
+  __shared__ FlushSmem fsm;
   __shared__ int s_fail[CHECK ? kFailCap : 1];
   __shared__ int s_nfail;
   __shared__ int s_rows[CHECK ? kRowTable : 1];
   if (threadIdx.x < 16) { Ss[threadIdx.x] = a.S[threadIdx.x]; Sl[threadIdx.x] = CHECK ? a.S_lb[threadIdx.x] : 0.f; }
-  if (threadIdx.x < kAcc) sacc[threadIdx.x] = 0ull;
   if (threadIdx.x == 0) s_nfail = 0;
   constexpr int KMAX = (DIM == 3) ? kRowTable : (2 * kMaxR + 1);
   if (CHECK) {
@@ -1077,8 +1125,9 @@ __global__ void __launch_bounds__(256, 2) linearize_kernel(const SliceArgs a) {
   int slot_n = i_n >= 0 ? a.c_fpos[i_n] : -1;
   float lb_n = (CHECK && i_n >= 0) ? a.c_lb[i_n] : 0.f;
   float4 m_n = zero4, nm_n = zero4, f_n = zero4, nf_n = zero4;
+  int pn = -1;  // candidate position of the prefetched query (travels with it through the pipeline)
   {
-    const int pn = regate ? slot_candidate(slot_n) : slot_n;
+    pn = regate ? slot_candidate(slot_n) : slot_n;
     if (i_n >= 0 && (pn >= 0 || CHECK)) m_n = a.mp[i_n];
     if (pn >= 0) {
       nm_n = a.mn[i_n];
@@ -1094,10 +1143,11 @@ __global__ void __launch_bounds__(256, 2) linearize_kernel(const SliceArgs a) {
     const int slot = slot_n;
     const float lb_old = lb_n;
     const float4 m = m_n, nm = nm_n, f = f_n, nf = nf_n;
+    const int bpos = pn;
     // advance the pipeline
     i_n = i_nn; slot_n = slot_nn; lb_n = lb_nn;
     {
-      const int pn = regate ? slot_candidate(slot_n) : slot_n;
+      pn = regate ? slot_candidate(slot_n) : slot_n;
       if (i_n >= 0 && (pn >= 0 || CHECK)) m_n = a.mp[i_n];
       if (pn >= 0) {
         nm_n = a.mn[i_n];
@@ -1108,7 +1158,6 @@ __global__ void __launch_bounds__(256, 2) linearize_kernel(const SliceArgs a) {
     slot_nn = i_nn >= 0 ? a.c_fpos[i_nn] : -1;
     lb_nn = (CHECK && i_nn >= 0) ? a.c_lb[i_nn] : 0.f;
     i_nnn = index_of(w + 3 * stride);
-    const int bpos = regate ? slot_candidate(slot) : slot;
     if (CHECK) {
       // exact temporal coherence (see the NN kernels): keep the neighbour / the "none" verdict when
       // the certified bound minus the query's motion still proves it; else hand over to the search
@@ -1175,7 +1224,7 @@ __global__ void __launch_bounds__(256, 2) linearize_kernel(const SliceArgs a) {
       else nn_far_body<DIM, false, FACTOR>(a, Ss, s_rows, K, cell, n_local, s_fail, &A, threadIdx.x >> 5, blockDim.x >> 5);
     }
   }
-  lin_flush<DIM>(a, A, sacc);
+  lin_flush<DIM>(a, A, fsm);
 }
 
 // ---------------------------------------------------------------------------------------------
