@@ -116,6 +116,7 @@ struct srrg2b_ctx {
   DevState* h_state = nullptr;  // pinned mirror (header part is copied back)
   // scratch
   DevBuf<unsigned> keys_a, keys_b;
+  DevBuf<unsigned long long> keys64_a, keys64_b;
   DevBuf<int> vals_a, vals_b, flags, positions, bounds;
   DevBuf<unsigned char> cub_tmp;
   DevBuf<int> o_fidx, o_midx, d_fidx;
@@ -146,6 +147,8 @@ struct srrg2b_ctx {
   };
   std::vector<RunGraph> run_graphs;
   bool use_graphs = true;  // env SRRG2B_NO_GRAPH=1 disables
+  unsigned long long* d_tile_stats = nullptr;  // experiments (S2B_TILE_STATS builds)
+  bool use_tile = false;   // env SRRG2B_TILE=1: "all" mode searches run tiled out of shared memory (nn_tile_kernel)
   s2b::Mat4f* d_T0 = nullptr;  // initial guess of the current run (read by icp_init_kernel)
   s2b::Mat4f* h_T0 = nullptr;  // pinned staging
   s2b::SolveArgs* d_solve = nullptr;  // solve-step arguments of the current run
@@ -178,6 +181,17 @@ int cub_sort_pairs(srrg2b_ctx* c, int n, int end_bit) {
   CK(c, c->cub_tmp.ensure(bytes));
   CK(c, cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, bytes, c->keys_a.p, c->keys_b.p, c->vals_a.p, c->vals_b.p, n, 0,
                                         end_bit, c->stream));
+  return SRRG2B_OK;
+}
+
+// 64-bit (cell, x) keys of the fixed index
+int cub_sort_pairs64(srrg2b_ctx* c, int n, int end_bit) {
+  size_t bytes = 0;
+  CK(c, cub::DeviceRadixSort::SortPairs(nullptr, bytes, c->keys64_a.p, c->keys64_b.p, c->vals_a.p, c->vals_b.p, n, 0,
+                                        end_bit, c->stream));
+  CK(c, c->cub_tmp.ensure(bytes));
+  CK(c, cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, bytes, c->keys64_a.p, c->keys64_b.p, c->vals_a.p, c->vals_b.p, n,
+                                        0, end_bit, c->stream));
   return SRRG2B_OK;
 }
 
@@ -260,7 +274,7 @@ int build_moving(srrg2b_ctx* c, SliceData& sd) {
   CK(c, c->keys_b.ensure(n));
   CK(c, c->vals_a.ensure(n));
   CK(c, c->vals_b.ensure(n));
-  morton_key_kernel<<<blocks_for(n, 256), 256, 0, c->stream>>>(rc.xyz.p, rc.has_valid ? rc.valid.p : nullptr, n, dim,
+  curve_key_kernel<<<blocks_for(n, 256), 256, 0, c->stream>>>(rc.xyz.p, rc.has_valid ? rc.valid.p : nullptr, n, dim,
                                                                mn[0], mn[1], mn[2], sc[0], sc[1], sc[2], c->keys_a.p,
                                                                c->vals_a.p);
   c->launches++;
@@ -309,8 +323,8 @@ int ensure_index(srrg2b_ctx* c, SliceData& sd, float max_distance) {
   CK(c, sd.f_nrm.ensure((size_t) n + 1));
   CK(c, sd.f_inverse.ensure((size_t) n + 1));
   if (n > 0) {
-    CK(c, c->keys_a.ensure(n));
-    CK(c, c->keys_b.ensure(n));
+    CK(c, c->keys64_a.ensure(n));
+    CK(c, c->keys64_b.ensure(n));
     CK(c, c->vals_a.ensure(n));
     CK(c, c->vals_b.ensure(n));
   }
@@ -356,15 +370,19 @@ int ensure_index(srrg2b_ctx* c, SliceData& sd, float max_distance) {
     if (n > 0) {
       cell_key_kernel<<<blocks_for(n, 256), 256, 0, c->stream>>>(rc.xyz.p, rc.has_valid ? rc.valid.p : nullptr, n,
                                                                  dim, sd.ox, sd.oy, sd.oz, sd.inv_cell, sd.nx, sd.ny,
-                                                                 sd.nz, c->keys_a.p, c->vals_a.p);
+                                                                 sd.nz, c->keys64_a.p, c->vals_a.p);
       c->launches++;
-      rcode = cub_sort_pairs(c, n, 32);
+      {  // invalid points carry all-ones keys and need the full width to sort last
+        int cell_bits = 1;
+        while (((int64_t) 1 << cell_bits) < (int64_t) sd.nx * sd.ny * sd.nz) ++cell_bits;
+        rcode = cub_sort_pairs64(c, n, rc.has_valid ? 64 : 32 + cell_bits);
+      }
       if (rcode) return rcode;
     }
     if (R == 1 || forced || sd.nf_valid == 0) break;
     CK(c, cudaMemsetAsync(c->bounds.p, 0, 4, c->stream));
     count_distinct_kernel<<<std::min(blocks_for(sd.nf_valid, 256), c->sm_count * 8), 256, 0, c->stream>>>(
-      c->keys_b.p, sd.nf_valid, c->bounds.p);
+      c->keys64_b.p, sd.nf_valid, c->bounds.p);
     c->launches++;
     CK(c, cudaMemcpyAsync(c->h_bounds, c->bounds.p, 4, cudaMemcpyDeviceToHost, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
@@ -383,7 +401,7 @@ int ensure_index(srrg2b_ctx* c, SliceData& sd, float max_distance) {
       c->launches++;
     }
   }
-  cell_start_kernel<<<blocks_for(ncells + 1, 256), 256, 0, c->stream>>>(c->keys_b.p, sd.nf_valid, ncells,
+  cell_start_kernel<<<blocks_for(ncells + 1, 256), 256, 0, c->stream>>>(c->keys64_b.p, sd.nf_valid, ncells,
                                                                         sd.cell_start.p);
   c->launches++;
   {
@@ -506,6 +524,8 @@ int fill_slice_args(srrg2b_ctx* c, SliceData& sd, int state_slot, const srrg2b_f
   a.work_list = sd.work_list.p; a.work_count = sd.far_count.p + 1;
   a.list_all = &c->d_state->list_all[state_slot];
   a.inline_check = 0; a.use_list = 0;
+  a.tile = c->use_tile ? 1 : 0;
+  a.tile_stats = S2B_TILE_STATS ? c->d_tile_stats : nullptr;
   a.projective = fp.kind == SRRG2B_FINDER_PROJECTIVE ? 1 : 0;
   a.fx = fp.fx; a.fy = fp.fy; a.pcx = fp.cx; a.pcy = fp.cy; a.min_depth = fp.min_depth; a.max_depth = fp.max_depth;
   a.width = fp.width; a.height = fp.height; a.image = sd.image.p;
@@ -542,6 +562,20 @@ void launch_far(srrg2b_ctx* c, const SliceArgs& a_in, int factor) {
   c->launches++;
 }
 
+// "all" mode searches: nn_tile_kernel (optional, staged in shared memory), else nn_kernel phase 1
+void launch_nn(srrg2b_ctx* c, const SliceArgs& a) {
+  if (a.tile) {
+    const int blocks = std::max(1, std::min(blocks_for(a.nm, kTileThreads), c->sm_count * 12));
+    if (c->dim == 3) nn_tile_kernel<3><<<blocks, kTileThreads, sizeof(TileSmem), c->stream>>>(a);
+    else nn_tile_kernel<2><<<blocks, kTileThreads, sizeof(TileSmem), c->stream>>>(a);
+    c->launches++;
+  }
+  const int blocks = std::max(1, std::min(blocks_for(a.nm, 256), c->sm_count * 8));
+  if (c->dim == 3) nn_kernel<3><<<blocks, 256, 0, c->stream>>>(a);
+  else nn_kernel<2><<<blocks, 256, 0, c->stream>>>(a);
+  c->launches++;
+}
+
 int launch_find(srrg2b_ctx* c, const SliceArgs& a) {
   if (a.nm <= 0) return SRRG2B_OK;
   const int threads = 256;
@@ -552,9 +586,7 @@ int launch_find(srrg2b_ctx* c, const SliceArgs& a) {
     return SRRG2B_OK;
   }
   CK(c, cudaMemsetAsync(a.far_count, 0, sizeof(int), c->stream));
-  if (c->dim == 3) nn_kernel<3><<<blocks, threads, 0, c->stream>>>(a);
-  else nn_kernel<2><<<blocks, threads, 0, c->stream>>>(a);
-  c->launches++;
+  launch_nn(c, a);
   if (a.R >= 2) launch_far(c, a, SRRG2B_FACTOR_P2P);
   return SRRG2B_OK;
 }
@@ -573,11 +605,11 @@ int launch_linearize_t(srrg2b_ctx* c, const SliceArgs& a_in, int factor) {
     a.few_terms = per_thread <= 30 ? 1 : 0;
   }
   if (c->dim == 3) {
-    if (factor == SRRG2B_FACTOR_P2P) linearize_kernel<3, SRRG2B_FACTOR_P2P, CHECK><<<blocks, threads, 0, c->stream>>>(a);
-    else linearize_kernel<3, SRRG2B_FACTOR_PLANE, CHECK><<<blocks, threads, 0, c->stream>>>(a);
+    if (factor == SRRG2B_FACTOR_P2P) linearize_kernel<3, SRRG2B_FACTOR_P2P, CHECK><<<blocks, threads, kLinSmemBytes, c->stream>>>(a);
+    else linearize_kernel<3, SRRG2B_FACTOR_PLANE, CHECK><<<blocks, threads, kLinSmemBytes, c->stream>>>(a);
   } else {
-    if (factor == SRRG2B_FACTOR_P2P) linearize_kernel<2, SRRG2B_FACTOR_P2P, CHECK><<<blocks, threads, 0, c->stream>>>(a);
-    else linearize_kernel<2, SRRG2B_FACTOR_PLANE, CHECK><<<blocks, threads, 0, c->stream>>>(a);
+    if (factor == SRRG2B_FACTOR_P2P) linearize_kernel<2, SRRG2B_FACTOR_P2P, CHECK><<<blocks, threads, kLinSmemBytes, c->stream>>>(a);
+    else linearize_kernel<2, SRRG2B_FACTOR_PLANE, CHECK><<<blocks, threads, kLinSmemBytes, c->stream>>>(a);
   }
   c->launches++;
   return SRRG2B_OK;
@@ -599,11 +631,7 @@ int launch_slice_iteration(srrg2b_ctx* c, const SliceArgs& a0, int factor) {
   CK(c, cudaMemsetAsync(a.far_count, 0, 2 * sizeof(int), c->stream));
   int rcode = launch_linearize_t<true>(c, a, factor);
   if (rcode) return rcode;
-  const int threads = 256;
-  const int blocks = std::max(1, std::min(blocks_for(a.nm, threads), c->sm_count * 8));
-  if (c->dim == 3) nn_kernel<3><<<blocks, threads, 0, c->stream>>>(a);
-  else nn_kernel<2><<<blocks, threads, 0, c->stream>>>(a);
-  c->launches++;
+  launch_nn(c, a);
   launch_far(c, a, factor);  // phase 2 of long lists, or the whole job for short ones (any R)
   return launch_linearize_t<false>(c, a, factor);
 }
@@ -900,6 +928,19 @@ int srrg2b_ctx_create(int dim, int device, srrg2b_ctx** out) {
   ok = ok && cudaMalloc((void**) &c->d_solve, sizeof(SolveArgs)) == cudaSuccess;
   ok = ok && cudaMallocHost((void**) &c->h_solve, sizeof(SolveArgs)) == cudaSuccess;
   if (const char* env = getenv("SRRG2B_NO_GRAPH")) c->use_graphs = atoi(env) == 0;
+  if (const char* env = getenv("SRRG2B_TILE")) c->use_tile = atoi(env) != 0;
+  {
+    const void* lin[] = {(const void*) linearize_kernel<3, SRRG2B_FACTOR_P2P, true>, (const void*) linearize_kernel<3, SRRG2B_FACTOR_P2P, false>,
+                         (const void*) linearize_kernel<3, SRRG2B_FACTOR_PLANE, true>, (const void*) linearize_kernel<3, SRRG2B_FACTOR_PLANE, false>,
+                         (const void*) linearize_kernel<2, SRRG2B_FACTOR_P2P, true>, (const void*) linearize_kernel<2, SRRG2B_FACTOR_P2P, false>,
+                         (const void*) linearize_kernel<2, SRRG2B_FACTOR_PLANE, true>, (const void*) linearize_kernel<2, SRRG2B_FACTOR_PLANE, false>};
+    for (const void* f : lin)
+      ok = ok && cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kLinSmemBytes) == cudaSuccess;
+  }
+  ok = ok && cudaFuncSetAttribute(nn_tile_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(TileSmem)) == cudaSuccess;
+  ok = ok && cudaFuncSetAttribute(nn_tile_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(TileSmem)) == cudaSuccess;
+  ok = ok && cudaMalloc((void**) &c->d_tile_stats, 12 * sizeof(unsigned long long)) == cudaSuccess;
+  ok = ok && cudaMemsetAsync(c->d_tile_stats, 0, 12 * sizeof(unsigned long long), c->stream) == cudaSuccess;
   ok = ok && cudaMemsetAsync(c->d_state, 0, sizeof(DevState), c->stream) == cudaSuccess;
   ok = ok && cudaStreamSynchronize(c->stream) == cudaSuccess;
   ok = ok && upload_row_tables() == SRRG2B_OK;
@@ -918,6 +959,17 @@ int srrg2b_ctx_destroy(srrg2b_ctx* c) {
   pgo_release(c);
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
+#if S2B_TILE_STATS
+  if (c->d_tile_stats) {
+    unsigned long long t[12];
+    if (cudaMemcpy(t, c->d_tile_stats, sizeof(t), cudaMemcpyDeviceToHost) == cudaSuccess && t[0] + t[1] + t[2]) {
+      fprintf(stderr, "[srrg2b tile stats] tiles staged %llu fallback %llu (of which points overflow %llu) idle %llu | cycles/tile stage %.0f | search cycles per warp: staged %.0f fallback %.0f | staged rows %.0f entries %.0f\n",
+              t[0], t[1], t[7], t[2], t[3] / (double) (t[0] + t[1] + t[2]), t[4] / (8.0 * std::max(1ull, t[0])), t[8] / (8.0 * std::max(1ull, t[1])),
+              t[5] / (double) std::max(1ull, t[0]), t[6] / (double) std::max(1ull, t[0]));
+    }
+  }
+#endif
+  if (c->d_tile_stats) cudaFree(c->d_tile_stats);
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   for (auto& kv : c->slices) {
     SliceData& s = kv.second;
@@ -927,7 +979,7 @@ int srrg2b_ctx_destroy(srrg2b_ctx* c) {
     s.m_pts.release(); s.m_nrm.release(); s.m_inverse.release();
     s.image.release(); s.c_lb.release(); s.S_lb.release(); s.c_fidx.release(); s.c_fpos.release(); s.far_list.release(); s.far_count.release(); s.work_list.release(); s.c_resp.release(); s.c_chi.release(); s.c_stat.release();
   }
-  c->keys_a.release(); c->keys_b.release(); c->vals_a.release(); c->vals_b.release();
+  c->keys_a.release(); c->keys_b.release(); c->keys64_a.release(); c->keys64_b.release(); c->vals_a.release(); c->vals_b.release();
   c->flags.release(); c->positions.release(); c->bounds.release(); c->cub_tmp.release();
   c->o_fidx.release(); c->o_midx.release(); c->d_fidx.release(); c->o_resp.release(); c->d_resp.release();
   c->o_chi.release(); c->d_chi.release(); c->o_stat.release(); c->d_stat.release();

@@ -87,6 +87,8 @@ struct SliceArgs {
   const int* list_all; // device flag: no usable bounds -> the work list is implicitly [0, nm)
   int inline_check;    // 1: nn_kernel does the coherence check itself (stand-alone finder)
   int use_list;        // 1: nn / linearise kernels iterate over the work list
+  unsigned long long* tile_stats;  // S2B_TILE_STATS builds: staged / fallback / idle tiles, cycles, sizes
+  int tile;            // 1: "all" mode searches run tiled out of shared memory (nn_tile_body)
   int few_terms;       // every thread of the accumulating kernel adds at most 30 terms per slot
   float* c_lb;         // certified lower bound per query (see nn kernels)
   const float* S_lb;   // transform the bounds are valid for
@@ -175,15 +177,17 @@ __device__ __forceinline__ float axis_gap(int d, float fr) {
   return fmaxf(g - 2e-3f, 0.f);
 }
 
-// fixed cloud: key = linear cell id (x fastest), invalid points -> 0xffffffff
+// fixed cloud: key = (linear cell id (x fastest) << 32) | order-preserving bits of x, invalid points
+// -> all ones.  Sorting by it leaves every run of consecutive cells of a grid row sorted by x, which is
+// what lets the row scans stop as soon as |x - q_x| alone exceeds the pruning radius.
 __global__ void cell_key_kernel(const float* __restrict__ xyz, const unsigned char* __restrict__ valid, int n,
                                 int dim, float ox, float oy, float oz, float inv, int nx, int ny, int nz,
-                                unsigned* __restrict__ keys, int* __restrict__ vals) {
+                                unsigned long long* __restrict__ keys, int* __restrict__ vals) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   vals[i] = i;
   if (valid && !valid[i]) {
-    keys[i] = 0xffffffffu;
+    keys[i] = ~0ull;
     return;
   }
   const float x = xyz[(size_t) i * dim], y = xyz[(size_t) i * dim + 1];
@@ -191,7 +195,8 @@ __global__ void cell_key_kernel(const float* __restrict__ xyz, const unsigned ch
   int cx = min(max(cell_coord(x, ox, inv, nx), 0), nx - 1);
   int cy = min(max(cell_coord(y, oy, inv, ny), 0), ny - 1);
   int cz = min(max(cell_coord(z, oz, inv, nz), 0), nz - 1);
-  keys[i] = (unsigned) ((cz * ny + cy) * nx + cx);
+  const unsigned xbits = (unsigned) f2ord(x + 0.f) ^ 0x80000000u;  // (+0.f: -0 sorts as +0)
+  keys[i] = ((unsigned long long) (unsigned) ((cz * ny + cy) * nx + cx) << 32) | xbits;
 }
 
 __device__ __forceinline__ unsigned spread3(unsigned v) {  // 10 bits -> every third bit
@@ -211,9 +216,38 @@ __device__ __forceinline__ unsigned spread2(unsigned v) {  // 15 bits -> every s
   return v;
 }
 
-// moving cloud: Morton key over its own bounding box (pose independent, so the spatial coherence
-// of a warp's queries survives every rigid transform the aligner applies)
-__global__ void morton_key_kernel(const float* __restrict__ xyz, const unsigned char* __restrict__ valid, int n,
+// Hilbert index of a quantised point (Skilling's transpose algorithm, B bits per axis): unlike the
+// Morton order, consecutive cells of the curve are always face neighbours, so ANY run of
+// consecutive points is a spatially compact blob -- which is what lets nn_tile_kernel stage the
+// whole search neighbourhood of a 256-query tile in shared memory.
+template <int N, int B>
+__device__ __forceinline__ void hilbert_transpose(unsigned* X) {
+  const unsigned M = 1u << (B - 1);
+  for (unsigned Q = M; Q > 1; Q >>= 1) {
+    const unsigned P = Q - 1;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      if (X[i] & Q) {
+        X[0] ^= P;
+      } else {
+        const unsigned t = (X[0] ^ X[i]) & P;
+        X[0] ^= t;
+        X[i] ^= t;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 1; i < N; ++i) X[i] ^= X[i - 1];
+  unsigned t = 0;
+  for (unsigned Q = M; Q > 1; Q >>= 1)
+    if (X[N - 1] & Q) t ^= Q - 1;
+#pragma unroll
+  for (int i = 0; i < N; ++i) X[i] ^= t;
+}
+
+// moving cloud: Hilbert key over its own bounding box (pose independent, so the spatial coherence
+// of a tile's queries survives every rigid transform the aligner applies)
+__global__ void curve_key_kernel(const float* __restrict__ xyz, const unsigned char* __restrict__ valid, int n,
                                   int dim, float ox, float oy, float oz, float sx, float sy, float sz,
                                   unsigned* __restrict__ keys, int* __restrict__ vals) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -226,14 +260,18 @@ __global__ void morton_key_kernel(const float* __restrict__ xyz, const unsigned 
   const float x = xyz[(size_t) i * dim], y = xyz[(size_t) i * dim + 1];
   if (dim == 3) {
     const float z = xyz[(size_t) i * dim + 2];
-    const unsigned qx = (unsigned) fminf(fmaxf((x - ox) * sx, 0.f), 1023.f);
-    const unsigned qy = (unsigned) fminf(fmaxf((y - oy) * sy, 0.f), 1023.f);
-    const unsigned qz = (unsigned) fminf(fmaxf((z - oz) * sz, 0.f), 1023.f);
-    keys[i] = spread3(qx) | (spread3(qy) << 1) | (spread3(qz) << 2);
+    unsigned X[3];
+    X[0] = (unsigned) fminf(fmaxf((x - ox) * sx, 0.f), 1023.f);
+    X[1] = (unsigned) fminf(fmaxf((y - oy) * sy, 0.f), 1023.f);
+    X[2] = (unsigned) fminf(fmaxf((z - oz) * sz, 0.f), 1023.f);
+    hilbert_transpose<3, 10>(X);
+    keys[i] = (spread3(X[0]) << 2) | (spread3(X[1]) << 1) | spread3(X[2]);
   } else {
-    const unsigned qx = (unsigned) fminf(fmaxf((x - ox) * sx, 0.f), 32767.f);
-    const unsigned qy = (unsigned) fminf(fmaxf((y - oy) * sy, 0.f), 32767.f);
-    keys[i] = spread2(qx) | (spread2(qy) << 1);
+    unsigned X[2];
+    X[0] = (unsigned) fminf(fmaxf((x - ox) * sx, 0.f), 32767.f);
+    X[1] = (unsigned) fminf(fmaxf((y - oy) * sy, 0.f), 32767.f);
+    hilbert_transpose<2, 15>(X);
+    keys[i] = (spread2(X[0]) << 1) | spread2(X[1]);
   }
 }
 
@@ -261,23 +299,23 @@ __global__ void gather_kernel(const float* __restrict__ xyz, const float* __rest
 }
 
 // cell_start[c] = first sorted position whose key >= c (lower bound), c in [0, ncells]
-__global__ void cell_start_kernel(const unsigned* __restrict__ keys, int n_valid, int ncells,
+__global__ void cell_start_kernel(const unsigned long long* __restrict__ keys, int n_valid, int ncells,
                                   int* __restrict__ cell_start) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c > ncells) return;
   int lo = 0, hi = n_valid;
   while (lo < hi) {
     const int mid = (lo + hi) >> 1;
-    if (keys[mid] < (unsigned) c) lo = mid + 1; else hi = mid;
+    if ((unsigned) (keys[mid] >> 32) < (unsigned) c) lo = mid + 1; else hi = mid;
   }
   cell_start[c] = lo;
 }
 
 // number of distinct keys among the first n sorted keys (= occupied cells)
-__global__ void count_distinct_kernel(const unsigned* __restrict__ keys, int n, int* __restrict__ out) {
+__global__ void count_distinct_kernel(const unsigned long long* __restrict__ keys, int n, int* __restrict__ out) {
   int c = 0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-    c += (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
+    c += (i == 0 || (keys[i] >> 32) != (keys[i - 1] >> 32)) ? 1 : 0;
   c = __reduce_add_sync(0xffffffffu, c);
   if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
 }
@@ -367,6 +405,53 @@ __device__ __forceinline__ void nn_consider(const SliceArgs& a, NNQuery& q, int 
   nn_consider_pt<DIM, TRACK2>(q, p, __ldg(a.fp + p));
 }
 
+// Candidates [ps, pe) of one run of consecutive cells xa..xb of a grid row are sorted by x.  Start at
+// the position the query's x interpolates to and walk outwards in both directions; a direction ends
+// as soon as (x - q_x)^2 alone exceeds the pruning radius, because every point further along is at
+// least that far away (fl(dx^2) <= the computed d^2: adding non-negative terms is monotone in fp32).
+// Exact for ANY starting position -- a bad guess only costs extra steps.  LOAD(p) fetches candidate p.
+template <int DIM, bool TRACK2, int WIDE, class Load>
+__device__ __forceinline__ void nn_scan_run(NNQuery& q, int ps, int pe, int xa, int xb, Load load) {
+  const int n = pe - ps;
+  if (n <= 0) return;
+  const float frac = __fdividef(q.cfx - (float) xa, (float) (xb - xa + 1));
+  const int g = ps + min(max((int) (frac * (float) n), 0), n - 1);
+  // right: g, g + 1, ...
+#pragma unroll 1
+  for (int p = g; p < pe; p += WIDE) {
+    float4 c[WIDE];
+#pragma unroll
+    for (int j = 0; j < WIDE; ++j) c[j] = load(min(p + j, pe - 1));
+    bool stop = false;
+#pragma unroll
+    for (int j = 0; j < WIDE; ++j) {
+      if (p + j < pe && !stop) {
+        const float ex = c[j].x - q.qx;
+        if (ex > 0.f && ex * ex > (TRACK2 ? q.sd2 : q.bd2)) stop = true;
+        else nn_consider_pt<DIM, TRACK2>(q, p + j, c[j]);
+      }
+    }
+    if (stop) break;
+  }
+  // left: g - 1, g - 2, ...
+#pragma unroll 1
+  for (int p = g - 1; p >= ps; p -= WIDE) {
+    float4 c[WIDE];
+#pragma unroll
+    for (int j = 0; j < WIDE; ++j) c[j] = load(max(p - j, ps));
+    bool stop = false;
+#pragma unroll
+    for (int j = 0; j < WIDE; ++j) {
+      if (p - j >= ps && !stop) {
+        const float ex = q.qx - c[j].x;
+        if (ex > 0.f && ex * ex > (TRACK2 ? q.sd2 : q.bd2)) stop = true;
+        else nn_consider_pt<DIM, TRACK2>(q, p - j, c[j]);
+      }
+    }
+    if (stop) break;
+  }
+}
+
 // scan the part of cell row (y, z) that can still matter, given the conservative squared distance
 // lb2 between the query and the row's y/z slab.  Pruning radius: bd2 (nearest only) or sd2 (two
 // nearest, needed to certify a bound).
@@ -380,8 +465,11 @@ __device__ __forceinline__ void nn_scan_row(const SliceArgs& a, NNQuery& q, int 
   const int row = (z * a.ny + y) * a.nx;
   const int ps = __ldg(a.cell_start + row + xa);
   const int pe = __ldg(a.cell_start + row + xb + 1);
-  // candidates in ascending position, four loads in flight per step (the compare chain is serial,
-  // the loads are not): out-of-range slots re-read the last point and are not considered
+  // several loads in flight per step (the compare chain is serial, the loads are not)
+#if S2B_XSCAN
+  const float4* fp = a.fp;
+  nn_scan_run<DIM, TRACK2, 4>(q, ps, pe, xa, xb, [fp](int p) { return __ldg(fp + p); });
+#else
   const int last = pe - 1;
 #pragma unroll 1
   for (int p = ps; p < pe; p += 4) {
@@ -394,6 +482,7 @@ __device__ __forceinline__ void nn_scan_row(const SliceArgs& a, NNQuery& q, int 
     if (p + 2 < pe) nn_consider_pt<DIM, TRACK2>(q, p + 2, c2);
     if (p + 3 < pe) nn_consider_pt<DIM, TRACK2>(q, p + 3, c3);
   }
+#endif
 }
 
 template <int DIM>
@@ -547,9 +636,344 @@ __device__ __forceinline__ void nn_phase1_body(const SliceArgs& a, const float* 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Tiled search ("all" mode: every query of the slice is searched).  A CTA takes a tile of 256
+// consecutive queries -- a compact blob, thanks to the Hilbert order -- and stages the WHOLE search
+// neighbourhood of the tile in shared memory: the bounding box of the queries' cells dilated by R,
+// i.e. for each (y, z) row of that box the contiguous run of cell-sorted fixed points and the row's
+// slice of the cell table.  Every query then walks its (2R+1)^(DIM-1) rows ring by ring out of
+// shared memory (~30 cycles per dependent access instead of an L2 round trip), so the far ring
+// queries of a badly aligned first iteration cost the same as the near ones and no phase 2 is
+// needed.  Tiles whose box does not fit (sparse regions) fall back to the global-memory walk.
+// ---------------------------------------------------------------------------------------------
+constexpr int kTileThreads = 256;
+constexpr int kTileCapPts = 2560;      // staged fixed points (40 KB)
+constexpr int kTileCapEntries = 5632;  // staged cell-table entries, (bx + 1) per row (22 KB)
+constexpr int kTileCapRows = 768;      // rows of the dilated box (3 per thread in the scan)
+
+struct TileSmem {
+  float4 pts[kTileCapPts];
+  int cs[kTileCapEntries];
+  int rdelta[kTileCapRows];  // staged index of the row's first point minus its cell-order position
+  int rows[kRowTable];
+  float S[16], Slb[16];
+  int box[8];       // min cx, cy, cz, max cx, cy, cz of the tile's queries
+  int wsum[kTileThreads / 32];
+  int npts;
+  unsigned long long bar;  // mbarrier of the bulk copies (TMA variant)
+};
+
+#ifndef S2B_XSCAN
+#define S2B_XSCAN 1  // global-memory row scans use the x order of the runs (0: plain 4-wide scan of the whole run)
+#endif
+#ifndef S2B_TILE_STATS
+#define S2B_TILE_STATS 0  // 1: per-run counters of the tiled search in a.tile_stats (experiments only)
+#endif
+#ifndef S2B_TILE_TMA
+#define S2B_TILE_TMA 1  // 1: rows staged with cp.async.bulk (TMA) + mbarrier; 0: 16-byte cp.async per point
+#endif
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned) __cvta_generic_to_shared(p); }
+
+// whole-neighbourhood walk of one query out of global memory (ring-ordered rows, pruned)
+template <int DIM, bool TRACK2>
+__device__ __forceinline__ void nn_search_global(const SliceArgs& a, NNQuery& q, const int* rows, int K, float cell) {
+  for (int k = 0; k < K; ++k) {
+    const int e = rows[k];
+    const int dy = (int) (signed char) (e & 0xff), dz = (int) (signed char) ((e >> 8) & 0xff);
+    const int ring = (e >> 16) & 0xff;
+    const float pr2 = TRACK2 ? q.sd2 : q.bd2;
+    if (ring >= 2) {  // every row of this and later rings is at least (ring - 1) cells away
+      const float g = ((float) (ring - 1) - 4e-3f) * cell;
+      if (g * g > pr2) break;
+    }
+    const int y = q.cy + dy, z = q.cz + dz;
+    if (y < 0 || y >= a.ny || z < 0 || z >= a.nz) continue;
+    const float gy = axis_gap(dy, q.fry) * cell;
+    float lb2 = gy * gy;
+    if (DIM == 3) {
+      const float gz = axis_gap(dz, q.frz) * cell;
+      lb2 = fmaf(gz, gz, lb2);
+    }
+    if (lb2 > pr2) continue;
+    nn_scan_row<DIM, TRACK2>(a, q, y, z, lb2);
+  }
+}
+
+// one staged row run: candidates [ps, pe) sorted by x in shared memory.  Binary search for the
+// query's x, then outwards in both directions until |x - q_x| alone exceeds the pruning radius.
+template <int DIM, bool TRACK2>
+__device__ __forceinline__ void nn_scan_staged(NNQuery& q, const float4* pr, int ps, int pe) {
+  int lo = ps, hi = pe;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (pr[mid].x < q.qx) lo = mid + 1; else hi = mid;
+  }
+#pragma unroll 1
+  for (int p = lo; p < pe; ++p) {
+    const float4 c = pr[p];
+    const float ex = c.x - q.qx;
+    if (ex * ex > (TRACK2 ? q.sd2 : q.bd2)) break;
+    nn_consider_pt<DIM, TRACK2>(q, p, c);
+  }
+#pragma unroll 1
+  for (int p = lo - 1; p >= ps; --p) {
+    const float4 c = pr[p];
+    const float ex = q.qx - c.x;
+    if (ex * ex > (TRACK2 ? q.sd2 : q.bd2)) break;
+    nn_consider_pt<DIM, TRACK2>(q, p, c);
+  }
+}
+
+template <int DIM, bool TRACK2>
+__device__ __forceinline__ void nn_tile_body(const SliceArgs& a, TileSmem& sm, float cell) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int R = a.R;
+  const int K = (DIM == 3) ? (2 * R + 1) * (2 * R + 1) : (2 * R + 1);
+  const int n_tiles = (a.nm + kTileThreads - 1) / kTileThreads;
+#if S2B_TILE_TMA
+  unsigned phase = 0;
+#endif
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+#if S2B_TILE_STATS
+    const long long t_begin = clock64();
+#endif
+    const int i = tile * kTileThreads + tid;
+    const bool valid = i < a.nm;
+    NNQuery q;
+    int old_slot = -1;
+    if (tid < 3) { sm.box[tid] = INT_MAX; sm.box[3 + tid] = INT_MIN; }
+    __syncthreads();  // also fences the previous tile's readers of the staged data
+    bool need = false;  // the query has to be searched (not answered by the dilated-occupancy bit)
+    float cfy = 0.f, cfz = 0.f;
+    if (valid) {
+      nn_setup<DIM>(a, sm.S, a.mp[i], q);
+      cfy = (float) q.cy + q.fry; cfz = (float) q.cz + q.frz;
+      old_slot = a.c_fpos[i];
+      const int p0 = slot_candidate(old_slot);
+      need = true;
+      if (a.warm && p0 >= 0) {
+        // last iteration's neighbour: a real candidate whose distance bounds the search radius
+        nn_consider<DIM, TRACK2>(a, q, p0);
+        if (TRACK2 && q.bpos >= 0) {
+          // certify "every other point is at least min(2 d0, cell / 4) away" at most: everything within
+          // sqrt(sd2) gets examined, a smaller start value only makes the certified bound smaller
+          const float r_t = fmaxf(4.f * q.bd2, 0.0625f * cell * cell);
+          q.sd2 = fminf(q.sd2, r_t);
+        }
+      } else if (q.cx >= 0 && q.cx < a.nx && q.cy >= 0 && q.cy < a.ny && q.cz >= 0 && q.cz < a.nz) {
+        const int c = (q.cz * a.ny + q.cy) * a.nx + q.cx;
+        need = ((__ldg(a.near_bits + (c >> 5)) >> (c & 31)) & 1u) != 0;
+      }
+    }
+    {  // bounding box of the cells within reach (the pruning radius) of the queries that search
+      int lo[3] = {INT_MAX, INT_MAX, INT_MAX}, hi[3] = {INT_MIN, INT_MIN, INT_MIN};
+      if (need) {
+        const float rq = __fsqrt_rn(TRACK2 ? q.sd2 : q.bd2) * a.inv_cell + 2e-3f;
+        lo[0] = max((int) floorf(q.cfx - rq), q.cx - R); hi[0] = min((int) floorf(q.cfx + rq), q.cx + R);
+        lo[1] = max((int) floorf(cfy - rq), q.cy - R); hi[1] = min((int) floorf(cfy + rq), q.cy + R);
+        if (DIM == 3) { lo[2] = max((int) floorf(cfz - rq), q.cz - R); hi[2] = min((int) floorf(cfz + rq), q.cz + R); }
+        else { lo[2] = 0; hi[2] = 0; }
+      }
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        lo[k] = __reduce_min_sync(0xffffffffu, lo[k]);
+        hi[k] = __reduce_max_sync(0xffffffffu, hi[k]);
+      }
+      if (lane < 3) {
+        const int l = lane == 0 ? lo[0] : (lane == 1 ? lo[1] : lo[2]);
+        const int h = lane == 0 ? hi[0] : (lane == 1 ? hi[1] : hi[2]);
+        if (l != INT_MAX) { atomicMin(&sm.box[lane], l); atomicMax(&sm.box[3 + lane], h); }
+      }
+    }
+    __syncthreads();
+    const bool any = sm.box[0] != INT_MAX;
+    const int x0 = min(max(sm.box[0], 0), a.nx - 1), x1 = min(max(sm.box[3], 0), a.nx - 1);
+    const int y0 = min(max(sm.box[1], 0), a.ny - 1), y1 = min(max(sm.box[4], 0), a.ny - 1);
+    const int z0 = (DIM == 3) ? min(max(sm.box[2], 0), a.nz - 1) : 0;
+    const int z1 = (DIM == 3) ? min(max(sm.box[5], 0), a.nz - 1) : 0;
+    const int bx1 = x1 - x0 + 2, by = y1 - y0 + 1, bz = z1 - z0 + 1;  // bx1 = table entries per row
+    const int nrows = by * bz;
+    bool staged = any && nrows <= kTileCapRows && nrows * bx1 <= kTileCapEntries;
+    if (staged) {
+      // the rows' slices of the cell table, entries dealt to the threads, four independent loads in
+      // flight per thread (divisions by multiply-high: exact while e * bx1 < 2^32)
+      {
+        const int E = nrows * bx1;
+        const unsigned inv_bx1 = (unsigned) (0x100000000ull / (unsigned) bx1) + 1u;
+        const unsigned inv_by = by > 1 ? (unsigned) (0x100000000ull / (unsigned) by) + 1u : 0u;
+        for (int e0 = tid; e0 < E; e0 += kTileThreads * 4) {
+          int v[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int e = e0 + j * kTileThreads;
+            if (e < E) {
+              const int r = (int) __umulhi((unsigned) e, inv_bx1), k = e - r * bx1;
+              const int rz = by > 1 ? (int) __umulhi((unsigned) r, inv_by) : r, ry = r - rz * by;
+              v[j] = __ldg(a.cell_start + (size_t) ((z0 + rz) * a.ny + y0 + ry) * a.nx + x0 + k);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int e = e0 + j * kTileThreads;
+            if (e < E) sm.cs[e] = v[j];
+          }
+        }
+      }
+      __syncthreads();
+      // exclusive scan of the rows' point counts -> staged offsets (3 consecutive rows per thread)
+      int cnt[3], mine = 0;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const int r = tid * 3 + j;
+        cnt[j] = r < nrows ? sm.cs[r * bx1 + bx1 - 1] - sm.cs[r * bx1] : 0;
+        mine += cnt[j];
+      }
+      int incl = mine;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += v;
+      }
+      if (lane == 31) sm.wsum[warp] = incl;
+      __syncthreads();
+      int wbase = 0, total = 0;
+#pragma unroll
+      for (int w = 0; w < kTileThreads / 32; ++w) {
+        const int v = sm.wsum[w];
+        if (w < warp) wbase += v;
+        total += v;
+      }
+      staged = total <= kTileCapPts;  // uniform across the CTA
+      if (staged) {
+        int off = wbase + incl - mine;
+#if S2B_TILE_TMA
+        // every thread announces the bytes of its own rows before issuing their copies
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&sm.bar)),
+                     "r"((unsigned) mine * 16u) : "memory");
+#endif
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const int r = tid * 3 + j;
+          if (r < nrows) {
+            const int g0 = sm.cs[r * bx1];
+            sm.rdelta[r] = off - g0;
+#if S2B_TILE_TMA
+            if (cnt[j] > 0) {  // one bulk copy per row: contiguous in cell order, 16-byte granules
+              asm volatile(
+                "cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                  smem_u32(&sm.pts[off])),
+                "l"(a.fp + g0), "r"((unsigned) cnt[j] * 16u), "r"(smem_u32(&sm.bar))
+                : "memory");
+            }
+#endif
+            off += cnt[j];
+          }
+        }
+#if S2B_TILE_TMA
+        {  // wait for all bytes of this tile's rows
+          unsigned done = 0;
+          while (!done) {
+            asm volatile(
+              "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+              : "=r"(done) : "r"(smem_u32(&sm.bar)), "r"(phase) : "memory");
+          }
+          phase ^= 1u;
+        }
+#else
+        __syncthreads();  // rdelta visible
+        for (int r = warp; r < nrows; r += kTileThreads / 32) {
+          const int g0 = sm.cs[r * bx1], n = sm.cs[r * bx1 + bx1 - 1] - g0, d = sm.rdelta[r];
+          for (int p = lane; p < n; p += 32)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(&sm.pts[d + g0 + p])), "l"(a.fp + g0 + p) : "memory");
+        }
+        asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+#endif
+      }
+    }
+    __syncthreads();
+#if S2B_TILE_STATS
+    const long long t_staged = clock64();
+    if (tid == 0 && a.tile_stats) {
+      atomicAdd(a.tile_stats + (staged ? 0 : (any ? 1 : 2)), 1ull);
+      if (!staged && any && nrows <= kTileCapRows && nrows * bx1 <= kTileCapEntries) atomicAdd(a.tile_stats + 7, 1ull);
+      atomicAdd(a.tile_stats + 3, (unsigned long long) (t_staged - t_begin));
+      if (staged) { atomicAdd(a.tile_stats + 5, (unsigned long long) nrows); atomicAdd(a.tile_stats + 6, (unsigned long long) (nrows * bx1)); }
+    }
+    struct SearchTimer {
+      long long t0; unsigned long long* out; bool on;
+      __device__ ~SearchTimer() { if (on) atomicAdd(out, (unsigned long long) (clock64() - t0)); }
+    } search_timer{t_staged, a.tile_stats + (staged ? 4 : 8), lane == 0 && a.tile_stats != nullptr};
+#endif
+    if (!valid) continue;
+    if (!need) {
+      // nothing occupied within R cells of the query's cell: no fixed point within the covered radius
+      nn_finish<DIM>(a, sm.S, q, i, TRACK2 ? __fsqrt_rn(a.rho_s2) * (1.f - 1e-5f) : 0.f, old_slot);
+      continue;
+    }
+    if (!staged) {
+      nn_search_global<DIM, TRACK2>(a, q, sm.rows, K, cell);
+    } else {
+      // one staged row: the cells within reach along x, then the x-sorted run
+      auto scan_row = [&](int y, int z, float lb2) {
+        const float pr2 = TRACK2 ? q.sd2 : q.bd2;
+        const float rr = __fsqrt_rn(fmaxf(pr2 - lb2, 0.f)) * a.inv_cell + 2e-3f;
+        const int xa = max(max((int) floorf(q.cfx - rr), q.cx - R), 0);
+        const int xb = min(min((int) floorf(q.cfx + rr), q.cx + R), a.nx - 1);
+        if (xa > xb) return;
+        const int r = (z - z0) * by + (y - y0);
+        const int* csr = sm.cs + r * bx1 - x0;
+        nn_scan_staged<DIM, TRACK2>(q, sm.pts + sm.rdelta[r], csr[xa], csr[xb + 1]);
+      };
+      // centre row first: it usually shrinks the pruning radius to a fraction of a cell ...
+      if (q.cy >= 0 && q.cy < a.ny && q.cz >= 0 && q.cz < a.nz) scan_row(q.cy, q.cz, 0.f);
+      // ... so that only the rows within that radius are left (each still pruned by its slab distance)
+      const float rq = __fsqrt_rn(TRACK2 ? q.sd2 : q.bd2) * a.inv_cell + 2e-3f;
+      const int ya = max(max((int) floorf(cfy - rq), q.cy - R), 0), yb = min(min((int) floorf(cfy + rq), q.cy + R), a.ny - 1);
+      const int za = (DIM == 3) ? max(max((int) floorf(cfz - rq), q.cz - R), 0) : 0;
+      const int zb = (DIM == 3) ? min(min((int) floorf(cfz + rq), q.cz + R), a.nz - 1) : 0;
+      for (int z = za; z <= zb; ++z) {
+        const float gz = (DIM == 3) ? axis_gap(z - q.cz, q.frz) * cell : 0.f;
+        for (int y = ya; y <= yb; ++y) {
+          if (y == q.cy && z == q.cz) continue;
+          const float gy = axis_gap(y - q.cy, q.fry) * cell;
+          const float lb2 = (DIM == 3) ? fmaf(gz, gz, gy * gy) : gy * gy;
+          if (lb2 > (TRACK2 ? q.sd2 : q.bd2)) continue;
+          scan_row(y, z, lb2);
+        }
+      }
+    }
+    nn_finish<DIM>(a, sm.S, q, i, TRACK2 ? __fsqrt_rn(q.sd2) * (1.f - 1e-5f) : 0.f, old_slot);
+  }
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(kTileThreads, 3) nn_tile_kernel(const SliceArgs a) {
+  if (*a.stop) return;
+  extern __shared__ __align__(16) unsigned char tile_smem_raw[];
+  TileSmem& sm = *reinterpret_cast<TileSmem*>(tile_smem_raw);
+  const bool all = !a.use_list || *a.list_all;
+  if (!all) return;
+  if (threadIdx.x < 16) { sm.S[threadIdx.x] = a.S[threadIdx.x]; sm.Slb[threadIdx.x] = a.S_lb[threadIdx.x]; }
+  const float cell = __fdiv_rn(1.f, a.inv_cell);
+  const int K = (DIM == 3) ? (2 * a.R + 1) * (2 * a.R + 1) : (2 * a.R + 1);
+  for (int k = threadIdx.x; k < K; k += blockDim.x)
+    sm.rows[k] = (DIM == 3) ? *reinterpret_cast<const int*>(c_rows3[k]) : *reinterpret_cast<const int*>(c_rows2[k]);
+#if S2B_TILE_TMA
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&sm.bar)), "r"(kTileThreads) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+#endif
+  __syncthreads();
+  if (*a.track2) nn_tile_body<DIM, true>(a, sm, cell);
+  else nn_tile_body<DIM, false>(a, sm, cell);
+}
+
 template <int DIM>
 __global__ void __launch_bounds__(256) nn_kernel(const SliceArgs a) {
   if (*a.stop) return;
+  if (a.tile && (!a.use_list || *a.list_all)) return;  // nn_tile_kernel searched everything
   __shared__ float S[16], Slb[16];
   if (threadIdx.x < 16) { S[threadIdx.x] = a.S[threadIdx.x]; Slb[threadIdx.x] = a.S_lb[threadIdx.x]; }
   __syncthreads();
@@ -1088,6 +1512,11 @@ __global__ void __launch_bounds__(256) nn_far_kernel(const SliceArgs a) {
 #define S2B_LIN_CTAS 2
 #endif
 constexpr int kLinThreads = S2B_LIN_THREADS, kLinCtas = S2B_LIN_CTAS;
+#ifndef S2B_LIN_STAGES
+#define S2B_LIN_STAGES 4
+#endif
+constexpr int kLinStages = S2B_LIN_STAGES;  // depth of the per-thread cp.async ring of point data
+constexpr size_t kLinSmemBytes = (size_t) kLinStages * kLinThreads * (4 * sizeof(float4) + 3 * sizeof(int));
 constexpr int kFailCap = 128;  // coherence-check failures a CTA of the fused kernel resolves in place
 
 template <int DIM, int FACTOR, bool CHECK>
@@ -1111,53 +1540,64 @@ __global__ void __launch_bounds__(kLinThreads, kLinCtas) linearize_kernel(const 
   LinAcc<DIM> A;
   A.clear();
 
-  // software pipeline, three deep: index (w + 2 strides) -> slot / bound (w + 1 stride) -> point data
-  // (w); the loads of later queries are in flight while the current one is linearised
+  // software pipeline: index (w + D + 1 strides) -> slot / bound (w + D strides) -> point data (w + D - 1
+  // strides .. w), the point data travelling through a per-thread ring in shared memory filled by
+  // 16-byte cp.async copies, so D - 1 gathers per thread are in flight while one correspondence is
+  // linearised and none of them occupies registers
+  constexpr int D = kLinStages;
+  extern __shared__ __align__(16) unsigned char lin_smem_raw[];
+  float4* ring = reinterpret_cast<float4*>(lin_smem_raw);                          // [D][4][threads]
+  int* ring_i = reinterpret_cast<int*>(lin_smem_raw + (size_t) D * 4 * kLinThreads * sizeof(float4));  // [D][3][threads]
   const int stride = gridDim.x * blockDim.x;
   const int n_work = CHECK ? a.nm : (all ? a.nm : *a.work_count);
   if (!CHECK && small_work_list(a, all, n_work)) return;  // nn_far_kernel linearises short lists itself
   const bool direct = CHECK || all;
   auto index_of = [&](int w) { return w < n_work ? (direct ? w : a.work_list[w]) : -1; };
   const bool regate = a.gate != 0;  // gated-out slots are re-checked every iteration
-  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  int w = blockIdx.x * blockDim.x + threadIdx.x;
-  int i_n = index_of(w);
-  int slot_n = i_n >= 0 ? a.c_fpos[i_n] : -1;
-  float lb_n = (CHECK && i_n >= 0) ? a.c_lb[i_n] : 0.f;
-  float4 m_n = zero4, nm_n = zero4, f_n = zero4, nf_n = zero4;
-  int pn = -1;  // candidate position of the prefetched query (travels with it through the pipeline)
-  {
-    pn = regate ? slot_candidate(slot_n) : slot_n;
-    if (i_n >= 0 && (pn >= 0 || CHECK)) m_n = a.mp[i_n];
+  const int tid = threadIdx.x;
+  // issue the copies of one element into ring stage st (always commits a group, possibly empty)
+  auto issue = [&](int st, int i, int slot, float lb) {
+    const int pn = regate ? slot_candidate(slot) : slot;
+    ring_i[(st * 3 + 0) * kLinThreads + tid] = i;
+    ring_i[(st * 3 + 1) * kLinThreads + tid] = slot;
+    ring_i[(st * 3 + 2) * kLinThreads + tid] = __float_as_int(lb);
+    float4* dst = ring + (size_t) st * 4 * kLinThreads + tid;
+    if (i >= 0 && (pn >= 0 || CHECK))
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(a.mp + i) : "memory");
     if (pn >= 0) {
-      nm_n = a.mn[i_n];
-      f_n = __ldg(a.fp + pn); nf_n = __ldg(a.fn + pn);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst + kLinThreads)), "l"(a.mn + i) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst + 2 * kLinThreads)), "l"(a.fp + pn) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst + 3 * kLinThreads)), "l"(a.fn + pn) : "memory");
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  int w = blockIdx.x * blockDim.x + threadIdx.x;
+  // prologue: stages 0 .. D-2 hold elements w .. w + (D-2) strides
+#pragma unroll
+  for (int d = 0; d < D - 1; ++d) {
+    const int i = index_of(w + d * stride);
+    issue(d, i, i >= 0 ? a.c_fpos[i] : -1, (CHECK && i >= 0) ? a.c_lb[i] : 0.f);
   }
-  int i_nn = index_of(w + stride);
-  int slot_nn = i_nn >= 0 ? a.c_fpos[i_nn] : -1;
-  float lb_nn = (CHECK && i_nn >= 0) ? a.c_lb[i_nn] : 0.f;
-  int i_nnn = index_of(w + 2 * stride);
+  int i_b = index_of(w + (D - 1) * stride);  // next element to issue: index, slot, bound in registers
+  int slot_b = i_b >= 0 ? a.c_fpos[i_b] : -1;
+  float lb_b = (CHECK && i_b >= 0) ? a.c_lb[i_b] : 0.f;
+  int i_a = index_of(w + D * stride);        // the one after: index only
+  int st = 0;                                // ring stage of the element processed now
   for (; w < n_work; w += stride) {
-    const int i = i_n;
-    const int slot = slot_n;
-    const float lb_old = lb_n;
-    const float4 m = m_n, nm = nm_n, f = f_n, nf = nf_n;
-    const int bpos = pn;
-    // advance the pipeline
-    i_n = i_nn; slot_n = slot_nn; lb_n = lb_nn;
-    {
-      pn = regate ? slot_candidate(slot_n) : slot_n;
-      if (i_n >= 0 && (pn >= 0 || CHECK)) m_n = a.mp[i_n];
-      if (pn >= 0) {
-        nm_n = a.mn[i_n];
-        f_n = __ldg(a.fp + pn); nf_n = __ldg(a.fn + pn);
-      }
-    }
-    i_nn = i_nnn;
-    slot_nn = i_nn >= 0 ? a.c_fpos[i_nn] : -1;
-    lb_nn = (CHECK && i_nn >= 0) ? a.c_lb[i_nn] : 0.f;
-    i_nnn = index_of(w + 3 * stride);
+    // refill the stage freed by the previous iteration, advance the register part of the pipeline
+    issue(st == 0 ? D - 1 : st - 1, i_b, slot_b, lb_b);
+    i_b = i_a;
+    slot_b = i_b >= 0 ? a.c_fpos[i_b] : -1;
+    lb_b = (CHECK && i_b >= 0) ? a.c_lb[i_b] : 0.f;
+    i_a = index_of(w + (D + 1) * stride);
+    asm volatile("cp.async.wait_group %0;" ::"n"(D - 1) : "memory");  // the oldest group (this element) has landed
+    const int i = ring_i[(st * 3 + 0) * kLinThreads + tid];
+    const int slot = ring_i[(st * 3 + 1) * kLinThreads + tid];
+    const float lb_old = __int_as_float(ring_i[(st * 3 + 2) * kLinThreads + tid]);
+    const int bpos = regate ? slot_candidate(slot) : slot;
+    const float4* src = ring + (size_t) st * 4 * kLinThreads + tid;
+    const float4 m = src[0], nm = src[kLinThreads], f = src[2 * kLinThreads], nf = src[3 * kLinThreads];
+    st = st == D - 1 ? 0 : st + 1;
     if (CHECK) {
       // exact temporal coherence (see the NN kernels): keep the neighbour / the "none" verdict when
       // the certified bound minus the query's motion still proves it; else hand over to the search
@@ -1214,6 +1654,7 @@ __global__ void __launch_bounds__(kLinThreads, kLinCtas) linearize_kernel(const 
     }
     lin_one<DIM, FACTOR>(a, Ss, i, slot, bpos, m, nm, f, nf, A);
   }
+  asm volatile("cp.async.wait_all;" ::: "memory");
   if (CHECK) {
     __syncthreads();
     const int n_local = min(s_nfail, kFailCap);
