@@ -6,8 +6,10 @@
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
+#include <thrust/iterator/reverse_iterator.h>
 #include <dlfcn.h>
 
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -124,6 +126,7 @@ struct srrg2b_ctx {
   DevBuf<unsigned char> o_stat, d_stat;
   DevBuf<int> imp_f, imp_m, imp_bad;
   int* h_bounds = nullptr;  // pinned 8 ints
+  int* h_bounds_init = nullptr;  // pinned: initial value of the bounds reduction
   // comm
   ncclComm_t comm = nullptr;
   int rank = 0, world = 1;
@@ -174,6 +177,27 @@ namespace {
 
 inline int blocks_for(int64_t n, int threads) { return (int) ((n + threads - 1) / threads); }
 
+// SRRG2B_TRACE=1: wall-clock checkpoints of the index builds on stderr (each one synchronises the stream)
+struct Trace {
+  srrg2b_ctx* c;
+  const char* what;
+  bool on;
+  std::chrono::steady_clock::time_point t0;
+  Trace(srrg2b_ctx* ctx, const char* w);
+  void mark(const char* label);
+};
+
+Trace::Trace(srrg2b_ctx* ctx, const char* w) : c(ctx), what(w), on(getenv("SRRG2B_TRACE") != nullptr) {
+  if (on) { cudaStreamSynchronize(c->stream); t0 = std::chrono::steady_clock::now(); }
+}
+void Trace::mark(const char* label) {
+  if (!on) return;
+  cudaStreamSynchronize(c->stream);
+  const auto t1 = std::chrono::steady_clock::now();
+  fprintf(stderr, "[srrg2b trace] %s: %s %.1f us\n", what, label, std::chrono::duration<double, std::micro>(t1 - t0).count());
+  t0 = std::chrono::steady_clock::now();
+}
+
 int cub_sort_pairs(srrg2b_ctx* c, int n, int end_bit) {
   size_t bytes = 0;
   CK(c, cub::DeviceRadixSort::SortPairs(nullptr, bytes, c->keys_a.p, c->keys_b.p, c->vals_a.p, c->vals_b.p, n, 0,
@@ -197,8 +221,8 @@ int cub_sort_pairs64(srrg2b_ctx* c, int n, int end_bit) {
 
 int compute_bounds(srrg2b_ctx* c, const RawCloud& rc) {
   CK(c, c->bounds.ensure(8));
-  const int init[8] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN, 0, 0};
-  CK(c, cudaMemcpyAsync(c->bounds.p, init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
+  // (pinned source: a pageable one makes the copy synchronous behind the cloud uploads queued before it)
+  CK(c, cudaMemcpyAsync(c->bounds.p, c->h_bounds_init, 8 * sizeof(int), cudaMemcpyHostToDevice, c->stream));
   if (rc.n > 0) {
     const int blocks = std::min(blocks_for(rc.n, 256), c->sm_count * 8);
     bounds_kernel<<<blocks, 256, 0, c->stream>>>(rc.xyz.p, rc.has_valid ? rc.valid.p : nullptr, (int) rc.n, c->dim,
@@ -236,8 +260,10 @@ int upload_raw(srrg2b_ctx* c, RawCloud& rc, const srrg2b_cloud* cl) {
 int build_moving(srrg2b_ctx* c, SliceData& sd) {
   RawCloud& rc = sd.moving_raw;
   const int n = (int) rc.n, dim = c->dim;
+  Trace tr(c, "build_moving");
   int rcode = compute_bounds(c, rc);
   if (rcode) return rcode;
+  tr.mark("bounds");
   sd.nm_valid = c->h_bounds[7];
   memcpy(&sd.coord_bound, &c->h_bounds[6], 4);
   sd.coord_bound_global = false;
@@ -258,6 +284,7 @@ int build_moving(srrg2b_ctx* c, SliceData& sd) {
   CK(c, sd.c_stat.ensure((size_t) n));
   sd.corr_valid = false;
   sd.stat_valid = false;
+  tr.mark("buffers");
   if (n == 0) return SRRG2B_OK;
   float mn[3] = {0, 0, 0}, mx[3] = {0, 0, 0};
   for (int a = 0; a < dim; ++a) {
@@ -278,8 +305,10 @@ int build_moving(srrg2b_ctx* c, SliceData& sd) {
                                                                mn[0], mn[1], mn[2], sc[0], sc[1], sc[2], c->keys_a.p,
                                                                c->vals_a.p);
   c->launches++;
+  tr.mark("keys");
   rcode = cub_sort_pairs(c, n, 32);
   if (rcode) return rcode;
+  tr.mark("sort");
   fill_int_kernel<<<blocks_for(n, 256), 256, 0, c->stream>>>(sd.m_inverse.p, n, -1);
   c->launches++;
   if (sd.nm_valid > 0) {
@@ -292,6 +321,7 @@ int build_moving(srrg2b_ctx* c, SliceData& sd) {
     c->launches += 2;
   }
   CK(c, cudaGetLastError());
+  tr.mark("gather");
   return SRRG2B_OK;
 }
 
@@ -309,8 +339,10 @@ int ensure_index(srrg2b_ctx* c, SliceData& sd, float max_distance) {
   if (!(max_distance > 0.f)) FAIL(c, SRRG2B_ERR_INVALID, "max_distance must be > 0");
   if (sd.built_for_max_distance == max_distance) return SRRG2B_OK;
   const int n = (int) rc.n, dim = c->dim;
+  Trace tr(c, "ensure_index");
   int rcode = compute_bounds(c, rc);
   if (rcode) return rcode;
+  tr.mark("bounds");
   sd.nf_valid = c->h_bounds[7];
   float mn[3] = {0, 0, 0}, mx[3] = {0, 0, 0};
   if (sd.nf_valid > 0) {
@@ -389,6 +421,7 @@ int ensure_index(srrg2b_ctx* c, SliceData& sd, float max_distance) {
     const double occupancy = (double) sd.nf_valid / (double) std::max(1, c->h_bounds[0]);
     if (occupancy >= 2.0) break;
   }
+  tr.mark("keys + sort + occupancy");
   const int ncells = sd.nx * sd.ny * sd.nz;
   CK(c, sd.cell_start.ensure((size_t) ncells + 1));
   if (n > 0) {
@@ -401,16 +434,33 @@ int ensure_index(srrg2b_ctx* c, SliceData& sd, float max_distance) {
       c->launches++;
     }
   }
-  cell_start_kernel<<<blocks_for(ncells + 1, 256), 256, 0, c->stream>>>(c->keys64_b.p, sd.nf_valid, ncells,
-                                                                        sd.cell_start.p);
-  c->launches++;
+  tr.mark("gather");
   {
-    const size_t words = ((size_t) ncells + 31) / 32;
-    CK(c, sd.near_bits.ensure(words));
-    CK(c, cudaMemsetAsync(sd.near_bits.p, 0, words * sizeof(unsigned), c->stream));
-    near_bits_kernel<<<blocks_for(ncells, 256), 256, 0, c->stream>>>(sd.cell_start.p, sd.nx, sd.ny, sd.nz, sd.R, dim,
-                                                                     sd.near_bits.p);
+    // run heads of the sorted cell ids, then a reverse running minimum fills the empty cells
+    CK(c, c->vals_a.ensure((size_t) ncells + 1));
+    fill_int_kernel<<<blocks_for(ncells + 1, 256), 256, 0, c->stream>>>(c->vals_a.p, ncells + 1, sd.nf_valid);
     c->launches++;
+    if (sd.nf_valid > 0) {
+      cell_head_kernel<<<blocks_for(sd.nf_valid, 256), 256, 0, c->stream>>>(c->keys64_b.p, sd.nf_valid, c->vals_a.p);
+      c->launches++;
+    }
+    auto rin = thrust::make_reverse_iterator(c->vals_a.p + ncells + 1);
+    auto rout = thrust::make_reverse_iterator(sd.cell_start.p + ncells + 1);
+    size_t bytes = 0;
+    CK(c, cub::DeviceScan::InclusiveScan(nullptr, bytes, rin, rout, cub::Min(), ncells + 1, c->stream));
+    CK(c, c->cub_tmp.ensure(bytes));
+    CK(c, cub::DeviceScan::InclusiveScan(c->cub_tmp.p, bytes, rin, rout, cub::Min(), ncells + 1, c->stream));
+  }
+  tr.mark("cell table");
+  {
+    const int nxw = near_words_per_row(sd.nx), nrows = sd.ny * sd.nz;
+    const size_t words = (size_t) nrows * nxw;
+    CK(c, sd.near_bits.ensure(words));
+    CK(c, c->keys_a.ensure(words));
+    near_bits_x_kernel<<<blocks_for(words, 256), 256, 0, c->stream>>>(sd.cell_start.p, sd.nx, nrows, sd.R, c->keys_a.p);
+    near_bits_yz_kernel<<<blocks_for(words, 256), 256, 0, c->stream>>>(c->keys_a.p, sd.nx, sd.ny, sd.nz, sd.R, dim,
+                                                                      sd.near_bits.p);
+    c->launches += 2;
   }
   // positions into the old ordering are meaningless now: drop the warm-start candidates
   if (sd.moving_raw.present && sd.nm_valid > 0) {
@@ -421,6 +471,7 @@ int ensure_index(srrg2b_ctx* c, SliceData& sd, float max_distance) {
     sd.corr_valid = false;
   }
   CK(c, cudaGetLastError());
+  tr.mark("near bits + resets");
   sd.built_for_max_distance = max_distance;
   return SRRG2B_OK;
 }
@@ -627,8 +678,7 @@ int launch_slice_iteration(srrg2b_ctx* c, const SliceArgs& a0, int factor) {
     if (rcode) return rcode;
     return launch_linearize(c, a, factor);
   }
-  a.use_list = 1;
-  CK(c, cudaMemsetAsync(a.far_count, 0, 2 * sizeof(int), c->stream));
+  a.use_list = 1;  // (the work-list counters were zeroed by icp_init_kernel / the previous solve step)
   int rcode = launch_linearize_t<true>(c, a, factor);
   if (rcode) return rcode;
   launch_nn(c, a);
@@ -725,6 +775,7 @@ int make_plan(srrg2b_ctx* c, int n_slices, const srrg2b_slice* slices, const srr
       ss.coord_bound = sdd.coord_bound;
       ss.track2_mode = c->track2_mode;
       ss.track2_frac = c->track2_frac;
+      ss.counters = sdd.far_count.p;
     }
     for (int k = 0; k < kKCount; ++k) ss.invk[k] = ldexp(1.0, -sc.k[k]);
   }
@@ -761,8 +812,8 @@ int enqueue_iterations(srrg2b_ctx* c, const Plan& plan, int iterations) {
     }
     int rcode = allreduce_acc(c, plan.solve.n_slices);
     if (rcode) return rcode;
-    if (c->dim == 3) icp_solve_kernel<3><<<1, 32, 0, c->stream>>>(c->d_solve, c->d_state);
-    else icp_solve_kernel<2><<<1, 32, 0, c->stream>>>(c->d_solve, c->d_state);
+    if (c->dim == 3) icp_solve_kernel<3><<<1, kSolveThreads, 0, c->stream>>>(c->d_solve, c->d_state);
+    else icp_solve_kernel<2><<<1, kSolveThreads, 0, c->stream>>>(c->d_solve, c->d_state);
     c->launches++;
   }
   CK(c, cudaGetLastError());
@@ -923,6 +974,11 @@ int srrg2b_ctx_create(int dim, int device, srrg2b_ctx** out) {
   ok = ok && cudaMalloc((void**) &c->d_state, sizeof(DevState)) == cudaSuccess;
   ok = ok && cudaMallocHost((void**) &c->h_state, sizeof(DevState)) == cudaSuccess;
   ok = ok && cudaMallocHost((void**) &c->h_bounds, 8 * sizeof(int)) == cudaSuccess;
+  ok = ok && cudaMallocHost((void**) &c->h_bounds_init, 8 * sizeof(int)) == cudaSuccess;
+  if (ok) {
+    const int init[8] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN, 0, 0};
+    memcpy(c->h_bounds_init, init, sizeof(init));
+  }
   ok = ok && cudaMalloc((void**) &c->d_T0, sizeof(Mat4f)) == cudaSuccess;
   ok = ok && cudaMallocHost((void**) &c->h_T0, sizeof(Mat4f)) == cudaSuccess;
   ok = ok && cudaMalloc((void**) &c->d_solve, sizeof(SolveArgs)) == cudaSuccess;
@@ -1050,6 +1106,9 @@ int srrg2b_set_cloud(srrg2b_ctx* c, int slot, int slice_id, const srrg2b_cloud* 
   }
   int rcode = upload_raw(c, sd.moving_raw, cl);
   if (rcode) return rcode;
+  // (measured: draining the copies before the first kernel is queued is 0.3 ms faster than queueing
+  // the index build behind them)
+  CK(c, cudaStreamSynchronize(c->stream));
   rcode = build_moving(c, sd);
   if (rcode) return rcode;
   CK(c, cudaStreamSynchronize(c->stream));

@@ -22,11 +22,14 @@ constexpr int kMaxStats = 256;
 constexpr int kMaxWindow = 64;
 
 struct Ring {
-  int window, count, head;
+  int window, count, head, pad_;
   double v[kMaxWindow];
 };
 
-struct DevState {
+// Everything the per-iteration solve step reads and writes, contiguous and 16-byte granular so that
+// icp_solve_kernel can stage it in shared memory with one round of wide loads and write it back the
+// same way (the serial part then never waits on global memory).  The IterationStats array follows.
+struct DevHeader {
   Mat4f X;                                   // variable 0 estimate (moving in fixed)
   Mat4f S[SRRG2B_MAX_SLICES];                // robot_in_sensor * X per slice (finder transform)
   unsigned long long acc[SRRG2B_MAX_SLICES][kAcc];
@@ -37,9 +40,14 @@ struct DevState {
   int n_stats;
   int not_enough_corr;
   int iterations_run;
-  srrg2b_iter_stats stats[kMaxStats];
   Ring r_ncorr, r_ninl, r_nout, r_chi;
   int tc_iterations;
+  int pad_[3];
+};
+static_assert(sizeof(DevHeader) % 16 == 0, "DevHeader is copied in 16-byte pieces");
+
+struct DevState : DevHeader {
+  srrg2b_iter_stats stats[kMaxStats];
 };
 
 struct SolveSlice {
@@ -51,9 +59,10 @@ struct SolveSlice {
   float cell, coord_bound;    // NN cell edge / max |coordinate| of the moving cloud
   int track2_mode;            // 0 never, 1 always, 2 automatic (small motion)
   float track2_frac;          // automatic: certify once the per-iteration motion bound is below this many cells
+  int* counters;              // slice's work-list counters {far, work}: zeroed for the next iteration
 };
 
-struct SolveArgs {
+struct alignas(16) SolveArgs {
   int dim, variable, n_slices;
   int use_tc, window, range_corr, range_inl, range_out;
   float chi_eps;
@@ -140,21 +149,31 @@ __global__ void bounds_kernel(const float* __restrict__ xyz, const unsigned char
       amax = max(amax, __float_as_int(fabsf(v)));
     }
   }
-  for (int off = 16; off; off >>= 1) {
-    for (int a = 0; a < 3; ++a) {
-      mn[a] = min(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], off));
-      mx[a] = max(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], off));
-    }
-    amax = max(amax, __shfl_xor_sync(0xffffffffu, amax, off));
-    cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+  // warp reduce (integer min / max / add are REDUX instructions), then one row per warp in shared
+  // memory, then ONE set of global atomics per CTA (they all hit the same eight words)
+  __shared__ int red[8][8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int a = 0; a < 3; ++a) {
+    mn[a] = __reduce_min_sync(0xffffffffu, mn[a]);
+    mx[a] = __reduce_max_sync(0xffffffffu, mx[a]);
   }
-  if ((threadIdx.x & 31) == 0) {
-    for (int a = 0; a < 3; ++a) {
-      atomicMin(&out[a], mn[a]);
-      atomicMax(&out[3 + a], mx[a]);
+  amax = __reduce_max_sync(0xffffffffu, amax);
+  cnt = __reduce_add_sync(0xffffffffu, cnt);
+  if (lane == 0) {
+    for (int a = 0; a < 3; ++a) { red[warp][a] = mn[a]; red[warp][3 + a] = mx[a]; }
+    red[warp][6] = amax; red[warp][7] = cnt;
+  }
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    const int k = threadIdx.x, nw = blockDim.x >> 5;
+    int v = red[0][k];
+    for (int w = 1; w < nw; ++w) {
+      const int o = red[w][k];
+      v = k < 3 ? min(v, o) : (k < 7 ? max(v, o) : v + o);
     }
-    atomicMax(&out[6], amax);
-    atomicAdd(&out[7], cnt);
+    if (k < 3) atomicMin(&out[k], v);
+    else if (k < 7) atomicMax(&out[k], v);
+    else if (v) atomicAdd(&out[7], v);
   }
 }
 
@@ -298,17 +317,14 @@ __global__ void gather_kernel(const float* __restrict__ xyz, const float* __rest
   if (inverse) inverse[src] = i;
 }
 
-// cell_start[c] = first sorted position whose key >= c (lower bound), c in [0, ncells]
-__global__ void cell_start_kernel(const unsigned long long* __restrict__ keys, int n_valid, int ncells,
-                                  int* __restrict__ cell_start) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c > ncells) return;
-  int lo = 0, hi = n_valid;
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if ((unsigned) (keys[mid] >> 32) < (unsigned) c) lo = mid + 1; else hi = mid;
-  }
-  cell_start[c] = lo;
+// cell_start[c] = first sorted position whose cell id >= c (lower bound), c in [0, ncells]:
+// cell_head_kernel writes the first position of every occupied cell into a table preset to n_valid,
+// a reverse running minimum (host: cub::DeviceScan over reverse iterators) fills the empty cells.
+__global__ void cell_head_kernel(const unsigned long long* __restrict__ keys, int n_valid, int* __restrict__ head) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_valid) return;
+  const unsigned c = (unsigned) (keys[i] >> 32);
+  if (i == 0 || (unsigned) (keys[i - 1] >> 32) != c) head[c] = i;
 }
 
 // number of distinct keys among the first n sorted keys (= occupied cells)
@@ -320,27 +336,48 @@ __global__ void count_distinct_kernel(const unsigned long long* __restrict__ key
   if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
 }
 
-// near_bits: bit c is set iff some fixed point lies in a cell within Chebyshev distance R of cell c
-// (the occupancy grid dilated by the search radius).  A query whose own cell has the bit clear has
+// near_bits: the bit of cell c is set iff some fixed point lies in a cell within Chebyshev distance R of
+// c (the occupancy grid dilated by the search radius).  A query whose own cell has the bit clear has
 // no fixed point within (R - slack) cells, i.e. nothing within max_distance: the finder can answer
 // "none" from one load instead of walking (2R+1)^(DIM-1) empty rows.
-__global__ void near_bits_kernel(const int* __restrict__ cell_start, int nx, int ny, int nz, int R, int dim,
-                                 unsigned* __restrict__ bits) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= nx * ny * nz) return;
-  if (cell_start[c + 1] <= cell_start[c]) return;
-  const int cx = c % nx, cy = (c / nx) % ny, cz = c / (nx * ny);
+// Layout: every grid row (y, z) owns nxw = ceil(nx / 32) words, bit x & 31 of word x >> 5, so that rows
+// never share a word.  Pass 1 dilates along x (one thread per word), pass 2 ORs the (2R+1)^(DIM-1) rows.
+__host__ __device__ __forceinline__ int near_words_per_row(int nx) { return (nx + 31) >> 5; }
+
+__device__ __forceinline__ bool near_bit(const unsigned* __restrict__ bits, int nx, int ny, int cx, int cy, int cz) {
+  const int nxw = near_words_per_row(nx);
+  return (__ldg(bits + (size_t) (cz * ny + cy) * nxw + (cx >> 5)) >> (cx & 31)) & 1u;
+}
+
+__global__ void near_bits_x_kernel(const int* __restrict__ cell_start, int nx, int nrows, int R,
+                                   unsigned* __restrict__ out) {
+  const int nxw = near_words_per_row(nx);
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nrows * nxw) return;
+  const int row = t / nxw, w = t - row * nxw;
+  const int* cs = cell_start + (size_t) row * nx;
+  unsigned word = 0;
+  for (int b = 0; b < 32; ++b) {
+    const int x = (w << 5) + b;
+    if (x >= nx) break;
+    const int xa = max(x - R, 0), xb = min(x + R, nx - 1);
+    if (cs[xb + 1] > cs[xa]) word |= 1u << b;  // some point in cells [x - R, x + R] of this row
+  }
+  out[t] = word;
+}
+
+__global__ void near_bits_yz_kernel(const unsigned* __restrict__ in, int nx, int ny, int nz, int R, int dim,
+                                    unsigned* __restrict__ out) {
+  const int nxw = near_words_per_row(nx);
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ny * nz * nxw) return;
+  const int row = t / nxw, w = t - row * nxw;
+  const int cy = row % ny, cz = row / ny;
   const int rz = dim == 3 ? R : 0;
+  unsigned word = 0;
   for (int z = max(cz - rz, 0); z <= min(cz + rz, nz - 1); ++z)
-    for (int y = max(cy - R, 0); y <= min(cy + R, ny - 1); ++y) {
-      const int row = (z * ny + y) * nx;
-      const int a = row + max(cx - R, 0), b = row + min(cx + R, nx - 1);  // bit range [a, b]
-      for (int w = a >> 5; w <= (b >> 5); ++w) {
-        const int lo = max(a - (w << 5), 0), hi = min(b - (w << 5), 31);
-        const unsigned m = (hi == 31 ? 0xffffffffu : ((1u << (hi + 1)) - 1u)) & ~((1u << lo) - 1u);
-        if ((bits[w] & m) != m) atomicOr(&bits[w], m);
-      }
-    }
+    for (int y = max(cy - R, 0); y <= min(cy + R, ny - 1); ++y) word |= in[(size_t) (z * ny + y) * nxw + w];
+  out[t] = word;
 }
 
 __global__ void fill_int_kernel(int* p, int n, int v) {
@@ -549,10 +586,7 @@ __device__ __forceinline__ int nn_finish(const SliceArgs& a, const float* S, con
 // (outliers, large initial misalignment) do not serialise the warps of the cheap ones.
 template <int DIM, bool TRACK2>
 __device__ __forceinline__ void nn_phase1_body(const SliceArgs& a, const float* S, const float* Slb, float cell,
-                                               float ring2, float ring2_sq) {
-  const bool all = !a.use_list || *a.list_all;
-  const int n_work = all ? a.nm : *a.work_count;
-  if (small_work_list(a, all, n_work)) return;
+                                               float ring2, float ring2_sq, bool all, int n_work) {
   for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < n_work; w += gridDim.x * blockDim.x) {
     const int i = all ? w : a.work_list[w];
     NNQuery q;
@@ -583,8 +617,7 @@ __device__ __forceinline__ void nn_phase1_body(const SliceArgs& a, const float* 
     }
     if (p0 < 0 && q.cx >= 0 && q.cx < a.nx && q.cy >= 0 && q.cy < a.ny && q.cz >= 0 && q.cz < a.nz) {
       // nothing occupied within R cells of the query's cell: no fixed point within the covered radius
-      const int c = (q.cz * a.ny + q.cy) * a.nx + q.cx;
-      if (!((__ldg(a.near_bits + (c >> 5)) >> (c & 31)) & 1u)) {
+      if (!near_bit(a.near_bits, a.nx, a.ny, q.cx, q.cy, q.cz)) {
         nn_finish<DIM>(a, S, q, i, TRACK2 ? __fsqrt_rn(a.rho_s2) * (1.f - 1e-5f) : 0.f, old_slot);
         continue;
       }
@@ -762,8 +795,7 @@ __device__ __forceinline__ void nn_tile_body(const SliceArgs& a, TileSmem& sm, f
           q.sd2 = fminf(q.sd2, r_t);
         }
       } else if (q.cx >= 0 && q.cx < a.nx && q.cy >= 0 && q.cy < a.ny && q.cz >= 0 && q.cz < a.nz) {
-        const int c = (q.cz * a.ny + q.cy) * a.nx + q.cx;
-        need = ((__ldg(a.near_bits + (c >> 5)) >> (c & 31)) & 1u) != 0;
+        need = near_bit(a.near_bits, a.nx, a.ny, q.cx, q.cy, q.cz);
       }
     }
     {  // bounding box of the cells within reach (the pruning radius) of the queries that search
@@ -972,8 +1004,14 @@ __global__ void __launch_bounds__(kTileThreads, 3) nn_tile_kernel(const SliceArg
 
 template <int DIM>
 __global__ void __launch_bounds__(256) nn_kernel(const SliceArgs a) {
-  if (*a.stop) return;
-  if (a.tile && (!a.use_list || *a.list_all)) return;  // nn_tile_kernel searched everything
+  // the control words are fetched together: on converged iterations this kernel has nothing to do and
+  // its cost is the latency of these loads
+  const int stop = *a.stop, list_all = *a.list_all, work_count = *a.work_count, track2 = *a.track2;
+  if (stop) return;
+  const bool all = !a.use_list || list_all;
+  if (a.tile && all) return;  // nn_tile_kernel searched everything
+  const int n_work = all ? a.nm : work_count;
+  if (small_work_list(a, all, n_work)) return;
   __shared__ float S[16], Slb[16];
   if (threadIdx.x < 16) { S[threadIdx.x] = a.S[threadIdx.x]; Slb[threadIdx.x] = a.S_lb[threadIdx.x]; }
   __syncthreads();
@@ -981,8 +1019,8 @@ __global__ void __launch_bounds__(256) nn_kernel(const SliceArgs a) {
   // distance below which a point cannot lie in ring 2 or beyond (for R == 1: the covered radius)
   const float ring2 = (a.R >= 2) ? (1.f - 4e-3f) * cell : __fsqrt_rn(a.rho_s2);
   const float ring2_sq = (a.R >= 2) ? ring2 * ring2 : 3.0e38f;
-  if (*a.track2) nn_phase1_body<DIM, true>(a, S, Slb, cell, ring2, ring2_sq);
-  else nn_phase1_body<DIM, false>(a, S, Slb, cell, ring2, ring2_sq);
+  if (track2) nn_phase1_body<DIM, true>(a, S, Slb, cell, ring2, ring2_sq, all, n_work);
+  else nn_phase1_body<DIM, false>(a, S, Slb, cell, ring2, ring2_sq, all, n_work);
 }
 
 // Phase 2: the queries phase 1 could not settle (worklist).  These are few but expensive
@@ -1473,11 +1511,13 @@ __device__ __forceinline__ void lin_flush(const SliceArgs& a, const LinAcc<DIM>&
 // that query -- because at this size the thread-per-query kernels would be pure load latency.
 template <int DIM, int FACTOR>
 __global__ void __launch_bounds__(256) nn_far_kernel(const SliceArgs a) {
-  if (*a.stop) return;
-  const bool all = !a.use_list || *a.list_all;
-  const int n_work = all ? a.nm : *a.work_count;
+  const int stop = *a.stop, list_all = *a.list_all, work_count = *a.work_count, far_count = *a.far_count;
+  const int track2_flag = *a.track2;
+  if (stop) return;
+  const bool all = !a.use_list || list_all;
+  const int n_work = all ? a.nm : work_count;
   const bool tail = small_work_list(a, all, n_work);
-  const int n_far = tail ? n_work : *a.far_count;
+  const int n_far = tail ? n_work : far_count;
   if (n_far == 0) return;
   __shared__ float S[16];
   __shared__ int rows[kRowTable];
@@ -1489,7 +1529,7 @@ __global__ void __launch_bounds__(256) nn_far_kernel(const SliceArgs a) {
     rows[k] = (DIM == 3) ? *reinterpret_cast<const int*>(c_rows3[k]) : *reinterpret_cast<const int*>(c_rows2[k]);
   __syncthreads();
   const float cell = __fdiv_rn(1.f, a.inv_cell);
-  const bool track2 = *a.track2 != 0;
+  const bool track2 = track2_flag != 0;
   const int wpb = blockDim.x >> 5, w0 = blockIdx.x * wpb + (threadIdx.x >> 5), ws = gridDim.x * wpb;
   if (!tail) {
     if (track2) nn_far_body<DIM, true>(a, S, rows, K, cell, n_far, a.far_list, nullptr, w0, ws);
@@ -1521,9 +1561,11 @@ constexpr int kFailCap = 128;  // coherence-check failures a CTA of the fused ke
 
 template <int DIM, int FACTOR, bool CHECK>
 __global__ void __launch_bounds__(kLinThreads, kLinCtas) linearize_kernel(const SliceArgs a) {
-  if (*a.stop) return;
-  const bool all = !a.use_list || *a.list_all;
+  const int stop = *a.stop, list_all = *a.list_all, work_count = *a.work_count;
+  if (stop) return;
+  const bool all = !a.use_list || list_all;
   if (CHECK && all) return;  // nothing is certified: everything goes through the search path
+  if (!CHECK && small_work_list(a, all, all ? a.nm : work_count)) return;  // nn_far_kernel linearises short lists itself
   __shared__ float Ss[16], Sl[16];
   __shared__ FlushSmem fsm;
   __shared__ int s_fail[CHECK ? kFailCap : 1];
@@ -1549,8 +1591,7 @@ __global__ void __launch_bounds__(kLinThreads, kLinCtas) linearize_kernel(const 
   float4* ring = reinterpret_cast<float4*>(lin_smem_raw);                          // [D][4][threads]
   int* ring_i = reinterpret_cast<int*>(lin_smem_raw + (size_t) D * 4 * kLinThreads * sizeof(float4));  // [D][3][threads]
   const int stride = gridDim.x * blockDim.x;
-  const int n_work = CHECK ? a.nm : (all ? a.nm : *a.work_count);
-  if (!CHECK && small_work_list(a, all, n_work)) return;  // nn_far_kernel linearises short lists itself
+  const int n_work = CHECK ? a.nm : (all ? a.nm : work_count);
   const bool direct = CHECK || all;
   auto index_of = [&](int w) { return w < n_work ? (direct ? w : a.work_list[w]) : -1; };
   const bool regate = a.gate != 0;  // gated-out slots are re-checked every iteration
@@ -1694,7 +1735,7 @@ __device__ inline double ring_min(const Ring& r) {
 
 // AlignerTerminationCriteriaStandard_::hasToStop,
 // R/registration/aligners/aligner_termination_criteria_impl.cpp:24-65 (quirks at :32-33,:46,:53 kept)
-__device__ inline bool has_to_stop(DevState* st, const SolveArgs& a, const srrg2b_iter_stats& s, long long ncorr) {
+__device__ inline bool has_to_stop(DevHeader* st, const SolveArgs& a, const srrg2b_iter_stats& s, long long ncorr) {
   ++st->tc_iterations;
   const int ninl = (int) s.num_inliers, nout = (int) s.num_outliers;
   const float chi = __fdiv_rn((float) s.chi_inliers, (float) ninl);
@@ -1748,6 +1789,7 @@ __global__ void icp_init_kernel(const SolveArgs* ap, DevState* st, const Mat4f* 
     // a fresh compute() starts from an arbitrary guess: search everything; the inlier-only second
     // run continues from certified bounds
     if (!keep_stats) st->list_all[s] = 1;  // (the last solve step already set it for a continued run)
+    if (a.sl[s].kind == SRRG2B_SLICE_POINTS && a.sl[s].counters) { a.sl[s].counters[0] = 0; a.sl[s].counters[1] = 0; }
   }
   st->stop = 0;
   st->not_enough_corr = 0;
@@ -1772,42 +1814,24 @@ __global__ void set_S_kernel(DevState* st, int slice, Mat4f S, int track2) {
 }
 
 // body of one _runSolver iteration after the per-slice kernels
-// (R/registration/aligners/multi_aligner_impl.cpp:106-126)
+// (R/registration/aligners/multi_aligner_impl.cpp:106-126), serial part: runs on one thread against the
+// shared-memory copy of the state; the IterationStats entry goes straight to global memory
 template <int DIM>
-__global__ void icp_solve_kernel(const SolveArgs* ap, DevState* st) {
+__device__ void icp_solve_serial(const SolveArgs& a, DevHeader& st, srrg2b_iter_stats* stats_out) {
   constexpr int P = (DIM == 3) ? 6 : 3;
-  __shared__ SolveArgs a;
-  load_solve_args(ap, &a);
-  // the accumulators of all slices are fetched by the whole warp in one go (and zeroed for the
-  // next iteration); the O(#slices) serial part then runs on lane 0 out of shared memory
-  __shared__ unsigned long long sacc[SRRG2B_MAX_SLICES][kAcc];
-  __shared__ int s_stop;
-  if (threadIdx.x == 0) s_stop = st->stop;
-  __syncthreads();
-  if (s_stop) return;
-  for (int k = threadIdx.x; k < a.n_slices * kAcc; k += blockDim.x) {
-    sacc[k / kAcc][k % kAcc] = st->acc[k / kAcc][k % kAcc];
-    st->acc[k / kAcc][k % kAcc] = 0ull;
-  }
-  // the NN pass of this iteration certified its bounds at S: record that before anything can bail out
-  for (int k = 0; k < a.n_slices; ++k)
-    if (a.sl[k].kind == SRRG2B_SLICE_POINTS && a.sl[k].S_lb && threadIdx.x < 16)
-      a.sl[k].S_lb[threadIdx.x] = st->S[k].m[threadIdx.x];
-  __syncthreads();
-  if (threadIdx.x != 0) return;
   double H[P * P], b[P];
 #pragma unroll
   for (int i = 0; i < P * P; ++i) H[i] = 0.0;
 #pragma unroll
   for (int i = 0; i < P; ++i) b[i] = 0.0;
   srrg2b_iter_stats s;
-  s.iteration = st->n_stats;
+  s.iteration = st.n_stats;
   s.solver_status = 0;
   s.num_inliers = 0; s.num_outliers = 0; s.num_suppressed = 0; s.num_correspondences = 0;
   s.chi_inliers = 0.0; s.chi_outliers = 0.0;
   bool good = false;
   long long total = 0;
-  Mat4f X = st->X;
+  Mat4f X = st.X;
   for (int k = 0; k < a.n_slices; ++k) {
     const SolveSlice& sl = a.sl[k];
     if (sl.kind == SRRG2B_SLICE_PRIOR) {
@@ -1821,10 +1845,10 @@ __global__ void icp_solve_kernel(const SolveArgs* ap, DevState* st) {
       s.num_inliers += 1; s.num_correspondences += 1; s.chi_inliers += chi;
       good = true;  // aligner_slice_processor_prior.h:65-67
       total += 1;   // :75-77
-      st->ncorr[k] = 1;
+      st.ncorr[k] = 1;
       continue;
     }
-    const unsigned long long* acc = sacc[k];
+    const unsigned long long* acc = st.acc[k];
     // the slice's H (both triangles) and b are added entry by entry in slice order
     int slot = 0;
 #pragma unroll
@@ -1846,24 +1870,24 @@ __global__ void icp_solve_kernel(const SolveArgs* ap, DevState* st) {
     s.chi_outliers += __ll2double_rn((long long) acc[kAccChiOut]) * sl.invk[kKChi] +
                       __ll2double_rn((long long) acc[kAccChiOut + 1]) * sl.invk[kKChiLo];
     const long long n = ni + no + ns;
-    st->ncorr[k] = n;
+    st.ncorr[k] = n;
     total += n;
     good = good || (n > (long long) sl.min_corr);  // aligner_slice_processor_impl.cpp:77-79
   }
-  st->iterations_run += 1;
+  st.iterations_run += 1;
   if (!good) {  // multi_aligner_impl.cpp:107-111 (estimate already equals the backup)
-    st->not_enough_corr = 1;
-    st->stop = 1;
+    st.not_enough_corr = 1;
+    st.stop = 1;
     return;
   }
   double dx[6] = {0, 0, 0, 0, 0, 0};
   if (spd_solve_t<P>(H, b, dx)) {
     box_plus(DIM, a.variable, dx, X);
-    st->X = X;
+    st.X = X;
     s.solver_status = 1;
   }
-  if (st->n_stats < kMaxStats) st->stats[st->n_stats] = s;
-  st->n_stats += 1;
+  if (st.n_stats < kMaxStats) stats_out[st.n_stats] = s;
+  st.n_stats += 1;
   for (int k = 0; k < a.n_slices; ++k) {
     Mat4f Sn;
     compose(a.sl[k].ris, X, Sn);
@@ -1874,20 +1898,56 @@ __global__ void icp_solve_kernel(const SolveArgs* ap, DevState* st) {
       float dr = 0.f, dt = 0.f;
       for (int r = 0; r < 3; ++r) {
         for (int c = 0; c < 3; ++c) {
-          const float d = Sn.m[r * 4 + c] - st->S[k].m[r * 4 + c];
+          const float d = Sn.m[r * 4 + c] - st.S[k].m[r * 4 + c];
           dr += d * d;
         }
-        const float d = Sn.m[r * 4 + 3] - st->S[k].m[r * 4 + 3];
+        const float d = Sn.m[r * 4 + 3] - st.S[k].m[r * 4 + 3];
         dt += d * d;
       }
       const float motion = sqrtf(dr) * 1.7321f * a.sl[k].coord_bound + sqrtf(dt);
       const int mode = a.sl[k].track2_mode;
-      st->list_all[k] = st->track2[k] ? 0 : 1;  // bounds exist only if the pass just done certified them
-      st->track2[k] = (mode == 1) || (mode == 2 && motion < a.sl[k].track2_frac * a.sl[k].cell) ? 1 : 0;
+      st.list_all[k] = st.track2[k] ? 0 : 1;  // bounds exist only if the pass just done certified them
+      st.track2[k] = (mode == 1) || (mode == 2 && motion < a.sl[k].track2_frac * a.sl[k].cell) ? 1 : 0;
     }
-    st->S[k] = Sn;
+    st.S[k] = Sn;
   }
-  if (a.use_tc && has_to_stop(st, a, s, total)) st->stop = 1;
+  if (a.use_tc && has_to_stop(&st, a, s, total)) st.stop = 1;
+}
+
+constexpr int kSolveThreads = 128;
+
+template <int DIM>
+__global__ void __launch_bounds__(kSolveThreads) icp_solve_kernel(const SolveArgs* ap, DevState* st) {
+  __shared__ __align__(16) SolveArgs a;
+  __shared__ __align__(16) DevHeader sh;
+  // one round of independent 16-byte loads stages the arguments and the whole mutable state
+  {
+    const int4* s0 = reinterpret_cast<const int4*>(ap);
+    int4* d0 = reinterpret_cast<int4*>(&a);
+    for (int k = threadIdx.x; k < (int) (sizeof(SolveArgs) / 16); k += kSolveThreads) d0[k] = s0[k];
+    const int4* s1 = reinterpret_cast<const int4*>(static_cast<const DevHeader*>(st));
+    int4* d1 = reinterpret_cast<int4*>(&sh);
+    for (int k = threadIdx.x; k < (int) (sizeof(DevHeader) / 16); k += kSolveThreads) d1[k] = s1[k];
+  }
+  __syncthreads();
+  if (sh.stop) return;
+  // the NN pass of this iteration certified its bounds at S: record that before anything can bail out;
+  // the work-list counters start the next iteration at zero
+  for (int k = 0; k < a.n_slices; ++k) {
+    if (a.sl[k].kind != SRRG2B_SLICE_POINTS) continue;
+    if (a.sl[k].S_lb && threadIdx.x < 16) a.sl[k].S_lb[threadIdx.x] = sh.S[k].m[threadIdx.x];
+    if (a.sl[k].counters && threadIdx.x >= 32 && threadIdx.x < 34) a.sl[k].counters[threadIdx.x - 32] = 0;
+  }
+  if (threadIdx.x == 0) icp_solve_serial<DIM>(a, sh, st->stats);
+  __syncthreads();
+  // accumulators restart at zero; everything else goes back as the serial part left it
+  for (int k = threadIdx.x; k < a.n_slices * kAcc; k += kSolveThreads) sh.acc[k / kAcc][k % kAcc] = 0ull;
+  __syncthreads();
+  {
+    const int4* s1 = reinterpret_cast<const int4*>(&sh);
+    int4* d1 = reinterpret_cast<int4*>(static_cast<DevHeader*>(st));
+    for (int k = threadIdx.x; k < (int) (sizeof(DevHeader) / 16); k += kSolveThreads) d1[k] = s1[k];
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
