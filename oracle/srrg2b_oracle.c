@@ -17,7 +17,7 @@
  *   * per-term arithmetic is fp32 with an explicitly written operation order; every fused
  *     multiply-add is spelled fmaf(); compile with -ffp-contract=off so nothing else fuses;
  *   * every per-correspondence contribution to H, b, chi is converted to 64-bit fixed point
- *     (llrint(term * 2^k), k from orc_scales) and summed as integers: the sums are exact, hence
+ *     (round(term * 2^k) by a saturating fp32 fma, see to_fix; k from orc_scales) and summed as integers: the sums are exact, hence
  *     independent of summation order, thread count and GPU count;
  *   * the 6x6 / 3x3 solve, pose update and prior factors are fp64 with plain (unfused) operations
  *     and in-house sin/cos/atan2/log so that host libm differences cannot leak in.
@@ -756,28 +756,32 @@ int orc_scales(int dim, int64_t n_global, float coord_bound, const orc_finder_pa
 /* a5 -- per-correspondence linearisation (FactorCorrespondenceDriven_<F,...> inside            */
 /* Solver::compute(), reached from R/registration/aligners/multi_aligner_impl.cpp:112)          */
 /* ------------------------------------------------------------------------------------------ */
-/* round(v * 2^k) for |v| <= 2^(21-k) (clamped), computed the way the GPU does it: adding the magic
- * constant 1.5 * 2^(23-k) leaves the rounded integer (ties to even) in the low mantissa bits. */
+/* Fixed-point value of one term with k fractional bits, |v| <= B = 2^(21-k), computed with the same two
+ * fp32 operations as the GPU: t = clamp(fma(v, 2^(k-22), 0.5), 0, 1) maps [-B, B] onto [0, 1] (and
+ * saturates everything else, NaN -> 0); u = t + 3 lies in [3, 4] where the fp32 spacing is 2^-22, one
+ * unit of 2^-k of v; bits(u) - bits(3.5f) is the term in those units (ties to even). */
 static inline int32_t to_fix(float v, int k) {
-  const float M = ldexpf(1.5f, 23 - k), B = ldexpf(1.f, 21 - k);
-  v = fminf(fmaxf(v, -B), B);
-  const float t = v + M;
-  int32_t ti, mi;
-  memcpy(&ti, &t, 4);
-  memcpy(&mi, &M, 4);
-  return ti - mi;
+  const float s = ldexpf(1.f, k - 22);
+  float t = fmaf(v, s, 0.5f);
+  t = fminf(fmaxf(t, 0.f), 1.f);
+  if (!(t == t)) t = 0.f;
+  const float u = t + 3.0f;
+  int32_t ui;
+  memcpy(&ui, &u, 4);
+  return ui - 0x40600000;
 }
 
 /* chi as a (coarse, residual) pair: the residual of the coarse rounding is exact in fp32 */
 static inline void to_fix2(float v, int k_hi, int k_lo, int64_t* hi, int64_t* lo) {
-  const float M = ldexpf(1.5f, 23 - k_hi), B = ldexpf(1.f, 21 - k_hi);
-  v = fminf(fmaxf(v, -B), B);
-  const float t = v + M;
-  int32_t ti, mi;
-  memcpy(&ti, &t, 4);
-  memcpy(&mi, &M, 4);
-  *hi += ti - mi;
-  const float rem = v - (t - M);
+  const float s = ldexpf(1.f, k_hi - 22), inv_s = ldexpf(1.f, 22 - k_hi);
+  float t = fmaf(v, s, 0.5f);
+  t = fminf(fmaxf(t, 0.f), 1.f);
+  if (!(t == t)) t = 0.f;
+  const float u = t + 3.0f;
+  int32_t ui;
+  memcpy(&ui, &u, 4);
+  *hi += ui - 0x40600000;
+  const float rem = v - (u - 3.5f) * inv_s;
   *lo += to_fix(rem, k_lo);
 }
 

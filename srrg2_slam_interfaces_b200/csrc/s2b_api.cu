@@ -208,14 +208,14 @@ int cub_sort_pairs(srrg2b_ctx* c, int n, int end_bit) {
   return SRRG2B_OK;
 }
 
-// 64-bit (cell, x) keys of the fixed index
-int cub_sort_pairs64(srrg2b_ctx* c, int n, int end_bit) {
+// 64-bit (cell, x) keys of the fixed index, sorted on bits [begin_bit, end_bit)
+int cub_sort_pairs64(srrg2b_ctx* c, int n, int begin_bit, int end_bit) {
   size_t bytes = 0;
-  CK(c, cub::DeviceRadixSort::SortPairs(nullptr, bytes, c->keys64_a.p, c->keys64_b.p, c->vals_a.p, c->vals_b.p, n, 0,
-                                        end_bit, c->stream));
+  CK(c, cub::DeviceRadixSort::SortPairs(nullptr, bytes, c->keys64_a.p, c->keys64_b.p, c->vals_a.p, c->vals_b.p, n,
+                                        begin_bit, end_bit, c->stream));
   CK(c, c->cub_tmp.ensure(bytes));
   CK(c, cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, bytes, c->keys64_a.p, c->keys64_b.p, c->vals_a.p, c->vals_b.p, n,
-                                        0, end_bit, c->stream));
+                                        begin_bit, end_bit, c->stream));
   return SRRG2B_OK;
 }
 
@@ -407,7 +407,8 @@ int ensure_index(srrg2b_ctx* c, SliceData& sd, float max_distance) {
       {  // invalid points carry all-ones keys and need the full width to sort last
         int cell_bits = 1;
         while (((int64_t) 1 << cell_bits) < (int64_t) sd.nx * sd.ny * sd.nz) ++cell_bits;
-        rcode = cub_sort_pairs64(c, n, rc.has_valid ? 64 : 32 + cell_bits);
+        // the x order inside a cell only matters to the tiled search
+        rcode = cub_sort_pairs64(c, n, c->use_tile ? 0 : 32, rc.has_valid ? 64 : 32 + cell_bits);
       }
       if (rcode) return rcode;
     }
@@ -564,10 +565,8 @@ int fill_slice_args(srrg2b_ctx* c, SliceData& sd, int state_slot, const srrg2b_f
   a.gate = (normals && fp.normal_cos > -1.f) ? 1 : 0;
   a.rob = fa.robustifier; a.tau = fa.chi_threshold; a.ip = fa.info_point; a.in_ = fa.info_normal;
   a.rs = (c->dim == 3 && variable == SRRG2B_VAR_SE3_QUAT_RIGHT) ? 2.f : 1.f;
-  for (int k = 0; k < kKCount; ++k) {
-    a.fM[k] = ldexpf(1.5f, 23 - sc.k[k]);
-    a.fB[k] = ldexpf(1.f, 21 - sc.k[k]);
-  }
+  for (int k = 0; k < kKCount; ++k) a.fS[k] = ldexpf(1.f, sc.k[k] - 22);
+  a.fSinvChi = ldexpf(1.f, 22 - sc.k[kKChi]);
   a.S = c->d_state->S[state_slot].m;
   a.c_fpos = sd.c_fpos.p;
   a.gate_in_nn = 0;
@@ -1200,10 +1199,8 @@ int srrg2b_linearize(srrg2b_ctx* c, int slice_id, const float* S, int variable, 
   if (rcode) return rcode;
   a.gate = 0;  // the correspondences are taken as they are (gated by the finder or supplied by the caller)
   sc = choose_scales(sd.moving_raw.n_global, sd.coord_bound, fp->max_distance, fa->info_point, fa->info_normal);
-  for (int k = 0; k < kKCount; ++k) {
-    a.fM[k] = ldexpf(1.5f, 23 - sc.k[k]);
-    a.fB[k] = ldexpf(1.f, 21 - sc.k[k]);
-  }
+  for (int k = 0; k < kKCount; ++k) a.fS[k] = ldexpf(1.f, sc.k[k] - 22);
+  a.fSinvChi = ldexpf(1.f, 22 - sc.k[kKChi]);
   Mat4f S4;
   embed(c->dim, S, S4);
   set_S_kernel<<<1, 32, 0, c->stream>>>(c->d_state, 0, S4, 0);

@@ -86,7 +86,8 @@ struct SliceArgs {
   int gate_in_nn;  // 1: the NN kernels gate and write responses (stand-alone find); 0: linearise gates
   int rob;
   float tau, ip, in_, rs;
-  float fM[kKCount], fB[kKCount];  // magic constant 1.5 * 2^(23-k) and clamp 2^(21-k) per class
+  float fS[kKCount];  // 2^(k-22) per class: scale of the saturating fixed-point conversion (to_raw)
+  float fSinvChi;     // 2^(22-k) of the coarse chi word
   const float* S;
   int* c_fpos;
   int* far_list;   // phase-2 worklist of the NN search (query positions) and its counter
@@ -197,8 +198,9 @@ __device__ __forceinline__ float axis_gap(int d, float fr) {
 }
 
 // fixed cloud: key = (linear cell id (x fastest) << 32) | order-preserving bits of x, invalid points
-// -> all ones.  Sorting by it leaves every run of consecutive cells of a grid row sorted by x, which is
-// what lets the row scans stop as soon as |x - q_x| alone exceeds the pruning radius.
+// -> all ones.  Sorting by the high word gives the cell order; sorting by the whole key (only when the
+// tiled search is enabled) also leaves every run of consecutive cells of a grid row sorted by x, which
+// lets nn_scan_staged stop as soon as |x - q_x| alone exceeds the pruning radius.
 __global__ void cell_key_kernel(const float* __restrict__ xyz, const unsigned char* __restrict__ valid, int n,
                                 int dim, float ox, float oy, float oz, float inv, int nx, int ny, int nz,
                                 unsigned long long* __restrict__ keys, int* __restrict__ vals) {
@@ -442,53 +444,6 @@ __device__ __forceinline__ void nn_consider(const SliceArgs& a, NNQuery& q, int 
   nn_consider_pt<DIM, TRACK2>(q, p, __ldg(a.fp + p));
 }
 
-// Candidates [ps, pe) of one run of consecutive cells xa..xb of a grid row are sorted by x.  Start at
-// the position the query's x interpolates to and walk outwards in both directions; a direction ends
-// as soon as (x - q_x)^2 alone exceeds the pruning radius, because every point further along is at
-// least that far away (fl(dx^2) <= the computed d^2: adding non-negative terms is monotone in fp32).
-// Exact for ANY starting position -- a bad guess only costs extra steps.  LOAD(p) fetches candidate p.
-template <int DIM, bool TRACK2, int WIDE, class Load>
-__device__ __forceinline__ void nn_scan_run(NNQuery& q, int ps, int pe, int xa, int xb, Load load) {
-  const int n = pe - ps;
-  if (n <= 0) return;
-  const float frac = __fdividef(q.cfx - (float) xa, (float) (xb - xa + 1));
-  const int g = ps + min(max((int) (frac * (float) n), 0), n - 1);
-  // right: g, g + 1, ...
-#pragma unroll 1
-  for (int p = g; p < pe; p += WIDE) {
-    float4 c[WIDE];
-#pragma unroll
-    for (int j = 0; j < WIDE; ++j) c[j] = load(min(p + j, pe - 1));
-    bool stop = false;
-#pragma unroll
-    for (int j = 0; j < WIDE; ++j) {
-      if (p + j < pe && !stop) {
-        const float ex = c[j].x - q.qx;
-        if (ex > 0.f && ex * ex > (TRACK2 ? q.sd2 : q.bd2)) stop = true;
-        else nn_consider_pt<DIM, TRACK2>(q, p + j, c[j]);
-      }
-    }
-    if (stop) break;
-  }
-  // left: g - 1, g - 2, ...
-#pragma unroll 1
-  for (int p = g - 1; p >= ps; p -= WIDE) {
-    float4 c[WIDE];
-#pragma unroll
-    for (int j = 0; j < WIDE; ++j) c[j] = load(max(p - j, ps));
-    bool stop = false;
-#pragma unroll
-    for (int j = 0; j < WIDE; ++j) {
-      if (p - j >= ps && !stop) {
-        const float ex = q.qx - c[j].x;
-        if (ex > 0.f && ex * ex > (TRACK2 ? q.sd2 : q.bd2)) stop = true;
-        else nn_consider_pt<DIM, TRACK2>(q, p - j, c[j]);
-      }
-    }
-    if (stop) break;
-  }
-}
-
 // scan the part of cell row (y, z) that can still matter, given the conservative squared distance
 // lb2 between the query and the row's y/z slab.  Pruning radius: bd2 (nearest only) or sd2 (two
 // nearest, needed to certify a bound).
@@ -502,11 +457,8 @@ __device__ __forceinline__ void nn_scan_row(const SliceArgs& a, NNQuery& q, int 
   const int row = (z * a.ny + y) * a.nx;
   const int ps = __ldg(a.cell_start + row + xa);
   const int pe = __ldg(a.cell_start + row + xb + 1);
-  // several loads in flight per step (the compare chain is serial, the loads are not)
-#if S2B_XSCAN
-  const float4* fp = a.fp;
-  nn_scan_run<DIM, TRACK2, 4>(q, ps, pe, xa, xb, [fp](int p) { return __ldg(fp + p); });
-#else
+  // candidates in ascending position, four loads in flight per step (the compare chain is serial,
+  // the loads are not): out-of-range slots re-read the last point and are not considered
   const int last = pe - 1;
 #pragma unroll 1
   for (int p = ps; p < pe; p += 4) {
@@ -519,7 +471,6 @@ __device__ __forceinline__ void nn_scan_row(const SliceArgs& a, NNQuery& q, int 
     if (p + 2 < pe) nn_consider_pt<DIM, TRACK2>(q, p + 2, c2);
     if (p + 3 < pe) nn_consider_pt<DIM, TRACK2>(q, p + 3, c3);
   }
-#endif
 }
 
 template <int DIM>
@@ -696,9 +647,6 @@ struct TileSmem {
   unsigned long long bar;  // mbarrier of the bulk copies (TMA variant)
 };
 
-#ifndef S2B_XSCAN
-#define S2B_XSCAN 1  // global-memory row scans use the x order of the runs (0: plain 4-wide scan of the whole run)
-#endif
 #ifndef S2B_TILE_STATS
 #define S2B_TILE_STATS 0  // 1: per-run counters of the tiled search in a.tile_stats (experiments only)
 #endif
@@ -1249,18 +1197,21 @@ __global__ void commit_S_kernel(const float* S, float* S_lb) {
   if (threadIdx.x < 16 && blockIdx.x == 0) S_lb[threadIdx.x] = S[threadIdx.x];
 }
 
-// round(v * 2^k) for |v| <= B = 2^(21-k) (clamped): adding M = 1.5 * 2^(23-k) leaves the rounded integer
-// (ties to even) in the low mantissa bits -- two full-rate instructions instead of fp64 conversions
-__device__ __forceinline__ int to_fixed(float v, float M, float B) {
-  v = fminf(fmaxf(v, -B), B);
-  return __float_as_int(v + M) - __float_as_int(M);
+// Fixed-point conversion of one term, k fractional bits, |v| <= B = 2^(21-k):
+//   t = sat(v * 2^(k-22) + 0.5)   one FFMA.SAT: maps [-B, B] onto [0, 1] and clamps everything else
+//   u = t + 3.0                   in [3, 4] the fp32 spacing is 2^-22, i.e. one unit of 2^-k of v
+// so bits(u) - bits(3.5f) is the term in units of 2^-k (t is rounded to a quarter unit or finer, then u
+// to the unit, ties to even: the oracle performs the same two fp32 operations).  The accumulators add the
+// RAW bit patterns -- integer addition wraps modulo 2^32 -- and lin_flush subtracts count * bits(3.5f).
+constexpr int kFixBias = 0x40600000;  // bit pattern of 3.5f
+__device__ __forceinline__ int to_raw(float v, float s) {
+  return __float_as_int(__saturatef(fmaf(v, s, 0.5f)) + 3.0f);
 }
 // chi as (coarse, residual): the residual of the coarse rounding is exact in fp32
-__device__ __forceinline__ void to_fixed2(float v, float M, float B, float Mlo, float Blo, int& hi, int& lo) {
-  v = fminf(fmaxf(v, -B), B);
-  const float t = v + M;
-  hi += __float_as_int(t) - __float_as_int(M);
-  lo += to_fixed(v - (t - M), Mlo, Blo);
+__device__ __forceinline__ void to_raw2(float v, float s, float inv_s, float s_lo, int& hi, int& lo) {
+  const float u = __saturatef(fmaf(v, s, 0.5f)) + 3.0f;
+  hi += __float_as_int(u);
+  lo += to_raw(v - (u - 3.5f) * inv_s, s_lo);
 }
 
 // robustifier on chi (threshold tau): weight, robustified chi, kernelized flag
@@ -1409,8 +1360,8 @@ __device__ __forceinline__ void lin_one(const SliceArgs& a, const float* Ss, int
   }
   float w, rho;
   const bool kern = robustify(a.rob, a.tau, chi, w, rho);
-  if (kern) { ++A.n_out; to_fixed2(rho, a.fM[kKChi], a.fB[kKChi], a.fM[kKChiLo], a.fB[kKChiLo], A.chi_out, A.chi_out_lo); }
-  else { ++A.n_in; to_fixed2(chi, a.fM[kKChi], a.fB[kKChi], a.fM[kKChiLo], a.fB[kKChiLo], A.chi_in, A.chi_in_lo); }
+  if (kern) { ++A.n_out; to_raw2(rho, a.fS[kKChi], a.fSinvChi, a.fS[kKChiLo], A.chi_out, A.chi_out_lo); }
+  else { ++A.n_in; to_raw2(chi, a.fS[kKChi], a.fSinvChi, a.fS[kKChiLo], A.chi_in, A.chi_in_lo); }
   if (a.c_stat) a.c_stat[i] = kern ? SRRG2B_STAT_KERNELIZED : SRRG2B_STAT_INLIER;
   // ---- H += J^T (w Om) J, b += J^T (w Om) e; structural zeros of the normal rows skipped ----
   constexpr int TR = (FACTOR == SRRG2B_FACTOR_P2P) ? 0 : DIM;  // columns < TR are zero in rows >= 1
@@ -1433,7 +1384,7 @@ __device__ __forceinline__ void lin_one(const SliceArgs& a, const float* Ss, int
       }
       constexpr int T = DIM;  // columns < T: translation part of the perturbation
       const int cls = (jj < T) ? kKHtt : ((ii < T) ? kKHtr : kKHrr);
-      A.aH[hslot++] += to_fixed(h, a.fM[cls], a.fB[cls]);
+      A.aH[hslot++] += to_raw(h, a.fS[cls]);
     }
   }
 #pragma unroll
@@ -1443,7 +1394,7 @@ __device__ __forceinline__ void lin_one(const SliceArgs& a, const float* Ss, int
 #pragma unroll
       for (int r = 1; r < E; ++r) g = fmaf(u[r][ii], e[r], g);
     }
-    A.ab[ii] += to_fixed(g, a.fM[ii < DIM ? kKBt : kKBr], a.fB[ii < DIM ? kKBt : kKBr]);
+    A.ab[ii] += to_raw(g, a.fS[ii < DIM ? kKBt : kKBr]);
   }
 }
 
@@ -1467,19 +1418,21 @@ __device__ __forceinline__ void lin_flush(const SliceArgs& a, const LinAcc<DIM>&
     return ((long long) hi << 16) + (long long) lo;
   };
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // the accumulators hold raw bit patterns (see to_raw): take out count * bits(3.5f), modulo 2^32
+  const int bias_in = A.n_in * kFixBias, bias_out = A.n_out * kFixBias, bias_all = bias_in + bias_out;
   long long mine0 = 0, mine1 = 0;  // lane l keeps slot l and slot 32 + l
 #pragma unroll
   for (int k = 0; k < NH; ++k) {
-    const long long v = wsum(A.aH[k]);
+    const long long v = wsum(A.aH[k] - bias_all);
     if (lane == k) mine0 = v;
   }
 #pragma unroll
   for (int k = 0; k < P; ++k) {
-    const long long v = wsum(A.ab[k]);
+    const long long v = wsum(A.ab[k] - bias_all);
     if (lane == kAccB + k) mine0 = v;
   }
   {
-    const int cv[4] = {A.chi_in, A.chi_in_lo, A.chi_out, A.chi_out_lo};
+    const int cv[4] = {A.chi_in - bias_in, A.chi_in_lo - bias_in, A.chi_out - bias_out, A.chi_out_lo - bias_out};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const long long v = wsum(cv[k]);
