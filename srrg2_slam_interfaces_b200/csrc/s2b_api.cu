@@ -150,6 +150,7 @@ struct srrg2b_ctx {
   };
   std::vector<RunGraph> run_graphs;
   bool use_graphs = true;  // env SRRG2B_NO_GRAPH=1 disables
+  bool graph_nccl = false;  // env SRRG2B_GRAPH_NCCL=1: capture the all-reduce too (experimental: failed the 2-GPU parity test)
   unsigned long long* d_tile_stats = nullptr;  // experiments (S2B_TILE_STATS builds)
   bool use_tile = false;   // env SRRG2B_TILE=1: "all" mode searches run tiled out of shared memory (nn_tile_kernel)
   s2b::Mat4f* d_T0 = nullptr;  // initial guess of the current run (read by icp_init_kernel)
@@ -828,7 +829,8 @@ int run_plan(srrg2b_ctx* c, const Plan& plan, const Mat4f& T0, int iterations, i
   *c->h_solve = plan.solve;
   CK(c, cudaMemcpyAsync(c->d_T0, c->h_T0, sizeof(Mat4f), cudaMemcpyHostToDevice, c->stream));
   CK(c, cudaMemcpyAsync(c->d_solve, c->h_solve, sizeof(SolveArgs), cudaMemcpyHostToDevice, c->stream));
-  const bool graph = c->use_graphs && !c->time_kernels && c->world <= 1;
+  // (with an NCCL communicator attached the iterations are stream launches unless SRRG2B_GRAPH_NCCL=1)
+  const bool graph = c->use_graphs && !c->time_kernels && (c->world <= 1 || c->graph_nccl);
   if (!graph) {
     icp_init_kernel<<<1, 32, 0, c->stream>>>(c->d_solve, c->d_state, c->d_T0, apply_prior_guess, reset_tc, keep_stats);
     c->launches++;
@@ -984,6 +986,7 @@ int srrg2b_ctx_create(int dim, int device, srrg2b_ctx** out) {
   ok = ok && cudaMallocHost((void**) &c->h_solve, sizeof(SolveArgs)) == cudaSuccess;
   if (const char* env = getenv("SRRG2B_NO_GRAPH")) c->use_graphs = atoi(env) == 0;
   if (const char* env = getenv("SRRG2B_TILE")) c->use_tile = atoi(env) != 0;
+  if (const char* env = getenv("SRRG2B_GRAPH_NCCL")) c->graph_nccl = atoi(env) != 0;
   {
     const void* lin[] = {(const void*) linearize_kernel<3, SRRG2B_FACTOR_P2P, true>, (const void*) linearize_kernel<3, SRRG2B_FACTOR_P2P, false>,
                          (const void*) linearize_kernel<3, SRRG2B_FACTOR_PLANE, true>, (const void*) linearize_kernel<3, SRRG2B_FACTOR_PLANE, false>,
