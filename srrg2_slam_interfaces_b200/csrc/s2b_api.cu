@@ -87,6 +87,7 @@ struct SliceData {
   float ox = 0, oy = 0, oz = 0, inv_cell = 1;
   int nx = 1, ny = 1, nz = 1;
   int R = 1;  // cells per max_distance
+  int xbits = 0;  // low key bits of the cell-order sort: x inside the cell (cell_key_kernel)
   // projective index (alternative to the grid): index image + SoA in original order
   bool index_is_projective = false;
   srrg2b_finder_params proj_params = {};
@@ -118,7 +119,6 @@ struct srrg2b_ctx {
   DevState* h_state = nullptr;  // pinned mirror (header part is copied back)
   // scratch
   DevBuf<unsigned> keys_a, keys_b;
-  DevBuf<unsigned long long> keys64_a, keys64_b;
   DevBuf<int> vals_a, vals_b, flags, positions, bounds;
   DevBuf<unsigned char> cub_tmp;
   DevBuf<int> o_fidx, o_midx, d_fidx;
@@ -206,17 +206,6 @@ int cub_sort_pairs(srrg2b_ctx* c, int n, int end_bit) {
   CK(c, c->cub_tmp.ensure(bytes));
   CK(c, cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, bytes, c->keys_a.p, c->keys_b.p, c->vals_a.p, c->vals_b.p, n, 0,
                                         end_bit, c->stream));
-  return SRRG2B_OK;
-}
-
-// 64-bit (cell, x) keys of the fixed index, sorted on bits [begin_bit, end_bit)
-int cub_sort_pairs64(srrg2b_ctx* c, int n, int begin_bit, int end_bit) {
-  size_t bytes = 0;
-  CK(c, cub::DeviceRadixSort::SortPairs(nullptr, bytes, c->keys64_a.p, c->keys64_b.p, c->vals_a.p, c->vals_b.p, n,
-                                        begin_bit, end_bit, c->stream));
-  CK(c, c->cub_tmp.ensure(bytes));
-  CK(c, cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, bytes, c->keys64_a.p, c->keys64_b.p, c->vals_a.p, c->vals_b.p, n,
-                                        begin_bit, end_bit, c->stream));
   return SRRG2B_OK;
 }
 
@@ -356,8 +345,8 @@ int ensure_index(srrg2b_ctx* c, SliceData& sd, float max_distance) {
   CK(c, sd.f_nrm.ensure((size_t) n + 1));
   CK(c, sd.f_inverse.ensure((size_t) n + 1));
   if (n > 0) {
-    CK(c, c->keys64_a.ensure(n));
-    CK(c, c->keys64_b.ensure(n));
+    CK(c, c->keys_a.ensure(n));
+    CK(c, c->keys_b.ensure(n));
     CK(c, c->vals_a.ensure(n));
     CK(c, c->vals_b.ensure(n));
   }
@@ -400,23 +389,23 @@ int ensure_index(srrg2b_ctx* c, SliceData& sd, float max_distance) {
     sd.inv_cell = 1.f / cell;
     sd.nx = dims[0]; sd.ny = dims[1]; sd.nz = dims[2];
     sd.R = R;
+    {  // the key bits the cell id leaves free order the points of a cell by x (at most 16 bits)
+      int cell_bits = 1;
+      while (((int64_t) 1 << cell_bits) < (int64_t) sd.nx * sd.ny * sd.nz) ++cell_bits;
+      sd.xbits = std::max(0, std::min(16, 32 - cell_bits));
+    }
     if (n > 0) {
       cell_key_kernel<<<blocks_for(n, 256), 256, 0, c->stream>>>(rc.xyz.p, rc.has_valid ? rc.valid.p : nullptr, n,
                                                                  dim, sd.ox, sd.oy, sd.oz, sd.inv_cell, sd.nx, sd.ny,
-                                                                 sd.nz, c->keys64_a.p, c->vals_a.p);
+                                                                 sd.nz, sd.xbits, c->keys_a.p, c->vals_a.p);
       c->launches++;
-      {  // invalid points carry all-ones keys and need the full width to sort last
-        int cell_bits = 1;
-        while (((int64_t) 1 << cell_bits) < (int64_t) sd.nx * sd.ny * sd.nz) ++cell_bits;
-        // the x order inside a cell only matters to the tiled search
-        rcode = cub_sort_pairs64(c, n, c->use_tile ? 0 : 32, rc.has_valid ? 64 : 32 + cell_bits);
-      }
+      rcode = cub_sort_pairs(c, n, 32);
       if (rcode) return rcode;
     }
     if (R == 1 || forced || sd.nf_valid == 0) break;
     CK(c, cudaMemsetAsync(c->bounds.p, 0, 4, c->stream));
     count_distinct_kernel<<<std::min(blocks_for(sd.nf_valid, 256), c->sm_count * 8), 256, 0, c->stream>>>(
-      c->keys64_b.p, sd.nf_valid, c->bounds.p);
+      c->keys_b.p, sd.nf_valid, sd.xbits, c->bounds.p);
     c->launches++;
     CK(c, cudaMemcpyAsync(c->h_bounds, c->bounds.p, 4, cudaMemcpyDeviceToHost, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
@@ -443,7 +432,7 @@ int ensure_index(srrg2b_ctx* c, SliceData& sd, float max_distance) {
     fill_int_kernel<<<blocks_for(ncells + 1, 256), 256, 0, c->stream>>>(c->vals_a.p, ncells + 1, sd.nf_valid);
     c->launches++;
     if (sd.nf_valid > 0) {
-      cell_head_kernel<<<blocks_for(sd.nf_valid, 256), 256, 0, c->stream>>>(c->keys64_b.p, sd.nf_valid, c->vals_a.p);
+      cell_head_kernel<<<blocks_for(sd.nf_valid, 256), 256, 0, c->stream>>>(c->keys_b.p, sd.nf_valid, sd.xbits, c->vals_a.p);
       c->launches++;
     }
     auto rin = thrust::make_reverse_iterator(c->vals_a.p + ncells + 1);
@@ -582,6 +571,7 @@ int fill_slice_args(srrg2b_ctx* c, SliceData& sd, int state_slot, const srrg2b_f
   a.width = fp.width; a.height = fp.height; a.image = sd.image.p;
   a.c_lb = sd.c_lb.p; a.S_lb = sd.S_lb.p;
   a.track2 = &c->d_state->track2[state_slot];
+  a.xq_slack = sd.index_is_projective ? 0.f : (1.01f * ldexpf(1.f, -sd.xbits) + 1e-4f) / sd.inv_cell;  // one key quantum + fp32 rounding of the cell coordinate
   {
     const float rho = ((float) sd.R - 4e-3f) / sd.inv_cell;
     a.rho_s2 = rho * rho;
@@ -1037,7 +1027,7 @@ int srrg2b_ctx_destroy(srrg2b_ctx* c) {
     s.m_pts.release(); s.m_nrm.release(); s.m_inverse.release();
     s.image.release(); s.c_lb.release(); s.S_lb.release(); s.c_fidx.release(); s.c_fpos.release(); s.far_list.release(); s.far_count.release(); s.work_list.release(); s.c_resp.release(); s.c_chi.release(); s.c_stat.release();
   }
-  c->keys_a.release(); c->keys_b.release(); c->keys64_a.release(); c->keys64_b.release(); c->vals_a.release(); c->vals_b.release();
+  c->keys_a.release(); c->keys_b.release(); c->vals_a.release(); c->vals_b.release();
   c->flags.release(); c->positions.release(); c->bounds.release(); c->cub_tmp.release();
   c->o_fidx.release(); c->o_midx.release(); c->d_fidx.release(); c->o_resp.release(); c->d_resp.release();
   c->o_chi.release(); c->d_chi.release(); c->o_stat.release(); c->d_stat.release();

@@ -104,6 +104,7 @@ struct SliceArgs {
   const float* S_lb;   // transform the bounds are valid for
   const int* track2;   // device flag: searches track the second neighbour (certify bounds)
   float rho_s2;        // squared radius the (2R+1) cell neighbourhood is guaranteed to cover
+  float xq_slack;      // x quantum of the cell-order sort (see cell_key_kernel), with rounding slack
   // projective finder (srrg2_proslam cue): pinhole + index image of the fixed cloud
   int projective;
   float fx, fy, pcx, pcy, min_depth, max_depth;
@@ -197,27 +198,32 @@ __device__ __forceinline__ float axis_gap(int d, float fr) {
   return fmaxf(g - 2e-3f, 0.f);
 }
 
-// fixed cloud: key = (linear cell id (x fastest) << 32) | order-preserving bits of x, invalid points
-// -> all ones.  Sorting by the high word gives the cell order; sorting by the whole key (only when the
-// tiled search is enabled) also leaves every run of consecutive cells of a grid row sorted by x, which
-// lets nn_scan_staged stop as soon as |x - q_x| alone exceeds the pruning radius.
+// fixed cloud: key = (linear cell id (x fastest) << xbits) | position of x inside its cell quantised to
+// xbits bits; invalid points -> all ones.  One 32-bit sort then leaves every run of consecutive cells
+// of a grid row ordered by x up to one quantum (cell / 2^xbits), which lets the row scans jump to the
+// query's x and stop as soon as |x - q_x| alone exceeds the pruning radius (plus that quantum).
 __global__ void cell_key_kernel(const float* __restrict__ xyz, const unsigned char* __restrict__ valid, int n,
-                                int dim, float ox, float oy, float oz, float inv, int nx, int ny, int nz,
-                                unsigned long long* __restrict__ keys, int* __restrict__ vals) {
+                                int dim, float ox, float oy, float oz, float inv, int nx, int ny, int nz, int xbits,
+                                unsigned* __restrict__ keys, int* __restrict__ vals) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   vals[i] = i;
   if (valid && !valid[i]) {
-    keys[i] = ~0ull;
+    keys[i] = 0xffffffffu;
     return;
   }
   const float x = xyz[(size_t) i * dim], y = xyz[(size_t) i * dim + 1];
   const float z = dim == 3 ? xyz[(size_t) i * dim + 2] : 0.f;
-  int cx = min(max(cell_coord(x, ox, inv, nx), 0), nx - 1);
+  const float cfx = cell_coord_f(x, ox, inv, nx);
+  int cx = min(max((int) floorf(cfx), 0), nx - 1);
   int cy = min(max(cell_coord(y, oy, inv, ny), 0), ny - 1);
   int cz = min(max(cell_coord(z, oz, inv, nz), 0), nz - 1);
-  const unsigned xbits = (unsigned) f2ord(x + 0.f) ^ 0x80000000u;  // (+0.f: -0 sorts as +0)
-  keys[i] = ((unsigned long long) (unsigned) ((cz * ny + cy) * nx + cx) << 32) | xbits;
+  const float frac = fminf(fmaxf(cfx - (float) cx, 0.f), 1.f);
+  const unsigned qmax = (1u << xbits) - 1u;
+  unsigned xq = min((unsigned) (frac * (float) (1u << xbits)), qmax);
+  unsigned key = ((unsigned) ((cz * ny + cy) * nx + cx) << xbits) | xq;
+  if (key == 0xffffffffu) key = 0xfffffffeu;  // all ones is reserved for invalid points
+  keys[i] = key;
 }
 
 __device__ __forceinline__ unsigned spread3(unsigned v) {  // 10 bits -> every third bit
@@ -322,18 +328,18 @@ __global__ void gather_kernel(const float* __restrict__ xyz, const float* __rest
 // cell_start[c] = first sorted position whose cell id >= c (lower bound), c in [0, ncells]:
 // cell_head_kernel writes the first position of every occupied cell into a table preset to n_valid,
 // a reverse running minimum (host: cub::DeviceScan over reverse iterators) fills the empty cells.
-__global__ void cell_head_kernel(const unsigned long long* __restrict__ keys, int n_valid, int* __restrict__ head) {
+__global__ void cell_head_kernel(const unsigned* __restrict__ keys, int n_valid, int xbits, int* __restrict__ head) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_valid) return;
-  const unsigned c = (unsigned) (keys[i] >> 32);
-  if (i == 0 || (unsigned) (keys[i - 1] >> 32) != c) head[c] = i;
+  const unsigned c = keys[i] >> xbits;
+  if (i == 0 || (keys[i - 1] >> xbits) != c) head[c] = i;
 }
 
 // number of distinct keys among the first n sorted keys (= occupied cells)
-__global__ void count_distinct_kernel(const unsigned long long* __restrict__ keys, int n, int* __restrict__ out) {
+__global__ void count_distinct_kernel(const unsigned* __restrict__ keys, int n, int xbits, int* __restrict__ out) {
   int c = 0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-    c += (i == 0 || (keys[i] >> 32) != (keys[i - 1] >> 32)) ? 1 : 0;
+    c += (i == 0 || (keys[i] >> xbits) != (keys[i - 1] >> xbits)) ? 1 : 0;
   c = __reduce_add_sync(0xffffffffu, c);
   if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
 }
@@ -458,7 +464,10 @@ __device__ __forceinline__ void nn_scan_row(const SliceArgs& a, NNQuery& q, int 
   const int ps = __ldg(a.cell_start + row + xa);
   const int pe = __ldg(a.cell_start + row + xb + 1);
   // candidates in ascending position, four loads in flight per step (the compare chain is serial,
-  // the loads are not): out-of-range slots re-read the last point and are not considered
+  // the loads are not): out-of-range slots re-read the last point and are not considered.
+  // (Measured: using the x order of the run here -- a 4-ary search for the query's x, then a windowed
+  // walk -- examines 4x fewer candidates but is 20-35% SLOWER: the search adds dependent L2 round trips
+  // to a walk whose loads are otherwise all independent.  The x order pays off in shared memory only.)
   const int last = pe - 1;
 #pragma unroll 1
   for (int p = ps; p < pe; p += 4) {
@@ -681,10 +690,11 @@ __device__ __forceinline__ void nn_search_global(const SliceArgs& a, NNQuery& q,
   }
 }
 
-// one staged row run: candidates [ps, pe) sorted by x in shared memory.  Binary search for the
-// query's x, then outwards in both directions until |x - q_x| alone exceeds the pruning radius.
+// one staged row run: candidates [ps, pe) ordered by x (up to one quantum) in shared memory.  Binary
+// search for the query's x, then outwards in both directions until |x - q_x| alone exceeds the pruning
+// radius (plus the quantum).
 template <int DIM, bool TRACK2>
-__device__ __forceinline__ void nn_scan_staged(NNQuery& q, const float4* pr, int ps, int pe) {
+__device__ __forceinline__ void nn_scan_staged(NNQuery& q, const float4* pr, int ps, int pe, float slack) {
   int lo = ps, hi = pe;
   while (lo < hi) {
     const int mid = (lo + hi) >> 1;
@@ -693,15 +703,15 @@ __device__ __forceinline__ void nn_scan_staged(NNQuery& q, const float4* pr, int
 #pragma unroll 1
   for (int p = lo; p < pe; ++p) {
     const float4 c = pr[p];
-    const float ex = c.x - q.qx;
-    if (ex * ex > (TRACK2 ? q.sd2 : q.bd2)) break;
+    const float ex = (c.x - q.qx) - slack;
+    if (ex > 0.f && ex * ex > (TRACK2 ? q.sd2 : q.bd2)) break;
     nn_consider_pt<DIM, TRACK2>(q, p, c);
   }
 #pragma unroll 1
   for (int p = lo - 1; p >= ps; --p) {
     const float4 c = pr[p];
-    const float ex = q.qx - c.x;
-    if (ex * ex > (TRACK2 ? q.sd2 : q.bd2)) break;
+    const float ex = (q.qx - c.x) - slack;
+    if (ex > 0.f && ex * ex > (TRACK2 ? q.sd2 : q.bd2)) break;
     nn_consider_pt<DIM, TRACK2>(q, p, c);
   }
 }
@@ -903,7 +913,7 @@ __device__ __forceinline__ void nn_tile_body(const SliceArgs& a, TileSmem& sm, f
         if (xa > xb) return;
         const int r = (z - z0) * by + (y - y0);
         const int* csr = sm.cs + r * bx1 - x0;
-        nn_scan_staged<DIM, TRACK2>(q, sm.pts + sm.rdelta[r], csr[xa], csr[xb + 1]);
+        nn_scan_staged<DIM, TRACK2>(q, sm.pts + sm.rdelta[r], csr[xa], csr[xb + 1], a.xq_slack);
       };
       // centre row first: it usually shrinks the pruning radius to a fraction of a cell ...
       if (q.cy >= 0 && q.cy < a.ny && q.cz >= 0 && q.cz < a.nz) scan_row(q.cy, q.cz, 0.f);
@@ -1572,18 +1582,24 @@ __global__ void __launch_bounds__(kLinThreads, kLinCtas) linearize_kernel(const 
     const int i = index_of(w + d * stride);
     issue(d, i, i >= 0 ? a.c_fpos[i] : -1, (CHECK && i >= 0) ? a.c_lb[i] : 0.f);
   }
-  int i_b = index_of(w + (D - 1) * stride);  // next element to issue: index, slot, bound in registers
+  // index, slot and bound of the next two elements to issue travel in registers (two iterations of
+  // lead: one is not enough to cover a DRAM round trip under load), the index of the third one too
+  int i_b = index_of(w + (D - 1) * stride);
   int slot_b = i_b >= 0 ? a.c_fpos[i_b] : -1;
   float lb_b = (CHECK && i_b >= 0) ? a.c_lb[i_b] : 0.f;
-  int i_a = index_of(w + D * stride);        // the one after: index only
+  int i_c = index_of(w + D * stride);
+  int slot_c = i_c >= 0 ? a.c_fpos[i_c] : -1;
+  float lb_c = (CHECK && i_c >= 0) ? a.c_lb[i_c] : 0.f;
+  int i_a = index_of(w + (D + 1) * stride);
   int st = 0;                                // ring stage of the element processed now
   for (; w < n_work; w += stride) {
     // refill the stage freed by the previous iteration, advance the register part of the pipeline
     issue(st == 0 ? D - 1 : st - 1, i_b, slot_b, lb_b);
-    i_b = i_a;
-    slot_b = i_b >= 0 ? a.c_fpos[i_b] : -1;
-    lb_b = (CHECK && i_b >= 0) ? a.c_lb[i_b] : 0.f;
-    i_a = index_of(w + (D + 1) * stride);
+    i_b = i_c; slot_b = slot_c; lb_b = lb_c;
+    i_c = i_a;
+    slot_c = i_c >= 0 ? a.c_fpos[i_c] : -1;
+    lb_c = (CHECK && i_c >= 0) ? a.c_lb[i_c] : 0.f;
+    i_a = index_of(w + (D + 2) * stride);
     asm volatile("cp.async.wait_group %0;" ::"n"(D - 1) : "memory");  // the oldest group (this element) has landed
     const int i = ring_i[(st * 3 + 0) * kLinThreads + tid];
     const int slot = ring_i[(st * 3 + 1) * kLinThreads + tid];
