@@ -237,3 +237,32 @@ def test_prior_only_reference_kat_on_gpu(oracle, capi):
         rot, trans = syn.pose_error(g["T"].astype(np.float64) @ motion_prev.astype(np.float64), np.eye(4))
         assert rot < 1e-5 and trans < 1e-5
     ctx.close()
+
+
+def test_tiled_search_matches_oracle(monkeypatch):
+    """The optional TMA-staged tiled search (SRRG2B_TILE=1, nn_tile_kernel) must give the same run as
+    the oracle, bit for bit: cold start, warm iterations, certified-bound iteration, coherence phase."""
+    from oracle import oracle as O
+    from srrg2_slam_interfaces_b200 import capi as A
+    from srrg2_slam_interfaces_b200 import synthetic as syn
+    monkeypatch.setenv("SRRG2B_TILE", "1")
+    d = syn.make_icp3d(30000, 27001, seed=11)
+    kw = dict(max_iterations=12, min_num_inliers=10)
+    ctx = A.Context(3, 0)
+    ctx.set_cloud(A.FIXED, 0, d["fixed"], d["fixed_normals"])
+    ctx.set_cloud(A.MOVING, 0, d["moving"], d["moving_normals"])
+    g = ctx.icp_run([A.make_slice(3, 0, None, A.finder_params(0.3, 0.8),
+                                  A.factor_params(A.FACTOR_PLANE, A.ROB_HUBER, 0.01))],
+                    A.aligner_params(**kw), np.eye(4))
+    gc = ctx.get_correspondences(0, 27001)
+    ctx.close()
+    F = O.CloudRef(d["fixed"], d["fixed_normals"])
+    M = O.CloudRef(d["moving"], d["moving_normals"])
+    o = O.icp_run(3, [O.make_slice(F, M, None, O.finder_params(0.3, 0.8),
+                                   O.factor_params(O.FACTOR_PLANE, O.ROB_HUBER, 0.01))],
+                  O.aligner_params(**kw), np.eye(4))
+    assert g["status"] == o["status"]
+    assert g["stats"] == o["stats"]
+    assert np.array_equal(g["T"], o["T"])
+    assert np.array_equal(gc[0], o["correspondences"][0][0])
+    assert np.array_equal(gc[1], o["correspondences"][0][1])
