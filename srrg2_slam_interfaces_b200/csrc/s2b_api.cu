@@ -74,6 +74,9 @@ struct RawCloud {
   DevBuf<unsigned char> valid;
   int64_t n = 0, n_global = 0, index_offset = 0;
   bool has_normals = false, has_valid = false, present = false;
+  // upload progress on the copy stream: coordinates (+ validity) landed / everything landed.  The index
+  // builds start on the coordinates while the normals are still crossing PCIe.
+  cudaEvent_t ev_coords = nullptr, ev_all = nullptr;
 };
 
 struct SliceData {
@@ -88,6 +91,10 @@ struct SliceData {
   int nx = 1, ny = 1, nz = 1;
   int R = 1;  // cells per max_distance
   int xbits = 0;  // low key bits of the cell-order sort: x inside the cell (cell_key_kernel)
+  // resolution chosen by the last build (skips the occupancy read-back while the cloud size is stable)
+  int cached_R = 0, cached_R_n = 0;
+  float cached_R_md = -1.f;
+  float last_max_distance = -1.f;  // finder radius of the last NN index: set_cloud(FIXED) rebuilds for it right away
   // projective index (alternative to the grid): index image + SoA in original order
   bool index_is_projective = false;
   srrg2b_finder_params proj_params = {};
@@ -111,6 +118,7 @@ struct SliceData {
 struct srrg2b_ctx {
   int dim = 3, device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;  // cloud uploads: they overlap the index build queued on `stream`
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::string err;
   int64_t launches = 0;
@@ -152,6 +160,7 @@ struct srrg2b_ctx {
   bool use_graphs = true;  // env SRRG2B_NO_GRAPH=1 disables
   bool graph_nccl = false;  // env SRRG2B_GRAPH_NCCL=1: capture the all-reduce too (experimental: failed the 2-GPU parity test)
   unsigned long long* d_tile_stats = nullptr;  // experiments (S2B_TILE_STATS builds)
+  bool eager_index = true;  // env SRRG2B_EAGER_INDEX=0: build the NN index on first use only
   bool use_tile = false;   // env SRRG2B_TILE=1: "all" mode searches run tiled out of shared memory (nn_tile_kernel)
   s2b::Mat4f* d_T0 = nullptr;  // initial guess of the current run (read by icp_init_kernel)
   s2b::Mat4f* h_T0 = nullptr;  // pinned staging
@@ -224,6 +233,9 @@ int compute_bounds(srrg2b_ctx* c, const RawCloud& rc) {
   return SRRG2B_OK;
 }
 
+// Queues the copies of a cloud on the copy stream -- validity and coordinates first, then the normals --
+// and records the two progress events.  Does NOT wait: the caller's buffers are borrowed until the copy
+// stream (or the compute stream after it waited for ev_all) has been synchronised.
 int upload_raw(srrg2b_ctx* c, RawCloud& rc, const srrg2b_cloud* cl) {
   const int dim = c->dim;
   const cudaMemcpyKind kind = cl->on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
@@ -232,25 +244,29 @@ int upload_raw(srrg2b_ctx* c, RawCloud& rc, const srrg2b_cloud* cl) {
   rc.index_offset = cl->index_offset;
   rc.has_normals = cl->normals != nullptr;
   rc.has_valid = cl->valid != nullptr;
+  if (!rc.ev_coords) CK(c, cudaEventCreateWithFlags(&rc.ev_coords, cudaEventDisableTiming));
+  if (!rc.ev_all) CK(c, cudaEventCreateWithFlags(&rc.ev_all, cudaEventDisableTiming));
   CK(c, rc.xyz.ensure((size_t) cl->n * dim));
-  if (cl->n) CK(c, cudaMemcpyAsync(rc.xyz.p, cl->coords, sizeof(float) * cl->n * dim, kind, c->stream));
-  if (rc.has_normals) {
-    CK(c, rc.nrm.ensure((size_t) cl->n * dim));
-    if (cl->n) CK(c, cudaMemcpyAsync(rc.nrm.p, cl->normals, sizeof(float) * cl->n * dim, kind, c->stream));
-  }
+  if (rc.has_normals) CK(c, rc.nrm.ensure((size_t) cl->n * dim));
   if (rc.has_valid) {
     CK(c, rc.valid.ensure((size_t) cl->n));
-    if (cl->n) CK(c, cudaMemcpyAsync(rc.valid.p, cl->valid, cl->n, kind, c->stream));
+    if (cl->n) CK(c, cudaMemcpyAsync(rc.valid.p, cl->valid, cl->n, kind, c->copy_stream));
   }
+  if (cl->n) CK(c, cudaMemcpyAsync(rc.xyz.p, cl->coords, sizeof(float) * cl->n * dim, kind, c->copy_stream));
+  CK(c, cudaEventRecord(rc.ev_coords, c->copy_stream));
+  if (rc.has_normals && cl->n)
+    CK(c, cudaMemcpyAsync(rc.nrm.p, cl->normals, sizeof(float) * cl->n * dim, kind, c->copy_stream));
+  CK(c, cudaEventRecord(rc.ev_all, c->copy_stream));
   rc.present = true;
   return SRRG2B_OK;
 }
 
-// moving cloud: Morton order over its own bounding box, float4 SoA, inverse permutation
+// moving cloud: Hilbert order over its own bounding box, float4 SoA, inverse permutation
 int build_moving(srrg2b_ctx* c, SliceData& sd) {
   RawCloud& rc = sd.moving_raw;
   const int n = (int) rc.n, dim = c->dim;
   Trace tr(c, "build_moving");
+  if (rc.ev_coords) CK(c, cudaStreamWaitEvent(c->stream, rc.ev_coords, 0));
   int rcode = compute_bounds(c, rc);
   if (rcode) return rcode;
   tr.mark("bounds");
@@ -302,6 +318,7 @@ int build_moving(srrg2b_ctx* c, SliceData& sd) {
   fill_int_kernel<<<blocks_for(n, 256), 256, 0, c->stream>>>(sd.m_inverse.p, n, -1);
   c->launches++;
   if (sd.nm_valid > 0) {
+    if (rc.ev_all) CK(c, cudaStreamWaitEvent(c->stream, rc.ev_all, 0));
     gather_kernel<<<blocks_for(sd.nm_valid, 256), 256, 0, c->stream>>>(
       rc.xyz.p, rc.has_normals ? rc.nrm.p : nullptr, c->vals_b.p, sd.nm_valid, dim, sd.m_pts.p, sd.m_nrm.p,
       sd.m_inverse.p);
@@ -330,6 +347,7 @@ int ensure_index(srrg2b_ctx* c, SliceData& sd, float max_distance) {
   if (sd.built_for_max_distance == max_distance) return SRRG2B_OK;
   const int n = (int) rc.n, dim = c->dim;
   Trace tr(c, "ensure_index");
+  if (rc.ev_coords) CK(c, cudaStreamWaitEvent(c->stream, rc.ev_coords, 0));
   int rcode = compute_bounds(c, rc);
   if (rcode) return rcode;
   tr.mark("bounds");
@@ -357,6 +375,12 @@ int ensure_index(srrg2b_ctx* c, SliceData& sd, float max_distance) {
   int R = kMaxR;
   if (const char* env = getenv("SRRG2B_GRID_R")) R = std::max(1, std::min(kMaxR, atoi(env)));
   const bool forced = getenv("SRRG2B_GRID_R") != nullptr;
+  // same finder radius and about the same number of points as the last build of this slice: start at
+  // (and keep) its resolution; a frame-to-frame stream of scans then builds without a host round trip
+  // after the bounds
+  const bool cached = !forced && sd.cached_R > 0 && sd.cached_R_md == max_distance &&
+                      std::abs(sd.nf_valid - sd.cached_R_n) <= sd.cached_R_n / 8;
+  if (cached) R = sd.cached_R;
   int dims[3] = {1, 1, 1};
   float cell = max_distance;
   for (;; --R) {
@@ -402,7 +426,7 @@ int ensure_index(srrg2b_ctx* c, SliceData& sd, float max_distance) {
       rcode = cub_sort_pairs(c, n, 32);
       if (rcode) return rcode;
     }
-    if (R == 1 || forced || sd.nf_valid == 0) break;
+    if (R == 1 || forced || sd.nf_valid == 0 || cached) break;
     CK(c, cudaMemsetAsync(c->bounds.p, 0, 4, c->stream));
     count_distinct_kernel<<<std::min(blocks_for(sd.nf_valid, 256), c->sm_count * 8), 256, 0, c->stream>>>(
       c->keys_b.p, sd.nf_valid, sd.xbits, c->bounds.p);
@@ -419,6 +443,7 @@ int ensure_index(srrg2b_ctx* c, SliceData& sd, float max_distance) {
     fill_int_kernel<<<blocks_for(n, 256), 256, 0, c->stream>>>(sd.f_inverse.p, n, -1);
     c->launches++;
     if (sd.nf_valid > 0) {
+      if (rc.ev_all) CK(c, cudaStreamWaitEvent(c->stream, rc.ev_all, 0));
       gather_kernel<<<blocks_for(sd.nf_valid, 256), 256, 0, c->stream>>>(
         rc.xyz.p, rc.has_normals ? rc.nrm.p : nullptr, c->vals_b.p, sd.nf_valid, dim, sd.f_pts.p, sd.f_nrm.p,
         sd.f_inverse.p);
@@ -464,6 +489,8 @@ int ensure_index(srrg2b_ctx* c, SliceData& sd, float max_distance) {
   CK(c, cudaGetLastError());
   tr.mark("near bits + resets");
   sd.built_for_max_distance = max_distance;
+  sd.last_max_distance = max_distance;
+  sd.cached_R = sd.R; sd.cached_R_n = sd.nf_valid; sd.cached_R_md = max_distance;
   return SRRG2B_OK;
 }
 
@@ -487,6 +514,7 @@ int ensure_proj_index(srrg2b_ctx* c, SliceData& sd, const srrg2b_finder_params& 
   CK(c, sd.image.ensure(npx));
   CK(c, cudaMemsetAsync(sd.image.p, 0xff, npx * sizeof(unsigned long long), c->stream));
   if (n > 0) {
+    if (rc.ev_all) CK(c, cudaStreamWaitEvent(c->stream, rc.ev_all, 0));
     gather_identity_kernel<<<blocks_for(n, 256), 256, 0, c->stream>>>(rc.xyz.p, rc.has_normals ? rc.nrm.p : nullptr, n,
                                                                       c->dim, sd.f_pts.p, sd.f_nrm.p, sd.f_inverse.p);
     proj_image_kernel<<<blocks_for(n, 256), 256, 0, c->stream>>>(rc.xyz.p, rc.has_valid ? rc.valid.p : nullptr, n, fp.fx,
@@ -961,6 +989,7 @@ int srrg2b_ctx_create(int dim, int device, srrg2b_ctx** out) {
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
   bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
+  ok = ok && cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
   ok = ok && cudaEventCreate(&c->ev0) == cudaSuccess && cudaEventCreate(&c->ev1) == cudaSuccess;
   ok = ok && cudaMalloc((void**) &c->d_state, sizeof(DevState)) == cudaSuccess;
   ok = ok && cudaMallocHost((void**) &c->h_state, sizeof(DevState)) == cudaSuccess;
@@ -976,6 +1005,7 @@ int srrg2b_ctx_create(int dim, int device, srrg2b_ctx** out) {
   ok = ok && cudaMallocHost((void**) &c->h_solve, sizeof(SolveArgs)) == cudaSuccess;
   if (const char* env = getenv("SRRG2B_NO_GRAPH")) c->use_graphs = atoi(env) == 0;
   if (const char* env = getenv("SRRG2B_TILE")) c->use_tile = atoi(env) != 0;
+  if (const char* env = getenv("SRRG2B_EAGER_INDEX")) c->eager_index = atoi(env) != 0;
   if (const char* env = getenv("SRRG2B_GRAPH_NCCL")) c->graph_nccl = atoi(env) != 0;
   {
     const void* lin[] = {(const void*) linearize_kernel<3, SRRG2B_FACTOR_P2P, true>, (const void*) linearize_kernel<3, SRRG2B_FACTOR_P2P, false>,
@@ -1007,6 +1037,7 @@ int srrg2b_ctx_destroy(srrg2b_ctx* c) {
   pgo_release(c);
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
 #if S2B_TILE_STATS
   if (c->d_tile_stats) {
     unsigned long long t[12];
@@ -1021,6 +1052,10 @@ int srrg2b_ctx_destroy(srrg2b_ctx* c) {
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   for (auto& kv : c->slices) {
     SliceData& s = kv.second;
+    for (RawCloud* rcp : {&s.fixed_raw, &s.moving_raw}) {
+      if (rcp->ev_coords) cudaEventDestroy(rcp->ev_coords);
+      if (rcp->ev_all) cudaEventDestroy(rcp->ev_all);
+    }
     s.fixed_raw.xyz.release(); s.fixed_raw.nrm.release(); s.fixed_raw.valid.release();
     s.moving_raw.xyz.release(); s.moving_raw.nrm.release(); s.moving_raw.valid.release();
     s.f_pts.release(); s.f_nrm.release(); s.f_inverse.release(); s.cell_start.release(); s.near_bits.release();
@@ -1088,20 +1123,24 @@ int srrg2b_set_cloud(srrg2b_ctx* c, int slot, int slice_id, const srrg2b_cloud* 
   CK(c, cudaSetDevice(c->device));
   SliceData& sd = c->slices[slice_id];
   if (slot == SRRG2B_FIXED) {
+    CK(c, cudaStreamSynchronize(c->stream));  // an index build of the previous fixed cloud may still be running
     int rcode = upload_raw(c, sd.fixed_raw, cl);
     if (rcode) return rcode;
-    sd.built_for_max_distance = -1.f;  // _fixed_changed_flag: rebuild the index on next use
+    const bool was_nn = !sd.index_is_projective;
+    sd.built_for_max_distance = -1.f;  // _fixed_changed_flag: the index has to be rebuilt
     sd.index_is_projective = false;
     sd.corr_valid = false;
-    CK(c, cudaStreamSynchronize(c->stream));
-    return SRRG2B_OK;
+    // The NN index is built for the finder radius the slice used last, right away and WITHOUT waiting for
+    // it: the kernels run on the compute stream while the caller uploads the moving cloud on the copy
+    // stream (a different radius at run time simply rebuilds).  First use of a slice: built lazily.
+    if (was_nn && sd.last_max_distance > 0.f && c->eager_index) rcode = ensure_index(c, sd, sd.last_max_distance);
+    CK(c, cudaStreamSynchronize(c->copy_stream));  // the caller's buffers are free again
+    return rcode;
   }
   int rcode = upload_raw(c, sd.moving_raw, cl);
   if (rcode) return rcode;
-  // (measured: draining the copies before the first kernel is queued is 0.3 ms faster than queueing
-  // the index build behind them)
-  CK(c, cudaStreamSynchronize(c->stream));
   rcode = build_moving(c, sd);
+  CK(c, cudaStreamSynchronize(c->copy_stream));
   if (rcode) return rcode;
   CK(c, cudaStreamSynchronize(c->stream));
   return SRRG2B_OK;
