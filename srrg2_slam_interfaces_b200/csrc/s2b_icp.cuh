@@ -78,6 +78,8 @@ struct SliceArgs {
   const int* __restrict__ cell_start;
   const unsigned* __restrict__ near_bits;  // dilated occupancy (see near_bits_kernel)
   float ox, oy, oz, inv_cell;
+  float inv_cell_x;  // cells are XF times finer along x (the direction the rows run): inv_cell_x = XF * inv_cell
+  int Rx;            // search radius in x cells = XF * R
   int nx, ny, nz;
   int R;      // search radius in cells (cell edge = 1.001 * max_distance / R)
   int warm;   // c_fpos holds a valid candidate position per query (previous iteration's NN)
@@ -203,8 +205,8 @@ __device__ __forceinline__ float axis_gap(int d, float fr) {
 // of a grid row ordered by x up to one quantum (cell / 2^xbits), which lets the row scans jump to the
 // query's x and stop as soon as |x - q_x| alone exceeds the pruning radius (plus that quantum).
 __global__ void cell_key_kernel(const float* __restrict__ xyz, const unsigned char* __restrict__ valid, int n,
-                                int dim, float ox, float oy, float oz, float inv, int nx, int ny, int nz, int xbits,
-                                unsigned* __restrict__ keys, int* __restrict__ vals) {
+                                int dim, float ox, float oy, float oz, float inv, float inv_x, int nx, int ny, int nz,
+                                int xbits, unsigned* __restrict__ keys, int* __restrict__ vals) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   vals[i] = i;
@@ -214,7 +216,7 @@ __global__ void cell_key_kernel(const float* __restrict__ xyz, const unsigned ch
   }
   const float x = xyz[(size_t) i * dim], y = xyz[(size_t) i * dim + 1];
   const float z = dim == 3 ? xyz[(size_t) i * dim + 2] : 0.f;
-  const float cfx = cell_coord_f(x, ox, inv, nx);
+  const float cfx = cell_coord_f(x, ox, inv_x, nx);
   int cx = min(max((int) floorf(cfx), 0), nx - 1);
   int cy = min(max(cell_coord(y, oy, inv, ny), 0), ny - 1);
   int cz = min(max(cell_coord(z, oz, inv, nz), 0), nz - 1);
@@ -336,10 +338,16 @@ __global__ void cell_head_kernel(const unsigned* __restrict__ keys, int n_valid,
 }
 
 // number of distinct keys among the first n sorted keys (= occupied cells)
-__global__ void count_distinct_kernel(const unsigned* __restrict__ keys, int n, int xbits, int* __restrict__ out) {
+// (cells counted at the isotropic resolution: xf consecutive x cells of a row are one cell here)
+__global__ void count_distinct_kernel(const unsigned* __restrict__ keys, int n, int xbits, int nx, int xf,
+                                      int* __restrict__ out) {
   int c = 0;
+  auto coarse = [=](unsigned key) {
+    const unsigned id = key >> xbits, row = id / (unsigned) nx, cx = id - row * (unsigned) nx;
+    return (unsigned long long) row * (unsigned) nx + cx / (unsigned) xf;
+  };
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-    c += (i == 0 || (keys[i] >> xbits) != (keys[i - 1] >> xbits)) ? 1 : 0;
+    c += (i == 0 || coarse(keys[i]) != coarse(keys[i - 1])) ? 1 : 0;
   c = __reduce_add_sync(0xffffffffu, c);
   if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
 }
@@ -357,21 +365,22 @@ __device__ __forceinline__ bool near_bit(const unsigned* __restrict__ bits, int 
   return (__ldg(bits + (size_t) (cz * ny + cy) * nxw + (cx >> 5)) >> (cx & 31)) & 1u;
 }
 
-__global__ void near_bits_x_kernel(const int* __restrict__ cell_start, int nx, int nrows, int R,
+__global__ void near_bits_x_kernel(const int* __restrict__ cell_start, int nx, int nrows, int R /* in x cells */,
                                    unsigned* __restrict__ out) {
+  // one warp per word, one lane per cell: two coalesced loads of the row's table and a ballot
   const int nxw = near_words_per_row(nx);
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= nrows * nxw) return;
-  const int row = t / nxw, w = t - row * nxw;
+  const long long t = ((long long) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (t >= (long long) nrows * nxw) return;
+  const int row = (int) (t / nxw), w = (int) (t - (long long) row * nxw), lane = threadIdx.x & 31;
   const int* cs = cell_start + (size_t) row * nx;
-  unsigned word = 0;
-  for (int b = 0; b < 32; ++b) {
-    const int x = (w << 5) + b;
-    if (x >= nx) break;
+  const int x = (w << 5) + lane;
+  bool near = false;
+  if (x < nx) {
     const int xa = max(x - R, 0), xb = min(x + R, nx - 1);
-    if (cs[xb + 1] > cs[xa]) word |= 1u << b;  // some point in cells [x - R, x + R] of this row
+    near = cs[xb + 1] > cs[xa];  // some point in cells [x - R, x + R] of this row
   }
-  out[t] = word;
+  const unsigned word = __ballot_sync(0xffffffffu, near);
+  if (lane == 0) out[t] = word;
 }
 
 __global__ void near_bits_yz_kernel(const unsigned* __restrict__ in, int nx, int ny, int nz, int R, int dim,
@@ -456,9 +465,9 @@ __device__ __forceinline__ void nn_consider(const SliceArgs& a, NNQuery& q, int 
 template <int DIM, bool TRACK2>
 __device__ __forceinline__ void nn_scan_row(const SliceArgs& a, NNQuery& q, int y, int z, float lb2) {
   const float pr2 = TRACK2 ? q.sd2 : q.bd2;
-  const float rr = __fsqrt_rn(fmaxf(pr2 - lb2, 0.f)) * a.inv_cell + 2e-3f;
-  const int xa = max(max((int) floorf(q.cfx - rr), q.cx - a.R), 0);
-  const int xb = min(min((int) floorf(q.cfx + rr), q.cx + a.R), a.nx - 1);
+  const float rr = __fsqrt_rn(fmaxf(pr2 - lb2, 0.f)) * a.inv_cell_x + 2e-3f;
+  const int xa = max(max((int) floorf(q.cfx - rr), q.cx - a.Rx), 0);
+  const int xb = min(min((int) floorf(q.cfx + rr), q.cx + a.Rx), a.nx - 1);
   if (xa > xb) return;
   const int row = (z * a.ny + y) * a.nx;
   const int ps = __ldg(a.cell_start + row + xa);
@@ -494,7 +503,7 @@ __device__ __forceinline__ void nn_transform(const float* S, const float4 m, flo
 template <int DIM>
 __device__ __forceinline__ void nn_setup(const SliceArgs& a, const float* S, const float4 m, NNQuery& q) {
   nn_transform<DIM>(S, m, q.qx, q.qy, q.qz);
-  q.cfx = cell_coord_f(q.qx, a.ox, a.inv_cell, a.nx);
+  q.cfx = cell_coord_f(q.qx, a.ox, a.inv_cell_x, a.nx);
   const float cfy = cell_coord_f(q.qy, a.oy, a.inv_cell, a.ny);
   const float cfz = (DIM == 3) ? cell_coord_f(q.qz, a.oz, a.inv_cell, a.nz) : 0.f;
   q.cx = (int) floorf(q.cfx); q.cy = (int) floorf(cfy); q.cz = (DIM == 3) ? (int) floorf(cfz) : 0;
@@ -759,8 +768,9 @@ __device__ __forceinline__ void nn_tile_body(const SliceArgs& a, TileSmem& sm, f
     {  // bounding box of the cells within reach (the pruning radius) of the queries that search
       int lo[3] = {INT_MAX, INT_MAX, INT_MAX}, hi[3] = {INT_MIN, INT_MIN, INT_MIN};
       if (need) {
-        const float rq = __fsqrt_rn(TRACK2 ? q.sd2 : q.bd2) * a.inv_cell + 2e-3f;
-        lo[0] = max((int) floorf(q.cfx - rq), q.cx - R); hi[0] = min((int) floorf(q.cfx + rq), q.cx + R);
+        const float rd = __fsqrt_rn(TRACK2 ? q.sd2 : q.bd2);
+        const float rq = rd * a.inv_cell + 2e-3f, rqx = rd * a.inv_cell_x + 2e-3f;
+        lo[0] = max((int) floorf(q.cfx - rqx), q.cx - a.Rx); hi[0] = min((int) floorf(q.cfx + rqx), q.cx + a.Rx);
         lo[1] = max((int) floorf(cfy - rq), q.cy - R); hi[1] = min((int) floorf(cfy + rq), q.cy + R);
         if (DIM == 3) { lo[2] = max((int) floorf(cfz - rq), q.cz - R); hi[2] = min((int) floorf(cfz + rq), q.cz + R); }
         else { lo[2] = 0; hi[2] = 0; }
@@ -907,9 +917,9 @@ __device__ __forceinline__ void nn_tile_body(const SliceArgs& a, TileSmem& sm, f
       // one staged row: the cells within reach along x, then the x-sorted run
       auto scan_row = [&](int y, int z, float lb2) {
         const float pr2 = TRACK2 ? q.sd2 : q.bd2;
-        const float rr = __fsqrt_rn(fmaxf(pr2 - lb2, 0.f)) * a.inv_cell + 2e-3f;
-        const int xa = max(max((int) floorf(q.cfx - rr), q.cx - R), 0);
-        const int xb = min(min((int) floorf(q.cfx + rr), q.cx + R), a.nx - 1);
+        const float rr = __fsqrt_rn(fmaxf(pr2 - lb2, 0.f)) * a.inv_cell_x + 2e-3f;
+        const int xa = max(max((int) floorf(q.cfx - rr), q.cx - a.Rx), 0);
+        const int xb = min(min((int) floorf(q.cfx + rr), q.cx + a.Rx), a.nx - 1);
         if (xa > xb) return;
         const int r = (z - z0) * by + (y - y0);
         const int* csr = sm.cs + r * bx1 - x0;
@@ -1062,9 +1072,9 @@ __device__ __forceinline__ void nn_far_body(const SliceArgs& a, const float* S, 
             }
             const float pr2 = TRACK2 ? q.sd2 : q.bd2;
             if (!(lb2 > pr2)) {
-              const float rr = __fsqrt_rn(fmaxf(pr2 - lb2, 0.f)) * a.inv_cell + 2e-3f;
-              const int xa = max(max((int) floorf(q.cfx - rr), q.cx - a.R), 0);
-              const int xb = min(min((int) floorf(q.cfx + rr), q.cx + a.R), a.nx - 1);
+              const float rr = __fsqrt_rn(fmaxf(pr2 - lb2, 0.f)) * a.inv_cell_x + 2e-3f;
+              const int xa = max(max((int) floorf(q.cfx - rr), q.cx - a.Rx), 0);
+              const int xb = min(min((int) floorf(q.cfx + rr), q.cx + a.Rx), a.nx - 1);
               if (xa <= xb) {
                 const int row = (z * a.ny + y) * a.nx;
                 ps = __ldg(a.cell_start + row + xa);

@@ -3,6 +3,8 @@ import sys, time
 sys.path.insert(0, '.')
 import numpy as np, torch
 from srrg2_slam_interfaces_b200 import capi as A, synthetic as syn
+from bench import bind_to_gpu_numa
+print('cores bound to the GPU-local NUMA node:', bind_to_gpu_numa(0))
 n = 1000000
 d = syn.make_icp3d(n, n, seed=2)
 host = {k: torch.from_numpy(np.ascontiguousarray(d[k])).pin_memory().numpy() for k in ("fixed", "fixed_normals", "moving", "moving_normals")}
