@@ -103,8 +103,8 @@ class ClockSampler:
 
 def bind_to_gpu_numa(gpu):
     """Pins this process to the CPU cores NVML reports as local to the GPU, BEFORE the pinned host
-    buffers are allocated: pinned pages land where the allocating thread runs, and a buffer on the
-    remote socket uploads at a third of the bandwidth (measured: 17 vs 52 GB/s)."""
+    buffers are allocated: pinned pages land where the allocating thread runs, and a buffer on a remote
+    socket uploads slower.  (A no-op on single-node hosts such as this pool's 16-core boxes.)"""
     try:
         import pynvml
         pynvml.nvmlInit()
