@@ -29,6 +29,7 @@ struct NcclApi {
   int (*GetUniqueId)(NcclId*) = nullptr;
   int (*CommInitRank)(ncclComm_t*, int, NcclId, int) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
   int (*CommDestroy)(ncclComm_t) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
   bool load() {
@@ -41,6 +42,7 @@ struct NcclApi {
     GetUniqueId = (int (*)(NcclId*)) dlsym(handle, "ncclGetUniqueId");
     CommInitRank = (int (*)(ncclComm_t*, int, NcclId, int)) dlsym(handle, "ncclCommInitRank");
     AllReduce = (int (*)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t)) dlsym(handle, "ncclAllReduce");
+    AllGather = (int (*)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t)) dlsym(handle, "ncclAllGather");
     CommDestroy = (int (*)(ncclComm_t)) dlsym(handle, "ncclCommDestroy");
     GetErrorString = (const char* (*) (int) ) dlsym(handle, "ncclGetErrorString");
     return GetUniqueId && CommInitRank && AllReduce && CommDestroy;
@@ -140,6 +142,11 @@ struct srrg2b_ctx {
   // comm
   ncclComm_t comm = nullptr;
   int rank = 0, world = 1;
+  // peer-memory exchange of the accumulators (PeerExchange in s2b_icp.cuh); null: NCCL all-reduce
+  s2b::PeerExchange* d_px = nullptr;
+  unsigned long long* d_mail = nullptr;
+  unsigned long long* d_epoch = nullptr;
+  std::vector<void*> peer_maps;
   float last_ms = 0.f;
   int last_iterations = 0;
   int sm_count = 148;
@@ -819,7 +826,7 @@ int make_plan(srrg2b_ctx* c, int n_slices, const srrg2b_slice* slices, const srr
 }
 
 int allreduce_acc(srrg2b_ctx* c, int n_slices) {
-  if (c->world <= 1) return SRRG2B_OK;
+  if (c->world <= 1 || c->d_px) return SRRG2B_OK;  // (peer exchange: done by the solve kernel itself)
   if (g_nccl.AllReduce(c->d_state->acc, c->d_state->acc, (size_t) n_slices * kAcc, kNcclUint64, kNcclSum, c->comm,
                        c->stream) != 0)
     FAIL(c, SRRG2B_ERR_NCCL, "ncclAllReduce(sum) of H/b/stats failed");
@@ -848,8 +855,8 @@ int enqueue_iterations(srrg2b_ctx* c, const Plan& plan, int iterations) {
     }
     int rcode = allreduce_acc(c, plan.solve.n_slices);
     if (rcode) return rcode;
-    if (c->dim == 3) icp_solve_kernel<3><<<1, kSolveThreads, 0, c->stream>>>(c->d_solve, c->d_state);
-    else icp_solve_kernel<2><<<1, kSolveThreads, 0, c->stream>>>(c->d_solve, c->d_state);
+    if (c->dim == 3) icp_solve_kernel<3><<<1, kSolveThreads, 0, c->stream>>>(c->d_solve, c->d_state, c->d_px);
+    else icp_solve_kernel<2><<<1, kSolveThreads, 0, c->stream>>>(c->d_solve, c->d_state, c->d_px);
     c->launches++;
   }
   CK(c, cudaGetLastError());
@@ -865,8 +872,8 @@ int run_plan(srrg2b_ctx* c, const Plan& plan, const Mat4f& T0, int iterations, i
   *c->h_solve = plan.solve;
   CK(c, cudaMemcpyAsync(c->d_T0, c->h_T0, sizeof(Mat4f), cudaMemcpyHostToDevice, c->stream));
   CK(c, cudaMemcpyAsync(c->d_solve, c->h_solve, sizeof(SolveArgs), cudaMemcpyHostToDevice, c->stream));
-  // (with an NCCL communicator attached the iterations are stream launches unless SRRG2B_GRAPH_NCCL=1)
-  const bool graph = c->use_graphs && !c->time_kernels && (c->world <= 1 || c->graph_nccl);
+  // (several ranks: graph replay needs the peer-memory exchange -- no NCCL call inside the iteration)
+  const bool graph = c->use_graphs && !c->time_kernels && (c->world <= 1 || c->graph_nccl || c->d_px);
   if (!graph) {
     icp_init_kernel<<<1, 32, 0, c->stream>>>(c->d_solve, c->d_state, c->d_T0, apply_prior_guess, reset_tc, keep_stats);
     c->launches++;
@@ -1067,6 +1074,16 @@ int srrg2b_ctx_destroy(srrg2b_ctx* c) {
   }
 #endif
   if (c->d_tile_stats) cudaFree(c->d_tile_stats);
+  if (c->d_px && c->comm && g_nccl.AllReduce && c->d_epoch) {
+    // a peer may still be adding this rank's last mailbox words: leave together (contexts of a
+    // communicator are destroyed collectively, like the communicator itself)
+    g_nccl.AllReduce(c->d_epoch, c->d_epoch, 1, kNcclUint64, kNcclMax, c->comm, c->stream);
+    cudaStreamSynchronize(c->stream);
+  }
+  for (void* p : c->peer_maps) cudaIpcCloseMemHandle(p);
+  if (c->d_px) cudaFree(c->d_px);
+  if (c->d_mail) cudaFree(c->d_mail);
+  if (c->d_epoch) cudaFree(c->d_epoch);
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   for (auto& kv : c->slices) {
     SliceData& s = kv.second;
@@ -1130,6 +1147,63 @@ int srrg2b_comm_init(srrg2b_ctx* c, const void* id, int rank, int world) {
   if (r != 0) FAIL(c, SRRG2B_ERR_NCCL, std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
   c->rank = rank;
   c->world = world;
+  // Peer-memory exchange (default; SRRG2B_PEER_EXCHANGE=0 keeps the NCCL all-reduce): every rank
+  // allocates its mailbox, the IPC handles travel through one ncclAllGather, peers are mapped.
+  const char* env = getenv("SRRG2B_PEER_EXCHANGE");
+  if ((env && atoi(env) == 0) || world > kMaxRanks || !g_nccl.AllGather) return SRRG2B_OK;
+  const size_t mail_bytes = 2 * kMailWords * sizeof(unsigned long long);
+  CK(c, cudaMalloc((void**) &c->d_mail, mail_bytes));
+  CK(c, cudaMemsetAsync(c->d_mail, 0, mail_bytes, c->stream));
+  CK(c, cudaMalloc((void**) &c->d_epoch, sizeof(unsigned long long)));
+  CK(c, cudaMemsetAsync(c->d_epoch, 0, sizeof(unsigned long long), c->stream));
+  cudaIpcMemHandle_t mine;
+  CK(c, cudaIpcGetMemHandle(&mine, c->d_mail));
+  unsigned char* d_handles = nullptr;
+  CK(c, cudaMalloc((void**) &d_handles, sizeof(mine) * (size_t) world));
+  CK(c, cudaMemcpyAsync(d_handles + sizeof(mine) * (size_t) rank, &mine, sizeof(mine), cudaMemcpyHostToDevice, c->stream));
+  if (g_nccl.AllGather(d_handles + sizeof(mine) * (size_t) rank, d_handles, sizeof(mine), /*ncclUint8*/ 1, c->comm,
+                       c->stream) != 0) {
+    cudaFree(d_handles);
+    FAIL(c, SRRG2B_ERR_NCCL, "ncclAllGather of the mailbox handles failed");
+  }
+  std::vector<cudaIpcMemHandle_t> all((size_t) world);
+  CK(c, cudaMemcpyAsync(all.data(), d_handles, sizeof(mine) * (size_t) world, cudaMemcpyDeviceToHost, c->stream));
+  CK(c, cudaStreamSynchronize(c->stream));
+  cudaFree(d_handles);
+  PeerExchange px;
+  memset(&px, 0, sizeof(px));
+  px.rank = rank;
+  px.world = world;
+  px.epoch = c->d_epoch;
+  bool mapped = true;
+  for (int r = 0; r < world && mapped; ++r) {
+    if (r == rank) { px.mail[r] = c->d_mail; continue; }
+    void* p = nullptr;
+    if (cudaIpcOpenMemHandle(&p, all[(size_t) r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      cudaGetLastError();
+      mapped = false;
+      break;
+    }
+    c->peer_maps.push_back(p);
+    px.mail[r] = (unsigned long long*) p;
+  }
+  // the decision must be the same on every rank: agree through a one-word all-reduce (min)
+  int* d_ok = nullptr;
+  CK(c, cudaMalloc((void**) &d_ok, sizeof(int)));
+  const int ok_mine = mapped ? 1 : 0;
+  CK(c, cudaMemcpyAsync(d_ok, &ok_mine, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  int ok_all = 0;
+  if (g_nccl.AllReduce(d_ok, d_ok, 1, /*ncclInt32*/ 2, /*ncclMin*/ 3, c->comm, c->stream) != 0) ok_all = 0;
+  else {
+    CK(c, cudaMemcpyAsync(&ok_all, d_ok, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+  }
+  cudaFree(d_ok);
+  if (ok_all) {
+    CK(c, cudaMalloc((void**) &c->d_px, sizeof(PeerExchange)));
+    CK(c, cudaMemcpyAsync(c->d_px, &px, sizeof(px), cudaMemcpyHostToDevice, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+  }
   return SRRG2B_OK;
 }
 

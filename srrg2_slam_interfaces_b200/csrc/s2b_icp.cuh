@@ -1894,9 +1894,37 @@ __device__ void icp_solve_serial(const SolveArgs& a, DevHeader& st, srrg2b_iter_
 }
 
 constexpr int kSolveThreads = 128;
+constexpr int kMaxRanks = 16;
+constexpr int kMailWords = SRRG2B_MAX_SLICES * kAcc + 8;  // accumulators + flag word (rest padding)
+
+// Multi-GPU exchange of the integer accumulators, fused into the solve step: every rank owns a
+// two-slot mailbox in its own HBM that the peers map through CUDA IPC (NVLink / NVSwitch peer loads).
+// Epoch e: write the accumulators into slot e & 1, fence, publish flag = e; then, per peer, spin on
+// its flag and add its words.  Integer sums: every rank gets the same bits whatever the order.
+// A slot is rewritten at epoch e + 2, after every peer has published e + 1, i.e. after it finished
+// reading e -- so two slots suffice.  No NCCL call inside the iteration: the run stays one CUDA graph.
+struct PeerExchange {
+  int rank, world;
+  unsigned long long* epoch;                 // device counter, advanced once per exchanged solve step
+  unsigned long long* mail[kMaxRanks];       // mail[r]: rank r's mailbox (own or IPC-mapped), 2 * kMailWords
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
 
 template <int DIM>
-__global__ void __launch_bounds__(kSolveThreads) icp_solve_kernel(const SolveArgs* ap, DevState* st) {
+__global__ void __launch_bounds__(kSolveThreads) icp_solve_kernel(const SolveArgs* ap, DevState* st, const PeerExchange* px) {
   __shared__ __align__(16) SolveArgs a;
   __shared__ __align__(16) DevHeader sh;
   // one round of independent 16-byte loads stages the arguments and the whole mutable state
@@ -1909,7 +1937,38 @@ __global__ void __launch_bounds__(kSolveThreads) icp_solve_kernel(const SolveArg
     for (int k = threadIdx.x; k < (int) (sizeof(DevHeader) / 16); k += kSolveThreads) d1[k] = s1[k];
   }
   __syncthreads();
-  if (sh.stop) return;
+  if (sh.stop) return;  // (every rank holds the same state, so every rank returns here or none does)
+  if (px) {
+    // all-reduce of the accumulators over peer memory (see PeerExchange)
+    __shared__ PeerExchange pe;
+    __shared__ unsigned long long s_epoch;
+    {
+      const int* src = reinterpret_cast<const int*>(px);
+      int* dst = reinterpret_cast<int*>(&pe);
+      for (int k = threadIdx.x; k < (int) (sizeof(PeerExchange) / sizeof(int)); k += kSolveThreads) dst[k] = src[k];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_epoch = *pe.epoch + 1ull;
+    __syncthreads();
+    const unsigned long long e = s_epoch;
+    const int n_words = a.n_slices * kAcc;
+    unsigned long long* mine = pe.mail[pe.rank] + (e & 1ull) * kMailWords;
+    for (int k = threadIdx.x; k < n_words; k += kSolveThreads) mine[k] = (&sh.acc[0][0])[k];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) st_release_sys(mine + SRRG2B_MAX_SLICES * kAcc, e);
+    for (int r = 0; r < pe.world; ++r) {
+      if (r == pe.rank) continue;
+      const unsigned long long* theirs = pe.mail[r] + (e & 1ull) * kMailWords;
+      if (threadIdx.x == 0) {
+        while (ld_acquire_sys(theirs + SRRG2B_MAX_SLICES * kAcc) != e) { }
+      }
+      __syncthreads();
+      for (int k = threadIdx.x; k < n_words; k += kSolveThreads) (&sh.acc[0][0])[k] += ld_relaxed_sys(theirs + k);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *pe.epoch = e;
+  }
   // the NN pass of this iteration certified its bounds at S: record that before anything can bail out;
   // the work-list counters start the next iteration at zero
   for (int k = 0; k < a.n_slices; ++k) {
