@@ -1174,7 +1174,6 @@ int srrg2b_comm_init(srrg2b_ctx* c, const void* id, int rank, int world) {
   memset(&px, 0, sizeof(px));
   px.rank = rank;
   px.world = world;
-  px.epoch = c->d_epoch;
   bool mapped = true;
   for (int r = 0; r < world && mapped; ++r) {
     if (r == rank) { px.mail[r] = c->d_mail; continue; }

@@ -42,7 +42,8 @@ struct DevHeader {
   int iterations_run;
   Ring r_ncorr, r_ninl, r_nout, r_chi;
   int tc_iterations;
-  int pad_[3];
+  int pad_;
+  unsigned long long epoch;                  // peer-exchange epoch (PeerExchange), survives across runs
 };
 static_assert(sizeof(DevHeader) % 16 == 0, "DevHeader is copied in 16-byte pieces");
 
@@ -1893,33 +1894,29 @@ __device__ void icp_solve_serial(const SolveArgs& a, DevHeader& st, srrg2b_iter_
   if (a.use_tc && has_to_stop(&st, a, s, total)) st.stop = 1;
 }
 
-constexpr int kSolveThreads = 128;
+constexpr int kSolveThreads = 256;
 constexpr int kMaxRanks = 16;
-constexpr int kMailWords = SRRG2B_MAX_SLICES * kAcc + 8;  // accumulators + flag word (rest padding)
+constexpr int kMailWords = 2 * SRRG2B_MAX_SLICES * kAcc;  // two tagged 8-byte words per accumulator
 
 // Multi-GPU exchange of the integer accumulators, fused into the solve step: every rank owns a
 // two-slot mailbox in its own HBM that the peers map through CUDA IPC (NVLink / NVSwitch peer loads).
-// Epoch e: write the accumulators into slot e & 1, fence, publish flag = e; then, per peer, spin on
-// its flag and add its words.  Integer sums: every rank gets the same bits whatever the order.
-// A slot is rewritten at epoch e + 2, after every peer has published e + 1, i.e. after it finished
-// reading e -- so two slots suffice.  No NCCL call inside the iteration: the run stays one CUDA graph.
+// Low-latency protocol (the idea of NCCL's LL): every 8-byte mailbox word carries 32 bits of payload
+// and the 32-bit epoch tag, and an aligned 8-byte store is indivisible, so a reader simply polls the
+// word until the tag matches -- no fence, no separate flag, one NVLink traversal.  Epoch e uses slot
+// e & 1; a slot is rewritten at epoch e + 2, which a rank reaches only after every peer delivered
+// e + 1, i.e. finished reading e -- so two slots suffice.  Integer sums: every rank gets the same bits
+// whatever the order.  No NCCL call inside the iteration: the run stays one CUDA graph.
 struct PeerExchange {
   int rank, world;
-  unsigned long long* epoch;                 // device counter, advanced once per exchanged solve step
   unsigned long long* mail[kMaxRanks];       // mail[r]: rank r's mailbox (own or IPC-mapped), 2 * kMailWords
 };
 
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+__device__ __forceinline__ void st_volatile_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+__device__ __forceinline__ unsigned long long ld_volatile_sys(const unsigned long long* p) {
   unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
 
@@ -1927,6 +1924,7 @@ template <int DIM>
 __global__ void __launch_bounds__(kSolveThreads) icp_solve_kernel(const SolveArgs* ap, DevState* st, const PeerExchange* px) {
   __shared__ __align__(16) SolveArgs a;
   __shared__ __align__(16) DevHeader sh;
+  __shared__ PeerExchange pe;
   // one round of independent 16-byte loads stages the arguments and the whole mutable state
   {
     const int4* s0 = reinterpret_cast<const int4*>(ap);
@@ -1935,39 +1933,44 @@ __global__ void __launch_bounds__(kSolveThreads) icp_solve_kernel(const SolveArg
     const int4* s1 = reinterpret_cast<const int4*>(static_cast<const DevHeader*>(st));
     int4* d1 = reinterpret_cast<int4*>(&sh);
     for (int k = threadIdx.x; k < (int) (sizeof(DevHeader) / 16); k += kSolveThreads) d1[k] = s1[k];
+    if (px) {
+      const int* s2 = reinterpret_cast<const int*>(px);
+      int* d2 = reinterpret_cast<int*>(&pe);
+      for (int k = threadIdx.x; k < (int) (sizeof(PeerExchange) / sizeof(int)); k += kSolveThreads) d2[k] = s2[k];
+    }
   }
   __syncthreads();
   if (sh.stop) return;  // (every rank holds the same state, so every rank returns here or none does)
   if (px) {
     // all-reduce of the accumulators over peer memory (see PeerExchange)
-    __shared__ PeerExchange pe;
-    __shared__ unsigned long long s_epoch;
-    {
-      const int* src = reinterpret_cast<const int*>(px);
-      int* dst = reinterpret_cast<int*>(&pe);
-      for (int k = threadIdx.x; k < (int) (sizeof(PeerExchange) / sizeof(int)); k += kSolveThreads) dst[k] = src[k];
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) s_epoch = *pe.epoch + 1ull;
-    __syncthreads();
-    const unsigned long long e = s_epoch;
+    const unsigned long long e = sh.epoch + 1ull;
+    const unsigned long long tag = (e & 0xffffffffull) << 32;
     const int n_words = a.n_slices * kAcc;
     unsigned long long* mine = pe.mail[pe.rank] + (e & 1ull) * kMailWords;
-    for (int k = threadIdx.x; k < n_words; k += kSolveThreads) mine[k] = (&sh.acc[0][0])[k];
-    __threadfence_system();
+    for (int k = threadIdx.x; k < n_words; k += kSolveThreads) {
+      const unsigned long long v = (&sh.acc[0][0])[k];
+      st_volatile_sys(mine + 2 * k, (v & 0xffffffffull) | tag);
+      st_volatile_sys(mine + 2 * k + 1, (v >> 32) | tag);
+    }
+    // (peer, word) pairs are dealt to the threads: both halves are requested together and polled until
+    // their tags are e, then added to the shared copy.  Everything a thread waits for is in flight at
+    // once, so the exchange costs about one NVLink round trip per ceil(pairs / threads).
     __syncthreads();
-    if (threadIdx.x == 0) st_release_sys(mine + SRRG2B_MAX_SLICES * kAcc, e);
-    for (int r = 0; r < pe.world; ++r) {
-      if (r == pe.rank) continue;
-      const unsigned long long* theirs = pe.mail[r] + (e & 1ull) * kMailWords;
-      if (threadIdx.x == 0) {
-        while (ld_acquire_sys(theirs + SRRG2B_MAX_SLICES * kAcc) != e) { }
-      }
-      __syncthreads();
-      for (int k = threadIdx.x; k < n_words; k += kSolveThreads) (&sh.acc[0][0])[k] += ld_relaxed_sys(theirs + k);
+    const int n_pairs = n_words * (pe.world - 1);
+    for (int t = threadIdx.x; t < n_pairs; t += kSolveThreads) {
+      int r = t / n_words;
+      const int k = t - r * n_words;
+      if (r >= pe.rank) ++r;  // peers in rank order, skipping this rank
+      const unsigned long long* theirs = pe.mail[r] + (e & 1ull) * kMailWords + 2 * k;
+      unsigned long long lo, hi;
+      do {
+        lo = ld_volatile_sys(theirs);
+        hi = ld_volatile_sys(theirs + 1);
+      } while ((lo & 0xffffffff00000000ull) != tag || (hi & 0xffffffff00000000ull) != tag);
+      atomicAdd(&sh.acc[0][0] + k, (lo & 0xffffffffull) | ((hi & 0xffffffffull) << 32));
     }
     __syncthreads();
-    if (threadIdx.x == 0) *pe.epoch = e;
+    if (threadIdx.x == 0) sh.epoch = e;  // (written back with the rest of the state)
   }
   // the NN pass of this iteration certified its bounds at S: record that before anything can bail out;
   // the work-list counters start the next iteration at zero
