@@ -628,7 +628,10 @@ __device__ __forceinline__ void nn_phase1_body(const SliceArgs& a, const float* 
       if (lb2 > (TRACK2 ? q.sd2 : q.bd2)) continue;
       nn_scan_row<DIM, TRACK2>(a, q, q.cy + jy - 1, q.cz + jz - 1, lb2);
     }
-    if (q.bd2 > ring2_sq) {  // not settled by rings 0-1: phase 2 redoes this query with a whole warp
+    if (q.bd2 > ring2_sq) {  // not settled by rings 0-1: phase 2 continues this query from ring 2
+      // rings 0-1 are done for good: their best point (if any) travels in the slot as the warm-start
+      // candidate, and phase 2 -- when it only needs the nearest point -- starts at ring 2
+      if (!TRACK2 && q.bpos >= 0 && q.bpos != old_slot) a.c_fpos[i] = q.bpos;
       const int w = atomicAdd(a.far_count, 1);
       a.far_list[w] = i;
       continue;
@@ -1016,7 +1019,8 @@ __device__ __forceinline__ void nn_far_body(const SliceArgs& a, const float* S, 
       const int old_slot = a.c_fpos[i];
       const int p0 = slot_candidate(old_slot);
       if (a.warm && p0 >= 0) nn_consider<DIM, TRACK2>(a, q, p0);
-      for (int k = 0; k < K; ++k) {
+      // (far list of phase 1, nearest point only: rings 0-1 were searched exhaustively there)
+      for (int k = TRACK2 ? 0 : min(K, (DIM == 3 ? 9 : 3)); k < K; ++k) {
         const int e = rows[k];
         const int dy = (int) (signed char) (e & 0xff), dz = (int) (signed char) ((e >> 8) & 0xff);
         const int ring = (e >> 16) & 0xff;
@@ -1054,7 +1058,8 @@ __device__ __forceinline__ void nn_far_body(const SliceArgs& a, const float* S, 
     // two stages: rings 0-1 first, merged across the warp, so that the outer rings are pruned with the
     // radius the near rows established (nearly always to nothing)
     const int K1 = min(K, (DIM == 3 ? 9 : 3));
-    for (int stage = 0; stage < 2; ++stage) {
+    // far list of phase 1 and only the nearest point wanted: rings 0-1 were searched exhaustively there
+    for (int stage = (!lin && !TRACK2) ? 1 : 0; stage < 2; ++stage) {
       const int kb = stage ? K1 : 0, ke = stage ? K : K1;
       if (kb >= ke) break;
       for (int k0 = kb; k0 < ke; k0 += 32) {
