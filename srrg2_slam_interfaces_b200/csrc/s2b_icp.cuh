@@ -460,6 +460,15 @@ __device__ __forceinline__ void nn_consider(const SliceArgs& a, NNQuery& q, int 
   nn_consider_pt<DIM, TRACK2>(q, p, __ldg(a.fp + p));
 }
 
+// A search that certifies a bound examines everything within sqrt(sd2).  With a warm-start neighbour
+// at distance d0 there is no point in certifying more than max(2 d0, cell / 4): later iterations only
+// need the bound to exceed d0 by the (sub-millimetre) motion of a converged estimate, and the smaller
+// start value prunes the rows of ring 1 like a nearest-only search.  (A smaller sd2 only makes the
+// certified bound smaller, never wrong.)
+__device__ __forceinline__ void nn_limit_bound(NNQuery& q, float cell) {
+  if (q.bpos >= 0) q.sd2 = fminf(q.sd2, fmaxf(4.f * q.bd2, 0.0625f * cell * cell));
+}
+
 // scan the part of cell row (y, z) that can still matter, given the conservative squared distance
 // lb2 between the query and the row's y/z slab.  Pruning radius: bd2 (nearest only) or sd2 (two
 // nearest, needed to certify a bound).
@@ -592,7 +601,10 @@ __device__ __forceinline__ void nn_phase1_body(const SliceArgs& a, const float* 
         continue;
       }
     }
-    if (a.warm && p0 >= 0) nn_consider<DIM, TRACK2>(a, q, p0);  // a real candidate: exactness untouched
+    if (a.warm && p0 >= 0) {  // a real candidate: exactness untouched
+      nn_consider<DIM, TRACK2>(a, q, p0);
+      if (TRACK2) nn_limit_bound(q, cell);
+    }
     // squared slab gaps for offsets -1 and +1 along y and z (offset 0 has gap 0)
     const float gym = fmaxf(q.fry - 2e-3f, 0.f) * cell, gyp = fmaxf(1.f - q.fry - 2e-3f, 0.f) * cell;
     const float gy2m = gym * gym, gy2p = gyp * gyp;
@@ -759,12 +771,7 @@ __device__ __forceinline__ void nn_tile_body(const SliceArgs& a, TileSmem& sm, f
       if (a.warm && p0 >= 0) {
         // last iteration's neighbour: a real candidate whose distance bounds the search radius
         nn_consider<DIM, TRACK2>(a, q, p0);
-        if (TRACK2 && q.bpos >= 0) {
-          // certify "every other point is at least min(2 d0, cell / 4) away" at most: everything within
-          // sqrt(sd2) gets examined, a smaller start value only makes the certified bound smaller
-          const float r_t = fmaxf(4.f * q.bd2, 0.0625f * cell * cell);
-          q.sd2 = fminf(q.sd2, r_t);
-        }
+        if (TRACK2) nn_limit_bound(q, cell);
       } else if (q.cx >= 0 && q.cx < a.nx && q.cy >= 0 && q.cy < a.ny && q.cz >= 0 && q.cz < a.nz) {
         need = near_bit(a.near_bits, a.nx, a.ny, q.cx, q.cy, q.cz);
       }
@@ -1018,7 +1025,7 @@ __device__ __forceinline__ void nn_far_body(const SliceArgs& a, const float* S, 
       nn_setup<DIM>(a, S, a.mp[i], q);
       const int old_slot = a.c_fpos[i];
       const int p0 = slot_candidate(old_slot);
-      if (a.warm && p0 >= 0) nn_consider<DIM, TRACK2>(a, q, p0);
+      if (a.warm && p0 >= 0) { nn_consider<DIM, TRACK2>(a, q, p0); if (TRACK2) nn_limit_bound(q, cell); }
       // (far list of phase 1, nearest point only: rings 0-1 were searched exhaustively there)
       for (int k = TRACK2 ? 0 : min(K, (DIM == 3 ? 9 : 3)); k < K; ++k) {
         const int e = rows[k];
@@ -1051,7 +1058,7 @@ __device__ __forceinline__ void nn_far_body(const SliceArgs& a, const float* S, 
     nn_setup<DIM>(a, S, m, q);
     const int old_slot = a.c_fpos[i];
     const int p0 = slot_candidate(old_slot);
-    if (a.warm && p0 >= 0) nn_consider<DIM, TRACK2>(a, q, p0);
+    if (a.warm && p0 >= 0) { nn_consider<DIM, TRACK2>(a, q, p0); if (TRACK2) nn_limit_bound(q, cell); }
     // the warp takes the rows 32 at a time: lane -> bounds of one row, then the points of all 32 rows
     // are dealt out to the lanes round robin (a handful of dependent loads per query instead of a
     // serial walk per row); every lane keeps its own (nearest, second nearest) pair
