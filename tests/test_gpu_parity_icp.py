@@ -266,3 +266,56 @@ def test_tiled_search_matches_oracle(monkeypatch):
     assert np.array_equal(g["T"], o["T"])
     assert np.array_equal(gc[0], o["correspondences"][0][0])
     assert np.array_equal(gc[1], o["correspondences"][0][1])
+
+
+def test_icp_run_c2_full_size(oracle, capi):
+    """Config C2 at BASELINE.json's full size (1M vs 1M points, 20 iterations, Huber, point+normal):
+    the CUDA run equals the oracle's bit for bit -- pose, IterationStats, every correspondence -- and
+    the size-independent properties of the correspondence list hold."""
+    n = 1000000
+    d = syn.make_icp3d(n, n, seed=2)
+    kw = dict(max_iterations=20, min_num_inliers=10)
+    o, g, corr = _run_both(oracle, capi, 3, d, oracle.aligner_params(**kw), capi.aligner_params(**kw),
+                           oracle.finder_params(0.3, 0.8), capi.finder_params(0.3, 0.8),
+                           oracle.factor_params(oracle.FACTOR_PLANE, oracle.ROB_HUBER, 0.01),
+                           capi.factor_params(capi.FACTOR_PLANE, capi.ROB_HUBER, 0.01), np.eye(4))
+    _assert_same_run(o, g, corr)
+    assert g["status"] == capi.ALIGNER_SUCCESS and len(g["stats"]) == 20
+    fi, mi, rs = corr
+    assert np.all(np.diff(mi) > 0), "ascending moving index, at most one entry per moving point"
+    assert fi.min() >= 0 and fi.max() < n and np.all(rs <= 0.3 + 1e-6) and np.all(rs >= 0)
+    assert g["stats"][-1]["num_correspondences"] == fi.size
+    rot, trans = syn.pose_error(g["T"], d["T_star"])
+    assert rot < 1e-5 and trans < 1e-4
+    # spot check of exactness against brute force: the reported neighbour is the nearest fixed point
+    T = np.asarray(g["T"], dtype=np.float64)
+    rng = np.random.default_rng(5)
+    F = d["fixed"].astype(np.float64)
+    for k in rng.choice(fi.size, size=24, replace=False):
+        q = T[:3, :3] @ d["moving"][mi[k]].astype(np.float64) + T[:3, 3]
+        d2 = ((F - q) ** 2).sum(axis=1)
+        assert d2[fi[k]] <= d2.min() * (1 + 1e-5) + 1e-9
+
+
+def test_fixed_cloud_replaced_between_runs(oracle, capi):
+    """setFixed with a new cloud (the eager index build, the cached grid resolution) and a finder
+    radius that changes between runs (lazy rebuild): every run equals the oracle's."""
+    ctx = capi.Context(3)
+    kw = dict(max_iterations=6, min_num_inliers=10)
+    for nf, nm, seed, md in ((20000, 15000, 3, 0.3), (21000, 15000, 4, 0.3), (9000, 15000, 5, 0.3), (9000, 8000, 6, 0.45),
+                             (30000, 8000, 7, 0.3)):
+        d = syn.make_icp3d(nf, nm, seed=seed)
+        ctx.set_cloud(capi.FIXED, 0, d["fixed"], d["fixed_normals"])
+        ctx.set_cloud(capi.MOVING, 0, d["moving"], d["moving_normals"])
+        g = ctx.icp_run([capi.make_slice(3, 0, None, capi.finder_params(md, 0.8),
+                                         capi.factor_params(capi.FACTOR_PLANE, capi.ROB_HUBER, 0.01))],
+                        capi.aligner_params(**kw), np.eye(4))
+        gc = ctx.get_correspondences(0, nm)
+        F = oracle.CloudRef(d["fixed"], d["fixed_normals"])
+        M = oracle.CloudRef(d["moving"], d["moving_normals"])
+        o = oracle.icp_run(3, [oracle.make_slice(F, M, None, oracle.finder_params(md, 0.8),
+                                                 oracle.factor_params(oracle.FACTOR_PLANE, oracle.ROB_HUBER, 0.01))],
+                           oracle.aligner_params(**kw), np.eye(4))
+        assert g["stats"] == o["stats"] and np.array_equal(g["T"], o["T"])
+        assert np.array_equal(gc[0], o["correspondences"][0][0]) and np.array_equal(gc[1], o["correspondences"][0][1])
+    ctx.close()
