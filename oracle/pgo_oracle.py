@@ -158,11 +158,99 @@ def linearize(poses, ij, Z, Omega, fixed):
     return H, b.ravel(), float(chi.sum()), chi
 
 
+# ---- two-level preconditioner (reference for the CUDA solver's next step) ----
+def rigid_prolongation(poses, fixed, aggregate_size):
+    """Coarse space of the two-level preconditioner: the poses are grouped into aggregates of
+    `aggregate_size` consecutive indices, each aggregate gets the 6 rigid motions (dt, w) of its
+    members about the aggregate's centroid c, expressed as the members' RIGHT perturbations:
+        dt_i = R_i^T (dt + w x (t_i - c)),   dq_i = R_i^T w / 2.
+    Returns (agg[V], Pi[V, 6, 6]); fixed poses get a zero block."""
+    poses = np.asarray(poses, np.float64)
+    V = poses.shape[0]
+    agg = np.arange(V) // int(aggregate_size)
+    R, t = poses[:, :3, :3], poses[:, :3, 3]
+    c = np.zeros((agg.max() + 1, 3))
+    np.add.at(c, agg, t)
+    c /= np.bincount(agg)[:, None]
+    Rt = np.swapaxes(R, 1, 2)
+    Pi = np.zeros((V, 6, 6))
+    Pi[:, :3, :3] = Rt
+    Pi[:, :3, 3:] = -Rt @ skew(t - c[agg])
+    Pi[:, 3:, 3:] = 0.5 * Rt
+    Pi[np.asarray(fixed, bool)] = 0.0
+    return agg, Pi
+
+
+def coarse_matrix(H, agg, Pi):
+    """Galerkin coarse operator Hc = P^T H P (dense, 6 * n_aggregates square) and P as a sparse matrix."""
+    V = agg.shape[0]
+    nc = int(agg.max()) + 1
+    rows = (np.arange(V)[:, None, None] * 6 + np.arange(6)[None, :, None] + 0 * np.arange(6)[None, None, :]).ravel()
+    cols = (agg[:, None, None] * 6 + 0 * np.arange(6)[None, :, None] + np.arange(6)[None, None, :]).ravel()
+    Pm = sp.csr_matrix((Pi.ravel(), (rows, cols)), shape=(6 * V, 6 * nc))
+    Hc = np.asarray((Pm.T @ H @ Pm).todense())
+    # aggregates made of fixed poses only have a zero block: give them a unit diagonal
+    dead = np.abs(Hc).sum(axis=1) == 0.0
+    Hc[dead, dead] = 1.0
+    return Hc, Pm
+
+
+def pcg(H, b, apply_M, rtol=1e-10, maxiter=20000):
+    """Preconditioned conjugate gradients for H x = -b; returns (x, iterations, relative residual)."""
+    n = b.shape[0]
+    x = np.zeros(n)
+    r = -b.copy()
+    z = apply_M(r)
+    p = z.copy()
+    rz = r @ z
+    b2 = b @ b
+    rel = 1.0
+    for it in range(1, maxiter + 1):
+        Ap = H @ p
+        a = rz / (p @ Ap)
+        x += a * p
+        r -= a * Ap
+        rel = np.sqrt((r @ r) / b2) if b2 > 0 else 0.0
+        if rel < rtol:
+            return x, it, rel
+        z = apply_M(r)
+        rz2 = r @ z
+        p = z + (rz2 / rz) * p
+        rz = rz2
+    return x, maxiter, rel
+
+
+def solve_two_level(H, b, poses, fixed, aggregate_size=32, rtol=1e-10, maxiter=20000):
+    """PCG with M^-1 = blockdiag(H)^-1 + P (P^T H P)^-1 P^T (additive two-level Schwarz)."""
+    import scipy.linalg as sla
+    V = np.asarray(poses).shape[0]
+    H = H.tocsr()
+    D = np.stack([H[6 * v:6 * v + 6, 6 * v:6 * v + 6].toarray() for v in range(V)])
+    Dinv = np.linalg.inv(D)
+    agg, Pi = rigid_prolongation(poses, fixed, aggregate_size)
+    Hc, Pm = coarse_matrix(H, agg, Pi)
+    cho = sla.cho_factor(Hc + 1e-12 * np.trace(Hc) / Hc.shape[0] * np.eye(Hc.shape[0]))
+
+    def apply_M(r):
+        return np.einsum("vij,vj->vi", Dinv, r.reshape(V, 6)).ravel() + Pm @ sla.cho_solve(cho, Pm.T @ r)
+
+    return pcg(H, b, apply_M, rtol, maxiter)
+
+
+def solve_block_jacobi(H, b, n_vars, rtol=1e-10, maxiter=20000):
+    H = H.tocsr()
+    D = np.stack([H[6 * v:6 * v + 6, 6 * v:6 * v + 6].toarray() for v in range(n_vars)])
+    Dinv = np.linalg.inv(D)
+    return pcg(H, b, lambda r: np.einsum("vij,vj->vi", Dinv, r.reshape(n_vars, 6)).ravel(), rtol, maxiter)
+
+
 def gn_step(poses, ij, Z, Omega, fixed, solver="direct"):
     """One Gauss-Newton iteration; returns (new poses, stats)."""
     H, b, chi, _ = linearize(poses, ij, Z, Omega, fixed)
     if solver == "direct":
         dx = spla.spsolve(H.tocsc(), -b)
+    elif solver == "two_level":
+        dx, _, _ = solve_two_level(H, b, poses, fixed)
     else:
         Minv = spla.LinearOperator(H.shape, matvec=lambda x: x / H.diagonal())
         dx, info = spla.cg(H, -b, rtol=1e-12, maxiter=20000, M=Minv)
