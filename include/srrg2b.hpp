@@ -1,0 +1,399 @@
+// srrg2b.hpp -- header-only C++17 host side above the C ABI of libsrrg2b.so (include/srrg2b.h).
+//
+// The reference is compiled C++ whose dependencies (srrg2_core, srrg2_solver, Eigen, catkin) are not
+// available where this repository is built, so the reference-side adapter classes of INTEGRATION.md
+// cannot be compiled here.  This header is the same host logic WITHOUT those dependencies: classes
+// that mirror the reference's plugin interfaces for the hot path -- same method names, argument
+// meaning, defaults and error behaviour -- on plain STL types, so that a test written against them
+// reads like the reference's own:
+//
+//   CorrespondenceFinderB200<Dim>   CorrespondenceFinder_  (R/registration/correspondence_finder.h:41-124)
+//   MultiAlignerB200<Dim>           Aligner_ / MultiAlignerBase_ (R/registration/aligners/aligner.h:46-127,
+//                                   multi_aligner.h:34-66) with its slice processors
+//                                   (aligner_slice_processor.h:56-66, aligner_slice_odometry_prior.h:9-45)
+//   PoseGraphSolverB200             Solver as used by MultiGraphSLAM_::optimize()
+//                                   (R/system/multi_graph_slam_impl.cpp:299-317)
+//
+// R/ = srrg2_slam_interfaces/src/srrg2_slam_interfaces/ of the reference tree.  Misconfiguration throws
+// std::runtime_error (aligner_slice_processor_impl.cpp:13-16); numeric outcomes are status values
+// (aligner.h:23-28).  There is no CPU fallback: without a CUDA device the constructors throw.
+#ifndef SRRG2B_HPP
+#define SRRG2B_HPP
+#include <array>
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "srrg2b.h"
+
+namespace srrg2b {
+
+// srrg2_core::Correspondence(fixed_idx, moving_idx, response): constructor order proven by
+// R/registration/loop_detector/multi_loop_detector_hbst_impl.cpp:183-191
+struct Correspondence {
+  int fixed_idx = -1, moving_idx = -1;
+  float response = 0.f;
+  Correspondence() = default;
+  Correspondence(int f, int m, float r) : fixed_idx(f), moving_idx(m), response(r) {}
+};
+using CorrespondenceVector = std::vector<Correspondence>;
+
+// PointNormal{2,3}fVectorCloud flattened: coordinates n x Dim, optional normals, optional validity
+template <int Dim>
+struct PointNormalCloud {
+  std::vector<float> coordinates, normals;
+  std::vector<uint8_t> valid;  // point.status == Valid; empty = all valid
+  size_t size() const { return coordinates.size() / Dim; }
+};
+
+// Isometry{2,3}f as the row-major (Dim+1) x (Dim+1) matrix the C ABI documents
+template <int Dim>
+struct Isometry {
+  static constexpr int N = (Dim + 1) * (Dim + 1);
+  std::array<float, N> m;
+  static Isometry Identity() {
+    Isometry T;
+    T.m.fill(0.f);
+    for (int i = 0; i <= Dim; ++i) T.m[i * (Dim + 1) + i] = 1.f;
+    return T;
+  }
+  const float* data() const { return m.data(); }
+  float* data() { return m.data(); }
+};
+
+// srrg2_solver::IterationStats fields the reference reads (aligner_termination_criteria_impl.cpp:30-32)
+using IterationStats = srrg2b_iter_stats;
+using IterationStatsVector = std::vector<IterationStats>;
+
+// AlignerBase::Status, aligner.h:23-28 (same numeric values)
+enum class AlignerStatus { Success = 0, NotEnoughCorrespondences = 1, NotEnoughInliers = 2, Fail = 3 };
+
+// one CUDA context (device, stream, resident clouds); shared by the modules built on it
+class Context {
+public:
+  explicit Context(int dim, int device = 0) {
+    const int rc = srrg2b_ctx_create(dim, device, &_ctx);
+    if (rc != SRRG2B_OK)
+      throw std::runtime_error(rc == SRRG2B_ERR_CUDA ? "srrg2b::Context|no usable CUDA device (there is no CPU fallback)"
+                                                     : "srrg2b::Context|invalid arguments");
+  }
+  ~Context() { srrg2b_ctx_destroy(_ctx); }
+  Context(const Context&) = delete;
+  Context& operator=(const Context&) = delete;
+  srrg2b_ctx* get() const { return _ctx; }
+  void check(int rc, const char* who) const {
+    if (rc != SRRG2B_OK) throw std::runtime_error(std::string(who) + "|" + srrg2b_last_error(_ctx));
+  }
+
+private:
+  srrg2b_ctx* _ctx = nullptr;
+};
+using ContextPtr = std::shared_ptr<Context>;
+
+namespace detail {
+template <int Dim>
+inline srrg2b_cloud describe(const PointNormalCloud<Dim>& c) {
+  if (!c.normals.empty() && c.normals.size() != c.coordinates.size())
+    throw std::runtime_error("srrg2b|normals and coordinates differ in size");
+  if (!c.valid.empty() && c.valid.size() != c.size()) throw std::runtime_error("srrg2b|validity mask has the wrong size");
+  srrg2b_cloud d;
+  std::memset(&d, 0, sizeof(d));
+  d.coords = c.coordinates.data();
+  d.normals = c.normals.empty() ? nullptr : c.normals.data();
+  d.valid = c.valid.empty() ? nullptr : c.valid.data();
+  d.n = (int64_t) c.size();
+  return d;
+}
+template <int Dim>
+inline void embed(const Isometry<Dim>& T, float* out16) {  // the slice descriptors always carry 16 floats
+  std::memset(out16, 0, 16 * sizeof(float));
+  std::memcpy(out16, T.data(), sizeof(float) * Isometry<Dim>::N);
+}
+}  // namespace detail
+
+// ---------------------------------------------------------------------------------------------
+// CorrespondenceFinder_ (a3): exact nearest neighbour within max_distance + normal gate
+// ---------------------------------------------------------------------------------------------
+template <int Dim>
+class CorrespondenceFinderB200 {
+public:
+  using CloudType = PointNormalCloud<Dim>;
+  using EstimateType = Isometry<Dim>;
+  float param_max_distance_m = 0.5f;  // kd-tree finder of srrg2_laser_slam_2d
+  float param_normal_cos = 0.8f;
+
+  explicit CorrespondenceFinderB200(ContextPtr ctx, int slice_id = 0) : _ctx(std::move(ctx)), _slice(slice_id) {}
+  // correspondence_finder.h:41-56
+  void setCorrespondences(CorrespondenceVector* c) { _correspondences = c; }
+  // correspondence_finder.h:80-91: change detection is by flag, not by content
+  void setFixed(const CloudType* f) { _fixed = f; _fixed_changed_flag = true; }
+  void setMoving(const CloudType* m) { _moving = m; _moving_changed_flag = true; }
+  // correspondence_finder.h:111-114
+  void setLocalMapInSensor(const EstimateType& T) { _local_map_in_sensor = T; }
+
+  void compute() {  // correspondence_finder.h:56
+    if (!_fixed || !_moving) throw std::runtime_error("CorrespondenceFinderB200::compute|fixed or moving not set");
+    if (!_correspondences) throw std::runtime_error("CorrespondenceFinderB200::compute|correspondence vector not set");
+    if (_fixed_changed_flag) {
+      const srrg2b_cloud d = detail::describe(*_fixed);
+      _ctx->check(srrg2b_set_cloud(_ctx->get(), SRRG2B_FIXED, _slice, &d), "CorrespondenceFinderB200::setFixed");
+      _fixed_changed_flag = false;
+    }
+    if (_moving_changed_flag) {
+      const srrg2b_cloud d = detail::describe(*_moving);
+      _ctx->check(srrg2b_set_cloud(_ctx->get(), SRRG2B_MOVING, _slice, &d), "CorrespondenceFinderB200::setMoving");
+      _moving_changed_flag = false;
+    }
+    srrg2b_finder_params fp;
+    std::memset(&fp, 0, sizeof(fp));
+    fp.kind = SRRG2B_FINDER_NN;
+    fp.max_distance = param_max_distance_m;
+    fp.normal_cos = param_normal_cos;
+    const size_t n = _moving->size();
+    std::vector<int32_t> fi(n), mi(n);
+    std::vector<float> rs(n);
+    int64_t m = 0;
+    _ctx->check(srrg2b_find_correspondences(_ctx->get(), _slice, _local_map_in_sensor.data(), &fp, fi.data(), mi.data(),
+                                            rs.data(), &m),
+                "CorrespondenceFinderB200::compute");
+    _correspondences->clear();
+    _correspondences->reserve((size_t) m);
+    for (int64_t k = 0; k < m; ++k) _correspondences->emplace_back(fi[(size_t) k], mi[(size_t) k], rs[(size_t) k]);
+  }
+
+private:
+  ContextPtr _ctx;
+  int _slice;
+  const CloudType* _fixed = nullptr;
+  const CloudType* _moving = nullptr;
+  bool _fixed_changed_flag = false, _moving_changed_flag = false;
+  EstimateType _local_map_in_sensor = EstimateType::Identity();
+  CorrespondenceVector* _correspondences = nullptr;
+};
+
+// ---------------------------------------------------------------------------------------------
+// MultiAlignerBase_ (a1-a9, a11): the whole compute() on the device
+// ---------------------------------------------------------------------------------------------
+template <int Dim>
+class MultiAlignerB200 {
+public:
+  using CloudType = PointNormalCloud<Dim>;
+  using EstimateType = Isometry<Dim>;
+
+  // AlignerSliceProcessor_ (points): aligner_slice_processor.h:56-66,142-150
+  struct SliceProcessor {
+    float finder_max_distance_m = 0.5f, finder_normal_cos = 0.8f;
+    int factor = SRRG2B_FACTOR_PLANE;
+    int robustifier = SRRG2B_ROB_NONE;
+    float robustifier_chi_threshold = 1.f;  // RobustifierBase::param_chi_threshold
+    float info_point = 1.f, info_normal = 1.f;
+    int param_min_num_correspondences = 0;
+    EstimateType robot_in_sensor = EstimateType::Identity();
+    const CloudType* fixed = nullptr;
+    const CloudType* moving = nullptr;
+    bool fixed_changed = false, moving_changed = false;
+    CorrespondenceVector correspondences;  // owned by the slice (aligner_slice_processor.h:156)
+  };
+  // AlignerSliceOdom{2,3}DPrior: aligner_slice_odometry_prior.h:9-45 (2D default information 1e2, 3D 1)
+  struct PriorSliceProcessor {
+    EstimateType measurement = EstimateType::Identity();
+    std::array<float, 6> param_diagonal_info_matrix;
+    PriorSliceProcessor() { param_diagonal_info_matrix.fill(Dim == 2 ? 100.f : 1.f); }
+  };
+  // AlignerTerminationCriteriaStandard_: aligner_termination_criteria.h:40-56
+  struct TerminationCriteria {
+    int param_window_size = 5, param_num_correspondences_range = 20, param_num_inliers_range = 20,
+        param_num_outliers_range = 20;
+    float param_chi_epsilon = 0.2f;
+  };
+
+  // aligner.h:30-35, multi_aligner.h:45-57 (same names and defaults)
+  int param_max_iterations = 10;
+  int param_min_num_inliers = 10;
+  bool param_enable_inlier_only_runs = false;
+  bool param_keep_only_inlier_correspondences = false;
+  std::shared_ptr<TerminationCriteria> param_termination_criteria;  // null: run all iterations
+  int variable = SRRG2B_VAR_SE3_QUAT_RIGHT;                         // MultiAligner3DQR / MultiAligner3D
+
+  explicit MultiAlignerB200(ContextPtr ctx) : _ctx(std::move(ctx)) {}
+
+  // param_slice_processors, in order (multi_aligner.h:34-37)
+  int addSliceProcessor(const SliceProcessor& s) {
+    _order.push_back({false, (int) _slices.size()});
+    _slices.push_back(s);
+    return (int) _order.size() - 1;
+  }
+  int addPriorSliceProcessor(const PriorSliceProcessor& p) {
+    _order.push_back({true, (int) _priors.size()});
+    _priors.push_back(p);
+    return (int) _order.size() - 1;
+  }
+  SliceProcessor& sliceProcessor(int k) { return _slices.at((size_t) entry(k, false).index); }
+  PriorSliceProcessor& priorSliceProcessor(int k) { return _priors.at((size_t) entry(k, true).index); }
+  // Aligner_::setFixed / setMoving (aligner.h:46-60), per slice
+  void setFixed(int k, const CloudType* c) { auto& s = sliceProcessor(k); s.fixed = c; s.fixed_changed = true; }
+  void setMoving(int k, const CloudType* c) { auto& s = sliceProcessor(k); s.moving = c; s.moving_changed = true; }
+  void setMovingInFixed(const EstimateType& T) { _moving_in_fixed = T; }
+  const EstimateType& movingInFixed() const { return _moving_in_fixed; }
+  AlignerStatus status() const { return _status; }
+  const IterationStatsVector& iterationStats() const { return _iteration_stats; }
+  int numCorrespondences() const {
+    int n = 0;
+    for (const auto& s : _slices) n += (int) s.correspondences.size();
+    return n;
+  }
+
+  void compute() {  // multi_aligner_impl.cpp:46-95
+    if (_order.empty()) throw std::runtime_error("MultiAlignerB200::compute|no slice processors");
+    if ((int) _order.size() > SRRG2B_MAX_SLICES) throw std::runtime_error("MultiAlignerB200::compute|too many slices");
+    std::vector<srrg2b_slice> sl(_order.size());
+    for (size_t k = 0; k < _order.size(); ++k) {
+      srrg2b_slice& d = sl[k];
+      std::memset(&d, 0, sizeof(d));
+      detail::embed(EstimateType::Identity(), d.robot_in_sensor);
+      detail::embed(EstimateType::Identity(), d.prior_measurement);
+      if (_order[k].prior) {
+        const PriorSliceProcessor& p = _priors[(size_t) _order[k].index];
+        d.kind = SRRG2B_SLICE_PRIOR;
+        detail::embed(p.measurement, d.prior_measurement);
+        for (int i = 0; i < 6; ++i) d.prior_info_diag[i] = p.param_diagonal_info_matrix[(size_t) i];
+        continue;
+      }
+      SliceProcessor& s = _slices[(size_t) _order[k].index];
+      if (!s.fixed || !s.moving) throw std::runtime_error("MultiAlignerB200::compute|slice without fixed or moving");
+      d.kind = SRRG2B_SLICE_POINTS;
+      d.slice_id = (int) k;
+      d.min_num_correspondences = s.param_min_num_correspondences;
+      detail::embed(s.robot_in_sensor, d.robot_in_sensor);
+      d.finder.kind = SRRG2B_FINDER_NN;
+      d.finder.max_distance = s.finder_max_distance_m;
+      d.finder.normal_cos = s.finder_normal_cos;
+      d.factor.factor = s.factor;
+      d.factor.robustifier = s.robustifier;
+      d.factor.chi_threshold = s.robustifier_chi_threshold;
+      d.factor.info_point = s.info_point;
+      d.factor.info_normal = s.info_normal;
+      if (s.fixed_changed) {  // fixed first: its index build overlaps the upload of the moving cloud
+        const srrg2b_cloud c = detail::describe(*s.fixed);
+        _ctx->check(srrg2b_set_cloud(_ctx->get(), SRRG2B_FIXED, (int) k, &c), "MultiAlignerB200::setFixed");
+        s.fixed_changed = false;
+      }
+      if (s.moving_changed) {
+        const srrg2b_cloud c = detail::describe(*s.moving);
+        _ctx->check(srrg2b_set_cloud(_ctx->get(), SRRG2B_MOVING, (int) k, &c), "MultiAlignerB200::setMoving");
+        s.moving_changed = false;
+      }
+    }
+    srrg2b_aligner_params ap;
+    std::memset(&ap, 0, sizeof(ap));
+    ap.variable = variable;
+    ap.max_iterations = param_max_iterations;
+    ap.min_num_inliers = param_min_num_inliers;
+    ap.enable_inlier_only_runs = param_enable_inlier_only_runs ? 1 : 0;
+    ap.keep_only_inlier_correspondences = param_keep_only_inlier_correspondences ? 1 : 0;
+    const TerminationCriteria tc = param_termination_criteria ? *param_termination_criteria : TerminationCriteria();
+    ap.use_termination_criteria = param_termination_criteria ? 1 : 0;
+    ap.window_size = tc.param_window_size;
+    ap.num_correspondences_range = tc.param_num_correspondences_range;
+    ap.num_inliers_range = tc.param_num_inliers_range;
+    ap.num_outliers_range = tc.param_num_outliers_range;
+    ap.chi_epsilon = tc.param_chi_epsilon;
+    std::vector<srrg2b_iter_stats> st(256);
+    int32_t n_stats = (int32_t) st.size(), status = SRRG2B_ALIGNER_FAIL;
+    EstimateType T = _moving_in_fixed;
+    _ctx->check(srrg2b_icp_run(_ctx->get(), (int) sl.size(), sl.data(), &ap, T.data(), st.data(), &n_stats, &status),
+                "MultiAlignerB200::compute");
+    _moving_in_fixed = T;
+    _status = static_cast<AlignerStatus>(status);
+    st.resize((size_t) std::min<int32_t>(n_stats, (int32_t) st.size()));
+    _iteration_stats = st;
+    // storeCorrespondences() (aligner_slice_processor_impl.cpp:50-74): the slices keep the final lists
+    for (size_t k = 0; k < _order.size(); ++k) {
+      if (_order[k].prior) continue;
+      SliceProcessor& s = _slices[(size_t) _order[k].index];
+      const size_t n = s.moving->size();
+      std::vector<int32_t> fi(n), mi(n);
+      std::vector<float> rs(n);
+      int64_t m = 0;
+      _ctx->check(srrg2b_get_correspondences(_ctx->get(), (int) k, fi.data(), mi.data(), rs.data(), &m),
+                  "MultiAlignerB200::storeCorrespondences");
+      s.correspondences.clear();
+      s.correspondences.reserve((size_t) m);
+      for (int64_t j = 0; j < m; ++j) s.correspondences.emplace_back(fi[(size_t) j], mi[(size_t) j], rs[(size_t) j]);
+    }
+  }
+
+private:
+  struct Entry {
+    bool prior;
+    int index;
+  };
+  const Entry& entry(int k, bool prior) const {
+    const Entry& e = _order.at((size_t) k);
+    if (e.prior != prior) throw std::runtime_error("MultiAlignerB200|slice has the other kind");
+    return e;
+  }
+  ContextPtr _ctx;
+  std::vector<Entry> _order;
+  std::vector<SliceProcessor> _slices;
+  std::vector<PriorSliceProcessor> _priors;
+  EstimateType _moving_in_fixed = EstimateType::Identity();
+  AlignerStatus _status = AlignerStatus::Fail;
+  IterationStatsVector _iteration_stats;
+};
+
+// ---------------------------------------------------------------------------------------------
+// Solver on a pose graph (a10): SE3PosePoseGeodesicErrorFactor between VariableSE3QuaternionRightAD
+// ---------------------------------------------------------------------------------------------
+class PoseGraphSolverB200 {
+public:
+  int param_max_iterations = 10;      // Solver::param_max_iterations
+  double param_dx_epsilon = 1e-6;     // stop when the largest perturbation component falls below
+  int param_max_cg_iterations = 0;    // 0 = library default
+  double param_cg_tolerance = 0.0;    // 0 = library default
+  enum Status { Error = 0, Success = 1 };
+
+  explicit PoseGraphSolverB200(ContextPtr ctx) : _ctx(std::move(ctx)) {}
+
+  // setGraph(): poses row-major 4x4 each, fixed mask, factor pairs (i, j), measurements 4x4, information 6x6
+  void setGraph(std::vector<float> poses16, std::vector<uint8_t> fixed, std::vector<int32_t> ij,
+                std::vector<float> Z16, std::vector<float> Omega36) {
+    _poses = std::move(poses16); _fixed = std::move(fixed); _ij = std::move(ij); _Z = std::move(Z16); _Omega = std::move(Omega36);
+    if (_poses.size() % 16 || _fixed.size() != _poses.size() / 16 || _ij.size() % 2 || _Z.size() != _ij.size() / 2 * 16 ||
+        _Omega.size() != _ij.size() / 2 * 36)
+      throw std::runtime_error("PoseGraphSolverB200::setGraph|inconsistent array sizes");
+  }
+  void compute() {
+    _ctx->check(srrg2b_pgo_upload(_ctx->get(), (int64_t) _fixed.size(), _poses.data(), _fixed.data(), (int64_t) _ij.size() / 2,
+                                  _ij.data(), _Z.data(), _Omega.data()),
+                "PoseGraphSolverB200::compute");
+    _stats.clear();
+    _status = Error;
+    for (int it = 0; it < param_max_iterations; ++it) {
+      srrg2b_pgo_stats st;
+      _ctx->check(srrg2b_pgo_iterate(_ctx->get(), param_max_cg_iterations, param_cg_tolerance, &st),
+                  "PoseGraphSolverB200::compute");
+      _stats.push_back(st);
+      if (st.dx_norm_inf < param_dx_epsilon) break;
+    }
+    _ctx->check(srrg2b_pgo_download(_ctx->get(), _poses.data()), "PoseGraphSolverB200::compute");
+    _status = Success;
+  }
+  Status status() const { return _status; }
+  const std::vector<srrg2b_pgo_stats>& iterationStats() const { return _stats; }
+  const std::vector<float>& poses() const { return _poses; }
+
+private:
+  ContextPtr _ctx;
+  std::vector<float> _poses, _Z, _Omega;
+  std::vector<uint8_t> _fixed;
+  std::vector<int32_t> _ij;
+  std::vector<srrg2b_pgo_stats> _stats;
+  Status _status = Error;
+};
+
+}  // namespace srrg2b
+#endif
