@@ -210,3 +210,42 @@ def test_status_paths(oracle):
     r = oracle.icp_run(3, [oracle.make_slice(F, M, None, fp, fa), pr],
                        oracle.aligner_params(max_iterations=3, min_num_inliers=0), np.eye(4))
     assert r["status"] == 0 and len(r["stats"]) == 3 and r["stats"][0]["num_correspondences"] == 1
+
+
+def _kabsch(m, f):
+    """Least-squares rigid transform T (R, t) minimising sum |R m + t - f|^2 (Kabsch / Umeyama, SVD)."""
+    mc, fc = m.mean(axis=0), f.mean(axis=0)
+    U, _, Vt = np.linalg.svd((m - mc).T @ (f - fc))
+    D = np.eye(m.shape[1])
+    D[-1, -1] = np.sign(np.linalg.det(Vt.T @ U.T))
+    R = Vt.T @ D @ U.T
+    return R, fc - R @ mc
+
+
+@pytest.mark.parametrize("dim,variable", [(3, 0), (3, 1), (2, 0)])
+def test_unrobustified_p2p_converges_to_the_closed_form_alignment(oracle, dim, variable):
+    """Independent cross-check of the whole loop (finder -> P2P factor -> GN step -> box-plus), SURVEY 8c:
+    with no robustifier the fixed point of the iteration is the least-squares rigid alignment of the
+    final correspondences, which has a closed form (Kabsch / Umeyama)."""
+    rng = np.random.default_rng(12)
+    n = 1500
+    fixed = rng.uniform(-5, 5, size=(n, dim))
+    if dim == 3:
+        T_star = syn.iso3([0.04, -0.03, 0.05], np.deg2rad([1.0, -0.8, 1.5]))
+    else:
+        T_star = syn.iso2(0.04, -0.03, np.deg2rad(1.5))
+    Ti = syn.inv_iso(T_star)
+    moving = (Ti[:dim, :dim] @ fixed.T).T + Ti[:dim, dim] + rng.normal(scale=0.003, size=(n, dim))
+    F = oracle.CloudRef(fixed.astype(np.float32))
+    M = oracle.CloudRef(moving.astype(np.float32))
+    fp = oracle.finder_params(0.5, -2.0)  # no normals: the gate is off
+    fa = oracle.factor_params(oracle.FACTOR_P2P, oracle.ROB_NONE)
+    r = oracle.icp_run(dim, [oracle.make_slice(F, M, None, fp, fa, dim=dim)],
+                       oracle.aligner_params(max_iterations=40, min_num_inliers=10, variable=variable), np.eye(dim + 1))
+    assert r["status"] == 0
+    fi, mi, _ = r["correspondences"][0]
+    assert fi.size > 0.95 * n and np.mean(fi == mi) > 0.95  # the points are far apart: the pairs are recovered
+    R, t = _kabsch(moving.astype(np.float32).astype(np.float64)[mi], fixed.astype(np.float32).astype(np.float64)[fi])
+    T = np.asarray(r["T"], dtype=np.float64)
+    assert np.abs(T[:dim, :dim] - R).max() < 2e-5 and np.abs(T[:dim, dim] - t).max() < 2e-4
+    assert np.abs(T[:dim, :dim] - T_star[:dim, :dim]).max() < 2e-3 and np.abs(T[:dim, dim] - T_star[:dim, dim]).max() < 5e-3
