@@ -170,7 +170,7 @@ def run_reference(args):
     n = args.points
     threads = os.cpu_count() or 1
     d = syn.make_icp3d(n, n, seed=2)
-    iters_per_step = 2
+    iters_per_step = ICP_ITERS  # one step = the whole 20-iteration _runSolver, like the graft arm's step
     for _ in range(max(0, min(args.warmup, 1))):
         cpu_iterations(O, d, threads, 1)
     total, t_build = 0.0, 0.0
@@ -318,10 +318,12 @@ def run_graft(args):
             from oracle import oracle as O
             os.sched_setaffinity(0, all_cpus)  # the CPU baseline may use every host core
             threads = os.cpu_count() or 1
-            dt, tb = cpu_iterations(O, d, threads, 3)
-            line["cpu_baseline"] = {"value": 3 / dt, "unit": UNIT, "cores": threads, "kind": "port",
-                                    "sample": "3 _runSolver iterations at the full %d x %d size, kd-tree prebuilt "
-                                              "(build %.2f s not counted), oracle with OpenMP" % (n, n, tb)}
+            dt, tb = cpu_iterations(O, d, threads, ICP_ITERS)
+            line["cpu_baseline"] = {"value": ICP_ITERS / dt, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": "one whole step: %d _runSolver iterations from the identity guess at the "
+                                              "full %d x %d size, kd-tree prebuilt (build %.2f s not counted), "
+                                              "oracle/srrg2b_oracle.c with OpenMP on all host cores"
+                                              % (ICP_ITERS, n, n, tb)}
         else:
             line["cpu_baseline"] = None
         print(json.dumps(line))
