@@ -56,7 +56,8 @@ class IterStats(C.Structure):
     _fields_ = [("iteration", C.c_int32), ("solver_status", C.c_int32),
                 ("num_inliers", C.c_int64), ("num_outliers", C.c_int64),
                 ("num_suppressed", C.c_int64), ("num_correspondences", C.c_int64),
-                ("chi_inliers", C.c_double), ("chi_outliers", C.c_double)]
+                ("chi_inliers", C.c_double), ("chi_outliers", C.c_double),
+                ("num_saturated", C.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -76,7 +77,7 @@ class CorrOut(C.Structure):
 
 
 class Scales(C.Structure):
-    _fields_ = [("k", C.c_int32 * 7)]
+    _fields_ = [("k", C.c_int32 * 7), ("err_bound", C.c_float)]
 
 
 ACC_SLOTS = 40
@@ -97,15 +98,19 @@ def lib():
                                   C.POINTER(FinderParams), C.c_void_p, C.c_void_p]
         _lib.orc_linearize.argtypes = [C.c_int, C.c_int, C.POINTER(Cloud), C.POINTER(Cloud), C.c_void_p,
                                        C.c_void_p, C.POINTER(FinderParams), C.POINTER(FactorParams),
-                                       C.c_int64, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
-                                       C.POINTER(IterStats), C.c_void_p, C.c_void_p]
+                                       C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.POINTER(IterStats), C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.orc_icp_run.argtypes = [C.c_int, C.c_int, C.POINTER(Slice), C.POINTER(AlignerParams),
                                      C.c_void_p, C.POINTER(IterStats), C.POINTER(C.c_int32),
                                      C.POINTER(C.c_int32), C.POINTER(CorrOut), C.c_int]
-        _lib.orc_scales.argtypes = [C.c_int, C.c_int64, C.c_float, C.POINTER(FinderParams),
+        _lib.orc_scales.argtypes = [C.c_int, C.c_int, C.c_float, C.c_float, C.POINTER(FinderParams),
                                     C.POINTER(FactorParams), C.POINTER(Scales)]
         _lib.orc_coord_bound.restype = C.c_float
         _lib.orc_coord_bound.argtypes = [C.c_int, C.POINTER(Cloud)]
+        _lib.orc_radius_bound2.restype = C.c_float
+        _lib.orc_radius_bound2.argtypes = [C.c_int, C.POINTER(Cloud)]
+        _lib.orc_normal_bound2.restype = C.c_float
+        _lib.orc_normal_bound2.argtypes = [C.c_int, C.POINTER(Cloud)]
         _lib.orc_sincos.argtypes = [C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         _lib.orc_atan2.restype = C.c_double
         _lib.orc_atan2.argtypes = [C.c_double, C.c_double]
@@ -180,8 +185,10 @@ def find(index, fixed, moving, S, fp):
     return fidx, resp
 
 
-def linearize(fixed, moving, fidx, S, fp, fa, variable=VAR_SE3_QUAT_RIGHT, n_global=0, want_status=True,
-              coord_bound=0.0):
+def linearize(fixed, moving, fidx, S, fp, fa, variable=VAR_SE3_QUAT_RIGHT, want_status=True,
+              radius_bound2=0.0, normal_bound2=0.0, want_plain=False):
+    """plain (want_plain): un-quantised fp64 sums of the same fp32 terms -- H upper triangle (21 | 6), b (6 | 3)
+    packed one after the other, chi_inliers at [27], chi_outliers at [28]."""
     dim = fixed.dim
     P = 6 if dim == 3 else 3
     S = _f32(S).reshape(-1)
@@ -192,11 +199,13 @@ def linearize(fixed, moving, fidx, S, fp, fa, variable=VAR_SE3_QUAT_RIGHT, n_glo
     st = IterStats()
     status = np.empty(moving.n, dtype=np.uint8) if want_status else None
     chi = np.empty(moving.n, dtype=np.float32) if want_status else None
+    plain = np.zeros(32, dtype=np.float64) if want_plain else None
     rc = lib().orc_linearize(dim, variable, C.byref(fixed.c), C.byref(moving.c), fidx.ctypes.data,
-                             S.ctypes.data, C.byref(fp), C.byref(fa), n_global, coord_bound, acc.ctypes.data,
-                             H.ctypes.data, b.ctypes.data, C.byref(st), _ptr(status), _ptr(chi))
+                             S.ctypes.data, C.byref(fp), C.byref(fa), radius_bound2, normal_bound2,
+                             acc.ctypes.data, H.ctypes.data, b.ctypes.data, C.byref(st), _ptr(status), _ptr(chi),
+                             _ptr(plain))
     assert rc == 0
-    return dict(acc=acc, H=H, b=b, stats=st.as_dict(), status=status, chi=chi)
+    return dict(acc=acc, H=H, b=b, stats=st.as_dict(), status=status, chi=chi, plain=plain)
 
 
 def make_slice(fixed=None, moving=None, robot_in_sensor=None, fp=None, fa=None, min_num_correspondences=0,
@@ -264,10 +273,18 @@ def icp_run(dim, slices, ap, T0, nn_method=NN_KDTREE, want_correspondences=True,
                 correspondences=corr)
 
 
-def scales(dim, n_global, coord_bound, fp, fa):
+def scales(dim, variable, radius_bound2, fp, fa, normal_bound2=1.0):
     s = Scales()
-    lib().orc_scales(dim, n_global, coord_bound, C.byref(fp), C.byref(fa), C.byref(s))
+    lib().orc_scales(dim, variable, radius_bound2, normal_bound2, C.byref(fp), C.byref(fa), C.byref(s))
     return tuple(s.k)
+
+
+def radius_bound2(cloud):
+    return float(lib().orc_radius_bound2(cloud.dim, C.byref(cloud.c)))
+
+
+def normal_bound2(cloud):
+    return float(lib().orc_normal_bound2(cloud.dim, C.byref(cloud.c)))
 
 
 def solve_update(dim, variable, H, b, T):

@@ -17,7 +17,8 @@
  *   * per-term arithmetic is fp32 with an explicitly written operation order; every fused
  *     multiply-add is spelled fmaf(); compile with -ffp-contract=off so nothing else fuses;
  *   * every per-correspondence contribution to H, b, chi is converted to 64-bit fixed point
- *     (round(term * 2^k) by a saturating fp32 fma, see to_fix; k from orc_scales) and summed as integers: the sums are exact, hence
+ *     (rint(term * 2^k) by one fp32 fma, see to_fix; ranges k from orc_scales, derived from the data so that no
+ *     term can leave them) and summed as integers: the sums are exact, hence
  *     independent of summation order, thread count and GPU count;
  *   * the 6x6 / 3x3 solve, pose update and prior factors are fp64 with plain (unfused) operations
  *     and in-house sin/cos/atan2/log so that host libm differences cannot leak in.
@@ -724,31 +725,82 @@ float orc_coord_bound(int dim, const orc_cloud* moving) {
   return b;
 }
 
-/* Per-TERM magnitude bounds (log2) of everything that is accumulated, from global quantities only:
- *   translation columns of J : |entry| <= 2 (rotation-matrix entries / unit normals, one spare bit)
- *   rotation columns of J    : |entry| <= max(2, 4 |coord|_max)      -> Jb bits
- *   error rows               : |e| <= max(max_distance, 2)            -> eb bits
- *   information              : <= max(info_point, info_normal, 1)     -> wb bits,  <= 4 rows -> 2 bits
- * A term is stored as round(term * 2^k) with k = 21 - bound, so |term * 2^k| < 2^21 (terms are
- * clamped to the bound before rounding).  chi gets a second, 2^20 times finer, residual word. */
-int orc_scales(int dim, int64_t n_global, float coord_bound, const orc_finder_params* fp,
+/* max |n|^2 over the valid points of a cloud (0 without normals): the fixed-point ranges below are
+ * derived from the data, so that no accumulated term can leave its range */
+float orc_normal_bound2(int dim, const orc_cloud* c) {
+  float b = 0.f;
+  if (!c->normals) return 0.f;
+  for (int64_t i = 0; i < c->n; ++i) {
+    if (c->valid && !c->valid[i]) continue;
+    const float* n = c->normals + i * dim;
+    float v = n[0] * n[0];
+    v = fmaf(n[1], n[1], v);
+    if (dim == 3) v = fmaf(n[2], n[2], v);
+    if (v > b) b = v;
+  }
+  return b;
+}
+
+/* max |m|^2 over the valid points of the moving cloud (the rotation columns of J scale with it) */
+float orc_radius_bound2(int dim, const orc_cloud* c) {
+  float b = 0.f;
+  for (int64_t i = 0; i < c->n; ++i) {
+    if (c->valid && !c->valid[i]) continue;
+    const float* p = c->coords + i * dim;
+    float v = p[0] * p[0];
+    v = fmaf(p[1], p[1], v);
+    if (dim == 3) v = fmaf(p[2], p[2], v);
+    if (v > b) b = v;
+  }
+  return b;
+}
+
+/* Per-TERM magnitude bounds of everything that is accumulated, derived from the DATA (global quantities
+ * only), so that no term can leave its fixed-point range -- there is nothing to clamp:
+ *   nb = max(1, |n|_max)   normal norms of both clouds      rm = |m|_max   moving point norms
+ *   E  = max_distance (1 + 2^-10): a correspondence with |S m - f| > E is suppressed and counted as
+ *        saturated (cannot happen for finder output; guards externally supplied pairs)
+ *   Gt = nb (1 + 2^-10) >= |R^T n_f|,   Gr = c rm Gt >= |c m x a|   (c = 2 quaternion, 1 otherwise)
+ *   PLANE: H_tt <= ip Gt^2, H_tr <= ip Gt Gr, H_rr <= ip Gr^2 + in c^2 nb^2, e0 <= nb E,
+ *          b_t <= ip Gt nb E, b_r <= ip Gr nb E + in c nb Gt, chi <= ip (nb E)^2 + in (2 nb)^2
+ *   P2P:   H_tt <= ip, H_tr <= ip c rm, H_rr <= ip (c rm)^2, b_t <= ip E, b_r <= ip c rm E, chi <= ip E^2
+ * (robust weights are <= 1).  A term of class X is stored as rint(term * 2^k_X), k_X = 21 - ceil(log2(1.01 B_X)),
+ * so |term * 2^k| < 2^21.  chi gets a second, 2^20 times finer, residual word.  All fp32, this order. */
+int orc_scales(int dim, int variable, float radius_bound2, float normal_bound2, const orc_finder_params* fp,
                const orc_factor_params* fa, orc_scales_t* out) {
-  (void) dim; (void) n_global;
-  float jm = 4.f * coord_bound;
-  if (jm < 2.f) jm = 2.f;
-  const int Jb = ceil_log2f_(jm);
-  float wm = fa->info_point > fa->info_normal ? fa->info_point : fa->info_normal;
-  if (!(wm > 1.f)) wm = 1.f;
-  const int wb = ceil_log2f_(wm);
-  const float em = fp->max_distance > 2.f ? fp->max_distance : 2.f;
-  const int eb = ceil_log2f_(em);
-  out->k[ORC_K_HTT] = 21 - (2 + wb + 2);
-  out->k[ORC_K_HTR] = 21 - (2 + wb + 1 + Jb);
-  out->k[ORC_K_HRR] = 21 - (2 + wb + 2 * Jb);
-  out->k[ORC_K_BT] = 21 - (2 + wb + 1 + eb);
-  out->k[ORC_K_BR] = 21 - (2 + wb + Jb + eb);
-  out->k[ORC_K_CHI] = 21 - (2 + wb + 2 * eb);
+  const float c = (dim == 3 && variable == ORC_VAR_SE3_QUAT_RIGHT) ? 2.f : 1.f;
+  const float slack = 1.0009765625f;
+  float nb = sqrtf(normal_bound2);
+  if (!(nb > 1.f)) nb = 1.f;
+  const float rm = sqrtf(radius_bound2);
+  const float E = fp->max_distance * slack;
+  const float ip = fa->info_point, in_ = fa->info_normal;
+  float B[ORC_K_COUNT];
+  if (fa->factor == ORC_FACTOR_PLANE) {
+    const float Gt = nb * slack, Gr = (c * rm) * Gt, e0 = nb * E;
+    B[ORC_K_HTT] = (ip * Gt) * Gt;
+    B[ORC_K_HTR] = (ip * Gt) * Gr;
+    B[ORC_K_HRR] = (ip * Gr) * Gr + ((in_ * c) * c) * (nb * nb);
+    B[ORC_K_BT] = (ip * Gt) * e0;
+    B[ORC_K_BR] = (ip * Gr) * e0 + (in_ * c) * (nb * Gt);
+    B[ORC_K_CHI] = (ip * e0) * e0 + (in_ * 4.f) * (nb * nb);
+  } else {
+    const float Gr = c * rm;
+    B[ORC_K_HTT] = ip;
+    B[ORC_K_HTR] = ip * Gr;
+    B[ORC_K_HRR] = (ip * Gr) * Gr;
+    B[ORC_K_BT] = ip * E;
+    B[ORC_K_BR] = (ip * Gr) * E;
+    B[ORC_K_CHI] = (ip * E) * E;
+  }
+  for (int k = 0; k < ORC_K_CHI_LO; ++k) {
+    float v = B[k] * 1.01f;
+    if (!(v > 1e-30f)) v = 1e-30f;   /* degenerate inputs (empty cloud, zero information) */
+    if (!(v < 1e30f)) v = 1e30f;
+    out->k[k] = 21 - ceil_log2f_(v);
+  }
   out->k[ORC_K_CHI_LO] = out->k[ORC_K_CHI] + 20;
+  out->err_bound = E;
   return 0;
 }
 
@@ -756,16 +808,12 @@ int orc_scales(int dim, int64_t n_global, float coord_bound, const orc_finder_pa
 /* a5 -- per-correspondence linearisation (FactorCorrespondenceDriven_<F,...> inside            */
 /* Solver::compute(), reached from R/registration/aligners/multi_aligner_impl.cpp:112)          */
 /* ------------------------------------------------------------------------------------------ */
-/* Fixed-point value of one term with k fractional bits, |v| <= B = 2^(21-k), computed with the same two
- * fp32 operations as the GPU: t = clamp(fma(v, 2^(k-22), 0.5), 0, 1) maps [-B, B] onto [0, 1] (and
- * saturates everything else, NaN -> 0); u = t + 3 lies in [3, 4] where the fp32 spacing is 2^-22, one
- * unit of 2^-k of v; bits(u) - bits(3.5f) is the term in those units (ties to even). */
+/* Fixed-point value of one term with k fractional bits, |v| <= 2^(21-k): ONE fp32 operation,
+ * u = fma(v, 2^(k-22), 3.5) lies in [3, 4] where the fp32 spacing is 2^-22, i.e. one unit of 2^-k of v, so
+ * bits(u) - bits(3.5f) = rint(v * 2^k) (ties to even).  The ranges are guaranteed by orc_scales. */
 static inline int32_t to_fix(float v, int k) {
   const float s = ldexpf(1.f, k - 22);
-  float t = fmaf(v, s, 0.5f);
-  t = fminf(fmaxf(t, 0.f), 1.f);
-  if (!(t == t)) t = 0.f;
-  const float u = t + 3.0f;
+  const float u = fmaf(v, s, 3.5f);
   int32_t ui;
   memcpy(&ui, &u, 4);
   return ui - 0x40600000;
@@ -774,10 +822,7 @@ static inline int32_t to_fix(float v, int k) {
 /* chi as a (coarse, residual) pair: the residual of the coarse rounding is exact in fp32 */
 static inline void to_fix2(float v, int k_hi, int k_lo, int64_t* hi, int64_t* lo) {
   const float s = ldexpf(1.f, k_hi - 22), inv_s = ldexpf(1.f, 22 - k_hi);
-  float t = fmaf(v, s, 0.5f);
-  t = fminf(fmaxf(t, 0.f), 1.f);
-  if (!(t == t)) t = 0.f;
-  const float u = t + 3.0f;
+  const float u = fmaf(v, s, 3.5f);
   int32_t ui;
   memcpy(&ui, &u, 4);
   *hi += ui - 0x40600000;
@@ -814,99 +859,168 @@ static int robustify(int kind, float tau, float chi, float* w, float* rho) {
   }
 }
 
-/* builds error rows e[E], info w[E], Jacobian J[E][P]; returns E */
-static int build_rows(int dim, int variable, int factor, const float* S4, const float* m, const float* nm,
-                      const float* f, const float* nf, const float* q, const float* nq,
-                      float ip, float in_, float* e, float* om, float J[4][6]) {
-  const float rs = (dim == 3 && variable == ORC_VAR_SE3_QUAT_RIGHT) ? 2.f : 1.f;
-  float d[3] = {q[0] - f[0], q[1] - f[1], q[2] - f[2]};
-  if (dim == 3) {
-    if (factor == ORC_FACTOR_P2P) {
-      for (int r = 0; r < 3; ++r) {
-        const float* R = S4 + r * 4;
-        J[r][0] = R[0]; J[r][1] = R[1]; J[r][2] = R[2];
-        float t;
-        t = R[2] * m[1]; J[r][3] = -rs * fmaf(R[1], m[2], -t);
-        t = R[0] * m[2]; J[r][4] = -rs * fmaf(R[2], m[0], -t);
-        t = R[1] * m[0]; J[r][5] = -rs * fmaf(R[0], m[1], -t);
-        e[r] = d[r]; om[r] = ip;
-      }
-      return 3;
-    }
-    float a[3];
-    for (int c = 0; c < 3; ++c) {
-      float t = S4[0 * 4 + c] * nf[0];
-      t = fmaf(S4[1 * 4 + c], nf[1], t);
-      t = fmaf(S4[2 * 4 + c], nf[2], t);
-      a[c] = t;
-    }
-    float t;
-    J[0][0] = a[0]; J[0][1] = a[1]; J[0][2] = a[2];
-    t = m[2] * a[1]; J[0][3] = rs * fmaf(m[1], a[2], -t);
-    t = m[0] * a[2]; J[0][4] = rs * fmaf(m[2], a[0], -t);
-    t = m[1] * a[0]; J[0][5] = rs * fmaf(m[0], a[1], -t);
-    e[0] = dot3(nf, d); om[0] = ip;
-    for (int r = 0; r < 3; ++r) {
-      const float* R = S4 + r * 4;
-      J[r + 1][0] = 0.f; J[r + 1][1] = 0.f; J[r + 1][2] = 0.f;
-      t = R[2] * nm[1]; J[r + 1][3] = -rs * fmaf(R[1], nm[2], -t);
-      t = R[0] * nm[2]; J[r + 1][4] = -rs * fmaf(R[2], nm[0], -t);
-      t = R[1] * nm[0]; J[r + 1][5] = -rs * fmaf(R[0], nm[1], -t);
-      e[r + 1] = nq[r] - nf[r]; om[r + 1] = in_;
-    }
-    return 4;
-  }
-  /* dim == 2 */
+/* One correspondence: chi (before the robustifier) and the 21 | 6 upper-triangle entries of J^T Om J and
+ * the 6 | 3 entries of J^T Om e for unit robust weight scale w, in the REDUCED form that holds for a
+ * rotation matrix R (R^T R = I), right perturbation X <- X v2t(dx), c = rs (2: quaternion, 1: Euler / SE2):
+ *   P2P    e = q - f,  J = [R | -c R [m]x]
+ *          H = s [ I, -c [m]x ; ., c^2 (|m|^2 I - m m^T) ],  b = s [ r ; c m x r ],  r = R^T e,  s = w ip
+ *   PLANE  e = [ n_f^T (q - f) ; R n_m - n_f ],  J = [ a^T, c (m x a)^T ; 0, -c R [n_m]x ],  a = R^T n_f
+ *          g = [ a ; c m x a ],  H = s0 g g^T + [ 0, 0 ; 0, s1 c^2 (|n_m|^2 I - n_m n_m^T) ],
+ *          b = s0 e0 g + [ 0 ; s1 c (a x n_m) ],  s0 = w ip,  s1 = w in
+ * (2D: the analogous forms with the single rotation column R (-m_y, m_x)^T.)  Every fused multiply-add is
+ * an explicit fmaf; the CUDA kernels perform the same operations in the same order.
+ * The weight-independent part is returned: e rows / chi first (terms_chi), then the H/b terms for weight w. */
+typedef struct {
+  float q[3], nq[3], d[3];
+  float a[3], g[6], e0, en[3], r[3];
+} lin_geo;
+
+static float lin_chi(int dim, int factor, const float* S4, const float* m, const float* nm, const float* f,
+                     const float* nf, float ip, float in_, float rs, lin_geo* G) {
+  xf_point(S4, m, G->q);
+  G->nq[0] = G->nq[1] = G->nq[2] = 0.f;
+  xf_dir(S4, nm, G->nq);
+  for (int k = 0; k < 3; ++k) G->d[k] = G->q[k] - f[k];
+  float chi;
   if (factor == ORC_FACTOR_P2P) {
-    for (int r = 0; r < 2; ++r) {
-      const float* R = S4 + r * 4;
-      J[r][0] = R[0]; J[r][1] = R[1];
-      float t = R[0] * m[1];
-      J[r][2] = fmaf(R[1], m[0], -t);
-      e[r] = d[r]; om[r] = ip;
+    chi = (ip * G->d[0]) * G->d[0];
+    chi = fmaf(ip * G->d[1], G->d[1], chi);
+    if (dim == 3) chi = fmaf(ip * G->d[2], G->d[2], chi);
+    /* r = R^T d */
+    for (int c = 0; c < dim; ++c) {
+      float t = S4[0 * 4 + c] * G->d[0];
+      t = fmaf(S4[1 * 4 + c], G->d[1], t);
+      if (dim == 3) t = fmaf(S4[2 * 4 + c], G->d[2], t);
+      G->r[c] = t;
     }
-    return 2;
+    return chi;
   }
-  float a[2];
-  for (int c = 0; c < 2; ++c) {
-    a[c] = fmaf(S4[1 * 4 + c], nf[1], S4[0 * 4 + c] * nf[0]);
+  /* a = R^T n_f */
+  for (int c = 0; c < dim; ++c) {
+    float t = S4[0 * 4 + c] * nf[0];
+    t = fmaf(S4[1 * 4 + c], nf[1], t);
+    if (dim == 3) t = fmaf(S4[2 * 4 + c], nf[2], t);
+    G->a[c] = t;
   }
-  float t = a[0] * m[1];
-  J[0][0] = a[0]; J[0][1] = a[1]; J[0][2] = fmaf(a[1], m[0], -t);
-  e[0] = fmaf(nf[1], d[1], nf[0] * d[0]); om[0] = ip;
-  for (int r = 0; r < 2; ++r) {
-    const float* R = S4 + r * 4;
-    J[r + 1][0] = 0.f; J[r + 1][1] = 0.f;
-    t = R[0] * nm[1];
-    J[r + 1][2] = fmaf(R[1], nm[0], -t);
-    e[r + 1] = nq[r] - nf[r]; om[r + 1] = in_;
+  float t;
+  if (dim == 3) {
+    G->g[0] = G->a[0]; G->g[1] = G->a[1]; G->g[2] = G->a[2];
+    t = m[2] * G->a[1]; G->g[3] = rs * fmaf(m[1], G->a[2], -t);
+    t = m[0] * G->a[2]; G->g[4] = rs * fmaf(m[2], G->a[0], -t);
+    t = m[1] * G->a[0]; G->g[5] = rs * fmaf(m[0], G->a[1], -t);
+    G->e0 = fmaf(nf[2], G->d[2], fmaf(nf[1], G->d[1], nf[0] * G->d[0]));
+  } else {
+    G->g[0] = G->a[0]; G->g[1] = G->a[1];
+    t = G->a[0] * m[1]; G->g[2] = fmaf(G->a[1], m[0], -t);
+    G->e0 = fmaf(nf[1], G->d[1], nf[0] * G->d[0]);
   }
-  return 3;
+  for (int k = 0; k < dim; ++k) G->en[k] = G->nq[k] - nf[k];
+  chi = (ip * G->e0) * G->e0;
+  for (int k = 0; k < dim; ++k) chi = fmaf(in_ * G->en[k], G->en[k], chi);
+  return chi;
 }
 
-/* slots of the 32-entry accumulator */
+/* Ht[21|6] (upper triangle, row-major), bt[6|3] for robust weight w */
+static void lin_terms(int dim, int factor, const lin_geo* G, const float* m, const float* nm, float ip, float in_,
+                      float rs, float w, float* Ht, float* bt) {
+  float t;
+  if (dim == 3 && factor == ORC_FACTOR_P2P) {
+    const float s = w * ip, sr = s * rs, srr = sr * rs;
+    const float* r = G->r;
+    /* rows 0..2 (translation): [ s I | sr * (-[m]x) ] */
+    Ht[0] = s;   Ht[1] = 0.f; Ht[2] = 0.f; Ht[3] = 0.f;          Ht[4] = sr * m[2];    Ht[5] = -(sr * m[1]);
+    Ht[6] = s;   Ht[7] = 0.f; Ht[8] = -(sr * m[2]);              Ht[9] = 0.f;          Ht[10] = sr * m[0];
+    Ht[11] = s;  Ht[12] = sr * m[1];   Ht[13] = -(sr * m[0]);    Ht[14] = 0.f;
+    /* rotation block: srr (|m|^2 I - m m^T) */
+    Ht[15] = srr * fmaf(m[1], m[1], m[2] * m[2]); Ht[16] = -(srr * (m[0] * m[1])); Ht[17] = -(srr * (m[0] * m[2]));
+    Ht[18] = srr * fmaf(m[0], m[0], m[2] * m[2]); Ht[19] = -(srr * (m[1] * m[2]));
+    Ht[20] = srr * fmaf(m[0], m[0], m[1] * m[1]);
+    bt[0] = s * r[0]; bt[1] = s * r[1]; bt[2] = s * r[2];
+    t = m[2] * r[1]; bt[3] = sr * fmaf(m[1], r[2], -t);
+    t = m[0] * r[2]; bt[4] = sr * fmaf(m[2], r[0], -t);
+    t = m[1] * r[0]; bt[5] = sr * fmaf(m[0], r[1], -t);
+    return;
+  }
+  if (dim == 3) { /* PLANE */
+    const float s0 = w * ip, s1 = w * in_, s1r = s1 * rs, s1rr = s1r * rs;
+    const float* g = G->g;
+    const float* a = G->a;
+    float u[6];
+    for (int i = 0; i < 6; ++i) u[i] = s0 * g[i];
+    /* normal rows: s1 c^2 (|n_m|^2 I - n_m n_m^T), s1 c (a x n_m) */
+    float N[6];
+    N[0] = s1rr * fmaf(nm[1], nm[1], nm[2] * nm[2]); N[1] = -(s1rr * (nm[0] * nm[1])); N[2] = -(s1rr * (nm[0] * nm[2]));
+    N[3] = s1rr * fmaf(nm[0], nm[0], nm[2] * nm[2]); N[4] = -(s1rr * (nm[1] * nm[2]));
+    N[5] = s1rr * fmaf(nm[0], nm[0], nm[1] * nm[1]);
+    float bn[3];
+    t = a[2] * nm[1]; bn[0] = s1r * fmaf(a[1], nm[2], -t);
+    t = a[0] * nm[2]; bn[1] = s1r * fmaf(a[2], nm[0], -t);
+    t = a[1] * nm[0]; bn[2] = s1r * fmaf(a[0], nm[1], -t);
+    int slot = 0, nslot = 0;
+    for (int i = 0; i < 6; ++i) {
+      for (int j = i; j < 6; ++j) {
+        if (i >= 3) Ht[slot++] = fmaf(u[i], g[j], N[nslot++]);
+        else Ht[slot++] = u[i] * g[j];
+      }
+    }
+    for (int i = 0; i < 3; ++i) bt[i] = u[i] * G->e0;
+    for (int i = 0; i < 3; ++i) bt[3 + i] = fmaf(u[3 + i], G->e0, bn[i]);
+    return;
+  }
+  if (factor == ORC_FACTOR_P2P) { /* 2D */
+    const float s = w * ip;
+    const float* r = G->r;
+    Ht[0] = s; Ht[1] = 0.f; Ht[2] = -(s * m[1]);
+    Ht[3] = s; Ht[4] = s * m[0];
+    Ht[5] = s * fmaf(m[0], m[0], m[1] * m[1]);
+    bt[0] = s * r[0]; bt[1] = s * r[1];
+    t = m[1] * r[0]; bt[2] = s * fmaf(m[0], r[1], -t);
+    return;
+  }
+  { /* 2D PLANE */
+    const float s0 = w * ip, s1 = w * in_;
+    const float* g = G->g;
+    const float* a = G->a;
+    float u[3];
+    for (int i = 0; i < 3; ++i) u[i] = s0 * g[i];
+    const float N = s1 * fmaf(nm[0], nm[0], nm[1] * nm[1]);
+    t = nm[0] * a[1];
+    const float bn = s1 * fmaf(nm[1], a[0], -t);
+    Ht[0] = u[0] * g[0]; Ht[1] = u[0] * g[1]; Ht[2] = u[0] * g[2];
+    Ht[3] = u[1] * g[1]; Ht[4] = u[1] * g[2];
+    Ht[5] = fmaf(u[2], g[2], N);
+    bt[0] = u[0] * G->e0; bt[1] = u[1] * G->e0;
+    bt[2] = fmaf(u[2], G->e0, bn);
+  }
+}
+
+/* slots of the 40-entry accumulator */
 #define ACC_B 21
 #define ACC_CHI_IN 27      /* coarse word; +1 = residual word */
 #define ACC_CHI_OUT 29     /* coarse word; +1 = residual word */
 #define ACC_N_IN 31
 #define ACC_N_OUT 32
 #define ACC_N_SUP 33
+#define ACC_N_SAT 34       /* suppressed because |S m - f| exceeds the fixed-point error range (also in N_SUP) */
 #define ACC_SLOTS ORC_ACC_SLOTS
 
+/* plain: when non-NULL, receives the un-quantised fp64 sums of the same fp32 terms (27 | 9 H/b entries,
+ * chi_in, chi_out): the independent check of the fixed-point accumulation */
 static void lin_one(int dim, int variable, const orc_factor_params* fa, const orc_scales_t* sc,
                     const float* S4, const float* m, const float* nm, const float* f, const float* nf,
-                    int64_t* acc, uint8_t* status, float* chi_out) {
-  const int P = (dim == 3) ? 6 : 3;
-  float q[3], nq[3] = {0, 0, 0}, e[4], om[4], J[4][6];
-  xf_point(S4, m, q);
-  xf_dir(S4, nm, nq);
-  int E = build_rows(dim, variable, fa->factor, S4, m, nm, f, nf, q, nq, fa->info_point, fa->info_normal, e, om, J);
-  float chi = (om[0] * e[0]) * e[0];
-  for (int r = 1; r < E; ++r) {
-    chi = fmaf(om[r] * e[r], e[r], chi);
-  }
-  if (!(chi == chi) || isinf(chi)) {
+                    int64_t* acc, double* plain, uint8_t* status, float* chi_out) {
+  const int P = (dim == 3) ? 6 : 3, NH = P * (P + 1) / 2;
+  const float rs = (dim == 3 && variable == ORC_VAR_SE3_QUAT_RIGHT) ? 2.f : 1.f;
+  lin_geo G;
+  memset(&G, 0, sizeof(G));
+  const float chi = lin_chi(dim, fa->factor, S4, m, nm, f, nf, fa->info_point, fa->info_normal, rs, &G);
+  float d2 = G.d[0] * G.d[0];
+  d2 = fmaf(G.d[1], G.d[1], d2);
+  if (dim == 3) d2 = fmaf(G.d[2], G.d[2], d2);
+  const int sat = !(d2 <= sc->err_bound * sc->err_bound);  /* also NaN */
+  if (sat || !(chi == chi) || isinf(chi)) {
     acc[ACC_N_SUP] += 1;
+    if (sat) acc[ACC_N_SAT] += 1;
     if (status) *status = ORC_STAT_SUPPRESSED;
     if (chi_out) *chi_out = chi;
     return;
@@ -916,36 +1030,28 @@ static void lin_one(int dim, int variable, const orc_factor_params* fa, const or
   if (kern) {
     acc[ACC_N_OUT] += 1;
     to_fix2(rho, sc->k[ORC_K_CHI], sc->k[ORC_K_CHI_LO], &acc[ACC_CHI_OUT], &acc[ACC_CHI_OUT + 1]);
+    if (plain) plain[28] += (double) rho;
   } else {
     acc[ACC_N_IN] += 1;
     to_fix2(chi, sc->k[ORC_K_CHI], sc->k[ORC_K_CHI_LO], &acc[ACC_CHI_IN], &acc[ACC_CHI_IN + 1]);
+    if (plain) plain[27] += (double) chi;
   }
   if (status) *status = kern ? ORC_STAT_KERNELIZED : ORC_STAT_INLIER;
   if (chi_out) *chi_out = chi;
+  float Ht[21], bt[6];
+  lin_terms(dim, fa->factor, &G, m, nm, fa->info_point, fa->info_normal, rs, w, Ht, bt);
   const int T = dim; /* columns < T are the translation part of the perturbation */
-  float u[4][6];
-  for (int r = 0; r < E; ++r) {
-    float s = w * om[r];
-    for (int i = 0; i < P; ++i) {
-      u[r][i] = s * J[r][i];
-    }
-  }
   int slot = 0;
   for (int i = 0; i < P; ++i) {
     for (int j = i; j < P; ++j) {
-      float h = u[0][i] * J[0][j];
-      for (int r = 1; r < E; ++r) {
-        h = fmaf(u[r][i], J[r][j], h);
-      }
-      acc[slot++] += to_fix(h, sc->k[(j < T) ? ORC_K_HTT : ((i < T) ? ORC_K_HTR : ORC_K_HRR)]);
+      acc[slot] += to_fix(Ht[slot], sc->k[(j < T) ? ORC_K_HTT : ((i < T) ? ORC_K_HTR : ORC_K_HRR)]);
+      if (plain) plain[slot] += (double) Ht[slot];
+      ++slot;
     }
   }
   for (int i = 0; i < P; ++i) {
-    float g = u[0][i] * e[0];
-    for (int r = 1; r < E; ++r) {
-      g = fmaf(u[r][i], e[r], g);
-    }
-    acc[ACC_B + i] += to_fix(g, sc->k[(i < T) ? ORC_K_BT : ORC_K_BR]);
+    acc[ACC_B + i] += to_fix(bt[i], sc->k[(i < T) ? ORC_K_BT : ORC_K_BR]);
+    if (plain) plain[NH + i] += (double) bt[i];
   }
 }
 
@@ -966,22 +1072,31 @@ static void acc_to_Hb(int dim, const int64_t* acc, const orc_scales_t* sc, doubl
 
 int orc_linearize(int dim, int variable, const orc_cloud* fixed, const orc_cloud* moving,
                   const int32_t* fidx, const float* S, const orc_finder_params* fp,
-                  const orc_factor_params* fa, int64_t n_global, float coord_bound, int64_t* acc_out, double* H,
-                  double* b, orc_iter_stats* stats, uint8_t* status_dense, float* chi_dense) {
+                  const orc_factor_params* fa, float radius_bound2, float normal_bound2,
+                  int64_t* acc_out, double* H, double* b, orc_iter_stats* stats, uint8_t* status_dense,
+                  float* chi_dense, double* plain_out) {
   float S4[16];
   embed4(dim, S, S4);
   orc_scales_t sc;
-  /* n_global / coord_bound describe the WHOLE moving cloud when `moving` is one shard of it */
-  orc_scales(dim, n_global > 0 ? n_global : moving->n, coord_bound > 0.f ? coord_bound : orc_coord_bound(dim, moving),
-             fp, fa, &sc);
+  /* radius_bound2 / normal_bound2 describe the WHOLE moving cloud when `moving` is one shard of it */
+  if (!(normal_bound2 > 0.f)) {
+    const float nf2 = orc_normal_bound2(dim, fixed), nm2 = orc_normal_bound2(dim, moving);
+    normal_bound2 = nf2 > nm2 ? nf2 : nm2;
+  }
+  if (!(radius_bound2 > 0.f)) radius_bound2 = orc_radius_bound2(dim, moving);
+  orc_scales(dim, variable, radius_bound2, normal_bound2, fp, fa, &sc);
   int64_t acc[ACC_SLOTS];
   memset(acc, 0, sizeof(acc));
+  double plain[32];
+  memset(plain, 0, sizeof(plain));
   const int have_n = (fixed->normals && moving->normals);
   if (fa->factor == ORC_FACTOR_PLANE && !have_n) return 1;
 #pragma omp parallel
   {
     int64_t loc[ACC_SLOTS];
+    double ploc[32];
     memset(loc, 0, sizeof(loc));
+    memset(ploc, 0, sizeof(ploc));
 #pragma omp for schedule(static)
     for (int64_t j = 0; j < moving->n; ++j) {
       if (status_dense) status_dense[j] = ORC_STAT_NONE;
@@ -1000,18 +1115,23 @@ int orc_linearize(int dim, int variable, const orc_cloud* fixed, const orc_cloud
         get3(moving->normals, dim, j, nm);
         get3(fixed->normals, dim, i, nf);
       }
-      lin_one(dim, variable, fa, &sc, S4, m, nm, f, nf, loc, status_dense ? status_dense + j : NULL,
-              chi_dense ? chi_dense + j : NULL);
+      lin_one(dim, variable, fa, &sc, S4, m, nm, f, nf, loc, plain_out ? ploc : NULL,
+              status_dense ? status_dense + j : NULL, chi_dense ? chi_dense + j : NULL);
     }
 #pragma omp critical
-    for (int k = 0; k < ACC_SLOTS; ++k) acc[k] += loc[k];
+    {
+      for (int k = 0; k < ACC_SLOTS; ++k) acc[k] += loc[k];
+      for (int k = 0; k < 32; ++k) plain[k] += ploc[k];
+    }
   }
   if (acc_out) memcpy(acc_out, acc, sizeof(acc));
+  if (plain_out) memcpy(plain_out, plain, sizeof(plain));
   if (H && b) acc_to_Hb(dim, acc, &sc, H, b);
   if (stats) {
     stats->num_inliers = acc[ACC_N_IN];
     stats->num_outliers = acc[ACC_N_OUT];
     stats->num_suppressed = acc[ACC_N_SUP];
+    stats->num_saturated = acc[ACC_N_SAT];
     stats->num_correspondences = acc[ACC_N_IN] + acc[ACC_N_OUT] + acc[ACC_N_SUP];
     stats->chi_inliers = ldexp((double) acc[ACC_CHI_IN], -sc.k[ORC_K_CHI]) + ldexp((double) acc[ACC_CHI_IN + 1], -sc.k[ORC_K_CHI_LO]);
     stats->chi_outliers = ldexp((double) acc[ACC_CHI_OUT], -sc.k[ORC_K_CHI]) + ldexp((double) acc[ACC_CHI_OUT + 1], -sc.k[ORC_K_CHI_LO]);
@@ -1084,6 +1204,7 @@ static int prior_terms(int dim, int variable, const float* Z4, const float* X4, 
   }
   return 1;
 }
+
 
 /* ------------------------------------------------------------------------------------------ */
 /* a6 -- AlignerTerminationCriteriaStandard_ (aligner_termination_criteria_impl.cpp:10-65)      */
@@ -1221,12 +1342,13 @@ static void run_solver(run_state* rs, int iterations, int use_tc, int clamp) {
       if (clamp && fa.robustifier != ORC_ROB_NONE) fa.robustifier = ORC_ROB_CLAMP; /* :193-199 */
       double Hs[36], bs[6];
       orc_iter_stats ss;
-      orc_linearize(dim, rs->ap->variable, &sl->fixed, &sl->moving, rs->fidx[s], S, &sl->finder, &fa, 0, 0.f,
-                    NULL, Hs, bs, &ss, rs->fstat[s], NULL);
+      orc_linearize(dim, rs->ap->variable, &sl->fixed, &sl->moving, rs->fidx[s], S, &sl->finder, &fa, 0.f, 0.f,
+                    NULL, Hs, bs, &ss, rs->fstat[s], NULL, NULL);
       for (int k = 0; k < P * P; ++k) H[k] = H[k] + Hs[k];
       for (int k = 0; k < P; ++k) b[k] = b[k] + bs[k];
       st.num_inliers += ss.num_inliers; st.num_outliers += ss.num_outliers;
       st.num_suppressed += ss.num_suppressed; st.num_correspondences += ss.num_correspondences;
+      st.num_saturated += ss.num_saturated;
       st.chi_inliers += ss.chi_inliers; st.chi_outliers += ss.chi_outliers;
     }
     float Xn[16], Xu[16];

@@ -73,6 +73,7 @@ typedef struct {
   int32_t solver_status; /* 1 = Success */
   int64_t num_inliers, num_outliers, num_suppressed, num_correspondences;
   double chi_inliers, chi_outliers;
+  int64_t num_saturated; /* suppressed because |S m - f| left the fixed-point error range (part of num_suppressed) */
 } orc_iter_stats;
 
 typedef struct {
@@ -97,7 +98,7 @@ typedef struct {
 /* fixed-point scale exponents per accumulated class (see oracle .c: orc_scales) */
 enum { ORC_K_HTT = 0, ORC_K_HTR = 1, ORC_K_HRR = 2, ORC_K_BT = 3, ORC_K_BR = 4, ORC_K_CHI = 5, ORC_K_CHI_LO = 6, ORC_K_COUNT = 7 };
 #define ORC_ACC_SLOTS 40
-typedef struct { int32_t k[ORC_K_COUNT]; } orc_scales_t;
+typedef struct { int32_t k[ORC_K_COUNT]; float err_bound; /* largest |S m - f| the ranges cover */ } orc_scales_t;
 
 int orc_set_threads(int n);   /* OpenMP threads for the finder / lineariser loops; returns actual */
 
@@ -111,14 +112,19 @@ int orc_find(const orc_index* index, int dim, const orc_cloud* fixed, const orc_
              const float* S, const orc_finder_params* fp, int32_t* fixed_idx_dense, float* response_dense);
 
 /* a5 (linearise part): from a dense per-moving-point fixed index */
-int orc_scales(int dim, int64_t n_moving_global, float coord_bound, const orc_finder_params* fp,
+int orc_scales(int dim, int variable, float radius_bound2, float normal_bound2, const orc_finder_params* fp,
                const orc_factor_params* fa, orc_scales_t* out);
 float orc_coord_bound(int dim, const orc_cloud* moving);
+float orc_radius_bound2(int dim, const orc_cloud* moving);  /* max |m|^2 over the valid points */
+float orc_normal_bound2(int dim, const orc_cloud* cloud);  /* max |n|^2 over the valid points, 0 without normals */
 int orc_linearize(int dim, int variable, const orc_cloud* fixed, const orc_cloud* moving,
                   const int32_t* fixed_idx_dense, const float* S, const orc_finder_params* fp,
-                  const orc_factor_params* fa, int64_t n_moving_global, float coord_bound_global /* <=0: from moving */,
+                  const orc_factor_params* fa, float radius_bound2_global /* <=0: from moving */,
+                  float normal_bound2_global /* <=0: from both clouds */,
                   int64_t* acc /*[ORC_ACC_SLOTS] fixed point*/, double* H /*36 or 9 full row-major*/, double* b,
-                  orc_iter_stats* stats, uint8_t* status_dense, float* chi_dense);
+                  orc_iter_stats* stats, uint8_t* status_dense, float* chi_dense,
+                  double* plain /* NULL or [32]: un-quantised fp64 sums of the same fp32 terms (H upper triangle,
+                                   b, chi_in at [27], chi_out at [28]) -- the independent check of the fixed point */);
 
 /* a1..a9: MultiAlignerBase_::compute() */
 int orc_icp_run(int dim, int n_slices, const orc_slice* slices, const orc_aligner_params* ap,

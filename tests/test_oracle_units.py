@@ -249,3 +249,136 @@ def test_unrobustified_p2p_converges_to_the_closed_form_alignment(oracle, dim, v
     T = np.asarray(r["T"], dtype=np.float64)
     assert np.abs(T[:dim, :dim] - R).max() < 2e-5 and np.abs(T[:dim, dim] - t).max() < 2e-4
     assert np.abs(T[:dim, :dim] - T_star[:dim, :dim]).max() < 2e-3 and np.abs(T[:dim, dim] - T_star[:dim, dim]).max() < 5e-3
+
+
+# ------------------------------------------------------------------------------------------------
+# Independent checks of the accumulation (VERDICT r1 "parity partly circular"): the fixed-point sums
+# against plain fp64 sums of the same fp32 terms, and the reduced (R^T R = I) forms of H / b against a
+# generic J^T Omega J built in float64 numpy from the textbook Jacobians.
+# ------------------------------------------------------------------------------------------------
+def _skew(v):
+    return np.array([[0, -v[2], v[1]], [v[2], 0, -v[0]], [-v[1], v[0], 0.0]])
+
+
+def _generic_Hb(dim, variable, factor, S, m, nm, f, nf, fidx, ip, in_, rob, tau):
+    """Textbook per-correspondence J (rows x P), H = sum w J^T Om J, b = sum w J^T Om e in float64."""
+    P = 6 if dim == 3 else 3
+    R, t = S[:dim, :dim].astype(np.float64), S[:dim, dim].astype(np.float64)
+    c = 2.0 if (dim == 3 and variable == 0) else 1.0
+    H, b, chi_in, chi_out = np.zeros((P, P)), np.zeros(P), 0.0, 0.0
+    for j, i in enumerate(fidx):
+        if i < 0:
+            continue
+        mj, fi = m[j].astype(np.float64), f[i].astype(np.float64)
+        q = R @ mj + t
+        if dim == 3:
+            Jp = np.hstack([R, -c * R @ _skew(mj)])
+        else:
+            Jp = np.hstack([R, (R @ np.array([-mj[1], mj[0]]))[:, None]])
+        if factor == 0:
+            e, J, om = q - fi, Jp, np.full(dim, ip)
+        else:
+            nmj, nfi = nm[j].astype(np.float64), nf[i].astype(np.float64)
+            if dim == 3:
+                Jn = np.hstack([np.zeros((3, 3)), -c * R @ _skew(nmj)])
+            else:
+                Jn = np.hstack([np.zeros((2, 2)), (R @ np.array([-nmj[1], nmj[0]]))[:, None]])
+            e = np.concatenate([[nfi @ (q - fi)], R @ nmj - nfi])
+            J = np.vstack([nfi @ Jp, Jn])
+            om = np.concatenate([[ip], np.full(dim, in_)])
+        chi = float(e @ (om * e))
+        w, rho, kern = 1.0, chi, False
+        if rob == 4 and chi > tau:
+            w, rho, kern = math.sqrt(tau / chi), 2 * math.sqrt(tau * chi) - tau, True
+        H += w * J.T @ (om[:, None] * J)
+        b += w * J.T @ (om * e)
+        if kern:
+            chi_out += rho
+        else:
+            chi_in += chi
+    return H, b, chi_in, chi_out
+
+
+def _unpack_plain(plain, P):
+    NH = P * (P + 1) // 2
+    H = np.zeros((P, P))
+    H[np.triu_indices(P)] = plain[:NH]
+    H = H + np.triu(H, 1).T
+    return H, plain[NH:NH + P].copy(), plain[27], plain[28]
+
+
+@pytest.mark.parametrize("dim,variable,factor", [(3, 0, 1), (3, 1, 0), (3, 0, 0), (2, 0, 1), (2, 0, 0)])
+def test_reduced_forms_match_generic_jacobians(oracle, dim, variable, factor):
+    d = syn.make_icp3d(1500, 1500, seed=21, cube=6.0, n_planes=8, n_spheres=2) if dim == 3 else syn.make_icp2d(1500, seed=22, half=4.0)
+    F = oracle.CloudRef(d["fixed"], d["fixed_normals"])
+    M = oracle.CloudRef(d["moving"], d["moving_normals"])
+    fp = oracle.finder_params(0.4, 0.7)
+    ip, in_, tau = 1.7, 0.6, 0.03
+    fa = oracle.factor_params(factor, oracle.ROB_HUBER, tau, ip, in_)
+    S = (syn.iso3([0.03, -0.02, 0.04], [0.01, -0.02, 0.015]) if dim == 3 else syn.iso2(0.03, -0.02, 0.02)).astype(np.float32)
+    fidx, _ = oracle.find(oracle.Index(F), F, M, S, fp)
+    r = oracle.linearize(F, M, fidx, S, fp, fa, variable=variable, want_plain=True)
+    Hg, bg, ci, co = _generic_Hb(dim, variable, factor, S, d["moving"], d["moving_normals"], d["fixed"],
+                                 d["fixed_normals"], fidx, ip, in_, 4, tau)
+    P = 6 if dim == 3 else 3
+    # the un-quantised sums of the reduced-form fp32 terms against the textbook float64 result: only fp32
+    # rounding of the individual terms separates them
+    Hp, bp, cip, cop = _unpack_plain(r["plain"], P)
+    scale = np.sqrt(np.outer(np.diag(Hg), np.diag(Hg)))
+    assert np.all(np.abs(Hp - Hg) < 1e-6 * scale), np.abs(Hp - Hg) / scale
+    bscale = np.sqrt(np.diag(Hg) * (ci + co))
+    assert np.all(np.abs(bp - bg) < 1e-6 * bscale), (bp, bg)
+    assert abs(cip - ci) < 1e-6 * ci and abs(cop - co) < 1e-6 * max(co, 1e-9)
+    assert abs(r["stats"]["chi_inliers"] - ci) < 1e-6 * ci and abs(r["stats"]["chi_outliers"] - co) < 1e-6 * max(co, 1e-9)
+
+
+@pytest.mark.parametrize("shape", ["c1", "c2", "c5"])
+def test_fixed_point_sums_match_plain_fp64_sums(oracle, shape):
+    """North-star chi^2 bar (1e-6 relative): the quantised integer sums against the un-quantised fp64 sums
+    of the same per-correspondence fp32 terms, on C1 / C2 / C5 shaped inputs (C2, C5 at reduced size)."""
+    if shape == "c2":
+        d, dim = syn.make_icp3d(200000, 200000, seed=2), 3
+        fp, fa = oracle.finder_params(0.3, 0.8), oracle.factor_params(oracle.FACTOR_PLANE, oracle.ROB_HUBER, 0.01)
+        S = np.eye(4, dtype=np.float32)
+        F, M = oracle.CloudRef(d["fixed"], d["fixed_normals"]), oracle.CloudRef(d["moving"], d["moving_normals"])
+    elif shape == "c1":
+        d, dim = syn.make_icp2d(10000, seed=1), 2
+        fp, fa = oracle.finder_params(0.5, 0.8), oracle.factor_params(oracle.FACTOR_PLANE, oracle.ROB_NONE, 1.0)
+        S = np.eye(3, dtype=np.float32)
+        F, M = oracle.CloudRef(d["fixed"], d["fixed_normals"]), oracle.CloudRef(d["moving"], d["moving_normals"])
+    else:
+        d, dim = syn.make_multicue2d(300000, seed=5), 2
+        sc = d["scans"][0]
+        fp, fa = oracle.finder_params(0.5, 0.8), oracle.factor_params(oracle.FACTOR_PLANE, oracle.ROB_HUBER, 0.05)
+        S = np.asarray(sc["robot_in_sensor"], dtype=np.float32)
+        F, M = oracle.CloudRef(sc["points"], sc["normals"]), oracle.CloudRef(d["map"], d["map_normals"])
+    fidx, _ = oracle.find(oracle.Index(F), F, M, S, fp)
+    assert (fidx >= 0).sum() > 500
+    r = oracle.linearize(F, M, fidx, S, fp, fa, want_plain=True)
+    P = 6 if dim == 3 else 3
+    Hp, bp, ci, co = _unpack_plain(r["plain"], P)
+    scale = np.sqrt(np.outer(np.diag(Hp), np.diag(Hp)))
+    assert np.all(np.abs(r["H"] - Hp) <= 1e-6 * scale), np.abs(r["H"] - Hp) / scale
+    n = r["stats"]["num_inliers"] + r["stats"]["num_outliers"]
+    bscale = np.sqrt(np.diag(Hp) * (ci + co))  # Cauchy-Schwarz size of a b entry
+    assert np.all(np.abs(r["b"] - bp) <= 1e-6 * bscale), np.abs(r["b"] - bp) / bscale
+    assert abs(r["stats"]["chi_inliers"] - ci) <= 1e-6 * ci
+    assert abs(r["stats"]["chi_outliers"] - co) <= 1e-6 * max(co, 1e-12)
+    assert n > 500
+
+
+def test_saturation_is_counted_not_silent(oracle):
+    """Externally supplied correspondences whose residual leaves the fixed-point error range are suppressed
+    and counted (num_saturated), never clamped silently."""
+    rng = np.random.default_rng(3)
+    f = rng.uniform(-1, 1, size=(200, 3)).astype(np.float32)
+    m = f.copy()
+    m[:7] += np.float32(50.0)  # 7 pairs 86 m apart: far outside max(max_distance, 2)
+    F, M = oracle.CloudRef(f), oracle.CloudRef(m)
+    fidx = np.arange(200, dtype=np.int32)
+    fp, fa = oracle.finder_params(0.5, -2.0), oracle.factor_params(oracle.FACTOR_P2P, oracle.ROB_NONE)
+    r = oracle.linearize(F, M, fidx, np.eye(4), fp, fa, want_plain=True)
+    st = r["stats"]
+    assert st["num_saturated"] == 7 and st["num_suppressed"] == 7 and st["num_inliers"] == 193
+    assert np.all(r["status"][:7] == oracle.STAT_SUPPRESSED)
+    assert abs(st["chi_inliers"] - r["plain"][27]) <= 1e-6 * max(r["plain"][27], 1e-12)

@@ -31,17 +31,17 @@ def _worker(rank, world, port, out):
     b, e = shard_range(5001, rank, world)
     Ms = O.CloudRef(d["moving"][b:e], d["moving_normals"][b:e])
     fidx, _ = O.find(ix, F, Ms, S, fp)
-    # the scale exponents must come from GLOBAL quantities: cloud size and coordinate bound
-    bound = torch.tensor([float(np.abs(d["moving"][b:e]).max())])
+    # the scale exponents must come from GLOBAL quantities: max |m|^2 and max |n|^2 over the whole moving cloud
+    bound = torch.tensor([O.radius_bound2(Ms), max(O.normal_bound2(Ms), O.normal_bound2(F))], dtype=torch.float32)
     dist.all_reduce(bound, op=dist.ReduceOp.MAX)
-    assert float(bound) == float(np.abs(d["moving"]).max())
-    part = O.linearize(F, Ms, fidx, S, fp, fa, n_global=5001, coord_bound=float(bound))
+    assert float(bound[0]) == O.radius_bound2(O.CloudRef(d["moving"], d["moving_normals"]))
+    part = O.linearize(F, Ms, fidx, S, fp, fa, radius_bound2=float(bound[0]), normal_bound2=float(bound[1]))
     acc = torch.from_numpy(part["acc"].copy())
     dist.all_reduce(acc, op=dist.ReduceOp.SUM)
     if rank == 0:
         M = O.CloudRef(d["moving"], d["moving_normals"])
         gfidx, _ = O.find(ix, F, M, S, fp)
-        full = O.linearize(F, M, gfidx, S, fp, fa, n_global=5001)
+        full = O.linearize(F, M, gfidx, S, fp, fa)
         out.put((acc.numpy().tolist(), full["acc"].tolist(), np.array_equal(gfidx[b:e], fidx)))
     dist.barrier()
     dist.destroy_process_group()
