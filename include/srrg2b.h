@@ -94,6 +94,9 @@ typedef struct {
   int32_t solver_status;            /* 1 = SolverBase::Success */
   int64_t num_inliers, num_outliers, num_suppressed, num_correspondences;
   double chi_inliers, chi_outliers;
+  /* correspondences suppressed because |S m - f| exceeds the finder radius the fixed-point ranges were derived
+   * for (part of num_suppressed).  Always 0 for finder output; counts bad pairs of srrg2b_set_correspondences. */
+  int64_t num_saturated;
 } srrg2b_iter_stats;
 
 /* AlignerBase / MultiAlignerBase_ / AlignerTerminationCriteriaStandard_ parameters, same names and
@@ -132,12 +135,17 @@ int srrg2b_set_cloud(srrg2b_ctx* ctx, int slot, int slice_id, const srrg2b_cloud
 int srrg2b_find_correspondences(srrg2b_ctx* ctx, int slice_id, const float* S, const srrg2b_finder_params* fp,
                                 int32_t* fixed_idx, int32_t* moving_idx, float* response, int64_t* n_out);
 /* HBST path (R/registration/loop_detector/multi_loop_detector_hbst_impl.cpp:331-352): externally
- * matched correspondences, then srrg2b_linearize / srrg2b_icp_iterate with fixed associations */
+ * matched correspondences, evaluated by srrg2b_linearize (srrg2b_icp_iterate / srrg2b_icp_run search their
+ * own correspondences and overwrite supplied ones).  Pairs naming a masked-out moving point are rejected
+ * with SRRG2B_ERR_INVALID; pairs naming an unknown fixed point are kept and counted as suppressed. */
 int srrg2b_set_correspondences(srrg2b_ctx* ctx, int slice_id, const int32_t* fixed_idx, const int32_t* moving_idx, int64_t n);
 
 /* ---- a5 (linearise): FactorCorrespondenceDriven_ accumulation over the slice's current
  * correspondences at S. H is PxP row-major (P = 6 | 3), b is P; acc (optional) receives the 40
- * exact fixed-point sums (21 H, 6 b, chi in/out as coarse+residual words, 3 counters, padding); status/chi (optional) are per correspondence in ascending moving_idx. */
+ * exact fixed-point sums (21 H, 6 b, chi in/out as coarse+residual words, 4 counters, padding); status/chi
+ * (optional) are per correspondence in ascending moving_idx.  fp->max_distance is the residual bound the
+ * fixed-point ranges are derived for: a pair with |S m - f| beyond it is suppressed and counted in
+ * num_saturated (never clamped).  With several ranks every rank receives the global sums. */
 int srrg2b_linearize(srrg2b_ctx* ctx, int slice_id, const float* S, int variable, const srrg2b_finder_params* fp,
                      const srrg2b_factor_params* fa, double* H, double* b, int64_t* acc,
                      srrg2b_iter_stats* stats, uint8_t* status, float* chi);

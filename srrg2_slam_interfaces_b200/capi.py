@@ -63,7 +63,7 @@ class Slice(C.Structure):
 class IterStats(C.Structure):
     _fields_ = [("iteration", C.c_int32), ("solver_status", C.c_int32), ("num_inliers", C.c_int64),
                 ("num_outliers", C.c_int64), ("num_suppressed", C.c_int64), ("num_correspondences", C.c_int64),
-                ("chi_inliers", C.c_double), ("chi_outliers", C.c_double)]
+                ("chi_inliers", C.c_double), ("chi_outliers", C.c_double), ("num_saturated", C.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -2,11 +2,12 @@
 // sequencing of the device-driven ICP loop, NCCL plumbing, and the extern "C" boundary declared in
 // include/srrg2b.h.  No CPU fallback: without a CUDA device every compute call returns
 // SRRG2B_ERR_CUDA.
-#include "s2b_icp.cuh"
+#include "s2b_loop.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include <thrust/iterator/reverse_iterator.h>
+#include <cuda/functional>
 #include <dlfcn.h>
 
 #include <chrono>
@@ -76,6 +77,12 @@ struct RawCloud {
   DevBuf<unsigned char> valid;
   int64_t n = 0, n_global = 0, index_offset = 0;
   bool has_normals = false, has_valid = false, present = false;
+  // max |n|^2 over the valid points (0 without normals): computed on the device right after the normals
+  // landed, read back lazily (nb2_pending) through the pinned word h_nb2
+  float nb2 = 0.f;
+  bool nb2_pending = false;
+  int* h_nb2 = nullptr;
+  int* d_nb2 = nullptr;
   // upload progress on the copy stream: coordinates (+ validity) landed / everything landed.  The index
   // builds start on the coordinates while the normals are still crossing PCIe.
   cudaEvent_t ev_coords = nullptr, ev_all = nullptr;
@@ -108,13 +115,17 @@ struct SliceData {
   DevBuf<int> m_inverse;
   int nm_valid = 0;
   float coord_bound = 0.f;
-  bool coord_bound_global = false;
+  float radius2 = 0.f;      // max |m|^2 over the valid moving points (all shards once bounds_global)
+  float nb2_moving_global = 0.f;
+  bool bounds_global = false;
   // correspondences in moving-sorted order
   DevBuf<int> c_fidx, c_fpos, far_list, far_count, work_list;
   DevBuf<float> c_resp, c_chi, c_lb, S_lb;
   DevBuf<unsigned char> c_stat;
   bool corr_valid = false, stat_valid = false;
   int prune_on_export = 0;
+  bool have_last_S = false;   // stand-alone finds: the transform of the previous pass (motion budget of the bounds)
+  s2b::Mat4f last_S;
 };
 
 }  // namespace
@@ -168,9 +179,11 @@ struct srrg2b_ctx {
   std::vector<RunGraph> run_graphs;
   bool use_graphs = true;  // env SRRG2B_NO_GRAPH=1 disables
   bool graph_nccl = false;  // env SRRG2B_GRAPH_NCCL=1: capture the all-reduce too (experimental: failed the 2-GPU parity test)
-  unsigned long long* d_tile_stats = nullptr;  // experiments (S2B_TILE_STATS builds)
   bool eager_index = true;  // env SRRG2B_EAGER_INDEX=0: build the NN index on first use only
-  bool use_tile = false;   // env SRRG2B_TILE=1: "all" mode searches run tiled out of shared memory (nn_tile_kernel)
+  int pre_iters = 3;       // env SRRG2B_PRE_ITERS: iterations run by the dedicated search kernels before the persistent loop takes over
+  bool use_loop = true;    // env SRRG2B_LOOP=0: no persistent loop kernel (every iteration is a kernel sequence)
+  s2b::GridBar* d_bar = nullptr;
+  long long timeout_cycles = 4000000000ll;  // ~2 s of SM clock: grid barrier / peer exchange give up (env SRRG2B_TIMEOUT_MS)
   s2b::Mat4f* d_T0 = nullptr;  // initial guess of the current run (read by icp_init_kernel)
   s2b::Mat4f* h_T0 = nullptr;  // pinned staging
   s2b::SolveArgs* d_solve = nullptr;  // solve-step arguments of the current run
@@ -228,17 +241,42 @@ int cub_sort_pairs(srrg2b_ctx* c, int n, int end_bit) {
 }
 
 int compute_bounds(srrg2b_ctx* c, const RawCloud& rc) {
-  CK(c, c->bounds.ensure(8));
+  CK(c, c->bounds.ensure(kBoundWords));
   // (pinned source: a pageable one makes the copy synchronous behind the cloud uploads queued before it)
-  CK(c, cudaMemcpyAsync(c->bounds.p, c->h_bounds_init, 8 * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  CK(c, cudaMemcpyAsync(c->bounds.p, c->h_bounds_init, kBoundWords * sizeof(int), cudaMemcpyHostToDevice, c->stream));
   if (rc.n > 0) {
     const int blocks = std::min(blocks_for(rc.n, 256), c->sm_count * 8);
     bounds_kernel<<<blocks, 256, 0, c->stream>>>(rc.xyz.p, rc.has_valid ? rc.valid.p : nullptr, (int) rc.n, c->dim,
                                                  c->bounds.p);
     c->launches++;
   }
-  CK(c, cudaMemcpyAsync(c->h_bounds, c->bounds.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CK(c, cudaMemcpyAsync(c->h_bounds, c->bounds.p, kBoundWords * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CK(c, cudaStreamSynchronize(c->stream));
+  return SRRG2B_OK;
+}
+
+// max |n|^2 of a cloud's normals: queued on the compute stream behind the upload, read back lazily
+int queue_normal_bound(srrg2b_ctx* c, RawCloud& rc) {
+  rc.nb2 = 0.f;
+  rc.nb2_pending = false;
+  if (!rc.has_normals || rc.n == 0) return SRRG2B_OK;
+  if (!rc.d_nb2) CK(c, cudaMalloc((void**) &rc.d_nb2, sizeof(int)));
+  if (!rc.h_nb2) CK(c, cudaMallocHost((void**) &rc.h_nb2, sizeof(int)));
+  if (rc.ev_all) CK(c, cudaStreamWaitEvent(c->stream, rc.ev_all, 0));
+  CK(c, cudaMemsetAsync(rc.d_nb2, 0, sizeof(int), c->stream));
+  const int blocks = std::min(blocks_for(rc.n, 256), c->sm_count * 8);
+  normal_bound_kernel<<<blocks, 256, 0, c->stream>>>(rc.nrm.p, rc.has_valid ? rc.valid.p : nullptr, (int) rc.n, c->dim, rc.d_nb2);
+  c->launches++;
+  CK(c, cudaMemcpyAsync(rc.h_nb2, rc.d_nb2, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  rc.nb2_pending = true;
+  return SRRG2B_OK;
+}
+
+int resolve_normal_bound(srrg2b_ctx* c, RawCloud& rc) {
+  if (!rc.nb2_pending) return SRRG2B_OK;
+  CK(c, cudaStreamSynchronize(c->stream));
+  memcpy(&rc.nb2, rc.h_nb2, 4);
+  rc.nb2_pending = false;
   return SRRG2B_OK;
 }
 
@@ -281,24 +319,27 @@ int build_moving(srrg2b_ctx* c, SliceData& sd) {
   tr.mark("bounds");
   sd.nm_valid = c->h_bounds[7];
   memcpy(&sd.coord_bound, &c->h_bounds[6], 4);
-  sd.coord_bound_global = false;
-  CK(c, sd.m_pts.ensure((size_t) n));
-  CK(c, sd.m_nrm.ensure((size_t) n));
+  memcpy(&sd.radius2, &c->h_bounds[8], 4);
+  sd.bounds_global = false;
+  // (+ 4: the streaming lineariser moves these arrays with bulk copies in multiples of 4 elements)
+  CK(c, sd.m_pts.ensure((size_t) n + 4));
+  CK(c, sd.m_nrm.ensure((size_t) n + 4));
   CK(c, sd.m_inverse.ensure((size_t) n));
   CK(c, sd.c_fidx.ensure((size_t) n));
-  CK(c, sd.c_fpos.ensure((size_t) n));
+  CK(c, sd.c_fpos.ensure((size_t) n + 4));
   CK(c, sd.far_list.ensure((size_t) n));
   CK(c, sd.far_count.ensure(2));  // [0] far worklist size, [1] coherence worklist size
   CK(c, sd.work_list.ensure((size_t) n));
-  CK(c, sd.c_lb.ensure((size_t) n));
-  CK(c, sd.S_lb.ensure(16));
+  CK(c, sd.c_lb.ensure((size_t) n + 4));
+  CK(c, sd.S_lb.ensure(20));
   if (n) CK(c, cudaMemsetAsync(sd.c_lb.p, 0, sizeof(float) * (size_t) n, c->stream));
-  CK(c, cudaMemsetAsync(sd.S_lb.p, 0, sizeof(float) * 16, c->stream));
+  CK(c, cudaMemsetAsync(sd.S_lb.p, 0, sizeof(float) * 20, c->stream));
   CK(c, sd.c_resp.ensure((size_t) n));
   CK(c, sd.c_chi.ensure((size_t) n));
   CK(c, sd.c_stat.ensure((size_t) n));
   sd.corr_valid = false;
   sd.stat_valid = false;
+  sd.have_last_S = false;
   tr.mark("buffers");
   if (n == 0) return SRRG2B_OK;
   float mn[3] = {0, 0, 0}, mx[3] = {0, 0, 0};
@@ -338,7 +379,7 @@ int build_moving(srrg2b_ctx* c, SliceData& sd) {
   }
   CK(c, cudaGetLastError());
   tr.mark("gather");
-  return SRRG2B_OK;
+  return queue_normal_bound(c, rc);
 }
 
 // The cell edge is kCellSlack * max_distance / R: the (2R+1)^dim neighbourhood of a query's cell is
@@ -486,9 +527,9 @@ int ensure_index(srrg2b_ctx* c, SliceData& sd, float max_distance) {
     auto rin = thrust::make_reverse_iterator(c->vals_a.p + ncells + 1);
     auto rout = thrust::make_reverse_iterator(sd.cell_start.p + ncells + 1);
     size_t bytes = 0;
-    CK(c, cub::DeviceScan::InclusiveScan(nullptr, bytes, rin, rout, cub::Min(), ncells + 1, c->stream));
+    CK(c, cub::DeviceScan::InclusiveScan(nullptr, bytes, rin, rout, ::cuda::minimum<>{}, ncells + 1, c->stream));
     CK(c, c->cub_tmp.ensure(bytes));
-    CK(c, cub::DeviceScan::InclusiveScan(c->cub_tmp.p, bytes, rin, rout, cub::Min(), ncells + 1, c->stream));
+    CK(c, cub::DeviceScan::InclusiveScan(c->cub_tmp.p, bytes, rin, rout, ::cuda::minimum<>{}, ncells + 1, c->stream));
   }
   tr.mark("cell table");
   {
@@ -509,6 +550,7 @@ int ensure_index(srrg2b_ctx* c, SliceData& sd, float max_distance) {
     c->launches += 2;
     CK(c, cudaMemsetAsync(sd.c_lb.p, 0, sizeof(float) * (size_t) sd.nm_valid, c->stream));
     sd.corr_valid = false;
+    sd.have_last_S = false;
   }
   CK(c, cudaGetLastError());
   tr.mark("near bits + resets");
@@ -554,6 +596,7 @@ int ensure_proj_index(srrg2b_ctx* c, SliceData& sd, const srrg2b_finder_params& 
     c->launches += 2;
     CK(c, cudaMemsetAsync(sd.c_lb.p, 0, sizeof(float) * (size_t) sd.nm_valid, c->stream));
     sd.corr_valid = false;
+    sd.have_last_S = false;
   }
   CK(c, cudaGetLastError());
   sd.index_is_projective = true;
@@ -572,15 +615,28 @@ int ensure_any_index(srrg2b_ctx* c, SliceData& sd, const srrg2b_finder_params& f
   return ensure_index(c, sd, fp.max_distance);
 }
 
+// The fixed-point ranges come from global quantities: max |m|^2 and max |n|^2 over ALL shards of the
+// moving cloud (and the replicated fixed cloud).  One small max all-reduce per upload.
 int ensure_global_bound(srrg2b_ctx* c, SliceData& sd) {
-  if (c->world <= 1 || sd.coord_bound_global) return SRRG2B_OK;
-  CK(c, c->bounds.ensure(8));
-  CK(c, cudaMemcpyAsync(c->bounds.p, &sd.coord_bound, 4, cudaMemcpyHostToDevice, c->stream));
-  if (g_nccl.AllReduce(c->bounds.p, c->bounds.p, 1, kNcclFloat32, kNcclMax, c->comm, c->stream) != 0)
-    FAIL(c, SRRG2B_ERR_NCCL, "ncclAllReduce(max) failed");
-  CK(c, cudaMemcpyAsync(&sd.coord_bound, c->bounds.p, 4, cudaMemcpyDeviceToHost, c->stream));
-  CK(c, cudaStreamSynchronize(c->stream));
-  sd.coord_bound_global = true;
+  int rcode = resolve_normal_bound(c, sd.moving_raw);
+  if (rcode) return rcode;
+  rcode = resolve_normal_bound(c, sd.fixed_raw);
+  if (rcode) return rcode;
+  if (sd.bounds_global) return SRRG2B_OK;
+  sd.nb2_moving_global = sd.moving_raw.nb2;
+  if (c->world > 1) {
+    CK(c, c->bounds.ensure(kBoundWords));
+    const float two[2] = {sd.radius2, sd.moving_raw.nb2};
+    CK(c, cudaMemcpyAsync(c->bounds.p, two, 8, cudaMemcpyHostToDevice, c->stream));
+    if (g_nccl.AllReduce(c->bounds.p, c->bounds.p, 2, kNcclFloat32, kNcclMax, c->comm, c->stream) != 0)
+      FAIL(c, SRRG2B_ERR_NCCL, "ncclAllReduce(max) failed");
+    float out[2] = {0.f, 0.f};
+    CK(c, cudaMemcpyAsync(out, c->bounds.p, 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    sd.radius2 = out[0];
+    sd.nb2_moving_global = out[1];
+  }
+  sd.bounds_global = true;
   return SRRG2B_OK;
 }
 
@@ -594,7 +650,10 @@ int fill_slice_args(srrg2b_ctx* c, SliceData& sd, int state_slot, const srrg2b_f
   const bool normals = sd.fixed_raw.has_normals && sd.moving_raw.has_normals;
   if (fa.factor == SRRG2B_FACTOR_PLANE && !normals)
     FAIL(c, SRRG2B_ERR_INVALID, "PLANE factor needs normals on both clouds");
-  const Scales sc = choose_scales(sd.moving_raw.n_global, sd.coord_bound, fp.max_distance, fa.info_point, fa.info_normal);
+  if (!(fa.info_point >= 0.f) || !(fa.info_normal >= 0.f) || !(fa.chi_threshold >= 0.f))
+    FAIL(c, SRRG2B_ERR_INVALID, "informations and the robustifier threshold must be non-negative");
+  const float nb2 = std::max(sd.nb2_moving_global, sd.fixed_raw.nb2);
+  const Scales sc = choose_scales(c->dim, variable, fa.factor, sd.radius2, nb2, fp.max_distance, fa.info_point, fa.info_normal);
   if (sc_out) *sc_out = sc;
   a.mp = sd.m_pts.p; a.mn = sd.m_nrm.p; a.nm = sd.nm_valid;
   a.fp = sd.f_pts.p; a.fn = sd.f_nrm.p; a.cell_start = sd.cell_start.p; a.near_bits = sd.near_bits.p;
@@ -606,8 +665,10 @@ int fill_slice_args(srrg2b_ctx* c, SliceData& sd, int state_slot, const srrg2b_f
   a.md2 = fp.max_distance * fp.max_distance;
   a.normal_cos = fp.normal_cos;
   a.gate = (normals && fp.normal_cos > -1.f) ? 1 : 0;
-  a.rob = fa.robustifier; a.tau = fa.chi_threshold; a.ip = fa.info_point; a.in_ = fa.info_normal;
+  a.rob = fa.robustifier; a.tau = fa.chi_threshold; a.delta = sqrtf(fa.chi_threshold);
+  a.ip = fa.info_point; a.in_ = fa.info_normal;
   a.rs = (c->dim == 3 && variable == SRRG2B_VAR_SE3_QUAT_RIGHT) ? 2.f : 1.f;
+  a.eb2 = sc.err_bound * sc.err_bound;
   for (int k = 0; k < kKCount; ++k) a.fS[k] = ldexpf(1.f, sc.k[k] - 22);
   a.fSinvChi = ldexpf(1.f, 22 - sc.k[kKChi]);
   a.S = c->d_state->S[state_slot].m;
@@ -617,8 +678,7 @@ int fill_slice_args(srrg2b_ctx* c, SliceData& sd, int state_slot, const srrg2b_f
   a.work_list = sd.work_list.p; a.work_count = sd.far_count.p + 1;
   a.list_all = &c->d_state->list_all[state_slot];
   a.inline_check = 0; a.use_list = 0;
-  a.tile = c->use_tile ? 1 : 0;
-  a.tile_stats = S2B_TILE_STATS ? c->d_tile_stats : nullptr;
+  a.few_terms = 0;
   a.projective = fp.kind == SRRG2B_FINDER_PROJECTIVE ? 1 : 0;
   a.fx = fp.fx; a.fy = fp.fy; a.pcx = fp.cx; a.pcy = fp.cy; a.min_depth = fp.min_depth; a.max_depth = fp.max_depth;
   a.width = fp.width; a.height = fp.height; a.image = sd.image.p;
@@ -637,7 +697,8 @@ int fill_slice_args(srrg2b_ctx* c, SliceData& sd, int state_slot, const srrg2b_f
   return SRRG2B_OK;
 }
 
-void launch_far(srrg2b_ctx* c, const SliceArgs& a_in, int factor) {
+// skip: device flag that turns the launch into a no-op (the persistent loop has taken over)
+void launch_far(srrg2b_ctx* c, const SliceArgs& a_in, int factor, const int* skip) {
   const int threads = 256;
   SliceArgs a = a_in;
   const int fblocks = std::max(1, std::min(blocks_for((int64_t) a.nm * 32, threads), c->sm_count * 8));
@@ -647,86 +708,70 @@ void launch_far(srrg2b_ctx* c, const SliceArgs& a_in, int factor) {
     a.few_terms = per_lane <= 30 ? 1 : 0;
   }
   if (c->dim == 3) {
-    if (factor == SRRG2B_FACTOR_P2P) nn_far_kernel<3, SRRG2B_FACTOR_P2P><<<fblocks, threads, 0, c->stream>>>(a);
-    else nn_far_kernel<3, SRRG2B_FACTOR_PLANE><<<fblocks, threads, 0, c->stream>>>(a);
+    if (factor == SRRG2B_FACTOR_P2P) nn_far_kernel<3, SRRG2B_FACTOR_P2P><<<fblocks, threads, 0, c->stream>>>(a, skip);
+    else nn_far_kernel<3, SRRG2B_FACTOR_PLANE><<<fblocks, threads, 0, c->stream>>>(a, skip);
   } else {
-    if (factor == SRRG2B_FACTOR_P2P) nn_far_kernel<2, SRRG2B_FACTOR_P2P><<<fblocks, threads, 0, c->stream>>>(a);
-    else nn_far_kernel<2, SRRG2B_FACTOR_PLANE><<<fblocks, threads, 0, c->stream>>>(a);
+    if (factor == SRRG2B_FACTOR_P2P) nn_far_kernel<2, SRRG2B_FACTOR_P2P><<<fblocks, threads, 0, c->stream>>>(a, skip);
+    else nn_far_kernel<2, SRRG2B_FACTOR_PLANE><<<fblocks, threads, 0, c->stream>>>(a, skip);
   }
   c->launches++;
 }
 
-// "all" mode searches: nn_tile_kernel (optional, staged in shared memory), else nn_kernel phase 1
-void launch_nn(srrg2b_ctx* c, const SliceArgs& a) {
-  if (a.tile) {
-    const int blocks = std::max(1, std::min(blocks_for(a.nm, kTileThreads), c->sm_count * 12));
-    if (c->dim == 3) nn_tile_kernel<3><<<blocks, kTileThreads, sizeof(TileSmem), c->stream>>>(a);
-    else nn_tile_kernel<2><<<blocks, kTileThreads, sizeof(TileSmem), c->stream>>>(a);
-    c->launches++;
-  }
+// phase 1 of the grid search (rings 0-1, thread per query)
+void launch_nn(srrg2b_ctx* c, const SliceArgs& a, const int* skip) {
   const int blocks = std::max(1, std::min(blocks_for(a.nm, 256), c->sm_count * 8));
-  if (c->dim == 3) nn_kernel<3><<<blocks, 256, 0, c->stream>>>(a);
-  else nn_kernel<2><<<blocks, 256, 0, c->stream>>>(a);
+  if (c->dim == 3) nn_kernel<3><<<blocks, 256, 0, c->stream>>>(a, skip);
+  else nn_kernel<2><<<blocks, 256, 0, c->stream>>>(a, skip);
   c->launches++;
 }
 
-int launch_find(srrg2b_ctx* c, const SliceArgs& a) {
+int launch_find(srrg2b_ctx* c, const SliceArgs& a, const int* skip) {
   if (a.nm <= 0) return SRRG2B_OK;
   const int threads = 256;
   const int blocks = std::max(1, std::min(blocks_for(a.nm, threads), c->sm_count * 8));
   if (a.projective) {
-    proj_find_kernel<<<blocks, threads, 0, c->stream>>>(a);
+    proj_find_kernel<<<blocks, threads, 0, c->stream>>>(a, skip);
     c->launches++;
     return SRRG2B_OK;
   }
-  CK(c, cudaMemsetAsync(a.far_count, 0, sizeof(int), c->stream));
-  launch_nn(c, a);
-  if (a.R >= 2) launch_far(c, a, SRRG2B_FACTOR_P2P);
+  launch_nn(c, a, skip);
+  if (a.R >= 2) launch_far(c, a, SRRG2B_FACTOR_P2P, skip);
   return SRRG2B_OK;
 }
 
-template <bool CHECK>
-int launch_linearize_t(srrg2b_ctx* c, const SliceArgs& a_in, int factor) {
+// tiles per CTA of the streaming lineariser for a slice of n correspondences on `ctas` CTAs, and whether a
+// thread's partial sums stay below 2^26 (one REDUX per slot in the flush)
+inline int lin_grid(const srrg2b_ctx* c, int n) { return std::max(1, std::min(blocks_for(n, kTile), c->sm_count)); }
+inline int lin_few_terms(int n, int ctas) {
+  const int tiles = blocks_for(n, kTile);
+  const int per_cta = (tiles + ctas - 1) / ctas;
+  return (2 * per_cta + kFailCap / (kLoopThreads / 32) + 2) <= 30 ? 1 : 0;
+}
+
+// streaming lineariser over every slot of the slice as it is
+int launch_linearize(srrg2b_ctx* c, const SliceArgs& a_in, int factor, const int* skip) {
   if (a_in.nm <= 0) return SRRG2B_OK;
-  const int threads = kLinThreads;
-  // one wave of resident CTAs, but never more than 512 correspondences per thread (32-bit partial sums)
-  const int blocks = std::max(1, std::min(blocks_for(a_in.nm, threads),
-                                          std::max(c->sm_count * kLinCtas, blocks_for(a_in.nm, threads * 512))));
   SliceArgs a = a_in;
-  {  // terms a thread can add to one slot: its share of the slice plus, fused kernel, the CTA's in-place tail
-    const int64_t per_thread = ((int64_t) a.nm + (int64_t) blocks * threads - 1) / ((int64_t) blocks * threads) +
-                               (CHECK ? kFailCap / (threads / 32) : 0);
-    a.few_terms = per_thread <= 30 ? 1 : 0;
-  }
+  const int blocks = lin_grid(c, a.nm);
+  a.few_terms = lin_few_terms(a.nm, blocks);
   if (c->dim == 3) {
-    if (factor == SRRG2B_FACTOR_P2P) linearize_kernel<3, SRRG2B_FACTOR_P2P, CHECK><<<blocks, threads, kLinSmemBytes, c->stream>>>(a);
-    else linearize_kernel<3, SRRG2B_FACTOR_PLANE, CHECK><<<blocks, threads, kLinSmemBytes, c->stream>>>(a);
+    if (factor == SRRG2B_FACTOR_P2P) lin_tiles_kernel<3, SRRG2B_FACTOR_P2P><<<blocks, kLoopThreads, kLoopSmemBytes, c->stream>>>(a, skip);
+    else lin_tiles_kernel<3, SRRG2B_FACTOR_PLANE><<<blocks, kLoopThreads, kLoopSmemBytes, c->stream>>>(a, skip);
   } else {
-    if (factor == SRRG2B_FACTOR_P2P) linearize_kernel<2, SRRG2B_FACTOR_P2P, CHECK><<<blocks, threads, kLinSmemBytes, c->stream>>>(a);
-    else linearize_kernel<2, SRRG2B_FACTOR_PLANE, CHECK><<<blocks, threads, kLinSmemBytes, c->stream>>>(a);
+    if (factor == SRRG2B_FACTOR_P2P) lin_tiles_kernel<2, SRRG2B_FACTOR_P2P><<<blocks, kLoopThreads, kLoopSmemBytes, c->stream>>>(a, skip);
+    else lin_tiles_kernel<2, SRRG2B_FACTOR_PLANE><<<blocks, kLoopThreads, kLoopSmemBytes, c->stream>>>(a, skip);
   }
   c->launches++;
   return SRRG2B_OK;
 }
 
-int launch_linearize(srrg2b_ctx* c, const SliceArgs& a, int factor) { return launch_linearize_t<false>(c, a, factor); }
-
-// one pass over a slice inside the ICP loop: fused coherence check + linearise, then search and
-// linearise whatever failed the check (everything, while no bounds are certified)
-int launch_slice_iteration(srrg2b_ctx* c, const SliceArgs& a0, int factor) {
-  if (a0.nm <= 0) return SRRG2B_OK;
-  SliceArgs a = a0;
-  if (a.projective) {  // no coherence machinery for the index-image finder
-    int rcode = launch_find(c, a);
-    if (rcode) return rcode;
-    return launch_linearize(c, a, factor);
-  }
-  a.use_list = 1;  // (the work-list counters were zeroed by icp_init_kernel / the previous solve step)
-  int rcode = launch_linearize_t<true>(c, a, factor);
+// one pass over a slice by the dedicated kernels: search everything, then linearise everything (the first
+// iterations of a run, before bounds are certified; whole runs when the persistent loop is disabled)
+int launch_slice_iteration(srrg2b_ctx* c, const SliceArgs& a, int factor, const int* skip) {
+  if (a.nm <= 0) return SRRG2B_OK;
+  int rcode = launch_find(c, a, skip);
   if (rcode) return rcode;
-  launch_nn(c, a);
-  launch_far(c, a, factor);  // phase 2 of long lists, or the whole job for short ones (any R)
-  return launch_linearize_t<false>(c, a, factor);
+  return launch_linearize(c, a, factor, skip);
 }
 
 // ring-ordered (dy, dz) row offsets of the NN search neighbourhood -> __constant__ tables
@@ -752,6 +797,17 @@ int upload_row_tables() {
   return SRRG2B_OK;
 }
 
+// a transform the fixed-point ranges were derived for: rotation block entries bounded by 1 (+ rounding)
+bool rigid_enough(int dim, const float* M) {
+  const int D1 = dim + 1;
+  for (int r = 0; r < dim; ++r)
+    for (int cc = 0; cc < dim; ++cc)
+      if (!(fabsf(M[r * D1 + cc]) <= 1.001f)) return false;
+  for (int k = 0; k < D1 * D1; ++k)
+    if (!(M[k] == M[k]) || isinf(M[k])) return false;
+  return true;
+}
+
 int validate_slices(srrg2b_ctx* c, int n_slices, const srrg2b_slice* slices, int variable) {
   if (n_slices < 1 || n_slices > SRRG2B_MAX_SLICES || !slices)
     FAIL(c, SRRG2B_ERR_INVALID, "n_slices must be in [1, SRRG2B_MAX_SLICES]");
@@ -768,6 +824,8 @@ int validate_slices(srrg2b_ctx* c, int n_slices, const srrg2b_slice* slices, int
       FAIL(c, SRRG2B_ERR_INVALID, "unknown factor kind");
     if (sl.factor.robustifier < 0 || sl.factor.robustifier > SRRG2B_ROB_HUBER)
       FAIL(c, SRRG2B_ERR_INVALID, "unknown robustifier");
+    if (!rigid_enough(c->dim, sl.robot_in_sensor))
+      FAIL(c, SRRG2B_ERR_INVALID, "robot_in_sensor is not a rigid transform");
   }
   return SRRG2B_OK;
 }
@@ -815,56 +873,108 @@ int make_plan(srrg2b_ctx* c, int n_slices, const srrg2b_slice* slices, const srr
       SliceData& sdd = c->slices[sl.slice_id];
       ss.S_lb = sdd.S_lb.p;
       ss.cell = 1.f / sdd.inv_cell;
-      ss.coord_bound = sdd.coord_bound;
+      ss.radius = sqrtf(sdd.radius2) * 1.0001f;
       ss.track2_mode = c->track2_mode;
       ss.track2_frac = c->track2_frac;
       ss.counters = sdd.far_count.p;
+      ss.nn_points = sl.finder.kind == SRRG2B_FINDER_NN ? 1 : 0;
     }
     for (int k = 0; k < kKCount; ++k) ss.invk[k] = ldexp(1.0, -sc.k[k]);
   }
   return SRRG2B_OK;
 }
 
-int allreduce_acc(srrg2b_ctx* c, int n_slices) {
-  if (c->world <= 1 || c->d_px) return SRRG2B_OK;  // (peer exchange: done by the solve kernel itself)
+int allreduce_acc(srrg2b_ctx* c, int n_slices, bool in_solve_kernel) {
+  // (peer exchange: done by the solve step itself when it runs)
+  if (c->world <= 1 || (c->d_px && in_solve_kernel)) return SRRG2B_OK;
   if (g_nccl.AllReduce(c->d_state->acc, c->d_state->acc, (size_t) n_slices * kAcc, kNcclUint64, kNcclSum, c->comm,
                        c->stream) != 0)
     FAIL(c, SRRG2B_ERR_NCCL, "ncclAllReduce(sum) of H/b/stats failed");
   return SRRG2B_OK;
 }
 
-// enqueue `iterations` _runSolver iterations (multi_aligner_impl.cpp:103-126); no host sync inside
-int enqueue_iterations(srrg2b_ctx* c, const Plan& plan, int iterations) {
-  for (int it = 0; it < iterations; ++it) {
-    for (int s = 0; s < plan.solve.n_slices; ++s) {
-      if (!plan.is_points[s]) continue;
-      if (c->time_kernels) {
-        while (c->kev.size() < c->kev_used + 2) {
-          cudaEvent_t e;
-          CK(c, cudaEventCreate(&e));
-          c->kev.push_back(e);
-        }
-        CK(c, cudaEventRecord(c->kev[c->kev_used], c->stream));
+// one _runSolver iteration (multi_aligner_impl.cpp:103-126) as a kernel sequence: full search +
+// linearisation per point slice, then the solve step.  skip: device flag that makes the whole group a no-op.
+int enqueue_iteration_group(srrg2b_ctx* c, const Plan& plan, const int* skip) {
+  for (int s = 0; s < plan.solve.n_slices; ++s) {
+    if (!plan.is_points[s]) continue;
+    if (c->time_kernels) {
+      while (c->kev.size() < c->kev_used + 2) {
+        cudaEvent_t e;
+        CK(c, cudaEventCreate(&e));
+        c->kev.push_back(e);
       }
-      int rcode = launch_slice_iteration(c, plan.sargs[s], plan.factor[s]);
-      if (rcode) return rcode;
-      if (c->time_kernels) {
-        CK(c, cudaEventRecord(c->kev[c->kev_used + 1], c->stream));
-        c->kev_used += 2;
-      }
+      CK(c, cudaEventRecord(c->kev[c->kev_used], c->stream));
     }
-    int rcode = allreduce_acc(c, plan.solve.n_slices);
+    int rcode = launch_slice_iteration(c, plan.sargs[s], plan.factor[s], skip);
     if (rcode) return rcode;
-    if (c->dim == 3) icp_solve_kernel<3><<<1, kSolveThreads, 0, c->stream>>>(c->d_solve, c->d_state, c->d_px);
-    else icp_solve_kernel<2><<<1, kSolveThreads, 0, c->stream>>>(c->d_solve, c->d_state, c->d_px);
-    c->launches++;
+    if (c->time_kernels) {
+      CK(c, cudaEventRecord(c->kev[c->kev_used + 1], c->stream));
+      c->kev_used += 2;
+    }
+  }
+  int rcode = allreduce_acc(c, plan.solve.n_slices, true);
+  if (rcode) return rcode;
+  if (c->dim == 3) icp_solve_kernel<3><<<1, kSolveThreads, 0, c->stream>>>(c->d_solve, c->d_state, c->d_px, skip);
+  else icp_solve_kernel<2><<<1, kSolveThreads, 0, c->stream>>>(c->d_solve, c->d_state, c->d_px, skip);
+  c->launches++;
+  return SRRG2B_OK;
+}
+
+// the persistent loop kernel: all remaining iterations in one cooperative launch
+int launch_loop(srrg2b_ctx* c, const Plan& plan) {
+  LoopArgs L;
+  memset(&L, 0, sizeof(L));
+  L.ap = c->d_solve; L.st = c->d_state; L.px = c->d_px; L.bar = c->d_bar;
+  L.timeout_cycles = c->timeout_cycles;
+  L.n_slices = plan.solve.n_slices;
+  const int grid = c->sm_count;
+  for (int s = 0; s < plan.solve.n_slices; ++s) {
+    L.factor[s] = plan.factor[s];
+    L.is_points[s] = plan.is_points[s] ? 1 : 0;
+    L.sl[s] = plan.sargs[s];
+    L.sl[s].few_terms = lin_few_terms(L.sl[s].nm, grid);
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned) grid);
+  cfg.blockDim = dim3(kLoopThreads);
+  cfg.dynamicSmemBytes = kLoopSmemBytes;
+  cfg.stream = c->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (c->dim == 3) CK(c, cudaLaunchKernelEx(&cfg, icp_loop_kernel<3>, L));
+  else CK(c, cudaLaunchKernelEx(&cfg, icp_loop_kernel<2>, L));
+  c->launches++;
+  return SRRG2B_OK;
+}
+
+// enqueue `iterations` _runSolver iterations; no host sync inside.  The first pre_iters iterations run as
+// kernel sequences with the dedicated (high-occupancy) search kernels -- each group after the first is a
+// no-op once every NN slice holds certified bounds --, the persistent loop kernel runs the rest.
+int enqueue_iterations(srrg2b_ctx* c, const Plan& plan, int iterations) {
+  // (several ranks without the peer exchange: NCCL all-reduce between kernels, no loop kernel)
+  const bool loop = c->use_loop && !c->time_kernels && (c->world <= 1 || c->d_px);
+  const int groups = loop ? std::min(iterations, std::max(0, c->pre_iters)) : iterations;
+  // (the groups may only stand down when the loop kernel follows them)
+  const int* skip = (loop && iterations > groups) ? &c->d_state->certified : nullptr;
+  for (int it = 0; it < groups; ++it) {
+    const int rcode = enqueue_iteration_group(c, plan, skip);
+    if (rcode) return rcode;
+  }
+  if (loop && iterations > groups) {
+    const int rcode = launch_loop(c, plan);
+    if (rcode) return rcode;
   }
   CK(c, cudaGetLastError());
   return SRRG2B_OK;
 }
 
-// icp_init_kernel + `iterations` iterations for `plan`, starting from guess T0.  Single rank, no
-// per-kernel timing: replay of the cached CUDA graph of that launch sequence (captured on first use).
+// icp_init_kernel + `iterations` iterations for `plan`, starting from guess T0: replay of the cached CUDA
+// graph of that launch sequence (captured on first use).
 int run_plan(srrg2b_ctx* c, const Plan& plan, const Mat4f& T0, int iterations, int apply_prior_guess, int reset_tc,
              int keep_stats) {
   // the previous run has been synchronised (fetch_state), so the pinned staging buffers are free
@@ -875,11 +985,12 @@ int run_plan(srrg2b_ctx* c, const Plan& plan, const Mat4f& T0, int iterations, i
   // (several ranks: graph replay needs the peer-memory exchange -- no NCCL call inside the iteration)
   const bool graph = c->use_graphs && !c->time_kernels && (c->world <= 1 || c->graph_nccl || c->d_px);
   if (!graph) {
-    icp_init_kernel<<<1, 32, 0, c->stream>>>(c->d_solve, c->d_state, c->d_T0, apply_prior_guess, reset_tc, keep_stats);
+    icp_init_kernel<<<1, 32, 0, c->stream>>>(c->d_solve, c->d_state, c->d_T0, apply_prior_guess, reset_tc, keep_stats,
+                                             iterations, c->d_bar);
     c->launches++;
     return enqueue_iterations(c, plan, iterations);
   }
-  const int tail[4] = {iterations, apply_prior_guess, reset_tc, keep_stats};
+  const int tail[6] = {iterations, apply_prior_guess, reset_tc, keep_stats, c->pre_iters, c->use_loop ? 1 : 0};
   // key = everything the launch sequence depends on (slice kernel arguments, factor kinds, counts);
   // the solve-step values are read from device memory and may change freely between replays
   const size_t nb = sizeof(plan.sargs) + sizeof(plan.factor) + sizeof(plan.is_points);
@@ -900,7 +1011,8 @@ int run_plan(srrg2b_ctx* c, const Plan& plan, const Mat4f& T0, int iterations, i
     const int64_t before = c->launches;
     cudaGraph_t g = nullptr;
     CK(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-    icp_init_kernel<<<1, 32, 0, c->stream>>>(c->d_solve, c->d_state, c->d_T0, apply_prior_guess, reset_tc, keep_stats);
+    icp_init_kernel<<<1, 32, 0, c->stream>>>(c->d_solve, c->d_state, c->d_T0, apply_prior_guess, reset_tc, keep_stats,
+                                             iterations, c->d_bar);
     c->launches++;
     const int rcode = enqueue_iterations(c, plan, iterations);
     const cudaError_t e = cudaStreamEndCapture(c->stream, &g);
@@ -925,6 +1037,8 @@ int run_plan(srrg2b_ctx* c, const Plan& plan, const Mat4f& T0, int iterations, i
 int fetch_state(srrg2b_ctx* c) {
   CK(c, cudaMemcpyAsync(c->h_state, c->d_state, sizeof(DevState), cudaMemcpyDeviceToHost, c->stream));
   CK(c, cudaStreamSynchronize(c->stream));
+  if (c->h_state->error == 1) FAIL(c, SRRG2B_ERR_NCCL, "peer exchange timed out: a rank never delivered its accumulators");
+  if (c->h_state->error == 2) FAIL(c, SRRG2B_ERR_CUDA, "grid barrier of the device loop timed out");
   if (c->time_kernels) {
     c->last_kernel_ms = 0.f;
     c->last_kernel_launches = 0;
@@ -1018,10 +1132,10 @@ int srrg2b_ctx_create(int dim, int device, srrg2b_ctx** out) {
   ok = ok && cudaEventCreate(&c->ev0) == cudaSuccess && cudaEventCreate(&c->ev1) == cudaSuccess;
   ok = ok && cudaMalloc((void**) &c->d_state, sizeof(DevState)) == cudaSuccess;
   ok = ok && cudaMallocHost((void**) &c->h_state, sizeof(DevState)) == cudaSuccess;
-  ok = ok && cudaMallocHost((void**) &c->h_bounds, 8 * sizeof(int)) == cudaSuccess;
-  ok = ok && cudaMallocHost((void**) &c->h_bounds_init, 8 * sizeof(int)) == cudaSuccess;
+  ok = ok && cudaMallocHost((void**) &c->h_bounds, kBoundWords * sizeof(int)) == cudaSuccess;
+  ok = ok && cudaMallocHost((void**) &c->h_bounds_init, kBoundWords * sizeof(int)) == cudaSuccess;
   if (ok) {
-    const int init[8] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN, 0, 0};
+    const int init[kBoundWords] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN, 0, 0, 0, 0, 0, 0};
     memcpy(c->h_bounds_init, init, sizeof(init));
   }
   ok = ok && cudaMalloc((void**) &c->d_T0, sizeof(Mat4f)) == cudaSuccess;
@@ -1029,21 +1143,31 @@ int srrg2b_ctx_create(int dim, int device, srrg2b_ctx** out) {
   ok = ok && cudaMalloc((void**) &c->d_solve, sizeof(SolveArgs)) == cudaSuccess;
   ok = ok && cudaMallocHost((void**) &c->h_solve, sizeof(SolveArgs)) == cudaSuccess;
   if (const char* env = getenv("SRRG2B_NO_GRAPH")) c->use_graphs = atoi(env) == 0;
-  if (const char* env = getenv("SRRG2B_TILE")) c->use_tile = atoi(env) != 0;
+  if (const char* env = getenv("SRRG2B_PRE_ITERS")) c->pre_iters = std::max(0, atoi(env));
+  if (const char* env = getenv("SRRG2B_LOOP")) c->use_loop = atoi(env) != 0;
+  {
+    int khz = 1965000;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
+    double ms = 2000.0;
+    if (const char* env = getenv("SRRG2B_TIMEOUT_MS")) ms = std::max(1.0, atof(env));
+    c->timeout_cycles = (long long) (ms * (double) khz);
+  }
+  ok = ok && cudaMalloc((void**) &c->d_bar, sizeof(GridBar)) == cudaSuccess;
+  ok = ok && cudaMemsetAsync(c->d_bar, 0, sizeof(GridBar), c->stream) == cudaSuccess;
   if (const char* env = getenv("SRRG2B_EAGER_INDEX")) c->eager_index = atoi(env) != 0;
   if (const char* env = getenv("SRRG2B_GRAPH_NCCL")) c->graph_nccl = atoi(env) != 0;
   {
-    const void* lin[] = {(const void*) linearize_kernel<3, SRRG2B_FACTOR_P2P, true>, (const void*) linearize_kernel<3, SRRG2B_FACTOR_P2P, false>,
-                         (const void*) linearize_kernel<3, SRRG2B_FACTOR_PLANE, true>, (const void*) linearize_kernel<3, SRRG2B_FACTOR_PLANE, false>,
-                         (const void*) linearize_kernel<2, SRRG2B_FACTOR_P2P, true>, (const void*) linearize_kernel<2, SRRG2B_FACTOR_P2P, false>,
-                         (const void*) linearize_kernel<2, SRRG2B_FACTOR_PLANE, true>, (const void*) linearize_kernel<2, SRRG2B_FACTOR_PLANE, false>};
+    const void* lin[] = {(const void*) lin_tiles_kernel<3, SRRG2B_FACTOR_P2P>, (const void*) lin_tiles_kernel<3, SRRG2B_FACTOR_PLANE>,
+                         (const void*) lin_tiles_kernel<2, SRRG2B_FACTOR_P2P>, (const void*) lin_tiles_kernel<2, SRRG2B_FACTOR_PLANE>,
+                         (const void*) icp_loop_kernel<3>, (const void*) icp_loop_kernel<2>};
     for (const void* f : lin)
-      ok = ok && cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kLinSmemBytes) == cudaSuccess;
+      ok = ok && cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kLoopSmemBytes) == cudaSuccess;
+    int per_sm = 0;
+    ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, icp_loop_kernel<3>, kLoopThreads, kLoopSmemBytes) == cudaSuccess;
+    int coop = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
+    if (per_sm < 1 || !coop) c->use_loop = false;  // (the kernel-sequence path still works)
   }
-  ok = ok && cudaFuncSetAttribute(nn_tile_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(TileSmem)) == cudaSuccess;
-  ok = ok && cudaFuncSetAttribute(nn_tile_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(TileSmem)) == cudaSuccess;
-  ok = ok && cudaMalloc((void**) &c->d_tile_stats, 12 * sizeof(unsigned long long)) == cudaSuccess;
-  ok = ok && cudaMemsetAsync(c->d_tile_stats, 0, 12 * sizeof(unsigned long long), c->stream) == cudaSuccess;
   ok = ok && cudaMemsetAsync(c->d_state, 0, sizeof(DevState), c->stream) == cudaSuccess;
   ok = ok && cudaStreamSynchronize(c->stream) == cudaSuccess;
   ok = ok && upload_row_tables() == SRRG2B_OK;
@@ -1063,17 +1187,7 @@ int srrg2b_ctx_destroy(srrg2b_ctx* c) {
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
-#if S2B_TILE_STATS
-  if (c->d_tile_stats) {
-    unsigned long long t[12];
-    if (cudaMemcpy(t, c->d_tile_stats, sizeof(t), cudaMemcpyDeviceToHost) == cudaSuccess && t[0] + t[1] + t[2]) {
-      fprintf(stderr, "[srrg2b tile stats] tiles staged %llu fallback %llu (of which points overflow %llu) idle %llu | cycles/tile stage %.0f | search cycles per warp: staged %.0f fallback %.0f | staged rows %.0f entries %.0f\n",
-              t[0], t[1], t[7], t[2], t[3] / (double) (t[0] + t[1] + t[2]), t[4] / (8.0 * std::max(1ull, t[0])), t[8] / (8.0 * std::max(1ull, t[1])),
-              t[5] / (double) std::max(1ull, t[0]), t[6] / (double) std::max(1ull, t[0]));
-    }
-  }
-#endif
-  if (c->d_tile_stats) cudaFree(c->d_tile_stats);
+  if (c->d_bar) cudaFree(c->d_bar);
   if (c->d_px && c->comm && g_nccl.AllReduce && c->d_epoch) {
     // a peer may still be adding this rank's last mailbox words: leave together (contexts of a
     // communicator are destroyed collectively, like the communicator itself)
@@ -1090,6 +1204,8 @@ int srrg2b_ctx_destroy(srrg2b_ctx* c) {
     for (RawCloud* rcp : {&s.fixed_raw, &s.moving_raw}) {
       if (rcp->ev_coords) cudaEventDestroy(rcp->ev_coords);
       if (rcp->ev_all) cudaEventDestroy(rcp->ev_all);
+      if (rcp->d_nb2) cudaFree(rcp->d_nb2);
+      if (rcp->h_nb2) cudaFreeHost(rcp->h_nb2);
     }
     s.fixed_raw.xyz.release(); s.fixed_raw.nrm.release(); s.fixed_raw.valid.release();
     s.moving_raw.xyz.release(); s.moving_raw.nrm.release(); s.moving_raw.valid.release();
@@ -1174,6 +1290,7 @@ int srrg2b_comm_init(srrg2b_ctx* c, const void* id, int rank, int world) {
   memset(&px, 0, sizeof(px));
   px.rank = rank;
   px.world = world;
+  px.timeout_cycles = c->timeout_cycles;
   bool mapped = true;
   for (int r = 0; r < world && mapped; ++r) {
     if (r == rank) { px.mail[r] = c->d_mail; continue; }
@@ -1225,6 +1342,7 @@ int srrg2b_set_cloud(srrg2b_ctx* c, int slot, int slice_id, const srrg2b_cloud* 
     // it: the kernels run on the compute stream while the caller uploads the moving cloud on the copy
     // stream (a different radius at run time simply rebuilds).  First use of a slice: built lazily.
     if (was_nn && sd.last_max_distance > 0.f && c->eager_index) rcode = ensure_index(c, sd, sd.last_max_distance);
+    if (!rcode) rcode = queue_normal_bound(c, sd.fixed_raw);
     CK(c, cudaStreamSynchronize(c->copy_stream));  // the caller's buffers are free again
     return rcode;
   }
@@ -1252,13 +1370,39 @@ int srrg2b_find_correspondences(srrg2b_ctx* c, int slice_id, const float* S, con
   a.inline_check = 1;
   Mat4f S4;
   embed(c->dim, S, S4);
-  set_S_kernel<<<1, 32, 0, c->stream>>>(c->d_state, 0, S4, c->track2_mode == 1 ? 1 : 0);
+  // how far any query can have moved since the previous stand-alone pass of this slice (the bounds that pass
+  // certified are spent by that much); a loop run in between, or new clouds, reset the bounds anyway
+  float motion = 0.f, slack = 0.f;
+  {
+    double dr = 0.0, dt = 0.0, tn = 0.0;
+    const Mat4f& P0 = sd.last_S;
+    for (int r = 0; r < 3; ++r) {
+      for (int cc = 0; cc < 3; ++cc) {
+        const double d = sd.have_last_S ? (double) S4.m[r * 4 + cc] - (double) P0.m[r * 4 + cc] : 0.0;
+        dr += d * d;
+      }
+      const double d = sd.have_last_S ? (double) S4.m[r * 4 + 3] - (double) P0.m[r * 4 + 3] : 0.0;
+      dt += d * d;
+      tn += (double) S4.m[r * 4 + 3] * (double) S4.m[r * 4 + 3];
+    }
+    const float radius = sqrtf(sd.radius2) * 1.0001f;
+    motion = (float) ((sqrt(dr) * (double) radius + sqrt(dt)) * (1.0 + 1e-6)) * (1.f + 2.4e-7f);
+    const float qmax = radius * 1.0001f + (float) sqrt(tn);
+    slack = 2e-6f * qmax + 1e-6f;
+    if (!sd.have_last_S) {  // no previous pass: whatever bounds exist are not trusted
+      CK(c, cudaMemsetAsync(sd.c_lb.p, 0, sizeof(float) * (size_t) std::max(sd.nm_valid, 1), c->stream));
+    }
+  }
+  set_S_kernel<<<1, 32, 0, c->stream>>>(c->d_state, 0, S4, c->track2_mode == 1 ? 1 : 0, sd.S_lb.p, motion, slack);
   c->launches++;
-  rcode = launch_find(c, a);
+  CK(c, cudaMemsetAsync(a.far_count, 0, 2 * sizeof(int), c->stream));
+  rcode = launch_find(c, a, nullptr);
   if (rcode) return rcode;
   commit_S_kernel<<<1, 32, 0, c->stream>>>(a.S, sd.S_lb.p);
   c->launches++;
   CK(c, cudaGetLastError());
+  sd.last_S = S4;
+  sd.have_last_S = true;
   sd.corr_valid = true;
   sd.stat_valid = false;
   return export_corr(c, sd, 0, false, fixed_idx, moving_idx, response, nullptr, nullptr, n_out);
@@ -1295,9 +1439,13 @@ int srrg2b_set_correspondences(srrg2b_ctx* c, int slice_id, const int32_t* fixed
     c->launches++;
   }
   CK(c, cudaGetLastError());
+  int n_bad = 0;
+  if (n > 0) CK(c, cudaMemcpyAsync(&n_bad, c->imp_bad.p, 4, cudaMemcpyDeviceToHost, c->stream));
   CK(c, cudaStreamSynchronize(c->stream));
+  sd.have_last_S = false;
   sd.corr_valid = true;
   sd.stat_valid = false;
+  if (n_bad > 0) FAIL(c, SRRG2B_ERR_INVALID, "correspondence list refers to invalid (masked-out) moving points");
   return SRRG2B_OK;
 }
 
@@ -1321,17 +1469,23 @@ int srrg2b_linearize(srrg2b_ctx* c, int slice_id, const float* S, int variable, 
   int rcode = fill_slice_args(c, sd, 0, fpl, *fa, variable, true, a, nullptr);
   if (rcode) return rcode;
   a.gate = 0;  // the correspondences are taken as they are (gated by the finder or supplied by the caller)
-  sc = choose_scales(sd.moving_raw.n_global, sd.coord_bound, fp->max_distance, fa->info_point, fa->info_normal);
+  // ranges for the caller's error bound (fp->max_distance): pairs farther apart are suppressed and counted
+  sc = choose_scales(c->dim, variable, fa->factor, sd.radius2, std::max(sd.nb2_moving_global, sd.fixed_raw.nb2),
+                     fp->max_distance, fa->info_point, fa->info_normal);
   for (int k = 0; k < kKCount; ++k) a.fS[k] = ldexpf(1.f, sc.k[k] - 22);
   a.fSinvChi = ldexpf(1.f, 22 - sc.k[kKChi]);
+  a.eb2 = sc.err_bound * sc.err_bound;
+  if (!rigid_enough(c->dim, S)) FAIL(c, SRRG2B_ERR_INVALID, "S is not a rigid transform");
   Mat4f S4;
   embed(c->dim, S, S4);
-  set_S_kernel<<<1, 32, 0, c->stream>>>(c->d_state, 0, S4, 0);
+  set_S_kernel<<<1, 32, 0, c->stream>>>(c->d_state, 0, S4, 0, nullptr, 0.f, 0.f);
   c->launches++;
-  rcode = launch_linearize(c, a, fa->factor);
+  rcode = launch_linearize(c, a, fa->factor, nullptr);
   if (rcode) return rcode;
   CK(c, cudaGetLastError());
-  rcode = allreduce_acc(c, 1);
+  // several ranks: the solve step (which exchanges the sums over peer memory) does not run here, so the
+  // partial sums are reduced explicitly -- the result is the global sum on every rank either way
+  rcode = allreduce_acc(c, 1, false);
   if (rcode) return rcode;
   rcode = fetch_state(c);
   if (rcode) return rcode;
@@ -1355,6 +1509,7 @@ int srrg2b_linearize(srrg2b_ctx* c, int slice_id, const float* S, int variable, 
     stats->num_inliers = (int64_t) A[kAccNIn];
     stats->num_outliers = (int64_t) A[kAccNOut];
     stats->num_suppressed = (int64_t) A[kAccNSup];
+    stats->num_saturated = (int64_t) A[kAccNSat];
     stats->num_correspondences = stats->num_inliers + stats->num_outliers + stats->num_suppressed;
     stats->chi_inliers = ldexp((double) (long long) A[kAccChiIn], -sc.k[kKChi]) + ldexp((double) (long long) A[kAccChiIn + 1], -sc.k[kKChiLo]);
     stats->chi_outliers = ldexp((double) (long long) A[kAccChiOut], -sc.k[kKChi]) + ldexp((double) (long long) A[kAccChiOut + 1], -sc.k[kKChiLo]);
@@ -1378,8 +1533,11 @@ int srrg2b_icp_run(srrg2b_ctx* c, int n_slices, const srrg2b_slice* slices, cons
   Plan plan;
   rcode = make_plan(c, n_slices, slices, *ap, false, want_status, plan);
   if (rcode) return rcode;
+  if (!rigid_enough(c->dim, T)) FAIL(c, SRRG2B_ERR_INVALID, "initial guess is not a rigid transform");
   Mat4f T0;
   embed(c->dim, T, T0);
+  for (int s = 0; s < n_slices; ++s)
+    if (slices[s].kind == SRRG2B_SLICE_POINTS) c->slices[slices[s].slice_id].have_last_S = false;
   CK(c, cudaEventRecord(c->ev0, c->stream));
   rcode = run_plan(c, plan, T0, ap->max_iterations, 1, 1, 0);  // multi_aligner_impl.cpp:72
   if (rcode) return rcode;
@@ -1397,8 +1555,7 @@ int srrg2b_icp_run(srrg2b_ctx* c, int n_slices, const srrg2b_slice* slices, cons
     status = SRRG2B_ALIGNER_FAIL;
     done = true;
   } else {
-    const int last = std::min(hs->n_stats, kMaxStats) - 1;
-    if (hs->stats[last].num_inliers < ap->min_num_inliers) {  // :81-85
+    if (hs->last_stats.num_inliers < ap->min_num_inliers) {  // :81-85 (newest entry, also when the array is full)
       status = SRRG2B_ALIGNER_NOT_ENOUGH_INLIERS;
       done = true;
     }
@@ -1455,8 +1612,11 @@ int srrg2b_icp_iterate(srrg2b_ctx* c, int n_slices, const srrg2b_slice* slices, 
   Plan plan;
   rcode = make_plan(c, n_slices, slices, ap, false, true, plan);
   if (rcode) return rcode;
+  if (!rigid_enough(c->dim, T)) FAIL(c, SRRG2B_ERR_INVALID, "T is not a rigid transform");
   Mat4f T0;
   embed(c->dim, T, T0);
+  for (int s = 0; s < n_slices; ++s)
+    if (slices[s].kind == SRRG2B_SLICE_POINTS) c->slices[slices[s].slice_id].have_last_S = false;
   rcode = run_plan(c, plan, T0, 1, 0, 1, 0);
   if (rcode) return rcode;
   rcode = fetch_state(c);

@@ -360,15 +360,22 @@ S2B_HD bool prior_accumulate(int dim, int variable, const Mat4f& Z, const Mat4f&
 }
 
 // ---- fixed-point scale exponents for the exact integer accumulation ----------------------------
-// Per-TERM magnitude bounds (log2), from global quantities only:
-//   translation columns of J : |entry| <= 2            rotation columns: <= max(2, 4 |coord|_max) (Jb bits)
-//   error rows               : <= max(max_distance, 2) (eb bits)
-//   information              : <= max(info_point, info_normal, 1) (wb bits), <= 4 rows (2 bits)
-// A term is stored as round(term * 2^k), k = 21 - bound, so |term * 2^k| < 2^21 (terms are clamped to
-// the bound first).  chi gets a second, 2^20 times finer, residual word.
+// Per-TERM magnitude bounds of everything that is accumulated, derived from the DATA (global quantities
+// only), so that no term can leave its fixed-point range -- there is nothing to clamp:
+//   nb = max(1, |n|_max)   normal norms of both clouds      rm = |m|_max   moving point norms
+//   E  = max_distance (1 + 2^-10): a correspondence with |S m - f| > E is suppressed and counted as
+//        saturated (cannot happen for finder output; guards externally supplied pairs)
+//   Gt = nb (1 + 2^-10) >= |R^T n_f|,   Gr = c rm Gt >= |c m x a|   (c = 2 quaternion, 1 otherwise)
+//   PLANE: H_tt <= ip Gt^2, H_tr <= ip Gt Gr, H_rr <= ip Gr^2 + in c^2 nb^2, e0 <= nb E,
+//          b_t <= ip Gt nb E, b_r <= ip Gr nb E + in c nb Gt, chi <= ip (nb E)^2 + in (2 nb)^2
+//   P2P:   H_tt <= ip, H_tr <= ip c rm, H_rr <= ip (c rm)^2, b_t <= ip E, b_r <= ip c rm E, chi <= ip E^2
+// (robust weights are <= 1).  A term of class X is stored as rint(term * 2^k_X), k_X = 21 - ceil(log2(1.01 B_X)),
+// so |term * 2^k| < 2^21.  chi gets a second, 2^20 times finer, residual word.  All fp32, this order
+// (the same sequence of operations as orc_scales in the oracle; host code is compiled without contraction).
 enum { kKHtt = 0, kKHtr = 1, kKHrr = 2, kKBt = 3, kKBr = 4, kKChi = 5, kKChiLo = 6, kKCount = 7 };
 struct Scales {
   int k[kKCount];
+  float err_bound;  // E
 };
 
 inline int ceil_log2_float(float x) {
@@ -378,25 +385,42 @@ inline int ceil_log2_float(float x) {
   return e;
 }
 
-inline Scales choose_scales(int64_t n_global, float coord_bound, float max_distance, float info_point,
-                            float info_normal) {
-  (void) n_global;
-  float jm = 4.f * coord_bound;
-  if (jm < 2.f) jm = 2.f;
-  const int Jb = ceil_log2_float(jm);
-  float wm = info_point > info_normal ? info_point : info_normal;
-  if (!(wm > 1.f)) wm = 1.f;
-  const int wb = ceil_log2_float(wm);
-  const float em = max_distance > 2.f ? max_distance : 2.f;
-  const int eb = ceil_log2_float(em);
+inline Scales choose_scales(int dim, int variable, int factor, float radius_bound2, float normal_bound2,
+                            float max_distance, float info_point, float info_normal) {
+  const float c = (dim == 3 && variable == 0) ? 2.f : 1.f;
+  const float slack = 1.0009765625f;
+  float nb = sqrtf(normal_bound2);
+  if (!(nb > 1.f)) nb = 1.f;
+  const float rm = sqrtf(radius_bound2);
+  const float E = max_distance * slack;
+  const float ip = info_point, in_ = info_normal;
+  float B[kKCount];
+  if (factor == 1) {  // PLANE
+    const float Gt = nb * slack, Gr = (c * rm) * Gt, e0 = nb * E;
+    B[kKHtt] = (ip * Gt) * Gt;
+    B[kKHtr] = (ip * Gt) * Gr;
+    B[kKHrr] = (ip * Gr) * Gr + ((in_ * c) * c) * (nb * nb);
+    B[kKBt] = (ip * Gt) * e0;
+    B[kKBr] = (ip * Gr) * e0 + (in_ * c) * (nb * Gt);
+    B[kKChi] = (ip * e0) * e0 + (in_ * 4.f) * (nb * nb);
+  } else {
+    const float Gr = c * rm;
+    B[kKHtt] = ip;
+    B[kKHtr] = ip * Gr;
+    B[kKHrr] = (ip * Gr) * Gr;
+    B[kKBt] = ip * E;
+    B[kKBr] = (ip * Gr) * E;
+    B[kKChi] = (ip * E) * E;
+  }
   Scales s;
-  s.k[kKHtt] = 21 - (2 + wb + 2);
-  s.k[kKHtr] = 21 - (2 + wb + 1 + Jb);
-  s.k[kKHrr] = 21 - (2 + wb + 2 * Jb);
-  s.k[kKBt] = 21 - (2 + wb + 1 + eb);
-  s.k[kKBr] = 21 - (2 + wb + Jb + eb);
-  s.k[kKChi] = 21 - (2 + wb + 2 * eb);
+  for (int k = 0; k < kKChiLo; ++k) {
+    float v = B[k] * 1.01f;
+    if (!(v > 1e-30f)) v = 1e-30f;  // degenerate inputs (empty cloud, zero information)
+    if (!(v < 1e30f)) v = 1e30f;
+    s.k[k] = 21 - ceil_log2_float(v);
+  }
   s.k[kKChiLo] = s.k[kKChi] + 20;
+  s.err_bound = E;
   return s;
 }
 

@@ -239,33 +239,87 @@ def test_prior_only_reference_kat_on_gpu(oracle, capi):
     ctx.close()
 
 
-def test_tiled_search_matches_oracle(monkeypatch):
-    """The optional TMA-staged tiled search (SRRG2B_TILE=1, nn_tile_kernel) must give the same run as
-    the oracle, bit for bit: cold start, warm iterations, certified-bound iteration, coherence phase."""
-    from oracle import oracle as O
-    from srrg2_slam_interfaces_b200 import capi as A
-    from srrg2_slam_interfaces_b200 import synthetic as syn
-    monkeypatch.setenv("SRRG2B_TILE", "1")
+@pytest.mark.parametrize("env", [{"SRRG2B_LOOP": "0"}, {"SRRG2B_PRE_ITERS": "0"}, {"SRRG2B_PRE_ITERS": "1"},
+                                 {"SRRG2B_NO_GRAPH": "1"}])
+def test_execution_modes_match_oracle(oracle, capi, env, monkeypatch):
+    """The same run through every execution mode of the device loop -- kernel sequences only (SRRG2B_LOOP=0),
+    the persistent loop kernel from the very first iteration (PRE_ITERS=0: its in-kernel full search) or after
+    one iteration, stream launches instead of graph replay -- equals the oracle's, bit for bit."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
     d = syn.make_icp3d(30000, 27001, seed=11)
     kw = dict(max_iterations=12, min_num_inliers=10)
-    ctx = A.Context(3, 0)
-    ctx.set_cloud(A.FIXED, 0, d["fixed"], d["fixed_normals"])
-    ctx.set_cloud(A.MOVING, 0, d["moving"], d["moving_normals"])
-    g = ctx.icp_run([A.make_slice(3, 0, None, A.finder_params(0.3, 0.8),
-                                  A.factor_params(A.FACTOR_PLANE, A.ROB_HUBER, 0.01))],
-                    A.aligner_params(**kw), np.eye(4))
-    gc = ctx.get_correspondences(0, 27001)
+    o, g, corr = _run_both(oracle, capi, 3, d, oracle.aligner_params(**kw), capi.aligner_params(**kw),
+                           oracle.finder_params(0.3, 0.8), capi.finder_params(0.3, 0.8),
+                           oracle.factor_params(oracle.FACTOR_PLANE, oracle.ROB_HUBER, 0.01),
+                           capi.factor_params(capi.FACTOR_PLANE, capi.ROB_HUBER, 0.01), np.eye(4))
+    _assert_same_run(o, g, corr)
+    d2 = syn.make_icp2d(9000, 7000, seed=4, paired=False)
+    o, g, corr = _run_both(oracle, capi, 2, d2, oracle.aligner_params(**kw), capi.aligner_params(**kw),
+                           oracle.finder_params(0.4, 0.8), capi.finder_params(0.4, 0.8),
+                           oracle.factor_params(oracle.FACTOR_PLANE, oracle.ROB_CAUCHY, 0.05),
+                           capi.factor_params(capi.FACTOR_PLANE, capi.ROB_CAUCHY, 0.05), np.eye(3))
+    _assert_same_run(o, g, corr)
+
+
+def test_warm_context_equals_fresh_context(oracle, capi):
+    """compute() twice on the same resident clouds (the second one starts from the first one's slots and
+    bounds) must equal a fresh context bit for bit -- and both equal the oracle."""
+    d = syn.make_icp3d(40000, 35000, seed=17)
+    kw = dict(max_iterations=10, min_num_inliers=10)
+    gsl = [capi.make_slice(3, 0, None, capi.finder_params(0.3, 0.8), capi.factor_params(capi.FACTOR_PLANE, capi.ROB_HUBER, 0.01))]
+    runs = []
+    for fresh in (True, False, False):
+        if fresh:
+            ctx = capi.Context(3)
+            ctx.set_cloud(capi.FIXED, 0, d["fixed"], d["fixed_normals"])
+            ctx.set_cloud(capi.MOVING, 0, d["moving"], d["moving_normals"])
+        g = ctx.icp_run(gsl, capi.aligner_params(**kw), np.eye(4))
+        runs.append((g, ctx.get_correspondences(0, 35000)))
     ctx.close()
-    F = O.CloudRef(d["fixed"], d["fixed_normals"])
-    M = O.CloudRef(d["moving"], d["moving_normals"])
-    o = O.icp_run(3, [O.make_slice(F, M, None, O.finder_params(0.3, 0.8),
-                                   O.factor_params(O.FACTOR_PLANE, O.ROB_HUBER, 0.01))],
-                  O.aligner_params(**kw), np.eye(4))
-    assert g["status"] == o["status"]
-    assert g["stats"] == o["stats"]
-    assert np.array_equal(g["T"], o["T"])
-    assert np.array_equal(gc[0], o["correspondences"][0][0])
-    assert np.array_equal(gc[1], o["correspondences"][0][1])
+    F, M = oracle.CloudRef(d["fixed"], d["fixed_normals"]), oracle.CloudRef(d["moving"], d["moving_normals"])
+    o = oracle.icp_run(3, [oracle.make_slice(F, M, None, oracle.finder_params(0.3, 0.8),
+                                             oracle.factor_params(oracle.FACTOR_PLANE, oracle.ROB_HUBER, 0.01))],
+                       oracle.aligner_params(**kw), np.eye(4))
+    for g, corr in runs:
+        _assert_same_run(o, g, corr)
+
+
+def test_supplied_correspondences_and_saturation(oracle, capi):
+    """HBST path (multi_loop_detector_hbst_impl.cpp:331-352): externally matched pairs evaluated by
+    srrg2b_linearize equal the oracle's sums; pairs whose residual leaves the fixed-point error range are
+    suppressed and COUNTED (num_saturated), pairs naming a masked-out moving point are rejected."""
+    rng = np.random.default_rng(8)
+    n = 6000
+    f = rng.uniform(-4, 4, size=(n, 3)).astype(np.float32)
+    nf = rng.normal(size=(n, 3)); nf = (nf / np.linalg.norm(nf, axis=1, keepdims=True)).astype(np.float32)
+    perm = rng.permutation(n)
+    m = (f[perm] + rng.normal(scale=0.01, size=(n, 3))).astype(np.float32)
+    nm = nf[perm].copy()
+    m[:9] += np.float32(30.0)  # nine pairs far outside the residual bound
+    mv = np.ones(n, np.uint8); mv[100] = 0
+    sel = np.setdiff1d(rng.choice(n, size=4000, replace=False), [100])
+    sel = np.union1d(sel, np.arange(9))
+    fidx_dense = np.full(n, -1, np.int32)
+    fidx_dense[sel] = perm[sel]
+    F, M = oracle.CloudRef(f, nf), oracle.CloudRef(m, nm, mv)
+    S = syn.iso3([0.004, -0.003, 0.002], [0.001, 0.002, -0.001]).astype(np.float32)
+    ctx = capi.Context(3)
+    ctx.set_cloud(capi.FIXED, 0, f, nf)
+    ctx.set_cloud(capi.MOVING, 0, m, nm, mv)
+    for factor in ("P2P", "PLANE"):
+        ofp, gfp = oracle.finder_params(0.5, -2.0), capi.finder_params(0.5, -2.0)
+        ofa = oracle.factor_params(getattr(oracle, "FACTOR_" + factor), oracle.ROB_CAUCHY, 0.01)
+        gfa = capi.factor_params(getattr(capi, "FACTOR_" + factor), capi.ROB_CAUCHY, 0.01)
+        o = oracle.linearize(F, M, fidx_dense, S, ofp, ofa)
+        ctx.set_correspondences(0, perm[sel].astype(np.int32), sel.astype(np.int32))
+        g = ctx.linearize(0, S, gfp, gfa, n_moving=n)
+        assert np.array_equal(g["acc"], o["acc"])
+        assert g["stats"] == o["stats"] and g["stats"]["num_saturated"] == 9 == g["stats"]["num_suppressed"]
+        assert np.array_equal(g["H"], o["H"]) and np.array_equal(g["b"], o["b"])
+    with pytest.raises(capi.Srrg2bError):
+        ctx.set_correspondences(0, np.array([5], np.int32), np.array([100], np.int32))  # masked-out moving point
+    ctx.close()
 
 
 def test_icp_run_c2_full_size(oracle, capi):
