@@ -91,7 +91,7 @@ struct RawCloud {
 struct SliceData {
   RawCloud fixed_raw, moving_raw;
   // fixed index (lazy, keyed by the cell size it was built for)
-  DevBuf<float4> f_pts, f_nrm;
+  DevBuf<float4> f_pts, f_rec;  // compact points (searches) / 32-byte {point | normal} records (lineariser gathers)
   DevBuf<int> f_inverse, cell_start;
   DevBuf<unsigned> near_bits;
   int nf_valid = 0;
@@ -111,7 +111,7 @@ struct SliceData {
   srrg2b_finder_params proj_params = {};
   DevBuf<unsigned long long> image;
   // moving, Morton order
-  DevBuf<float4> m_pts, m_nrm;
+  DevBuf<float4> m_pts, m_nrm, m_pair;
   DevBuf<int> m_inverse;
   int nm_valid = 0;
   float coord_bound = 0.f;
@@ -124,7 +124,7 @@ struct SliceData {
   DevBuf<unsigned char> c_stat;
   bool corr_valid = false, stat_valid = false;
   int prune_on_export = 0;
-  bool have_last_S = false;   // stand-alone finds: the transform of the previous pass (motion budget of the bounds)
+  bool have_last_S = false;   // stand-alone finds: last_S is the anchor transform of the slice's certified bounds
   s2b::Mat4f last_S;
 };
 
@@ -183,6 +183,8 @@ struct srrg2b_ctx {
   int pre_iters = 3;       // env SRRG2B_PRE_ITERS: iterations run by the dedicated search kernels before the persistent loop takes over
   bool use_loop = true;    // env SRRG2B_LOOP=0: no persistent loop kernel (every iteration is a kernel sequence)
   s2b::GridBar* d_bar = nullptr;
+  long long* d_part = nullptr;  // per-CTA partial sums of the loop kernel
+  unsigned long long* d_loop_dbg = nullptr;  // SRRG2B_LOOP_DEBUG=1: phase time stamps of the loop kernel
   long long timeout_cycles = 4000000000ll;  // ~2 s of SM clock: grid barrier / peer exchange give up (env SRRG2B_TIMEOUT_MS)
   s2b::Mat4f* d_T0 = nullptr;  // initial guess of the current run (read by icp_init_kernel)
   s2b::Mat4f* h_T0 = nullptr;  // pinned staging
@@ -324,16 +326,17 @@ int build_moving(srrg2b_ctx* c, SliceData& sd) {
   // (+ 4: the streaming lineariser moves these arrays with bulk copies in multiples of 4 elements)
   CK(c, sd.m_pts.ensure((size_t) n + 4));
   CK(c, sd.m_nrm.ensure((size_t) n + 4));
+  CK(c, sd.m_pair.ensure(((size_t) n / 2 + 2) * 3));
   CK(c, sd.m_inverse.ensure((size_t) n));
   CK(c, sd.c_fidx.ensure((size_t) n));
   CK(c, sd.c_fpos.ensure((size_t) n + 4));
   CK(c, sd.far_list.ensure((size_t) n));
-  CK(c, sd.far_count.ensure(2));  // [0] far worklist size, [1] coherence worklist size
+  CK(c, sd.far_count.ensure(4));  // [0] far worklist size, [1] coherence worklist size, [2] tile ticket
   CK(c, sd.work_list.ensure((size_t) n));
   CK(c, sd.c_lb.ensure((size_t) n + 4));
-  CK(c, sd.S_lb.ensure(20));
+  CK(c, sd.S_lb.ensure(kSlbFloats));
   if (n) CK(c, cudaMemsetAsync(sd.c_lb.p, 0, sizeof(float) * (size_t) n, c->stream));
-  CK(c, cudaMemsetAsync(sd.S_lb.p, 0, sizeof(float) * 20, c->stream));
+  CK(c, cudaMemsetAsync(sd.S_lb.p, 0, sizeof(float) * kSlbFloats, c->stream));
   CK(c, sd.c_resp.ensure((size_t) n));
   CK(c, sd.c_chi.ensure((size_t) n));
   CK(c, sd.c_stat.ensure((size_t) n));
@@ -371,11 +374,12 @@ int build_moving(srrg2b_ctx* c, SliceData& sd) {
     if (rc.ev_all) CK(c, cudaStreamWaitEvent(c->stream, rc.ev_all, 0));
     gather_kernel<<<blocks_for(sd.nm_valid, 256), 256, 0, c->stream>>>(
       rc.xyz.p, rc.has_normals ? rc.nrm.p : nullptr, c->vals_b.p, sd.nm_valid, dim, sd.m_pts.p, sd.m_nrm.p,
-      sd.m_inverse.p);
+      sd.m_inverse.p, nullptr);
     c->launches++;
+    pair_pack_kernel<<<blocks_for((sd.nm_valid + 1) / 2, 256), 256, 0, c->stream>>>(sd.m_pts.p, sd.m_nrm.p, sd.nm_valid, sd.m_pair.p);
     fill_int_kernel<<<blocks_for(sd.nm_valid, 256), 256, 0, c->stream>>>(sd.c_fidx.p, sd.nm_valid, -1);
     fill_int_kernel<<<blocks_for(sd.nm_valid, 256), 256, 0, c->stream>>>(sd.c_fpos.p, sd.nm_valid, -1);
-    c->launches += 2;
+    c->launches += 3;
   }
   CK(c, cudaGetLastError());
   tr.mark("gather");
@@ -410,7 +414,8 @@ int ensure_index(srrg2b_ctx* c, SliceData& sd, float max_distance) {
     }
   }
   CK(c, sd.f_pts.ensure((size_t) n + 1));
-  CK(c, sd.f_nrm.ensure((size_t) n + 1));
+  CK(c, sd.f_rec.ensure(2 * ((size_t) n + 1)));
+  CK(c, cudaMemsetAsync(sd.f_rec.p, 0, 2 * sizeof(float4), c->stream));  // (position 0 stands in for "no candidate")
   CK(c, sd.f_inverse.ensure((size_t) n + 1));
   if (n > 0) {
     CK(c, c->keys_a.ensure(n));
@@ -509,8 +514,8 @@ int ensure_index(srrg2b_ctx* c, SliceData& sd, float max_distance) {
     if (sd.nf_valid > 0) {
       if (rc.ev_all) CK(c, cudaStreamWaitEvent(c->stream, rc.ev_all, 0));
       gather_kernel<<<blocks_for(sd.nf_valid, 256), 256, 0, c->stream>>>(
-        rc.xyz.p, rc.has_normals ? rc.nrm.p : nullptr, c->vals_b.p, sd.nf_valid, dim, sd.f_pts.p, sd.f_nrm.p,
-        sd.f_inverse.p);
+        rc.xyz.p, rc.has_normals ? rc.nrm.p : nullptr, c->vals_b.p, sd.nf_valid, dim, sd.f_pts.p, nullptr,
+        sd.f_inverse.p, sd.f_rec.p);
       c->launches++;
     }
   }
@@ -575,14 +580,15 @@ int ensure_proj_index(srrg2b_ctx* c, SliceData& sd, const srrg2b_finder_params& 
   const int n = (int) rc.n;
   const size_t npx = (size_t) fp.width * fp.height;
   CK(c, sd.f_pts.ensure((size_t) n + 1));
-  CK(c, sd.f_nrm.ensure((size_t) n + 1));
+  CK(c, sd.f_rec.ensure(2 * ((size_t) n + 1)));
+  CK(c, cudaMemsetAsync(sd.f_rec.p, 0, 2 * sizeof(float4), c->stream));
   CK(c, sd.f_inverse.ensure((size_t) n + 1));
   CK(c, sd.image.ensure(npx));
   CK(c, cudaMemsetAsync(sd.image.p, 0xff, npx * sizeof(unsigned long long), c->stream));
   if (n > 0) {
     if (rc.ev_all) CK(c, cudaStreamWaitEvent(c->stream, rc.ev_all, 0));
     gather_identity_kernel<<<blocks_for(n, 256), 256, 0, c->stream>>>(rc.xyz.p, rc.has_normals ? rc.nrm.p : nullptr, n,
-                                                                      c->dim, sd.f_pts.p, sd.f_nrm.p, sd.f_inverse.p);
+                                                                      c->dim, sd.f_pts.p, sd.f_rec.p, sd.f_inverse.p);
     proj_image_kernel<<<blocks_for(n, 256), 256, 0, c->stream>>>(rc.xyz.p, rc.has_valid ? rc.valid.p : nullptr, n, fp.fx,
                                                                  fp.fy, fp.cx, fp.cy, fp.min_depth, fp.max_depth,
                                                                  fp.width, fp.height, sd.image.p);
@@ -655,8 +661,8 @@ int fill_slice_args(srrg2b_ctx* c, SliceData& sd, int state_slot, const srrg2b_f
   const float nb2 = std::max(sd.nb2_moving_global, sd.fixed_raw.nb2);
   const Scales sc = choose_scales(c->dim, variable, fa.factor, sd.radius2, nb2, fp.max_distance, fa.info_point, fa.info_normal);
   if (sc_out) *sc_out = sc;
-  a.mp = sd.m_pts.p; a.mn = sd.m_nrm.p; a.nm = sd.nm_valid;
-  a.fp = sd.f_pts.p; a.fn = sd.f_nrm.p; a.cell_start = sd.cell_start.p; a.near_bits = sd.near_bits.p;
+  a.mp = sd.m_pts.p; a.mn = sd.m_nrm.p; a.mpair = sd.m_pair.p; a.nm = sd.nm_valid;
+  a.fp = sd.f_pts.p; a.frec = sd.f_rec.p; a.cell_start = sd.cell_start.p; a.near_bits = sd.near_bits.p;
   a.ox = sd.ox; a.oy = sd.oy; a.oz = sd.oz; a.inv_cell = sd.inv_cell;
   a.inv_cell_x = sd.inv_cell * (float) sd.xf; a.Rx = sd.R * sd.xf;
   a.nx = sd.nx; a.ny = sd.ny; a.nz = sd.nz;
@@ -675,7 +681,7 @@ int fill_slice_args(srrg2b_ctx* c, SliceData& sd, int state_slot, const srrg2b_f
   a.c_fpos = sd.c_fpos.p;
   a.gate_in_nn = 0;
   a.far_list = sd.far_list.p; a.far_count = sd.far_count.p;
-  a.work_list = sd.work_list.p; a.work_count = sd.far_count.p + 1;
+  a.work_list = sd.work_list.p; a.work_count = sd.far_count.p + 1; a.tile_ticket = sd.far_count.p + 2;
   a.list_all = &c->d_state->list_all[state_slot];
   a.inline_check = 0; a.use_list = 0;
   a.few_terms = 0;
@@ -684,6 +690,7 @@ int fill_slice_args(srrg2b_ctx* c, SliceData& sd, int state_slot, const srrg2b_f
   a.width = fp.width; a.height = fp.height; a.image = sd.image.p;
   a.c_lb = sd.c_lb.p; a.S_lb = sd.S_lb.p;
   a.track2 = &c->d_state->track2[state_slot];
+  a.radius = sqrtf(sd.radius2) * 1.0001f;
   a.xq_slack = sd.index_is_projective ? 0.f : (1.01f * ldexpf(1.f, -sd.xbits) + 1e-4f) / sd.inv_cell;  // one key quantum + fp32 rounding of the cell coordinate
   {
     const float rho = ((float) sd.R - 4e-3f) / sd.inv_cell;
@@ -739,21 +746,13 @@ int launch_find(srrg2b_ctx* c, const SliceArgs& a, const int* skip) {
   return SRRG2B_OK;
 }
 
-// tiles per CTA of the streaming lineariser for a slice of n correspondences on `ctas` CTAs, and whether a
-// thread's partial sums stay below 2^26 (one REDUX per slot in the flush)
-inline int lin_grid(const srrg2b_ctx* c, int n) { return std::max(1, std::min(blocks_for(n, kTile), c->sm_count)); }
-inline int lin_few_terms(int n, int ctas) {
-  const int tiles = blocks_for(n, kTile);
-  const int per_cta = (tiles + ctas - 1) / ctas;
-  return (2 * per_cta + kFailCap / (kLoopThreads / 32) + 2) <= 30 ? 1 : 0;
-}
+inline int lin_grid(const srrg2b_ctx* c, int n) { return std::max(1, std::min(blocks_for(n, kWTile * kLoopWarps), c->sm_count)); }
 
 // streaming lineariser over every slot of the slice as it is
 int launch_linearize(srrg2b_ctx* c, const SliceArgs& a_in, int factor, const int* skip) {
   if (a_in.nm <= 0) return SRRG2B_OK;
   SliceArgs a = a_in;
   const int blocks = lin_grid(c, a.nm);
-  a.few_terms = lin_few_terms(a.nm, blocks);
   if (c->dim == 3) {
     if (factor == SRRG2B_FACTOR_P2P) lin_tiles_kernel<3, SRRG2B_FACTOR_P2P><<<blocks, kLoopThreads, kLoopSmemBytes, c->stream>>>(a, skip);
     else lin_tiles_kernel<3, SRRG2B_FACTOR_PLANE><<<blocks, kLoopThreads, kLoopSmemBytes, c->stream>>>(a, skip);
@@ -927,13 +926,14 @@ int launch_loop(srrg2b_ctx* c, const Plan& plan) {
   memset(&L, 0, sizeof(L));
   L.ap = c->d_solve; L.st = c->d_state; L.px = c->d_px; L.bar = c->d_bar;
   L.timeout_cycles = c->timeout_cycles;
+  L.dbg = c->d_loop_dbg;
+  L.part = c->d_part;
   L.n_slices = plan.solve.n_slices;
   const int grid = c->sm_count;
   for (int s = 0; s < plan.solve.n_slices; ++s) {
     L.factor[s] = plan.factor[s];
     L.is_points[s] = plan.is_points[s] ? 1 : 0;
     L.sl[s] = plan.sargs[s];
-    L.sl[s].few_terms = lin_few_terms(L.sl[s].nm, grid);
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -1152,7 +1152,15 @@ int srrg2b_ctx_create(int dim, int device, srrg2b_ctx** out) {
     if (const char* env = getenv("SRRG2B_TIMEOUT_MS")) ms = std::max(1.0, atof(env));
     c->timeout_cycles = (long long) (ms * (double) khz);
   }
+  if (getenv("SRRG2B_LOOP_DEBUG")) {
+    const size_t nb = sizeof(unsigned long long) * kDbgIters * 2 * kDbgWords;
+    ok = ok && cudaMalloc((void**) &c->d_loop_dbg, nb) == cudaSuccess && cudaMemset(c->d_loop_dbg, 0, nb) == cudaSuccess;
+  }
   ok = ok && cudaMalloc((void**) &c->d_bar, sizeof(GridBar)) == cudaSuccess;
+  {
+    const size_t nb = sizeof(long long) * (size_t) c->sm_count * SRRG2B_MAX_SLICES * kAcc;
+    ok = ok && cudaMalloc((void**) &c->d_part, nb) == cudaSuccess && cudaMemsetAsync(c->d_part, 0, nb, c->stream) == cudaSuccess;
+  }
   ok = ok && cudaMemsetAsync(c->d_bar, 0, sizeof(GridBar), c->stream) == cudaSuccess;
   if (const char* env = getenv("SRRG2B_EAGER_INDEX")) c->eager_index = atoi(env) != 0;
   if (const char* env = getenv("SRRG2B_GRAPH_NCCL")) c->graph_nccl = atoi(env) != 0;
@@ -1188,6 +1196,39 @@ int srrg2b_ctx_destroy(srrg2b_ctx* c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
   if (c->d_bar) cudaFree(c->d_bar);
+  if (c->d_part) cudaFree(c->d_part);
+  if (c->d_loop_dbg) {
+    std::vector<unsigned long long> t((size_t) kDbgIters * 2 * kDbgWords);
+    if (cudaMemcpy(t.data(), c->d_loop_dbg, t.size() * 8, cudaMemcpyDeviceToHost) == cudaSuccess) {
+      fprintf(stderr, "[srrg2b loop debug] last run, per loop iteration: CTA0 | last CTA : tiles tail arrive [all-arrived solved] released (us from iteration start), fails\n");
+      for (int it = 0; it < kDbgIters; ++it) {
+        const unsigned long long* a = &t[((size_t) it * 2) * kDbgWords];
+        const unsigned long long* b = a + kDbgWords;
+        if (!a[0] || !a[6]) continue;
+        auto us = [](unsigned long long x, unsigned long long x0) { return x ? (double) (long long) (x - x0) * 1e-3 : -1.0; };
+        fprintf(stderr, "  it %2d | %6.1f %6.1f %6.1f [%6.1f %6.1f] %6.1f  f=%llu | %6.1f %6.1f %6.1f %6.1f  f=%llu\n", it, us(a[1], a[0]),
+                us(a[2], a[0]), us(a[3], a[0]), us(a[4], a[0]), us(a[5], a[0]), us(a[6], a[0]), a[7], us(b[1], b[0]), us(b[2], b[0]),
+                us(b[3], b[0]), us(b[6], b[0]), b[7]);
+      }
+    }
+    cudaFree(c->d_loop_dbg);
+#ifdef S2B_FAIL_STATS
+    {
+      unsigned long long fs[8];
+      if (cudaMemcpyFromSymbol(fs, g_fail_stats, sizeof(fs)) == cudaSuccess)
+        fprintf(stderr, "[srrg2b fail stats] all loop iterations of all runs: no bound %llu | budget spent %llu | runner-up too close %llu (mean margin %.1f um) | none too close %llu | out of range %llu\n",
+                fs[0], fs[1], fs[2], fs[2] ? (double) fs[5] / (double) fs[2] - 1000.0 : 0.0, fs[3], fs[4]);
+    }
+#endif
+#if S2B_SOLVE_STAMPS
+    unsigned long long st8[8];
+    if (cudaMemcpyFromSymbol(st8, g_solve_stamps, sizeof(st8)) == cudaSuccess) {
+      fprintf(stderr, "[srrg2b solve stamps] last solve step (us): stage+exchange %.2f | assemble %.2f | cholesky %.2f | box_plus %.2f | transforms+budget %.2f | termination %.2f | write-back %.2f\n",
+              (st8[1] - st8[0]) * 1e-3, (st8[2] - st8[1]) * 1e-3, (st8[3] - st8[2]) * 1e-3, (st8[4] - st8[3]) * 1e-3,
+              (st8[5] - st8[4]) * 1e-3, (st8[6] - st8[5]) * 1e-3, (st8[7] - st8[6]) * 1e-3);
+    }
+#endif
+  }
   if (c->d_px && c->comm && g_nccl.AllReduce && c->d_epoch) {
     // a peer may still be adding this rank's last mailbox words: leave together (contexts of a
     // communicator are destroyed collectively, like the communicator itself)
@@ -1209,8 +1250,8 @@ int srrg2b_ctx_destroy(srrg2b_ctx* c) {
     }
     s.fixed_raw.xyz.release(); s.fixed_raw.nrm.release(); s.fixed_raw.valid.release();
     s.moving_raw.xyz.release(); s.moving_raw.nrm.release(); s.moving_raw.valid.release();
-    s.f_pts.release(); s.f_nrm.release(); s.f_inverse.release(); s.cell_start.release(); s.near_bits.release();
-    s.m_pts.release(); s.m_nrm.release(); s.m_inverse.release();
+    s.f_pts.release(); s.f_rec.release(); s.f_inverse.release(); s.cell_start.release(); s.near_bits.release();
+    s.m_pts.release(); s.m_nrm.release(); s.m_pair.release(); s.m_inverse.release();
     s.image.release(); s.c_lb.release(); s.S_lb.release(); s.c_fidx.release(); s.c_fpos.release(); s.far_list.release(); s.far_count.release(); s.work_list.release(); s.c_resp.release(); s.c_chi.release(); s.c_stat.release();
   }
   c->keys_a.release(); c->keys_b.release(); c->vals_a.release(); c->vals_b.release();
@@ -1370,8 +1411,9 @@ int srrg2b_find_correspondences(srrg2b_ctx* c, int slice_id, const float* S, con
   a.inline_check = 1;
   Mat4f S4;
   embed(c->dim, S, S4);
-  // how far any query can have moved since the previous stand-alone pass of this slice (the bounds that pass
-  // certified are spent by that much); a loop run in between, or new clouds, reset the bounds anyway
+  // how far any query can be from its position at the slice's ANCHOR pass (the first stand-alone pass after a
+  // reset): certified bounds are stored relative to the anchor (encode_bound); a loop run in between, or new
+  // clouds, reset the bounds
   float motion = 0.f, slack = 0.f;
   {
     double dr = 0.0, dt = 0.0, tn = 0.0;
@@ -1388,21 +1430,23 @@ int srrg2b_find_correspondences(srrg2b_ctx* c, int slice_id, const float* S, con
     const float radius = sqrtf(sd.radius2) * 1.0001f;
     motion = (float) ((sqrt(dr) * (double) radius + sqrt(dt)) * (1.0 + 1e-6)) * (1.f + 2.4e-7f);
     const float qmax = radius * 1.0001f + (float) sqrt(tn);
-    slack = 2e-6f * qmax + 1e-6f;
+    slack = 1e-6f * qmax + 2e-7f;
     if (!sd.have_last_S) {  // no previous pass: whatever bounds exist are not trusted
       CK(c, cudaMemsetAsync(sd.c_lb.p, 0, sizeof(float) * (size_t) std::max(sd.nm_valid, 1), c->stream));
     }
   }
   set_S_kernel<<<1, 32, 0, c->stream>>>(c->d_state, 0, S4, c->track2_mode == 1 ? 1 : 0, sd.S_lb.p, motion, slack);
   c->launches++;
-  CK(c, cudaMemsetAsync(a.far_count, 0, 2 * sizeof(int), c->stream));
+  CK(c, cudaMemsetAsync(a.far_count, 0, 3 * sizeof(int), c->stream));
   rcode = launch_find(c, a, nullptr);
   if (rcode) return rcode;
   commit_S_kernel<<<1, 32, 0, c->stream>>>(a.S, sd.S_lb.p);
   c->launches++;
   CK(c, cudaGetLastError());
-  sd.last_S = S4;
-  sd.have_last_S = true;
+  if (!sd.have_last_S) {  // the first stand-alone pass after a reset anchors the bounds
+    sd.last_S = S4;
+    sd.have_last_S = true;
+  }
   sd.corr_valid = true;
   sd.stat_valid = false;
   return export_corr(c, sd, 0, false, fixed_idx, moving_idx, response, nullptr, nullptr, n_out);
@@ -1480,6 +1524,7 @@ int srrg2b_linearize(srrg2b_ctx* c, int slice_id, const float* S, int variable, 
   embed(c->dim, S, S4);
   set_S_kernel<<<1, 32, 0, c->stream>>>(c->d_state, 0, S4, 0, nullptr, 0.f, 0.f);
   c->launches++;
+  CK(c, cudaMemsetAsync(a.tile_ticket, 0, sizeof(int), c->stream));
   rcode = launch_linearize(c, a, fa->factor, nullptr);
   if (rcode) return rcode;
   CK(c, cudaGetLastError());

@@ -45,6 +45,7 @@ struct DevHeader {
   int certified;                             // every NN point slice holds certified bounds: the device loop takes over
   int error;                                 // sticky: 1 = peer exchange timed out, 2 = grid barrier timed out
   int pad_[2];
+  int ep_next[SRRG2B_MAX_SLICES];            // epoch of the slice's next pass (see the bound state below)
 };
 static_assert(sizeof(DevHeader) % 16 == 0, "DevHeader is copied in 16-byte pieces");
 
@@ -57,12 +58,11 @@ struct SolveSlice {
   Mat4f ris, Z;
   float info[6];
   double invk[kKCount];       // 2^-k of the slice's fixed-point scales, per accumulated class
-  float* S_lb;                // slice's bound state: [0..15] transform of the last pass, [16] motion budget B,
-                              // [17] B + absolute slack (what the coherence check subtracts)
+  float* S_lb;                // slice's bound state (kSlb* layout below)
   float cell, radius;         // NN cell edge / max |m| of the moving cloud (global)
   int track2_mode;            // 0 never, 1 always, 2 automatic (small motion)
   float track2_frac;          // automatic: certify once the per-iteration motion bound is below this many cells
-  int* counters;              // slice's work-list counters {far, work}: zeroed for the next iteration
+  int* counters;              // slice's counters {far list, work list, tile ticket}: zeroed for the next iteration
   int nn_points;              // point slice searched by the grid NN finder (takes part in `certified`)
   int pad_;
 };
@@ -78,9 +78,10 @@ struct alignas(16) SolveArgs {
 struct SliceArgs {
   const float4* __restrict__ mp;   // moving points, Hilbert order: x y z | local index bits
   const float4* __restrict__ mn;   // moving normals
+  const float4* __restrict__ mpair;  // the same cloud, two consecutive points per 48-byte record (pair_pack_kernel)
   int nm;
-  const float4* __restrict__ fp;   // fixed points, cell order: x y z | original index bits
-  const float4* __restrict__ fn;
+  const float4* __restrict__ fp;   // fixed points, cell order: x y z | original index bits (compact: the searches scan it)
+  const float4* __restrict__ frec; // the same points as 32-byte records {point | normal} (the gathers of the lineariser)
   const int* __restrict__ cell_start;
   const unsigned* __restrict__ near_bits;  // dilated occupancy (see near_bits_kernel)
   float ox, oy, oz, inv_cell;
@@ -102,6 +103,7 @@ struct SliceArgs {
   int* far_count;
   int* work_list;      // queries whose coherence check failed (need a search + a second linearise pass)
   int* work_count;
+  int* tile_ticket;    // next tile of the streaming lineariser (tiles are drawn dynamically by the CTAs)
   const int* list_all; // device flag: no usable bounds -> the work list is implicitly [0, nm)
   int inline_check;    // 1: nn_kernel does the coherence check itself (stand-alone finder)
   int use_list;        // 1: nn / linearise kernels iterate over the work list
@@ -109,6 +111,7 @@ struct SliceArgs {
   float* c_lb;         // certified lower bound per query PLUS the motion budget at certification (0: none)
   const float* S_lb;   // bound state of the slice (see SolveSlice::S_lb)
   const int* track2;   // device flag: searches track the second neighbour (certify bounds)
+  float radius;        // max |m| over the (whole, unsharded) moving cloud
   float rho_s2;        // squared radius the (2R+1) cell neighbourhood is guaranteed to cover
   float xq_slack;      // x quantum of the cell-order sort (see cell_key_kernel), with rounding slack
   // projective finder (srrg2_proslam cue): pinhole + index image of the fixed cloud
@@ -344,9 +347,11 @@ __global__ void curve_key_kernel(const float* __restrict__ xyz, const unsigned c
 }
 
 // sorted float4 SoA: points carry the original index in .w
+// rec (fixed cloud): additionally the interleaved 32-byte record {point | normal} per sorted position, so that
+// the lineariser's gather of a correspondence's fixed point AND normal costs exactly one DRAM sector
 __global__ void gather_kernel(const float* __restrict__ xyz, const float* __restrict__ nrm,
                               const int* __restrict__ order, int n_valid, int dim, float4* __restrict__ op,
-                              float4* __restrict__ on, int* __restrict__ inverse) {
+                              float4* __restrict__ on, int* __restrict__ inverse, float4* __restrict__ rec) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_valid) return;
   const int src = order[i];
@@ -362,8 +367,24 @@ __global__ void gather_kernel(const float* __restrict__ xyz, const float* __rest
     q.y = nrm[(size_t) src * dim + 1];
     q.z = dim == 3 ? nrm[(size_t) src * dim + 2] : 0.f;
   }
-  on[i] = q;
+  if (on) on[i] = q;
+  if (rec) { rec[2 * (size_t) i] = p; rec[2 * (size_t) i + 1] = q; }
   if (inverse) inverse[src] = i;
+}
+
+// Pair-interleaved copy of the sorted moving cloud for the packed (fp32x2) lineariser: record p holds points
+// 2p and 2p + 1 component by component -- (x0 x1 y0 y1) (z0 z1 nx0 nx1) (ny0 ny1 nz0 nz1) -- so that one
+// 16-byte shared-memory load yields two ready-made register pairs.  24 bytes per point instead of 32.
+__global__ void pair_pack_kernel(const float4* __restrict__ mp, const float4* __restrict__ mn, int n,
+                                 float4* __restrict__ out) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (2 * p >= n) return;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 a = mp[2 * p], na = mn[2 * p];
+  const float4 b = (2 * p + 1 < n) ? mp[2 * p + 1] : z4, nb = (2 * p + 1 < n) ? mn[2 * p + 1] : z4;
+  out[3 * p] = make_float4(a.x, b.x, a.y, b.y);
+  out[3 * p + 1] = make_float4(a.z, b.z, na.x, nb.x);
+  out[3 * p + 2] = make_float4(na.y, nb.y, na.z, nb.z);
 }
 
 // cell_start[c] = first sorted position whose cell id >= c (lower bound), c in [0, ncells]:
@@ -571,11 +592,30 @@ __device__ __forceinline__ int slot_candidate(int slot) {
   return slot == kSlotSuppressed ? -1 : c;
 }
 
-// A certified bound is stored together with the slice's motion budget B at certification time (rounded
-// down); the coherence check subtracts the CURRENT budget plus an absolute slack (S_lb[17]), see
-// icp_solve_serial.  0 = no bound.
-__device__ __forceinline__ float encode_bound(float lb, float budget) {
-  return lb > 0.f ? (lb + budget) * (1.f - 2.4e-7f) : 0.f;
+// Bound state of a slice (float words of SolveSlice::S_lb / SliceArgs::S_lb):
+//   [0..15]  transform of the last pass (export recomputes the responses with it)
+//   [16]     D_cert: how far any query is from its position at the CURRENT EPOCH's transform while the running
+//            pass certifies bounds (0 inside the ICP loop: a pass certifies exactly at its epoch's transform)
+//   [18]     id of the current epoch (integer bits)
+//   [32..95] dtab[e]: what the coherence check subtracts from a bound of epoch e = a bound of any query's
+//            displacement between the current transform and epoch e's (+ absolute rounding slack); 3e38 = dead
+//   [96.. ]  transforms of the epochs (12 floats each)
+// Every pass of the ICP loop is an epoch of its own, so a bound is always measured against the transform it
+// was certified at -- a converged estimate spends nothing of it, however long the run.  A certified bound
+// lb is stored as (lb - D_cert), rounded down, with the epoch id in its 6 low mantissa bits; 0 = no bound.
+constexpr int kEpochs = 64, kSlbDcert = 16, kSlbEpoch = 18, kSlbDtab = 32, kSlbEpS = 96, kSlbFloats = 96 + 12 * kEpochs;
+__device__ __forceinline__ float encode_bound(float lb, const float* S_lb) {
+  const float d_cert = *reinterpret_cast<const volatile float*>(S_lb + kSlbDcert);
+  const int ep = *reinterpret_cast<const volatile int*>(S_lb + kSlbEpoch);
+  const float v = (lb - d_cert) * (1.f - 2.4e-7f) - 1e-9f;
+  if (!(lb > 0.f) || !(v > 1e-30f)) return 0.f;
+  return __int_as_float((__float_as_int(v) & ~(kEpochs - 1)) | (ep & (kEpochs - 1)));
+}
+// bound minus everything the query can have moved since certification (<= 0: nothing left / no bound)
+__device__ __forceinline__ float decode_bound(float stored, const float* dtab) {
+  if (!(stored > 0.f)) return 0.f;
+  const int b = __float_as_int(stored);
+  return __int_as_float(b & ~(kEpochs - 1)) - dtab[b & (kEpochs - 1)];
 }
 
 // slot / bound of a finished query.  Inside the ICP loop the normal gate is evaluated by the
@@ -585,7 +625,7 @@ __device__ __forceinline__ int nn_finish_keep(const SliceArgs& a, const float* S
   int slot = q.bpos;
   if (q.bpos >= 0 && a.gate && a.gate_in_nn) {
     const float4 nm = a.mn[i];
-    const float4 nf = __ldg(a.fn + q.bpos);
+    const float4 nf = __ldg(a.frec + 2 * (size_t) q.bpos + 1);
     float t;
     t = S[0] * nm.x; t = fmaf(S[1], nm.y, t); if (DIM == 3) t = fmaf(S[2], nm.z, t); const float nqx = t;
     t = S[4] * nm.x; t = fmaf(S[5], nm.y, t); if (DIM == 3) t = fmaf(S[6], nm.z, t); const float nqy = t;
@@ -604,7 +644,7 @@ __device__ __forceinline__ int nn_finish_keep(const SliceArgs& a, const float* S
 template <int DIM>
 __device__ __forceinline__ int nn_finish(const SliceArgs& a, const float* S, const NNQuery& q, int i, float lb,
                                          int old_slot) {
-  a.c_lb[i] = encode_bound(lb, *reinterpret_cast<const volatile float*>(a.S_lb + 16));
+  a.c_lb[i] = encode_bound(lb, a.S_lb);
   return nn_finish_keep<DIM>(a, S, q, i, old_slot);
 }
 
@@ -613,7 +653,7 @@ __device__ __forceinline__ int nn_finish(const SliceArgs& a, const float* S, con
 // distance to ring 2 is handed to phase 2 through a worklist, so that the rare expensive queries
 // (outliers, large initial misalignment) do not serialise the warps of the cheap ones.
 template <int DIM, bool TRACK2>
-__device__ __forceinline__ void nn_phase1_body(const SliceArgs& a, const float* S, float bsub, float cell,
+__device__ __forceinline__ void nn_phase1_body(const SliceArgs& a, const float* S, float cell,
                                                float ring2, float ring2_sq, bool all, int n_work) {
   for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < n_work; w += gridDim.x * blockDim.x) {
     const int i = all ? w : __ldcg(a.work_list + w);
@@ -625,7 +665,7 @@ __device__ __forceinline__ void nn_phase1_body(const SliceArgs& a, const float* 
     const float lb_old = a.inline_check ? __ldcg(a.c_lb + i) : 0.f;
     if (lb_old > 0.f) {
       // exact temporal coherence: the bound minus everything the query can have moved since certification
-      const float lbn = lb_old - bsub;
+      const float lbn = decode_bound(lb_old, a.S_lb + kSlbDtab);
       if (lbn > 0.f) {
         if (p0 >= 0) {
           nn_consider<DIM, false>(a, q, p0);
@@ -711,14 +751,13 @@ __global__ void __launch_bounds__(256) nn_kernel(const SliceArgs a, const int* s
   if (small_work_list(a, all, n_work)) return;
   __shared__ float S[16];
   if (threadIdx.x < 16) S[threadIdx.x] = a.S[threadIdx.x];
-  const float bsub = *reinterpret_cast<const volatile float*>(a.S_lb + 17);
   __syncthreads();
   const float cell = __fdiv_rn(1.f, a.inv_cell);
   // distance below which a point cannot lie in ring 2 or beyond (for R == 1: the covered radius)
   const float ring2 = (a.R >= 2) ? (1.f - 4e-3f) * cell : __fsqrt_rn(a.rho_s2);
   const float ring2_sq = (a.R >= 2) ? ring2 * ring2 : 3.0e38f;
-  if (track2) nn_phase1_body<DIM, true>(a, S, bsub, cell, ring2, ring2_sq, all, n_work);
-  else nn_phase1_body<DIM, false>(a, S, bsub, cell, ring2, ring2_sq, all, n_work);
+  if (track2) nn_phase1_body<DIM, true>(a, S, cell, ring2, ring2_sq, all, n_work);
+  else nn_phase1_body<DIM, false>(a, S, cell, ring2, ring2_sq, all, n_work);
 }
 
 // Phase 2: the queries phase 1 could not settle (worklist).  These are few but expensive
@@ -863,7 +902,7 @@ __device__ __forceinline__ void nn_far_body(const SliceArgs& a, const float* S, 
       const int slot = nn_finish<DIM>(a, S, q, i, TRACK2 ? __fsqrt_rn(q.sd2) * (1.f - 1e-5f) : 0.f, old_slot);
       if (lin) {  // tail mode: linearise the query right away (the gate is re-evaluated there)
         const int bpos = a.gate ? slot_candidate(slot) : slot;
-        if (bpos >= 0) lin_one_slot<DIM, FACTOR>(a, *lk, i, slot, bpos, m, a.mn[i], __ldg(a.fp + bpos), __ldg(a.fn + bpos), *lin);
+        if (bpos >= 0) lin_one_slot<DIM, FACTOR>(a, *lk, i, slot, bpos, m, a.mn[i], __ldg(a.frec + 2 * (size_t) bpos), __ldg(a.frec + 2 * (size_t) bpos + 1), *lin);
         else if (a.c_stat) a.c_stat[i] = SRRG2B_STAT_NONE;
       }
     }
@@ -901,7 +940,7 @@ __global__ void proj_image_kernel(const float* __restrict__ xyz, const unsigned 
 
 // float4 SoA in ORIGINAL order (position == index) for the projective finder
 __global__ void gather_identity_kernel(const float* __restrict__ xyz, const float* __restrict__ nrm, int n, int dim,
-                                       float4* __restrict__ op, float4* __restrict__ on, int* __restrict__ inverse) {
+                                       float4* __restrict__ op, float4* __restrict__ rec, int* __restrict__ inverse) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float4 p;
@@ -916,7 +955,8 @@ __global__ void gather_identity_kernel(const float* __restrict__ xyz, const floa
     q.y = nrm[(size_t) i * dim + 1];
     q.z = dim == 3 ? nrm[(size_t) i * dim + 2] : 0.f;
   }
-  on[i] = q;
+  rec[2 * (size_t) i] = p;
+  rec[2 * (size_t) i + 1] = q;
   if (inverse) inverse[i] = i;
 }
 
@@ -975,8 +1015,11 @@ struct FlushSmem {
   long long w[kMaxWarps][kAcc];
 };
 
+// cta_dst: when non-null the CTA's sums are ADDED to these shared-memory words (one writer per slot) instead of
+// going to the global accumulators with atomics -- the persistent loop publishes them once per iteration
 template <int DIM>
-__device__ __forceinline__ void lin_flush(unsigned long long* acc, bool few, const LinAcc<DIM>& A, FlushSmem& sm) {
+__device__ __forceinline__ void lin_flush(unsigned long long* acc, bool few, const LinAcc<DIM>& A, FlushSmem& sm,
+                                          long long* cta_dst = nullptr) {
   constexpr int P = LinAcc<DIM>::P, NH = LinAcc<DIM>::NH;
   auto wsum = [few](int v) -> long long {
     if (few) return (long long) __reduce_add_sync(0xffffffffu, v);
@@ -1022,9 +1065,27 @@ __device__ __forceinline__ void lin_flush(unsigned long long* acc, bool few, con
     long long v = 0;
     const int nw = blockDim.x >> 5;
     for (int w = 0; w < nw; ++w) v += sm.w[w][threadIdx.x];
-    if (v) atomicAdd(&acc[threadIdx.x], (unsigned long long) v);
+    if (cta_dst) cta_dst[threadIdx.x] += v;
+    else if (v) atomicAdd(&acc[threadIdx.x], (unsigned long long) v);
   }
   __syncthreads();  // sm may be reused right away (the persistent loop flushes once per slice and iteration)
+}
+
+// one thread's partial sums (a few scalar-path correspondences) into shared-memory accumulators, bias removed
+template <int DIM>
+__device__ __forceinline__ void lin_push_tail(const LinAcc<DIM>& A, long long* tail) {
+  constexpr int P = LinAcc<DIM>::P, NH = LinAcc<DIM>::NH;
+  if (A.n_terms == 0 && A.n_ss == 0) return;
+  auto add = [tail](int slot, long long v) { if (v) atomicAdd(reinterpret_cast<unsigned long long*>(tail + slot), (unsigned long long) v); };
+  const int bias = A.n_terms * kFixBias;
+#pragma unroll
+  for (int k = 0; k < NH; ++k) add(k, (long long) (A.aH[k] - bias));
+#pragma unroll
+  for (int k = 0; k < P; ++k) add(kAccB + k, (long long) (A.ab[k] - bias));
+  add(kAccChiIn, (long long) (A.chi_all - A.chi_out)); add(kAccChiIn + 1, (long long) (A.chi_all_lo - A.chi_out_lo));
+  add(kAccChiOut, (long long) (A.chi_out - bias)); add(kAccChiOut + 1, (long long) (A.chi_out_lo - bias));
+  add(kAccNIn, A.n_io & 0xffff); add(kAccNOut, (unsigned) A.n_io >> 16);
+  add(kAccNSup, A.n_ss & 0xffff); add(kAccNSat, (unsigned) A.n_ss >> 16);
 }
 
 // Phase 2 / tail kernel.  Large work lists: the far list of phase 1 (see nn_far_body).  Short work
@@ -1155,13 +1216,18 @@ __global__ void icp_init_kernel(const SolveArgs* ap, DevState* st, const Mat4f* 
     // a fresh compute() starts from an arbitrary guess: search everything; the inlier-only second
     // run continues from certified bounds
     if (!keep_stats) st->list_all[s] = 1;  // (the last solve step already set it for a continued run)
-    if (a.sl[s].kind == SRRG2B_SLICE_POINTS && a.sl[s].counters) { a.sl[s].counters[0] = 0; a.sl[s].counters[1] = 0; }
+    if (a.sl[s].kind == SRRG2B_SLICE_POINTS && a.sl[s].counters) { a.sl[s].counters[0] = 0; a.sl[s].counters[1] = 0; a.sl[s].counters[2] = 0; }
     if (!keep_stats && a.sl[s].kind == SRRG2B_SLICE_POINTS && a.sl[s].S_lb) {
-      // a fresh run rewrites every bound in its first pass: the motion budget restarts at zero
+      // a fresh run rewrites every bound in its first pass: that pass is epoch 0
       const Mat4f& S = st->S[s];
       const float tn = sqrtf(S.m[3] * S.m[3] + S.m[7] * S.m[7] + S.m[11] * S.m[11]);
-      a.sl[s].S_lb[16] = 0.f;
-      a.sl[s].S_lb[17] = 2e-6f * (a.sl[s].radius * 1.0001f + tn) + 1e-6f;
+      float* B = a.sl[s].S_lb;
+      st->ep_next[s] = 1;
+      B[kSlbDcert] = 0.f;
+      reinterpret_cast<int*>(B)[kSlbEpoch] = 0;
+      for (int e = 0; e < kEpochs; ++e) B[kSlbDtab + e] = 3e38f;
+      B[kSlbDtab] = 1e-6f * (a.sl[s].radius * 1.0001f + tn) + 2e-7f;
+      for (int j = 0; j < 12; ++j) B[kSlbEpS + j] = S.m[j];
     }
   }
   if (!keep_stats) st->certified = 0;
@@ -1186,9 +1252,12 @@ __global__ void set_S_kernel(DevState* st, int slice, Mat4f S, int track2, float
     for (int k = 0; k < kAcc; ++k) st->acc[slice][k] = 0ull;
     st->stop = 0;
     if (S_lb) {
-      const float B = (S_lb[16] + motion) * (1.f + 2.4e-7f);
-      S_lb[16] = B;
-      S_lb[17] = (B + slack) * (1.f + 2.4e-7f);
+      // stand-alone passes use epoch 0 only, anchored at the first pass after a reset.  motion: bound of any
+      // query's displacement between S and that anchor (host-computed): bounds certified now are stored
+      // relative to the anchor, the check subtracts the same displacement (+ slack)
+      S_lb[kSlbDcert] = motion;
+      reinterpret_cast<int*>(S_lb)[kSlbEpoch] = 0;
+      S_lb[kSlbDtab] = (motion + slack) * (1.f + 2.4e-7f);
     }
   }
 }
@@ -1196,6 +1265,18 @@ __global__ void set_S_kernel(DevState* st, int slice, Mat4f S, int track2, float
 // body of one _runSolver iteration after the per-slice kernels
 // (R/registration/aligners/multi_aligner_impl.cpp:106-126), serial part: runs on one thread against the
 // shared-memory copy of the state; the IterationStats entry goes straight to global memory
+#ifndef S2B_SOLVE_STAMPS
+#define S2B_SOLVE_STAMPS 0
+#endif
+__device__ unsigned long long g_solve_stamps[8];
+__device__ __forceinline__ void solve_stamp(int k) {
+#if S2B_SOLVE_STAMPS
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  g_solve_stamps[k] = t;
+#endif
+}
+
 template <int DIM>
 __device__ void icp_solve_serial(const SolveArgs& a, DevHeader& st, srrg2b_iter_stats* stats_out) {
   constexpr int P = (DIM == 3) ? 6 : 3;
@@ -1255,6 +1336,7 @@ __device__ void icp_solve_serial(const SolveArgs& a, DevHeader& st, srrg2b_iter_
     total += n;
     good = good || (n > (long long) sl.min_corr);  // aligner_slice_processor_impl.cpp:77-79
   }
+  solve_stamp(2);
   st.iterations_run += 1;
   st.iterations_left -= 1;
   if (st.iterations_left <= 0) st.stop = 1;
@@ -1264,11 +1346,14 @@ __device__ void icp_solve_serial(const SolveArgs& a, DevHeader& st, srrg2b_iter_
     return;
   }
   double dx[6] = {0, 0, 0, 0, 0, 0};
-  if (spd_solve_t<P>(H, b, dx)) {
+  const bool solved = spd_solve_t<P>(H, b, dx);
+  solve_stamp(3);
+  if (solved) {
     box_plus(DIM, a.variable, dx, X);
     st.X = X;
     s.solver_status = 1;
   }
+  solve_stamp(4);
   if (st.n_stats < kMaxStats) stats_out[st.n_stats] = s;
   st.last_stats = s;
   st.n_stats += 1;
@@ -1277,11 +1362,11 @@ __device__ void icp_solve_serial(const SolveArgs& a, DevHeader& st, srrg2b_iter_
     Mat4f Sn;
     compose(a.sl[k].ris, X, Sn);
     if (a.sl[k].kind == SRRG2B_SLICE_POINTS) {
-      // upper bound of how far any query of the slice moves between this iteration and the next:
-      // |dS m| <= |dR|_F |m|_max + |dt|.  It feeds (i) the decision to certify bounds in the next NN pass
-      // (track2: once the motion is small against the cell edge) and (ii) the slice's motion BUDGET: the
-      // coherence check of a later iteration subtracts everything accumulated since a bound was certified
-      double dr = 0.0, dt = 0.0, tn = 0.0;
+      // |dS m| <= |dR|_F |m|_max + |dt| bounds how far any query of the slice moves between this iteration and
+      // the next: it decides whether the next NN pass certifies bounds (track2: once the motion is small against
+      // the cell edge).  The displacement tables of the epochs are refreshed by the whole CTA afterwards
+      // (solve_refresh_epochs).
+      double dr = 0.0, dt = 0.0;
       for (int r = 0; r < 3; ++r) {
         for (int c = 0; c < 3; ++c) {
           const double d = (double) Sn.m[r * 4 + c] - (double) st.S[k].m[r * 4 + c];
@@ -1289,27 +1374,63 @@ __device__ void icp_solve_serial(const SolveArgs& a, DevHeader& st, srrg2b_iter_
         }
         const double d = (double) Sn.m[r * 4 + 3] - (double) st.S[k].m[r * 4 + 3];
         dt += d * d;
-        tn += (double) Sn.m[r * 4 + 3] * (double) Sn.m[r * 4 + 3];
       }
-      const double motion_d = (sqrt(dr) * (double) a.sl[k].radius + sqrt(dt)) * (1.0 + 1e-6);
-      const float motion = (float) motion_d * (1.f + 2.4e-7f);
+      const float motion = (float) ((sqrt(dr) * (double) a.sl[k].radius + sqrt(dt)) * (1.0 + 1e-6)) * (1.f + 2.4e-7f);
       const int mode = a.sl[k].track2_mode;
       st.list_all[k] = st.track2[k] ? 0 : 1;  // bounds exist only if the pass just done certified them
       st.track2[k] = (mode == 1) || (mode == 2 && motion < a.sl[k].track2_frac * a.sl[k].cell) ? 1 : 0;
+      // every pass is an epoch of the slice's bounds; a full pass rewrites every bound and restarts the ids,
+      // and so does running out of ids
+      if (st.ep_next[k] >= kEpochs) st.list_all[k] = 1;
+      if (st.list_all[k]) st.ep_next[k] = 0;
       if (a.sl[k].nn_points && st.list_all[k]) certified = 0;
-      if (a.sl[k].S_lb) {
-        // budget after this step, and what the check subtracts: budget + absolute slack for the fp32
-        // rounding of the two transformed queries (a few ulp of the largest coordinate) and of the sums
-        const float B = (a.sl[k].S_lb[16] + motion) * (1.f + 2.4e-7f);
-        const float qmax = a.sl[k].radius * 1.0001f + (float) sqrt(tn);
-        a.sl[k].S_lb[16] = B;
-        a.sl[k].S_lb[17] = (B + (2e-6f * qmax + 1e-6f * (1.f + B))) * (1.f + 2.4e-7f);
-      }
     }
     st.S[k] = Sn;
   }
   st.certified = certified;
+  solve_stamp(5);
   if (a.use_tc && has_to_stop(&st, a, s, total)) st.stop = 1;
+  solve_stamp(6);
+}
+
+// What the coherence check subtracts from a bound of an epoch whose transform is E (12 floats), at the transform
+// Sn: a bound of any query's displacement between the two, |dS m| <= |dR|_F |m|_max + |dt|, plus absolute slack
+// for the fp32 rounding of the two transformed queries (each component: 4 roundings of partial sums bounded by
+// qmax = |m|_max + |t|, i.e. <= 4.1e-7 qmax per query as a vector) and of the bound arithmetic.
+__device__ __forceinline__ float epoch_displacement(const float* Sn, const float* E, float radius, bool same) {
+  double dr = 0.0, dt = 0.0, tn = 0.0;
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c) {
+      const double d = same ? 0.0 : (double) Sn[r * 4 + c] - (double) __ldcg(E + r * 4 + c);
+      dr += d * d;
+    }
+    const double d = same ? 0.0 : (double) Sn[r * 4 + 3] - (double) __ldcg(E + r * 4 + 3);
+    dt += d * d;
+    tn += (double) Sn[r * 4 + 3] * (double) Sn[r * 4 + 3];
+  }
+  const float Dm = (float) ((sqrt(dr) * (double) radius + sqrt(dt)) * (1.0 + 1e-6)) * (1.f + 2.4e-7f);
+  const float qmax = radius * 1.0001f + (float) sqrt(tn);
+  return (Dm + (1e-6f * qmax + 2e-7f * (1.f + Dm))) * (1.f + 2.4e-7f);
+}
+
+// After the serial part: the next pass of every point slice becomes epoch ep_next: its transform and id are
+// recorded in the slice's bound state.  The displacement table dtab is computed by whoever runs the pass
+// (the loop kernel's CTAs, in parallel with their pipeline prologue: loop_load_lin_const), so the solve step
+// only publishes.  (Every thread of the CTA calls this; sh.S[k] already holds the NEXT transform.)
+__device__ __forceinline__ void solve_refresh_epochs(const SolveArgs& a, DevHeader& sh) {
+  const int tid = threadIdx.x;
+  for (int k = 0; k < a.n_slices; ++k) {
+    if (a.sl[k].kind != SRRG2B_SLICE_POINTS || !a.sl[k].S_lb) continue;
+    float* B = a.sl[k].S_lb;
+    const int ep = sh.ep_next[k];  // (< kEpochs: the serial part restarts the ids in time)
+    if (tid < 12) B[kSlbEpS + 12 * ep + tid] = sh.S[k].m[tid];
+    if (tid == 32) { B[kSlbDcert] = 0.f; reinterpret_cast<int*>(B)[kSlbEpoch] = ep; }
+  }
+  __syncthreads();
+  if (tid == 0)
+    for (int k = 0; k < a.n_slices; ++k)
+      if (a.sl[k].kind == SRRG2B_SLICE_POINTS && a.sl[k].S_lb) sh.ep_next[k] += 1;
+  __syncthreads();
 }
 
 constexpr int kSolveThreads = 256;
@@ -1341,21 +1462,27 @@ __device__ __forceinline__ unsigned long long ld_volatile_sys(const unsigned lon
   return v;
 }
 
+constexpr int kPartGroups = 8;
 // shared-memory staging of the solve step
 struct SolveSmem {
   alignas(16) SolveArgs a;
   alignas(16) DevHeader sh;
   PeerExchange pe;
   int timed_out;
+  long long part[kPartGroups][SRRG2B_MAX_SLICES * kAcc];
 };
 
 // The solve step of one iteration, executed by ONE CTA with at least kSolveThreads threads (the first
 // kSolveThreads take part): stage arguments + state, all-reduce over the peers, serial solve, write back.
 // Returns (to every participating thread) whether the iteration loop has to stop.
+// part / n_part: per-CTA partial sums [n_part][SRRG2B_MAX_SLICES * kAcc] published by the persistent loop's
+// CTAs (added to the global accumulators here, in a fixed order -- integers, so any order gives the same bits)
 template <int DIM>
-__device__ __forceinline__ bool icp_solve_block(const SolveArgs* ap, DevState* st, const PeerExchange* px, SolveSmem& sm) {
+__device__ __forceinline__ bool icp_solve_block(const SolveArgs* ap, DevState* st, const PeerExchange* px, SolveSmem& sm,
+                                                const long long* part_rows = nullptr, int n_part = 0) {
   const int tid = threadIdx.x;
   const bool part = tid < kSolveThreads;
+  if (tid == 0) solve_stamp(0);
   SolveArgs& a = sm.a;
   DevHeader& sh = sm.sh;
   PeerExchange& pe = sm.pe;
@@ -1376,6 +1503,34 @@ __device__ __forceinline__ bool icp_solve_block(const SolveArgs* ap, DevState* s
   }
   __syncthreads();
   if (sh.stop) return true;  // (every rank holds the same state, so every rank returns here or none does)
+  if (part_rows) {
+    // groups of 64 threads sum a share of the rows each, eight independent loads in flight per thread
+    const int n_words = a.n_slices * kAcc;
+    const int n_groups = min((int) blockDim.x >> 6, kPartGroups);
+    if (tid < n_groups * 64) {
+      const int g = tid >> 6, k0 = tid & 63;
+      for (int k = k0; k < n_words; k += 64) {
+        long long v = 0;
+        int r = g;
+        for (; r + 7 * n_groups < n_part; r += 8 * n_groups) {
+          long long t[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) t[u] = __ldcg(part_rows + (size_t) (r + u * n_groups) * (SRRG2B_MAX_SLICES * kAcc) + k);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) v += t[u];
+        }
+        for (; r < n_part; r += n_groups) v += __ldcg(part_rows + (size_t) r * (SRRG2B_MAX_SLICES * kAcc) + k);
+        sm.part[g][k] = v;
+      }
+    }
+    __syncthreads();
+    for (int k = tid; k < n_words; k += blockDim.x) {
+      long long v = 0;
+      for (int g = 0; g < n_groups; ++g) v += sm.part[g][k];
+      (&sh.acc[0][0])[k] += (unsigned long long) v;
+    }
+    __syncthreads();
+  }
   if (px) {
     // all-reduce of the accumulators over peer memory (see PeerExchange)
     const unsigned long long e = sh.epoch + 1ull;
@@ -1425,10 +1580,11 @@ __device__ __forceinline__ bool icp_solve_block(const SolveArgs* ap, DevState* s
   for (int k = 0; k < a.n_slices; ++k) {
     if (a.sl[k].kind != SRRG2B_SLICE_POINTS) continue;
     if (a.sl[k].S_lb && tid < 16) a.sl[k].S_lb[tid] = sh.S[k].m[tid];
-    if (a.sl[k].counters && tid >= 32 && tid < 34) a.sl[k].counters[tid - 32] = 0;
+    if (a.sl[k].counters && tid >= 32 && tid < 35) a.sl[k].counters[tid - 32] = 0;
   }
-  if (tid == 0) icp_solve_serial<DIM>(a, sh, st->stats);
+  if (tid == 0) { solve_stamp(1); icp_solve_serial<DIM>(a, sh, st->stats); }
   __syncthreads();
+  solve_refresh_epochs(a, sh);
   // accumulators restart at zero; everything else goes back as the serial part left it
   if (part)
     for (int k = tid; k < a.n_slices * kAcc; k += kSolveThreads) sh.acc[k / kAcc][k % kAcc] = 0ull;
@@ -1438,6 +1594,7 @@ __device__ __forceinline__ bool icp_solve_block(const SolveArgs* ap, DevState* s
     int4* d1 = reinterpret_cast<int4*>(static_cast<DevHeader*>(st));
     for (int k = tid; k < (int) (sizeof(DevHeader) / 16); k += kSolveThreads) d1[k] = s1[k];
   }
+  if (tid == 0) solve_stamp(7);
   return sh.stop != 0;
 }
 

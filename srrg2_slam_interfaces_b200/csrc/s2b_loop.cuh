@@ -19,28 +19,56 @@
 
 namespace s2b {
 
-constexpr int kLoopThreads = 512;          // one CTA per SM, 16 warps, <= 128 registers per thread
-constexpr int kTile = 2 * kLoopThreads;    // correspondences per tile: two per thread
-constexpr int kStages = 3;
-constexpr int kFailCap = 128;              // coherence-check failures a CTA resolves in place per pass
+#ifndef S2B_LOOP_THREADS
+#define S2B_LOOP_THREADS 384
+#define S2B_LOOP_STAGES 4
+#define S2B_LOOP_PPL 1
+#endif
+// One CTA of 12 warps per SM: the lineariser wants registers (35 accumulators + ~90 temporaries of a pair),
+// not warps.  Measured on C2 (pass over 1M correspondences inside the loop kernel): 512 threads x 128
+// registers spill the accumulators: 30 us; 384 x 168: 19-21 us; 256 x 255: 21 us; two independent pairs
+// per lane (256 x 255, kPPL = 2): 24-28 us.
+constexpr int kLoopThreads = S2B_LOOP_THREADS;
+constexpr int kLoopWarps = kLoopThreads / 32;
+constexpr int kPPL = S2B_LOOP_PPL;         // pairs per lane and tile
+constexpr int kSubTile = 64;               // correspondences of one sub-tile: one pair per lane
+constexpr int kWTile = kSubTile * kPPL;    // correspondences per warp tile
+constexpr int kStages = S2B_LOOP_STAGES;
+constexpr int kFailCap = 24;               // coherence-check failures a CTA resolves in place per pass (one warp per
+                                           // query: two rounds of its 12 warps); the rest go to the global work list
+constexpr int kBigList = 1024;             // global work lists from this size on are searched thread-per-query
 
+// One sub-tile (one pair per lane) of one ring stage of ONE warp (4 KB).  Every warp runs its own pipeline
+// over its own tiles, so the steady state has no CTA-wide barrier and the warps drift apart freely.
+struct SubTile {
+  float4 mp[kSubTile / 2 * 3];     // pair records of the moving cloud (see pair_pack_kernel): lane l owns [3l, 3l + 3)
+  float4 f[kSubTile];              // gathered fixed points: lane l owns [l] (first of its pair) and [32 + l]
+  float4 nf[kSubTile];             // gathered fixed normals: lane l owns [l] and [32 + l]
+  int slot[kSubTile];              // lane l owns [2l], [2l + 1]
+  float lb[kSubTile];
+};
+static_assert(sizeof(SubTile) == 4096, "one sub-tile is 4 KB");
+struct WarpStage {
+  SubTile sub[kPPL];
+};
 struct TileStage {
-  float4 m[kTile], nm[kTile], f[kTile], nf[kTile];
-  int slot[kTile];
-  float lb[kTile];
+  WarpStage w[kLoopWarps];
 };
 constexpr size_t kLoopSmemBytes = sizeof(TileStage) * kStages;
+static_assert(kLoopSmemBytes <= 200 * 1024, "ring does not fit");
 
 // static shared memory of the tile pass
 struct TileCtl {
   LinConst lk;
   FlushSmem fsm;
-  unsigned long long full[kStages];  // mbarriers: the bulk copies of a stage have landed
+  unsigned long long full[kLoopWarps][kStages];  // mbarriers: the bulk copies of a warp's stage have landed
   int fail[kFailCap];
   int nfail;
   int rows[kRowTable];
-  float S[16];
-  unsigned phase_bits;  // parity of the next wait per stage
+  unsigned phase_bits[kLoopWarps];  // parity of the next wait per stage, per warp (survives between passes)
+  long long tail[kAcc];  // sums of the correspondences resolved by the CTA's search warps (lin_push_tail)
+  long long cta_acc[SRRG2B_MAX_SLICES][kAcc];  // this CTA's sums of the current iteration (persistent loop)
+  float dtab[kEpochs];   // displacement table of the slice's epochs (see encode_bound), refreshed per pass
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned) __cvta_generic_to_shared(p); }
@@ -67,173 +95,246 @@ __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
 
-// tiles are dealt to the CTAs round robin: CTA b takes tiles b, b + G, b + 2G, ...
-// One elected thread issues the bulk copies of tile `t` into stage `st` (count rounded up to a multiple of
-// 4 elements: the arrays are padded, sizes must be multiples of 16 bytes).
+// One elected lane issues the bulk copies (TMA) of warp tile `tile` into the warp's stage, sub-tile by
+// sub-tile (slot / bound counts rounded up to a multiple of 4 elements: the arrays are padded, sizes must be
+// multiples of 16 bytes).  One mbarrier phase covers the whole warp tile.
 template <bool CHECK>
-__device__ __forceinline__ void tile_issue_bulk(const SliceArgs& a, TileStage* stages, TileCtl& ctl, int st, int tile) {
-  const int base = tile * kTile;
-  const int cnt = min(kTile, a.nm - base);
-  const unsigned c4 = (unsigned) ((cnt + 3) & ~3);
-  TileStage& S = stages[st];
-  const unsigned bytes = c4 * (16u + 16u + 4u + (CHECK ? 4u : 0u));
-  mbar_expect_tx(&ctl.full[st], bytes);
-  bulk_g2s(S.m, a.mp + base, c4 * 16u, &ctl.full[st]);
-  bulk_g2s(S.nm, a.mn + base, c4 * 16u, &ctl.full[st]);
-  bulk_g2s(S.slot, a.c_fpos + base, c4 * 4u, &ctl.full[st]);
-  if (CHECK) bulk_g2s(S.lb, a.c_lb + base, c4 * 4u, &ctl.full[st]);
+__device__ __forceinline__ void tile_issue_bulk(const SliceArgs& a, WarpStage& S, unsigned long long* bar, int tile) {
+  unsigned cnt[kPPL], bytes = 0;
+#pragma unroll
+  for (int q = 0; q < kPPL; ++q) {
+    const int base = tile * kWTile + q * kSubTile;
+    cnt[q] = (unsigned) max(0, min(kSubTile, a.nm - base));
+    const unsigned c4 = (cnt[q] + 3u) & ~3u, pairs = (cnt[q] + 1u) >> 1;
+    bytes += pairs * 48u + c4 * (4u + (CHECK ? 4u : 0u));
+  }
+  mbar_expect_tx(bar, bytes);
+#pragma unroll
+  for (int q = 0; q < kPPL; ++q) {
+    if (cnt[q] == 0) continue;
+    const int base = tile * kWTile + q * kSubTile;
+    const unsigned c4 = (cnt[q] + 3u) & ~3u, pairs = (cnt[q] + 1u) >> 1;
+    bulk_g2s(S.sub[q].mp, a.mpair + (size_t) (base >> 1) * 3, pairs * 48u, bar);
+    bulk_g2s(S.sub[q].slot, a.c_fpos + base, c4 * 4u, bar);
+    if (CHECK) bulk_g2s(S.sub[q].lb, a.c_lb + base, c4 * 4u, bar);
+  }
 }
 
-// every thread issues the gathers of its two correspondences of the tile in stage st (slots have landed);
-// elements beyond the end of the slice (last tile) are neutralised: zero point, no slot, no bound
-__device__ __forceinline__ void tile_issue_gather(const SliceArgs& a, TileStage& S, int base, int tid) {
+// every lane issues the gathers of its correspondences of the warp tile (slots have landed); elements beyond
+// the end of the slice (last tile) are neutralised: zero point, no slot, no bound
+__device__ __forceinline__ void tile_issue_gather(const SliceArgs& a, WarpStage& W, int tile_base, int lane) {
 #pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const int e = tid + h * kLoopThreads;
-    int pn = 0;
-    if (base + e < a.nm) {
-      // no candidate: position 0 stands in (always initialised, finite data; the half is masked later)
-      pn = max(slot_candidate(S.slot[e]), 0);
-    } else {
-      S.m[e] = make_float4(0.f, 0.f, 0.f, 0.f);
-      S.nm[e] = make_float4(0.f, 0.f, 0.f, 0.f);
-      S.slot[e] = -1;
-      S.lb[e] = 0.f;
+  for (int q = 0; q < kPPL; ++q) {
+    SubTile& S = W.sub[q];
+    const int i0 = tile_base + q * kSubTile + 2 * lane;
+    int2 sl = *reinterpret_cast<const int2*>(&S.slot[2 * lane]);
+    if (i0 + 1 >= a.nm) {
+      if (i0 >= a.nm) {
+        sl.x = -1;
+        S.mp[3 * lane] = S.mp[3 * lane + 1] = S.mp[3 * lane + 2] = make_float4(0.f, 0.f, 0.f, 0.f);
+        S.lb[2 * lane] = 0.f;
+      }
+      sl.y = -1;
+      S.lb[2 * lane + 1] = 0.f;
+      *reinterpret_cast<int2*>(&S.slot[2 * lane]) = sl;
     }
-    cp_async16(&S.f[e], a.fp + pn);
-    cp_async16(&S.nf[e], a.fn + pn);
+    // no candidate: position 0 stands in (always initialised, finite data; the half is masked later)
+    const int pa = max(slot_candidate(sl.x), 0), pb = max(slot_candidate(sl.y), 0);
+    cp_async16(&S.f[lane], a.frec + 2 * (size_t) pa);
+    cp_async16(&S.nf[lane], a.frec + 2 * (size_t) pa + 1);
+    cp_async16(&S.f[32 + lane], a.frec + 2 * (size_t) pb);
+    cp_async16(&S.nf[32 + lane], a.frec + 2 * (size_t) pb + 1);
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
+#ifdef S2B_FAIL_STATS
+__device__ unsigned long long g_fail_stats[8];
+#endif
+
+// everything one lane holds of one pair between the two halves of its evaluation
+template <int DIM, int FACTOR>
+struct PairWork {
+  P3<F2> m, nm;
+  NF2 nf;
+  float4 fA, fB;
+  LinGeo<DIM, FACTOR, F2> G;
+  int slotA, slotB, bposA, bposB, iA;
+  bool okA, okB;
+};
+
 // One pass over the slice: CHECK = temporal-coherence test fused with the linearisation (bounds certified),
-// else every slot is linearised as it is.  The CTA's accumulators end up in A (flushed by the caller).
-// Requires blockDim.x == kLoopThreads and all threads of the CTA.
+// else every slot is linearised as it is.  Every warp streams its own tiles (warp w of CTA b takes tiles
+// g, g + W, g + 2W, ... with g = w * gridDim + b, W = all warps of the grid) through its own ring; every lane
+// evaluates kPPL independent pairs per tile back to back, so that their instruction streams interleave.
+// The warp's accumulators end up in A (flushed by the caller).  Requires blockDim.x == kLoopThreads.
 template <int DIM, int FACTOR, bool CHECK>
-__device__ __forceinline__ void lin_tiles_body(const SliceArgs& a, TileStage* stages, TileCtl& ctl, LinAcc<DIM>& A,
-                                               int cta, int n_ctas) {
-  const int tid = threadIdx.x;
-  const int n_tiles = (a.nm + kTile - 1) / kTile;
-  const int my_tiles = cta < n_tiles ? (n_tiles - cta + n_ctas - 1) / n_ctas : 0;
+__device__ __forceinline__ void lin_tiles_body(const SliceArgs& a, TileStage* stages, TileCtl& ctl, LinAcc<DIM>& A) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n_tiles = (a.nm + kWTile - 1) / kWTile;
+  const int W = gridDim.x * kLoopWarps, g0 = warp * gridDim.x + blockIdx.x;
+  const int my_tiles = g0 < n_tiles ? (n_tiles - g0 + W - 1) / W : 0;
   const LinConst& k = ctl.lk;
-  const float bsub = CHECK ? *reinterpret_cast<const volatile float*>(a.S_lb + 17) : 0.f;
   const bool regate = a.gate != 0;  // gated-out slots are re-checked every iteration
   if (my_tiles == 0) return;
-  // prologue: bulk copies of the first kStages tiles, gathers of the first
-  if (tid == 0) {
+  unsigned long long* bars = ctl.full[warp];
+  // prologue: bulk copies of the warp's first kStages tiles, gathers of the first
+  if (lane == 0) {
     asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy writes (slots, bounds) before the bulk reads
-    for (int j = 0; j < kStages && j < my_tiles; ++j) tile_issue_bulk<CHECK>(a, stages, ctl, j, cta + j * n_ctas);
+    for (int j = 0; j < kStages && j < my_tiles; ++j) tile_issue_bulk<CHECK>(a, stages[j].w[warp], &bars[j], g0 + j * W);
   }
-  unsigned phase = ctl.phase_bits;  // (uniform: every thread tracks the same parities)
-  mbar_wait(&ctl.full[0], phase & 1u);
+  unsigned phase = ctl.phase_bits[warp];
+  mbar_wait(&bars[0], phase & 1u);
   phase ^= 1u;
-  tile_issue_gather(a, stages[0], cta * kTile, tid);
+  tile_issue_gather(a, stages[0].w[warp], g0 * kWTile, lane);
   for (int j = 0; j < my_tiles; ++j) {
     const int st = j % kStages;
-    TileStage& S = stages[st];
+    WarpStage& WS = stages[st].w[warp];
     if (j + 1 < my_tiles) {  // gathers of the next tile (its bulk copies were issued two tiles ago)
       const int sn = (j + 1) % kStages;
-      mbar_wait(&ctl.full[sn], (phase >> sn) & 1u);
+      mbar_wait(&bars[sn], (phase >> sn) & 1u);
       phase ^= 1u << sn;
-      tile_issue_gather(a, stages[sn], (cta + (j + 1) * n_ctas) * kTile, tid);
+      tile_issue_gather(a, stages[sn].w[warp], (g0 + (j + 1) * W) * kWTile, lane);
       asm volatile("cp.async.wait_group 1;" ::: "memory");
     } else {
       asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
-    const int base = (cta + j * n_ctas) * kTile;
-    const int iA = base + tid, iB = iA + kLoopThreads;
-    const bool inA = iA < a.nm, inB = iB < a.nm;
-    const int slotA = S.slot[tid], slotB = S.slot[tid + kLoopThreads];
-    const int bposA = regate ? slot_candidate(slotA) : (slotA == kSlotSuppressed ? -1 : slotA);
-    const int bposB = regate ? slot_candidate(slotB) : (slotB == kSlotSuppressed ? -1 : slotB);
-    bool okA = bposA >= 0, okB = bposB >= 0;
-    const float4 mA = S.m[tid], mB = S.m[tid + kLoopThreads];
-    const float4 nmA = S.nm[tid], nmB = S.nm[tid + kLoopThreads];
-    const float4 fA = S.f[tid], fB = S.f[tid + kLoopThreads];
-    const float4 nfA = S.nf[tid], nfB = S.nf[tid + kLoopThreads];
-    const P3<F2> m = pack3(mA, mB), nm = pack3(nmA, nmB);
-    LinGeo<DIM, FACTOR, F2> G;
-    lin_geo<DIM, FACTOR, F2>(k, m, nm, pack3(fA, fB), pack3(nfA, nfB), G);
-    if (CHECK) {
-      // exact temporal coherence (see the NN kernels): keep the neighbour / the "none" verdict when the
-      // certified bound minus the motion budget still proves it; else hand the query to the search.
-      // The squared distances come from the same packed evaluation that linearises the pair.
-      const float lbA = S.lb[tid], lbB = S.lb[tid + kLoopThreads];
-      const float lbnA = lbA - bsub, lbnB = lbB - bsub;
-      bool failA = false, failB = false;
-      if (inA) {
-        const bool cert = lbA > 0.f && lbnA > 0.f;
-        const bool keep = cert && bposA >= 0 && G.d2.v.x <= a.md2 && G.d2.v.x * (1.f + 1e-5f) < lbnA * lbnA;
-        const bool none = cert && slotA == -1 && lbnA * lbnA > a.md2 * (1.f + 1e-5f);
-        failA = !(keep || none);
-        if (none && a.c_stat) a.c_stat[iA] = SRRG2B_STAT_NONE;
-        okA = keep;
-      }
-      if (inB) {
-        const bool cert = lbB > 0.f && lbnB > 0.f;
-        const bool keep = cert && bposB >= 0 && G.d2.v.y <= a.md2 && G.d2.v.y * (1.f + 1e-5f) < lbnB * lbnB;
-        const bool none = cert && slotB == -1 && lbnB * lbnB > a.md2 * (1.f + 1e-5f);
-        failB = !(keep || none);
-        if (none && a.c_stat) a.c_stat[iB] = SRRG2B_STAT_NONE;
-        okB = keep;
-      }
-      if (failA | failB) {
-        // the first kFailCap failures of the CTA are searched and linearised by its own warps after the
-        // tiles (converged iterations: a handful per CTA); the rest go to the global work list
+    const int base = (g0 + j * W) * kWTile;
+    PairWork<DIM, FACTOR> pw[kPPL];
+    // ---- first half, all pairs: loads, geometry (transform, residual, chi), coherence verdicts ----
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          if (!(h ? failB : failA)) continue;
-          const int i = h ? iB : iA;
-          const int kf = atomicAdd(&ctl.nfail, 1);
-          if (kf < kFailCap) ctl.fail[kf] = i;
-          else a.work_list[atomicAdd(a.work_count, 1)] = i;
+    for (int q = 0; q < kPPL; ++q) {
+      PairWork<DIM, FACTOR>& w = pw[q];
+      const SubTile& S = WS.sub[q];
+      w.iA = base + q * kSubTile + 2 * lane;
+      const int2 sl = *reinterpret_cast<const int2*>(&S.slot[2 * lane]);
+      w.slotA = sl.x; w.slotB = sl.y;
+      w.bposA = regate ? slot_candidate(sl.x) : (sl.x == kSlotSuppressed ? -1 : sl.x);
+      w.bposB = regate ? slot_candidate(sl.y) : (sl.y == kSlotSuppressed ? -1 : sl.y);
+      w.okA = w.bposA >= 0; w.okB = w.bposB >= 0;
+      const float4 Q0 = S.mp[3 * lane], Q1 = S.mp[3 * lane + 1], Q2 = S.mp[3 * lane + 2];
+      w.fA = S.f[lane]; w.fB = S.f[32 + lane];
+      w.nf = NF2{S.nf[lane], S.nf[32 + lane]};
+      w.m = P3<F2>{F2{make_float2(Q0.x, Q0.y)}, F2{make_float2(Q0.z, Q0.w)}, F2{make_float2(Q1.x, Q1.y)}};
+      w.nm = P3<F2>{F2{make_float2(Q1.z, Q1.w)}, F2{make_float2(Q2.x, Q2.y)}, F2{make_float2(Q2.z, Q2.w)}};
+      lin_geo<DIM, FACTOR, F2, NF2>(k, w.m, w.nm, pack3(w.fA, w.fB), w.nf, w.G);
+    }
+#pragma unroll
+    for (int q = 0; q < kPPL; ++q) {
+      PairWork<DIM, FACTOR>& w = pw[q];
+      const SubTile& S = WS.sub[q];
+      const int iA = w.iA, iB = iA + 1;
+      if (CHECK) {
+        // exact temporal coherence (see the NN kernels): keep the neighbour / the "none" verdict when the
+        // certified bound minus the motion budget still proves it; else hand the query to the search.
+        // The squared distances come from the same packed evaluation that linearises the pair.
+        const float2 lb2 = *reinterpret_cast<const float2*>(&S.lb[2 * lane]);
+        const float lbA = lb2.x, lbB = lb2.y;
+        const float lbnA = decode_bound(lbA, ctl.dtab), lbnB = decode_bound(lbB, ctl.dtab);
+        const bool inA = iA < a.nm, inB = iB < a.nm;
+        bool failA = false, failB = false;
+        if (inA) {
+          const bool cert = lbA > 0.f && lbnA > 0.f;
+          const bool keep = cert && w.bposA >= 0 && w.G.d2.v.x <= a.md2 && w.G.d2.v.x * (1.f + 1e-5f) < lbnA * lbnA;
+          const bool none = cert && w.slotA == -1 && lbnA * lbnA > a.md2 * (1.f + 1e-5f);
+          failA = !(keep || none);
+          if (none && a.c_stat) a.c_stat[iA] = SRRG2B_STAT_NONE;
+          w.okA = keep;
+        }
+        if (inB) {
+          const bool cert = lbB > 0.f && lbnB > 0.f;
+          const bool keep = cert && w.bposB >= 0 && w.G.d2.v.y <= a.md2 && w.G.d2.v.y * (1.f + 1e-5f) < lbnB * lbnB;
+          const bool none = cert && w.slotB == -1 && lbnB * lbnB > a.md2 * (1.f + 1e-5f);
+          failB = !(keep || none);
+          if (none && a.c_stat) a.c_stat[iB] = SRRG2B_STAT_NONE;
+          w.okB = keep;
+        }
+#ifdef S2B_FAIL_STATS
+        if (failA | failB) {  // why: 0 no bound, 1 budget spent, 2 runner-up too close, 3 "none" too close, 4 out of range
+          for (int h = 0; h < 2; ++h) {
+            if (!(h ? failB : failA)) continue;
+            const float lb = h ? lbB : lbA, lbn = h ? lbnB : lbnA, d2 = h ? w.G.d2.v.y : w.G.d2.v.x;
+            const int slot = h ? w.slotB : w.slotA, bpos = h ? w.bposB : w.bposA;
+            int why = 2;
+            if (!(lb > 0.f)) why = 0; else if (!(lbn > 0.f)) why = 1; else if (slot == -1) why = 3; else if (bpos >= 0 && !(d2 <= a.md2)) why = 4;
+            atomicAdd(&g_fail_stats[why], 1ull);
+            if (why == 2) { atomicAdd(&g_fail_stats[5], (unsigned long long) (1e6f * (lbn - sqrtf(d2)) + 1000.f)); }
+          }
+        }
+#endif
+        if (failA | failB) {
+          // the first kFailCap failures of the CTA are searched and linearised by its own warps after the
+          // tiles (converged iterations: a handful per CTA); the rest go to the global work list
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            if (!(h ? failB : failA)) continue;
+            const int i = h ? iB : iA;
+            const int kf = atomicAdd(&ctl.nfail, 1);
+            if (kf < kFailCap) ctl.fail[kf] = i;
+            else a.work_list[atomicAdd(a.work_count, 1)] = i;
+          }
+        }
+      } else {
+        if (w.slotA == kSlotSuppressed) { A.n_ss += 1; if (a.c_stat) a.c_stat[iA] = SRRG2B_STAT_SUPPRESSED; }
+        else if (!w.okA && a.c_stat && iA < a.nm) a.c_stat[iA] = SRRG2B_STAT_NONE;
+        if (w.slotB == kSlotSuppressed) { A.n_ss += 1; if (a.c_stat) a.c_stat[iB] = SRRG2B_STAT_SUPPRESSED; }
+        else if (!w.okB && a.c_stat && iB < a.nm) a.c_stat[iB] = SRRG2B_STAT_NONE;
+      }
+    }
+    // ---- second half, all pairs: gate, robustifier, chi words, H / b terms ----
+    bool any = false;
+#pragma unroll
+    for (int q = 0; q < kPPL; ++q) any = any || pw[q].okA || pw[q].okB;
+    if (__any_sync(0xffffffffu, any)) {
+#pragma unroll
+      for (int q = 0; q < kPPL; ++q) {
+        PairWork<DIM, FACTOR>& w = pw[q];
+        const int iA = w.iA, iB = iA + 1;
+        PairOut o;
+        if (lin_pair_finish<DIM, FACTOR>(k, w.G, w.m, w.nm, w.okA, w.okB, A, o)) {
+          if (w.okA) {
+            if (regate && o.gateA != (w.slotA >= 0)) a.c_fpos[iA] = o.gateA ? w.bposA : -(w.bposA + 2);
+            if (a.c_stat) a.c_stat[iA] = (unsigned char) o.statA;
+            if (a.c_chi && o.gateA) a.c_chi[iA] = o.chiA;
+          }
+          if (w.okB) {
+            if (regate && o.gateB != (w.slotB >= 0)) a.c_fpos[iB] = o.gateB ? w.bposB : -(w.bposB + 2);
+            if (a.c_stat) a.c_stat[iB] = (unsigned char) o.statB;
+            if (a.c_chi && o.gateB) a.c_chi[iB] = o.chiB;
+          }
+        } else {  // a non-finite chi in the pair (overflowing / NaN input): one correspondence at a time
+          const float4 mA = make_float4(w.m.x.v.x, w.m.y.v.x, w.m.z.v.x, 0.f), mB = make_float4(w.m.x.v.y, w.m.y.v.y, w.m.z.v.y, 0.f);
+          const float4 nmA = make_float4(w.nm.x.v.x, w.nm.y.v.x, w.nm.z.v.x, 0.f), nmB = make_float4(w.nm.x.v.y, w.nm.y.v.y, w.nm.z.v.y, 0.f);
+          if (w.okA) lin_one_slot<DIM, FACTOR>(a, k, iA, w.slotA, w.bposA, mA, nmA, w.fA, w.nf.a, A);
+          if (w.okB) lin_one_slot<DIM, FACTOR>(a, k, iB, w.slotB, w.bposB, mB, nmB, w.fB, w.nf.b, A);
         }
       }
-    } else {
-      if (inA && slotA == kSlotSuppressed) { A.n_ss += 1; if (a.c_stat) a.c_stat[iA] = SRRG2B_STAT_SUPPRESSED; }
-      else if (inA && !okA && a.c_stat) a.c_stat[iA] = SRRG2B_STAT_NONE;
-      if (inB && slotB == kSlotSuppressed) { A.n_ss += 1; if (a.c_stat) a.c_stat[iB] = SRRG2B_STAT_SUPPRESSED; }
-      else if (inB && !okB && a.c_stat) a.c_stat[iB] = SRRG2B_STAT_NONE;
     }
-    if (__any_sync(0xffffffffu, okA | okB)) {
-      PairOut o;
-      if (lin_pair_finish<DIM, FACTOR>(k, G, m, nm, okA, okB, A, o)) {
-        if (okA) {
-          if (regate && o.gateA != (slotA >= 0)) a.c_fpos[iA] = o.gateA ? bposA : -(bposA + 2);
-          if (a.c_stat) a.c_stat[iA] = (unsigned char) o.statA;
-          if (a.c_chi && o.gateA) a.c_chi[iA] = o.chiA;
-        }
-        if (okB) {
-          if (regate && o.gateB != (slotB >= 0)) a.c_fpos[iB] = o.gateB ? bposB : -(bposB + 2);
-          if (a.c_stat) a.c_stat[iB] = (unsigned char) o.statB;
-          if (a.c_chi && o.gateB) a.c_chi[iB] = o.chiB;
-        }
-      } else {  // a non-finite chi in the pair (overflowing / NaN input): one correspondence at a time
-        if (okA) lin_one_slot<DIM, FACTOR>(a, k, iA, slotA, bposA, mA, nmA, fA, nfA, A);
-        if (okB) lin_one_slot<DIM, FACTOR>(a, k, iB, slotB, bposB, mB, nmB, fB, nfB, A);
-      }
-    }
-    // the stage is free once every thread has read it: refill it with the tile kStages ahead
+    // the stage is free once every lane has read it: refill it with the warp's tile kStages ahead
     if (j + kStages < my_tiles) {
-      __syncthreads();
-      if (tid == 0) tile_issue_bulk<CHECK>(a, stages, ctl, st, cta + (j + kStages) * n_ctas);
-    }
-    if ((j & 127) == 127) {  // 32-bit partial sums: a thread stays below 512 terms per flush
-      lin_flush<DIM>(a.acc, false, A, ctl.fsm);
-      A.clear();
+      __syncwarp();
+      if (lane == 0) tile_issue_bulk<CHECK>(a, WS, &bars[st], g0 + (j + kStages) * W);
     }
   }
-  if (tid == 0) ctl.phase_bits = phase;
+  if (lane == 0) ctl.phase_bits[warp] = phase;
+}
+
+// (a thread adds at most 2 kPPL terms per tile of its warp: one REDUX per slot suffices up to 30 terms)
+__device__ __forceinline__ bool lin_tiles_few(const SliceArgs& a) {
+  const int n_tiles = (a.nm + kWTile - 1) / kWTile, W = gridDim.x * kLoopWarps;
+  return 2 * kPPL * ((n_tiles + W - 1) / W) <= 30;
 }
 
 // the CTA's control block: mbarriers of the ring, lineariser constants of the slice about to be processed
 __device__ __forceinline__ void tile_ctl_init(TileCtl& ctl) {
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) mbar_init(&ctl.full[s], 1);
+  if (threadIdx.x < kLoopWarps) {
+    for (int s = 0; s < kStages; ++s) mbar_init(&ctl.full[threadIdx.x][s], 1);
+    ctl.phase_bits[threadIdx.x] = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    ctl.phase_bits = 0;
-    ctl.nfail = 0;
   }
+  if (threadIdx.x == 0) ctl.nfail = 0;
+  if (threadIdx.x < kAcc) ctl.tail[threadIdx.x] = 0;
+  for (int k = threadIdx.x; k < SRRG2B_MAX_SLICES * kAcc; k += blockDim.x) (&ctl.cta_acc[0][0])[k] = 0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -251,8 +352,8 @@ __global__ void __launch_bounds__(kLoopThreads, 1) lin_tiles_kernel(const SliceA
   __syncthreads();
   LinAcc<DIM> A;
   A.clear();
-  lin_tiles_body<DIM, FACTOR, false>(a, stages, ctl, A, blockIdx.x, gridDim.x);
-  lin_flush<DIM>(a.acc, a.few_terms != 0, A, ctl.fsm);
+  lin_tiles_body<DIM, FACTOR, false>(a, stages, ctl, A);
+  lin_flush<DIM>(a.acc, lin_tiles_few(a), A, ctl.fsm);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -267,8 +368,24 @@ struct LoopArgs {
   int n_slices;
   int factor[SRRG2B_MAX_SLICES];
   int is_points[SRRG2B_MAX_SLICES];
+  long long* part;          // [gridDim][SRRG2B_MAX_SLICES * kAcc] per-CTA sums of the iteration (no atomics on the hot path)
+  unsigned long long* dbg;  // SRRG2B_LOOP_DEBUG=1: [iteration][cta in {0, last}][8] phase time stamps (ns) + fail counts
   SliceArgs sl[SRRG2B_MAX_SLICES];
 };
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+constexpr int kDbgIters = 64, kDbgWords = 8;
+// time stamp `k` of the current iteration (only CTA 0 and the last CTA record, thread 0)
+__device__ __forceinline__ void loop_dbg(const LoopArgs& L, int it, int k, unsigned long long v) {
+  if (!L.dbg || threadIdx.x != 0 || it >= kDbgIters) return;
+  const int who = blockIdx.x == 0 ? 0 : (blockIdx.x == gridDim.x - 1 ? 1 : -1);
+  if (who < 0) return;
+  L.dbg[((size_t) it * 2 + who) * kDbgWords + k] = v;
+}
 
 __device__ __forceinline__ unsigned ld_volatile_u32(const unsigned* p) {
   unsigned v;
@@ -276,30 +393,28 @@ __device__ __forceinline__ unsigned ld_volatile_u32(const unsigned* p) {
   return v;
 }
 
+// Grid barrier of the loop kernel.  Everything but the sequence number is read from the kernel parameters
+// (constant bank) when needed, so the barrier costs one live register in the hot loop.
 struct LoopSync {
-  GridBar* bar;
-  int* error;
-  long long timeout;
-  unsigned n_ctas, seq;  // seq: barriers completed so far (identical on every CTA)
-  int* bcast;            // one shared word
+  unsigned seq;  // barriers completed so far (identical on every CTA)
 
   // every CTA: everything this CTA wrote is visible before the arrival counts
-  __device__ __forceinline__ void arrive() {
+  __device__ __forceinline__ void arrive(const LoopArgs& L) {
     __syncthreads();
-    if (threadIdx.x == 0) { __threadfence(); atomicAdd(&bar->count, 1u); }
+    if (threadIdx.x == 0) { __threadfence(); atomicAdd(&L.bar->count, 1u); }
     ++seq;
   }
   // leader CTA: wait until every CTA has arrived at barrier `seq`
-  __device__ __forceinline__ bool wait_all() {
+  __device__ __forceinline__ bool wait_all(const LoopArgs& L, int* bcast) {
     if (threadIdx.x == 0) {
-      const unsigned target = n_ctas * seq;
+      const unsigned target = gridDim.x * seq;
       const long long t0 = clock64();
       int ok = 1, spins = 0;
-      while (ld_volatile_u32(&bar->count) < target) {
-        if ((++spins & 255) == 0 && (ld_volatile_u32(&bar->abort) || clock64() - t0 > timeout)) { ok = 0; break; }
+      while (ld_volatile_u32(&L.bar->count) < target) {
+        if ((++spins & 255) == 0 && (ld_volatile_u32(&L.bar->abort) || clock64() - t0 > L.timeout_cycles)) { ok = 0; break; }
       }
       __threadfence();
-      if (!ok) { *error = 2; atomicExch(&bar->abort, 1u); __threadfence(); }
+      if (!ok) { L.st->error = 2; atomicExch(&L.bar->abort, 1u); __threadfence(); }
       *bcast = ok;
     }
     __syncthreads();
@@ -308,25 +423,25 @@ struct LoopSync {
     return ok;
   }
   // leader CTA: let everybody pass barrier `seq`; mode travels with the release
-  __device__ __forceinline__ void release(unsigned mode) {
+  __device__ __forceinline__ void release(const LoopArgs& L, unsigned mode) {
     __syncthreads();
     if (threadIdx.x == 0) {
-      bar->mode = mode;
+      L.bar->mode = mode;
       __threadfence();
-      atomicExch(&bar->gen, seq);
+      atomicExch(&L.bar->gen, seq);
     }
   }
   // every CTA: wait for the release of barrier `seq`; returns the mode, or -1 on abort / timeout
-  __device__ __forceinline__ int wait_release() {
+  __device__ __forceinline__ int wait_release(const LoopArgs& L, int* bcast) {
     if (threadIdx.x == 0) {
       const long long t0 = clock64();
       int ok = 1, spins = 0;
-      while (ld_volatile_u32(&bar->gen) < seq) {
-        if ((++spins & 255) == 0 && (ld_volatile_u32(&bar->abort) || clock64() - t0 > timeout)) { ok = 0; break; }
+      while (ld_volatile_u32(&L.bar->gen) < seq) {
+        if ((++spins & 255) == 0 && (ld_volatile_u32(&L.bar->abort) || clock64() - t0 > L.timeout_cycles)) { ok = 0; break; }
       }
       __threadfence();
-      if (!ok) { *error = 2; atomicExch(&bar->abort, 1u); __threadfence(); }
-      *bcast = ok ? (int) ld_volatile_u32(&bar->mode) : -1;
+      if (!ok) { L.st->error = 2; atomicExch(&L.bar->abort, 1u); __threadfence(); }
+      *bcast = ok ? (int) ld_volatile_u32(&L.bar->mode) : -1;
     }
     __syncthreads();
     const int m = *bcast;
@@ -334,13 +449,13 @@ struct LoopSync {
     return m;
   }
   // plain barrier (leader releases as soon as everybody has arrived)
-  __device__ __forceinline__ bool sync_all(bool leader) {
-    arrive();
-    if (leader) {
-      if (!wait_all()) return false;
-      release(0);
+  __device__ __forceinline__ bool sync_all(const LoopArgs& L, int* bcast) {
+    arrive(L);
+    if (blockIdx.x == 0) {
+      if (!wait_all(L, bcast)) return false;
+      release(L, 0);
     }
-    return wait_release() >= 0;
+    return wait_release(L, bcast) >= 0;
   }
 };
 
@@ -370,6 +485,13 @@ __device__ __forceinline__ void loop_load_lin_const(const SliceArgs& a, const De
   const int tid = threadIdx.x;
   if (tid == 0) ctl.nfail = 0;
   if (tid < 12) ctl.lk.S[tid] = __ldcg(&st->S[s].m[tid]);
+  if (tid >= 64 && tid < 64 + kEpochs && a.S_lb) {
+    // displacement table of the slice's epochs at this pass's transform (epoch ep_cur = this pass)
+    const int e = tid - 64, ep_cur = __ldcg(reinterpret_cast<const int*>(a.S_lb) + kSlbEpoch);
+    float Sn[12];
+    for (int j = 0; j < 12; ++j) Sn[j] = __ldcg(&st->S[s].m[j]);
+    ctl.dtab[e] = e <= ep_cur ? epoch_displacement(Sn, a.S_lb + kSlbEpS + 12 * e, a.radius, e == ep_cur) : 3e38f;
+  }
   if (tid == 32) {
     LinConst& k = ctl.lk;
     for (int i = 0; i < kKCount; ++i) k.fS[i] = a.fS[i];
@@ -382,34 +504,49 @@ __device__ __forceinline__ void loop_load_lin_const(const SliceArgs& a, const De
 
 // One warp per listed query: search, slot + bound, linearisation; the sums go to the slice's accumulators.
 // (cold path of the loop kernel: its own accumulator registers and flush, kept out of line)
+// push: the sums go to the CTA's shared tail accumulators (added by the pass's flush); else flushed here
 template <int DIM, int FACTOR>
-__device__ __noinline__ void loop_search_list(const SliceArgs& a, TileCtl& ctl, int track2, int n, const int* list, int w0, int ws) {
+__device__ __noinline__ void loop_search_list(const SliceArgs& a, TileCtl& ctl, int track2, int n, const int* list, int w0, int ws,
+                                              int push) {
   const float cell = __fdiv_rn(1.f, a.inv_cell);
   const int K = (DIM == 3) ? (2 * a.R + 1) * (2 * a.R + 1) : (2 * a.R + 1);
   LinAcc<DIM> A;
   A.clear();
   if (track2) nn_far_body<DIM, true, FACTOR>(a, ctl.lk.S, ctl.rows, K, cell, n, list, &A, &ctl.lk, w0, ws);
   else nn_far_body<DIM, false, FACTOR>(a, ctl.lk.S, ctl.rows, K, cell, n, list, &A, &ctl.lk, w0, ws);
-  lin_flush<DIM>(a.acc, false, A, ctl.fsm);
+  if (push) lin_push_tail<DIM>(A, ctl.tail);
+  else lin_flush<DIM>(a.acc, false, A, ctl.fsm);
 }
 
-// one pass of the streaming lineariser over a slice inside the loop kernel, flush included
+// one pass of the streaming lineariser over a slice inside the loop kernel; the CTA's sums are added to
+// cta_acc (shared memory, published once per iteration: no global atomics on the hot path)
 template <int DIM, int FACTOR, bool CHECK>
-__device__ __forceinline__ void loop_lin_pass(const SliceArgs& a, TileStage* stages, TileCtl& ctl, int track2) {
-  LinAcc<DIM> A;
-  A.clear();
-  lin_tiles_body<DIM, FACTOR, CHECK>(a, stages, ctl, A, blockIdx.x, gridDim.x);
-  lin_flush<DIM>(a.acc, a.few_terms != 0, A, ctl.fsm);
+__device__ __forceinline__ void loop_lin_pass(const SliceArgs& a, TileStage* stages, TileCtl& ctl, int track2, long long* cta_acc,
+                                              unsigned long long* dbg = nullptr) {
+  {
+    LinAcc<DIM> A;
+    A.clear();
+    lin_tiles_body<DIM, FACTOR, CHECK>(a, stages, ctl, A);
+    if (dbg) dbg[1] = globaltimer_ns();
+    lin_flush<DIM>(a.acc, lin_tiles_few(a), A, ctl.fsm, cta_acc);  // (before the search below: the accumulators are dead across that call)
+  }
   if (CHECK) {
-    // the CTA's coherence-check failures: one warp per query (search, slot + bound, linearisation)
+    // the CTA's coherence-check failures: one warp per query (search, slot + bound, linearisation); their
+    // sums travel through the shared tail accumulators
     const int n_local = min(ctl.nfail, kFailCap);
-    if (n_local > 0) loop_search_list<DIM, FACTOR>(a, ctl, track2, n_local, ctl.fail, threadIdx.x >> 5, blockDim.x >> 5);
+    if (dbg) dbg[7] = (unsigned long long) ctl.nfail;
+    if (n_local > 0) {
+      loop_search_list<DIM, FACTOR>(a, ctl, track2, n_local, ctl.fail, threadIdx.x >> 5, blockDim.x >> 5, 1);
+      __syncthreads();
+      if (threadIdx.x < kAcc) { cta_acc[threadIdx.x] += ctl.tail[threadIdx.x]; ctl.tail[threadIdx.x] = 0; }
+    }
+    if (dbg) dbg[2] = globaltimer_ns();
   }
 }
 
 template <int DIM, int FACTOR>
 __device__ __noinline__ void loop_lin_all(const SliceArgs& a, TileStage* stages, TileCtl& ctl) {
-  loop_lin_pass<DIM, FACTOR, false>(a, stages, ctl, 0);
+  loop_lin_pass<DIM, FACTOR, false>(a, stages, ctl, 0, nullptr);
 }
 
 // first phase of a from-scratch search of the whole slice (rings 0-1, thread per query)
@@ -418,8 +555,8 @@ __device__ __noinline__ void loop_search_phase1(const SliceArgs& a, TileCtl& ctl
   const float cell = __fdiv_rn(1.f, a.inv_cell);
   const float ring2 = (a.R >= 2) ? (1.f - 4e-3f) * cell : __fsqrt_rn(a.rho_s2);
   const float ring2_sq = (a.R >= 2) ? ring2 * ring2 : 3.0e38f;
-  if (track2) nn_phase1_body<DIM, true>(a, ctl.lk.S, 0.f, cell, ring2, ring2_sq, true, a.nm);
-  else nn_phase1_body<DIM, false>(a, ctl.lk.S, 0.f, cell, ring2, ring2_sq, true, a.nm);
+  if (track2) nn_phase1_body<DIM, true>(a, ctl.lk.S, cell, ring2, ring2_sq, true, a.nm);
+  else nn_phase1_body<DIM, false>(a, ctl.lk.S, cell, ring2, ring2_sq, true, a.nm);
 }
 
 // second phase: the queries rings 0-1 did not settle
@@ -432,12 +569,62 @@ __device__ __noinline__ void loop_search_far(const SliceArgs& a, TileCtl& ctl, i
   else nn_far_body<DIM, false>(a, ctl.lk.S, ctl.rows, K, cell, n_far, a.far_list, nullptr, nullptr, w0, ws);
 }
 
+// linearise the listed correspondences as their slots are now (thread per correspondence, scalar path)
+template <int DIM, int FACTOR>
+__device__ __noinline__ void loop_lin_list(const SliceArgs& a, TileCtl& ctl, int n, const int* list) {
+  LinAcc<DIM> A;
+  A.clear();
+  const bool regate = a.gate != 0;
+  int done = 0;
+  for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < n; w += gridDim.x * blockDim.x) {
+    const int i = __ldcg(list + w);
+    const int slot = __ldcg(a.c_fpos + i);
+    const int bpos = regate ? slot_candidate(slot) : (slot == kSlotSuppressed ? -1 : slot);
+    if (bpos < 0) {
+      if (slot == kSlotSuppressed) A.n_ss += 1;
+      if (a.c_stat) a.c_stat[i] = slot == kSlotSuppressed ? SRRG2B_STAT_SUPPRESSED : SRRG2B_STAT_NONE;
+      continue;
+    }
+    lin_one_slot<DIM, FACTOR>(a, ctl.lk, i, slot, bpos, a.mp[i], a.mn[i], __ldg(a.frec + 2 * (size_t) bpos),
+                              __ldg(a.frec + 2 * (size_t) bpos + 1), A);
+    if (++done >= 400) {  // 32-bit partial sums: a thread stays below 512 terms per flush
+      lin_flush<DIM>(a.acc, false, A, ctl.fsm);
+      A.clear();
+      done = 0;
+    }
+  }
+  lin_flush<DIM>(a.acc, false, A, ctl.fsm);
+}
+
+// thread-per-query search of a long work list (rings 0-1; the unsettled go to the far list)
+template <int DIM>
+__device__ __noinline__ void loop_search_list_phase1(const SliceArgs& a, TileCtl& ctl, int track2, int n_work) {
+  const float cell = __fdiv_rn(1.f, a.inv_cell);
+  const float ring2 = (a.R >= 2) ? (1.f - 4e-3f) * cell : __fsqrt_rn(a.rho_s2);
+  const float ring2_sq = (a.R >= 2) ? ring2 * ring2 : 3.0e38f;
+  if (track2) nn_phase1_body<DIM, true>(a, ctl.lk.S, cell, ring2, ring2_sq, false, n_work);
+  else nn_phase1_body<DIM, false>(a, ctl.lk.S, cell, ring2, ring2_sq, false, n_work);
+}
+
 template <int DIM>
 __device__ __noinline__ void loop_solve(const LoopArgs& L, SolveSmem& ssm) {
-  icp_solve_block<DIM>(L.ap, L.st, L.px, ssm);
+  icp_solve_block<DIM>(L.ap, L.st, L.px, ssm, L.part, (int) gridDim.x);
 }
 
 __device__ __noinline__ void loop_proj_find(const SliceArgs& a, const float* S) { proj_find_body(a, S); }
+
+// The hot pass (coherence check + linearisation of a certified slice).  SLOT >= 0: the slice arguments are
+// the compile-time entry L.sl[SLOT] of the kernel parameters, i.e. constant-bank operands that occupy no
+// registers; SLOT < 0: any slice (run-time index).
+template <int DIM, int SLOT>
+__device__ __forceinline__ void loop_check_pass(const LoopArgs& L, int s, TileStage* stages, TileCtl& ctl, int track2, int it) {
+  const SliceArgs& a = SLOT >= 0 ? L.sl[SLOT] : L.sl[s];
+  unsigned long long* dbg = nullptr;
+  if (L.dbg && threadIdx.x == 0 && it < kDbgIters && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1))
+    dbg = L.dbg + ((size_t) it * 2 + (blockIdx.x == 0 ? 0 : 1)) * kDbgWords;
+  if (L.factor[SLOT >= 0 ? SLOT : s] == SRRG2B_FACTOR_P2P) loop_lin_pass<DIM, SRRG2B_FACTOR_P2P, true>(a, stages, ctl, track2, ctl.cta_acc[s], dbg);
+  else loop_lin_pass<DIM, SRRG2B_FACTOR_PLANE, true>(a, stages, ctl, track2, ctl.cta_acc[s], dbg);
+}
 
 template <int DIM>
 __global__ void __launch_bounds__(kLoopThreads, 1) icp_loop_kernel(const __grid_constant__ LoopArgs L) {
@@ -449,21 +636,21 @@ __global__ void __launch_bounds__(kLoopThreads, 1) icp_loop_kernel(const __grid_
   __shared__ TileCtl ctl;
   __shared__ int s_ctrl[4 + 2 * SRRG2B_MAX_SLICES];  // stop, -, -, bcast | list_all[s] | track2[s]
   const int tid = threadIdx.x;
-  const bool leader = blockIdx.x == 0;
-  DevState* st = L.st;
   tile_ctl_init(ctl);
-  LoopSync sync{L.bar, &st->error, L.timeout_cycles, gridDim.x, 0u, &s_ctrl[3]};
+  LoopSync sync{0u};
+  int* const bcast = &s_ctrl[3];
   constexpr int KMAX = (DIM == 3) ? kRowTable : (2 * kMaxR + 1);
   for (int k = tid; k < KMAX; k += blockDim.x)
     ctl.rows[k] = (DIM == 3) ? *reinterpret_cast<const int*>(c_rows3[k]) : *reinterpret_cast<const int*>(c_rows2[k]);
   __syncthreads();
 
-  for (;;) {
+  for (int it = 0;; ++it) {
+    loop_dbg(L, it, 0, globaltimer_ns());
     // ---- state of this iteration (written by the solve step of the previous one) ----
-    if (tid == 0) s_ctrl[0] = __ldcg(&st->stop);
+    if (tid == 0) s_ctrl[0] = __ldcg(&L.st->stop);
     if (tid < L.n_slices) {
-      s_ctrl[4 + tid] = __ldcg(&st->list_all[tid]);
-      s_ctrl[4 + SRRG2B_MAX_SLICES + tid] = __ldcg(&st->track2[tid]);
+      s_ctrl[4 + tid] = __ldcg(&L.st->list_all[tid]);
+      s_ctrl[4 + SRRG2B_MAX_SLICES + tid] = __ldcg(&L.st->track2[tid]);
     }
     __syncthreads();
     if (s_ctrl[0]) break;
@@ -472,28 +659,35 @@ __global__ void __launch_bounds__(kLoopThreads, 1) icp_loop_kernel(const __grid_
     // ---- phase A: certified slices: coherence check + linearisation; others: first search phase ----
     for (int s = 0; s < L.n_slices; ++s) {
       if (!L.is_points[s]) continue;
-      const SliceArgs& a = L.sl[s];
-      if (a.nm <= 0) continue;
+      if (L.sl[s].nm <= 0) continue;
       const int track2 = s_ctrl[4 + SRRG2B_MAX_SLICES + s];
-      loop_load_lin_const(a, st, s, ctl);
-      if (a.projective) {
+      loop_load_lin_const(L.sl[s], L.st, s, ctl);
+      if (L.sl[s].projective) {
         fallback = true;
-        loop_proj_find(a, ctl.lk.S);
+        loop_proj_find(L.sl[s], ctl.lk.S);
       } else if (s_ctrl[4 + s]) {  // no certified bounds: search everything, rings 0-1 here, the rest after the barrier
         fallback = true;
-        loop_search_phase1<DIM>(a, ctl, track2);
-      } else if (L.factor[s] == SRRG2B_FACTOR_P2P) {
-        loop_lin_pass<DIM, SRRG2B_FACTOR_P2P, true>(a, stages, ctl, track2);
+        loop_search_phase1<DIM>(L.sl[s], ctl, track2);
+      } else if (s == 0) {
+        loop_check_pass<DIM, 0>(L, s, stages, ctl, track2, it);
+      } else if (s == 1) {
+        loop_check_pass<DIM, 1>(L, s, stages, ctl, track2, it);
       } else {
-        loop_lin_pass<DIM, SRRG2B_FACTOR_PLANE, true>(a, stages, ctl, track2);
+        loop_check_pass<DIM, -1>(L, s, stages, ctl, track2, it);
       }
       __syncthreads();
     }
 
-    // ---- barrier; in the all-certified case CTA 0 goes straight to the solve step ----
-    sync.arrive();
-    if (leader) {
-      if (!sync.wait_all()) break;
+    // ---- publish this CTA's sums, barrier; in the all-certified case CTA 0 goes straight to the solve step ----
+    for (int k = tid; k < L.n_slices * kAcc; k += blockDim.x) {
+      L.part[(size_t) blockIdx.x * (SRRG2B_MAX_SLICES * kAcc) + k] = (&ctl.cta_acc[0][0])[k];
+      (&ctl.cta_acc[0][0])[k] = 0;
+    }
+    loop_dbg(L, it, 3, globaltimer_ns());
+    sync.arrive(L);
+    if (blockIdx.x == 0) {
+      if (!sync.wait_all(L, bcast)) break;
+      loop_dbg(L, it, 4, globaltimer_ns());
       bool lists = false;
       if (!fallback) {
         for (int s = 0; s < L.n_slices; ++s)
@@ -501,12 +695,14 @@ __global__ void __launch_bounds__(kLoopThreads, 1) icp_loop_kernel(const __grid_
       }
       if (!fallback && !lists) {
         loop_solve<DIM>(L, ssm);
-        sync.release(0);
+        loop_dbg(L, it, 5, globaltimer_ns());
+        sync.release(L, 0);
       } else {
-        sync.release(1);
+        sync.release(L, 1);
       }
     }
-    const int mode = sync.wait_release();
+    const int mode = sync.wait_release(L, bcast);
+    loop_dbg(L, it, 6, globaltimer_ns());
     if (mode < 0) break;
     if (mode == 0) continue;
 
@@ -517,7 +713,7 @@ __global__ void __launch_bounds__(kLoopThreads, 1) icp_loop_kernel(const __grid_
       const SliceArgs& a = L.sl[s];
       if (a.nm <= 0 || a.projective) continue;
       const int track2 = s_ctrl[4 + SRRG2B_MAX_SLICES + s];
-      loop_load_lin_const(a, st, s, ctl);
+      loop_load_lin_const(a, L.st, s, ctl);
       if (s_ctrl[4 + s]) {
         far_phase = true;
         const int n_far = __ldcg(a.far_count);
@@ -525,32 +721,59 @@ __global__ void __launch_bounds__(kLoopThreads, 1) icp_loop_kernel(const __grid_
       } else {
         const int n_work = __ldcg(a.work_count);
         const int wpb = blockDim.x >> 5, w0 = blockIdx.x * wpb + (tid >> 5), ws = gridDim.x * wpb;
-        if (n_work > 0) {
-          if (L.factor[s] == SRRG2B_FACTOR_P2P) loop_search_list<DIM, SRRG2B_FACTOR_P2P>(a, ctl, track2, n_work, a.work_list, w0, ws);
-          else loop_search_list<DIM, SRRG2B_FACTOR_PLANE>(a, ctl, track2, n_work, a.work_list, w0, ws);
+        if (n_work >= kBigList) {  // long list: thread per query, then the far phase and a list linearisation
+          far_phase = true;
+          loop_search_list_phase1<DIM>(a, ctl, track2, n_work);
+        } else if (n_work > 0) {   // short list: one warp per query does the whole job
+          if (L.factor[s] == SRRG2B_FACTOR_P2P) loop_search_list<DIM, SRRG2B_FACTOR_P2P>(a, ctl, track2, n_work, a.work_list, w0, ws, 0);
+          else loop_search_list<DIM, SRRG2B_FACTOR_PLANE>(a, ctl, track2, n_work, a.work_list, w0, ws, 0);
         }
       }
       __syncthreads();
     }
-    if (far_phase && !sync.sync_all(leader)) break;
+    if (far_phase) {
+      if (!sync.sync_all(L, bcast)) break;
+      // far phase of the long work lists (the from-scratch searches ran theirs above, in phase order)
+      bool any = false;
+      for (int s = 0; s < L.n_slices; ++s) {
+        if (!L.is_points[s]) continue;
+        const SliceArgs& a = L.sl[s];
+        if (a.nm <= 0 || a.projective || s_ctrl[4 + s] || __ldcg(a.work_count) < kBigList) continue;
+        any = true;
+        loop_load_lin_const(a, L.st, s, ctl);
+        const int n_far = __ldcg(a.far_count);
+        if (n_far > 0) loop_search_far<DIM>(a, ctl, s_ctrl[4 + SRRG2B_MAX_SLICES + s], n_far);
+        __syncthreads();
+      }
+      if (any && !sync.sync_all(L, bcast)) break;
+    }
 
-    // ---- phase C (rare): linearise the slices that were searched from scratch ----
+    // ---- phase C (rare): linearise the slices that were searched from scratch, and the long work lists ----
     for (int s = 0; s < L.n_slices; ++s) {
       if (!L.is_points[s]) continue;
       const SliceArgs& a = L.sl[s];
-      if (a.nm <= 0 || !(a.projective || s_ctrl[4 + s])) continue;
-      loop_load_lin_const(a, st, s, ctl);
-      if (L.factor[s] == SRRG2B_FACTOR_P2P) loop_lin_all<DIM, SRRG2B_FACTOR_P2P>(a, stages, ctl);
-      else loop_lin_all<DIM, SRRG2B_FACTOR_PLANE>(a, stages, ctl);
-      __syncthreads();
+      if (a.nm <= 0) continue;
+      if (a.projective || s_ctrl[4 + s]) {
+        loop_load_lin_const(a, L.st, s, ctl);
+        if (L.factor[s] == SRRG2B_FACTOR_P2P) loop_lin_all<DIM, SRRG2B_FACTOR_P2P>(a, stages, ctl);
+        else loop_lin_all<DIM, SRRG2B_FACTOR_PLANE>(a, stages, ctl);
+        __syncthreads();
+      } else {
+        const int n_work = __ldcg(a.work_count);
+        if (n_work < kBigList) continue;
+        loop_load_lin_const(a, L.st, s, ctl);
+        if (L.factor[s] == SRRG2B_FACTOR_P2P) loop_lin_list<DIM, SRRG2B_FACTOR_P2P>(a, ctl, n_work, a.work_list);
+        else loop_lin_list<DIM, SRRG2B_FACTOR_PLANE>(a, ctl, n_work, a.work_list);
+        __syncthreads();
+      }
     }
-    sync.arrive();
-    if (leader) {
-      if (!sync.wait_all()) break;
+    sync.arrive(L);
+    if (blockIdx.x == 0) {
+      if (!sync.wait_all(L, bcast)) break;
       loop_solve<DIM>(L, ssm);
-      sync.release(0);
+      sync.release(L, 0);
     }
-    if (sync.wait_release() < 0) break;
+    if (sync.wait_release(L, bcast) < 0) break;
   }
 }
 
