@@ -163,6 +163,10 @@ int srrg2b_icp_iterate(srrg2b_ctx* ctx, int n_slices, const srrg2b_slice* slices
 int srrg2b_get_correspondences(srrg2b_ctx* ctx, int slice_id, int32_t* fixed_idx, int32_t* moving_idx,
                                float* response, int64_t* n_out);
 
+/* Forgets the slice's correspondences, warm-start candidates and certified bounds, as a fresh setMoving()
+ * would (the clouds and the NN index stay): the next compute() starts cold.  Results never depend on it. */
+int srrg2b_reset_correspondences(srrg2b_ctx* ctx, int slice_id);
+
 /* ---- benchmarking support: device time of the last srrg2b_icp_run between its first and last
  * kernel (CUDA events on the context stream), and how many _runSolver iterations it executed ---- */
 int srrg2b_last_run_timing(srrg2b_ctx* ctx, float* device_ms, int32_t* iterations);

@@ -24,7 +24,7 @@ EXPORTED_SYMBOLS = [
     "srrg2b_version", "srrg2b_ctx_create", "srrg2b_ctx_destroy", "srrg2b_last_error", "srrg2b_stream",
     "srrg2b_launch_count", "srrg2b_comm_unique_id", "srrg2b_comm_init", "srrg2b_set_cloud",
     "srrg2b_find_correspondences", "srrg2b_set_correspondences", "srrg2b_linearize", "srrg2b_icp_run",
-    "srrg2b_icp_iterate", "srrg2b_get_correspondences", "srrg2b_last_run_timing",
+    "srrg2b_icp_iterate", "srrg2b_get_correspondences", "srrg2b_reset_correspondences", "srrg2b_last_run_timing",
     "srrg2b_set_kernel_timing", "srrg2b_last_kernel_timing", "srrg2b_debug_info",
     "srrg2b_pgo_upload", "srrg2b_pgo_iterate", "srrg2b_pgo_download",
 ]
@@ -118,6 +118,7 @@ def load_library():
                                    C.POINTER(IterStats), i32p, i32p]
     lib.srrg2b_icp_iterate.argtypes = [vp, C.c_int, C.POINTER(Slice), C.c_int, vp, C.POINTER(IterStats), i32p]
     lib.srrg2b_get_correspondences.argtypes = [vp, C.c_int, vp, vp, vp, i64p]
+    lib.srrg2b_reset_correspondences.argtypes = [vp, C.c_int]
     lib.srrg2b_last_run_timing.argtypes = [vp, C.POINTER(C.c_float), i32p]
     lib.srrg2b_debug_info.argtypes = [vp, C.c_int, vp]
     lib.srrg2b_pgo_upload.argtypes = [vp, C.c_int64, vp, vp, C.c_int64, vp, vp, vp]
@@ -303,6 +304,10 @@ class Context:
         self._check(self.lib.srrg2b_get_correspondences(self.h, slice_id, fi.ctypes.data, mi.ctypes.data,
                                                         rs.ctypes.data, C.byref(n)))
         return fi[:n.value], mi[:n.value], rs[:n.value]
+
+    def reset_correspondences(self, slice_id):
+        """Forget the slice's correspondences / warm-start candidates / certified bounds (cold start)."""
+        self._check(self.lib.srrg2b_reset_correspondences(self.h, slice_id))
 
     def debug_info(self, slice_id):
         out = np.zeros(16, dtype=np.int32)

@@ -1692,6 +1692,25 @@ int srrg2b_get_correspondences(srrg2b_ctx* c, int slice_id, int32_t* fixed_idx, 
   return export_corr(c, sd, sd.prune_on_export, false, fixed_idx, moving_idx, response, nullptr, nullptr, n_out);
 }
 
+int srrg2b_reset_correspondences(srrg2b_ctx* c, int slice_id) {
+  if (!c) return SRRG2B_ERR_INVALID;
+  if (!c->slices.count(slice_id)) FAIL(c, SRRG2B_ERR_STATE, "unknown slice");
+  CK(c, cudaSetDevice(c->device));
+  SliceData& sd = c->slices[slice_id];
+  if (sd.moving_raw.present && sd.nm_valid > 0) {
+    fill_int_kernel<<<blocks_for(sd.nm_valid, 256), 256, 0, c->stream>>>(sd.c_fpos.p, sd.nm_valid, -1);
+    fill_int_kernel<<<blocks_for(sd.nm_valid, 256), 256, 0, c->stream>>>(sd.c_fidx.p, sd.nm_valid, -1);
+    c->launches += 2;
+    CK(c, cudaMemsetAsync(sd.c_lb.p, 0, sizeof(float) * (size_t) sd.nm_valid, c->stream));
+    CK(c, cudaGetLastError());
+  }
+  CK(c, cudaStreamSynchronize(c->stream));
+  sd.corr_valid = false;
+  sd.stat_valid = false;
+  sd.have_last_S = false;
+  return SRRG2B_OK;
+}
+
 int srrg2b_last_run_timing(srrg2b_ctx* c, float* device_ms, int32_t* iterations) {
   if (!c) return SRRG2B_ERR_INVALID;
   if (device_ms) *device_ms = c->last_ms;

@@ -1412,6 +1412,25 @@ __device__ __forceinline__ float epoch_displacement(const float* Sn, const float
   const float qmax = radius * 1.0001f + (float) sqrt(tn);
   return (Dm + (1e-6f * qmax + 2e-7f * (1.f + Dm))) * (1.f + 2.4e-7f);
 }
+// The same, split per query: the displacement of query m is at most kr |m| + kt (kr = |dR|_F rounded up, kt =
+// |dt| + the absolute slack, which is computed for the worst query).
+__device__ __forceinline__ float2 epoch_displacement2(const float* Sn, const float* E, float radius, bool same) {
+  double dr = 0.0, dt = 0.0, tn = 0.0;
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c) {
+      const double d = same ? 0.0 : (double) Sn[r * 4 + c] - (double) __ldcg(E + r * 4 + c);
+      dr += d * d;
+    }
+    const double d = same ? 0.0 : (double) Sn[r * 4 + 3] - (double) __ldcg(E + r * 4 + 3);
+    dt += d * d;
+    tn += (double) Sn[r * 4 + 3] * (double) Sn[r * 4 + 3];
+  }
+  const float kr = (float) (sqrt(dr) * (1.0 + 1e-6)) * (1.f + 2.4e-7f);
+  const float Dm = (kr * radius + (float) (sqrt(dt) * (1.0 + 1e-6))) * (1.f + 4.8e-7f);
+  const float qmax = radius * 1.0001f + (float) sqrt(tn);
+  const float kt = ((float) (sqrt(dt) * (1.0 + 1e-6)) + (1e-6f * qmax + 2e-7f * (1.f + Dm))) * (1.f + 4.8e-7f);
+  return make_float2(kr, kt);
+}
 
 // After the serial part: the next pass of every point slice becomes epoch ep_next: its transform and id are
 // recorded in the slice's bound state.  The displacement table dtab is computed by whoever runs the pass
@@ -1462,7 +1481,7 @@ __device__ __forceinline__ unsigned long long ld_volatile_sys(const unsigned lon
   return v;
 }
 
-constexpr int kPartGroups = 8;
+constexpr int kPartGroups = 6;
 // shared-memory staging of the solve step
 struct SolveSmem {
   alignas(16) SolveArgs a;
@@ -1477,17 +1496,24 @@ struct SolveSmem {
 // Returns (to every participating thread) whether the iteration loop has to stop.
 // part / n_part: per-CTA partial sums [n_part][SRRG2B_MAX_SLICES * kAcc] published by the persistent loop's
 // CTAs (added to the global accumulators here, in a fixed order -- integers, so any order gives the same bits)
+// resident: sm still holds the arguments and the state this CTA wrote back at the end of its previous solve step
+// (nothing else modifies them inside the persistent loop): only the accumulators are fetched.
 template <int DIM>
 __device__ __forceinline__ bool icp_solve_block(const SolveArgs* ap, DevState* st, const PeerExchange* px, SolveSmem& sm,
-                                                const long long* part_rows = nullptr, int n_part = 0) {
+                                                const long long* part_rows = nullptr, int n_part = 0, bool resident = false) {
   const int tid = threadIdx.x;
   const bool part = tid < kSolveThreads;
   if (tid == 0) solve_stamp(0);
   SolveArgs& a = sm.a;
   DevHeader& sh = sm.sh;
   PeerExchange& pe = sm.pe;
-  // one round of independent 16-byte loads stages the arguments and the whole mutable state
-  if (part) {
+  if (resident) {
+    // (the accumulators the cold paths may have added to with atomics; the CTAs' sums come from part_rows)
+    const int n_words = a.n_slices * kAcc;
+    for (int k = tid; k < n_words; k += blockDim.x) (&sh.acc[0][0])[k] = __ldcg(&st->acc[0][0] + k);
+    if (tid == 0) { sh.error = __ldcg(&st->error); sm.timed_out = 0; }
+  } else if (part) {
+    // one round of independent 16-byte loads stages the arguments and the whole mutable state
     const int4* s0 = reinterpret_cast<const int4*>(ap);
     int4* d0 = reinterpret_cast<int4*>(&a);
     for (int k = tid; k < (int) (sizeof(SolveArgs) / 16); k += kSolveThreads) d0[k] = s0[k];

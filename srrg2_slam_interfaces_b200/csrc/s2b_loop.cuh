@@ -68,7 +68,8 @@ struct TileCtl {
   unsigned phase_bits[kLoopWarps];  // parity of the next wait per stage, per warp (survives between passes)
   long long tail[kAcc];  // sums of the correspondences resolved by the CTA's search warps (lin_push_tail)
   long long cta_acc[SRRG2B_MAX_SLICES][kAcc];  // this CTA's sums of the current iteration (persistent loop)
-  float dtab[kEpochs];   // displacement table of the slice's epochs (see encode_bound), refreshed per pass
+  float2 dtab[kEpochs];  // displacement table of the slice's epochs (see encode_bound), refreshed per pass: a query
+                         // m has moved at most dtab[e].x |m| + dtab[e].y since epoch e
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned) __cvta_generic_to_shared(p); }
@@ -230,7 +231,23 @@ __device__ __forceinline__ void lin_tiles_body(const SliceArgs& a, TileStage* st
         // The squared distances come from the same packed evaluation that linearises the pair.
         const float2 lb2 = *reinterpret_cast<const float2*>(&S.lb[2 * lane]);
         const float lbA = lb2.x, lbB = lb2.y;
-        const float lbnA = decode_bound(lbA, ctl.dtab), lbnB = decode_bound(lbB, ctl.dtab);
+        // |m| of the two queries, rounded up (approximate root: 2 ulp, covered by the factor)
+        const F2 m2 = t_fma(w.m.z, w.m.z, t_fma(w.m.y, w.m.y, t_mul(w.m.x, w.m.x)));
+        float rA, rB;
+        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rA) : "f"(m2.v.x));
+        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rB) : "f"(m2.v.y));
+        rA = rA * (1.f + 1e-6f) + 1e-30f; rB = rB * (1.f + 1e-6f) + 1e-30f;
+        float lbnA = 0.f, lbnB = 0.f;
+        if (lbA > 0.f) {
+          const int b = __float_as_int(lbA);
+          const float2 d = ctl.dtab[b & (kEpochs - 1)];
+          lbnA = __int_as_float(b & ~(kEpochs - 1)) - fmaf(d.x, rA, d.y) * (1.f + 2.4e-7f);
+        }
+        if (lbB > 0.f) {
+          const int b = __float_as_int(lbB);
+          const float2 d = ctl.dtab[b & (kEpochs - 1)];
+          lbnB = __int_as_float(b & ~(kEpochs - 1)) - fmaf(d.x, rB, d.y) * (1.f + 2.4e-7f);
+        }
         const bool inA = iA < a.nm, inB = iB < a.nm;
         bool failA = false, failB = false;
         if (inA) {
@@ -490,7 +507,7 @@ __device__ __forceinline__ void loop_load_lin_const(const SliceArgs& a, const De
     const int e = tid - 64, ep_cur = __ldcg(reinterpret_cast<const int*>(a.S_lb) + kSlbEpoch);
     float Sn[12];
     for (int j = 0; j < 12; ++j) Sn[j] = __ldcg(&st->S[s].m[j]);
-    ctl.dtab[e] = e <= ep_cur ? epoch_displacement(Sn, a.S_lb + kSlbEpS + 12 * e, a.radius, e == ep_cur) : 3e38f;
+    ctl.dtab[e] = e <= ep_cur ? epoch_displacement2(Sn, a.S_lb + kSlbEpS + 12 * e, a.radius, e == ep_cur) : make_float2(0.f, 3e38f);
   }
   if (tid == 32) {
     LinConst& k = ctl.lk;
@@ -607,8 +624,8 @@ __device__ __noinline__ void loop_search_list_phase1(const SliceArgs& a, TileCtl
 }
 
 template <int DIM>
-__device__ __noinline__ void loop_solve(const LoopArgs& L, SolveSmem& ssm) {
-  icp_solve_block<DIM>(L.ap, L.st, L.px, ssm, L.part, (int) gridDim.x);
+__device__ __noinline__ void loop_solve(const LoopArgs& L, SolveSmem& ssm, bool resident) {
+  icp_solve_block<DIM>(L.ap, L.st, L.px, ssm, L.part, (int) gridDim.x, resident);
 }
 
 __device__ __noinline__ void loop_proj_find(const SliceArgs& a, const float* S) { proj_find_body(a, S); }
@@ -630,9 +647,9 @@ template <int DIM>
 __global__ void __launch_bounds__(kLoopThreads, 1) icp_loop_kernel(const __grid_constant__ LoopArgs L) {
   extern __shared__ __align__(128) unsigned char loop_smem_raw[];
   TileStage* stages = reinterpret_cast<TileStage*>(loop_smem_raw);
-  // the solve step's staging area lives in the last ring stage (no tile is in flight while CTA 0 solves)
-  SolveSmem& ssm = *reinterpret_cast<SolveSmem*>(&stages[kStages - 1]);
-  static_assert(sizeof(SolveSmem) <= sizeof(TileStage), "solve staging must fit a ring stage");
+  // the solve step's arguments and state stay resident in CTA 0's shared memory between iterations
+  __shared__ SolveSmem ssm;
+  bool solved_before = false;
   __shared__ TileCtl ctl;
   __shared__ int s_ctrl[4 + 2 * SRRG2B_MAX_SLICES];  // stop, -, -, bcast | list_all[s] | track2[s]
   const int tid = threadIdx.x;
@@ -694,7 +711,8 @@ __global__ void __launch_bounds__(kLoopThreads, 1) icp_loop_kernel(const __grid_
           if (L.is_points[s] && L.sl[s].nm > 0 && !L.sl[s].projective && __ldcg(L.sl[s].work_count) > 0) lists = true;
       }
       if (!fallback && !lists) {
-        loop_solve<DIM>(L, ssm);
+        loop_solve<DIM>(L, ssm, solved_before);
+        solved_before = true;
         loop_dbg(L, it, 5, globaltimer_ns());
         sync.release(L, 0);
       } else {
@@ -770,7 +788,8 @@ __global__ void __launch_bounds__(kLoopThreads, 1) icp_loop_kernel(const __grid_
     sync.arrive(L);
     if (blockIdx.x == 0) {
       if (!sync.wait_all(L, bcast)) break;
-      loop_solve<DIM>(L, ssm);
+      loop_solve<DIM>(L, ssm, solved_before);
+      solved_before = true;
       sync.release(L, 0);
     }
     if (sync.wait_release(L, bcast) < 0) break;

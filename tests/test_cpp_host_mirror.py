@@ -55,7 +55,7 @@ def test_cpp_mirror_matches_oracle(binary, tmp_path, oracle):
     corr_t = np.dtype([("f", "<i4"), ("m", "<i4"), ("r", "<f4")])
     stats_t = np.dtype([("iteration", "<i4"), ("solver_status", "<i4"), ("num_inliers", "<i8"), ("num_outliers", "<i8"),
                         ("num_suppressed", "<i8"), ("num_correspondences", "<i8"), ("chi_inliers", "<f8"),
-                        ("chi_outliers", "<f8")])
+                        ("chi_outliers", "<f8"), ("num_saturated", "<i8")])
     off = 0
     nf = struct.unpack_from("<q", buf, off)[0]; off += 8
     find = np.frombuffer(buf, corr_t, nf, off); off += nf * corr_t.itemsize
