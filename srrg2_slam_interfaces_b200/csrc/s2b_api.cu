@@ -17,6 +17,7 @@
 #include <map>
 #include <string>
 #include <vector>
+#include <algorithm>
 
 using namespace s2b;
 
@@ -180,6 +181,7 @@ struct srrg2b_ctx {
   bool use_graphs = true;  // env SRRG2B_NO_GRAPH=1 disables
   bool graph_nccl = false;  // env SRRG2B_GRAPH_NCCL=1: capture the all-reduce too (experimental: failed the 2-GPU parity test)
   bool eager_index = true;  // env SRRG2B_EAGER_INDEX=0: build the NN index on first use only
+  int big_list = kBigList;  // env SRRG2B_BIG_LIST
   int pre_iters = 3;       // env SRRG2B_PRE_ITERS: iterations run by the dedicated search kernels before the persistent loop takes over
   bool use_loop = true;    // env SRRG2B_LOOP=0: no persistent loop kernel (every iteration is a kernel sequence)
   s2b::GridBar* d_bar = nullptr;
@@ -926,6 +928,7 @@ int launch_loop(srrg2b_ctx* c, const Plan& plan) {
   memset(&L, 0, sizeof(L));
   L.ap = c->d_solve; L.st = c->d_state; L.px = c->d_px; L.bar = c->d_bar;
   L.timeout_cycles = c->timeout_cycles;
+  L.big_list = c->big_list;
   L.dbg = c->d_loop_dbg;
   L.part = c->d_part;
   L.n_slices = plan.solve.n_slices;
@@ -1145,6 +1148,7 @@ int srrg2b_ctx_create(int dim, int device, srrg2b_ctx** out) {
   if (const char* env = getenv("SRRG2B_NO_GRAPH")) c->use_graphs = atoi(env) == 0;
   if (const char* env = getenv("SRRG2B_PRE_ITERS")) c->pre_iters = std::max(0, atoi(env));
   if (const char* env = getenv("SRRG2B_LOOP")) c->use_loop = atoi(env) != 0;
+  if (const char* env = getenv("SRRG2B_BIG_LIST")) c->big_list = std::max(1, atoi(env));
   {
     int khz = 1965000;
     cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
@@ -1153,7 +1157,7 @@ int srrg2b_ctx_create(int dim, int device, srrg2b_ctx** out) {
     c->timeout_cycles = (long long) (ms * (double) khz);
   }
   if (getenv("SRRG2B_LOOP_DEBUG")) {
-    const size_t nb = sizeof(unsigned long long) * kDbgIters * 2 * kDbgWords;
+    const size_t nb = sizeof(unsigned long long) * (kDbgIters * 2 * kDbgWords + kDbgCtas * 4);
     ok = ok && cudaMalloc((void**) &c->d_loop_dbg, nb) == cudaSuccess && cudaMemset(c->d_loop_dbg, 0, nb) == cudaSuccess;
   }
   ok = ok && cudaMalloc((void**) &c->d_bar, sizeof(GridBar)) == cudaSuccess;
@@ -1198,7 +1202,7 @@ int srrg2b_ctx_destroy(srrg2b_ctx* c) {
   if (c->d_bar) cudaFree(c->d_bar);
   if (c->d_part) cudaFree(c->d_part);
   if (c->d_loop_dbg) {
-    std::vector<unsigned long long> t((size_t) kDbgIters * 2 * kDbgWords);
+    std::vector<unsigned long long> t((size_t) kDbgIters * 2 * kDbgWords + kDbgCtas * 4);
     if (cudaMemcpy(t.data(), c->d_loop_dbg, t.size() * 8, cudaMemcpyDeviceToHost) == cudaSuccess) {
       fprintf(stderr, "[srrg2b loop debug] last run, per loop iteration: CTA0 | last CTA : tiles tail arrive [all-arrived solved] released (us from iteration start), fails\n");
       for (int it = 0; it < kDbgIters; ++it) {
@@ -1206,9 +1210,24 @@ int srrg2b_ctx_destroy(srrg2b_ctx* c) {
         const unsigned long long* b = a + kDbgWords;
         if (!a[0] || !a[6]) continue;
         auto us = [](unsigned long long x, unsigned long long x0) { return x ? (double) (long long) (x - x0) * 1e-3 : -1.0; };
-        fprintf(stderr, "  it %2d | %6.1f %6.1f %6.1f [%6.1f %6.1f] %6.1f  f=%llu | %6.1f %6.1f %6.1f %6.1f  f=%llu\n", it, us(a[1], a[0]),
-                us(a[2], a[0]), us(a[3], a[0]), us(a[4], a[0]), us(a[5], a[0]), us(a[6], a[0]), a[7], us(b[1], b[0]), us(b[2], b[0]),
-                us(b[3], b[0]), us(b[6], b[0]), b[7]);
+        fprintf(stderr, "  it %2d | %6.1f %6.1f %6.1f [%6.1f %6.1f] %6.1f  f=%llu work=%llu | %6.1f %6.1f %6.1f %6.1f  f=%llu | next it +%.1f\n", it, us(a[1], a[0]),
+                us(a[2], a[0]), us(a[3], a[0]), us(a[4], a[0]), us(a[5], a[0]), us(a[6], a[0]), a[7] & 0xffffffffull, a[7] >> 32, us(b[1], b[0]), us(b[2], b[0]),
+                us(b[3], b[0]), us(b[6], b[0]), b[7] & 0xffffffffull, it + 1 < kDbgIters ? us(a[kDbgWords * 2], a[0]) : -1.0);
+      }
+    }
+    {  // per-CTA view of loop iteration kDbgCtaIter: when the CTA's pass ended and when it arrived at the barrier
+      const unsigned long long* q = &t[(size_t) kDbgIters * 2 * kDbgWords];
+      const unsigned long long t0 = t[((size_t) kDbgCtaIter * 2) * kDbgWords];
+      if (t0) {
+        std::vector<std::pair<double, int>> order;
+        for (int b = 0; b < kDbgCtas; ++b) if (q[4 * b + 1]) order.push_back({(double) (long long) (q[4 * b + 1] - t0) * 1e-3, b});
+        std::sort(order.begin(), order.end());
+        fprintf(stderr, "[srrg2b loop debug] iteration %d, CTAs by barrier arrival (us from CTA 0's iteration start): cta: pass-end arrive fails\n", kDbgCtaIter);
+        for (size_t k = 0; k < order.size(); ++k) {
+          if (k >= 4 && k + 12 < order.size()) continue;
+          const int b = order[k].second;
+          fprintf(stderr, "   cta %3d: %6.1f %6.1f  f=%llu\n", b, (double) (long long) (q[4 * b] - t0) * 1e-3, order[k].first, q[4 * b + 2]);
+        }
       }
     }
     cudaFree(c->d_loop_dbg);

@@ -604,12 +604,15 @@ __device__ __forceinline__ int slot_candidate(int slot) {
 // was certified at -- a converged estimate spends nothing of it, however long the run.  A certified bound
 // lb is stored as (lb - D_cert), rounded down, with the epoch id in its 6 low mantissa bits; 0 = no bound.
 constexpr int kEpochs = 64, kSlbDcert = 16, kSlbEpoch = 18, kSlbDtab = 32, kSlbEpS = 96, kSlbFloats = 96 + 12 * kEpochs;
-__device__ __forceinline__ float encode_bound(float lb, const float* S_lb) {
-  const float d_cert = *reinterpret_cast<const volatile float*>(S_lb + kSlbDcert);
-  const int ep = *reinterpret_cast<const volatile int*>(S_lb + kSlbEpoch);
+__device__ __forceinline__ float encode_bound_at(float lb, float d_cert, int ep) {
   const float v = (lb - d_cert) * (1.f - 2.4e-7f) - 1e-9f;
   if (!(lb > 0.f) || !(v > 1e-30f)) return 0.f;
   return __int_as_float((__float_as_int(v) & ~(kEpochs - 1)) | (ep & (kEpochs - 1)));
+}
+__device__ __forceinline__ float encode_bound(float lb, const float* S_lb) {
+  const float d_cert = *reinterpret_cast<const volatile float*>(S_lb + kSlbDcert);
+  const int ep = *reinterpret_cast<const volatile int*>(S_lb + kSlbEpoch);
+  return encode_bound_at(lb, d_cert, ep);
 }
 // bound minus everything the query can have moved since certification (<= 0: nothing left / no bound)
 __device__ __forceinline__ float decode_bound(float stored, const float* dtab) {
@@ -1010,16 +1013,14 @@ __device__ __forceinline__ void lin_one_slot(const SliceArgs& a, const LinConst&
 // per-thread sums are known to stay below 2^26, else two over 16-bit halves, which cannot overflow the
 // 32-bit warp sum), the warp's 40 sums parked in lanes, one plain shared store per lane, then 40
 // threads add the warps' rows and issue one global atomic per slot and CTA.
-constexpr int kMaxWarps = 16;  // CTAs of the accumulating kernels have at most 512 threads
+constexpr int kMaxWarps = 12;  // CTAs of the accumulating kernels have at most 384 threads (s2b_loop.cuh: kLoopThreads)
 struct FlushSmem {
   long long w[kMaxWarps][kAcc];
 };
 
-// cta_dst: when non-null the CTA's sums are ADDED to these shared-memory words (one writer per slot) instead of
-// going to the global accumulators with atomics -- the persistent loop publishes them once per iteration
+// first half: the warp's sums, parked in lanes (lane l keeps slot l in mine0 and slot 32 + l in mine1)
 template <int DIM>
-__device__ __forceinline__ void lin_flush(unsigned long long* acc, bool few, const LinAcc<DIM>& A, FlushSmem& sm,
-                                          long long* cta_dst = nullptr) {
+__device__ __forceinline__ void lin_warp_reduce(bool few, const LinAcc<DIM>& A, long long& mine0, long long& mine1) {
   constexpr int P = LinAcc<DIM>::P, NH = LinAcc<DIM>::NH;
   auto wsum = [few](int v) -> long long {
     if (few) return (long long) __reduce_add_sync(0xffffffffu, v);
@@ -1027,10 +1028,10 @@ __device__ __forceinline__ void lin_flush(unsigned long long* acc, bool few, con
     const int hi = __reduce_add_sync(0xffffffffu, v >> 16);
     return ((long long) hi << 16) + (long long) lo;
   };
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
   // the accumulators hold raw bit patterns (see to_raw): take out count * bits(3.5f), modulo 2^32
   const int bias = A.n_terms * kFixBias;
-  long long mine0 = 0, mine1 = 0;  // lane l keeps slot l and slot 32 + l
+  mine0 = 0; mine1 = 0;
 #pragma unroll
   for (int k = 0; k < NH; ++k) {
     const long long v = wsum(A.aH[k] - bias);
@@ -1058,6 +1059,14 @@ __device__ __forceinline__ void lin_flush(unsigned long long* acc, bool few, con
       else { if (lane == kAccNIn + k - 32) mine1 = v; }
     }
   }
+}
+
+// second half: the warps' rows through shared memory, one writer per slot.
+// cta_dst: when non-null the CTA's sums are ADDED to these shared-memory words (one writer per slot) instead of
+// going to the global accumulators with atomics -- the persistent loop publishes them once per iteration
+__device__ __forceinline__ void lin_cta_reduce(unsigned long long* acc, long long mine0, long long mine1, FlushSmem& sm,
+                                               long long* cta_dst = nullptr) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   sm.w[warp][lane] = mine0;
   if (lane < kAcc - 32) sm.w[warp][32 + lane] = mine1;
   __syncthreads();
@@ -1069,6 +1078,14 @@ __device__ __forceinline__ void lin_flush(unsigned long long* acc, bool few, con
     else if (v) atomicAdd(&acc[threadIdx.x], (unsigned long long) v);
   }
   __syncthreads();  // sm may be reused right away (the persistent loop flushes once per slice and iteration)
+}
+
+template <int DIM>
+__device__ __forceinline__ void lin_flush(unsigned long long* acc, bool few, const LinAcc<DIM>& A, FlushSmem& sm,
+                                          long long* cta_dst = nullptr) {
+  long long mine0, mine1;
+  lin_warp_reduce<DIM>(few, A, mine0, mine1);
+  lin_cta_reduce(acc, mine0, mine1, sm, cta_dst);
 }
 
 // one thread's partial sums (a few scalar-path correspondences) into shared-memory accumulators, bias removed
@@ -1086,6 +1103,31 @@ __device__ __forceinline__ void lin_push_tail(const LinAcc<DIM>& A, long long* t
   add(kAccChiOut, (long long) (A.chi_out - bias)); add(kAccChiOut + 1, (long long) (A.chi_out_lo - bias));
   add(kAccNIn, A.n_io & 0xffff); add(kAccNOut, (unsigned) A.n_io >> 16);
   add(kAccNSup, A.n_ss & 0xffff); add(kAccNSat, (unsigned) A.n_ss >> 16);
+}
+
+// the same for a warp in which only lane 0 holds sums: the lanes take a slot each (one atomic per lane instead
+// of 40 serial ones)
+template <int DIM>
+__device__ __forceinline__ void lin_push_tail_lane0(const LinAcc<DIM>& A, long long* tail) {
+  constexpr int P = LinAcc<DIM>::P, NH = LinAcc<DIM>::NH;
+  const int lane = threadIdx.x & 31;
+  const int bias = A.n_terms * kFixBias;
+  long long mine0 = 0, mine1 = 0;
+  auto give = [&](int slot, int v) {
+    const int t = __shfl_sync(0xffffffffu, v, 0);
+    if (slot < 32) { if (lane == slot) mine0 = (long long) t; }
+    else { if (lane == slot - 32) mine1 = (long long) t; }
+  };
+#pragma unroll
+  for (int k = 0; k < NH; ++k) give(k, A.aH[k] - bias);
+#pragma unroll
+  for (int k = 0; k < P; ++k) give(kAccB + k, A.ab[k] - bias);
+  give(kAccChiIn, A.chi_all - A.chi_out); give(kAccChiIn + 1, A.chi_all_lo - A.chi_out_lo);
+  give(kAccChiOut, A.chi_out - bias); give(kAccChiOut + 1, A.chi_out_lo - bias);
+  give(kAccNIn, A.n_io & 0xffff); give(kAccNOut, (int) ((unsigned) A.n_io >> 16));
+  give(kAccNSup, A.n_ss & 0xffff); give(kAccNSat, (int) ((unsigned) A.n_ss >> 16));
+  if (mine0) atomicAdd(reinterpret_cast<unsigned long long*>(tail + lane), (unsigned long long) mine0);
+  if (lane < kAcc - 32 && mine1) atomicAdd(reinterpret_cast<unsigned long long*>(tail + 32 + lane), (unsigned long long) mine1);
 }
 
 // Phase 2 / tail kernel.  Large work lists: the far list of phase 1 (see nn_far_body).  Short work
@@ -1425,10 +1467,12 @@ __device__ __forceinline__ float2 epoch_displacement2(const float* Sn, const flo
     dt += d * d;
     tn += (double) Sn[r * 4 + 3] * (double) Sn[r * 4 + 3];
   }
-  const float kr = (float) (sqrt(dr) * (1.0 + 1e-6)) * (1.f + 2.4e-7f);
-  const float Dm = (kr * radius + (float) (sqrt(dt) * (1.0 + 1e-6))) * (1.f + 4.8e-7f);
-  const float qmax = radius * 1.0001f + (float) sqrt(tn);
-  const float kt = ((float) (sqrt(dt) * (1.0 + 1e-6)) + (1e-6f * qmax + 2e-7f * (1.f + Dm))) * (1.f + 4.8e-7f);
+  // (the rounding slack 1e-6 (|m| + |t|) of the two transformed queries is split the same way: the partial sums of
+  //  query m are bounded by 1.001 |m| + |t|, not only by the slice-wide maximum)
+  const float kr0 = (float) (sqrt(dr) * (1.0 + 1e-6)) * (1.f + 2.4e-7f);
+  const float Dm = (kr0 * radius + (float) (sqrt(dt) * (1.0 + 1e-6))) * (1.f + 4.8e-7f);
+  const float kr = (kr0 + 1.0011e-6f) * (1.f + 2.4e-7f);
+  const float kt = ((float) (sqrt(dt) * (1.0 + 1e-6)) + (1e-6f * (float) (sqrt(tn) * (1.0 + 1e-6)) + 2e-7f * (1.f + Dm))) * (1.f + 4.8e-7f);
   return make_float2(kr, kt);
 }
 
@@ -1481,14 +1525,14 @@ __device__ __forceinline__ unsigned long long ld_volatile_sys(const unsigned lon
   return v;
 }
 
-constexpr int kPartGroups = 6;
+constexpr int kPartSlots = 384;  // (group, word) partial sums of the per-CTA rows: one per thread of the loop kernel's CTA
 // shared-memory staging of the solve step
 struct SolveSmem {
   alignas(16) SolveArgs a;
   alignas(16) DevHeader sh;
   PeerExchange pe;
   int timed_out;
-  long long part[kPartGroups][SRRG2B_MAX_SLICES * kAcc];
+  long long part[kPartSlots];
 };
 
 // The solve step of one iteration, executed by ONE CTA with at least kSolveThreads threads (the first
@@ -1530,29 +1574,34 @@ __device__ __forceinline__ bool icp_solve_block(const SolveArgs* ap, DevState* s
   __syncthreads();
   if (sh.stop) return true;  // (every rank holds the same state, so every rank returns here or none does)
   if (part_rows) {
-    // groups of 64 threads sum a share of the rows each, eight independent loads in flight per thread
+    // the threads are dealt out word-major: group g = tid / n_words sums the rows g, g + G, ... of word tid % n_words,
+    // all of a thread's loads in flight together (one or two L2 round trips for the whole reduction)
     const int n_words = a.n_slices * kAcc;
-    const int n_groups = min((int) blockDim.x >> 6, kPartGroups);
-    if (tid < n_groups * 64) {
-      const int g = tid >> 6, k0 = tid & 63;
-      for (int k = k0; k < n_words; k += 64) {
-        long long v = 0;
-        int r = g;
-        for (; r + 7 * n_groups < n_part; r += 8 * n_groups) {
-          long long t[8];
+    const int n_groups = max(min((int) blockDim.x, kPartSlots) / n_words, 1);
+    if (tid < n_groups * n_words) {
+      const int g = tid / n_words, k = tid - g * n_words;
+      long long v = 0;
+      int r = g;
+      for (; r + 15 * n_groups < n_part; r += 16 * n_groups) {
+        long long t[16];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) t[u] = __ldcg(part_rows + (size_t) (r + u * n_groups) * (SRRG2B_MAX_SLICES * kAcc) + k);
+        for (int u = 0; u < 16; ++u) t[u] = __ldcg(part_rows + (size_t) (r + u * n_groups) * (SRRG2B_MAX_SLICES * kAcc) + k);
 #pragma unroll
-          for (int u = 0; u < 8; ++u) v += t[u];
-        }
-        for (; r < n_part; r += n_groups) v += __ldcg(part_rows + (size_t) r * (SRRG2B_MAX_SLICES * kAcc) + k);
-        sm.part[g][k] = v;
+        for (int u = 0; u < 16; ++u) v += t[u];
       }
+      {
+        long long t[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) { const int rr = r + u * n_groups; t[u] = rr < n_part ? __ldcg(part_rows + (size_t) rr * (SRRG2B_MAX_SLICES * kAcc) + k) : 0ll; }
+#pragma unroll
+        for (int u = 0; u < 16; ++u) v += t[u];
+      }
+      sm.part[g * n_words + k] = v;
     }
     __syncthreads();
     for (int k = tid; k < n_words; k += blockDim.x) {
       long long v = 0;
-      for (int g = 0; g < n_groups; ++g) v += sm.part[g][k];
+      for (int g = 0; g < n_groups; ++g) v += sm.part[g * n_words + k];
       (&sh.acc[0][0])[k] += (unsigned long long) v;
     }
     __syncthreads();

@@ -34,8 +34,8 @@ constexpr int kPPL = S2B_LOOP_PPL;         // pairs per lane and tile
 constexpr int kSubTile = 64;               // correspondences of one sub-tile: one pair per lane
 constexpr int kWTile = kSubTile * kPPL;    // correspondences per warp tile
 constexpr int kStages = S2B_LOOP_STAGES;
-constexpr int kFailCap = 24;               // coherence-check failures a CTA resolves in place per pass (one warp per
-                                           // query: two rounds of its 12 warps); the rest go to the global work list
+constexpr int kFailCap = 48;               // coherence-check failures a CTA resolves in place per pass (one warp per
+                                           // query); the rest go to the global work list
 constexpr int kBigList = 1024;             // global work lists from this size on are searched thread-per-query
 
 // One sub-tile (one pair per lane) of one ring stage of ONE warp (4 KB).  Every warp runs its own pipeline
@@ -57,13 +57,23 @@ struct TileStage {
 constexpr size_t kLoopSmemBytes = sizeof(TileStage) * kStages;
 static_assert(kLoopSmemBytes <= 200 * 1024, "ring does not fit");
 
+// a query that failed the coherence check, with everything its tile held about it (64 bytes)
+struct FailRec {
+  float4 m, nm, f, nf;  // moving point (.w: its index, integer bits) / normal (.w: old slot), the slot's fixed
+                        // point (.w: original index) / normal
+};
 // static shared memory of the tile pass
 struct TileCtl {
   LinConst lk;
   FlushSmem fsm;
   unsigned long long full[kLoopWarps][kStages];  // mbarriers: the bulk copies of a warp's stage have landed
-  int fail[kFailCap];
-  int nfail;
+  int nfail;                        // coherence-check failures of the CTA in the running pass
+  int nfail_prev[SRRG2B_MAX_SLICES];  // ... in the slice's previous check pass (decides who searches them)
+  FailRec rec[kFailCap];            // the failures the CTA resolves itself after its tiles (one warp per query)
+  int nrec;                         // ... how many
+  int ep_cur;                       // id of the epoch this pass certifies bounds for
+  int pref;                         // prefetch state of the next check pass (see loop_prefetch)
+  int inline_ok;                    // this pass: the warps resolve their (few) failures themselves
   int rows[kRowTable];
   unsigned phase_bits[kLoopWarps];  // parity of the next wait per stage, per warp (survives between passes)
   long long tail[kAcc];  // sums of the correspondences resolved by the CTA's search warps (lin_push_tail)
@@ -168,26 +178,33 @@ struct PairWork {
 // else every slot is linearised as it is.  Every warp streams its own tiles (warp w of CTA b takes tiles
 // g, g + W, g + 2W, ... with g = w * gridDim + b, W = all warps of the grid) through its own ring; every lane
 // evaluates kPPL independent pairs per tile back to back, so that their instruction streams interleave.
-// The warp's accumulators end up in A (flushed by the caller).  Requires blockDim.x == kLoopThreads.
+// The warp's accumulators end up in A (flushed by the caller); returns the number of terms a thread may have added
+// to a slot since A was last cleared.  Requires blockDim.x == kLoopThreads.
+// CHECK: the first failures of the CTA are recorded in ctl.rec (the caller has them searched once the tiles are
+// done); beyond the cap they go to the global work list.
 template <int DIM, int FACTOR, bool CHECK>
-__device__ __forceinline__ void lin_tiles_body(const SliceArgs& a, TileStage* stages, TileCtl& ctl, LinAcc<DIM>& A) {
+__device__ __forceinline__ int lin_tiles_body(const SliceArgs& a, TileStage* stages, TileCtl& ctl, LinAcc<DIM>& A) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n_tiles = (a.nm + kWTile - 1) / kWTile;
   const int W = gridDim.x * kLoopWarps, g0 = warp * gridDim.x + blockIdx.x;
   const int my_tiles = g0 < n_tiles ? (n_tiles - g0 + W - 1) / W : 0;
   const LinConst& k = ctl.lk;
   const bool regate = a.gate != 0;  // gated-out slots are re-checked every iteration
-  if (my_tiles == 0) return;
+  if (my_tiles == 0) return 0;
   unsigned long long* bars = ctl.full[warp];
-  // prologue: bulk copies of the warp's first kStages tiles, gathers of the first
-  if (lane == 0) {
+  // prologue: bulk copies of the warp's first kStages tiles, gathers of the first -- unless the CTA prefetched
+  // them while it waited at the previous barrier (pref: 1 = bulk copies issued, 3 = the first gathers too)
+  const int pref = CHECK ? ctl.pref : 0;
+  if (!(pref & 1) && lane == 0) {
     asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy writes (slots, bounds) before the bulk reads
     for (int j = 0; j < kStages && j < my_tiles; ++j) tile_issue_bulk<CHECK>(a, stages[j].w[warp], &bars[j], g0 + j * W);
   }
   unsigned phase = ctl.phase_bits[warp];
-  mbar_wait(&bars[0], phase & 1u);
-  phase ^= 1u;
-  tile_issue_gather(a, stages[0].w[warp], g0 * kWTile, lane);
+  if (!(pref & 2)) {
+    mbar_wait(&bars[0], phase & 1u);
+    phase ^= 1u;
+    tile_issue_gather(a, stages[0].w[warp], g0 * kWTile, lane);
+  }
   for (int j = 0; j < my_tiles; ++j) {
     const int st = j % kStages;
     WarpStage& WS = stages[st].w[warp];
@@ -279,16 +296,36 @@ __device__ __forceinline__ void lin_tiles_body(const SliceArgs& a, TileStage* st
           }
         }
 #endif
-        if (failA | failB) {
-          // the first kFailCap failures of the CTA are searched and linearised by its own warps after the
-          // tiles (converged iterations: a handful per CTA); the rest go to the global work list
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            if (!(h ? failB : failA)) continue;
-            const int i = h ? iB : iA;
-            const int kf = atomicAdd(&ctl.nfail, 1);
-            if (kf < kFailCap) ctl.fail[kf] = i;
-            else a.work_list[atomicAdd(a.work_count, 1)] = i;
+        const unsigned fmA = __ballot_sync(0xffffffffu, failA), fmB = __ballot_sync(0xffffffffu, failB);
+        if (fmA | fmB) {
+          // a few failures (converged iterations: a handful per CTA and pass): recorded -- with everything the
+          // search and the lineariser need, so that nothing is fetched twice -- in the warp's list; more: the
+          // global work list (searched grid-wide after the barrier)
+          const int nA = __popc(fmA), n = nA + __popc(fmB);
+          const unsigned lt = (1u << lane) - 1u;
+          int before = 0;
+          if (lane == 0) before = atomicAdd(&ctl.nfail, n);
+          before = __shfl_sync(0xffffffffu, before, 0);
+          if (ctl.inline_ok && before + n <= kFailCap) {
+            if (failA) {
+              FailRec& r = ctl.rec[before + __popc(fmA & lt)];
+              r.m = make_float4(w.m.x.v.x, w.m.y.v.x, w.m.z.v.x, __int_as_float(iA));
+              r.nm = make_float4(w.nm.x.v.x, w.nm.y.v.x, w.nm.z.v.x, __int_as_float(w.slotA));
+              r.f = w.fA; r.nf = w.nf.a;
+            }
+            if (failB) {
+              FailRec& r = ctl.rec[before + nA + __popc(fmB & lt)];
+              r.m = make_float4(w.m.x.v.y, w.m.y.v.y, w.m.z.v.y, __int_as_float(iB));
+              r.nm = make_float4(w.nm.x.v.y, w.nm.y.v.y, w.nm.z.v.y, __int_as_float(w.slotB));
+              r.f = w.fB; r.nf = w.nf.b;
+            }
+            if (lane == 0) atomicMax(&ctl.nrec, before + n);
+          } else {
+            int at = 0;
+            if (lane == 0) at = atomicAdd(a.work_count, n);
+            at = __shfl_sync(0xffffffffu, at, 0);
+            if (failA) a.work_list[at + __popc(fmA & lt)] = iA;
+            if (failB) a.work_list[at + nA + __popc(fmB & lt)] = iB;
           }
         }
       } else {
@@ -332,14 +369,13 @@ __device__ __forceinline__ void lin_tiles_body(const SliceArgs& a, TileStage* st
       __syncwarp();
       if (lane == 0) tile_issue_bulk<CHECK>(a, WS, &bars[st], g0 + (j + kStages) * W);
     }
+    if ((j & 127) == 127) {  // 32-bit partial sums: a thread stays below 512 terms per flush (huge slices only)
+      lin_push_tail<DIM>(A, ctl.tail);
+      A.clear();
+    }
   }
   if (lane == 0) ctl.phase_bits[warp] = phase;
-}
-
-// (a thread adds at most 2 kPPL terms per tile of its warp: one REDUX per slot suffices up to 30 terms)
-__device__ __forceinline__ bool lin_tiles_few(const SliceArgs& a) {
-  const int n_tiles = (a.nm + kWTile - 1) / kWTile, W = gridDim.x * kLoopWarps;
-  return 2 * kPPL * ((n_tiles + W - 1) / W) <= 30;
+  return 2 * kPPL * (my_tiles & 127);
 }
 
 // the CTA's control block: mbarriers of the ring, lineariser constants of the slice about to be processed
@@ -349,7 +385,8 @@ __device__ __forceinline__ void tile_ctl_init(TileCtl& ctl) {
     ctl.phase_bits[threadIdx.x] = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (threadIdx.x == 0) ctl.nfail = 0;
+  if (threadIdx.x == 0) { ctl.nfail = 0; ctl.nrec = 0; ctl.inline_ok = 0; ctl.ep_cur = 0; ctl.pref = 0; }
+  if (threadIdx.x < SRRG2B_MAX_SLICES) ctl.nfail_prev[threadIdx.x] = INT_MAX;
   if (threadIdx.x < kAcc) ctl.tail[threadIdx.x] = 0;
   for (int k = threadIdx.x; k < SRRG2B_MAX_SLICES * kAcc; k += blockDim.x) (&ctl.cta_acc[0][0])[k] = 0;
 }
@@ -369,8 +406,10 @@ __global__ void __launch_bounds__(kLoopThreads, 1) lin_tiles_kernel(const SliceA
   __syncthreads();
   LinAcc<DIM> A;
   A.clear();
-  lin_tiles_body<DIM, FACTOR, false>(a, stages, ctl, A);
-  lin_flush<DIM>(a.acc, lin_tiles_few(a), A, ctl.fsm);
+  const int terms = lin_tiles_body<DIM, FACTOR, false>(a, stages, ctl, A);
+  lin_flush<DIM>(a.acc, terms <= 30, A, ctl.fsm);
+  // (sums a warp parked in the shared tail accumulators on the way: huge slices only)
+  if (threadIdx.x < kAcc && ctl.tail[threadIdx.x]) atomicAdd(&a.acc[threadIdx.x], (unsigned long long) ctl.tail[threadIdx.x]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -382,6 +421,7 @@ struct LoopArgs {
   const PeerExchange* px;
   GridBar* bar;
   long long timeout_cycles;
+  int big_list;             // global work lists from this size on are searched thread-per-query (else warp-per-query)
   int n_slices;
   int factor[SRRG2B_MAX_SLICES];
   int is_points[SRRG2B_MAX_SLICES];
@@ -395,7 +435,7 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
-constexpr int kDbgIters = 64, kDbgWords = 8;
+constexpr int kDbgIters = 64, kDbgWords = 8, kDbgCtas = 160, kDbgCtaIter = 10;
 // time stamp `k` of the current iteration (only CTA 0 and the last CTA record, thread 0)
 __device__ __forceinline__ void loop_dbg(const LoopArgs& L, int it, int k, unsigned long long v) {
   if (!L.dbg || threadIdx.x != 0 || it >= kDbgIters) return;
@@ -500,8 +540,9 @@ __device__ __forceinline__ void proj_find_body(const SliceArgs& a, const float* 
 // lineariser constants of slice s into the control block (S from the device state, coherently)
 __device__ __forceinline__ void loop_load_lin_const(const SliceArgs& a, const DevState* st, int s, TileCtl& ctl) {
   const int tid = threadIdx.x;
-  if (tid == 0) ctl.nfail = 0;
+  if (tid == 0) { ctl.nfail = 0; ctl.nrec = 0; ctl.inline_ok = ctl.nfail_prev[s] <= kFailCap ? 1 : 0; }
   if (tid < 12) ctl.lk.S[tid] = __ldcg(&st->S[s].m[tid]);
+  if (tid == 33 && a.S_lb) ctl.ep_cur = __ldcg(reinterpret_cast<const int*>(a.S_lb) + kSlbEpoch);
   if (tid >= 64 && tid < 64 + kEpochs && a.S_lb) {
     // displacement table of the slice's epochs at this pass's transform (epoch ep_cur = this pass)
     const int e = tid - 64, ep_cur = __ldcg(reinterpret_cast<const int*>(a.S_lb) + kSlbEpoch);
@@ -517,6 +558,118 @@ __device__ __forceinline__ void loop_load_lin_const(const SliceArgs& a, const De
     k.normal_cos = a.normal_cos; k.eb2 = a.eb2; k.rob = a.rob; k.gate = a.gate;
   }
   __syncthreads();
+}
+
+// The failures a warp recorded during its tiles: one query at a time, the whole warp searches (the lanes
+// fetch the bounds of the rows, the rows' points are dealt out to the lanes, shuffle arg-min -- nn_far_body's
+// scheme), lane 0 writes slot + bound and linearises.  Everything the tile already held (query, old slot, the
+// slot's fixed point and both normals) comes from the record: the dependent chain is row bounds -> points.
+// The sums travel through the CTA's shared tail accumulators.  Cold path, kept out of line.
+template <int DIM, bool TRACK2, int FACTOR>
+__device__ __forceinline__ void fail_search_body(const SliceArgs& a, TileCtl& ctl, int n, const FailRec* recs, LinAcc<DIM>& A) {
+  const int w0 = threadIdx.x >> 5, ws = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const float* S = ctl.lk.S;
+  const float cell = __fdiv_rn(1.f, a.inv_cell);
+  const int K = (DIM == 3) ? (2 * a.R + 1) * (2 * a.R + 1) : (2 * a.R + 1);
+  const int K1 = min(K, (DIM == 3 ? 9 : 3));
+  for (int w = w0; w < n; w += ws) {
+    const FailRec& rec = recs[w];
+    const float4 m = rec.m;
+    const int i = __float_as_int(m.w), old_slot = __float_as_int(rec.nm.w);
+    NNQuery q;
+    nn_setup<DIM>(a, S, m, q);
+    const int p0 = slot_candidate(old_slot);
+    if (a.warm && p0 >= 0) { nn_consider_pt<DIM, TRACK2>(q, p0, rec.f); if (TRACK2) nn_limit_bound(q, cell); }
+    for (int stage = 0; stage < 2; ++stage) {
+      const int kb = stage ? K1 : 0, ke = stage ? K : K1;
+      if (kb >= ke) break;
+      for (int k0 = kb; k0 < ke; k0 += 32) {
+        int ps = 0, cnt = 0;
+        const int k = k0 + lane;
+        if (k < ke) {
+          const int e = ctl.rows[k];
+          const int dy = (int) (signed char) (e & 0xff), dz = (int) (signed char) ((e >> 8) & 0xff);
+          const int y = q.cy + dy, z = q.cz + dz;
+          if (y >= 0 && y < a.ny && z >= 0 && z < a.nz) {
+            const float gy = axis_gap(dy, q.fry) * cell;
+            float lb2 = gy * gy;
+            if (DIM == 3) {
+              const float gz = axis_gap(dz, q.frz) * cell;
+              lb2 = fmaf(gz, gz, lb2);
+            }
+            const float pr2 = TRACK2 ? q.sd2 : q.bd2;
+            if (!(lb2 > pr2)) {
+              const float rr = __fsqrt_rn(fmaxf(pr2 - lb2, 0.f)) * a.inv_cell_x + 2e-3f;
+              const int xa = max(max((int) floorf(q.cfx - rr), q.cx - a.Rx), 0);
+              const int xb = min(min((int) floorf(q.cfx + rr), q.cx + a.Rx), a.nx - 1);
+              if (xa <= xb) {
+                const int row = (z * a.ny + y) * a.nx;
+                ps = __ldg(a.cell_start + row + xa);
+                cnt = __ldg(a.cell_start + row + xb + 1) - ps;
+              }
+            }
+          }
+        }
+        int incl = cnt;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+          const int v = __shfl_up_sync(0xffffffffu, incl, off);
+          if (lane >= off) incl += v;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        const int excl = incl - cnt;
+        for (int t0 = 0; t0 < total; t0 += 32) {
+          // candidate t lives in the last row whose exclusive prefix is <= t (empty rows are skipped)
+          const int ta = t0 + lane;
+          int ra = 0;
+#pragma unroll
+          for (int step = 16; step; step >>= 1) {
+            const int ea = __shfl_sync(0xffffffffu, excl, ra + step);
+            if (ea <= ta) ra += step;
+          }
+          const int pa = __shfl_sync(0xffffffffu, ps, ra) + (ta - __shfl_sync(0xffffffffu, excl, ra));
+          if (ta < total) nn_consider_pt<DIM, TRACK2>(q, pa, __ldg(a.fp + pa));
+        }
+      }
+#pragma unroll
+      for (int off = 16; off; off >>= 1) {
+        const float od2 = __shfl_xor_sync(0xffffffffu, q.bd2, off);
+        const float os2 = __shfl_xor_sync(0xffffffffu, q.sd2, off);
+        const int oidx = __shfl_xor_sync(0xffffffffu, q.bidx, off);
+        const int opos = __shfl_xor_sync(0xffffffffu, q.bpos, off);
+        const bool other_wins = od2 < q.bd2 || (od2 == q.bd2 && oidx < q.bidx);
+        if (TRACK2) {
+          // the loser's best is a runner-up unless both lanes hold the same point (shared warm start)
+          float s2 = fminf(q.sd2, os2);
+          if (q.bpos >= 0 && opos >= 0 && q.bpos != opos) s2 = fminf(s2, other_wins ? q.bd2 : od2);
+          q.sd2 = s2;
+        }
+        if (other_wins) { q.bd2 = od2; q.bidx = oidx; q.bpos = opos; }
+      }
+    }
+    if (lane == 0) {
+      // (inside the ICP loop a pass certifies exactly at its epoch's transform: D_cert = 0)
+      a.c_lb[i] = encode_bound_at(TRACK2 ? __fsqrt_rn(q.sd2) * (1.f - 1e-5f) : 0.f, 0.f, ctl.ep_cur);
+      const int slot = nn_finish_keep<DIM>(a, S, q, i, old_slot);
+      const int bpos = a.gate ? slot_candidate(slot) : slot;
+      if (bpos >= 0) {
+        const bool same = bpos == p0;  // (the usual outcome: the neighbour stands, only its bound is renewed)
+        const float4 f = same ? rec.f : __ldg(a.frec + 2 * (size_t) bpos), nf = same ? rec.nf : __ldg(a.frec + 2 * (size_t) bpos + 1);
+        lin_one_slot<DIM, FACTOR>(a, ctl.lk, i, slot, bpos, m, rec.nm, f, nf, A);
+      } else if (a.c_stat) {
+        a.c_stat[i] = SRRG2B_STAT_NONE;
+      }
+    }
+  }
+}
+template <int DIM, int FACTOR>
+__device__ __noinline__ void loop_search_recs(const SliceArgs& a, TileCtl& ctl, int track2, int n, const FailRec* recs) {
+  LinAcc<DIM> A;
+  A.clear();
+  if (track2) fail_search_body<DIM, true, FACTOR>(a, ctl, n, recs, A);
+  else fail_search_body<DIM, false, FACTOR>(a, ctl, n, recs, A);
+  lin_push_tail_lane0<DIM>(A, ctl.tail);
 }
 
 // One warp per listed query: search, slot + bound, linearisation; the sums go to the slice's accumulators.
@@ -535,35 +688,45 @@ __device__ __noinline__ void loop_search_list(const SliceArgs& a, TileCtl& ctl, 
   else lin_flush<DIM>(a.acc, false, A, ctl.fsm);
 }
 
-// one pass of the streaming lineariser over a slice inside the loop kernel; the CTA's sums are added to
+// one pass of the streaming lineariser over slice s inside the loop kernel; the CTA's sums are added to
 // cta_acc (shared memory, published once per iteration: no global atomics on the hot path)
 template <int DIM, int FACTOR, bool CHECK>
-__device__ __forceinline__ void loop_lin_pass(const SliceArgs& a, TileStage* stages, TileCtl& ctl, int track2, long long* cta_acc,
-                                              unsigned long long* dbg = nullptr) {
+__device__ __forceinline__ void loop_lin_pass(const SliceArgs& a, TileStage* stages, TileCtl& ctl, int s, int track2, long long* cta_acc,
+                                              unsigned long long* dbg = nullptr, unsigned long long* dbgc = nullptr) {
   {
-    LinAcc<DIM> A;
-    A.clear();
-    lin_tiles_body<DIM, FACTOR, CHECK>(a, stages, ctl, A);
-    if (dbg) dbg[1] = globaltimer_ns();
-    lin_flush<DIM>(a.acc, lin_tiles_few(a), A, ctl.fsm, cta_acc);  // (before the search below: the accumulators are dead across that call)
+    long long mine0, mine1;
+    {
+      LinAcc<DIM> A;
+      A.clear();
+      const int terms = lin_tiles_body<DIM, FACTOR, CHECK>(a, stages, ctl, A);
+      if (dbg) dbg[1] = globaltimer_ns();
+      if (dbgc && (threadIdx.x & 31) == 0) atomicMax(dbgc, globaltimer_ns());
+      lin_warp_reduce<DIM>(terms <= 30, A, mine0, mine1);
+    }
+    // the warp's failures: searched and linearised here, while the other warps are still streaming (the
+    // accumulators are reduced to two words per lane by now: nothing to spill around the call)
+    if (CHECK) {
+      __syncthreads();  // every warp is done with its tiles: the record list is complete
+      if ((int) (threadIdx.x >> 5) < ctl.nrec) loop_search_recs<DIM, FACTOR>(a, ctl, track2, ctl.nrec, ctl.rec);
+    }
+    lin_cta_reduce(a.acc, mine0, mine1, ctl.fsm, cta_acc);
+  }
+  // the sums of the failures the warps resolved on the way (and of mid-pass flushes) sit in the shared tail
+  if (threadIdx.x < kAcc) {
+    const long long v = ctl.tail[threadIdx.x];
+    if (cta_acc) cta_acc[threadIdx.x] += v;
+    else if (v) atomicAdd(&a.acc[threadIdx.x], (unsigned long long) v);
+    ctl.tail[threadIdx.x] = 0;
   }
   if (CHECK) {
-    // the CTA's coherence-check failures: one warp per query (search, slot + bound, linearisation); their
-    // sums travel through the shared tail accumulators
-    const int n_local = min(ctl.nfail, kFailCap);
-    if (dbg) dbg[7] = (unsigned long long) ctl.nfail;
-    if (n_local > 0) {
-      loop_search_list<DIM, FACTOR>(a, ctl, track2, n_local, ctl.fail, threadIdx.x >> 5, blockDim.x >> 5, 1);
-      __syncthreads();
-      if (threadIdx.x < kAcc) { cta_acc[threadIdx.x] += ctl.tail[threadIdx.x]; ctl.tail[threadIdx.x] = 0; }
-    }
-    if (dbg) dbg[2] = globaltimer_ns();
+    if (dbg) { dbg[7] = (unsigned long long) ctl.nfail; dbg[2] = globaltimer_ns(); }
+    if (threadIdx.x == 0) ctl.nfail_prev[s] = ctl.nfail;
   }
 }
 
 template <int DIM, int FACTOR>
 __device__ __noinline__ void loop_lin_all(const SliceArgs& a, TileStage* stages, TileCtl& ctl) {
-  loop_lin_pass<DIM, FACTOR, false>(a, stages, ctl, 0, nullptr);
+  loop_lin_pass<DIM, FACTOR, false>(a, stages, ctl, 0, 0, nullptr);
 }
 
 // first phase of a from-scratch search of the whole slice (rings 0-1, thread per query)
@@ -630,6 +793,58 @@ __device__ __noinline__ void loop_solve(const LoopArgs& L, SolveSmem& ssm, bool 
 
 __device__ __noinline__ void loop_proj_find(const SliceArgs& a, const float* S) { proj_find_body(a, S); }
 
+// Prefetch of the next iteration's check pass over slice `a`: none of it depends on the transform the solve step
+// is about to produce, so the CTA starts its pipeline while it waits at the barrier.
+//   part 1 (before the arrival): the bulk copies of every warp's first kStages tiles;
+//   part 2 (after the arrival, by the CTAs that only wait): the gathers of the first tile.
+// Whoever cannot use the prefetched tiles (stop, a full search, work lists that rewrite slots) drains them.
+__device__ __forceinline__ void loop_prefetch_bulk(const SliceArgs& a, TileStage* stages, TileCtl& ctl) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n_tiles = (a.nm + kWTile - 1) / kWTile;
+  const int W = gridDim.x * kLoopWarps, g0 = warp * gridDim.x + blockIdx.x;
+  const int my_tiles = g0 < n_tiles ? (n_tiles - g0 + W - 1) / W : 0;
+  if (lane == 0 && my_tiles > 0) {
+    asm volatile("fence.proxy.async;" ::: "memory");
+    for (int j = 0; j < kStages && j < my_tiles; ++j) tile_issue_bulk<true>(a, stages[j].w[warp], &ctl.full[warp][j], g0 + j * W);
+  }
+  if (threadIdx.x == 0) ctl.pref = 1;  // (read behind the barrier's __syncthreads)
+}
+__device__ __forceinline__ void loop_prefetch_gather(const SliceArgs& a, TileStage* stages, TileCtl& ctl) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n_tiles = (a.nm + kWTile - 1) / kWTile;
+  const int g0 = warp * gridDim.x + blockIdx.x;
+  if (g0 < n_tiles) {
+    unsigned phase = ctl.phase_bits[warp];
+    mbar_wait(&ctl.full[warp][0], phase & 1u);
+    phase ^= 1u;
+    tile_issue_gather(a, stages[0].w[warp], g0 * kWTile, lane);
+    if (lane == 0) ctl.phase_bits[warp] = phase;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) ctl.pref = 3;
+}
+// the prefetched tiles will not be used: wait for the copies in flight (the mbarrier phases stay in step)
+__device__ __forceinline__ void loop_prefetch_drain(const SliceArgs& a, TileCtl& ctl) {
+  __syncthreads();
+  const int pref = ctl.pref;
+  if (pref) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n_tiles = (a.nm + kWTile - 1) / kWTile;
+    const int W = gridDim.x * kLoopWarps, g0 = warp * gridDim.x + blockIdx.x;
+    const int my_tiles = g0 < n_tiles ? (n_tiles - g0 + W - 1) / W : 0;
+    unsigned phase = ctl.phase_bits[warp];
+    for (int j = (pref & 2) ? 1 : 0; j < kStages && j < my_tiles; ++j) {
+      mbar_wait(&ctl.full[warp][j], (phase >> j) & 1u);
+      phase ^= 1u << j;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (lane == 0) ctl.phase_bits[warp] = phase;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) ctl.pref = 0;
+  __syncthreads();
+}
+
 // The hot pass (coherence check + linearisation of a certified slice).  SLOT >= 0: the slice arguments are
 // the compile-time entry L.sl[SLOT] of the kernel parameters, i.e. constant-bank operands that occupy no
 // registers; SLOT < 0: any slice (run-time index).
@@ -639,8 +854,10 @@ __device__ __forceinline__ void loop_check_pass(const LoopArgs& L, int s, TileSt
   unsigned long long* dbg = nullptr;
   if (L.dbg && threadIdx.x == 0 && it < kDbgIters && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1))
     dbg = L.dbg + ((size_t) it * 2 + (blockIdx.x == 0 ? 0 : 1)) * kDbgWords;
-  if (L.factor[SLOT >= 0 ? SLOT : s] == SRRG2B_FACTOR_P2P) loop_lin_pass<DIM, SRRG2B_FACTOR_P2P, true>(a, stages, ctl, track2, ctl.cta_acc[s], dbg);
-  else loop_lin_pass<DIM, SRRG2B_FACTOR_PLANE, true>(a, stages, ctl, track2, ctl.cta_acc[s], dbg);
+  unsigned long long* dbgc = nullptr;  // (latest pass end over the CTA's warps)
+  if (L.dbg && it == kDbgCtaIter && blockIdx.x < kDbgCtas) dbgc = L.dbg + (size_t) kDbgIters * 2 * kDbgWords + 4 * blockIdx.x;
+  if (L.factor[SLOT >= 0 ? SLOT : s] == SRRG2B_FACTOR_P2P) loop_lin_pass<DIM, SRRG2B_FACTOR_P2P, true>(a, stages, ctl, s, track2, ctl.cta_acc[s], dbg, dbgc);
+  else loop_lin_pass<DIM, SRRG2B_FACTOR_PLANE, true>(a, stages, ctl, s, track2, ctl.cta_acc[s], dbg, dbgc);
 }
 
 template <int DIM>
@@ -660,6 +877,11 @@ __global__ void __launch_bounds__(kLoopThreads, 1) icp_loop_kernel(const __grid_
   for (int k = tid; k < KMAX; k += blockDim.x)
     ctl.rows[k] = (DIM == 3) ? *reinterpret_cast<const int*>(c_rows3[k]) : *reinterpret_cast<const int*>(c_rows2[k]);
   __syncthreads();
+  // the slice whose check pass opens an iteration: its first tiles are prefetched across the barrier
+  int s0 = -1;
+  for (int s = L.n_slices - 1; s >= 0; --s)
+    if (L.is_points[s] && L.sl[s].nm > 0) s0 = s;
+  if (s0 >= 0 && L.sl[s0].projective) s0 = -1;
 
   for (int it = 0;; ++it) {
     loop_dbg(L, it, 0, globaltimer_ns());
@@ -670,6 +892,7 @@ __global__ void __launch_bounds__(kLoopThreads, 1) icp_loop_kernel(const __grid_
       s_ctrl[4 + SRRG2B_MAX_SLICES + tid] = __ldcg(&L.st->track2[tid]);
     }
     __syncthreads();
+    if (s0 >= 0 && ctl.pref && (s_ctrl[0] || s_ctrl[4 + s0])) loop_prefetch_drain(L.sl[s0], ctl);  // (not a check pass after all)
     if (s_ctrl[0]) break;
     bool fallback = false;  // some slice needs the full search path this iteration (uniform over the grid)
 
@@ -693,7 +916,9 @@ __global__ void __launch_bounds__(kLoopThreads, 1) icp_loop_kernel(const __grid_
         loop_check_pass<DIM, -1>(L, s, stages, ctl, track2, it);
       }
       __syncthreads();
+      if (tid == 0) ctl.pref = 0;  // (consumed by the pass of slice s0)
     }
+    if (!fallback && s0 >= 0) loop_prefetch_bulk(L.sl[s0], stages, ctl);
 
     // ---- publish this CTA's sums, barrier; in the all-certified case CTA 0 goes straight to the solve step ----
     for (int k = tid; k < L.n_slices * kAcc; k += blockDim.x) {
@@ -701,7 +926,12 @@ __global__ void __launch_bounds__(kLoopThreads, 1) icp_loop_kernel(const __grid_
       (&ctl.cta_acc[0][0])[k] = 0;
     }
     loop_dbg(L, it, 3, globaltimer_ns());
+    if (L.dbg && it == kDbgCtaIter && tid == 0 && blockIdx.x < kDbgCtas) {
+      unsigned long long* q = L.dbg + (size_t) kDbgIters * 2 * kDbgWords + 4 * blockIdx.x;
+      q[1] = globaltimer_ns(); q[2] = (unsigned long long) ctl.nfail_prev[0];
+    }
     sync.arrive(L);
+    if (blockIdx.x != 0 && ctl.pref == 1) loop_prefetch_gather(L.sl[s0], stages, ctl);  // (while CTA 0 solves)
     if (blockIdx.x == 0) {
       if (!sync.wait_all(L, bcast)) break;
       loop_dbg(L, it, 4, globaltimer_ns());
@@ -709,6 +939,7 @@ __global__ void __launch_bounds__(kLoopThreads, 1) icp_loop_kernel(const __grid_
       if (!fallback) {
         for (int s = 0; s < L.n_slices; ++s)
           if (L.is_points[s] && L.sl[s].nm > 0 && !L.sl[s].projective && __ldcg(L.sl[s].work_count) > 0) lists = true;
+        if (L.dbg && tid == 0 && it < kDbgIters) L.dbg[((size_t) it * 2) * kDbgWords + 7] |= (unsigned long long) __ldcg(L.sl[0].work_count) << 32;
       }
       if (!fallback && !lists) {
         loop_solve<DIM>(L, ssm, solved_before);
@@ -723,6 +954,7 @@ __global__ void __launch_bounds__(kLoopThreads, 1) icp_loop_kernel(const __grid_
     loop_dbg(L, it, 6, globaltimer_ns());
     if (mode < 0) break;
     if (mode == 0) continue;
+    if (s0 >= 0) loop_prefetch_drain(L.sl[s0], ctl);  // the work lists may rewrite slots and bounds of the prefetched tiles
 
     // ---- phase B (rare): overflow work lists of certified slices, far phase of the full searches ----
     bool far_phase = false;
@@ -739,7 +971,7 @@ __global__ void __launch_bounds__(kLoopThreads, 1) icp_loop_kernel(const __grid_
       } else {
         const int n_work = __ldcg(a.work_count);
         const int wpb = blockDim.x >> 5, w0 = blockIdx.x * wpb + (tid >> 5), ws = gridDim.x * wpb;
-        if (n_work >= kBigList) {  // long list: thread per query, then the far phase and a list linearisation
+        if (n_work >= L.big_list) {  // long list: thread per query, then the far phase and a list linearisation
           far_phase = true;
           loop_search_list_phase1<DIM>(a, ctl, track2, n_work);
         } else if (n_work > 0) {   // short list: one warp per query does the whole job
@@ -756,7 +988,7 @@ __global__ void __launch_bounds__(kLoopThreads, 1) icp_loop_kernel(const __grid_
       for (int s = 0; s < L.n_slices; ++s) {
         if (!L.is_points[s]) continue;
         const SliceArgs& a = L.sl[s];
-        if (a.nm <= 0 || a.projective || s_ctrl[4 + s] || __ldcg(a.work_count) < kBigList) continue;
+        if (a.nm <= 0 || a.projective || s_ctrl[4 + s] || __ldcg(a.work_count) < L.big_list) continue;
         any = true;
         loop_load_lin_const(a, L.st, s, ctl);
         const int n_far = __ldcg(a.far_count);
@@ -778,7 +1010,7 @@ __global__ void __launch_bounds__(kLoopThreads, 1) icp_loop_kernel(const __grid_
         __syncthreads();
       } else {
         const int n_work = __ldcg(a.work_count);
-        if (n_work < kBigList) continue;
+        if (n_work < L.big_list) continue;
         loop_load_lin_const(a, L.st, s, ctl);
         if (L.factor[s] == SRRG2B_FACTOR_P2P) loop_lin_list<DIM, SRRG2B_FACTOR_P2P>(a, ctl, n_work, a.work_list);
         else loop_lin_list<DIM, SRRG2B_FACTOR_PLANE>(a, ctl, n_work, a.work_list);
@@ -794,6 +1026,7 @@ __global__ void __launch_bounds__(kLoopThreads, 1) icp_loop_kernel(const __grid_
     }
     if (sync.wait_release(L, bcast) < 0) break;
   }
+  if (s0 >= 0) loop_prefetch_drain(L.sl[s0], ctl);  // nothing may be in flight when the CTA exits
 }
 
 }  // namespace s2b
