@@ -183,7 +183,7 @@ struct srrg2b_ctx {
   bool eager_index = true;  // env SRRG2B_EAGER_INDEX=0: build the NN index on first use only
   int big_list = kBigList;  // env SRRG2B_BIG_LIST
   int pre_iters = 3;       // env SRRG2B_PRE_ITERS: iterations run by the dedicated search kernels before the persistent loop takes over
-  bool use_loop = true;    // env SRRG2B_LOOP=0: no persistent loop kernel (every iteration is a kernel sequence)
+  bool use_loop = false;    // env SRRG2B_LOOP=0: no persistent loop kernel (every iteration is a kernel sequence)
   s2b::GridBar* d_bar = nullptr;
   long long* d_part = nullptr;  // per-CTA partial sums of the loop kernel
   unsigned long long* d_loop_dbg = nullptr;  // SRRG2B_LOOP_DEBUG=1: phase time stamps of the loop kernel
@@ -766,13 +766,38 @@ int launch_linearize(srrg2b_ctx* c, const SliceArgs& a_in, int factor, const int
   return SRRG2B_OK;
 }
 
-// one pass over a slice by the dedicated kernels: search everything, then linearise everything (the first
-// iterations of a run, before bounds are certified; whole runs when the persistent loop is disabled)
-int launch_slice_iteration(srrg2b_ctx* c, const SliceArgs& a, int factor, const int* skip) {
-  if (a.nm <= 0) return SRRG2B_OK;
-  int rcode = launch_find(c, a, skip);
-  if (rcode) return rcode;
-  return launch_linearize(c, a, factor, skip);
+template <typename K3P, typename K3L, typename K2P, typename K2L>
+void launch_tiles_kernel(srrg2b_ctx* c, const SliceArgs& a, int factor, K3P k3p, K3L k3l, K2P k2p, K2L k2l) {
+  const int blocks = lin_grid(c, a.nm);
+  if (c->dim == 3) {
+    if (factor == SRRG2B_FACTOR_P2P) k3p<<<blocks, kLoopThreads, kLoopSmemBytes, c->stream>>>(a);
+    else k3l<<<blocks, kLoopThreads, kLoopSmemBytes, c->stream>>>(a);
+  } else {
+    if (factor == SRRG2B_FACTOR_P2P) k2p<<<blocks, kLoopThreads, kLoopSmemBytes, c->stream>>>(a);
+    else k2l<<<blocks, kLoopThreads, kLoopSmemBytes, c->stream>>>(a);
+  }
+  c->launches++;
+}
+
+// One pass over a slice inside the ICP loop (R/registration/aligners/aligner_slice_processor_impl.cpp:38-48):
+// coherence check fused with the linearisation when the slice holds certified bounds, then the searches of
+// whatever failed the check (everything, while no bounds exist) and the linearisation of what they found.
+int launch_slice_iteration(srrg2b_ctx* c, const SliceArgs& a0, int factor, const int* skip) {
+  if (a0.nm <= 0) return SRRG2B_OK;
+  if (a0.projective || skip) {  // no coherence machinery for the index-image finder / the groups in front of the loop kernel
+    int rcode = launch_find(c, a0, skip);
+    if (rcode) return rcode;
+    return launch_linearize(c, a0, factor, skip);
+  }
+  SliceArgs a = a0;
+  a.use_list = 1;  // (the work-list counters were zeroed by icp_init_kernel / the previous solve step)
+  launch_tiles_kernel(c, a, factor, check_tiles_kernel<3, SRRG2B_FACTOR_P2P>, check_tiles_kernel<3, SRRG2B_FACTOR_PLANE>,
+                      check_tiles_kernel<2, SRRG2B_FACTOR_P2P>, check_tiles_kernel<2, SRRG2B_FACTOR_PLANE>);
+  launch_nn(c, a, nullptr);
+  launch_far(c, a, factor, nullptr);  // phase 2 of long lists, or the whole job for short ones (any R)
+  launch_tiles_kernel(c, a, factor, lin_after_search_kernel<3, SRRG2B_FACTOR_P2P>, lin_after_search_kernel<3, SRRG2B_FACTOR_PLANE>,
+                      lin_after_search_kernel<2, SRRG2B_FACTOR_P2P>, lin_after_search_kernel<2, SRRG2B_FACTOR_PLANE>);
+  return SRRG2B_OK;
 }
 
 // ring-ordered (dy, dz) row offsets of the NN search neighbourhood -> __constant__ tables
@@ -1171,6 +1196,10 @@ int srrg2b_ctx_create(int dim, int device, srrg2b_ctx** out) {
   {
     const void* lin[] = {(const void*) lin_tiles_kernel<3, SRRG2B_FACTOR_P2P>, (const void*) lin_tiles_kernel<3, SRRG2B_FACTOR_PLANE>,
                          (const void*) lin_tiles_kernel<2, SRRG2B_FACTOR_P2P>, (const void*) lin_tiles_kernel<2, SRRG2B_FACTOR_PLANE>,
+                         (const void*) check_tiles_kernel<3, SRRG2B_FACTOR_P2P>, (const void*) check_tiles_kernel<3, SRRG2B_FACTOR_PLANE>,
+                         (const void*) check_tiles_kernel<2, SRRG2B_FACTOR_P2P>, (const void*) check_tiles_kernel<2, SRRG2B_FACTOR_PLANE>,
+                         (const void*) lin_after_search_kernel<3, SRRG2B_FACTOR_P2P>, (const void*) lin_after_search_kernel<3, SRRG2B_FACTOR_PLANE>,
+                         (const void*) lin_after_search_kernel<2, SRRG2B_FACTOR_P2P>, (const void*) lin_after_search_kernel<2, SRRG2B_FACTOR_PLANE>,
                          (const void*) icp_loop_kernel<3>, (const void*) icp_loop_kernel<2>};
     for (const void* f : lin)
       ok = ok && cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kLoopSmemBytes) == cudaSuccess;

@@ -149,12 +149,22 @@ __device__ __forceinline__ void tile_issue_gather(const SliceArgs& a, WarpStage&
       S.lb[2 * lane + 1] = 0.f;
       *reinterpret_cast<int2*>(&S.slot[2 * lane]) = sl;
     }
-    // no candidate: position 0 stands in (always initialised, finite data; the half is masked later)
-    const int pa = max(slot_candidate(sl.x), 0), pb = max(slot_candidate(sl.y), 0);
-    cp_async16(&S.f[lane], a.frec + 2 * (size_t) pa);
-    cp_async16(&S.nf[lane], a.frec + 2 * (size_t) pa + 1);
-    cp_async16(&S.f[32 + lane], a.frec + 2 * (size_t) pb);
-    cp_async16(&S.nf[32 + lane], a.frec + 2 * (size_t) pb + 1);
+    // no candidate: zeros stand in (finite data; the half is masked later).  Written by the lane itself -- a
+    // gather of some fixed stand-in record by every such lane of the grid would hammer one L2 sector.
+    const int pa = slot_candidate(sl.x), pb = slot_candidate(sl.y);
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (pa >= 0) {
+      cp_async16(&S.f[lane], a.frec + 2 * (size_t) pa);
+      cp_async16(&S.nf[lane], a.frec + 2 * (size_t) pa + 1);
+    } else {
+      S.f[lane] = z4; S.nf[lane] = z4;
+    }
+    if (pb >= 0) {
+      cp_async16(&S.f[32 + lane], a.frec + 2 * (size_t) pb);
+      cp_async16(&S.nf[32 + lane], a.frec + 2 * (size_t) pb + 1);
+    } else {
+      S.f[32 + lane] = z4; S.nf[32 + lane] = z4;
+    }
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
 }
@@ -538,16 +548,16 @@ __device__ __forceinline__ void proj_find_body(const SliceArgs& a, const float* 
 }
 
 // lineariser constants of slice s into the control block (S from the device state, coherently)
-__device__ __forceinline__ void loop_load_lin_const(const SliceArgs& a, const DevState* st, int s, TileCtl& ctl) {
+__device__ __forceinline__ void load_lin_const(const SliceArgs& a, const float* Sg, int inline_ok, TileCtl& ctl) {
   const int tid = threadIdx.x;
-  if (tid == 0) { ctl.nfail = 0; ctl.nrec = 0; ctl.inline_ok = ctl.nfail_prev[s] <= kFailCap ? 1 : 0; }
-  if (tid < 12) ctl.lk.S[tid] = __ldcg(&st->S[s].m[tid]);
+  if (tid == 0) { ctl.nfail = 0; ctl.nrec = 0; ctl.inline_ok = inline_ok; }
+  if (tid < 12) ctl.lk.S[tid] = __ldcg(Sg + tid);
   if (tid == 33 && a.S_lb) ctl.ep_cur = __ldcg(reinterpret_cast<const int*>(a.S_lb) + kSlbEpoch);
   if (tid >= 64 && tid < 64 + kEpochs && a.S_lb) {
     // displacement table of the slice's epochs at this pass's transform (epoch ep_cur = this pass)
     const int e = tid - 64, ep_cur = __ldcg(reinterpret_cast<const int*>(a.S_lb) + kSlbEpoch);
     float Sn[12];
-    for (int j = 0; j < 12; ++j) Sn[j] = __ldcg(&st->S[s].m[j]);
+    for (int j = 0; j < 12; ++j) Sn[j] = __ldcg(Sg + j);
     ctl.dtab[e] = e <= ep_cur ? epoch_displacement2(Sn, a.S_lb + kSlbEpS + 12 * e, a.radius, e == ep_cur) : make_float2(0.f, 3e38f);
   }
   if (tid == 32) {
@@ -558,6 +568,9 @@ __device__ __forceinline__ void loop_load_lin_const(const SliceArgs& a, const De
     k.normal_cos = a.normal_cos; k.eb2 = a.eb2; k.rob = a.rob; k.gate = a.gate;
   }
   __syncthreads();
+}
+__device__ __forceinline__ void loop_load_lin_const(const SliceArgs& a, const DevState* st, int s, TileCtl& ctl) {
+  load_lin_const(a, st->S[s].m, ctl.nfail_prev[s] <= kFailCap ? 1 : 0, ctl);
 }
 
 // The failures a warp recorded during its tiles: one query at a time, the whole warp searches (the lanes
@@ -776,23 +789,6 @@ __device__ __noinline__ void loop_lin_list(const SliceArgs& a, TileCtl& ctl, int
   lin_flush<DIM>(a.acc, false, A, ctl.fsm);
 }
 
-// thread-per-query search of a long work list (rings 0-1; the unsettled go to the far list)
-template <int DIM>
-__device__ __noinline__ void loop_search_list_phase1(const SliceArgs& a, TileCtl& ctl, int track2, int n_work) {
-  const float cell = __fdiv_rn(1.f, a.inv_cell);
-  const float ring2 = (a.R >= 2) ? (1.f - 4e-3f) * cell : __fsqrt_rn(a.rho_s2);
-  const float ring2_sq = (a.R >= 2) ? ring2 * ring2 : 3.0e38f;
-  if (track2) nn_phase1_body<DIM, true>(a, ctl.lk.S, cell, ring2, ring2_sq, false, n_work);
-  else nn_phase1_body<DIM, false>(a, ctl.lk.S, cell, ring2, ring2_sq, false, n_work);
-}
-
-template <int DIM>
-__device__ __noinline__ void loop_solve(const LoopArgs& L, SolveSmem& ssm, bool resident) {
-  icp_solve_block<DIM>(L.ap, L.st, L.px, ssm, L.part, (int) gridDim.x, resident);
-}
-
-__device__ __noinline__ void loop_proj_find(const SliceArgs& a, const float* S) { proj_find_body(a, S); }
-
 // Prefetch of the next iteration's check pass over slice `a`: none of it depends on the transform the solve step
 // is about to produce, so the CTA starts its pipeline while it waits at the barrier.
 //   part 1 (before the arrival): the bulk copies of every warp's first kStages tiles;
@@ -844,6 +840,83 @@ __device__ __forceinline__ void loop_prefetch_drain(const SliceArgs& a, TileCtl&
   if (threadIdx.x == 0) ctl.pref = 0;
   __syncthreads();
 }
+
+// ---------------------------------------------------------------------------------------------
+// the kernels of one _runSolver iteration when it runs as a launch sequence (the default):
+//   check_tiles_kernel   certified slice: coherence check + linearisation of every correspondence in one
+//                        streaming pass; the failures are searched in place (records) or listed
+//   nn_kernel / nn_far_kernel (s2b_icp.cuh)   the listed queries -- or everything while no bounds exist
+//   lin_after_search_kernel   linearises what those two searched (everything / a long work list; short lists
+//                        are linearised by nn_far_kernel itself)
+//   icp_solve_kernel     all-reduce, solve, update, statistics, termination, next transforms
+// Every kernel decides from the control words what it has to do; a launch with nothing to do costs the
+// latency of those loads.
+// ---------------------------------------------------------------------------------------------
+template <int DIM, int FACTOR>
+__global__ void __launch_bounds__(kLoopThreads, 1) check_tiles_kernel(const __grid_constant__ SliceArgs a) {
+  extern __shared__ __align__(128) unsigned char loop_smem_raw[];
+  TileStage* stages = reinterpret_cast<TileStage*>(loop_smem_raw);
+  __shared__ TileCtl ctl;
+  const int stop = __ldcg(a.stop), list_all = __ldcg(a.list_all), track2 = __ldcg(a.track2);
+  if (stop || list_all) return;
+  tile_ctl_init(ctl);
+  constexpr int KMAX = (DIM == 3) ? kRowTable : (2 * kMaxR + 1);
+  for (int k = threadIdx.x; k < KMAX; k += blockDim.x)
+    ctl.rows[k] = (DIM == 3) ? *reinterpret_cast<const int*>(c_rows3[k]) : *reinterpret_cast<const int*>(c_rows2[k]);
+  __syncthreads();
+  load_lin_const(a, a.S, 1, ctl);
+  long long mine0, mine1;
+  {
+    LinAcc<DIM> A;
+    A.clear();
+    const int terms = lin_tiles_body<DIM, FACTOR, true>(a, stages, ctl, A);
+    lin_warp_reduce<DIM>(terms <= 30, A, mine0, mine1);
+  }
+  __syncthreads();  // every warp is done with its tiles: the record list is complete
+  if ((int) (threadIdx.x >> 5) < ctl.nrec) loop_search_recs<DIM, FACTOR>(a, ctl, track2, ctl.nrec, ctl.rec);
+  lin_cta_reduce(a.acc, mine0, mine1, ctl.fsm);
+  if (threadIdx.x < kAcc && ctl.tail[threadIdx.x]) atomicAdd(&a.acc[threadIdx.x], (unsigned long long) ctl.tail[threadIdx.x]);
+}
+
+template <int DIM, int FACTOR>
+__global__ void __launch_bounds__(kLoopThreads, 1) lin_after_search_kernel(const __grid_constant__ SliceArgs a) {
+  const int stop = *a.stop, list_all = *a.list_all, work_count = *a.work_count;
+  if (stop) return;
+  const bool all = !a.use_list || list_all;
+  if (!all && (work_count == 0 || small_work_list(a, false, work_count))) return;
+  extern __shared__ __align__(128) unsigned char loop_smem_raw[];
+  TileStage* stages = reinterpret_cast<TileStage*>(loop_smem_raw);
+  __shared__ TileCtl ctl;
+  tile_ctl_init(ctl);
+  if (threadIdx.x == 32) make_lin_const(a, a.S, ctl.lk);
+  __syncthreads();
+  if (all) {
+    LinAcc<DIM> A;
+    A.clear();
+    const int terms = lin_tiles_body<DIM, FACTOR, false>(a, stages, ctl, A);
+    lin_flush<DIM>(a.acc, terms <= 30, A, ctl.fsm);
+    if (threadIdx.x < kAcc && ctl.tail[threadIdx.x]) atomicAdd(&a.acc[threadIdx.x], (unsigned long long) ctl.tail[threadIdx.x]);
+  } else {
+    loop_lin_list<DIM, FACTOR>(a, ctl, work_count, a.work_list);
+  }
+}
+
+// thread-per-query search of a long work list (rings 0-1; the unsettled go to the far list)
+template <int DIM>
+__device__ __noinline__ void loop_search_list_phase1(const SliceArgs& a, TileCtl& ctl, int track2, int n_work) {
+  const float cell = __fdiv_rn(1.f, a.inv_cell);
+  const float ring2 = (a.R >= 2) ? (1.f - 4e-3f) * cell : __fsqrt_rn(a.rho_s2);
+  const float ring2_sq = (a.R >= 2) ? ring2 * ring2 : 3.0e38f;
+  if (track2) nn_phase1_body<DIM, true>(a, ctl.lk.S, cell, ring2, ring2_sq, false, n_work);
+  else nn_phase1_body<DIM, false>(a, ctl.lk.S, cell, ring2, ring2_sq, false, n_work);
+}
+
+template <int DIM>
+__device__ __noinline__ void loop_solve(const LoopArgs& L, SolveSmem& ssm, bool resident) {
+  icp_solve_block<DIM>(L.ap, L.st, L.px, ssm, L.part, (int) gridDim.x, resident);
+}
+
+__device__ __noinline__ void loop_proj_find(const SliceArgs& a, const float* S) { proj_find_body(a, S); }
 
 // The hot pass (coherence check + linearisation of a certified slice).  SLOT >= 0: the slice arguments are
 // the compile-time entry L.sl[SLOT] of the kernel parameters, i.e. constant-bank operands that occupy no
