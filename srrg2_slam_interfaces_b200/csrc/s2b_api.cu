@@ -2,7 +2,7 @@
 // sequencing of the device-driven ICP loop, NCCL plumbing, and the extern "C" boundary declared in
 // include/srrg2b.h.  No CPU fallback: without a CUDA device every compute call returns
 // SRRG2B_ERR_CUDA.
-#include "s2b_loop.cuh"
+#include "s2b_tiles.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
@@ -181,13 +181,7 @@ struct srrg2b_ctx {
   bool use_graphs = true;  // env SRRG2B_NO_GRAPH=1 disables
   bool graph_nccl = false;  // env SRRG2B_GRAPH_NCCL=1: capture the all-reduce too (experimental: failed the 2-GPU parity test)
   bool eager_index = true;  // env SRRG2B_EAGER_INDEX=0: build the NN index on first use only
-  int big_list = kBigList;  // env SRRG2B_BIG_LIST
-  int pre_iters = 3;       // env SRRG2B_PRE_ITERS: iterations run by the dedicated search kernels before the persistent loop takes over
-  bool use_loop = false;    // env SRRG2B_LOOP=0: no persistent loop kernel (every iteration is a kernel sequence)
-  s2b::GridBar* d_bar = nullptr;
-  long long* d_part = nullptr;  // per-CTA partial sums of the loop kernel
-  unsigned long long* d_loop_dbg = nullptr;  // SRRG2B_LOOP_DEBUG=1: phase time stamps of the loop kernel
-  long long timeout_cycles = 4000000000ll;  // ~2 s of SM clock: grid barrier / peer exchange give up (env SRRG2B_TIMEOUT_MS)
+  long long timeout_cycles = 4000000000ll;  // ~2 s of SM clock: the peer exchange gives up (env SRRG2B_TIMEOUT_MS)
   s2b::Mat4f* d_T0 = nullptr;  // initial guess of the current run (read by icp_init_kernel)
   s2b::Mat4f* h_T0 = nullptr;  // pinned staging
   s2b::SolveArgs* d_solve = nullptr;  // solve-step arguments of the current run
@@ -947,54 +941,10 @@ int enqueue_iteration_group(srrg2b_ctx* c, const Plan& plan, const int* skip) {
   return SRRG2B_OK;
 }
 
-// the persistent loop kernel: all remaining iterations in one cooperative launch
-int launch_loop(srrg2b_ctx* c, const Plan& plan) {
-  LoopArgs L;
-  memset(&L, 0, sizeof(L));
-  L.ap = c->d_solve; L.st = c->d_state; L.px = c->d_px; L.bar = c->d_bar;
-  L.timeout_cycles = c->timeout_cycles;
-  L.big_list = c->big_list;
-  L.dbg = c->d_loop_dbg;
-  L.part = c->d_part;
-  L.n_slices = plan.solve.n_slices;
-  const int grid = c->sm_count;
-  for (int s = 0; s < plan.solve.n_slices; ++s) {
-    L.factor[s] = plan.factor[s];
-    L.is_points[s] = plan.is_points[s] ? 1 : 0;
-    L.sl[s] = plan.sargs[s];
-  }
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3((unsigned) grid);
-  cfg.blockDim = dim3(kLoopThreads);
-  cfg.dynamicSmemBytes = kLoopSmemBytes;
-  cfg.stream = c->stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeCooperative;
-  attr[0].val.cooperative = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  if (c->dim == 3) CK(c, cudaLaunchKernelEx(&cfg, icp_loop_kernel<3>, L));
-  else CK(c, cudaLaunchKernelEx(&cfg, icp_loop_kernel<2>, L));
-  c->launches++;
-  return SRRG2B_OK;
-}
-
-// enqueue `iterations` _runSolver iterations; no host sync inside.  The first pre_iters iterations run as
-// kernel sequences with the dedicated (high-occupancy) search kernels -- each group after the first is a
-// no-op once every NN slice holds certified bounds --, the persistent loop kernel runs the rest.
+// enqueue `iterations` _runSolver iterations; no host sync inside
 int enqueue_iterations(srrg2b_ctx* c, const Plan& plan, int iterations) {
-  // (several ranks without the peer exchange: NCCL all-reduce between kernels, no loop kernel)
-  const bool loop = c->use_loop && !c->time_kernels && (c->world <= 1 || c->d_px);
-  const int groups = loop ? std::min(iterations, std::max(0, c->pre_iters)) : iterations;
-  // (the groups may only stand down when the loop kernel follows them)
-  const int* skip = (loop && iterations > groups) ? &c->d_state->certified : nullptr;
-  for (int it = 0; it < groups; ++it) {
-    const int rcode = enqueue_iteration_group(c, plan, skip);
-    if (rcode) return rcode;
-  }
-  if (loop && iterations > groups) {
-    const int rcode = launch_loop(c, plan);
+  for (int it = 0; it < iterations; ++it) {
+    const int rcode = enqueue_iteration_group(c, plan, nullptr);
     if (rcode) return rcode;
   }
   CK(c, cudaGetLastError());
@@ -1014,11 +964,11 @@ int run_plan(srrg2b_ctx* c, const Plan& plan, const Mat4f& T0, int iterations, i
   const bool graph = c->use_graphs && !c->time_kernels && (c->world <= 1 || c->graph_nccl || c->d_px);
   if (!graph) {
     icp_init_kernel<<<1, 32, 0, c->stream>>>(c->d_solve, c->d_state, c->d_T0, apply_prior_guess, reset_tc, keep_stats,
-                                             iterations, c->d_bar);
+                                             iterations);
     c->launches++;
     return enqueue_iterations(c, plan, iterations);
   }
-  const int tail[6] = {iterations, apply_prior_guess, reset_tc, keep_stats, c->pre_iters, c->use_loop ? 1 : 0};
+  const int tail[6] = {iterations, apply_prior_guess, reset_tc, keep_stats, 0, 0};
   // key = everything the launch sequence depends on (slice kernel arguments, factor kinds, counts);
   // the solve-step values are read from device memory and may change freely between replays
   const size_t nb = sizeof(plan.sargs) + sizeof(plan.factor) + sizeof(plan.is_points);
@@ -1040,7 +990,7 @@ int run_plan(srrg2b_ctx* c, const Plan& plan, const Mat4f& T0, int iterations, i
     cudaGraph_t g = nullptr;
     CK(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
     icp_init_kernel<<<1, 32, 0, c->stream>>>(c->d_solve, c->d_state, c->d_T0, apply_prior_guess, reset_tc, keep_stats,
-                                             iterations, c->d_bar);
+                                             iterations);
     c->launches++;
     const int rcode = enqueue_iterations(c, plan, iterations);
     const cudaError_t e = cudaStreamEndCapture(c->stream, &g);
@@ -1171,9 +1121,6 @@ int srrg2b_ctx_create(int dim, int device, srrg2b_ctx** out) {
   ok = ok && cudaMalloc((void**) &c->d_solve, sizeof(SolveArgs)) == cudaSuccess;
   ok = ok && cudaMallocHost((void**) &c->h_solve, sizeof(SolveArgs)) == cudaSuccess;
   if (const char* env = getenv("SRRG2B_NO_GRAPH")) c->use_graphs = atoi(env) == 0;
-  if (const char* env = getenv("SRRG2B_PRE_ITERS")) c->pre_iters = std::max(0, atoi(env));
-  if (const char* env = getenv("SRRG2B_LOOP")) c->use_loop = atoi(env) != 0;
-  if (const char* env = getenv("SRRG2B_BIG_LIST")) c->big_list = std::max(1, atoi(env));
   {
     int khz = 1965000;
     cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
@@ -1181,16 +1128,6 @@ int srrg2b_ctx_create(int dim, int device, srrg2b_ctx** out) {
     if (const char* env = getenv("SRRG2B_TIMEOUT_MS")) ms = std::max(1.0, atof(env));
     c->timeout_cycles = (long long) (ms * (double) khz);
   }
-  if (getenv("SRRG2B_LOOP_DEBUG")) {
-    const size_t nb = sizeof(unsigned long long) * (kDbgIters * 2 * kDbgWords + kDbgCtas * 4);
-    ok = ok && cudaMalloc((void**) &c->d_loop_dbg, nb) == cudaSuccess && cudaMemset(c->d_loop_dbg, 0, nb) == cudaSuccess;
-  }
-  ok = ok && cudaMalloc((void**) &c->d_bar, sizeof(GridBar)) == cudaSuccess;
-  {
-    const size_t nb = sizeof(long long) * (size_t) c->sm_count * SRRG2B_MAX_SLICES * kAcc;
-    ok = ok && cudaMalloc((void**) &c->d_part, nb) == cudaSuccess && cudaMemsetAsync(c->d_part, 0, nb, c->stream) == cudaSuccess;
-  }
-  ok = ok && cudaMemsetAsync(c->d_bar, 0, sizeof(GridBar), c->stream) == cudaSuccess;
   if (const char* env = getenv("SRRG2B_EAGER_INDEX")) c->eager_index = atoi(env) != 0;
   if (const char* env = getenv("SRRG2B_GRAPH_NCCL")) c->graph_nccl = atoi(env) != 0;
   {
@@ -1199,15 +1136,12 @@ int srrg2b_ctx_create(int dim, int device, srrg2b_ctx** out) {
                          (const void*) check_tiles_kernel<3, SRRG2B_FACTOR_P2P>, (const void*) check_tiles_kernel<3, SRRG2B_FACTOR_PLANE>,
                          (const void*) check_tiles_kernel<2, SRRG2B_FACTOR_P2P>, (const void*) check_tiles_kernel<2, SRRG2B_FACTOR_PLANE>,
                          (const void*) lin_after_search_kernel<3, SRRG2B_FACTOR_P2P>, (const void*) lin_after_search_kernel<3, SRRG2B_FACTOR_PLANE>,
-                         (const void*) lin_after_search_kernel<2, SRRG2B_FACTOR_P2P>, (const void*) lin_after_search_kernel<2, SRRG2B_FACTOR_PLANE>,
-                         (const void*) icp_loop_kernel<3>, (const void*) icp_loop_kernel<2>};
+                         (const void*) lin_after_search_kernel<2, SRRG2B_FACTOR_P2P>, (const void*) lin_after_search_kernel<2, SRRG2B_FACTOR_PLANE>};
     for (const void* f : lin)
       ok = ok && cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kLoopSmemBytes) == cudaSuccess;
+    // (static + dynamic shared memory of the tile kernels must fit one CTA per SM: fail loudly here, not at launch)
     int per_sm = 0;
-    ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, icp_loop_kernel<3>, kLoopThreads, kLoopSmemBytes) == cudaSuccess;
-    int coop = 0;
-    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
-    if (per_sm < 1 || !coop) c->use_loop = false;  // (the kernel-sequence path still works)
+    ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, check_tiles_kernel<3, SRRG2B_FACTOR_PLANE>, kLoopThreads, kLoopSmemBytes) == cudaSuccess && per_sm >= 1;
   }
   ok = ok && cudaMemsetAsync(c->d_state, 0, sizeof(DevState), c->stream) == cudaSuccess;
   ok = ok && cudaStreamSynchronize(c->stream) == cudaSuccess;
@@ -1228,38 +1162,7 @@ int srrg2b_ctx_destroy(srrg2b_ctx* c) {
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
-  if (c->d_bar) cudaFree(c->d_bar);
-  if (c->d_part) cudaFree(c->d_part);
-  if (c->d_loop_dbg) {
-    std::vector<unsigned long long> t((size_t) kDbgIters * 2 * kDbgWords + kDbgCtas * 4);
-    if (cudaMemcpy(t.data(), c->d_loop_dbg, t.size() * 8, cudaMemcpyDeviceToHost) == cudaSuccess) {
-      fprintf(stderr, "[srrg2b loop debug] last run, per loop iteration: CTA0 | last CTA : tiles tail arrive [all-arrived solved] released (us from iteration start), fails\n");
-      for (int it = 0; it < kDbgIters; ++it) {
-        const unsigned long long* a = &t[((size_t) it * 2) * kDbgWords];
-        const unsigned long long* b = a + kDbgWords;
-        if (!a[0] || !a[6]) continue;
-        auto us = [](unsigned long long x, unsigned long long x0) { return x ? (double) (long long) (x - x0) * 1e-3 : -1.0; };
-        fprintf(stderr, "  it %2d | %6.1f %6.1f %6.1f [%6.1f %6.1f] %6.1f  f=%llu work=%llu | %6.1f %6.1f %6.1f %6.1f  f=%llu | next it +%.1f\n", it, us(a[1], a[0]),
-                us(a[2], a[0]), us(a[3], a[0]), us(a[4], a[0]), us(a[5], a[0]), us(a[6], a[0]), a[7] & 0xffffffffull, a[7] >> 32, us(b[1], b[0]), us(b[2], b[0]),
-                us(b[3], b[0]), us(b[6], b[0]), b[7] & 0xffffffffull, it + 1 < kDbgIters ? us(a[kDbgWords * 2], a[0]) : -1.0);
-      }
-    }
-    {  // per-CTA view of loop iteration kDbgCtaIter: when the CTA's pass ended and when it arrived at the barrier
-      const unsigned long long* q = &t[(size_t) kDbgIters * 2 * kDbgWords];
-      const unsigned long long t0 = t[((size_t) kDbgCtaIter * 2) * kDbgWords];
-      if (t0) {
-        std::vector<std::pair<double, int>> order;
-        for (int b = 0; b < kDbgCtas; ++b) if (q[4 * b + 1]) order.push_back({(double) (long long) (q[4 * b + 1] - t0) * 1e-3, b});
-        std::sort(order.begin(), order.end());
-        fprintf(stderr, "[srrg2b loop debug] iteration %d, CTAs by barrier arrival (us from CTA 0's iteration start): cta: pass-end arrive fails\n", kDbgCtaIter);
-        for (size_t k = 0; k < order.size(); ++k) {
-          if (k >= 4 && k + 12 < order.size()) continue;
-          const int b = order[k].second;
-          fprintf(stderr, "   cta %3d: %6.1f %6.1f  f=%llu\n", b, (double) (long long) (q[4 * b] - t0) * 1e-3, order[k].first, q[4 * b + 2]);
-        }
-      }
-    }
-    cudaFree(c->d_loop_dbg);
+  {
 #ifdef S2B_FAIL_STATS
     {
       unsigned long long fs[8];

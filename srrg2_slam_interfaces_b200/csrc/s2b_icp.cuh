@@ -1013,7 +1013,7 @@ __device__ __forceinline__ void lin_one_slot(const SliceArgs& a, const LinConst&
 // per-thread sums are known to stay below 2^26, else two over 16-bit halves, which cannot overflow the
 // 32-bit warp sum), the warp's 40 sums parked in lanes, one plain shared store per lane, then 40
 // threads add the warps' rows and issue one global atomic per slot and CTA.
-constexpr int kMaxWarps = 12;  // CTAs of the accumulating kernels have at most 384 threads (s2b_loop.cuh: kLoopThreads)
+constexpr int kMaxWarps = 12;  // CTAs of the accumulating kernels have at most 384 threads (s2b_tiles.cuh: kLoopThreads)
 struct FlushSmem {
   long long w[kMaxWarps][kAcc];
 };
@@ -1226,17 +1226,11 @@ __device__ __forceinline__ void load_solve_args(const SolveArgs* ap, SolveArgs* 
   __syncthreads();
 }
 
-// grid barrier of the persistent loop kernel (s2b_loop.cuh): arrival counter, release generation, mode word
-struct GridBar {
-  unsigned int count, gen, mode, abort;
-};
-
 __global__ void icp_init_kernel(const SolveArgs* ap, DevState* st, const Mat4f* T0, int apply_prior_guess, int reset_tc,
-                                int keep_stats, int iterations, GridBar* bar) {
+                                int keep_stats, int iterations) {
   __shared__ SolveArgs a;
   load_solve_args(ap, &a);
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  if (bar) { bar->count = 0; bar->gen = 0; bar->mode = 0; bar->abort = 0; }
   if (!keep_stats) {
     Mat4f X = *T0;
     if (apply_prior_guess) {
@@ -1525,38 +1519,26 @@ __device__ __forceinline__ unsigned long long ld_volatile_sys(const unsigned lon
   return v;
 }
 
-constexpr int kPartSlots = 384;  // (group, word) partial sums of the per-CTA rows: one per thread of the loop kernel's CTA
 // shared-memory staging of the solve step
 struct SolveSmem {
   alignas(16) SolveArgs a;
   alignas(16) DevHeader sh;
   PeerExchange pe;
   int timed_out;
-  long long part[kPartSlots];
 };
 
 // The solve step of one iteration, executed by ONE CTA with at least kSolveThreads threads (the first
 // kSolveThreads take part): stage arguments + state, all-reduce over the peers, serial solve, write back.
 // Returns (to every participating thread) whether the iteration loop has to stop.
-// part / n_part: per-CTA partial sums [n_part][SRRG2B_MAX_SLICES * kAcc] published by the persistent loop's
-// CTAs (added to the global accumulators here, in a fixed order -- integers, so any order gives the same bits)
-// resident: sm still holds the arguments and the state this CTA wrote back at the end of its previous solve step
-// (nothing else modifies them inside the persistent loop): only the accumulators are fetched.
 template <int DIM>
-__device__ __forceinline__ bool icp_solve_block(const SolveArgs* ap, DevState* st, const PeerExchange* px, SolveSmem& sm,
-                                                const long long* part_rows = nullptr, int n_part = 0, bool resident = false) {
+__device__ __forceinline__ bool icp_solve_block(const SolveArgs* ap, DevState* st, const PeerExchange* px, SolveSmem& sm) {
   const int tid = threadIdx.x;
   const bool part = tid < kSolveThreads;
   if (tid == 0) solve_stamp(0);
   SolveArgs& a = sm.a;
   DevHeader& sh = sm.sh;
   PeerExchange& pe = sm.pe;
-  if (resident) {
-    // (the accumulators the cold paths may have added to with atomics; the CTAs' sums come from part_rows)
-    const int n_words = a.n_slices * kAcc;
-    for (int k = tid; k < n_words; k += blockDim.x) (&sh.acc[0][0])[k] = __ldcg(&st->acc[0][0] + k);
-    if (tid == 0) { sh.error = __ldcg(&st->error); sm.timed_out = 0; }
-  } else if (part) {
+  if (part) {
     // one round of independent 16-byte loads stages the arguments and the whole mutable state
     const int4* s0 = reinterpret_cast<const int4*>(ap);
     int4* d0 = reinterpret_cast<int4*>(&a);
@@ -1573,39 +1555,6 @@ __device__ __forceinline__ bool icp_solve_block(const SolveArgs* ap, DevState* s
   }
   __syncthreads();
   if (sh.stop) return true;  // (every rank holds the same state, so every rank returns here or none does)
-  if (part_rows) {
-    // the threads are dealt out word-major: group g = tid / n_words sums the rows g, g + G, ... of word tid % n_words,
-    // all of a thread's loads in flight together (one or two L2 round trips for the whole reduction)
-    const int n_words = a.n_slices * kAcc;
-    const int n_groups = max(min((int) blockDim.x, kPartSlots) / n_words, 1);
-    if (tid < n_groups * n_words) {
-      const int g = tid / n_words, k = tid - g * n_words;
-      long long v = 0;
-      int r = g;
-      for (; r + 15 * n_groups < n_part; r += 16 * n_groups) {
-        long long t[16];
-#pragma unroll
-        for (int u = 0; u < 16; ++u) t[u] = __ldcg(part_rows + (size_t) (r + u * n_groups) * (SRRG2B_MAX_SLICES * kAcc) + k);
-#pragma unroll
-        for (int u = 0; u < 16; ++u) v += t[u];
-      }
-      {
-        long long t[16];
-#pragma unroll
-        for (int u = 0; u < 16; ++u) { const int rr = r + u * n_groups; t[u] = rr < n_part ? __ldcg(part_rows + (size_t) rr * (SRRG2B_MAX_SLICES * kAcc) + k) : 0ll; }
-#pragma unroll
-        for (int u = 0; u < 16; ++u) v += t[u];
-      }
-      sm.part[g * n_words + k] = v;
-    }
-    __syncthreads();
-    for (int k = tid; k < n_words; k += blockDim.x) {
-      long long v = 0;
-      for (int g = 0; g < n_groups; ++g) v += sm.part[g * n_words + k];
-      (&sh.acc[0][0])[k] += (unsigned long long) v;
-    }
-    __syncthreads();
-  }
   if (px) {
     // all-reduce of the accumulators over peer memory (see PeerExchange)
     const unsigned long long e = sh.epoch + 1ull;

@@ -1,19 +1,22 @@
-// s2b_loop.cuh -- the streaming lineariser and the persistent device loop of the aligner.
+// s2b_tiles.cuh -- the streaming lineariser of the aligner and the kernels of one _runSolver iteration built on it.
 //
 //   lin_tiles_body    tile-pipelined pass over a slice's correspondences: the contiguous arrays of the
-//                     moving cloud (points, normals, slots, bounds) travel as TMA bulk copies
-//                     (cp.async.bulk + mbarrier, UBLKCP) into a 3-stage shared-memory ring, the gathered
-//                     fixed points / normals as 16-byte cp.async copies issued one tile ahead; every
-//                     thread linearises TWO correspondences at a time with the packed fp32x2 pipeline
-//                     (s2b_lin.cuh).  CHECK fuses the exact temporal-coherence test: failures are searched
-//                     and linearised in place by the CTA's warps (nn_far_body), overflow goes to a global
-//                     work list.
-//   lin_tiles_kernel  stand-alone launch of that body (iterations that search with the dedicated NN
-//                     kernels, srrg2b_linearize).
-//   icp_loop_kernel   ONE cooperative kernel runs all remaining _runSolver iterations
-//                     (R/registration/aligners/multi_aligner_impl.cpp:97-128): per iteration the slices'
-//                     passes, one grid barrier, the solve step on CTA 0 (all-reduce over the peers included),
-//                     release.  No kernel boundary, no host round trip between iterations.
+//                     moving cloud (pair records, slots, bounds) travel as TMA bulk copies (cp.async.bulk +
+//                     mbarrier, UBLKCP) into a 4-stage shared-memory ring PER WARP, the gathered fixed
+//                     points / normals as 16-byte cp.async copies issued one tile ahead; every thread
+//                     linearises TWO correspondences at a time with the packed fp32x2 pipeline (s2b_lin.cuh).
+//                     CHECK fuses the exact temporal-coherence test: the first failures of a CTA are kept as
+//                     64-byte records and searched + linearised by its warps after the tiles, the rest go to a
+//                     global work list.
+//   check_tiles_kernel        certified slice: coherence check + linearisation of every correspondence
+//   lin_after_search_kernel   linearises what the NN kernels searched (everything / a long work list)
+//   lin_tiles_kernel          linearises every slot as it is (srrg2b_linearize, projective slices)
+// One iteration (R/registration/aligners/multi_aligner_impl.cpp:97-128) is the launch sequence
+// check_tiles -> nn_kernel -> nn_far_kernel -> lin_after_search -> icp_solve_kernel; every kernel decides from
+// the device-side control words what it has to do.  (A persistent cooperative kernel that ran all iterations
+// behind a grid barrier was measured slower -- 1.51 ms against 1.34 ms per 20-iteration C2 run: grid barrier,
+// in-kernel solve and release cost 28 us per iteration against ~10 us of launch boundaries -- and was removed;
+// see DESIGN.md section 5.)
 #pragma once
 #include "s2b_icp.cuh"
 
@@ -36,7 +39,6 @@ constexpr int kWTile = kSubTile * kPPL;    // correspondences per warp tile
 constexpr int kStages = S2B_LOOP_STAGES;
 constexpr int kFailCap = 48;               // coherence-check failures a CTA resolves in place per pass (one warp per
                                            // query); the rest go to the global work list
-constexpr int kBigList = 1024;             // global work lists from this size on are searched thread-per-query
 
 // One sub-tile (one pair per lane) of one ring stage of ONE warp (4 KB).  Every warp runs its own pipeline
 // over its own tiles, so the steady state has no CTA-wide barrier and the warps drift apart freely.
@@ -68,16 +70,13 @@ struct TileCtl {
   FlushSmem fsm;
   unsigned long long full[kLoopWarps][kStages];  // mbarriers: the bulk copies of a warp's stage have landed
   int nfail;                        // coherence-check failures of the CTA in the running pass
-  int nfail_prev[SRRG2B_MAX_SLICES];  // ... in the slice's previous check pass (decides who searches them)
   FailRec rec[kFailCap];            // the failures the CTA resolves itself after its tiles (one warp per query)
   int nrec;                         // ... how many
   int ep_cur;                       // id of the epoch this pass certifies bounds for
-  int pref;                         // prefetch state of the next check pass (see loop_prefetch)
   int inline_ok;                    // this pass: the warps resolve their (few) failures themselves
   int rows[kRowTable];
   unsigned phase_bits[kLoopWarps];  // parity of the next wait per stage, per warp (survives between passes)
   long long tail[kAcc];  // sums of the correspondences resolved by the CTA's search warps (lin_push_tail)
-  long long cta_acc[SRRG2B_MAX_SLICES][kAcc];  // this CTA's sums of the current iteration (persistent loop)
   float2 dtab[kEpochs];  // displacement table of the slice's epochs (see encode_bound), refreshed per pass: a query
                          // m has moved at most dtab[e].x |m| + dtab[e].y since epoch e
 };
@@ -202,19 +201,15 @@ __device__ __forceinline__ int lin_tiles_body(const SliceArgs& a, TileStage* sta
   const bool regate = a.gate != 0;  // gated-out slots are re-checked every iteration
   if (my_tiles == 0) return 0;
   unsigned long long* bars = ctl.full[warp];
-  // prologue: bulk copies of the warp's first kStages tiles, gathers of the first -- unless the CTA prefetched
-  // them while it waited at the previous barrier (pref: 1 = bulk copies issued, 3 = the first gathers too)
-  const int pref = CHECK ? ctl.pref : 0;
-  if (!(pref & 1) && lane == 0) {
+  // prologue: bulk copies of the warp's first kStages tiles, gathers of the first
+  if (lane == 0) {
     asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy writes (slots, bounds) before the bulk reads
     for (int j = 0; j < kStages && j < my_tiles; ++j) tile_issue_bulk<CHECK>(a, stages[j].w[warp], &bars[j], g0 + j * W);
   }
   unsigned phase = ctl.phase_bits[warp];
-  if (!(pref & 2)) {
-    mbar_wait(&bars[0], phase & 1u);
-    phase ^= 1u;
-    tile_issue_gather(a, stages[0].w[warp], g0 * kWTile, lane);
-  }
+  mbar_wait(&bars[0], phase & 1u);
+  phase ^= 1u;
+  tile_issue_gather(a, stages[0].w[warp], g0 * kWTile, lane);
   for (int j = 0; j < my_tiles; ++j) {
     const int st = j % kStages;
     WarpStage& WS = stages[st].w[warp];
@@ -395,10 +390,8 @@ __device__ __forceinline__ void tile_ctl_init(TileCtl& ctl) {
     ctl.phase_bits[threadIdx.x] = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (threadIdx.x == 0) { ctl.nfail = 0; ctl.nrec = 0; ctl.inline_ok = 0; ctl.ep_cur = 0; ctl.pref = 0; }
-  if (threadIdx.x < SRRG2B_MAX_SLICES) ctl.nfail_prev[threadIdx.x] = INT_MAX;
+  if (threadIdx.x == 0) { ctl.nfail = 0; ctl.nrec = 0; ctl.inline_ok = 0; ctl.ep_cur = 0; }
   if (threadIdx.x < kAcc) ctl.tail[threadIdx.x] = 0;
-  for (int k = threadIdx.x; k < SRRG2B_MAX_SLICES * kAcc; k += blockDim.x) (&ctl.cta_acc[0][0])[k] = 0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -420,131 +413,6 @@ __global__ void __launch_bounds__(kLoopThreads, 1) lin_tiles_kernel(const SliceA
   lin_flush<DIM>(a.acc, terms <= 30, A, ctl.fsm);
   // (sums a warp parked in the shared tail accumulators on the way: huge slices only)
   if (threadIdx.x < kAcc && ctl.tail[threadIdx.x]) atomicAdd(&a.acc[threadIdx.x], (unsigned long long) ctl.tail[threadIdx.x]);
-}
-
-// ---------------------------------------------------------------------------------------------
-// the persistent device loop
-// ---------------------------------------------------------------------------------------------
-struct LoopArgs {
-  const SolveArgs* ap;
-  DevState* st;
-  const PeerExchange* px;
-  GridBar* bar;
-  long long timeout_cycles;
-  int big_list;             // global work lists from this size on are searched thread-per-query (else warp-per-query)
-  int n_slices;
-  int factor[SRRG2B_MAX_SLICES];
-  int is_points[SRRG2B_MAX_SLICES];
-  long long* part;          // [gridDim][SRRG2B_MAX_SLICES * kAcc] per-CTA sums of the iteration (no atomics on the hot path)
-  unsigned long long* dbg;  // SRRG2B_LOOP_DEBUG=1: [iteration][cta in {0, last}][8] phase time stamps (ns) + fail counts
-  SliceArgs sl[SRRG2B_MAX_SLICES];
-};
-
-__device__ __forceinline__ unsigned long long globaltimer_ns() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-  return t;
-}
-constexpr int kDbgIters = 64, kDbgWords = 8, kDbgCtas = 160, kDbgCtaIter = 10;
-// time stamp `k` of the current iteration (only CTA 0 and the last CTA record, thread 0)
-__device__ __forceinline__ void loop_dbg(const LoopArgs& L, int it, int k, unsigned long long v) {
-  if (!L.dbg || threadIdx.x != 0 || it >= kDbgIters) return;
-  const int who = blockIdx.x == 0 ? 0 : (blockIdx.x == gridDim.x - 1 ? 1 : -1);
-  if (who < 0) return;
-  L.dbg[((size_t) it * 2 + who) * kDbgWords + k] = v;
-}
-
-__device__ __forceinline__ unsigned ld_volatile_u32(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-
-// Grid barrier of the loop kernel.  Everything but the sequence number is read from the kernel parameters
-// (constant bank) when needed, so the barrier costs one live register in the hot loop.
-struct LoopSync {
-  unsigned seq;  // barriers completed so far (identical on every CTA)
-
-  // every CTA: everything this CTA wrote is visible before the arrival counts
-  __device__ __forceinline__ void arrive(const LoopArgs& L) {
-    __syncthreads();
-    if (threadIdx.x == 0) { __threadfence(); atomicAdd(&L.bar->count, 1u); }
-    ++seq;
-  }
-  // leader CTA: wait until every CTA has arrived at barrier `seq`
-  __device__ __forceinline__ bool wait_all(const LoopArgs& L, int* bcast) {
-    if (threadIdx.x == 0) {
-      const unsigned target = gridDim.x * seq;
-      const long long t0 = clock64();
-      int ok = 1, spins = 0;
-      while (ld_volatile_u32(&L.bar->count) < target) {
-        if ((++spins & 255) == 0 && (ld_volatile_u32(&L.bar->abort) || clock64() - t0 > L.timeout_cycles)) { ok = 0; break; }
-      }
-      __threadfence();
-      if (!ok) { L.st->error = 2; atomicExch(&L.bar->abort, 1u); __threadfence(); }
-      *bcast = ok;
-    }
-    __syncthreads();
-    const bool ok = *bcast != 0;
-    __syncthreads();
-    return ok;
-  }
-  // leader CTA: let everybody pass barrier `seq`; mode travels with the release
-  __device__ __forceinline__ void release(const LoopArgs& L, unsigned mode) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      L.bar->mode = mode;
-      __threadfence();
-      atomicExch(&L.bar->gen, seq);
-    }
-  }
-  // every CTA: wait for the release of barrier `seq`; returns the mode, or -1 on abort / timeout
-  __device__ __forceinline__ int wait_release(const LoopArgs& L, int* bcast) {
-    if (threadIdx.x == 0) {
-      const long long t0 = clock64();
-      int ok = 1, spins = 0;
-      while (ld_volatile_u32(&L.bar->gen) < seq) {
-        if ((++spins & 255) == 0 && (ld_volatile_u32(&L.bar->abort) || clock64() - t0 > L.timeout_cycles)) { ok = 0; break; }
-      }
-      __threadfence();
-      if (!ok) { L.st->error = 2; atomicExch(&L.bar->abort, 1u); __threadfence(); }
-      *bcast = ok ? (int) ld_volatile_u32(&L.bar->mode) : -1;
-    }
-    __syncthreads();
-    const int m = *bcast;
-    __syncthreads();
-    return m;
-  }
-  // plain barrier (leader releases as soon as everybody has arrived)
-  __device__ __forceinline__ bool sync_all(const LoopArgs& L, int* bcast) {
-    arrive(L);
-    if (blockIdx.x == 0) {
-      if (!wait_all(L, bcast)) return false;
-      release(L, 0);
-    }
-    return wait_release(L, bcast) >= 0;
-  }
-};
-
-// projective association of the whole slice (grid-stride), see proj_find_kernel
-__device__ __forceinline__ void proj_find_body(const SliceArgs& a, const float* S) {
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.nm; i += gridDim.x * blockDim.x) {
-    NNQuery q;
-    nn_transform<3>(S, a.mp[i], q.qx, q.qy, q.qz);
-    q.bd2 = a.md2; q.sd2 = a.md2; q.bidx = INT_MAX; q.bpos = -1;
-    int pix;
-    if (project_pixel(q.qx, q.qy, q.qz, a.fx, a.fy, a.pcx, a.pcy, a.min_depth, a.max_depth, a.width, a.height, pix)) {
-      const unsigned long long key = __ldg(a.image + pix);
-      if (key != ~0ull) {
-        const int idx = (int) (key & 0xffffffffull);
-        const float4 c = __ldg(a.fp + idx);
-        const float ddx = q.qx - c.x, ddy = q.qy - c.y, ddz = q.qz - c.z;
-        const float d2 = fmaf(ddz, ddz, fmaf(ddy, ddy, ddx * ddx));
-        if (d2 <= a.md2) { q.bd2 = d2; q.bidx = idx; q.bpos = idx; }
-      }
-    }
-    nn_finish<3>(a, S, q, i, 0.f, __ldcg(a.c_fpos + i));
-  }
 }
 
 // lineariser constants of slice s into the control block (S from the device state, coherently)
@@ -569,10 +437,6 @@ __device__ __forceinline__ void load_lin_const(const SliceArgs& a, const float* 
   }
   __syncthreads();
 }
-__device__ __forceinline__ void loop_load_lin_const(const SliceArgs& a, const DevState* st, int s, TileCtl& ctl) {
-  load_lin_const(a, st->S[s].m, ctl.nfail_prev[s] <= kFailCap ? 1 : 0, ctl);
-}
-
 // The failures a warp recorded during its tiles: one query at a time, the whole warp searches (the lanes
 // fetch the bounds of the rows, the rows' points are dealt out to the lanes, shuffle arg-min -- nn_far_body's
 // scheme), lane 0 writes slot + bound and linearises.  Everything the tile already held (query, old slot, the
@@ -685,83 +549,6 @@ __device__ __noinline__ void loop_search_recs(const SliceArgs& a, TileCtl& ctl, 
   lin_push_tail_lane0<DIM>(A, ctl.tail);
 }
 
-// One warp per listed query: search, slot + bound, linearisation; the sums go to the slice's accumulators.
-// (cold path of the loop kernel: its own accumulator registers and flush, kept out of line)
-// push: the sums go to the CTA's shared tail accumulators (added by the pass's flush); else flushed here
-template <int DIM, int FACTOR>
-__device__ __noinline__ void loop_search_list(const SliceArgs& a, TileCtl& ctl, int track2, int n, const int* list, int w0, int ws,
-                                              int push) {
-  const float cell = __fdiv_rn(1.f, a.inv_cell);
-  const int K = (DIM == 3) ? (2 * a.R + 1) * (2 * a.R + 1) : (2 * a.R + 1);
-  LinAcc<DIM> A;
-  A.clear();
-  if (track2) nn_far_body<DIM, true, FACTOR>(a, ctl.lk.S, ctl.rows, K, cell, n, list, &A, &ctl.lk, w0, ws);
-  else nn_far_body<DIM, false, FACTOR>(a, ctl.lk.S, ctl.rows, K, cell, n, list, &A, &ctl.lk, w0, ws);
-  if (push) lin_push_tail<DIM>(A, ctl.tail);
-  else lin_flush<DIM>(a.acc, false, A, ctl.fsm);
-}
-
-// one pass of the streaming lineariser over slice s inside the loop kernel; the CTA's sums are added to
-// cta_acc (shared memory, published once per iteration: no global atomics on the hot path)
-template <int DIM, int FACTOR, bool CHECK>
-__device__ __forceinline__ void loop_lin_pass(const SliceArgs& a, TileStage* stages, TileCtl& ctl, int s, int track2, long long* cta_acc,
-                                              unsigned long long* dbg = nullptr, unsigned long long* dbgc = nullptr) {
-  {
-    long long mine0, mine1;
-    {
-      LinAcc<DIM> A;
-      A.clear();
-      const int terms = lin_tiles_body<DIM, FACTOR, CHECK>(a, stages, ctl, A);
-      if (dbg) dbg[1] = globaltimer_ns();
-      if (dbgc && (threadIdx.x & 31) == 0) atomicMax(dbgc, globaltimer_ns());
-      lin_warp_reduce<DIM>(terms <= 30, A, mine0, mine1);
-    }
-    // the warp's failures: searched and linearised here, while the other warps are still streaming (the
-    // accumulators are reduced to two words per lane by now: nothing to spill around the call)
-    if (CHECK) {
-      __syncthreads();  // every warp is done with its tiles: the record list is complete
-      if ((int) (threadIdx.x >> 5) < ctl.nrec) loop_search_recs<DIM, FACTOR>(a, ctl, track2, ctl.nrec, ctl.rec);
-    }
-    lin_cta_reduce(a.acc, mine0, mine1, ctl.fsm, cta_acc);
-  }
-  // the sums of the failures the warps resolved on the way (and of mid-pass flushes) sit in the shared tail
-  if (threadIdx.x < kAcc) {
-    const long long v = ctl.tail[threadIdx.x];
-    if (cta_acc) cta_acc[threadIdx.x] += v;
-    else if (v) atomicAdd(&a.acc[threadIdx.x], (unsigned long long) v);
-    ctl.tail[threadIdx.x] = 0;
-  }
-  if (CHECK) {
-    if (dbg) { dbg[7] = (unsigned long long) ctl.nfail; dbg[2] = globaltimer_ns(); }
-    if (threadIdx.x == 0) ctl.nfail_prev[s] = ctl.nfail;
-  }
-}
-
-template <int DIM, int FACTOR>
-__device__ __noinline__ void loop_lin_all(const SliceArgs& a, TileStage* stages, TileCtl& ctl) {
-  loop_lin_pass<DIM, FACTOR, false>(a, stages, ctl, 0, 0, nullptr);
-}
-
-// first phase of a from-scratch search of the whole slice (rings 0-1, thread per query)
-template <int DIM>
-__device__ __noinline__ void loop_search_phase1(const SliceArgs& a, TileCtl& ctl, int track2) {
-  const float cell = __fdiv_rn(1.f, a.inv_cell);
-  const float ring2 = (a.R >= 2) ? (1.f - 4e-3f) * cell : __fsqrt_rn(a.rho_s2);
-  const float ring2_sq = (a.R >= 2) ? ring2 * ring2 : 3.0e38f;
-  if (track2) nn_phase1_body<DIM, true>(a, ctl.lk.S, cell, ring2, ring2_sq, true, a.nm);
-  else nn_phase1_body<DIM, false>(a, ctl.lk.S, cell, ring2, ring2_sq, true, a.nm);
-}
-
-// second phase: the queries rings 0-1 did not settle
-template <int DIM>
-__device__ __noinline__ void loop_search_far(const SliceArgs& a, TileCtl& ctl, int track2, int n_far) {
-  const float cell = __fdiv_rn(1.f, a.inv_cell);
-  const int K = (DIM == 3) ? (2 * a.R + 1) * (2 * a.R + 1) : (2 * a.R + 1);
-  const int wpb = blockDim.x >> 5, w0 = blockIdx.x * wpb + (threadIdx.x >> 5), ws = gridDim.x * wpb;
-  if (track2) nn_far_body<DIM, true>(a, ctl.lk.S, ctl.rows, K, cell, n_far, a.far_list, nullptr, nullptr, w0, ws);
-  else nn_far_body<DIM, false>(a, ctl.lk.S, ctl.rows, K, cell, n_far, a.far_list, nullptr, nullptr, w0, ws);
-}
-
 // linearise the listed correspondences as their slots are now (thread per correspondence, scalar path)
 template <int DIM, int FACTOR>
 __device__ __noinline__ void loop_lin_list(const SliceArgs& a, TileCtl& ctl, int n, const int* list) {
@@ -787,58 +574,6 @@ __device__ __noinline__ void loop_lin_list(const SliceArgs& a, TileCtl& ctl, int
     }
   }
   lin_flush<DIM>(a.acc, false, A, ctl.fsm);
-}
-
-// Prefetch of the next iteration's check pass over slice `a`: none of it depends on the transform the solve step
-// is about to produce, so the CTA starts its pipeline while it waits at the barrier.
-//   part 1 (before the arrival): the bulk copies of every warp's first kStages tiles;
-//   part 2 (after the arrival, by the CTAs that only wait): the gathers of the first tile.
-// Whoever cannot use the prefetched tiles (stop, a full search, work lists that rewrite slots) drains them.
-__device__ __forceinline__ void loop_prefetch_bulk(const SliceArgs& a, TileStage* stages, TileCtl& ctl) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int n_tiles = (a.nm + kWTile - 1) / kWTile;
-  const int W = gridDim.x * kLoopWarps, g0 = warp * gridDim.x + blockIdx.x;
-  const int my_tiles = g0 < n_tiles ? (n_tiles - g0 + W - 1) / W : 0;
-  if (lane == 0 && my_tiles > 0) {
-    asm volatile("fence.proxy.async;" ::: "memory");
-    for (int j = 0; j < kStages && j < my_tiles; ++j) tile_issue_bulk<true>(a, stages[j].w[warp], &ctl.full[warp][j], g0 + j * W);
-  }
-  if (threadIdx.x == 0) ctl.pref = 1;  // (read behind the barrier's __syncthreads)
-}
-__device__ __forceinline__ void loop_prefetch_gather(const SliceArgs& a, TileStage* stages, TileCtl& ctl) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int n_tiles = (a.nm + kWTile - 1) / kWTile;
-  const int g0 = warp * gridDim.x + blockIdx.x;
-  if (g0 < n_tiles) {
-    unsigned phase = ctl.phase_bits[warp];
-    mbar_wait(&ctl.full[warp][0], phase & 1u);
-    phase ^= 1u;
-    tile_issue_gather(a, stages[0].w[warp], g0 * kWTile, lane);
-    if (lane == 0) ctl.phase_bits[warp] = phase;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) ctl.pref = 3;
-}
-// the prefetched tiles will not be used: wait for the copies in flight (the mbarrier phases stay in step)
-__device__ __forceinline__ void loop_prefetch_drain(const SliceArgs& a, TileCtl& ctl) {
-  __syncthreads();
-  const int pref = ctl.pref;
-  if (pref) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int n_tiles = (a.nm + kWTile - 1) / kWTile;
-    const int W = gridDim.x * kLoopWarps, g0 = warp * gridDim.x + blockIdx.x;
-    const int my_tiles = g0 < n_tiles ? (n_tiles - g0 + W - 1) / W : 0;
-    unsigned phase = ctl.phase_bits[warp];
-    for (int j = (pref & 2) ? 1 : 0; j < kStages && j < my_tiles; ++j) {
-      mbar_wait(&ctl.full[warp][j], (phase >> j) & 1u);
-      phase ^= 1u << j;
-    }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    if (lane == 0) ctl.phase_bits[warp] = phase;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) ctl.pref = 0;
-  __syncthreads();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -899,207 +634,6 @@ __global__ void __launch_bounds__(kLoopThreads, 1) lin_after_search_kernel(const
   } else {
     loop_lin_list<DIM, FACTOR>(a, ctl, work_count, a.work_list);
   }
-}
-
-// thread-per-query search of a long work list (rings 0-1; the unsettled go to the far list)
-template <int DIM>
-__device__ __noinline__ void loop_search_list_phase1(const SliceArgs& a, TileCtl& ctl, int track2, int n_work) {
-  const float cell = __fdiv_rn(1.f, a.inv_cell);
-  const float ring2 = (a.R >= 2) ? (1.f - 4e-3f) * cell : __fsqrt_rn(a.rho_s2);
-  const float ring2_sq = (a.R >= 2) ? ring2 * ring2 : 3.0e38f;
-  if (track2) nn_phase1_body<DIM, true>(a, ctl.lk.S, cell, ring2, ring2_sq, false, n_work);
-  else nn_phase1_body<DIM, false>(a, ctl.lk.S, cell, ring2, ring2_sq, false, n_work);
-}
-
-template <int DIM>
-__device__ __noinline__ void loop_solve(const LoopArgs& L, SolveSmem& ssm, bool resident) {
-  icp_solve_block<DIM>(L.ap, L.st, L.px, ssm, L.part, (int) gridDim.x, resident);
-}
-
-__device__ __noinline__ void loop_proj_find(const SliceArgs& a, const float* S) { proj_find_body(a, S); }
-
-// The hot pass (coherence check + linearisation of a certified slice).  SLOT >= 0: the slice arguments are
-// the compile-time entry L.sl[SLOT] of the kernel parameters, i.e. constant-bank operands that occupy no
-// registers; SLOT < 0: any slice (run-time index).
-template <int DIM, int SLOT>
-__device__ __forceinline__ void loop_check_pass(const LoopArgs& L, int s, TileStage* stages, TileCtl& ctl, int track2, int it) {
-  const SliceArgs& a = SLOT >= 0 ? L.sl[SLOT] : L.sl[s];
-  unsigned long long* dbg = nullptr;
-  if (L.dbg && threadIdx.x == 0 && it < kDbgIters && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1))
-    dbg = L.dbg + ((size_t) it * 2 + (blockIdx.x == 0 ? 0 : 1)) * kDbgWords;
-  unsigned long long* dbgc = nullptr;  // (latest pass end over the CTA's warps)
-  if (L.dbg && it == kDbgCtaIter && blockIdx.x < kDbgCtas) dbgc = L.dbg + (size_t) kDbgIters * 2 * kDbgWords + 4 * blockIdx.x;
-  if (L.factor[SLOT >= 0 ? SLOT : s] == SRRG2B_FACTOR_P2P) loop_lin_pass<DIM, SRRG2B_FACTOR_P2P, true>(a, stages, ctl, s, track2, ctl.cta_acc[s], dbg, dbgc);
-  else loop_lin_pass<DIM, SRRG2B_FACTOR_PLANE, true>(a, stages, ctl, s, track2, ctl.cta_acc[s], dbg, dbgc);
-}
-
-template <int DIM>
-__global__ void __launch_bounds__(kLoopThreads, 1) icp_loop_kernel(const __grid_constant__ LoopArgs L) {
-  extern __shared__ __align__(128) unsigned char loop_smem_raw[];
-  TileStage* stages = reinterpret_cast<TileStage*>(loop_smem_raw);
-  // the solve step's arguments and state stay resident in CTA 0's shared memory between iterations
-  __shared__ SolveSmem ssm;
-  bool solved_before = false;
-  __shared__ TileCtl ctl;
-  __shared__ int s_ctrl[4 + 2 * SRRG2B_MAX_SLICES];  // stop, -, -, bcast | list_all[s] | track2[s]
-  const int tid = threadIdx.x;
-  tile_ctl_init(ctl);
-  LoopSync sync{0u};
-  int* const bcast = &s_ctrl[3];
-  constexpr int KMAX = (DIM == 3) ? kRowTable : (2 * kMaxR + 1);
-  for (int k = tid; k < KMAX; k += blockDim.x)
-    ctl.rows[k] = (DIM == 3) ? *reinterpret_cast<const int*>(c_rows3[k]) : *reinterpret_cast<const int*>(c_rows2[k]);
-  __syncthreads();
-  // the slice whose check pass opens an iteration: its first tiles are prefetched across the barrier
-  int s0 = -1;
-  for (int s = L.n_slices - 1; s >= 0; --s)
-    if (L.is_points[s] && L.sl[s].nm > 0) s0 = s;
-  if (s0 >= 0 && L.sl[s0].projective) s0 = -1;
-
-  for (int it = 0;; ++it) {
-    loop_dbg(L, it, 0, globaltimer_ns());
-    // ---- state of this iteration (written by the solve step of the previous one) ----
-    if (tid == 0) s_ctrl[0] = __ldcg(&L.st->stop);
-    if (tid < L.n_slices) {
-      s_ctrl[4 + tid] = __ldcg(&L.st->list_all[tid]);
-      s_ctrl[4 + SRRG2B_MAX_SLICES + tid] = __ldcg(&L.st->track2[tid]);
-    }
-    __syncthreads();
-    if (s0 >= 0 && ctl.pref && (s_ctrl[0] || s_ctrl[4 + s0])) loop_prefetch_drain(L.sl[s0], ctl);  // (not a check pass after all)
-    if (s_ctrl[0]) break;
-    bool fallback = false;  // some slice needs the full search path this iteration (uniform over the grid)
-
-    // ---- phase A: certified slices: coherence check + linearisation; others: first search phase ----
-    for (int s = 0; s < L.n_slices; ++s) {
-      if (!L.is_points[s]) continue;
-      if (L.sl[s].nm <= 0) continue;
-      const int track2 = s_ctrl[4 + SRRG2B_MAX_SLICES + s];
-      loop_load_lin_const(L.sl[s], L.st, s, ctl);
-      if (L.sl[s].projective) {
-        fallback = true;
-        loop_proj_find(L.sl[s], ctl.lk.S);
-      } else if (s_ctrl[4 + s]) {  // no certified bounds: search everything, rings 0-1 here, the rest after the barrier
-        fallback = true;
-        loop_search_phase1<DIM>(L.sl[s], ctl, track2);
-      } else if (s == 0) {
-        loop_check_pass<DIM, 0>(L, s, stages, ctl, track2, it);
-      } else if (s == 1) {
-        loop_check_pass<DIM, 1>(L, s, stages, ctl, track2, it);
-      } else {
-        loop_check_pass<DIM, -1>(L, s, stages, ctl, track2, it);
-      }
-      __syncthreads();
-      if (tid == 0) ctl.pref = 0;  // (consumed by the pass of slice s0)
-    }
-    if (!fallback && s0 >= 0) loop_prefetch_bulk(L.sl[s0], stages, ctl);
-
-    // ---- publish this CTA's sums, barrier; in the all-certified case CTA 0 goes straight to the solve step ----
-    for (int k = tid; k < L.n_slices * kAcc; k += blockDim.x) {
-      L.part[(size_t) blockIdx.x * (SRRG2B_MAX_SLICES * kAcc) + k] = (&ctl.cta_acc[0][0])[k];
-      (&ctl.cta_acc[0][0])[k] = 0;
-    }
-    loop_dbg(L, it, 3, globaltimer_ns());
-    if (L.dbg && it == kDbgCtaIter && tid == 0 && blockIdx.x < kDbgCtas) {
-      unsigned long long* q = L.dbg + (size_t) kDbgIters * 2 * kDbgWords + 4 * blockIdx.x;
-      q[1] = globaltimer_ns(); q[2] = (unsigned long long) ctl.nfail_prev[0];
-    }
-    sync.arrive(L);
-    if (blockIdx.x != 0 && ctl.pref == 1) loop_prefetch_gather(L.sl[s0], stages, ctl);  // (while CTA 0 solves)
-    if (blockIdx.x == 0) {
-      if (!sync.wait_all(L, bcast)) break;
-      loop_dbg(L, it, 4, globaltimer_ns());
-      bool lists = false;
-      if (!fallback) {
-        for (int s = 0; s < L.n_slices; ++s)
-          if (L.is_points[s] && L.sl[s].nm > 0 && !L.sl[s].projective && __ldcg(L.sl[s].work_count) > 0) lists = true;
-        if (L.dbg && tid == 0 && it < kDbgIters) L.dbg[((size_t) it * 2) * kDbgWords + 7] |= (unsigned long long) __ldcg(L.sl[0].work_count) << 32;
-      }
-      if (!fallback && !lists) {
-        loop_solve<DIM>(L, ssm, solved_before);
-        solved_before = true;
-        loop_dbg(L, it, 5, globaltimer_ns());
-        sync.release(L, 0);
-      } else {
-        sync.release(L, 1);
-      }
-    }
-    const int mode = sync.wait_release(L, bcast);
-    loop_dbg(L, it, 6, globaltimer_ns());
-    if (mode < 0) break;
-    if (mode == 0) continue;
-    if (s0 >= 0) loop_prefetch_drain(L.sl[s0], ctl);  // the work lists may rewrite slots and bounds of the prefetched tiles
-
-    // ---- phase B (rare): overflow work lists of certified slices, far phase of the full searches ----
-    bool far_phase = false;
-    for (int s = 0; s < L.n_slices; ++s) {
-      if (!L.is_points[s]) continue;
-      const SliceArgs& a = L.sl[s];
-      if (a.nm <= 0 || a.projective) continue;
-      const int track2 = s_ctrl[4 + SRRG2B_MAX_SLICES + s];
-      loop_load_lin_const(a, L.st, s, ctl);
-      if (s_ctrl[4 + s]) {
-        far_phase = true;
-        const int n_far = __ldcg(a.far_count);
-        if (n_far > 0) loop_search_far<DIM>(a, ctl, track2, n_far);
-      } else {
-        const int n_work = __ldcg(a.work_count);
-        const int wpb = blockDim.x >> 5, w0 = blockIdx.x * wpb + (tid >> 5), ws = gridDim.x * wpb;
-        if (n_work >= L.big_list) {  // long list: thread per query, then the far phase and a list linearisation
-          far_phase = true;
-          loop_search_list_phase1<DIM>(a, ctl, track2, n_work);
-        } else if (n_work > 0) {   // short list: one warp per query does the whole job
-          if (L.factor[s] == SRRG2B_FACTOR_P2P) loop_search_list<DIM, SRRG2B_FACTOR_P2P>(a, ctl, track2, n_work, a.work_list, w0, ws, 0);
-          else loop_search_list<DIM, SRRG2B_FACTOR_PLANE>(a, ctl, track2, n_work, a.work_list, w0, ws, 0);
-        }
-      }
-      __syncthreads();
-    }
-    if (far_phase) {
-      if (!sync.sync_all(L, bcast)) break;
-      // far phase of the long work lists (the from-scratch searches ran theirs above, in phase order)
-      bool any = false;
-      for (int s = 0; s < L.n_slices; ++s) {
-        if (!L.is_points[s]) continue;
-        const SliceArgs& a = L.sl[s];
-        if (a.nm <= 0 || a.projective || s_ctrl[4 + s] || __ldcg(a.work_count) < L.big_list) continue;
-        any = true;
-        loop_load_lin_const(a, L.st, s, ctl);
-        const int n_far = __ldcg(a.far_count);
-        if (n_far > 0) loop_search_far<DIM>(a, ctl, s_ctrl[4 + SRRG2B_MAX_SLICES + s], n_far);
-        __syncthreads();
-      }
-      if (any && !sync.sync_all(L, bcast)) break;
-    }
-
-    // ---- phase C (rare): linearise the slices that were searched from scratch, and the long work lists ----
-    for (int s = 0; s < L.n_slices; ++s) {
-      if (!L.is_points[s]) continue;
-      const SliceArgs& a = L.sl[s];
-      if (a.nm <= 0) continue;
-      if (a.projective || s_ctrl[4 + s]) {
-        loop_load_lin_const(a, L.st, s, ctl);
-        if (L.factor[s] == SRRG2B_FACTOR_P2P) loop_lin_all<DIM, SRRG2B_FACTOR_P2P>(a, stages, ctl);
-        else loop_lin_all<DIM, SRRG2B_FACTOR_PLANE>(a, stages, ctl);
-        __syncthreads();
-      } else {
-        const int n_work = __ldcg(a.work_count);
-        if (n_work < L.big_list) continue;
-        loop_load_lin_const(a, L.st, s, ctl);
-        if (L.factor[s] == SRRG2B_FACTOR_P2P) loop_lin_list<DIM, SRRG2B_FACTOR_P2P>(a, ctl, n_work, a.work_list);
-        else loop_lin_list<DIM, SRRG2B_FACTOR_PLANE>(a, ctl, n_work, a.work_list);
-        __syncthreads();
-      }
-    }
-    sync.arrive(L);
-    if (blockIdx.x == 0) {
-      if (!sync.wait_all(L, bcast)) break;
-      loop_solve<DIM>(L, ssm, solved_before);
-      solved_before = true;
-      sync.release(L, 0);
-    }
-    if (sync.wait_release(L, bcast) < 0) break;
-  }
-  if (s0 >= 0) loop_prefetch_drain(L.sl[s0], ctl);  // nothing may be in flight when the CTA exits
 }
 
 }  // namespace s2b

@@ -1,7 +1,8 @@
 """Multi-GPU parity (needs >= 2 CUDA devices, skipped otherwise): the moving cloud is sharded by
-rank, one NCCL all-reduce of the integer accumulators per iteration; every rank must end with the
-oracle's single-process pose / IterationStats bit for bit, and the per-rank correspondence lists
-concatenate to the oracle's list."""
+rank, the integer accumulators are all-reduced over the peer mailboxes inside the solve kernel; every
+rank must end with the oracle's single-process pose / IterationStats bit for bit, the per-rank
+correspondence lists concatenate to the oracle's list, and the stand-alone linearize call returns the
+GLOBAL sums on every rank."""
 import os
 import sys
 
@@ -39,13 +40,19 @@ def _worker(rank, world, uid_q, out_q):
     for _ in range(2):
         res = ctx.icp_run(sl, A.aligner_params(**KW), np.eye(4))
     corr = ctx.get_correspondences(0, e - b)
-    out_q.put((rank, res["T"], res["status"], res["stats"], corr))
+    # stand-alone find + linearize at a fixed transform: every rank must return the global accumulators
+    S = syn.iso3([0.02, -0.01, 0.03], [0.004, -0.003, 0.005])
+    fp, fa = A.finder_params(0.3, 0.8), A.factor_params(A.FACTOR_PLANE, A.ROB_HUBER, 0.01)
+    ctx.find_correspondences(0, S, fp, e - b)
+    lin = ctx.linearize(0, S, fp, fa, n_moving=e - b)
+    out_q.put((rank, res["T"], res["status"], res["stats"], corr, lin["acc"], lin["H"], lin["b"]))
     ctx.close()
 
 
-@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("world", [2])
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_sharded_run_equals_oracle(oracle, world):
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
     from srrg2_slam_interfaces_b200 import synthetic as syn
     ctx = mp.get_context("spawn")
     uid_q, out_q = ctx.Queue(), ctx.Queue()
@@ -62,10 +69,16 @@ def test_sharded_run_equals_oracle(oracle, world):
     o = oracle.icp_run(3, [oracle.make_slice(F, M, None, oracle.finder_params(0.3, 0.8),
                                              oracle.factor_params(oracle.FACTOR_PLANE, oracle.ROB_HUBER, 0.01))],
                        oracle.aligner_params(**KW), np.eye(4))
-    for rank, T, status, stats, corr in results:
+    S = syn.iso3([0.02, -0.01, 0.03], [0.004, -0.003, 0.005])
+    ofp = oracle.finder_params(0.3, 0.8)
+    ofi, _ = oracle.find(oracle.Index(F, oracle.NN_KDTREE), F, M, S, ofp)
+    ol = oracle.linearize(F, M, ofi, S, ofp, oracle.factor_params(oracle.FACTOR_PLANE, oracle.ROB_HUBER, 0.01))
+    for rank, T, status, stats, corr, acc, H, b in results:
         assert status == o["status"]
         assert np.array_equal(T, o["T"])
         assert stats == o["stats"]
+        assert np.array_equal(acc, ol["acc"]), "rank %d: stand-alone linearize did not return the global sums" % rank
+        assert np.array_equal(H, ol["H"]) and np.array_equal(b, ol["b"])
     fi = np.concatenate([r[4][0] for r in results])
     mi = np.concatenate([r[4][1] for r in results])
     rs = np.concatenate([r[4][2] for r in results])
