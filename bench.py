@@ -10,7 +10,8 @@ iterations of the configuration over the resident clouds.
          every timed step, as a tracker's fresh setMoving() would (the warm figure is reported beside it)
   e2e    the same step through the C ABI with HOST (pinned) buffers: H2D of the clouds, index build, all
          iterations, D2H of pose + IterationStats inside the timed region.  N > 1: the replicated fixed cloud
-         crosses PCIe once (rank 0) and is fanned out over NVLink (NCCL broadcast), every rank uploads its shard
+         crosses PCIe once IN TOTAL (every rank uploads 1/N of it) and is all-gathered over NVLink; every rank
+         uploads its own shard of the moving cloud
 Configurations (BASELINE.json `configs`):
   c2 (default, the metric's configuration)  SE(3) point+normal, 1M vs 1M, 20 iterations, Huber.  N > 1: weak
      scaling -- the fixed cloud is replicated, every rank owns a 1M-point shard of an N x 1M moving cloud; value
@@ -18,7 +19,8 @@ Configurations (BASELINE.json `configs`):
   c5  2D multi-cue: 2 scans x 1080 beams (fixed) + odometry prior against a 10M-point local map (moving), 10
      iterations; STRONG scaling: the map is sharded over the N ranks (R/trackers/multi_tracker_impl.cpp:97-98)
   c3  RGB-D projective association, 640x480, 30-frame sequence (29 aligner calls x 10 iterations per step); N = 1
-  c4  pose-graph Gauss-Newton, 100k SE(3) poses / 500k factors; one GN iteration per step; N = 1
+  c4  pose-graph optimisation, 100k SE(3) poses / 500k factors: damped Gauss-Newton to |dx| < 1e-6, a step = one
+     iteration (linearise + PCG solve + update); factor-sharded under torchrun (all-reduce of H / b / chi only)
 The accumulators of the ranks are exchanged inside the solve kernel over peer mailboxes (NVLink loads / stores);
 NCCL only bootstraps (IPC handles, coordinate bounds).  With N > 1 rank 0 runs the CPU oracle on the GLOBAL
 clouds and compares pose bits, IterationStats and the concatenated correspondence lists (`result_check.parity`).
@@ -84,13 +86,16 @@ class C2:
     def replicated(self):  # arrays every rank holds identically (fanned out over NVLink in the e2e step)
         return ["fixed", "fixed_normals"]
 
-    def upload(self, A, ctx, host, dev=None):
+    def upload(self, A, ctx, host):
+        ctx.set_cloud(A.FIXED, 0, host["fixed"], host["fixed_normals"])
+        self.upload_sharded(A, ctx, host)
+
+    def upload_sharded(self, A, ctx, host):  # this rank's part of the sharded operand
         n, r, w = self.n, self.rank, self.world
-        if dev is None:
-            ctx.set_cloud(A.FIXED, 0, host["fixed"], host["fixed_normals"])
-        else:
-            ctx.set_cloud_device(A.FIXED, 0, dev["fixed"].data_ptr(), dev["fixed_normals"].data_ptr(), None, n)
         ctx.set_cloud(A.MOVING, 0, host["moving"], host["moving_normals"], index_offset=r * n, n_global=w * n)
+
+    def upload_replicated_from_device(self, A, ctx, dev):
+        ctx.set_cloud_device(A.FIXED, 0, dev["fixed"].data_ptr(), dev["fixed_normals"].data_ptr(), None, self.n)
 
     def slices(self, A):
         return [A.make_slice(3, 0, None, A.finder_params(self.max_distance, self.normal_cos),
@@ -163,7 +168,7 @@ class C5:
     def replicated(self):
         return []  # (the scans are 2 x 1080 points: not worth a broadcast)
 
-    def upload(self, A, ctx, host, dev=None):
+    def upload(self, A, ctx, host):
         for k in range(2):
             ctx.set_cloud(A.FIXED, k, host["scan%d" % k], host["scan%d_normals" % k])
             ctx.set_cloud(A.MOVING, k, host["map"], host["map_normals"], index_offset=self.b, n_global=self.n_map)
@@ -388,7 +393,10 @@ def run_aligner(args):
         keep.append(t)
         host[k] = t.numpy()
     # device staging of the replicated arrays for the NVLink fan-out of the e2e step
-    dev = {k: torch.empty(host[k].shape, dtype=torch.float32, device="cuda") for k in cfg.replicated()} if world > 1 else None
+    dev = None
+    if world > 1 and cfg.replicated() and all(host[k].shape[0] % world == 0 for k in cfg.replicated()):
+        dev = {k: torch.empty(host[k].shape, dtype=torch.float32, device="cuda") for k in cfg.replicated()}
+        shard = {k: torch.empty((host[k].shape[0] // world,) + host[k].shape[1:], dtype=torch.float32, device="cuda") for k in dev}
 
     ctx = A.Context(cfg.dim, local_rank)
     if world > 1:
@@ -398,13 +406,18 @@ def run_aligner(args):
     sl, ap, T0 = cfg.slices(A), cfg.aligner_params(A), cfg.T0()
 
     def upload_e2e():
-        if dev:
-            for k in dev:  # one PCIe crossing on rank 0, then NVLink
-                if rank == 0:
-                    dev[k].copy_(torch.from_numpy(host[k]), non_blocking=True)
-                dist.broadcast(dev[k], src=0)
-            torch.cuda.current_stream().synchronize()
-        cfg.upload(A, ctx, host, dev)
+        if not dev:
+            cfg.upload(A, ctx, host)
+            return
+        # the sharded operand first (its H2D copy runs on the library's copy stream), then the replicated cloud:
+        # every rank uploads 1/N of it over its own PCIe link and the parts are all-gathered over NVLink
+        cfg.upload_sharded(A, ctx, host)
+        for k in dev:
+            rows = host[k].shape[0] // world
+            shard[k].copy_(torch.from_numpy(host[k][rank * rows:(rank + 1) * rows]), non_blocking=True)
+            dist.all_gather_into_tensor(dev[k].view(-1), shard[k].view(-1))
+        torch.cuda.current_stream().synchronize()
+        cfg.upload_replicated_from_device(A, ctx, dev)
 
     flush_buf = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device="cuda")
 
@@ -518,7 +531,7 @@ def run_aligner(args):
                              "kernel_ms": k_ms, "algorithmic_bytes_per_launch": abytes, "peak_source": peak_src},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": 1e3 * e2e_s_max / args.steps,
-                        "fixed_cloud_fan_out": "rank 0 uploads, NCCL broadcast over NVLink" if dev else "none"},
+                        "fixed_cloud_fan_out": "every rank uploads 1/N of the replicated fixed cloud, NCCL all-gather over NVLink" if dev else "none"},
                 "gpu_launches": int(gpu_launches), "clocks": clocks,
                 "result_check": {"status": res["status"], "iterations": len(res["stats"]),
                                  "pose_error_rad_m": list(syn.pose_error(res["T"], d["T_star"])),
@@ -631,7 +644,9 @@ def run_c4(args):
         sampler.start()
     t0 = time.perf_counter()
     ctx.pgo_upload(g["guess"], g["fixed"], g["ij"], g["Z"], g["Omega"])
-    hist = [ctx.pgo_iterate(max_cg_iterations=5000, cg_tolerance=1e-8) for _ in range(max(1, args.steps))]
+    # Solver::compute() as optimize() runs it: damped Gauss-Newton until |dx|_inf < 1e-6 (BASELINE C4: or 10 iterations;
+    # the synthetic guess -- integrated noisy odometry, 47 m mean error -- needs more, so the cap is args.steps * 5)
+    hist = ctx.pgo_optimize(max_iterations=max(10, 5 * args.steps), dx_tolerance=1e-6, max_cg_iterations=5000)
     poses = ctx.pgo_download().astype(np.float64)
     e2e_s = time.perf_counter() - t0
     if rank == 0:
@@ -646,14 +661,16 @@ def run_c4(args):
                 "steps": len(hist), "warmup": 0, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": "C4: pose-graph GN, %d SE(3) poses / %d factors (synthetic Manhattan-3D)" % (V, F),
-                           "solver": hist[0].get("solver", "pcg"), "sharding": "factors round-robin over ranks" if world > 1 else "none"},
+                           "solver": "Levenberg-Marquardt steps, inexact block-Jacobi PCG (fp64), atomics-free assembly", "sharding": "factors round-robin over ranks" if world > 1 else "none"},
                 "roofline": {"bound": "hbm", "achieved": lin_bytes / (lin_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                              "frac": lin_bytes / (lin_ms * 1e-3) / 1e9 / peak, "traffic": None, "kernel": "pgo_linearize_kernel",
                              "kernel_ms": lin_ms, "algorithmic_bytes_per_launch": lin_bytes, "peak_source": peak_src},
                 "e2e": {"value": len(hist) / e2e_s, "unit": "GN iters/s", "h2d_bytes_per_step": int(sum(g[k].nbytes for k in ("guess", "ij", "Z", "Omega")) // len(hist)),
                         "d2h_bytes_per_step": int(poses.shape[0] * 64 // len(hist)), "ms_per_step": 1e3 * e2e_s / len(hist)},
                 "gpu_launches": int(ctx.launch_count), "clocks": sampler.stop(),
-                "result_check": {"chi": [h["chi"] for h in hist], "dx_norm_inf": [h["dx_norm_inf"] for h in hist],
+                "result_check": {"converged": bool(hist[-1]["dx_norm_inf"] < 1e-6), "iterations": len(hist),
+                                 "accepted": [h["accepted"] for h in hist], "lambda": [h["lambda"] for h in hist],
+                                 "chi": [h["chi"] for h in hist], "dx_norm_inf": [h["dx_norm_inf"] for h in hist],
                                  "cg_iterations": [h["cg_iterations"] for h in hist], "solve_ms": [round(h["solve_ms"], 3) for h in hist],
                                  "position_error_mean_m": [float(err0.mean()), float(err.mean())]},
                 "cpu_baseline": None}

@@ -179,23 +179,37 @@ int srrg2b_set_kernel_timing(srrg2b_ctx* ctx, int enable);
 int srrg2b_last_kernel_timing(srrg2b_ctx* ctx, float* slice_kernel_ms, int32_t* slice_kernel_launches);
 
 /* ---- a10: pose-graph Gauss-Newton, MultiGraphSLAM_::optimize() -> Solver::compute()
- * (R/system/multi_graph_slam_impl.cpp:299-317).  Variables are SE(3) poses (row-major 4x4 float each),
- * factors are SE3PosePoseGeodesicErrorFactor (R/registration/loop_closure.h:110-111): pair (i, j),
- * measurement Z (4x4) and 6x6 information.  With a communicator the factor list is sharded over the
- * ranks (every rank uploads the whole graph) and only H / b are all-reduced. ---- */
+ * (R/system/multi_graph_slam_impl.cpp:299-317).  Variables are the local maps' poses (R/mapping/local_map.h:64,75):
+ * context dim 3: SE(3), row-major 4x4 float each, factors SE3PosePoseGeodesicErrorFactor
+ * (R/registration/loop_closure.h:111) with a 4x4 measurement Z and a 6x6 information; context dim 2: SE(2),
+ * row-major 3x3 float each, factors SE2PosePoseGeodesicErrorFactor (R/registration/loop_closure.h:110) with a 3x3
+ * measurement and a 3x3 information.  e = t2v(Z^-1 Xi^-1 Xj), right perturbation.  With a communicator the factor
+ * list is sharded over the ranks (every rank uploads the whole graph) and only H / b / chi are all-reduced.
+ * H and b are assembled without atomics (per-factor records gathered in factor order) and every dot product of
+ * the linear solve is summed in a fixed order: results are bit-identical from run to run. ---- */
 typedef struct {
   double chi;                   /* sum of e^T Omega e at the linearisation point */
-  double dx_norm_inf;           /* largest perturbation component applied */
+  double chi_after;             /* ... at the updated poses (srrg2b_pgo_optimize; -1 from srrg2b_pgo_iterate) */
+  double dx_norm_inf;           /* largest perturbation component of the step */
   double cg_relative_residual;  /* |H dx + b| / |b| reached by the linear solve */
+  double lambda;                /* Levenberg-Marquardt damping used (0 for srrg2b_pgo_iterate) */
+  double gain_ratio;            /* actual / predicted decrease of chi */
   int32_t cg_iterations;
   int32_t num_factors;
-  int32_t num_blocks;           /* 6x6 blocks of the block-CSR system matrix */
+  int32_t num_blocks;           /* DxD blocks of the block-CSR system matrix */
+  int32_t accepted;             /* the step was applied (a rejected Levenberg-Marquardt step leaves the poses unchanged) */
   float linearize_ms, solve_ms; /* device times of the two phases */
 } srrg2b_pgo_stats;
-int srrg2b_pgo_upload(srrg2b_ctx* ctx, int64_t n_vars, const float* poses16, const uint8_t* fixed_mask,
-                      int64_t n_factors, const int32_t* ij, const float* Z16, const float* Omega36);
+int srrg2b_pgo_upload(srrg2b_ctx* ctx, int64_t n_vars, const float* poses, const uint8_t* fixed_mask,
+                      int64_t n_factors, const int32_t* ij, const float* Z, const float* Omega);
+/* one plain Gauss-Newton iteration: linearise, solve H dx = -b (block-Jacobi PCG to cg_tolerance), X <- X [+] dx */
 int srrg2b_pgo_iterate(srrg2b_ctx* ctx, int max_cg_iterations, double cg_tolerance, srrg2b_pgo_stats* stats);
-int srrg2b_pgo_download(srrg2b_ctx* ctx, float* poses16);
+/* Solver::compute() as optimize() uses it: iterate until |dx|_inf < dx_tolerance or max_iterations; the steps are
+ * guarded by Levenberg-Marquardt damping with a gain-ratio test, the linear solves are inexact (their tolerance
+ * follows the outer convergence).  stats: one entry per iteration (NULL allowed), *n_done: iterations run. */
+int srrg2b_pgo_optimize(srrg2b_ctx* ctx, int max_iterations, double dx_tolerance, int max_cg_iterations,
+                        srrg2b_pgo_stats* stats, int32_t* n_done);
+int srrg2b_pgo_download(srrg2b_ctx* ctx, float* poses);
 
 #ifdef __cplusplus
 }

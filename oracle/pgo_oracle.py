@@ -268,3 +268,92 @@ def solve(poses, ij, Z, Omega, fixed, iterations=10, tol=1e-6):
         if st["dx_norm_inf"] < tol:
             break
     return poses, hist
+
+
+# ----------------------------------------------------------------------------------------------
+# SE(2): SE2PosePoseGeodesicErrorFactor between VariableSE2Right poses (R/registration/loop_closure.h:110,
+# R/mapping/local_map.h:64).  Poses are 3x3 homogeneous matrices; e = t2v(Z^-1 Xi^-1 Xj) = (t_E, angle(R_E)),
+# right perturbation X <- X v2t([dx, dy, dtheta]).
+# ----------------------------------------------------------------------------------------------
+def v2t2(dx):
+    dx = np.asarray(dx, dtype=np.float64)
+    c, s = np.cos(dx[..., 2]), np.sin(dx[..., 2])
+    T = np.zeros(dx.shape[:-1] + (3, 3))
+    T[..., 0, 0] = c; T[..., 0, 1] = -s; T[..., 1, 0] = s; T[..., 1, 1] = c
+    T[..., 0, 2] = dx[..., 0]; T[..., 1, 2] = dx[..., 1]; T[..., 2, 2] = 1.0
+    return T
+
+
+def t2v2(T):
+    return np.stack([T[..., 0, 2], T[..., 1, 2], np.arctan2(T[..., 1, 0], T[..., 0, 0])], -1)
+
+
+def inv_iso2(T):
+    R = np.swapaxes(T[..., :2, :2], -1, -2)
+    o = np.zeros_like(T)
+    o[..., :2, :2] = R
+    o[..., :2, 2] = -np.einsum("...ij,...j->...i", R, T[..., :2, 2])
+    o[..., 2, 2] = 1.0
+    return o
+
+
+def factor_terms2(poses, ij, Z, Omega):
+    """Per factor: e (F,3), J_i (F,3,3), J_j (F,3,3), chi (F,)."""
+    Xi, Xj = poses[ij[:, 0]], poses[ij[:, 1]]
+    A = inv_iso2(Xi) @ Xj
+    Zi = inv_iso2(Z)
+    E = Zi @ A
+    e = t2v2(E)
+    F = ij.shape[0]
+    Jj = np.zeros((F, 3, 3))
+    Jj[:, :2, :2] = E[:, :2, :2]
+    Jj[:, 2, 2] = 1.0
+    Ji = np.zeros((F, 3, 3))
+    Rzi = Zi[:, :2, :2]
+    Ji[:, :2, :2] = -Rzi
+    St = np.stack([-A[:, 1, 2], A[:, 0, 2]], -1)  # S t_A, S = [0 -1; 1 0]
+    Ji[:, :2, 2] = -np.einsum("fij,fj->fi", Rzi, St)
+    Ji[:, 2, 2] = -1.0
+    chi = np.einsum("fi,fij,fj->f", e, Omega, e)
+    return e, Ji, Jj, chi
+
+
+def linearize2(poses, ij, Z, Omega, fixed):
+    poses = np.asarray(poses, np.float64); Z = np.asarray(Z, np.float64); Omega = np.asarray(Omega, np.float64)
+    V = poses.shape[0]
+    e, Ji, Jj, chi = factor_terms2(poses, ij, Z, Omega)
+    JiT_O = np.swapaxes(Ji, 1, 2) @ Omega
+    JjT_O = np.swapaxes(Jj, 1, 2) @ Omega
+    blocks = [(ij[:, 0], ij[:, 0], JiT_O @ Ji), (ij[:, 0], ij[:, 1], JiT_O @ Jj),
+              (ij[:, 1], ij[:, 0], JjT_O @ Ji), (ij[:, 1], ij[:, 1], JjT_O @ Jj)]
+    free = ~np.asarray(fixed, bool)
+    rows, cols, vals = [], [], []
+    r3, c3 = np.meshgrid(np.arange(3), np.arange(3), indexing="ij")
+    for bi, bj, blk in blocks:
+        keep = free[bi] & free[bj]
+        rows.append((bi[keep, None, None] * 3 + r3).ravel())
+        cols.append((bj[keep, None, None] * 3 + c3).ravel())
+        vals.append(blk[keep].ravel())
+    fx = np.nonzero(~free)[0]
+    rows.append((fx[:, None] * 3 + np.arange(3)).ravel()); cols.append((fx[:, None] * 3 + np.arange(3)).ravel())
+    vals.append(np.ones(fx.size * 3))
+    H = sp.coo_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(3 * V, 3 * V)).tocsr()
+    b = np.zeros((V, 3))
+    np.add.at(b, ij[:, 0], np.einsum("fij,fj->fi", JiT_O, e))
+    np.add.at(b, ij[:, 1], np.einsum("fij,fj->fi", JjT_O, e))
+    b[~free] = 0.0
+    return H, b.ravel(), float(chi.sum()), chi
+
+
+def gn_step2(poses, ij, Z, Omega, fixed):
+    """One SE(2) Gauss-Newton iteration (direct sparse solve); returns (new poses, stats)."""
+    H, b, chi, _ = linearize2(poses, ij, Z, Omega, fixed)
+    dx = spla.spsolve(H.tocsc(), -b).reshape(-1, 3)
+    new = np.asarray(poses, np.float64) @ v2t2(dx)
+    return new, dict(chi=chi, dx_norm_inf=float(np.abs(dx).max()), num_factors=int(ij.shape[0]))
+
+
+def total_chi(poses, ij, Z, Omega):
+    poses = np.asarray(poses, np.float64)
+    f = factor_terms2 if poses.shape[-1] == 3 else factor_terms
+    return float(f(poses, ij, np.asarray(Z, np.float64), np.asarray(Omega, np.float64))[3].sum())

@@ -26,7 +26,7 @@ EXPORTED_SYMBOLS = [
     "srrg2b_find_correspondences", "srrg2b_set_correspondences", "srrg2b_linearize", "srrg2b_icp_run",
     "srrg2b_icp_iterate", "srrg2b_get_correspondences", "srrg2b_reset_correspondences", "srrg2b_last_run_timing",
     "srrg2b_set_kernel_timing", "srrg2b_last_kernel_timing", "srrg2b_debug_info",
-    "srrg2b_pgo_upload", "srrg2b_pgo_iterate", "srrg2b_pgo_download",
+    "srrg2b_pgo_upload", "srrg2b_pgo_iterate", "srrg2b_pgo_optimize", "srrg2b_pgo_download",
 ]
 
 
@@ -70,9 +70,10 @@ class IterStats(C.Structure):
 
 
 class PgoStats(C.Structure):
-    _fields_ = [("chi", C.c_double), ("dx_norm_inf", C.c_double), ("cg_relative_residual", C.c_double),
+    _fields_ = [("chi", C.c_double), ("chi_after", C.c_double), ("dx_norm_inf", C.c_double),
+                ("cg_relative_residual", C.c_double), ("lambda", C.c_double), ("gain_ratio", C.c_double),
                 ("cg_iterations", C.c_int32), ("num_factors", C.c_int32), ("num_blocks", C.c_int32),
-                ("linearize_ms", C.c_float), ("solve_ms", C.c_float)]
+                ("accepted", C.c_int32), ("linearize_ms", C.c_float), ("solve_ms", C.c_float)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -123,6 +124,7 @@ def load_library():
     lib.srrg2b_debug_info.argtypes = [vp, C.c_int, vp]
     lib.srrg2b_pgo_upload.argtypes = [vp, C.c_int64, vp, vp, C.c_int64, vp, vp, vp]
     lib.srrg2b_pgo_iterate.argtypes = [vp, C.c_int, C.c_double, C.POINTER(PgoStats)]
+    lib.srrg2b_pgo_optimize.argtypes = [vp, C.c_int, C.c_double, C.c_int, C.POINTER(PgoStats), i32p]
     lib.srrg2b_pgo_download.argtypes = [vp, vp]
     lib.srrg2b_set_kernel_timing.argtypes = [vp, C.c_int]
     lib.srrg2b_last_kernel_timing.argtypes = [vp, C.POINTER(C.c_float), i32p]
@@ -327,11 +329,13 @@ class Context:
 
     # ---- a10: pose graph ----
     def pgo_upload(self, poses, fixed, ij, Z, Omega):
-        poses = np.ascontiguousarray(poses, dtype=np.float32).reshape(-1, 16)
+        """dim 3: poses / Z n x 4 x 4, Omega n x 6 x 6; dim 2: poses / Z n x 3 x 3, Omega n x 3 x 3."""
+        m, b = (16, 36) if self.dim == 3 else (9, 9)
+        poses = np.ascontiguousarray(poses, dtype=np.float32).reshape(-1, m)
         fixed = np.ascontiguousarray(fixed, dtype=np.uint8)
         ij = np.ascontiguousarray(ij, dtype=np.int32).reshape(-1, 2)
-        Z = np.ascontiguousarray(Z, dtype=np.float32).reshape(-1, 16)
-        Omega = np.ascontiguousarray(Omega, dtype=np.float32).reshape(-1, 36)
+        Z = np.ascontiguousarray(Z, dtype=np.float32).reshape(-1, m)
+        Omega = np.ascontiguousarray(Omega, dtype=np.float32).reshape(-1, b)
         self._pgo_n = poses.shape[0]
         self._check(self.lib.srrg2b_pgo_upload(self.h, poses.shape[0], poses.ctypes.data, fixed.ctypes.data,
                                                ij.shape[0], ij.ctypes.data, Z.ctypes.data, Omega.ctypes.data))
@@ -341,8 +345,16 @@ class Context:
         self._check(self.lib.srrg2b_pgo_iterate(self.h, max_cg_iterations, cg_tolerance, C.byref(st)))
         return st.as_dict()
 
+    def pgo_optimize(self, max_iterations=10, dx_tolerance=1e-6, max_cg_iterations=2000):
+        """Damped Gauss-Newton until |dx|_inf < dx_tolerance: list of per-iteration stats."""
+        arr = (PgoStats * max_iterations)()
+        n = C.c_int32(0)
+        self._check(self.lib.srrg2b_pgo_optimize(self.h, max_iterations, dx_tolerance, max_cg_iterations, arr, C.byref(n)))
+        return [arr[k].as_dict() for k in range(n.value)]
+
     def pgo_download(self):
-        out = np.empty((self._pgo_n, 4, 4), dtype=np.float32)
+        d1 = self.dim + 1
+        out = np.empty((self._pgo_n, d1, d1), dtype=np.float32)
         self._check(self.lib.srrg2b_pgo_download(self.h, out.ctypes.data))
         return out
 

@@ -382,3 +382,71 @@ def _v2t_batch(dx):
     T[..., :3, 3] = dx[..., :3]
     T[..., 3, 3] = 1.0
     return T
+
+
+def make_pose_graph2d(n_poses, n_factors, seed=6, box=(30, 30), sigma_t=0.02, sigma_r_deg=0.5, max_loop_dist=2.0):
+    """SE(2) analogue of make_pose_graph3d (LoopClosure2D, R/registration/loop_closure.h:110): lattice walk with
+    90 deg turns inside a box, odometry + loop factors between poses within max_loop_dist, measurements =
+    truth (+) noise, Omega = diag(1/sigma^2), guess = integrated noisy odometry, pose 0 fixed.  3x3 matrices."""
+    rng = np.random.default_rng([seed, 0xE22])
+    box = np.asarray(box)
+    dirs = np.array([[1, 0], [0, 1], [-1, 0], [0, -1]])
+    pos = np.zeros((n_poses, 2), dtype=np.int64)
+    pos[0] = box // 2
+    head = np.zeros(n_poses, dtype=np.int64)
+    turn = rng.integers(-1, 2, size=n_poses)
+    keep = rng.uniform(size=n_poses) < 0.7
+    for k in range(1, n_poses):
+        h = head[k - 1] if keep[k] else (head[k - 1] + turn[k]) % 4
+        p = pos[k - 1] + dirs[h]
+        if np.any(p < 0) or np.any(p >= box):
+            h = (h + 2) % 4
+            p = pos[k - 1] + dirs[h]
+        pos[k], head[k] = p, h
+
+    def iso(x, y, th):
+        T = np.zeros(np.shape(x) + (3, 3))
+        T[..., 0, 0] = np.cos(th); T[..., 0, 1] = -np.sin(th); T[..., 1, 0] = np.sin(th); T[..., 1, 1] = np.cos(th)
+        T[..., 0, 2] = x; T[..., 1, 2] = y; T[..., 2, 2] = 1.0
+        return T
+
+    truth = iso(pos[:, 0].astype(np.float64), pos[:, 1].astype(np.float64), head * (np.pi / 2))
+    pairs = [(k, k + 1) for k in range(n_poses - 1)]
+    cells = {}
+    for k in range(n_poses):
+        cells.setdefault((int(pos[k, 0]), int(pos[k, 1])), []).append(k)
+    cand = []
+    for k in range(n_poses):
+        for dx in range(-2, 3):
+            for dy in range(-2, 3):
+                if dx * dx + dy * dy > max_loop_dist ** 2:
+                    continue
+                for j in cells.get((int(pos[k, 0]) + dx, int(pos[k, 1]) + dy), ()):
+                    if j > k + 1:
+                        cand.append((k, j))
+    cand = np.asarray(cand, dtype=np.int64).reshape(-1, 2)
+    n_loops = max(0, min(n_factors - len(pairs), cand.shape[0]))
+    if n_loops:
+        pairs += [tuple(c) for c in cand[rng.choice(cand.shape[0], size=n_loops, replace=False)]]
+    ij = np.asarray(pairs, dtype=np.int32)
+
+    def inv(T):
+        o = np.zeros_like(T)
+        R = np.swapaxes(T[..., :2, :2], -1, -2)
+        o[..., :2, :2] = R
+        o[..., :2, 2] = -np.einsum("...ij,...j->...i", R, T[..., :2, 2])
+        o[..., 2, 2] = 1.0
+        return o
+
+    rel = inv(truth[ij[:, 0]]) @ truth[ij[:, 1]]
+    noise = iso(rng.normal(scale=sigma_t, size=ij.shape[0]), rng.normal(scale=sigma_t, size=ij.shape[0]),
+                rng.normal(scale=np.deg2rad(sigma_r_deg), size=ij.shape[0]))
+    Z = rel @ noise
+    Omega = np.tile(np.diag([1 / sigma_t ** 2, 1 / sigma_t ** 2, 1 / np.deg2rad(sigma_r_deg) ** 2]), (ij.shape[0], 1, 1))
+    guess = np.zeros_like(truth)
+    guess[0] = truth[0]
+    for k in range(1, n_poses):
+        guess[k] = guess[k - 1] @ Z[k - 1]
+    fixed = np.zeros(n_poses, dtype=np.uint8)
+    fixed[0] = 1
+    return dict(truth=truth, guess=guess.astype(np.float32), ij=ij, Z=Z.astype(np.float32), Omega=Omega.astype(np.float32), fixed=fixed)

@@ -85,3 +85,54 @@ def test_sharded_run_equals_oracle(oracle, world):
     assert np.array_equal(fi, o["correspondences"][0][0])
     assert np.array_equal(mi, o["correspondences"][0][1])
     assert np.array_equal(rs, o["correspondences"][0][2])
+
+
+# ---- pose graph, factor-sharded (row e2): every rank ends with the single-process result within the north-star
+# tolerances (the all-reduce changes the fp64 summation order of H / b, nothing else) ----
+def _pgo_worker(rank, world, uid_q, out_q):
+    sys.path.insert(0, ROOT)
+    from srrg2_slam_interfaces_b200 import capi as A
+    from srrg2_slam_interfaces_b200 import synthetic as syn
+    g = syn.make_pose_graph3d(1500, 7000, seed=4, box=(10, 10, 3))
+    ctx = A.Context(3, rank)
+    if world > 1:
+        if rank == 0:
+            uid = ctx.unique_id()
+            for _ in range(world - 1):
+                uid_q.put(uid)
+        else:
+            uid = uid_q.get(timeout=60)
+        ctx.comm_init(uid, rank, world)
+    ctx.pgo_upload(g["guess"], g["fixed"], g["ij"], g["Z"], g["Omega"])
+    st = [ctx.pgo_iterate(max_cg_iterations=4000, cg_tolerance=1e-11) for _ in range(4)]
+    out_q.put((rank, ctx.pgo_download(), [(s["chi"], s["dx_norm_inf"]) for s in st]))
+    ctx.close()
+
+
+def test_sharded_pose_graph_equals_oracle():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from oracle import pgo_oracle as P
+    from srrg2_slam_interfaces_b200 import synthetic as syn
+    world = 2
+    ctx = mp.get_context("spawn")
+    uid_q, out_q = ctx.Queue(), ctx.Queue()
+    procs = [ctx.Process(target=_pgo_worker, args=(r, world, uid_q, out_q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = sorted([out_q.get(timeout=300) for _ in range(world)], key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    g = syn.make_pose_graph3d(1500, 7000, seed=4, box=(10, 10, 3))
+    poses = g["guess"].astype(np.float64)
+    chis = []
+    for _ in range(4):
+        poses, so = P.gn_step(poses, g["ij"], g["Z"].astype(np.float64), g["Omega"].astype(np.float64), g["fixed"])
+        chis.append(so["chi"])
+    assert np.array_equal(results[0][1], results[1][1]), "ranks disagree on the optimised poses"
+    for rank, got, st in results:
+        got = got.astype(np.float64)
+        assert np.abs(got[:, :3, 3] - poses[:, :3, 3]).max() < 1e-4
+        for (chi, _), co in zip(st, chis):
+            assert abs(chi - co) <= 1e-6 * co

@@ -1,5 +1,8 @@
 """Pose-graph Gauss-Newton (row a10, config C4 at reduced size): CUDA (fp64 linearise + PCG) vs the
-numpy/scipy oracle.  Tolerances from BASELINE.json north_star: pose 1e-5 rad / 1e-4 m, chi^2 1e-6 rel."""
+numpy/scipy oracle.  Tolerances from BASELINE.json north_star: pose 1e-5 rad / 1e-4 m, chi^2 1e-6 rel.
+SE(3) and SE(2) (LoopClosure3D / LoopClosure2D, R/registration/loop_closure.h:110-111), plain GN steps against
+the oracle's direct sparse solve, the damped optimize() against the oracle's converged optimum, and run-to-run
+bit-reproducibility of the atomics-free assembly and the ordered reductions."""
 import numpy as np
 import pytest
 
@@ -33,3 +36,69 @@ def test_gn_iterations_match_oracle(capi, n, f, box):
     assert so["dx_norm_inf"] < 1e-3
     assert np.array_equal(got[0], g["guess"][0].astype(np.float64))
     ctx.close()
+
+
+@pytest.mark.parametrize("n,f", [(300, 1200), (2000, 9000)])
+def test_se2_gn_iterations_match_oracle(capi, n, f):
+    from oracle import pgo_oracle as P
+    g = syn.make_pose_graph2d(n, f, seed=6)
+    ctx = capi.Context(2)
+    ctx.pgo_upload(g["guess"], g["fixed"], g["ij"], g["Z"], g["Omega"])
+    poses = g["guess"].astype(np.float64)
+    Z, Om = g["Z"].astype(np.float64), g["Omega"].astype(np.float64)
+    for it in range(5):
+        poses, so = P.gn_step2(poses, g["ij"], Z, Om, g["fixed"])
+        sg = ctx.pgo_iterate(max_cg_iterations=4000, cg_tolerance=1e-11)
+        assert sg["cg_relative_residual"] <= 1e-10
+        assert abs(sg["chi"] - so["chi"]) <= 1e-6 * so["chi"], (it, sg["chi"], so["chi"])
+        got = ctx.pgo_download().astype(np.float64)
+        assert np.abs(got[:, :2, 2] - poses[:, :2, 2]).max() < 1e-4
+        dth = np.arctan2(got[:, 1, 0], got[:, 0, 0]) - np.arctan2(poses[:, 1, 0], poses[:, 0, 0])
+        assert np.abs(np.arctan2(np.sin(dth), np.cos(dth))).max() < 1e-5
+    assert so["dx_norm_inf"] < 1e-3
+    ctx.close()
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_optimize_reaches_the_oracle_optimum(capi, dim):
+    """The damped, inexact-solve optimize() must end at the same optimum as the oracle's plain GN with direct solves."""
+    from oracle import pgo_oracle as P
+    if dim == 3:
+        g = syn.make_pose_graph3d(1200, 5000, seed=4, box=(9, 9, 3))
+        step = P.gn_step
+    else:
+        g = syn.make_pose_graph2d(1500, 6000, seed=6)
+        step = P.gn_step2
+    poses = g["guess"].astype(np.float64)
+    Z, Om = g["Z"].astype(np.float64), g["Omega"].astype(np.float64)
+    for _ in range(12):
+        poses, so = step(poses, g["ij"], Z, Om, g["fixed"])
+        if so["dx_norm_inf"] < 1e-9:
+            break
+    chi_opt = P.total_chi(poses, g["ij"], Z, Om) if dim == 2 else float(P.factor_terms(poses, g["ij"], Z, Om)[3].sum())
+    ctx = capi.Context(dim)
+    ctx.pgo_upload(g["guess"], g["fixed"], g["ij"], g["Z"], g["Omega"])
+    hist = ctx.pgo_optimize(max_iterations=30, dx_tolerance=1e-7, max_cg_iterations=4000)
+    assert hist[-1]["dx_norm_inf"] < 1e-7 and hist[-1]["lambda"] <= 1.0, hist[-1]
+    chi_end = min(hist[-1]["chi"], hist[-1]["chi_after"])
+    assert abs(chi_end - chi_opt) <= 1e-6 * chi_opt, (chi_end, chi_opt)
+    for a, b in zip(hist, hist[1:]):  # chi never increases over accepted steps
+        assert b["chi"] <= a["chi"] * (1 + 1e-12)
+    got = ctx.pgo_download().astype(np.float64)
+    d = dim
+    assert np.abs(got[:, :d, d] - poses[:, :d, d]).max() < 1e-4
+    ctx.close()
+
+
+def test_runs_are_bit_reproducible(capi):
+    """No atomics in the assembly, fixed-order reductions: two runs give the same bits."""
+    g = syn.make_pose_graph3d(1500, 7000, seed=4, box=(10, 10, 3))
+    outs = []
+    for _ in range(2):
+        ctx = capi.Context(3)
+        ctx.pgo_upload(g["guess"], g["fixed"], g["ij"], g["Z"], g["Omega"])
+        st = [ctx.pgo_iterate(max_cg_iterations=300, cg_tolerance=1e-9) for _ in range(3)]
+        outs.append((ctx.pgo_download(), [(s["chi"], s["dx_norm_inf"], s["cg_iterations"], s["cg_relative_residual"]) for s in st]))
+        ctx.close()
+    assert np.array_equal(outs[0][0], outs[1][0])
+    assert outs[0][1] == outs[1][1]
