@@ -19,6 +19,7 @@
 // (aligner.h:23-28).  There is no CPU fallback: without a CUDA device the constructors throw.
 #ifndef SRRG2B_HPP
 #define SRRG2B_HPP
+#include <algorithm>
 #include <array>
 #include <cstdint>
 #include <cstring>
@@ -62,6 +63,27 @@ struct Isometry {
   }
   const float* data() const { return m.data(); }
   float* data() { return m.data(); }
+  float operator()(int r, int c) const { return m[(size_t) (r * (Dim + 1) + c)]; }
+  float& operator()(int r, int c) { return m[(size_t) (r * (Dim + 1) + c)]; }
+  Isometry inverse() const {  // [R t]^-1 = [R^T, -R^T t]
+    Isometry o = Identity();
+    for (int r = 0; r < Dim; ++r) {
+      float t = 0.f;
+      for (int c = 0; c < Dim; ++c) { o(r, c) = (*this)(c, r); t += (*this)(c, r) * (*this)(c, Dim); }
+      o(r, Dim) = -t;
+    }
+    return o;
+  }
+  Isometry operator*(const Isometry& B) const {
+    Isometry o;
+    for (int r = 0; r <= Dim; ++r)
+      for (int c = 0; c <= Dim; ++c) {
+        float t = 0.f;
+        for (int k = 0; k <= Dim; ++k) t += (*this)(r, k) * B(k, c);
+        o(r, c) = t;
+      }
+    return o;
+  }
 };
 
 // srrg2_solver::IterationStats fields the reference reads (aligner_termination_criteria_impl.cpp:30-32)
@@ -185,6 +207,11 @@ public:
 
   // AlignerSliceProcessor_ (points): aligner_slice_processor.h:56-66,142-150
   struct SliceProcessor {
+    // param_finder: SRRG2B_FINDER_NN (kd-tree finders of srrg2_laser_slam_2d) or SRRG2B_FINDER_PROJECTIVE (the
+    // projective finder of srrg2_proslam: needs the pinhole intrinsics and the image size below, Dim == 3)
+    int finder_kind = SRRG2B_FINDER_NN;
+    float finder_fx = 0.f, finder_fy = 0.f, finder_cx = 0.f, finder_cy = 0.f, finder_min_depth = 0.f, finder_max_depth = 1e9f;
+    int finder_width = 0, finder_height = 0;
     float finder_max_distance_m = 0.5f, finder_normal_cos = 0.8f;
     int factor = SRRG2B_FACTOR_PLANE;
     int robustifier = SRRG2B_ROB_NONE;
@@ -202,6 +229,17 @@ public:
     EstimateType measurement = EstimateType::Identity();
     std::array<float, 6> param_diagonal_info_matrix;
     PriorSliceProcessor() { param_diagonal_info_matrix.fill(Dim == 2 ? 100.f : 1.f); }
+    // AlignerSliceOdom{2,3}DPrior::setupFactor (aligner_slice_odometry_prior.cpp:6-37): the measurement is the
+    // odometry increment fixed^-1 * moving -- but only from the THIRD call on (`_count > 1`, :8,:25); the first two
+    // calls leave it at the identity (the tracker has no previous odometry pose yet).
+    void setOdometry(const EstimateType& fixed_pose, const EstimateType& moving_pose) {
+      measurement = _count > 1 ? fixed_pose.inverse() * moving_pose : EstimateType::Identity();
+      ++_count;
+    }
+    int count() const { return _count; }
+
+  private:
+    int _count = 0;
   };
   // AlignerTerminationCriteriaStandard_: aligner_termination_criteria.h:40-56
   struct TerminationCriteria {
@@ -268,9 +306,14 @@ public:
       d.slice_id = (int) k;
       d.min_num_correspondences = s.param_min_num_correspondences;
       detail::embed(s.robot_in_sensor, d.robot_in_sensor);
-      d.finder.kind = SRRG2B_FINDER_NN;
+      if (s.finder_kind == SRRG2B_FINDER_PROJECTIVE && Dim != 3)
+        throw std::runtime_error("MultiAlignerB200::compute|the projective finder needs a 3D aligner");
+      d.finder.kind = s.finder_kind;
       d.finder.max_distance = s.finder_max_distance_m;
       d.finder.normal_cos = s.finder_normal_cos;
+      d.finder.fx = s.finder_fx; d.finder.fy = s.finder_fy; d.finder.cx = s.finder_cx; d.finder.cy = s.finder_cy;
+      d.finder.width = s.finder_width; d.finder.height = s.finder_height;
+      d.finder.min_depth = s.finder_min_depth; d.finder.max_depth = s.finder_max_depth;
       d.factor.factor = s.factor;
       d.factor.robustifier = s.robustifier;
       d.factor.chi_threshold = s.robustifier_chi_threshold;
@@ -346,24 +389,29 @@ private:
 };
 
 // ---------------------------------------------------------------------------------------------
-// Solver on a pose graph (a10): SE3PosePoseGeodesicErrorFactor between VariableSE3QuaternionRightAD
+// Solver on a pose graph (a10): SE{2,3}PosePoseGeodesicErrorFactor between VariableSE2RightAD /
+// VariableSE3QuaternionRightAD poses (R/registration/loop_closure.h:110-111, R/mapping/local_map.h:64,75).
+// The context's dim selects the group: 3 -> 4x4 poses, 6x6 informations; 2 -> 3x3 poses, 3x3 informations.
 // ---------------------------------------------------------------------------------------------
 class PoseGraphSolverB200 {
 public:
   int param_max_iterations = 10;      // Solver::param_max_iterations
   double param_dx_epsilon = 1e-6;     // stop when the largest perturbation component falls below
   int param_max_cg_iterations = 0;    // 0 = library default
-  double param_cg_tolerance = 0.0;    // 0 = library default
+  bool param_damped = true;           // Levenberg-Marquardt guard + inexact solves (srrg2b_pgo_optimize); false: plain GN
+  double param_cg_tolerance = 0.0;    // plain GN only; 0 = library default
   enum Status { Error = 0, Success = 1 };
 
-  explicit PoseGraphSolverB200(ContextPtr ctx) : _ctx(std::move(ctx)) {}
+  PoseGraphSolverB200(ContextPtr ctx, int dim = 3) : _ctx(std::move(ctx)), _m((dim + 1) * (dim + 1)), _b(dim == 3 ? 36 : 9) {
+    if (dim != 2 && dim != 3) throw std::runtime_error("PoseGraphSolverB200|dim must be 2 or 3");
+  }
 
-  // setGraph(): poses row-major 4x4 each, fixed mask, factor pairs (i, j), measurements 4x4, information 6x6
-  void setGraph(std::vector<float> poses16, std::vector<uint8_t> fixed, std::vector<int32_t> ij,
-                std::vector<float> Z16, std::vector<float> Omega36) {
-    _poses = std::move(poses16); _fixed = std::move(fixed); _ij = std::move(ij); _Z = std::move(Z16); _Omega = std::move(Omega36);
-    if (_poses.size() % 16 || _fixed.size() != _poses.size() / 16 || _ij.size() % 2 || _Z.size() != _ij.size() / 2 * 16 ||
-        _Omega.size() != _ij.size() / 2 * 36)
+  // setGraph(): poses row-major (dim+1)^2 each, fixed mask, factor pairs (i, j), measurements, informations
+  void setGraph(std::vector<float> poses, std::vector<uint8_t> fixed, std::vector<int32_t> ij, std::vector<float> Z,
+                std::vector<float> Omega) {
+    _poses = std::move(poses); _fixed = std::move(fixed); _ij = std::move(ij); _Z = std::move(Z); _Omega = std::move(Omega);
+    if (_poses.size() % _m || _fixed.size() != _poses.size() / _m || _ij.size() % 2 || _Z.size() != _ij.size() / 2 * _m ||
+        _Omega.size() != _ij.size() / 2 * _b)
       throw std::runtime_error("PoseGraphSolverB200::setGraph|inconsistent array sizes");
   }
   void compute() {
@@ -372,12 +420,19 @@ public:
                 "PoseGraphSolverB200::compute");
     _stats.clear();
     _status = Error;
-    for (int it = 0; it < param_max_iterations; ++it) {
-      srrg2b_pgo_stats st;
-      _ctx->check(srrg2b_pgo_iterate(_ctx->get(), param_max_cg_iterations, param_cg_tolerance, &st),
+    if (param_damped) {
+      _stats.resize((size_t) std::max(param_max_iterations, 1));
+      int32_t n = 0;
+      _ctx->check(srrg2b_pgo_optimize(_ctx->get(), param_max_iterations, param_dx_epsilon, param_max_cg_iterations, _stats.data(), &n),
                   "PoseGraphSolverB200::compute");
-      _stats.push_back(st);
-      if (st.dx_norm_inf < param_dx_epsilon) break;
+      _stats.resize((size_t) n);
+    } else {
+      for (int it = 0; it < param_max_iterations; ++it) {
+        srrg2b_pgo_stats st;
+        _ctx->check(srrg2b_pgo_iterate(_ctx->get(), param_max_cg_iterations, param_cg_tolerance, &st), "PoseGraphSolverB200::compute");
+        _stats.push_back(st);
+        if (st.dx_norm_inf < param_dx_epsilon) break;
+      }
     }
     _ctx->check(srrg2b_pgo_download(_ctx->get(), _poses.data()), "PoseGraphSolverB200::compute");
     _status = Success;
@@ -388,6 +443,7 @@ public:
 
 private:
   ContextPtr _ctx;
+  size_t _m, _b;
   std::vector<float> _poses, _Z, _Omega;
   std::vector<uint8_t> _fixed;
   std::vector<int32_t> _ij;

@@ -1,0 +1,31 @@
+"""The reference-side adapter classes (adapters/*.h: CorrespondenceFinderB200_, MultiAlignerB200_, PoseGraphSolverB200_)
+are real headers: they must instantiate against the stand-in headers of SURVEY.md Appendix A (adapters/stubs) and the
+C ABI of include/srrg2b.h.  (With srrg2_core / srrg2_solver installed the same headers build against the real ones.)"""
+import os
+import shutil
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++")
+def test_adapters_instantiate_against_the_stub_surface():
+    out = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                          "-I", os.path.join(ROOT, "adapters", "stubs"), "-I", os.path.join(ROOT, "adapters"),
+                          os.path.join(ROOT, "adapters", "check_adapters.cpp")], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr[-3000:]
+
+
+def test_adapters_name_every_entry_point_they_bind():
+    """Every srrg2b_* call in the adapters is declared in include/srrg2b.h."""
+    import re
+    header = open(os.path.join(ROOT, "include", "srrg2b.h")).read()
+    declared = set(re.findall(r"\b(srrg2b_[a-z_0-9]+)\s*\(", header))
+    used = set()
+    for name in os.listdir(os.path.join(ROOT, "adapters")):
+        if name.endswith(".h"):
+            used |= set(re.findall(r"\b(srrg2b_[a-z_0-9]+)\s*\(", open(os.path.join(ROOT, "adapters", name)).read()))
+    used = {u for u in used if not u.startswith("srrg2b_adapters")}
+    assert used and used <= declared, used - declared
