@@ -239,12 +239,11 @@ def test_prior_only_reference_kat_on_gpu(oracle, capi):
     ctx.close()
 
 
-@pytest.mark.parametrize("env", [{"SRRG2B_LOOP": "0"}, {"SRRG2B_PRE_ITERS": "0"}, {"SRRG2B_PRE_ITERS": "1"},
-                                 {"SRRG2B_NO_GRAPH": "1"}])
+@pytest.mark.parametrize("env", [{}, {"SRRG2B_NO_GRAPH": "1"}, {"SRRG2B_TRACK2": "1"}, {"SRRG2B_TRACK2": "0"}])
 def test_execution_modes_match_oracle(oracle, capi, env, monkeypatch):
-    """The same run through every execution mode of the device loop -- kernel sequences only (SRRG2B_LOOP=0),
-    the persistent loop kernel from the very first iteration (PRE_ITERS=0: its in-kernel full search) or after
-    one iteration, stream launches instead of graph replay -- equals the oracle's, bit for bit."""
+    """The same run through every execution mode of the device loop -- CUDA-graph replay (default), plain stream
+    launches, bounds certified from the first iteration on (every later iteration is a coherence-check pass) or
+    never (every iteration searches) -- equals the oracle's, bit for bit."""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     d = syn.make_icp3d(30000, 27001, seed=11)

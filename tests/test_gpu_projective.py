@@ -12,7 +12,7 @@ def _params(mod, K, max_distance=0.15, normal_cos=0.8):
                              cy=K["cy"], width=K["width"], height=K["height"], min_depth=0.2, max_depth=15.0)
 
 
-@pytest.mark.parametrize("width,height,n_frames", [(160, 120, 4), (640, 480, 2)])
+@pytest.mark.parametrize("width,height,n_frames", [(160, 120, 4), (640, 480, 30)])  # C3: the configured 30 frames
 def test_projective_sequence(oracle, capi, width, height, n_frames):
     frames, K = syn.make_rgbd_sequence(n_frames, width, height, seed=3)
     ctx = capi.Context(3)
