@@ -37,6 +37,7 @@ constexpr int kPPL = S2B_LOOP_PPL;         // pairs per lane and tile
 constexpr int kSubTile = 64;               // correspondences of one sub-tile: one pair per lane
 constexpr int kWTile = kSubTile * kPPL;    // correspondences per warp tile
 constexpr int kStages = S2B_LOOP_STAGES;
+constexpr int kFailInPlace = 2 * (S2B_LOOP_THREADS / 32);  // ... unless the CTA saw more failures than two rounds of its warps
 constexpr int kFailCap = 48;               // coherence-check failures a CTA resolves in place per pass (one warp per
                                            // query); the rest go to the global work list
 
@@ -191,6 +192,20 @@ struct PairWork {
 // to a slot since A was last cleared.  Requires blockDim.x == kLoopThreads.
 // CHECK: the first failures of the CTA are recorded in ctl.rec (the caller has them searched once the tiles are
 // done); beyond the cap they go to the global work list.
+// the bulk copies of a warp's first kStages tiles: issued by the kernels BEFORE they load the lineariser constants
+// (nothing here depends on the transform), so the first tiles are in flight meanwhile
+template <bool CHECK>
+__device__ __forceinline__ void lin_tiles_prologue(const SliceArgs& a, TileStage* stages, TileCtl& ctl) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n_tiles = (a.nm + kWTile - 1) / kWTile;
+  const int W = gridDim.x * kLoopWarps, g0 = warp * gridDim.x + blockIdx.x;
+  const int my_tiles = g0 < n_tiles ? (n_tiles - g0 + W - 1) / W : 0;
+  if (lane == 0 && my_tiles > 0) {
+    asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy writes (slots, bounds) before the bulk reads
+    for (int j = 0; j < kStages && j < my_tiles; ++j) tile_issue_bulk<CHECK>(a, stages[j].w[warp], &ctl.full[warp][j], g0 + j * W);
+  }
+}
+
 template <int DIM, int FACTOR, bool CHECK>
 __device__ __forceinline__ int lin_tiles_body(const SliceArgs& a, TileStage* stages, TileCtl& ctl, LinAcc<DIM>& A) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -201,11 +216,7 @@ __device__ __forceinline__ int lin_tiles_body(const SliceArgs& a, TileStage* sta
   const bool regate = a.gate != 0;  // gated-out slots are re-checked every iteration
   if (my_tiles == 0) return 0;
   unsigned long long* bars = ctl.full[warp];
-  // prologue: bulk copies of the warp's first kStages tiles, gathers of the first
-  if (lane == 0) {
-    asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy writes (slots, bounds) before the bulk reads
-    for (int j = 0; j < kStages && j < my_tiles; ++j) tile_issue_bulk<CHECK>(a, stages[j].w[warp], &bars[j], g0 + j * W);
-  }
+  // (the bulk copies of the first kStages tiles were issued by lin_tiles_prologue); gathers of the first tile
   unsigned phase = ctl.phase_bits[warp];
   mbar_wait(&bars[0], phase & 1u);
   phase ^= 1u;
@@ -405,6 +416,8 @@ __global__ void __launch_bounds__(kLoopThreads, 1) lin_tiles_kernel(const SliceA
   TileStage* stages = reinterpret_cast<TileStage*>(loop_smem_raw);
   __shared__ TileCtl ctl;
   tile_ctl_init(ctl);
+  __syncthreads();
+  lin_tiles_prologue<false>(a, stages, ctl);
   if (threadIdx.x == 32) make_lin_const(a, a.S, ctl.lk);
   __syncthreads();
   LinAcc<DIM> A;
@@ -599,6 +612,7 @@ __global__ void __launch_bounds__(kLoopThreads, 1) check_tiles_kernel(const __gr
   for (int k = threadIdx.x; k < KMAX; k += blockDim.x)
     ctl.rows[k] = (DIM == 3) ? *reinterpret_cast<const int*>(c_rows3[k]) : *reinterpret_cast<const int*>(c_rows2[k]);
   __syncthreads();
+  lin_tiles_prologue<true>(a, stages, ctl);
   load_lin_const(a, a.S, 1, ctl);
   long long mine0, mine1;
   {
@@ -608,7 +622,13 @@ __global__ void __launch_bounds__(kLoopThreads, 1) check_tiles_kernel(const __gr
     lin_warp_reduce<DIM>(terms <= 30, A, mine0, mine1);
   }
   __syncthreads();  // every warp is done with its tiles: the record list is complete
-  if ((int) (threadIdx.x >> 5) < ctl.nrec) loop_search_recs<DIM, FACTOR>(a, ctl, track2, ctl.nrec, ctl.rec);
+  if (ctl.nfail > kFailInPlace) {
+    // many failures (the first check pass after a certification): the work-list kernels search them at full
+    // occupancy -- several rounds of this CTA's 12 warps would only hold the pass up
+    if ((int) threadIdx.x < ctl.nrec) a.work_list[atomicAdd(a.work_count, 1)] = __float_as_int(ctl.rec[threadIdx.x].m.w);
+  } else if ((int) (threadIdx.x >> 5) < ctl.nrec) {
+    loop_search_recs<DIM, FACTOR>(a, ctl, track2, ctl.nrec, ctl.rec);
+  }
   lin_cta_reduce(a.acc, mine0, mine1, ctl.fsm);
   if (threadIdx.x < kAcc && ctl.tail[threadIdx.x]) atomicAdd(&a.acc[threadIdx.x], (unsigned long long) ctl.tail[threadIdx.x]);
 }
@@ -623,6 +643,8 @@ __global__ void __launch_bounds__(kLoopThreads, 1) lin_after_search_kernel(const
   TileStage* stages = reinterpret_cast<TileStage*>(loop_smem_raw);
   __shared__ TileCtl ctl;
   tile_ctl_init(ctl);
+  __syncthreads();
+  if (all) lin_tiles_prologue<false>(a, stages, ctl);
   if (threadIdx.x == 32) make_lin_const(a, a.S, ctl.lk);
   __syncthreads();
   if (all) {
