@@ -181,6 +181,7 @@ struct srrg2b_ctx {
   bool use_graphs = true;  // env SRRG2B_NO_GRAPH=1 disables
   bool graph_nccl = false;  // env SRRG2B_GRAPH_NCCL=1: capture the all-reduce too (experimental: failed the 2-GPU parity test)
   bool eager_index = true;  // env SRRG2B_EAGER_INDEX=0: build the NN index on first use only
+  int full_iters = 4;  // iterations of a run that launch the three-kernel search pipeline (env SRRG2B_FULL_ITERS)
   long long timeout_cycles = 4000000000ll;  // ~2 s of SM clock: the peer exchange gives up (env SRRG2B_TIMEOUT_MS)
   s2b::Mat4f* d_T0 = nullptr;  // initial guess of the current run (read by icp_init_kernel)
   s2b::Mat4f* h_T0 = nullptr;  // pinned staging
@@ -679,7 +680,7 @@ int fill_slice_args(srrg2b_ctx* c, SliceData& sd, int state_slot, const srrg2b_f
   a.far_list = sd.far_list.p; a.far_count = sd.far_count.p;
   a.work_list = sd.work_list.p; a.work_count = sd.far_count.p + 1; a.tile_ticket = sd.far_count.p + 2;
   a.list_all = &c->d_state->list_all[state_slot];
-  a.inline_check = 0; a.use_list = 0;
+  a.inline_check = 0; a.use_list = 0; a.sole_list = 0;
   a.few_terms = 0;
   a.projective = fp.kind == SRRG2B_FINDER_PROJECTIVE ? 1 : 0;
   a.fx = fp.fx; a.fy = fp.fy; a.pcx = fp.cx; a.pcy = fp.cy; a.min_depth = fp.min_depth; a.max_depth = fp.max_depth;
@@ -776,7 +777,12 @@ void launch_tiles_kernel(srrg2b_ctx* c, const SliceArgs& a, int factor, K3P k3p,
 // One pass over a slice inside the ICP loop (R/registration/aligners/aligner_slice_processor_impl.cpp:38-48):
 // coherence check fused with the linearisation when the slice holds certified bounds, then the searches of
 // whatever failed the check (everything, while no bounds exist) and the linearisation of what they found.
-int launch_slice_iteration(srrg2b_ctx* c, const SliceArgs& a0, int factor, const int* skip) {
+// sole: the iteration launches ONE search kernel (nn_far_kernel: short lists warp-per-query, long lists and late full
+// searches thread-per-query, each with its linearisation) instead of nn_kernel + nn_far_kernel +
+// lin_after_search_kernel -- three launches that have nothing to do in a converged iteration, yet cost 6 us of
+// every iteration in the replayed graph (measured at C2).  The first full_iters iterations of a run, which search
+// everything, keep the three-kernel pipeline.
+int launch_slice_iteration(srrg2b_ctx* c, const SliceArgs& a0, int factor, const int* skip, bool sole = false) {
   if (a0.nm <= 0) return SRRG2B_OK;
   if (a0.projective || skip) {  // no coherence machinery for the index-image finder / the groups in front of the loop kernel
     int rcode = launch_find(c, a0, skip);
@@ -787,6 +793,11 @@ int launch_slice_iteration(srrg2b_ctx* c, const SliceArgs& a0, int factor, const
   a.use_list = 1;  // (the work-list counters were zeroed by icp_init_kernel / the previous solve step)
   launch_tiles_kernel(c, a, factor, check_tiles_kernel<3, SRRG2B_FACTOR_P2P>, check_tiles_kernel<3, SRRG2B_FACTOR_PLANE>,
                       check_tiles_kernel<2, SRRG2B_FACTOR_P2P>, check_tiles_kernel<2, SRRG2B_FACTOR_PLANE>);
+  if (sole) {
+    a.sole_list = 1;
+    launch_far(c, a, factor, nullptr);
+    return SRRG2B_OK;
+  }
   launch_nn(c, a, nullptr);
   launch_far(c, a, factor, nullptr);  // phase 2 of long lists, or the whole job for short ones (any R)
   launch_tiles_kernel(c, a, factor, lin_after_search_kernel<3, SRRG2B_FACTOR_P2P>, lin_after_search_kernel<3, SRRG2B_FACTOR_PLANE>,
@@ -915,7 +926,7 @@ int allreduce_acc(srrg2b_ctx* c, int n_slices, bool in_solve_kernel) {
 
 // one _runSolver iteration (multi_aligner_impl.cpp:103-126) as a kernel sequence: full search +
 // linearisation per point slice, then the solve step.  skip: device flag that makes the whole group a no-op.
-int enqueue_iteration_group(srrg2b_ctx* c, const Plan& plan, const int* skip) {
+int enqueue_iteration_group(srrg2b_ctx* c, const Plan& plan, const int* skip, bool sole = false) {
   for (int s = 0; s < plan.solve.n_slices; ++s) {
     if (!plan.is_points[s]) continue;
     if (c->time_kernels) {
@@ -926,7 +937,7 @@ int enqueue_iteration_group(srrg2b_ctx* c, const Plan& plan, const int* skip) {
       }
       CK(c, cudaEventRecord(c->kev[c->kev_used], c->stream));
     }
-    int rcode = launch_slice_iteration(c, plan.sargs[s], plan.factor[s], skip);
+    int rcode = launch_slice_iteration(c, plan.sargs[s], plan.factor[s], skip, sole);
     if (rcode) return rcode;
     if (c->time_kernels) {
       CK(c, cudaEventRecord(c->kev[c->kev_used + 1], c->stream));
@@ -944,7 +955,7 @@ int enqueue_iteration_group(srrg2b_ctx* c, const Plan& plan, const int* skip) {
 // enqueue `iterations` _runSolver iterations; no host sync inside
 int enqueue_iterations(srrg2b_ctx* c, const Plan& plan, int iterations) {
   for (int it = 0; it < iterations; ++it) {
-    const int rcode = enqueue_iteration_group(c, plan, nullptr);
+    const int rcode = enqueue_iteration_group(c, plan, nullptr, it >= c->full_iters);
     if (rcode) return rcode;
   }
   CK(c, cudaGetLastError());
@@ -968,7 +979,7 @@ int run_plan(srrg2b_ctx* c, const Plan& plan, const Mat4f& T0, int iterations, i
     c->launches++;
     return enqueue_iterations(c, plan, iterations);
   }
-  const int tail[6] = {iterations, apply_prior_guess, reset_tc, keep_stats, 0, 0};
+  const int tail[6] = {iterations, apply_prior_guess, reset_tc, keep_stats, c->full_iters, 0};
   // key = everything the launch sequence depends on (slice kernel arguments, factor kinds, counts);
   // the solve-step values are read from device memory and may change freely between replays
   const size_t nb = sizeof(plan.sargs) + sizeof(plan.factor) + sizeof(plan.is_points);
@@ -1128,6 +1139,7 @@ int srrg2b_ctx_create(int dim, int device, srrg2b_ctx** out) {
     if (const char* env = getenv("SRRG2B_TIMEOUT_MS")) ms = std::max(1.0, atof(env));
     c->timeout_cycles = (long long) (ms * (double) khz);
   }
+  if (const char* env = getenv("SRRG2B_FULL_ITERS")) c->full_iters = std::max(0, atoi(env));
   if (const char* env = getenv("SRRG2B_EAGER_INDEX")) c->eager_index = atoi(env) != 0;
   if (const char* env = getenv("SRRG2B_GRAPH_NCCL")) c->graph_nccl = atoi(env) != 0;
   {

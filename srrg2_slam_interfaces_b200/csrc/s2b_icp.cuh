@@ -107,6 +107,7 @@ struct SliceArgs {
   const int* list_all; // device flag: no usable bounds -> the work list is implicitly [0, nm)
   int inline_check;    // 1: nn_kernel does the coherence check itself (stand-alone finder)
   int use_list;        // 1: nn / linearise kernels iterate over the work list
+  int sole_list;       // 1: nn_far_kernel is the ONLY search kernel of this iteration (see launch_slice_iteration)
   int few_terms;       // every thread of the accumulating kernel adds at most 30 terms per slot
   float* c_lb;         // certified lower bound per query PLUS the motion budget at certification (0: none)
   const float* S_lb;   // bound state of the slice (see SolveSlice::S_lb)
@@ -1130,6 +1131,64 @@ __device__ __forceinline__ void lin_push_tail_lane0(const LinAcc<DIM>& A, long l
   if (lane < kAcc - 32 && mine1) atomicAdd(reinterpret_cast<unsigned long long*>(tail + 32 + lane), (unsigned long long) mine1);
 }
 
+// One THREAD per listed query does the whole job: exact search over all rings (nearest ring first, pruned by the
+// best / second-best distance), slot + bound, linearisation.  The fallback of the iterations that launch a single
+// search kernel (sole_list): long work lists and -- list == nullptr -- full searches that turn up late in a run.
+// Slower per query than the phase-1 / phase-2 kernels, but it keeps three kernel launches out of every iteration
+// that does not need them.
+template <int DIM, bool TRACK2, int FACTOR>
+__device__ __forceinline__ void nn_full_lin_body(const SliceArgs& a, const float* S, const int* rows, int K, float cell, int n,
+                                                 const int* list, LinAcc<DIM>& A, const LinConst& lk, FlushSmem& fsm) {
+  int done = 0;
+  // (every thread of a CTA makes the same number of trips: the mid-loop flush below is a CTA-wide barrier)
+  for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+    const int w = base + threadIdx.x;
+    if (w < n) {
+    const int i = list ? *reinterpret_cast<const volatile int*>(list + w) : w;
+    NNQuery q;
+    const float4 m = a.mp[i];
+    nn_setup<DIM>(a, S, m, q);
+    const int old_slot = __ldcg(a.c_fpos + i);
+    const int p0 = slot_candidate(old_slot);
+    if (a.warm && p0 >= 0) { nn_consider<DIM, TRACK2>(a, q, p0); if (TRACK2) nn_limit_bound(q, cell); }
+    for (int k = 0; k < K; ++k) {
+      const int e = rows[k];
+      const int dy = (int) (signed char) (e & 0xff), dz = (int) (signed char) ((e >> 8) & 0xff);
+      const int ring = (e >> 16) & 0xff;
+      const float pr2 = TRACK2 ? q.sd2 : q.bd2;
+      if (ring >= 2) {  // every row of this and later rings is at least (ring - 1) cells away
+        const float g = ((float) (ring - 1) - 4e-3f) * cell;
+        if (g * g > pr2) break;
+      }
+      const int y = q.cy + dy, z = q.cz + dz;
+      if (y < 0 || y >= a.ny || z < 0 || z >= a.nz) continue;
+      const float gy = axis_gap(dy, q.fry) * cell;
+      float lb2 = gy * gy;
+      if (DIM == 3) {
+        const float gz = axis_gap(dz, q.frz) * cell;
+        lb2 = fmaf(gz, gz, lb2);
+      }
+      if (lb2 > pr2) continue;
+      nn_scan_row<DIM, TRACK2>(a, q, y, z, lb2);
+    }
+    const int slot = nn_finish<DIM>(a, S, q, i, TRACK2 ? __fsqrt_rn(q.sd2) * (1.f - 1e-5f) : 0.f, old_slot);
+    const int bpos = a.gate ? slot_candidate(slot) : slot;
+    if (bpos >= 0) {
+      lin_one_slot<DIM, FACTOR>(a, lk, i, slot, bpos, m, a.mn[i], __ldg(a.frec + 2 * (size_t) bpos), __ldg(a.frec + 2 * (size_t) bpos + 1), A);
+      ++done;
+    } else if (a.c_stat) {
+      a.c_stat[i] = SRRG2B_STAT_NONE;
+    }
+    }
+    // 32-bit partial sums: a thread stays below 512 terms per flush
+    if (__syncthreads_or(done >= 400)) {
+      lin_flush<DIM>(a.acc, false, A, fsm);
+      A.clear();
+      done = 0;
+    }
+  }
+}
+
 // Phase 2 / tail kernel.  Large work lists: the far list of phase 1 (see nn_far_body).  Short work
 // lists: one warp per query does the whole job here -- search of all rows, slot + certified bound, and
 // the linearisation of that query.
@@ -1142,7 +1201,8 @@ __global__ void __launch_bounds__(256) nn_far_kernel(const SliceArgs a, const in
   const bool all = !a.use_list || list_all;
   const int n_work = all ? a.nm : work_count;
   const bool tail = small_work_list(a, all, n_work);
-  const int n_far = tail ? n_work : far_count;
+  const bool sole_full = a.sole_list && !tail;  // the only search kernel of the iteration, and the list is long (or everything)
+  const int n_far = (tail || sole_full) ? n_work : far_count;
   if (n_far == 0) return;
   __shared__ float S[16];
   __shared__ int rows[kRowTable];
@@ -1158,6 +1218,15 @@ __global__ void __launch_bounds__(256) nn_far_kernel(const SliceArgs a, const in
   const float cell = __fdiv_rn(1.f, a.inv_cell);
   const bool track2 = track2_flag != 0;
   const int wpb = blockDim.x >> 5, w0 = blockIdx.x * wpb + (threadIdx.x >> 5), ws = gridDim.x * wpb;
+  if (sole_full) {
+    LinAcc<DIM> A;
+    A.clear();
+    const int* list = all ? nullptr : a.work_list;
+    if (track2) nn_full_lin_body<DIM, true, FACTOR>(a, S, rows, K, cell, n_far, list, A, lk, fsm);
+    else nn_full_lin_body<DIM, false, FACTOR>(a, S, rows, K, cell, n_far, list, A, lk, fsm);
+    lin_flush<DIM>(a.acc, false, A, fsm);
+    return;
+  }
   if (!tail) {
     if (track2) nn_far_body<DIM, true>(a, S, rows, K, cell, n_far, a.far_list, nullptr, nullptr, w0, ws);
     else nn_far_body<DIM, false>(a, S, rows, K, cell, n_far, a.far_list, nullptr, nullptr, w0, ws);

@@ -239,11 +239,15 @@ def test_prior_only_reference_kat_on_gpu(oracle, capi):
     ctx.close()
 
 
-@pytest.mark.parametrize("env", [{}, {"SRRG2B_NO_GRAPH": "1"}, {"SRRG2B_TRACK2": "1"}, {"SRRG2B_TRACK2": "0"}])
+@pytest.mark.parametrize("env", [{}, {"SRRG2B_NO_GRAPH": "1"}, {"SRRG2B_TRACK2": "1"}, {"SRRG2B_TRACK2": "0"},
+                                 {"SRRG2B_FULL_ITERS": "0"}, {"SRRG2B_FULL_ITERS": "1", "SRRG2B_TRACK2": "1"},
+                                 {"SRRG2B_FULL_ITERS": "100"}])
 def test_execution_modes_match_oracle(oracle, capi, env, monkeypatch):
     """The same run through every execution mode of the device loop -- CUDA-graph replay (default), plain stream
     launches, bounds certified from the first iteration on (every later iteration is a coherence-check pass) or
-    never (every iteration searches) -- equals the oracle's, bit for bit."""
+    never (every iteration searches: from iteration 5 on through the single-kernel fallback), the single search
+    kernel from the first iteration on (full searches and long work lists thread-per-query), the three-kernel
+    pipeline throughout -- equals the oracle's, bit for bit."""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     d = syn.make_icp3d(30000, 27001, seed=11)
