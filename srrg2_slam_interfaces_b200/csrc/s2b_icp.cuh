@@ -1383,7 +1383,9 @@ __device__ __forceinline__ void solve_stamp(int k) {
 }
 
 template <int DIM>
-__device__ void icp_solve_serial(const SolveArgs& a, DevHeader& st, srrg2b_iter_stats* stats_out) {
+// conv[k][slot]: the accumulators of slice k already converted to double and scaled (done by the whole CTA in
+// parallel: 35 int64 -> fp64 conversions per slice are the slowest part of the assembly when one thread does them)
+__device__ void icp_solve_serial(const SolveArgs& a, DevHeader& st, srrg2b_iter_stats* stats_out, const double (*conv)[kAcc]) {
   constexpr int P = (DIM == 3) ? 6 : 3;
   double H[P * P], b[P];
 #pragma unroll
@@ -1421,21 +1423,19 @@ __device__ void icp_solve_serial(const SolveArgs& a, DevHeader& st, srrg2b_iter_
     for (int i = 0; i < P; ++i) {
 #pragma unroll
       for (int j = i; j < P; ++j) {
-        const double v = __ll2double_rn((long long) acc[slot++]) * sl.invk[(j < DIM) ? kKHtt : ((i < DIM) ? kKHtr : kKHrr)];
+        const double v = conv[k][slot++];
         H[i * P + j] = H[i * P + j] + v;
         if (j != i) H[j * P + i] = H[j * P + i] + v;
       }
     }
 #pragma unroll
     for (int i = 0; i < P; ++i)
-      b[i] = b[i] + __ll2double_rn((long long) acc[kAccB + i]) * sl.invk[(i < DIM) ? kKBt : kKBr];
+      b[i] = b[i] + conv[k][kAccB + i];
     const long long ni = (long long) acc[kAccNIn], no = (long long) acc[kAccNOut], ns = (long long) acc[kAccNSup];
     s.num_inliers += ni; s.num_outliers += no; s.num_suppressed += ns; s.num_correspondences += ni + no + ns;
     s.num_saturated += (long long) acc[kAccNSat];
-    s.chi_inliers += __ll2double_rn((long long) acc[kAccChiIn]) * sl.invk[kKChi] +
-                     __ll2double_rn((long long) acc[kAccChiIn + 1]) * sl.invk[kKChiLo];
-    s.chi_outliers += __ll2double_rn((long long) acc[kAccChiOut]) * sl.invk[kKChi] +
-                      __ll2double_rn((long long) acc[kAccChiOut + 1]) * sl.invk[kKChiLo];
+    s.chi_inliers += conv[k][kAccChiIn] + conv[k][kAccChiIn + 1];
+    s.chi_outliers += conv[k][kAccChiOut] + conv[k][kAccChiOut + 1];
     const long long n = ni + no + ns;
     st.ncorr[k] = n;
     total += n;
@@ -1594,6 +1594,7 @@ struct SolveSmem {
   alignas(16) DevHeader sh;
   PeerExchange pe;
   int timed_out;
+  double conv[SRRG2B_MAX_SLICES][kAcc];  // accumulators as scaled doubles (see icp_solve_serial)
 };
 
 // The solve step of one iteration, executed by ONE CTA with at least kSolveThreads threads (the first
@@ -1675,7 +1676,30 @@ __device__ __forceinline__ bool icp_solve_block(const SolveArgs* ap, DevState* s
     if (a.sl[k].S_lb && tid < 16) a.sl[k].S_lb[tid] = sh.S[k].m[tid];
     if (a.sl[k].counters && tid >= 32 && tid < 35) a.sl[k].counters[tid - 32] = 0;
   }
-  if (tid == 0) { solve_stamp(1); icp_solve_serial<DIM>(a, sh, st->stats); }
+  {
+    // the accumulators as scaled doubles, one (slice, slot) pair per thread
+    constexpr int P = (DIM == 3) ? 6 : 3, NH = P * (P + 1) / 2;
+    __syncthreads();
+    for (int t = tid; t < a.n_slices * kAcc; t += blockDim.x) {
+      const int k = t / kAcc, slot = t - k * kAcc;
+      int cls = -1;
+      if (slot < NH) {
+        int i = 0, rem = slot;  // slot -> (i, j) of the upper triangle, row-major
+        while (rem >= P - i) { rem -= P - i; ++i; }
+        const int j = i + rem;
+        cls = (j < DIM) ? kKHtt : ((i < DIM) ? kKHtr : kKHrr);
+      } else if (slot >= kAccB && slot < kAccB + P) {
+        cls = (slot - kAccB < DIM) ? kKBt : kKBr;
+      } else if (slot == kAccChiIn || slot == kAccChiOut) {
+        cls = kKChi;
+      } else if (slot == kAccChiIn + 1 || slot == kAccChiOut + 1) {
+        cls = kKChiLo;
+      }
+      sm.conv[k][slot] = cls >= 0 ? __ll2double_rn((long long) sh.acc[k][slot]) * a.sl[k].invk[cls] : 0.0;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) { solve_stamp(1); icp_solve_serial<DIM>(a, sh, st->stats, sm.conv); }
   __syncthreads();
   solve_refresh_epochs(a, sh);
   // accumulators restart at zero; everything else goes back as the serial part left it
