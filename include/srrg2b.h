@@ -129,6 +129,18 @@ int srrg2b_comm_init(srrg2b_ctx* ctx, const void* id_128_bytes, int rank, int wo
 /* ---- data: CorrespondenceFinder_::setFixed / setMoving (correspondence_finder.h:80-91) ---- */
 int srrg2b_set_cloud(srrg2b_ctx* ctx, int slot, int slice_id, const srrg2b_cloud* cloud);
 
+/* ---- N1: the local map stays in HBM between frames and is clipped on the device.
+ * Replaces TrackerSliceProcessor_::clip (R/trackers/tracker_slice_processor_impl.cpp:194-205) with a range clipper
+ * behind SceneClipper's contract (R/mapping/scene_clipper.h:104-107: clipped scene in the robot frame + the indices
+ * of its points in the full scene): a valid scene point p is kept iff |T p| <= max_range (T = scene_in_robot,
+ * row-major (dim+1)^2); the kept points T p (normals R n), in ascending scene index, become the MOVING cloud of
+ * `slice_id` without crossing PCIe.  srrg2b_scene_clip_indices returns the scene index of every clipped point
+ * (n_clipped entries): correspondences of the slice carry indices into the clipped cloud. ---- */
+int srrg2b_scene_set(srrg2b_ctx* ctx, int scene_id, const srrg2b_cloud* cloud);
+int srrg2b_scene_clip(srrg2b_ctx* ctx, int scene_id, int slice_id, const float* scene_in_robot, float max_range,
+                      int64_t* n_clipped);
+int srrg2b_scene_clip_indices(srrg2b_ctx* ctx, int slice_id, int32_t* global_indices);
+
 /* ---- a3: CorrespondenceFinder_::compute() (correspondence_finder.h:56). S = local_map_in_sensor
  * (:111-114). Output: ascending moving_idx, at most one entry per moving point; buffers must hold
  * n_moving entries; any of them may be NULL. */

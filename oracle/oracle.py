@@ -117,6 +117,8 @@ def lib():
         _lib.orc_log.restype = C.c_double
         _lib.orc_log.argtypes = [C.c_double]
         _lib.orc_solve_update.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.orc_scene_clip.restype = C.c_int64
+        _lib.orc_scene_clip.argtypes = [C.c_int, C.POINTER(Cloud), C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
     return _lib
 
 
@@ -304,3 +306,15 @@ def mat_op(name, dim, *mats):
     f.argtypes = [C.c_int] + [C.c_void_p] * (len(ms) + 1)
     f(dim, *[m.ctypes.data for m in ms], out.ctypes.data)
     return out
+
+
+def scene_clip(scene, T, max_range):
+    """Range clip of a resident scene: (coords, normals | None, global_indices) of the kept points."""
+    dim = scene.dim
+    D1 = dim + 1
+    T = np.ascontiguousarray(np.asarray(T, dtype=np.float32).reshape(D1, D1))
+    oc = np.empty((scene.n, dim), dtype=np.float32)
+    on = np.empty((scene.n, dim), dtype=np.float32) if scene.normals is not None else None
+    gi = np.empty(scene.n, dtype=np.int32)
+    k = lib().orc_scene_clip(dim, C.byref(scene.c), T.ctypes.data, float(max_range), oc.ctypes.data, _ptr(on), gi.ctypes.data)
+    return oc[:k].copy(), (None if on is None else on[:k].copy()), gi[:k].copy()

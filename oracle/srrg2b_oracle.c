@@ -448,6 +448,40 @@ static inline void xf_dir(const float* S4, const float* n, float* o) {
   }
 }
 
+/* N1: the clip of the tracker slice, TrackerSliceProcessor_::clip
+ * (R/trackers/tracker_slice_processor_impl.cpp:194-205) -> SceneClipper::compute, whose contract is
+ * "clipped scene in the robot frame + the indices of its points in the full scene" (R/mapping/scene_clipper.h:104-107;
+ * the concrete clippers live in srrg2_laser_slam_2d / srrg2_proslam, not in the tree).  Range clipper: a scene point
+ * is kept iff it is valid and |T p| <= max_range (T = scene in robot); the kept point is T p, its normal R n; order =
+ * ascending scene index.  fp32, operation order as in the finder's query transform.  Returns the number kept. */
+int64_t orc_scene_clip(int dim, const orc_cloud* scene, const float* T, float max_range, float* out_coords, float* out_normals,
+                       int32_t* global_indices) {
+  float T4[16];
+  embed4(dim, T, T4);
+  const float r2 = max_range * max_range;
+  int64_t k = 0;
+  for (int64_t i = 0; i < scene->n; ++i) {
+    if (scene->valid && !scene->valid[i]) continue;
+    float m[3], q[3];
+    get3(scene->coords, dim, i, m);
+    xf_point(T4, m, q);
+    float d2 = fmaf(q[1], q[1], q[0] * q[0]);
+    if (dim == 3) d2 = fmaf(q[2], q[2], d2);
+    if (!(d2 <= r2)) continue;
+    for (int c = 0; c < dim; ++c) out_coords[k * dim + c] = q[c];
+    if (scene->normals && out_normals) {
+      float n[3], o[3];
+      get3(scene->normals, dim, i, n);
+      xf_dir(T4, n, o);
+      for (int c = 0; c < dim; ++c) out_normals[k * dim + c] = o[c];
+    }
+    if (global_indices) global_indices[k] = (int32_t) i;
+    ++k;
+  }
+  return k;
+}
+
+
 static inline float dist2(const float* q, const float* f) {
   float dx = q[0] - f[0], dy = q[1] - f[1], dz = q[2] - f[2];
   return fmaf(dz, dz, fmaf(dy, dy, dx * dx));

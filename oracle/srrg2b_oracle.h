@@ -140,6 +140,9 @@ void orc_t2v(int dim, const float* T, float* v);
 void orc_v2t(int dim, int variable, const float* v, float* T);
 void orc_mul(int dim, const float* A, const float* B, float* C);
 void orc_inverse(int dim, const float* A, float* Ainv);
+/* N1: range clip of a resident scene (see the .c file); returns the number of points kept */
+int64_t orc_scene_clip(int dim, const orc_cloud* scene, const float* T, float max_range, float* out_coords, float* out_normals,
+                       int32_t* global_indices);
 int orc_solve_update(int dim, int variable, const double* H, const double* b, float* T);
 
 #ifdef __cplusplus

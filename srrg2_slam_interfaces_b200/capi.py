@@ -22,7 +22,7 @@ MAX_SLICES = 8
 
 EXPORTED_SYMBOLS = [
     "srrg2b_version", "srrg2b_ctx_create", "srrg2b_ctx_destroy", "srrg2b_last_error", "srrg2b_stream",
-    "srrg2b_launch_count", "srrg2b_comm_unique_id", "srrg2b_comm_init", "srrg2b_set_cloud",
+    "srrg2b_launch_count", "srrg2b_comm_unique_id", "srrg2b_comm_init", "srrg2b_set_cloud", "srrg2b_scene_set", "srrg2b_scene_clip", "srrg2b_scene_clip_indices",
     "srrg2b_find_correspondences", "srrg2b_set_correspondences", "srrg2b_linearize", "srrg2b_icp_run",
     "srrg2b_icp_iterate", "srrg2b_get_correspondences", "srrg2b_reset_correspondences", "srrg2b_last_run_timing",
     "srrg2b_set_kernel_timing", "srrg2b_last_kernel_timing", "srrg2b_debug_info",
@@ -120,6 +120,9 @@ def load_library():
     lib.srrg2b_icp_iterate.argtypes = [vp, C.c_int, C.POINTER(Slice), C.c_int, vp, C.POINTER(IterStats), i32p]
     lib.srrg2b_get_correspondences.argtypes = [vp, C.c_int, vp, vp, vp, i64p]
     lib.srrg2b_reset_correspondences.argtypes = [vp, C.c_int]
+    lib.srrg2b_scene_set.argtypes = [vp, C.c_int, C.POINTER(Cloud)]
+    lib.srrg2b_scene_clip.argtypes = [vp, C.c_int, C.c_int, vp, C.c_float, i64p]
+    lib.srrg2b_scene_clip_indices.argtypes = [vp, C.c_int, vp]
     lib.srrg2b_last_run_timing.argtypes = [vp, C.POINTER(C.c_float), i32p]
     lib.srrg2b_debug_info.argtypes = [vp, C.c_int, vp]
     lib.srrg2b_pgo_upload.argtypes = [vp, C.c_int64, vp, vp, C.c_int64, vp, vp, vp]
@@ -236,6 +239,28 @@ class Context:
         valid = None if valid is None else np.ascontiguousarray(valid, dtype=np.uint8)
         cl = Cloud(_ptr(coords), _ptr(normals), _ptr(valid), coords.shape[0], index_offset, n_global, 0, 0)
         self._check(self.lib.srrg2b_set_cloud(self.h, slot, slice_id, C.byref(cl)))
+
+    # ---- N1: device-resident local map, clipped on the device ----
+    def scene_set(self, scene_id, coords, normals=None, valid=None):
+        coords = np.ascontiguousarray(coords, dtype=np.float32)
+        normals = None if normals is None else np.ascontiguousarray(normals, dtype=np.float32)
+        valid = None if valid is None else np.ascontiguousarray(valid, dtype=np.uint8)
+        cl = Cloud(_ptr(coords), _ptr(normals), _ptr(valid), coords.shape[0], 0, 0, 0, 0)
+        self._check(self.lib.srrg2b_scene_set(self.h, scene_id, C.byref(cl)))
+
+    def scene_clip(self, scene_id, slice_id, scene_in_robot, max_range):
+        """Clips the resident scene into the MOVING cloud of slice_id; returns the number of points kept."""
+        T = np.ascontiguousarray(np.asarray(scene_in_robot, dtype=np.float32).reshape(-1))
+        n = C.c_int64(0)
+        self._check(self.lib.srrg2b_scene_clip(self.h, scene_id, slice_id, T.ctypes.data, float(max_range), C.byref(n)))
+        self._clip_n = getattr(self, "_clip_n", {})
+        self._clip_n[slice_id] = n.value
+        return n.value
+
+    def scene_clip_indices(self, slice_id):
+        out = np.empty(self._clip_n[slice_id], dtype=np.int32)
+        self._check(self.lib.srrg2b_scene_clip_indices(self.h, slice_id, out.ctypes.data))
+        return out
 
     def set_cloud_device(self, slot, slice_id, coords_ptr, normals_ptr, valid_ptr, n, index_offset=0, n_global=0):
         cl = Cloud(coords_ptr, normals_ptr, valid_ptr, n, index_offset, n_global, 1, 0)

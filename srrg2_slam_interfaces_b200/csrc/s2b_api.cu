@@ -95,6 +95,9 @@ struct SliceData {
   DevBuf<float4> f_pts, f_rec;  // compact points (searches) / 32-byte {point | normal} records (lineariser gathers)
   DevBuf<int> f_inverse, cell_start;
   DevBuf<unsigned> near_bits;
+  DevBuf<float> clip_xyz, clip_nrm;  // N1: the clipped scene this slice's moving cloud was built from
+  DevBuf<int> clip_gidx;             // ... and the indices of its points in the full scene
+  int64_t n_clipped = 0;
   int nf_valid = 0;
   float built_for_max_distance = -1.f;
   float ox = 0, oy = 0, oz = 0, inv_cell = 1;
@@ -139,6 +142,7 @@ struct srrg2b_ctx {
   std::string err;
   int64_t launches = 0;
   std::map<int, SliceData> slices;
+  std::map<int, RawCloud> scenes;  // N1: local maps resident in HBM between frames (srrg2b_scene_set / _clip)
   DevState* d_state = nullptr;
   DevState* h_state = nullptr;  // pinned mirror (header part is copied back)
   // scratch
@@ -1355,6 +1359,81 @@ int srrg2b_set_cloud(srrg2b_ctx* c, int slot, int slice_id, const srrg2b_cloud* 
   rcode = build_moving(c, sd);
   CK(c, cudaStreamSynchronize(c->copy_stream));
   if (rcode) return rcode;
+  CK(c, cudaStreamSynchronize(c->stream));
+  return SRRG2B_OK;
+}
+
+// ---- N1: device-resident scene, clipped on the device into a slice's moving cloud ----
+int srrg2b_scene_set(srrg2b_ctx* c, int scene_id, const srrg2b_cloud* cl) {
+  if (!c) return SRRG2B_ERR_INVALID;
+  if (!cl || cl->n < 0 || (cl->n > 0 && !cl->coords) || cl->n > 0x7fffffff00ll / 16) FAIL(c, SRRG2B_ERR_INVALID, "bad cloud descriptor");
+  CK(c, cudaSetDevice(c->device));
+  CK(c, cudaStreamSynchronize(c->stream));  // a clip of the previous scene may still be running
+  const int rcode = upload_raw(c, c->scenes[scene_id], cl);
+  CK(c, cudaStreamSynchronize(c->copy_stream));
+  return rcode;
+}
+
+int srrg2b_scene_clip(srrg2b_ctx* c, int scene_id, int slice_id, const float* scene_in_robot, float max_range, int64_t* n_clipped) {
+  if (!c) return SRRG2B_ERR_INVALID;
+  if (!scene_in_robot || !(max_range > 0.f)) FAIL(c, SRRG2B_ERR_INVALID, "bad clip arguments");
+  if (!c->scenes.count(scene_id) || !c->scenes[scene_id].present) FAIL(c, SRRG2B_ERR_STATE, "unknown scene");
+  CK(c, cudaSetDevice(c->device));
+  RawCloud& sc = c->scenes[scene_id];
+  SliceData& sd = c->slices[slice_id];
+  const int n = (int) sc.n, dim = c->dim;
+  Mat4f T;
+  embed(dim, scene_in_robot, T);
+  if (!rigid_enough(dim, scene_in_robot)) FAIL(c, SRRG2B_ERR_INVALID, "scene_in_robot is not a rigid transform");
+  int kept = 0;
+  if (n > 0) {
+    CK(c, c->flags.ensure(n));
+    CK(c, c->positions.ensure(n));
+    const float r2 = max_range * max_range;
+    const unsigned char* valid = sc.has_valid ? sc.valid.p : nullptr;
+    if (dim == 3) scene_clip_flag_kernel<3><<<blocks_for(n, 256), 256, 0, c->stream>>>(sc.xyz.p, valid, n, T, r2, c->flags.p);
+    else scene_clip_flag_kernel<2><<<blocks_for(n, 256), 256, 0, c->stream>>>(sc.xyz.p, valid, n, T, r2, c->flags.p);
+    size_t bytes = 0;
+    CK(c, cub::DeviceScan::ExclusiveSum(nullptr, bytes, c->flags.p, c->positions.p, n, c->stream));
+    CK(c, c->cub_tmp.ensure(bytes));
+    CK(c, cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, bytes, c->flags.p, c->positions.p, n, c->stream));
+    int last_flag = 0, last_pos = 0;
+    CK(c, cudaMemcpyAsync(&last_flag, c->flags.p + (n - 1), 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaMemcpyAsync(&last_pos, c->positions.p + (n - 1), 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    kept = last_pos + last_flag;
+    CK(c, sd.clip_xyz.ensure((size_t) std::max(kept, 1) * dim));
+    CK(c, sd.clip_nrm.ensure((size_t) std::max(kept, 1) * dim));
+    CK(c, sd.clip_gidx.ensure((size_t) std::max(kept, 1)));
+    const float* nrm = sc.has_normals ? sc.nrm.p : nullptr;
+    if (dim == 3) scene_clip_compact_kernel<3><<<blocks_for(n, 256), 256, 0, c->stream>>>(sc.xyz.p, nrm, c->flags.p, c->positions.p, n, T,
+                                                                                       sd.clip_xyz.p, sd.clip_nrm.p, sd.clip_gidx.p);
+    else scene_clip_compact_kernel<2><<<blocks_for(n, 256), 256, 0, c->stream>>>(sc.xyz.p, nrm, c->flags.p, c->positions.p, n, T,
+                                                                                  sd.clip_xyz.p, sd.clip_nrm.p, sd.clip_gidx.p);
+    c->launches += 2;
+    CK(c, cudaGetLastError());
+    CK(c, cudaStreamSynchronize(c->stream));  // the moving-cloud path below copies on the copy stream
+  }
+  sd.n_clipped = kept;
+  if (n_clipped) *n_clipped = kept;
+  // the clipped scene becomes the slice's moving cloud without leaving the device
+  srrg2b_cloud cl;
+  memset(&cl, 0, sizeof(cl));
+  cl.coords = sd.clip_xyz.p;
+  cl.normals = sc.has_normals ? sd.clip_nrm.p : nullptr;
+  cl.n = kept;
+  cl.on_device = 1;
+  if (kept == 0) { static const float dummy = 0.f; cl.coords = &dummy; cl.on_device = 0; }
+  return srrg2b_set_cloud(c, SRRG2B_MOVING, slice_id, &cl);
+}
+
+int srrg2b_scene_clip_indices(srrg2b_ctx* c, int slice_id, int32_t* global_indices) {
+  if (!c) return SRRG2B_ERR_INVALID;
+  if (!c->slices.count(slice_id) || !global_indices) FAIL(c, SRRG2B_ERR_STATE, "unknown slice");
+  CK(c, cudaSetDevice(c->device));
+  SliceData& sd = c->slices[slice_id];
+  if (sd.n_clipped > 0)
+    CK(c, cudaMemcpyAsync(global_indices, sd.clip_gidx.p, sizeof(int32_t) * (size_t) sd.n_clipped, cudaMemcpyDeviceToHost, c->stream));
   CK(c, cudaStreamSynchronize(c->stream));
   return SRRG2B_OK;
 }

@@ -1725,6 +1725,54 @@ __global__ void __launch_bounds__(kSolveThreads) icp_solve_kernel(const SolveArg
 }
 
 // ---------------------------------------------------------------------------------------------
+// N1: the clip of the tracker slice on the device.  TrackerSliceProcessor_::clip
+// (R/trackers/tracker_slice_processor_impl.cpp:194-205) hands the full scene to a SceneClipper, whose contract is
+// "clipped scene in the robot frame + the indices of its points in the full scene" (R/mapping/scene_clipper.h:104-107).
+// Range clipper: keep a valid scene point iff |T p| <= max_range; output T p, R n in ascending scene index.
+// Two passes around a CUB exclusive scan: flag, then transform + compact.
+// ---------------------------------------------------------------------------------------------
+template <int DIM>
+__global__ void scene_clip_flag_kernel(const float* __restrict__ xyz, const unsigned char* __restrict__ valid, int n, Mat4f T,
+                                       float r2, int* __restrict__ flag) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int keep = 0;
+  if (!valid || valid[i]) {
+    const float4 m = make_float4(xyz[(size_t) i * DIM], xyz[(size_t) i * DIM + 1], DIM == 3 ? xyz[(size_t) i * DIM + 2] : 0.f, 0.f);
+    float qx, qy, qz;
+    nn_transform<DIM>(T.m, m, qx, qy, qz);
+    float d2 = fmaf(qy, qy, qx * qx);
+    if (DIM == 3) d2 = fmaf(qz, qz, d2);
+    keep = d2 <= r2 ? 1 : 0;
+  }
+  flag[i] = keep;
+}
+
+template <int DIM>
+__global__ void scene_clip_compact_kernel(const float* __restrict__ xyz, const float* __restrict__ nrm, const int* __restrict__ flag,
+                                          const int* __restrict__ pos, int n, Mat4f T, float* __restrict__ out_xyz,
+                                          float* __restrict__ out_nrm, int* __restrict__ gidx) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || !flag[i]) return;
+  const int k = pos[i];
+  const float* S = T.m;
+  const float4 m = make_float4(xyz[(size_t) i * DIM], xyz[(size_t) i * DIM + 1], DIM == 3 ? xyz[(size_t) i * DIM + 2] : 0.f, 0.f);
+  float qx, qy, qz;
+  nn_transform<DIM>(S, m, qx, qy, qz);
+  out_xyz[(size_t) k * DIM] = qx;
+  out_xyz[(size_t) k * DIM + 1] = qy;
+  if (DIM == 3) out_xyz[(size_t) k * DIM + 2] = qz;
+  if (nrm) {
+    const float nx = nrm[(size_t) i * DIM], ny = nrm[(size_t) i * DIM + 1], nz = DIM == 3 ? nrm[(size_t) i * DIM + 2] : 0.f;
+    float t;
+    t = S[0] * nx; t = fmaf(S[1], ny, t); if (DIM == 3) t = fmaf(S[2], nz, t); out_nrm[(size_t) k * DIM] = t;
+    t = S[4] * nx; t = fmaf(S[5], ny, t); if (DIM == 3) t = fmaf(S[6], nz, t); out_nrm[(size_t) k * DIM + 1] = t;
+    if (DIM == 3) { t = S[8] * nx; t = fmaf(S[9], ny, t); t = fmaf(S[10], nz, t); out_nrm[(size_t) k * DIM + 2] = t; }
+  }
+  gidx[k] = i;
+}
+
+// ---------------------------------------------------------------------------------------------
 // k2b: export (sorted order -> dense by local moving index), then compaction
 // ---------------------------------------------------------------------------------------------
 __global__ void export_dense_kernel(const float4* __restrict__ mp, const float4* __restrict__ fp,
