@@ -141,6 +141,27 @@ int srrg2b_scene_clip(srrg2b_ctx* ctx, int scene_id, int slice_id, const float* 
                       int64_t* n_clipped);
 int srrg2b_scene_clip_indices(srrg2b_ctx* ctx, int slice_id, int32_t* global_indices);
 
+/* ---- N2: MergerCorrespondenceHomo_::compute() (R/mapping/merger_correspondence_homo_impl.cpp:11-126)
+ * on the resident scene.  The measurement is the FIXED cloud of `slice_id` (the new scan, already on the device), the
+ * correspondences are the ones the aligner left in that slice -- flipped and mapped to the global scene through the
+ * clip's indices, as R/trackers/tracker_slice_processor_impl.cpp:159-191 does on the host -- so nothing crosses PCIe.
+ * For every correspondence with response < maximum_response whose points lie closer than
+ * sqrt(maximum_distance_geometry_squared) in the scene frame, the scene point takes the measurement point's fields and
+ * the mid-point as coordinates; if fewer than target_number_of_merges DISTINCT measurement points were merged, the
+ * valid unmerged ones are appended (transformed into the scene frame).  without_correspondences = 1: the
+ * "no correspondences set" branch (:31-42, first frame of a local map): every valid measurement point is appended.
+ * Parameter names and defaults: merger_correspondence_homo.h:22-31, merger.h:126-131. ---- */
+typedef struct {
+  float maximum_response;                    /* 50 */
+  float maximum_distance_geometry_squared;   /* 0.25 */
+  int32_t target_number_of_merges;           /* 200 */
+  int32_t without_correspondences;           /* 0 */
+} srrg2b_merge_params;
+int srrg2b_scene_merge(srrg2b_ctx* ctx, int scene_id, int slice_id, const float* measurement_in_scene,
+                       const srrg2b_merge_params* params, int64_t* n_merged, int64_t* n_added);
+/* the resident scene back on the host (map serialisation, tests); any output pointer may be NULL; *n = its size */
+int srrg2b_scene_get(srrg2b_ctx* ctx, int scene_id, float* coords, float* normals, uint8_t* valid, int64_t* n);
+
 /* ---- a3: CorrespondenceFinder_::compute() (correspondence_finder.h:56). S = local_map_in_sensor
  * (:111-114). Output: ascending moving_idx, at most one entry per moving point; buffers must hold
  * n_moving entries; any of them may be NULL. */

@@ -117,6 +117,10 @@ def lib():
         _lib.orc_log.restype = C.c_double
         _lib.orc_log.argtypes = [C.c_double]
         _lib.orc_solve_update.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.orc_scene_merge.restype = C.c_int64
+        _lib.orc_scene_merge.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(Cloud), C.c_void_p, C.c_int64,
+                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_int64,
+                                         C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         _lib.orc_scene_clip.restype = C.c_int64
         _lib.orc_scene_clip.argtypes = [C.c_int, C.POINTER(Cloud), C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
     return _lib
@@ -318,3 +322,31 @@ def scene_clip(scene, T, max_range):
     gi = np.empty(scene.n, dtype=np.int32)
     k = lib().orc_scene_clip(dim, C.byref(scene.c), T.ctypes.data, float(max_range), oc.ctypes.data, _ptr(on), gi.ctypes.data)
     return oc[:k].copy(), (None if on is None else on[:k].copy()), gi[:k].copy()
+
+
+def scene_merge(scene_coords, scene_normals, scene_valid, meas, T, corr=None, maximum_response=50.0,
+                maximum_distance_geometry_squared=0.25, target_number_of_merges=200):
+    """MergerCorrespondenceHomo_::compute (SURVEY 8f N2).  corr = (scene_idx, meas_idx, response) arrays or None (no
+    correspondences set).  Returns (coords, normals | None, valid | None, n_merged, n_added) of the merged scene."""
+    dim = meas.dim
+    D1 = dim + 1
+    T = np.ascontiguousarray(np.asarray(T, dtype=np.float32).reshape(D1, D1))
+    ns = scene_coords.shape[0]
+    cap = ns + meas.n
+    sc = np.zeros((cap, dim), np.float32); sc[:ns] = scene_coords
+    sn = None
+    if scene_normals is not None:
+        sn = np.zeros((cap, dim), np.float32); sn[:ns] = scene_normals
+    sv = None
+    if scene_valid is not None:
+        sv = np.zeros(cap, np.uint8); sv[:ns] = scene_valid
+    nm, na = C.c_int64(0), C.c_int64(0)
+    if corr is None:
+        n = lib().orc_scene_merge(dim, sc.ctypes.data, _ptr(sn), _ptr(sv), ns, C.byref(meas.c), T.ctypes.data, -1, None, None, None,
+                                  maximum_response, maximum_distance_geometry_squared, target_number_of_merges, C.byref(nm), C.byref(na))
+    else:
+        cs = np.ascontiguousarray(corr[0], np.int32); cm = np.ascontiguousarray(corr[1], np.int32); cr = np.ascontiguousarray(corr[2], np.float32)
+        n = lib().orc_scene_merge(dim, sc.ctypes.data, _ptr(sn), _ptr(sv), ns, C.byref(meas.c), T.ctypes.data, cs.shape[0], cs.ctypes.data,
+                                  cm.ctypes.data, cr.ctypes.data, maximum_response, maximum_distance_geometry_squared,
+                                  target_number_of_merges, C.byref(nm), C.byref(na))
+    return sc[:n], (None if sn is None else sn[:n]), (None if sv is None else sv[:n]), nm.value, na.value

@@ -481,6 +481,68 @@ int64_t orc_scene_clip(int dim, const orc_cloud* scene, const float* T, float ma
   return k;
 }
 
+/* N2: MergerCorrespondenceHomo_::compute(), R/mapping/merger_correspondence_homo_impl.cpp:11-126, on
+ * flat arrays.  corr_scene / corr_meas / corr_resp: the correspondences as the tracker hands them over -- flipped and
+ * mapped to the global scene (R/trackers/tracker_slice_processor_impl.cpp:159-191): (scene index, measurement index,
+ * response).  n_corr < 0: "no correspondences set" (:31-42, the initial frame): every valid measurement point is
+ * appended.  The scene arrays must hold n_scene + n_meas points.  Arithmetic (upstream: Eigen fp32, order unpinned):
+ * q = T m in the finder's operation order, d2 = fma chain, merged coordinates (q + s) * 0.5; a merged scene point takes
+ * the measurement point's other fields as they are -- its normal is NOT rotated (:71 copies the point, :74 overwrites
+ * only the coordinates) --, appended points are transformed in place (coordinates and normal, :112-113).
+ * Returns the new scene size. */
+int64_t orc_scene_merge(int dim, float* scene_coords, float* scene_normals, uint8_t* scene_valid, int64_t n_scene,
+                        const orc_cloud* meas, const float* T, int64_t n_corr, const int32_t* corr_scene, const int32_t* corr_meas,
+                        const float* corr_resp, float maximum_response, float maximum_distance_geometry_squared,
+                        int64_t target_number_of_merges, int64_t* n_merged_out, int64_t* n_added_out) {
+  float T4[16];
+  embed4(dim, T, T4);
+  uint8_t* merged = (uint8_t*) calloc((size_t) (meas->n > 0 ? meas->n : 1), 1);
+  int64_t n_merged = 0, n_added = 0, n = n_scene;
+  int append = 1;
+  if (n_corr >= 0) {
+    for (int64_t c = 0; c < n_corr; ++c) {
+      const int64_t g = corr_scene[c], j = corr_meas[c];
+      if (!(corr_resp[c] < maximum_response)) continue;
+      float m[3], q[3], sp[3];
+      get3(meas->coords, dim, j, m);
+      xf_point(T4, m, q);
+      get3(scene_coords, dim, g, sp);
+      const float dx = q[0] - sp[0], dy = q[1] - sp[1], dz = q[2] - sp[2];
+      float d2 = fmaf(dy, dy, dx * dx);
+      if (dim == 3) d2 = fmaf(dz, dz, d2);
+      if (!(d2 < maximum_distance_geometry_squared)) continue;
+      for (int k = 0; k < dim; ++k) {
+        scene_coords[g * dim + k] = (q[k] + sp[k]) * 0.5f;
+        if (scene_normals && meas->normals) scene_normals[g * dim + k] = meas->normals[j * dim + k];
+      }
+      if (!merged[j]) { merged[j] = 1; ++n_merged; }
+    }
+    append = n_merged < target_number_of_merges;
+  }
+  if (append) {
+    for (int64_t j = 0; j < meas->n; ++j) {
+      if (merged[j] || (meas->valid && !meas->valid[j])) continue;
+      float m[3], q[3];
+      get3(meas->coords, dim, j, m);
+      xf_point(T4, m, q);
+      for (int k = 0; k < dim; ++k) scene_coords[n * dim + k] = q[k];
+      if (scene_normals && meas->normals) {
+        float nn[3], o[3];
+        get3(meas->normals, dim, j, nn);
+        xf_dir(T4, nn, o);
+        for (int k = 0; k < dim; ++k) scene_normals[n * dim + k] = o[k];
+      }
+      if (scene_valid) scene_valid[n] = 1;
+      ++n; ++n_added;
+    }
+  }
+  free(merged);
+  if (n_merged_out) *n_merged_out = n_merged;
+  if (n_added_out) *n_added_out = n_added;
+  return n;
+}
+
+
 
 static inline float dist2(const float* q, const float* f) {
   float dx = q[0] - f[0], dy = q[1] - f[1], dz = q[2] - f[2];

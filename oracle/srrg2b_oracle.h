@@ -140,6 +140,11 @@ void orc_t2v(int dim, const float* T, float* v);
 void orc_v2t(int dim, int variable, const float* v, float* T);
 void orc_mul(int dim, const float* A, const float* B, float* C);
 void orc_inverse(int dim, const float* A, float* Ainv);
+/* N2: MergerCorrespondenceHomo_::compute() on flat arrays (see the .c file); returns the new scene size */
+int64_t orc_scene_merge(int dim, float* scene_coords, float* scene_normals, uint8_t* scene_valid, int64_t n_scene,
+                        const orc_cloud* meas, const float* T, int64_t n_corr, const int32_t* corr_scene, const int32_t* corr_meas,
+                        const float* corr_resp, float maximum_response, float maximum_distance_geometry_squared,
+                        int64_t target_number_of_merges, int64_t* n_merged_out, int64_t* n_added_out);
 /* N1: range clip of a resident scene (see the .c file); returns the number of points kept */
 int64_t orc_scene_clip(int dim, const orc_cloud* scene, const float* T, float max_range, float* out_coords, float* out_normals,
                        int32_t* global_indices);

@@ -22,7 +22,7 @@ MAX_SLICES = 8
 
 EXPORTED_SYMBOLS = [
     "srrg2b_version", "srrg2b_ctx_create", "srrg2b_ctx_destroy", "srrg2b_last_error", "srrg2b_stream",
-    "srrg2b_launch_count", "srrg2b_comm_unique_id", "srrg2b_comm_init", "srrg2b_set_cloud", "srrg2b_scene_set", "srrg2b_scene_clip", "srrg2b_scene_clip_indices",
+    "srrg2b_launch_count", "srrg2b_comm_unique_id", "srrg2b_comm_init", "srrg2b_set_cloud", "srrg2b_scene_set", "srrg2b_scene_clip", "srrg2b_scene_clip_indices", "srrg2b_scene_merge", "srrg2b_scene_get",
     "srrg2b_find_correspondences", "srrg2b_set_correspondences", "srrg2b_linearize", "srrg2b_icp_run",
     "srrg2b_icp_iterate", "srrg2b_get_correspondences", "srrg2b_reset_correspondences", "srrg2b_last_run_timing",
     "srrg2b_set_kernel_timing", "srrg2b_last_kernel_timing", "srrg2b_debug_info",
@@ -79,6 +79,11 @@ class PgoStats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class MergeParams(C.Structure):
+    _fields_ = [("maximum_response", C.c_float), ("maximum_distance_geometry_squared", C.c_float),
+                ("target_number_of_merges", C.c_int32), ("without_correspondences", C.c_int32)]
+
+
 class AlignerParams(C.Structure):
     _fields_ = [("variable", C.c_int32), ("max_iterations", C.c_int32), ("min_num_inliers", C.c_int32),
                 ("enable_inlier_only_runs", C.c_int32), ("keep_only_inlier_correspondences", C.c_int32),
@@ -123,6 +128,8 @@ def load_library():
     lib.srrg2b_scene_set.argtypes = [vp, C.c_int, C.POINTER(Cloud)]
     lib.srrg2b_scene_clip.argtypes = [vp, C.c_int, C.c_int, vp, C.c_float, i64p]
     lib.srrg2b_scene_clip_indices.argtypes = [vp, C.c_int, vp]
+    lib.srrg2b_scene_merge.argtypes = [vp, C.c_int, C.c_int, vp, C.POINTER(MergeParams), i64p, i64p]
+    lib.srrg2b_scene_get.argtypes = [vp, C.c_int, vp, vp, vp, i64p]
     lib.srrg2b_last_run_timing.argtypes = [vp, C.POINTER(C.c_float), i32p]
     lib.srrg2b_debug_info.argtypes = [vp, C.c_int, vp]
     lib.srrg2b_pgo_upload.argtypes = [vp, C.c_int64, vp, vp, C.c_int64, vp, vp, vp]
@@ -261,6 +268,24 @@ class Context:
         out = np.empty(self._clip_n[slice_id], dtype=np.int32)
         self._check(self.lib.srrg2b_scene_clip_indices(self.h, slice_id, out.ctypes.data))
         return out
+
+    def scene_merge(self, scene_id, slice_id, measurement_in_scene, maximum_response=50.0, maximum_distance_geometry_squared=0.25,
+                    target_number_of_merges=200, without_correspondences=False):
+        """MergerCorrespondenceHomo_::compute on the resident scene; returns (n_merged, n_added)."""
+        T = np.ascontiguousarray(np.asarray(measurement_in_scene, dtype=np.float32).reshape(-1))
+        mp = MergeParams(maximum_response, maximum_distance_geometry_squared, target_number_of_merges, int(without_correspondences))
+        a, b = C.c_int64(0), C.c_int64(0)
+        self._check(self.lib.srrg2b_scene_merge(self.h, scene_id, slice_id, T.ctypes.data, C.byref(mp), C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def scene_get(self, scene_id, normals=True, valid=False):
+        n = C.c_int64(0)
+        self._check(self.lib.srrg2b_scene_get(self.h, scene_id, None, None, None, C.byref(n)))
+        co = np.empty((n.value, self.dim), np.float32)
+        no = np.empty((n.value, self.dim), np.float32) if normals else None
+        va = np.empty(n.value, np.uint8) if valid else None
+        self._check(self.lib.srrg2b_scene_get(self.h, scene_id, co.ctypes.data, _ptr(no), _ptr(va), C.byref(n)))
+        return co, no, va
 
     def set_cloud_device(self, slot, slice_id, coords_ptr, normals_ptr, valid_ptr, n, index_offset=0, n_global=0):
         cl = Cloud(coords_ptr, normals_ptr, valid_ptr, n, index_offset, n_global, 1, 0)

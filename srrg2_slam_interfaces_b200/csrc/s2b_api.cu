@@ -73,6 +73,22 @@ struct DevBuf {
   }
 };
 
+// a device buffer that keeps its first `used` elements when it grows (the resident scene is appended to)
+template <typename T>
+cudaError_t grow_preserve(DevBuf<T>& b, size_t used, size_t need, cudaStream_t st) {
+  if (need <= b.cap) return cudaSuccess;
+  const size_t cap = std::max(need, b.cap + b.cap / 2);
+  T* np_ = nullptr;
+  cudaError_t e = cudaMalloc((void**) &np_, sizeof(T) * (cap ? cap : 1));
+  if (e != cudaSuccess) return e;
+  if (b.p && used) e = cudaMemcpyAsync(np_, b.p, sizeof(T) * used, cudaMemcpyDeviceToDevice, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (b.p) cudaFree(b.p);
+  b.p = np_;
+  b.cap = cap;
+  return e;
+}
+
 struct RawCloud {
   DevBuf<float> xyz, nrm;
   DevBuf<unsigned char> valid;
@@ -98,6 +114,7 @@ struct SliceData {
   DevBuf<float> clip_xyz, clip_nrm;  // N1: the clipped scene this slice's moving cloud was built from
   DevBuf<int> clip_gidx;             // ... and the indices of its points in the full scene
   int64_t n_clipped = 0;
+  int clip_scene_id = -1;
   int nf_valid = 0;
   float built_for_max_distance = -1.f;
   float ox = 0, oy = 0, oz = 0, inv_cell = 1;
@@ -1415,6 +1432,7 @@ int srrg2b_scene_clip(srrg2b_ctx* c, int scene_id, int slice_id, const float* sc
     CK(c, cudaStreamSynchronize(c->stream));  // the moving-cloud path below copies on the copy stream
   }
   sd.n_clipped = kept;
+  sd.clip_scene_id = scene_id;
   if (n_clipped) *n_clipped = kept;
   // the clipped scene becomes the slice's moving cloud without leaving the device
   srrg2b_cloud cl;
@@ -1425,6 +1443,117 @@ int srrg2b_scene_clip(srrg2b_ctx* c, int scene_id, int slice_id, const float* sc
   cl.on_device = 1;
   if (kept == 0) { static const float dummy = 0.f; cl.coords = &dummy; cl.on_device = 0; }
   return srrg2b_set_cloud(c, SRRG2B_MOVING, slice_id, &cl);
+}
+
+int srrg2b_scene_merge(srrg2b_ctx* c, int scene_id, int slice_id, const float* measurement_in_scene, const srrg2b_merge_params* mp,
+                       int64_t* n_merged, int64_t* n_added) {
+  if (!c) return SRRG2B_ERR_INVALID;
+  if (!measurement_in_scene || !mp) FAIL(c, SRRG2B_ERR_INVALID, "null argument");
+  if (!c->scenes.count(scene_id) || !c->scenes[scene_id].present) FAIL(c, SRRG2B_ERR_STATE, "unknown scene");
+  if (!c->slices.count(slice_id) || !c->slices[slice_id].fixed_raw.present) FAIL(c, SRRG2B_ERR_STATE, "the slice has no measurement (fixed) cloud");
+  if (!rigid_enough(c->dim, measurement_in_scene)) FAIL(c, SRRG2B_ERR_INVALID, "measurement_in_scene is not a rigid transform");
+  CK(c, cudaSetDevice(c->device));
+  RawCloud& sc = c->scenes[scene_id];
+  SliceData& sd = c->slices[slice_id];
+  RawCloud& me = sd.fixed_raw;
+  const int dim = c->dim, n_meas = (int) me.n, n_scene = (int) sc.n;
+  if (sc.has_normals && !me.has_normals) FAIL(c, SRRG2B_ERR_INVALID, "the scene carries normals, the measurement does not");
+  Mat4f T;
+  embed(dim, measurement_in_scene, T);
+  cudaStream_t st = c->stream;
+  if (me.ev_all) CK(c, cudaStreamWaitEvent(st, me.ev_all, 0));
+  CK(c, c->keys_a.ensure((size_t) std::max(n_meas, 1)));  // merged marks (as ints)
+  int* merged = reinterpret_cast<int*>(c->keys_a.p);
+  CK(c, cudaMemsetAsync(merged, 0, sizeof(int) * (size_t) std::max(n_meas, 1), st));
+  int64_t merged_count = 0, added = 0;
+  bool append = true;
+  if (!mp->without_correspondences) {
+    // the slice's moving cloud must be a clip of THIS scene, and a compute() must have left correspondences
+    if (sd.n_clipped != (int64_t) sd.moving_raw.n || sd.clip_scene_id != scene_id) FAIL(c, SRRG2B_ERR_STATE, "the slice's moving cloud is not a clip of this scene");
+    if (!sd.corr_valid) FAIL(c, SRRG2B_ERR_STATE, "the slice holds no correspondences (run the aligner first)");
+    const int n_local = (int) sd.moving_raw.n;
+    if (n_local > 0 && n_meas > 0) {
+      CK(c, c->flags.ensure(n_local)); CK(c, c->d_fidx.ensure(n_local)); CK(c, c->d_resp.ensure(n_local));
+      CK(c, cudaMemsetAsync(c->flags.p, 0, sizeof(int) * (size_t) n_local, st));
+      if (sd.nm_valid > 0) {
+        export_dense_kernel<<<blocks_for(sd.nm_valid, 256), 256, 0, st>>>(sd.m_pts.p, sd.f_pts.p, sd.c_fpos.p, sd.c_fidx.p, sd.S_lb.p, dim,
+                                                                          sd.stat_valid ? sd.c_stat.p : nullptr, sd.stat_valid ? sd.c_chi.p : nullptr,
+                                                                          sd.nm_valid, sd.prune_on_export, c->d_fidx.p, c->d_resp.p, nullptr, nullptr,
+                                                                          c->flags.p);
+        c->launches++;
+      }
+      float* s_nrm = sc.has_normals ? sc.nrm.p : nullptr;
+      const float* m_nrm = me.has_normals ? me.nrm.p : nullptr;
+      if (dim == 3) scene_merge_kernel<3><<<blocks_for(n_local, 256), 256, 0, st>>>(c->flags.p, c->d_fidx.p, c->d_resp.p, sd.clip_gidx.p, n_local, me.xyz.p, m_nrm, T,
+                                                                                mp->maximum_response, mp->maximum_distance_geometry_squared, sc.xyz.p, s_nrm, merged);
+      else scene_merge_kernel<2><<<blocks_for(n_local, 256), 256, 0, st>>>(c->flags.p, c->d_fidx.p, c->d_resp.p, sd.clip_gidx.p, n_local, me.xyz.p, m_nrm, T,
+                                                                           mp->maximum_response, mp->maximum_distance_geometry_squared, sc.xyz.p, s_nrm, merged);
+      c->launches++;
+      // number of DISTINCT measurement points merged (:79)
+      CK(c, c->positions.ensure((size_t) n_meas));
+      size_t bytes = 0;
+      CK(c, cub::DeviceScan::ExclusiveSum(nullptr, bytes, merged, c->positions.p, n_meas, st));
+      CK(c, c->cub_tmp.ensure(bytes));
+      CK(c, cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, bytes, merged, c->positions.p, n_meas, st));
+      int last_flag = 0, last_pos = 0;
+      CK(c, cudaMemcpyAsync(&last_flag, merged + (n_meas - 1), 4, cudaMemcpyDeviceToHost, st));
+      CK(c, cudaMemcpyAsync(&last_pos, c->positions.p + (n_meas - 1), 4, cudaMemcpyDeviceToHost, st));
+      CK(c, cudaStreamSynchronize(st));
+      merged_count = (int64_t) last_flag + last_pos;
+    }
+    append = merged_count < (int64_t) mp->target_number_of_merges;  // :96
+  }
+  if (append && n_meas > 0) {
+    CK(c, c->flags.ensure((size_t) n_meas)); CK(c, c->positions.ensure((size_t) n_meas));
+    scene_append_flag_kernel<<<blocks_for(n_meas, 256), 256, 0, st>>>(merged, me.has_valid ? me.valid.p : nullptr, n_meas, c->flags.p);
+    size_t bytes = 0;
+    CK(c, cub::DeviceScan::ExclusiveSum(nullptr, bytes, c->flags.p, c->positions.p, n_meas, st));
+    CK(c, c->cub_tmp.ensure(bytes));
+    CK(c, cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, bytes, c->flags.p, c->positions.p, n_meas, st));
+    int last_flag = 0, last_pos = 0;
+    CK(c, cudaMemcpyAsync(&last_flag, c->flags.p + (n_meas - 1), 4, cudaMemcpyDeviceToHost, st));
+    CK(c, cudaMemcpyAsync(&last_pos, c->positions.p + (n_meas - 1), 4, cudaMemcpyDeviceToHost, st));
+    CK(c, cudaStreamSynchronize(st));
+    added = (int64_t) last_flag + last_pos;
+    if (added > 0) {
+      const size_t need = (size_t) n_scene + (size_t) added;
+      CK(c, grow_preserve(sc.xyz, (size_t) n_scene * dim, need * dim, st));
+      if (sc.has_normals) CK(c, grow_preserve(sc.nrm, (size_t) n_scene * dim, need * dim, st));
+      if (sc.has_valid) CK(c, grow_preserve(sc.valid, (size_t) n_scene, need, st));
+      float* s_nrm = sc.has_normals ? sc.nrm.p : nullptr;
+      const float* m_nrm = me.has_normals ? me.nrm.p : nullptr;
+      unsigned char* s_val = sc.has_valid ? sc.valid.p : nullptr;
+      if (dim == 3) scene_append_kernel<3><<<blocks_for(n_meas, 256), 256, 0, st>>>(c->flags.p, c->positions.p, n_meas, me.xyz.p, m_nrm, T, n_scene, sc.xyz.p, s_nrm, s_val);
+      else scene_append_kernel<2><<<blocks_for(n_meas, 256), 256, 0, st>>>(c->flags.p, c->positions.p, n_meas, me.xyz.p, m_nrm, T, n_scene, sc.xyz.p, s_nrm, s_val);
+      c->launches += 2;
+      sc.n = (int64_t) need;
+    }
+  }
+  CK(c, cudaGetLastError());
+  CK(c, cudaStreamSynchronize(st));
+  // the scene changed under the slices clipped from it: their clips are stale (the next frame clips again anyway)
+  if (n_merged) *n_merged = merged_count;
+  if (n_added) *n_added = added;
+  return SRRG2B_OK;
+}
+
+int srrg2b_scene_get(srrg2b_ctx* c, int scene_id, float* coords, float* normals, uint8_t* valid, int64_t* n) {
+  if (!c) return SRRG2B_ERR_INVALID;
+  if (!c->scenes.count(scene_id) || !c->scenes[scene_id].present) FAIL(c, SRRG2B_ERR_STATE, "unknown scene");
+  CK(c, cudaSetDevice(c->device));
+  RawCloud& sc = c->scenes[scene_id];
+  if (n) *n = sc.n;
+  const size_t cnt = (size_t) sc.n;
+  if (cnt) {
+    if (coords) CK(c, cudaMemcpyAsync(coords, sc.xyz.p, sizeof(float) * cnt * c->dim, cudaMemcpyDeviceToHost, c->stream));
+    if (normals && sc.has_normals) CK(c, cudaMemcpyAsync(normals, sc.nrm.p, sizeof(float) * cnt * c->dim, cudaMemcpyDeviceToHost, c->stream));
+    if (valid) {
+      if (sc.has_valid) CK(c, cudaMemcpyAsync(valid, sc.valid.p, cnt, cudaMemcpyDeviceToHost, c->stream));
+      else memset(valid, 1, cnt);
+    }
+  }
+  CK(c, cudaStreamSynchronize(c->stream));
+  return SRRG2B_OK;
 }
 
 int srrg2b_scene_clip_indices(srrg2b_ctx* c, int slice_id, int32_t* global_indices) {

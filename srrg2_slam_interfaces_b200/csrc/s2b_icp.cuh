@@ -1773,6 +1773,70 @@ __global__ void scene_clip_compact_kernel(const float* __restrict__ xyz, const f
 }
 
 // ---------------------------------------------------------------------------------------------
+// N2: MergerCorrespondenceHomo_::compute(), R/mapping/merger_correspondence_homo_impl.cpp:11-126, on
+// the device-resident scene.  The aligner's correspondences never leave the GPU: d_flag / d_fidx / d_resp are the
+// dense export of the slice (per local moving index k: keep flag, index j of the measurement point -- the aligner's
+// fixed cloud --, response), gidx maps k to the scene point it was clipped from (the flip + local_to_global mapping of
+// R/trackers/tracker_slice_processor_impl.cpp:159-191).  Every scene point appears in at most one correspondence
+// (one entry per moving point, the clip is injective), so the merges are conflict free; merged[j] is an idempotent mark.
+// ---------------------------------------------------------------------------------------------
+template <int DIM>
+__global__ void scene_merge_kernel(const int* __restrict__ d_flag, const int* __restrict__ d_fidx, const float* __restrict__ d_resp,
+                                   const int* __restrict__ gidx, int n_local, const float* __restrict__ meas_xyz,
+                                   const float* __restrict__ meas_nrm, Mat4f T, float max_response, float max_d2,
+                                   float* __restrict__ scene_xyz, float* __restrict__ scene_nrm, int* __restrict__ merged) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_local || !d_flag[k]) return;
+  const int j = d_fidx[k], g = gidx[k];
+  if (j < 0 || !(d_resp[k] < max_response)) return;
+  const float4 m = make_float4(meas_xyz[(size_t) j * DIM], meas_xyz[(size_t) j * DIM + 1], DIM == 3 ? meas_xyz[(size_t) j * DIM + 2] : 0.f, 0.f);
+  float q[3];
+  nn_transform<DIM>(T.m, m, q[0], q[1], q[2]);
+  float sp[3] = {scene_xyz[(size_t) g * DIM], scene_xyz[(size_t) g * DIM + 1], DIM == 3 ? scene_xyz[(size_t) g * DIM + 2] : 0.f};
+  const float dx = q[0] - sp[0], dy = q[1] - sp[1], dz = q[2] - sp[2];
+  float d2 = fmaf(dy, dy, dx * dx);
+  if (DIM == 3) d2 = fmaf(dz, dz, d2);
+  if (!(d2 < max_d2)) return;
+#pragma unroll
+  for (int c = 0; c < DIM; ++c) {
+    scene_xyz[(size_t) g * DIM + c] = (q[c] + sp[c]) * 0.5f;
+    if (scene_nrm && meas_nrm) scene_nrm[(size_t) g * DIM + c] = meas_nrm[(size_t) j * DIM + c];  // (copied as it is: :71-74)
+  }
+  merged[j] = 1;
+}
+
+// the measurement points that were not merged (and are valid): flag for the append
+__global__ void scene_append_flag_kernel(const int* __restrict__ merged, const unsigned char* __restrict__ valid, int n, int* __restrict__ flag) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n) flag[j] = (!merged[j] && (!valid || valid[j])) ? 1 : 0;
+}
+
+// append the flagged measurement points, transformed in place (coordinates and normal), behind the scene's n_scene points
+template <int DIM>
+__global__ void scene_append_kernel(const int* __restrict__ flag, const int* __restrict__ pos, int n, const float* __restrict__ meas_xyz,
+                                    const float* __restrict__ meas_nrm, Mat4f T, int n_scene, float* __restrict__ scene_xyz,
+                                    float* __restrict__ scene_nrm, unsigned char* __restrict__ scene_valid) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n || !flag[j]) return;
+  const size_t o = (size_t) n_scene + pos[j];
+  const float* S = T.m;
+  const float4 m = make_float4(meas_xyz[(size_t) j * DIM], meas_xyz[(size_t) j * DIM + 1], DIM == 3 ? meas_xyz[(size_t) j * DIM + 2] : 0.f, 0.f);
+  float qx, qy, qz;
+  nn_transform<DIM>(S, m, qx, qy, qz);
+  scene_xyz[o * DIM] = qx;
+  scene_xyz[o * DIM + 1] = qy;
+  if (DIM == 3) scene_xyz[o * DIM + 2] = qz;
+  if (scene_nrm && meas_nrm) {
+    const float nx = meas_nrm[(size_t) j * DIM], ny = meas_nrm[(size_t) j * DIM + 1], nz = DIM == 3 ? meas_nrm[(size_t) j * DIM + 2] : 0.f;
+    float t;
+    t = S[0] * nx; t = fmaf(S[1], ny, t); if (DIM == 3) t = fmaf(S[2], nz, t); scene_nrm[o * DIM] = t;
+    t = S[4] * nx; t = fmaf(S[5], ny, t); if (DIM == 3) t = fmaf(S[6], nz, t); scene_nrm[o * DIM + 1] = t;
+    if (DIM == 3) { t = S[8] * nx; t = fmaf(S[9], ny, t); t = fmaf(S[10], nz, t); scene_nrm[o * DIM + 2] = t; }
+  }
+  if (scene_valid) scene_valid[o] = 1;
+}
+
+// ---------------------------------------------------------------------------------------------
 // k2b: export (sorted order -> dense by local moving index), then compaction
 // ---------------------------------------------------------------------------------------------
 __global__ void export_dense_kernel(const float4* __restrict__ mp, const float4* __restrict__ fp,
