@@ -202,6 +202,8 @@ struct srrg2b_ctx {
   bool use_graphs = true;  // env SRRG2B_NO_GRAPH=1 disables
   bool graph_nccl = false;  // env SRRG2B_GRAPH_NCCL=1: capture the all-reduce too (experimental: failed the 2-GPU parity test)
   bool eager_index = true;  // env SRRG2B_EAGER_INDEX=0: build the NN index on first use only
+  int small_shift = 6;  // env SRRG2B_SMALL_SHIFT
+  int nn_flat = 3;  // thread-per-query searches walk their rows in chunks of 8 (env SRRG2B_NN_FLAT=0: one row at a time)
   int full_iters = 4;  // iterations of a run that launch the three-kernel search pipeline (env SRRG2B_FULL_ITERS)
   long long timeout_cycles = 4000000000ll;  // ~2 s of SM clock: the peer exchange gives up (env SRRG2B_TIMEOUT_MS)
   s2b::Mat4f* d_T0 = nullptr;  // initial guess of the current run (read by icp_init_kernel)
@@ -703,6 +705,8 @@ int fill_slice_args(srrg2b_ctx* c, SliceData& sd, int state_slot, const srrg2b_f
   a.list_all = &c->d_state->list_all[state_slot];
   a.inline_check = 0; a.use_list = 0; a.sole_list = 0;
   a.few_terms = 0;
+  a.nn_flat = c->nn_flat;
+  a.small_shift = c->small_shift;
   a.projective = fp.kind == SRRG2B_FINDER_PROJECTIVE ? 1 : 0;
   a.fx = fp.fx; a.fy = fp.fy; a.pcx = fp.cx; a.pcy = fp.cy; a.min_depth = fp.min_depth; a.max_depth = fp.max_depth;
   a.width = fp.width; a.height = fp.height; a.image = sd.image.p;
@@ -729,7 +733,7 @@ void launch_far(srrg2b_ctx* c, const SliceArgs& a_in, int factor, const int* ski
   const int fblocks = std::max(1, std::min(blocks_for((int64_t) a.nm * 32, threads), c->sm_count * 8));
   {  // tail mode: lane 0 of a warp linearises its share of a short (< nm / 64 + 64) work list
     const int64_t warps = (int64_t) fblocks * (threads / 32);
-    const int64_t per_lane = (((int64_t) a.nm >> 6) + 64 + warps - 1) / warps;
+    const int64_t per_lane = (((int64_t) a.nm >> a.small_shift) + 64 + warps - 1) / warps;
     a.few_terms = per_lane <= 30 ? 1 : 0;
   }
   if (c->dim == 3) {
@@ -1161,6 +1165,8 @@ int srrg2b_ctx_create(int dim, int device, srrg2b_ctx** out) {
     c->timeout_cycles = (long long) (ms * (double) khz);
   }
   if (const char* env = getenv("SRRG2B_FULL_ITERS")) c->full_iters = std::max(0, atoi(env));
+  if (const char* env = getenv("SRRG2B_NN_FLAT")) c->nn_flat = atoi(env);
+  if (const char* env = getenv("SRRG2B_SMALL_SHIFT")) c->small_shift = std::min(20, std::max(0, atoi(env)));
   if (const char* env = getenv("SRRG2B_EAGER_INDEX")) c->eager_index = atoi(env) != 0;
   if (const char* env = getenv("SRRG2B_GRAPH_NCCL")) c->graph_nccl = atoi(env) != 0;
   {

@@ -109,6 +109,8 @@ struct SliceArgs {
   int use_list;        // 1: nn / linearise kernels iterate over the work list
   int sole_list;       // 1: nn_far_kernel is the ONLY search kernel of this iteration (see launch_slice_iteration)
   int few_terms;       // every thread of the accumulating kernel adds at most 30 terms per slot
+  int small_shift;     // work lists shorter than nm >> small_shift are searched + linearised one warp per query (small_work_list)
+  int nn_flat;         // 1: thread-per-query searches walk their rows in chunks of 8 with one flat candidate loop (nn_scan_rows8)
   float* c_lb;         // certified lower bound per query PLUS the motion budget at certification (0: none)
   const float* S_lb;   // bound state of the slice (see SolveSlice::S_lb)
   const int* track2;   // device flag: searches track the second neighbour (certify bounds)
@@ -561,6 +563,102 @@ __device__ __forceinline__ void nn_scan_row(const SliceArgs& a, NNQuery& q, int 
   }
 }
 
+// Up to 8 rows of the search neighbourhood in one go, SIMT-friendly.  rows[k0..k1) are packed table entries
+// (dy | dz << 8 | ring << 16).  Stage A: every lane prunes its 8 rows arithmetically and fetches the bounds of the
+// survivors together -- 16 independent loads in flight instead of 8 dependent pairs one after the other; runs
+// that hold points are parked in the lane's column of shared memory (park[0..8) first positions, [8..16) ends,
+// [16..24) slab distances; stride = blockDim.x).  Stage B: ONE loop over the parked runs, four candidates per
+// trip, so the lanes of a warp diverge by their total candidate count only and no longer per row (the nested
+// row / candidate loops ran at 12 of 32 lanes).  A row whose slab distance the shrinking radius has overtaken is
+// dropped when its turn comes.  The x range of a row is fixed by the radius at stage A: a few more
+// candidates than the one-row-at-a-time walk, same result -- (nearest, second nearest) do not depend on the order or
+// on how much beyond the final radius was examined.
+constexpr int kRowChunk = 8;
+template <int DIM, bool TRACK2>
+__device__ __forceinline__ void nn_scan_rows8(const SliceArgs& a, NNQuery& q, const int* rows, int k0, int k1, float cell,
+                                              int* park, int stride) {
+  const unsigned am = __activemask();
+  const float pr2 = TRACK2 ? q.sd2 : q.bd2;
+  int ps[kRowChunk], pe[kRowChunk];
+  float lbs[kRowChunk];
+#pragma unroll
+  for (int u = 0; u < kRowChunk; ++u) {
+    ps[u] = 0; pe[u] = 0; lbs[u] = 0.f;
+    const int k = k0 + u;
+    if (k < k1) {  // (uniform)
+      const int e = rows[k];
+      const int dy = (int) (signed char) (e & 0xff), dz = (int) (signed char) ((e >> 8) & 0xff);
+      const int y = q.cy + dy, z = q.cz + dz;
+      const float gy = axis_gap(dy, q.fry) * cell;
+      float lb2 = gy * gy;
+      if (DIM == 3) {
+        const float gz = axis_gap(dz, q.frz) * cell;
+        lb2 = fmaf(gz, gz, lb2);
+      }
+      bool ok = y >= 0 && y < a.ny && z >= 0 && z < a.nz && !(lb2 > pr2);
+      if (__any_sync(am, ok)) {
+        const float rr = __fsqrt_rn(fmaxf(pr2 - lb2, 0.f)) * a.inv_cell_x + 2e-3f;
+        const int xa = max(max((int) floorf(q.cfx - rr), q.cx - a.Rx), 0);
+        const int xb = min(min((int) floorf(q.cfx + rr), q.cx + a.Rx), a.nx - 1);
+        ok = ok && xa <= xb;
+        const int row = (z * a.ny + y) * a.nx;
+        // (a lane without this row reads cell_start[0] twice: an empty run)
+        ps[u] = __ldg(a.cell_start + (ok ? row + xa : 0));
+        pe[u] = __ldg(a.cell_start + (ok ? row + xb + 1 : 0));
+        lbs[u] = lb2;
+      }
+    }
+  }
+  int nr = 0;
+#pragma unroll
+  for (int u = 0; u < kRowChunk; ++u) {
+    if (pe[u] > ps[u]) {
+      park[nr * stride] = ps[u];
+      park[(kRowChunk + nr) * stride] = pe[u];
+      park[(2 * kRowChunk + nr) * stride] = __float_as_int(lbs[u]);
+      ++nr;
+    }
+  }
+  int j = 0, p = 0, end = 0;
+#pragma unroll 1
+  for (;;) {
+    if (p >= end) {
+      if (j >= nr) break;
+      p = park[j * stride];
+      end = park[(kRowChunk + j) * stride];
+      const float lb2 = __int_as_float(park[(2 * kRowChunk + j) * stride]);
+      ++j;
+      if (lb2 > (TRACK2 ? q.sd2 : q.bd2)) end = p;
+    }
+    if (p < end) {
+      const int last = end - 1;
+      const float4 c0 = __ldg(a.fp + p);
+      const float4 c1 = __ldg(a.fp + min(p + 1, last));
+      const float4 c2 = __ldg(a.fp + min(p + 2, last));
+      const float4 c3 = __ldg(a.fp + min(p + 3, last));
+      nn_consider_pt<DIM, TRACK2>(q, p, c0);
+      if (p + 1 < end) nn_consider_pt<DIM, TRACK2>(q, p + 1, c1);
+      if (p + 2 < end) nn_consider_pt<DIM, TRACK2>(q, p + 2, c2);
+      if (p + 3 < end) nn_consider_pt<DIM, TRACK2>(q, p + 3, c3);
+      p += 4;
+    }
+  }
+}
+
+// rings >= 1 of a thread-per-query search in chunks of 8 rows, nearest ring first (rows[] is ordered by ring)
+template <int DIM, bool TRACK2>
+__device__ __forceinline__ void nn_scan_rings_flat(const SliceArgs& a, NNQuery& q, const int* rows, int k_first, int K,
+                                                   float cell, int* park, int stride) {
+  for (int k = k_first; k < K; k += kRowChunk) {
+    const int ring = (rows[k] >> 16) & 0xff;
+    if (ring >= 2) {  // every row of this and later rings is at least (ring - 1) cells away
+      const float g = ((float) (ring - 1) - 4e-3f) * cell;
+      if (g * g > (TRACK2 ? q.sd2 : q.bd2)) break;
+    }
+    nn_scan_rows8<DIM, TRACK2>(a, q, rows, k, min(k + kRowChunk, K), cell, park, stride);
+  }
+}
+
 template <int DIM>
 __device__ __forceinline__ void nn_transform(const float* S, const float4 m, float& x, float& y, float& z) {
   float t;  // q = S m  (operation order is part of the numerics contract)
@@ -585,7 +683,7 @@ __device__ __forceinline__ void nn_setup(const SliceArgs& a, const float* S, con
 // linearise), where the chain of dependent loads of a search is short; the thread-per-query kernels
 // then return at once
 __device__ __forceinline__ bool small_work_list(const SliceArgs& a, bool all, int n_work) {
-  return a.use_list && !all && n_work < max(a.nm >> 6, 64);
+  return a.use_list && !all && n_work < max(a.nm >> a.small_shift, 64);
 }
 
 __device__ __forceinline__ int slot_candidate(int slot) {
@@ -656,9 +754,9 @@ __device__ __forceinline__ int nn_finish(const SliceArgs& a, const float* S, con
 // lane walks only its own surviving rows).  A query whose best distance is still larger than the
 // distance to ring 2 is handed to phase 2 through a worklist, so that the rare expensive queries
 // (outliers, large initial misalignment) do not serialise the warps of the cheap ones.
-template <int DIM, bool TRACK2>
+template <int DIM, bool TRACK2, bool FLAT>
 __device__ __forceinline__ void nn_phase1_body(const SliceArgs& a, const float* S, float cell,
-                                               float ring2, float ring2_sq, bool all, int n_work) {
+                                               float ring2, float ring2_sq, bool all, int n_work, const int* rows, int* park) {
   for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < n_work; w += gridDim.x * blockDim.x) {
     const int i = all ? w : __ldcg(a.work_list + w);
     NNQuery q;
@@ -706,7 +804,17 @@ __device__ __forceinline__ void nn_phase1_body(const SliceArgs& a, const float* 
     if (q.cy >= 0 && q.cy < a.ny && q.cz >= 0 && q.cz < a.nz) nn_scan_row<DIM, TRACK2>(a, q, q.cy, q.cz, 0.f);
     // ring 1: bit b = jz * 3 + jy marks a row this lane still has to visit
     unsigned mask = 0;
-    {
+    // Ring 1 as one flat chunk pays when the centre row leaves much to do -- searches that certify bounds, and warps
+    // whose queries start without a warm-start candidate (the first iteration of a run: 248 -> 230 us at C2); with a
+    // good candidate most lanes drop all of ring 1 and the per-lane walk below is cheaper (measured: 164 vs 181 us).
+    bool flat = FLAT;
+    if (FLAT && !TRACK2) {
+      const unsigned am = __activemask();
+      flat = 2 * __popc(__ballot_sync(am, p0 < 0)) > __popc(am);
+    }
+    if (flat) {  // the 3^(DIM-1) - 1 rows of ring 1 as one chunk
+      nn_scan_rows8<DIM, TRACK2>(a, q, rows, 1, DIM == 3 ? 9 : 3, cell, park, blockDim.x);
+    } else {
       const float pr2 = TRACK2 ? q.sd2 : q.bd2;
 #pragma unroll
       for (int jz = (DIM == 3 ? 0 : 1); jz < (DIM == 3 ? 3 : 2); ++jz) {
@@ -754,14 +862,25 @@ __global__ void __launch_bounds__(256) nn_kernel(const SliceArgs a, const int* s
   const int n_work = all ? a.nm : work_count;
   if (small_work_list(a, all, n_work)) return;
   __shared__ float S[16];
+  __shared__ int rows[16];
+  __shared__ int park_all[3 * kRowChunk * 256];
   if (threadIdx.x < 16) S[threadIdx.x] = a.S[threadIdx.x];
+  if (threadIdx.x >= 32 && threadIdx.x < 32 + (DIM == 3 ? 9 : 3))
+    rows[threadIdx.x - 32] = (DIM == 3) ? *reinterpret_cast<const int*>(c_rows3[threadIdx.x - 32])
+                                        : *reinterpret_cast<const int*>(c_rows2[threadIdx.x - 32]);
+  int* park = park_all + threadIdx.x;
   __syncthreads();
   const float cell = __fdiv_rn(1.f, a.inv_cell);
   // distance below which a point cannot lie in ring 2 or beyond (for R == 1: the covered radius)
   const float ring2 = (a.R >= 2) ? (1.f - 4e-3f) * cell : __fsqrt_rn(a.rho_s2);
   const float ring2_sq = (a.R >= 2) ? ring2 * ring2 : 3.0e38f;
-  if (track2) nn_phase1_body<DIM, true>(a, S, cell, ring2, ring2_sq, all, n_work);
-  else nn_phase1_body<DIM, false>(a, S, cell, ring2, ring2_sq, all, n_work);
+  if (a.nn_flat & 1) {
+    if (track2) nn_phase1_body<DIM, true, true>(a, S, cell, ring2, ring2_sq, all, n_work, rows, park);
+    else nn_phase1_body<DIM, false, true>(a, S, cell, ring2, ring2_sq, all, n_work, rows, park);
+  } else {
+    if (track2) nn_phase1_body<DIM, true, false>(a, S, cell, ring2, ring2_sq, all, n_work, rows, park);
+    else nn_phase1_body<DIM, false, false>(a, S, cell, ring2, ring2_sq, all, n_work, rows, park);
+  }
 }
 
 // Phase 2: the queries phase 1 could not settle (worklist).  These are few but expensive
@@ -777,7 +896,7 @@ __device__ __forceinline__ void lin_one_slot(const SliceArgs& a, const LinConst&
 template <int DIM, bool TRACK2, int FACTOR = SRRG2B_FACTOR_P2P>
 __device__ __forceinline__ void nn_far_body(const SliceArgs& a, const float* S, const int* rows, int K, float cell,
                                             int n_far, const int* list, LinAcc<DIM>* lin, const LinConst* lk, int w_first,
-                                            int w_stride) {
+                                            int w_stride, int* park) {
   const int lane = threadIdx.x & 31;
   if (!lin && n_far > (a.nm >> 4)) {
     // long worklist (large initial misalignment): one THREAD per query, rows nearest ring first
@@ -789,6 +908,14 @@ __device__ __forceinline__ void nn_far_body(const SliceArgs& a, const float* S, 
       const int p0 = slot_candidate(old_slot);
       if (a.warm && p0 >= 0) { nn_consider<DIM, TRACK2>(a, q, p0); if (TRACK2) nn_limit_bound(q, cell); }
       // (far list of phase 1, nearest point only: rings 0-1 were searched exhaustively there)
+      if (a.nn_flat & 2) {
+        int k = TRACK2 ? 0 : min(K, (DIM == 3 ? 9 : 3));
+        if (k == 0) {
+          if (q.cy >= 0 && q.cy < a.ny && q.cz >= 0 && q.cz < a.nz) nn_scan_row<DIM, TRACK2>(a, q, q.cy, q.cz, 0.f);
+          k = 1;
+        }
+        nn_scan_rings_flat<DIM, TRACK2>(a, q, rows, k, K, cell, park, blockDim.x);
+      } else
       for (int k = TRACK2 ? 0 : min(K, (DIM == 3 ? 9 : 3)); k < K; ++k) {
         const int e = rows[k];
         const int dy = (int) (signed char) (e & 0xff), dz = (int) (signed char) ((e >> 8) & 0xff);
@@ -1138,7 +1265,7 @@ __device__ __forceinline__ void lin_push_tail_lane0(const LinAcc<DIM>& A, long l
 // that does not need them.
 template <int DIM, bool TRACK2, int FACTOR>
 __device__ __forceinline__ void nn_full_lin_body(const SliceArgs& a, const float* S, const int* rows, int K, float cell, int n,
-                                                 const int* list, LinAcc<DIM>& A, const LinConst& lk, FlushSmem& fsm) {
+                                                 const int* list, LinAcc<DIM>& A, const LinConst& lk, FlushSmem& fsm, int* park) {
   int done = 0;
   // (every thread of a CTA makes the same number of trips: the mid-loop flush below is a CTA-wide barrier)
   for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
@@ -1151,6 +1278,10 @@ __device__ __forceinline__ void nn_full_lin_body(const SliceArgs& a, const float
     const int old_slot = __ldcg(a.c_fpos + i);
     const int p0 = slot_candidate(old_slot);
     if (a.warm && p0 >= 0) { nn_consider<DIM, TRACK2>(a, q, p0); if (TRACK2) nn_limit_bound(q, cell); }
+    if (a.nn_flat & 2) {
+      if (q.cy >= 0 && q.cy < a.ny && q.cz >= 0 && q.cz < a.nz) nn_scan_row<DIM, TRACK2>(a, q, q.cy, q.cz, 0.f);
+      nn_scan_rings_flat<DIM, TRACK2>(a, q, rows, 1, K, cell, park, blockDim.x);
+    } else
     for (int k = 0; k < K; ++k) {
       const int e = rows[k];
       const int dy = (int) (signed char) (e & 0xff), dz = (int) (signed char) ((e >> 8) & 0xff);
@@ -1208,6 +1339,8 @@ __global__ void __launch_bounds__(256) nn_far_kernel(const SliceArgs a, const in
   __shared__ int rows[kRowTable];
   __shared__ FlushSmem fsm;
   __shared__ LinConst lk;
+  __shared__ int park_all[3 * kRowChunk * 256];
+  int* park = park_all + threadIdx.x;
   if (threadIdx.x < 16) S[threadIdx.x] = a.S[threadIdx.x];
   if (threadIdx.x == 32) make_lin_const(a, a.S, lk);
   const int R = a.R;
@@ -1222,20 +1355,20 @@ __global__ void __launch_bounds__(256) nn_far_kernel(const SliceArgs a, const in
     LinAcc<DIM> A;
     A.clear();
     const int* list = all ? nullptr : a.work_list;
-    if (track2) nn_full_lin_body<DIM, true, FACTOR>(a, S, rows, K, cell, n_far, list, A, lk, fsm);
-    else nn_full_lin_body<DIM, false, FACTOR>(a, S, rows, K, cell, n_far, list, A, lk, fsm);
+    if (track2) nn_full_lin_body<DIM, true, FACTOR>(a, S, rows, K, cell, n_far, list, A, lk, fsm, park);
+    else nn_full_lin_body<DIM, false, FACTOR>(a, S, rows, K, cell, n_far, list, A, lk, fsm, park);
     lin_flush<DIM>(a.acc, false, A, fsm);
     return;
   }
   if (!tail) {
-    if (track2) nn_far_body<DIM, true>(a, S, rows, K, cell, n_far, a.far_list, nullptr, nullptr, w0, ws);
-    else nn_far_body<DIM, false>(a, S, rows, K, cell, n_far, a.far_list, nullptr, nullptr, w0, ws);
+    if (track2) nn_far_body<DIM, true>(a, S, rows, K, cell, n_far, a.far_list, nullptr, nullptr, w0, ws, park);
+    else nn_far_body<DIM, false>(a, S, rows, K, cell, n_far, a.far_list, nullptr, nullptr, w0, ws, park);
     return;
   }
   LinAcc<DIM> A;
   A.clear();
-  if (track2) nn_far_body<DIM, true, FACTOR>(a, S, rows, K, cell, n_far, a.work_list, &A, &lk, w0, ws);
-  else nn_far_body<DIM, false, FACTOR>(a, S, rows, K, cell, n_far, a.work_list, &A, &lk, w0, ws);
+  if (track2) nn_far_body<DIM, true, FACTOR>(a, S, rows, K, cell, n_far, a.work_list, &A, &lk, w0, ws, park);
+  else nn_far_body<DIM, false, FACTOR>(a, S, rows, K, cell, n_far, a.work_list, &A, &lk, w0, ws, park);
   lin_flush<DIM>(a.acc, a.few_terms != 0, A, fsm);
 }
 
