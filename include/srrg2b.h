@@ -200,6 +200,53 @@ int srrg2b_get_correspondences(srrg2b_ctx* ctx, int slice_id, int32_t* fixed_idx
  * would (the clouds and the NN index stay): the next compute() starts cold.  Results never depend on it. */
 int srrg2b_reset_correspondences(srrg2b_ctx* ctx, int slice_id);
 
+/* ---- N3: candidate-batched loop closing / relocalisation.
+ * MultiLoopDetectorBruteForce_::compute (R/registration/loop_detector/multi_loop_detector_brute_force_impl.cpp:63-133)
+ * and MultiRelocalizer_::compute (R/registration/relocalization/multi_relocalizer_impl.cpp:74-138) run ONE aligner
+ * serially over K candidate local maps: setFixed(source) once, then per candidate setMoving(target),
+ * setMovingInFixed(guess), compute(), and the three gates on the last IterationStats.  Here every candidate owns
+ * a context (its own stream, solver state and CUDA graph), the K runs are in flight together -- first runs of all
+ * candidates, then the inlier-only runs of those that passed -- and the gates are applied in candidate order.
+ *
+ * srrg2b_share_fixed: the source local map is uploaded and indexed ONCE (srrg2b_set_cloud(FIXED) on `src`) and lent
+ * to the candidates' contexts: `dst`'s slice reads src's fixed cloud and NN index in place (no copy).  Contract: same
+ * device and dimension; `src`'s slice must not be re-set or destroyed while a borrower still uses it; a borrower that
+ * sets its own fixed cloud, or searches with a different radius, silently gets private buffers again. */
+int srrg2b_share_fixed(srrg2b_ctx* dst, int dst_slice_id, srrg2b_ctx* src, int src_slice_id);
+
+typedef struct {
+  int32_t relocalize_min_inliers;        /* multi_loop_detector_brute_force.h: param_relocalize_min_inliers */
+  float relocalize_max_chi_inliers;      /* param_relocalize_max_chi_inliers (chi per inlier) */
+  float relocalize_min_inliers_ratio;    /* param_relocalize_min_inliers_ratio */
+} srrg2b_closure_params;
+
+#define SRRG2B_CLOSURE_ACCEPT 0
+#define SRRG2B_CLOSURE_ALIGNER_DROP 1        /* :80-84  status != Success */
+#define SRRG2B_CLOSURE_NUM_INLIERS_DROP 2    /* :94-97 */
+#define SRRG2B_CLOSURE_MAX_CHI_DROP 3        /* :99-103 */
+#define SRRG2B_CLOSURE_INLIER_RATIO_DROP 4   /* :105-111 */
+
+typedef struct {
+  int32_t verdict;                 /* SRRG2B_CLOSURE_* */
+  int32_t aligner_status;          /* SRRG2B_ALIGNER_* */
+  int32_t iterations;              /* IterationStats entries of the run(s) */
+  int32_t reserved;
+  int64_t num_correspondences;     /* aligner->numCorrespondences() after compute(): point slices' lists (pruned when
+                                      keep_only_inlier_correspondences) + 1 per prior slice (multi_aligner_impl.cpp:275-285) */
+  int64_t num_inliers;             /* last IterationStats */
+  float chi_inliers;               /* istat.chi_inliers / num_inliers, fp32 division (:91) */
+  float device_ms;                 /* device time of this candidate's run(s) */
+  float moving_in_fixed[16];       /* aligner->movingInFixed(), row-major (dim+1)^2; the closure's measurement */
+} srrg2b_closure_result;
+
+/* ctxs[k]: candidate k's context, holding the slices' clouds (fixed side typically lent by srrg2b_share_fixed);
+ * guesses: K row-major (dim+1)^2 initial guesses (h->initial_guess); the slice list and aligner parameters are the
+ * detector's one aligner configuration, used for every candidate.  Results in candidate order.  The correspondences
+ * of candidate k stay in ctxs[k] (srrg2b_get_correspondences / srrg2b_scene_merge). */
+int srrg2b_closure_batch(srrg2b_ctx* const* ctxs, int k, int n_slices, const srrg2b_slice* slices,
+                         const srrg2b_aligner_params* ap, const float* guesses, const srrg2b_closure_params* cp,
+                         srrg2b_closure_result* results);
+
 /* ---- benchmarking support: device time of the last srrg2b_icp_run between its first and last
  * kernel (CUDA events on the context stream), and how many _runSolver iterations it executed ---- */
 int srrg2b_last_run_timing(srrg2b_ctx* ctx, float* device_ms, int32_t* iterations);

@@ -279,6 +279,42 @@ def icp_run(dim, slices, ap, T0, nn_method=NN_KDTREE, want_correspondences=True,
                 correspondences=corr)
 
 
+CLOSURE_ACCEPT, CLOSURE_ALIGNER_DROP, CLOSURE_NUM_INLIERS_DROP, CLOSURE_MAX_CHI_DROP, CLOSURE_INLIER_RATIO_DROP = 0, 1, 2, 3, 4
+
+
+def closure_loop(dim, candidate_slices, ap, guesses, min_inliers=500, max_chi_inliers=0.005, min_inliers_ratio=0.7):
+    """MultiLoopDetectorBruteForce_::compute's candidate loop
+    (R/registration/loop_detector/multi_loop_detector_brute_force_impl.cpp:63-133; the same gates in
+    R/registration/relocalization/multi_relocalizer_impl.cpp:86-118), restated over the oracle aligner: one compute()
+    per candidate, serially, then -- in this order -- status, num_inliers, chi per inlier, inlier ratio.
+    candidate_slices[k]: the slice list of candidate k (same configuration, candidate k's moving cloud)."""
+    out = []
+    for slices, g in zip(candidate_slices, guesses):
+        r = icp_run(dim, slices, ap, g)                                   # :75-78 setMoving / setMovingInFixed / compute
+        res = dict(aligner_status=r["status"], iterations=len(r["stats"]), T=r["T"], num_correspondences=0,
+                   num_inliers=0, chi_inliers=np.float32(0))
+        out.append(res)
+        if r["status"] != 0:                                               # :80-84
+            res["verdict"] = CLOSURE_ALIGNER_DROP
+            continue
+        istat = r["stats"][-1]                                             # :86
+        ncorr = 0                                                          # multi_aligner_impl.cpp:275-285
+        for s, c in zip(slices, r["correspondences"]):
+            ncorr += 1 if c is None else len(c[0])                         # a prior slice counts 1
+        ninl = istat["num_inliers"]
+        chi = np.float32(istat["chi_inliers"]) / np.float32(ninl)          # :91
+        res.update(num_correspondences=ncorr, num_inliers=ninl, chi_inliers=np.float32(chi))
+        if ninl < min_inliers:                                             # :94
+            res["verdict"] = CLOSURE_NUM_INLIERS_DROP
+        elif chi > np.float32(max_chi_inliers):                            # :99
+            res["verdict"] = CLOSURE_MAX_CHI_DROP
+        elif np.float32(ninl) / np.float32(ncorr) < np.float32(min_inliers_ratio):  # :105
+            res["verdict"] = CLOSURE_INLIER_RATIO_DROP
+        else:
+            res["verdict"] = CLOSURE_ACCEPT
+    return out
+
+
 def scales(dim, variable, radius_bound2, fp, fa, normal_bound2=1.0):
     s = Scales()
     lib().orc_scales(dim, variable, radius_bound2, normal_bound2, C.byref(fp), C.byref(fa), C.byref(s))

@@ -26,6 +26,7 @@ EXPORTED_SYMBOLS = [
     "srrg2b_find_correspondences", "srrg2b_set_correspondences", "srrg2b_linearize", "srrg2b_icp_run",
     "srrg2b_icp_iterate", "srrg2b_get_correspondences", "srrg2b_reset_correspondences", "srrg2b_last_run_timing",
     "srrg2b_set_kernel_timing", "srrg2b_last_kernel_timing", "srrg2b_debug_info",
+    "srrg2b_share_fixed", "srrg2b_closure_batch",
     "srrg2b_pgo_upload", "srrg2b_pgo_iterate", "srrg2b_pgo_optimize", "srrg2b_pgo_download",
 ]
 
@@ -84,6 +85,20 @@ class MergeParams(C.Structure):
                 ("target_number_of_merges", C.c_int32), ("without_correspondences", C.c_int32)]
 
 
+class ClosureParams(C.Structure):
+    _fields_ = [("relocalize_min_inliers", C.c_int32), ("relocalize_max_chi_inliers", C.c_float),
+                ("relocalize_min_inliers_ratio", C.c_float)]
+
+
+class ClosureResult(C.Structure):
+    _fields_ = [("verdict", C.c_int32), ("aligner_status", C.c_int32), ("iterations", C.c_int32),
+                ("reserved", C.c_int32), ("num_correspondences", C.c_int64), ("num_inliers", C.c_int64),
+                ("chi_inliers", C.c_float), ("device_ms", C.c_float), ("moving_in_fixed", C.c_float * 16)]
+
+
+CLOSURE_ACCEPT, CLOSURE_ALIGNER_DROP, CLOSURE_NUM_INLIERS_DROP, CLOSURE_MAX_CHI_DROP, CLOSURE_INLIER_RATIO_DROP = 0, 1, 2, 3, 4
+
+
 class AlignerParams(C.Structure):
     _fields_ = [("variable", C.c_int32), ("max_iterations", C.c_int32), ("min_num_inliers", C.c_int32),
                 ("enable_inlier_only_runs", C.c_int32), ("keep_only_inlier_correspondences", C.c_int32),
@@ -130,6 +145,9 @@ def load_library():
     lib.srrg2b_scene_clip_indices.argtypes = [vp, C.c_int, vp]
     lib.srrg2b_scene_merge.argtypes = [vp, C.c_int, C.c_int, vp, C.POINTER(MergeParams), i64p, i64p]
     lib.srrg2b_scene_get.argtypes = [vp, C.c_int, vp, vp, vp, i64p]
+    lib.srrg2b_share_fixed.argtypes = [vp, C.c_int, vp, C.c_int]
+    lib.srrg2b_closure_batch.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.POINTER(Slice), C.POINTER(AlignerParams), vp,
+                                         C.POINTER(ClosureParams), C.POINTER(ClosureResult)]
     lib.srrg2b_last_run_timing.argtypes = [vp, C.POINTER(C.c_float), i32p]
     lib.srrg2b_debug_info.argtypes = [vp, C.c_int, vp]
     lib.srrg2b_pgo_upload.argtypes = [vp, C.c_int64, vp, vp, C.c_int64, vp, vp, vp]
@@ -183,6 +201,34 @@ def make_slice(dim, slice_id=0, robot_in_sensor=None, fp=None, fa=None, min_num_
     s.finder = fp
     s.factor = fa
     return s
+
+
+def closure_params(relocalize_min_inliers=500, relocalize_max_chi_inliers=0.005, relocalize_min_inliers_ratio=0.7):
+    """Defaults of MultiLoopDetectorBruteForce_ (multi_loop_detector_brute_force.h:25-40)."""
+    return ClosureParams(relocalize_min_inliers, relocalize_max_chi_inliers, relocalize_min_inliers_ratio)
+
+
+def closure_batch(contexts, slices, ap, guesses, cp):
+    """srrg2b_closure_batch: the detector's aligner over K candidate contexts, all runs in flight together."""
+    k = len(contexts)
+    if k == 0:
+        return []
+    dim = contexts[0].dim
+    D1 = dim + 1
+    lib = contexts[0].lib
+    hs = (C.c_void_p * k)(*[c.h for c in contexts])
+    n = len(slices)
+    arr = (Slice * n)(*slices)
+    g = np.ascontiguousarray(np.asarray(guesses, dtype=np.float32).reshape(k, D1 * D1))
+    res = (ClosureResult * k)()
+    contexts[0]._check(lib.srrg2b_closure_batch(hs, k, n, arr, C.byref(ap), g.ctypes.data, C.byref(cp), res))
+    out = []
+    for r in res:
+        out.append(dict(verdict=r.verdict, aligner_status=r.aligner_status, iterations=r.iterations,
+                        num_correspondences=r.num_correspondences, num_inliers=r.num_inliers,
+                        chi_inliers=np.float32(r.chi_inliers), device_ms=r.device_ms,
+                        T=np.array(r.moving_in_fixed[:D1 * D1], dtype=np.float32).reshape(D1, D1)))
+    return out
 
 
 def _ptr(a):
@@ -337,6 +383,10 @@ class Context:
         self._check(self.lib.srrg2b_icp_run(self.h, n, arr, C.byref(ap), T.ctypes.data, stats, C.byref(n_stats),
                                             C.byref(status)))
         return dict(T=T, status=status.value, stats=[stats[i].as_dict() for i in range(min(n_stats.value, cap))])
+
+    def share_fixed(self, slice_id, src, src_slice_id):
+        """Borrow the fixed cloud and NN index of another context's slice (srrg2b_share_fixed): no copy."""
+        self._check(self.lib.srrg2b_share_fixed(self.h, slice_id, src.h, src_slice_id))
 
     def icp_iterate(self, slices, variable, T):
         D1 = self.dim + 1

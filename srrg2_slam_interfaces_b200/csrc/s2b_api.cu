@@ -18,6 +18,7 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <array>
 
 using namespace s2b;
 
@@ -57,7 +58,11 @@ template <typename T>
 struct DevBuf {
   T* p = nullptr;
   size_t cap = 0;
+  // borrowed: the memory belongs to another context (srrg2b_share_fixed) and is read-only here.  ensure() announces
+  // a write, so it lets go of a borrowed buffer and allocates a private one.
+  bool borrowed = false;
   cudaError_t ensure(size_t n) {
+    if (borrowed) { p = nullptr; cap = 0; borrowed = false; }
     if (n <= cap) return cudaSuccess;
     if (p) cudaFree(p);
     p = nullptr;
@@ -67,9 +72,16 @@ struct DevBuf {
     return e;
   }
   void release() {
-    if (p) cudaFree(p);
+    if (p && !borrowed) cudaFree(p);
     p = nullptr;
     cap = 0;
+    borrowed = false;
+  }
+  void borrow(const DevBuf<T>& o) {
+    release();
+    p = o.p;
+    cap = o.cap;
+    borrowed = o.p != nullptr;
   }
 };
 
@@ -1048,8 +1060,16 @@ int run_plan(srrg2b_ctx* c, const Plan& plan, const Mat4f& T0, int iterations, i
   return SRRG2B_OK;
 }
 
-int fetch_state(srrg2b_ctx* c) {
+int fetch_state_async(srrg2b_ctx* c) {
   CK(c, cudaMemcpyAsync(c->h_state, c->d_state, sizeof(DevState), cudaMemcpyDeviceToHost, c->stream));
+  return SRRG2B_OK;
+}
+int fetch_state_wait(srrg2b_ctx* c);
+int fetch_state(srrg2b_ctx* c) {
+  const int rcode = fetch_state_async(c);
+  return rcode ? rcode : fetch_state_wait(c);
+}
+int fetch_state_wait(srrg2b_ctx* c) {
   CK(c, cudaStreamSynchronize(c->stream));
   if (c->h_state->error == 1) FAIL(c, SRRG2B_ERR_NCCL, "peer exchange timed out: a rank never delivered its accumulators");
   if (c->h_state->error == 2) FAIL(c, SRRG2B_ERR_CUDA, "grid barrier of the device loop timed out");
@@ -1116,6 +1136,113 @@ int export_corr(srrg2b_ctx* c, SliceData& sd, int prune, bool want_stat, int32_t
     CK(c, cudaStreamSynchronize(c->stream));
   }
   *n_out = m;
+  return SRRG2B_OK;
+}
+
+// MultiAlignerBase_::compute() (R/registration/aligners/multi_aligner_impl.cpp:46-95, :162-180) in three host steps, so
+// that several contexts can have their runs in flight at once (srrg2b_closure_batch): begin() queues the first run
+// and the read-back of its state, mid() waits for it, decides the status and queues the inlier-only run when one is
+// due, end() waits for that and writes the results.  srrg2b_icp_run is begin + mid + end on one context.
+struct RunCall {
+  srrg2b_ctx* c;
+  int n_slices;
+  const srrg2b_slice* slices;
+  const srrg2b_aligner_params* ap;
+  float* T;
+  srrg2b_iter_stats* stats_out;
+  int32_t* n_stats;
+  int32_t* aligner_status;
+  Mat4f T0 = {};
+  bool want_status = false, done = false, second = false;
+  int status = SRRG2B_ALIGNER_FAIL;
+};
+
+int run_begin(RunCall& r) {
+  srrg2b_ctx* c = r.c;
+  const srrg2b_aligner_params* ap = r.ap;
+  if (!ap || !r.T || !r.aligner_status) FAIL(c, SRRG2B_ERR_INVALID, "null argument");
+  if (ap->max_iterations < 0) FAIL(c, SRRG2B_ERR_INVALID, "max_iterations < 0");
+  int rcode = validate_slices(c, r.n_slices, r.slices, ap->variable);
+  if (rcode) return rcode;
+  CK(c, cudaSetDevice(c->device));
+  r.want_status = ap->keep_only_inlier_correspondences != 0;
+  Plan plan;
+  rcode = make_plan(c, r.n_slices, r.slices, *ap, false, r.want_status, plan);
+  if (rcode) return rcode;
+  if (!rigid_enough(c->dim, r.T)) FAIL(c, SRRG2B_ERR_INVALID, "initial guess is not a rigid transform");
+  embed(c->dim, r.T, r.T0);
+  for (int s = 0; s < r.n_slices; ++s)
+    if (r.slices[s].kind == SRRG2B_SLICE_POINTS) c->slices[r.slices[s].slice_id].have_last_S = false;
+  CK(c, cudaEventRecord(c->ev0, c->stream));
+  rcode = run_plan(c, plan, r.T0, ap->max_iterations, 1, 1, 0);  // multi_aligner_impl.cpp:72
+  if (rcode) return rcode;
+  CK(c, cudaEventRecord(c->ev1, c->stream));
+  return fetch_state_async(c);
+}
+
+int run_mid(RunCall& r) {
+  srrg2b_ctx* c = r.c;
+  const srrg2b_aligner_params* ap = r.ap;
+  CK(c, cudaSetDevice(c->device));
+  int rcode = fetch_state_wait(c);
+  if (rcode) return rcode;
+  float ms = 0.f;
+  CK(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+  c->last_ms = ms;
+  c->last_iterations = c->h_state->iterations_run;
+  const DevState* hs = c->h_state;
+  if (hs->n_stats == 0) {  // :75-78
+    r.status = SRRG2B_ALIGNER_FAIL;
+    r.done = true;
+  } else if (hs->last_stats.num_inliers < ap->min_num_inliers) {  // :81-85 (newest entry, also when the array is full)
+    r.status = SRRG2B_ALIGNER_NOT_ENOUGH_INLIERS;
+    r.done = true;
+  }
+  if (!r.done && ap->enable_inlier_only_runs) {  // _postCompute, :162-175
+    Plan plan2;
+    rcode = make_plan(c, r.n_slices, r.slices, *ap, true, r.want_status, plan2);
+    if (rcode) return rcode;
+    CK(c, cudaEventRecord(c->ev0, c->stream));
+    rcode = run_plan(c, plan2, r.T0, ap->max_iterations, 0, 0, 1);
+    if (rcode) return rcode;
+    CK(c, cudaEventRecord(c->ev1, c->stream));
+    r.second = true;
+    return fetch_state_async(c);
+  }
+  return SRRG2B_OK;
+}
+
+int run_end(RunCall& r) {
+  srrg2b_ctx* c = r.c;
+  CK(c, cudaSetDevice(c->device));
+  if (r.second) {
+    const int rcode = fetch_state_wait(c);
+    if (rcode) return rcode;
+    float ms = 0.f;
+    CK(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    c->last_ms += ms;
+    c->last_iterations = c->h_state->iterations_run;
+  }
+  Mat4f X = c->h_state->X;
+  if (!r.done) {
+    fix_transform(c->dim, X);  // :90-93
+    r.status = SRRG2B_ALIGNER_SUCCESS;
+  }
+  unembed(c->dim, X, r.T);
+  const int have = std::min(c->h_state->n_stats, kMaxStats);
+  if (r.stats_out && r.n_stats) {
+    const int cap = *r.n_stats;
+    for (int i = 0; i < have && i < cap; ++i) r.stats_out[i] = c->h_state->stats[i];
+  }
+  if (r.n_stats) *r.n_stats = c->h_state->n_stats;
+  *r.aligner_status = r.status;
+  for (int s = 0; s < r.n_slices; ++s) {
+    if (r.slices[s].kind != SRRG2B_SLICE_POINTS) continue;
+    SliceData& sd = c->slices[r.slices[s].slice_id];
+    sd.corr_valid = c->h_state->iterations_run > 0;
+    sd.stat_valid = r.want_status && sd.corr_valid;
+    sd.prune_on_export = (!r.done && r.want_status) ? 1 : 0;  // :177-180
+  }
   return SRRG2B_OK;
 }
 
@@ -1746,75 +1873,120 @@ int srrg2b_linearize(srrg2b_ctx* c, int slice_id, const float* S, int variable, 
 int srrg2b_icp_run(srrg2b_ctx* c, int n_slices, const srrg2b_slice* slices, const srrg2b_aligner_params* ap,
                    float* T, srrg2b_iter_stats* stats_out, int32_t* n_stats, int32_t* aligner_status) {
   if (!c) return SRRG2B_ERR_INVALID;
-  if (!ap || !T || !aligner_status) FAIL(c, SRRG2B_ERR_INVALID, "null argument");
-  if (ap->max_iterations < 0) FAIL(c, SRRG2B_ERR_INVALID, "max_iterations < 0");
-  int rcode = validate_slices(c, n_slices, slices, ap->variable);
-  if (rcode) return rcode;
-  CK(c, cudaSetDevice(c->device));
-  const bool want_status = ap->keep_only_inlier_correspondences != 0;
-  Plan plan;
-  rcode = make_plan(c, n_slices, slices, *ap, false, want_status, plan);
-  if (rcode) return rcode;
-  if (!rigid_enough(c->dim, T)) FAIL(c, SRRG2B_ERR_INVALID, "initial guess is not a rigid transform");
-  Mat4f T0;
-  embed(c->dim, T, T0);
-  for (int s = 0; s < n_slices; ++s)
-    if (slices[s].kind == SRRG2B_SLICE_POINTS) c->slices[slices[s].slice_id].have_last_S = false;
-  CK(c, cudaEventRecord(c->ev0, c->stream));
-  rcode = run_plan(c, plan, T0, ap->max_iterations, 1, 1, 0);  // multi_aligner_impl.cpp:72
-  if (rcode) return rcode;
-  CK(c, cudaEventRecord(c->ev1, c->stream));
-  rcode = fetch_state(c);
-  if (rcode) return rcode;
-  float ms = 0.f;
-  CK(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
-  c->last_ms = ms;
-  c->last_iterations = c->h_state->iterations_run;
-  int status = SRRG2B_ALIGNER_FAIL;
-  bool done = false;
-  const DevState* hs = c->h_state;
-  if (hs->n_stats == 0) {  // :75-78
-    status = SRRG2B_ALIGNER_FAIL;
-    done = true;
-  } else {
-    if (hs->last_stats.num_inliers < ap->min_num_inliers) {  // :81-85 (newest entry, also when the array is full)
-      status = SRRG2B_ALIGNER_NOT_ENOUGH_INLIERS;
-      done = true;
+  RunCall r{c, n_slices, slices, ap, T, stats_out, n_stats, aligner_status};
+  int rcode = run_begin(r);
+  if (!rcode) rcode = run_mid(r);
+  if (!rcode) rcode = run_end(r);
+  return rcode;
+}
+
+// ---- N3: candidate-batched loop closing ----
+int srrg2b_share_fixed(srrg2b_ctx* dst, int dst_slice_id, srrg2b_ctx* src, int src_slice_id) {
+  if (!dst || !src) return SRRG2B_ERR_INVALID;
+  if (dst == src && dst_slice_id == src_slice_id) FAIL(dst, SRRG2B_ERR_INVALID, "a slice cannot borrow from itself");
+  if (dst->dim != src->dim || dst->device != src->device) FAIL(dst, SRRG2B_ERR_INVALID, "contexts differ in dimension or device");
+  if (!src->slices.count(src_slice_id) || !src->slices[src_slice_id].fixed_raw.present)
+    FAIL(dst, SRRG2B_ERR_STATE, "source slice has no fixed cloud");
+  CK(dst, cudaSetDevice(dst->device));
+  SliceData& a = src->slices[src_slice_id];
+  // everything the source queued for this cloud (upload, index build, normal bound) has to be complete: the
+  // borrower's stream does not know the source's events
+  CK(dst, cudaStreamSynchronize(src->copy_stream));
+  CK(dst, cudaStreamSynchronize(src->stream));
+  int rcode = resolve_normal_bound(src, a.fixed_raw);
+  if (rcode) { dst->err = src->err; return rcode; }
+  CK(dst, cudaStreamSynchronize(dst->stream));  // a run on the borrower's previous fixed cloud may still be in flight
+  SliceData& b = dst->slices[dst_slice_id];
+  RawCloud& ra = a.fixed_raw;
+  RawCloud& rb = b.fixed_raw;
+  rb.xyz.borrow(ra.xyz); rb.nrm.borrow(ra.nrm); rb.valid.borrow(ra.valid);
+  rb.n = ra.n; rb.n_global = ra.n_global; rb.index_offset = ra.index_offset;
+  rb.has_normals = ra.has_normals; rb.has_valid = ra.has_valid; rb.present = true;
+  rb.nb2 = ra.nb2; rb.nb2_pending = false;
+  b.f_pts.borrow(a.f_pts); b.f_rec.borrow(a.f_rec); b.f_inverse.borrow(a.f_inverse);
+  b.cell_start.borrow(a.cell_start); b.near_bits.borrow(a.near_bits); b.image.borrow(a.image);
+  b.nf_valid = a.nf_valid;
+  b.built_for_max_distance = a.built_for_max_distance;
+  b.ox = a.ox; b.oy = a.oy; b.oz = a.oz; b.inv_cell = a.inv_cell;
+  b.nx = a.nx; b.ny = a.ny; b.nz = a.nz; b.R = a.R; b.xbits = a.xbits; b.nx_coarse = a.nx_coarse; b.xf = a.xf;
+  b.cached_R = a.cached_R; b.cached_R_n = a.cached_R_n; b.cached_R_md = a.cached_R_md;
+  b.last_max_distance = a.last_max_distance;
+  b.index_is_projective = a.index_is_projective;
+  b.proj_params = a.proj_params;
+  b.corr_valid = false;
+  b.have_last_S = false;
+  return SRRG2B_OK;
+}
+
+int srrg2b_closure_batch(srrg2b_ctx* const* ctxs, int k, int n_slices, const srrg2b_slice* slices,
+                         const srrg2b_aligner_params* ap, const float* guesses, const srrg2b_closure_params* cp,
+                         srrg2b_closure_result* results) {
+  if (!ctxs || k < 0) return SRRG2B_ERR_INVALID;
+  if (k == 0) return SRRG2B_OK;
+  for (int i = 0; i < k; ++i) if (!ctxs[i]) return SRRG2B_ERR_INVALID;
+  srrg2b_ctx* c0 = ctxs[0];
+  if (!slices || !ap || !guesses || !cp || !results) FAIL(c0, SRRG2B_ERR_INVALID, "null argument");
+  for (int i = 0; i < k; ++i) {
+    if (ctxs[i]->dim != c0->dim) FAIL(c0, SRRG2B_ERR_INVALID, "contexts differ in dimension");
+    for (int j = 0; j < i; ++j) if (ctxs[j] == ctxs[i]) FAIL(c0, SRRG2B_ERR_INVALID, "a context appears twice in the batch");
+  }
+  const int D1 = c0->dim + 1, DD = D1 * D1;
+  std::vector<RunCall> calls;
+  std::vector<std::array<float, 16>> T(k);
+  std::vector<int32_t> status(k, SRRG2B_ALIGNER_FAIL);
+  calls.reserve(k);
+  for (int i = 0; i < k; ++i) {
+    for (int e = 0; e < DD; ++e) T[i][e] = guesses[(size_t) i * DD + e];
+    calls.push_back(RunCall{ctxs[i], n_slices, slices, ap, T[i].data(), nullptr, nullptr, &status[i]});
+  }
+  // the three host steps of compute(), each over all candidates: while the host waits for candidate i, the runs of
+  // the candidates behind it are executing
+  int first_error = SRRG2B_OK;
+  auto note = [&](int i, int rcode) {
+    if (rcode && !first_error) { first_error = rcode; if (ctxs[i] != c0) c0->err = ctxs[i]->err; }
+    return rcode;
+  };
+  std::vector<char> alive(k, 1);
+  for (int i = 0; i < k; ++i) if (note(i, run_begin(calls[i]))) alive[i] = 0;
+  for (int i = 0; i < k; ++i) if (alive[i] && note(i, run_mid(calls[i]))) alive[i] = 0;
+  for (int i = 0; i < k; ++i) if (alive[i] && note(i, run_end(calls[i]))) alive[i] = 0;
+  if (first_error) {  // leave no run in flight behind an error
+    for (int i = 0; i < k; ++i) cudaStreamSynchronize(ctxs[i]->stream);
+    return first_error;
+  }
+  int n_prior = 0;
+  for (int s = 0; s < n_slices; ++s) n_prior += slices[s].kind != SRRG2B_SLICE_POINTS;
+  for (int i = 0; i < k; ++i) {
+    srrg2b_ctx* c = ctxs[i];
+    srrg2b_closure_result& r = results[i];
+    memset(&r, 0, sizeof(r));
+    const DevState* hs = c->h_state;
+    r.aligner_status = status[i];
+    r.iterations = hs->n_stats;
+    r.device_ms = c->last_ms;
+    for (int e = 0; e < DD; ++e) r.moving_in_fixed[e] = T[i][e];
+    if (status[i] != SRRG2B_ALIGNER_SUCCESS) {  // :80-84
+      r.verdict = SRRG2B_CLOSURE_ALIGNER_DROP;
+      continue;
     }
-  }
-  if (!done && ap->enable_inlier_only_runs) {  // _postCompute, :162-175
-    Plan plan2;
-    rcode = make_plan(c, n_slices, slices, *ap, true, want_status, plan2);
-    if (rcode) return rcode;
-    CK(c, cudaEventRecord(c->ev0, c->stream));
-    rcode = run_plan(c, plan2, T0, ap->max_iterations, 0, 0, 1);
-    if (rcode) return rcode;
-    CK(c, cudaEventRecord(c->ev1, c->stream));
-    rcode = fetch_state(c);
-    if (rcode) return rcode;
-    CK(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
-    c->last_ms += ms;
-    c->last_iterations = c->h_state->iterations_run;
-  }
-  Mat4f X = c->h_state->X;
-  if (!done) {
-    fix_transform(c->dim, X);  // :90-93
-    status = SRRG2B_ALIGNER_SUCCESS;
-  }
-  unembed(c->dim, X, T);
-  const int have = std::min(c->h_state->n_stats, kMaxStats);
-  if (stats_out && n_stats) {
-    const int cap = *n_stats;
-    for (int i = 0; i < have && i < cap; ++i) stats_out[i] = c->h_state->stats[i];
-  }
-  if (n_stats) *n_stats = c->h_state->n_stats;
-  *aligner_status = status;
-  for (int s = 0; s < n_slices; ++s) {
-    if (slices[s].kind != SRRG2B_SLICE_POINTS) continue;
-    SliceData& sd = c->slices[slices[s].slice_id];
-    sd.corr_valid = c->h_state->iterations_run > 0;
-    sd.stat_valid = want_status && sd.corr_valid;
-    sd.prune_on_export = (!done && want_status) ? 1 : 0;  // :177-180
+    const srrg2b_iter_stats& is = hs->last_stats;  // iterationStats().back(), :86
+    int64_t ncorr = n_prior;  // AlignerSliceProcessorPrior_::numCorrespondences() == 1
+    for (int s = 0; s < n_slices; ++s) {
+      if (slices[s].kind != SRRG2B_SLICE_POINTS) continue;
+      SliceData& sd = c->slices[slices[s].slice_id];
+      int64_t m = 0;
+      const int rcode = export_corr(c, sd, sd.prune_on_export, false, nullptr, nullptr, nullptr, nullptr, nullptr, &m);
+      if (rcode) { if (c != c0) c0->err = c->err; return rcode; }
+      ncorr += m;
+    }
+    r.num_correspondences = ncorr;
+    r.num_inliers = is.num_inliers;
+    r.chi_inliers = (float) is.chi_inliers / (float) is.num_inliers;  // :91 (IterationStats holds floats upstream)
+    if (is.num_inliers < (int64_t) cp->relocalize_min_inliers) { r.verdict = SRRG2B_CLOSURE_NUM_INLIERS_DROP; continue; }
+    if (r.chi_inliers > cp->relocalize_max_chi_inliers) { r.verdict = SRRG2B_CLOSURE_MAX_CHI_DROP; continue; }
+    const float ratio = (float) is.num_inliers / (float) ncorr;  // :105
+    if (ratio < cp->relocalize_min_inliers_ratio) { r.verdict = SRRG2B_CLOSURE_INLIER_RATIO_DROP; continue; }
+    r.verdict = SRRG2B_CLOSURE_ACCEPT;
   }
   return SRRG2B_OK;
 }
