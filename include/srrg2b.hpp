@@ -389,6 +389,138 @@ private:
 };
 
 // ---------------------------------------------------------------------------------------------
+// MultiLoopDetectorBruteForce_ / MultiRelocalizer_ candidate loop:
+// R/registration/loop_detector/multi_loop_detector_brute_force_impl.cpp:63-133.  The reference aligns the K
+// candidate local maps one after the other with ONE aligner; here every candidate gets a context of its own (created
+// on demand, kept between calls), the source map is uploaded and indexed once and lent to all of them, and the K
+// runs are in flight together.  Same parameters, same gates, same order of the detected closures.
+// ---------------------------------------------------------------------------------------------
+template <int Dim>
+class LoopDetectorBruteForceB200 {
+public:
+  using CloudType = PointNormalCloud<Dim>;
+  using EstimateType = Isometry<Dim>;
+  using SliceProcessor = typename MultiAlignerB200<Dim>::SliceProcessor;
+
+  // multi_loop_detector_brute_force.h:25-40 (same names and defaults)
+  int param_relocalize_min_inliers = 500;
+  float param_relocalize_max_chi_inliers = 0.005f;
+  float param_relocalize_min_inliers_ratio = 0.7f;
+  // param_relocalize_aligner: one point slice (finder / factor / robustifier) + the aligner's own parameters
+  SliceProcessor aligner_slice;
+  int aligner_max_iterations = 10, aligner_min_num_inliers = 10;
+  bool aligner_enable_inlier_only_runs = false, aligner_keep_only_inlier_correspondences = false;
+  int variable = SRRG2B_VAR_SE3_QUAT_RIGHT;
+
+  struct Hint {  // LoopClosureHint: target local map + initial guess (:64-76)
+    const CloudType* local_map = nullptr;
+    EstimateType initial_guess = EstimateType::Identity();
+  };
+  struct Closure {  // what the LoopClosure factor is built from (:113-127)
+    int target = -1;  // index of the hint
+    EstimateType moving_in_fixed = EstimateType::Identity();
+    float chi_inliers = 0.f;
+    int64_t num_inliers = 0, num_correspondences = 0;
+  };
+
+  explicit LoopDetectorBruteForceB200(int device = 0) : _device(device), _source(std::make_shared<Context>(Dim, device)) {}
+
+  // aligner->setFixed(&source_local_map->dynamic_properties) (:63)
+  void setSource(const CloudType* source) { _fixed = source; _fixed_changed = true; }
+  const std::vector<Closure>& detectedClosures() const { return _detected; }
+  const std::vector<srrg2b_closure_result>& results() const { return _results; }
+
+  void compute(const std::vector<Hint>& hints) {
+    _detected.clear();
+    _results.clear();
+    if (!_fixed) throw std::runtime_error("LoopDetectorBruteForceB200::compute|no source local map");
+    srrg2b_slice d;
+    std::memset(&d, 0, sizeof(d));
+    detail::embed(aligner_slice.robot_in_sensor, d.robot_in_sensor);
+    detail::embed(EstimateType::Identity(), d.prior_measurement);
+    d.kind = SRRG2B_SLICE_POINTS;
+    d.slice_id = 0;
+    d.min_num_correspondences = aligner_slice.param_min_num_correspondences;
+    d.finder.kind = aligner_slice.finder_kind;
+    d.finder.max_distance = aligner_slice.finder_max_distance_m;
+    d.finder.normal_cos = aligner_slice.finder_normal_cos;
+    d.factor.factor = aligner_slice.factor;
+    d.factor.robustifier = aligner_slice.robustifier;
+    d.factor.chi_threshold = aligner_slice.robustifier_chi_threshold;
+    d.factor.info_point = aligner_slice.info_point;
+    d.factor.info_normal = aligner_slice.info_normal;
+    srrg2b_aligner_params ap;
+    std::memset(&ap, 0, sizeof(ap));
+    ap.variable = variable;
+    ap.max_iterations = aligner_max_iterations;
+    ap.min_num_inliers = aligner_min_num_inliers;
+    ap.enable_inlier_only_runs = aligner_enable_inlier_only_runs ? 1 : 0;
+    ap.keep_only_inlier_correspondences = aligner_keep_only_inlier_correspondences ? 1 : 0;
+    ap.window_size = 5; ap.num_correspondences_range = 20; ap.num_inliers_range = 20; ap.num_outliers_range = 20;
+    ap.chi_epsilon = 0.2f;
+    // candidates without a local map are skipped (:70-72)
+    std::vector<int> live;
+    for (size_t k = 0; k < hints.size(); ++k) if (hints[k].local_map) live.push_back((int) k);
+    if (live.empty()) return;
+    if (_fixed_changed) {
+      const srrg2b_cloud c = detail::describe(*_fixed);
+      _source->check(srrg2b_set_cloud(_source->get(), SRRG2B_FIXED, 0, &c), "LoopDetectorBruteForceB200::setSource");
+      // build the index for the detector's finder radius before lending it: a one-point find does that
+      const srrg2b_cloud m = detail::describe(*hints[(size_t) live[0]].local_map);
+      srrg2b_cloud one = m;
+      one.n = std::min<int64_t>(m.n, 1);
+      _source->check(srrg2b_set_cloud(_source->get(), SRRG2B_MOVING, 0, &one), "LoopDetectorBruteForceB200::setSource");
+      int64_t n = 0;
+      EstimateType I = EstimateType::Identity();
+      _source->check(srrg2b_find_correspondences(_source->get(), 0, I.data(), &d.finder, nullptr, nullptr, nullptr, &n),
+                     "LoopDetectorBruteForceB200::setSource");
+    }
+    while (_candidates.size() < live.size()) _candidates.push_back(std::make_shared<Context>(Dim, _device));
+    std::vector<srrg2b_ctx*> ctxs(live.size());
+    std::vector<float> guesses(live.size() * EstimateType::N);
+    for (size_t i = 0; i < live.size(); ++i) {
+      const Hint& h = hints[(size_t) live[i]];
+      Context& c = *_candidates[i];
+      if (_fixed_changed || i >= _lent) c.check(srrg2b_share_fixed(c.get(), 0, _source->get(), 0), "LoopDetectorBruteForceB200::share");
+      const srrg2b_cloud m = detail::describe(*h.local_map);  // aligner->setMoving (:76)
+      c.check(srrg2b_set_cloud(c.get(), SRRG2B_MOVING, 0, &m), "LoopDetectorBruteForceB200::setMoving");
+      std::memcpy(&guesses[i * EstimateType::N], h.initial_guess.data(), sizeof(float) * EstimateType::N);
+      ctxs[i] = c.get();
+    }
+    _lent = std::max(_lent, live.size());
+    _fixed_changed = false;
+    srrg2b_closure_params cp;
+    cp.relocalize_min_inliers = param_relocalize_min_inliers;
+    cp.relocalize_max_chi_inliers = param_relocalize_max_chi_inliers;
+    cp.relocalize_min_inliers_ratio = param_relocalize_min_inliers_ratio;
+    _results.resize(live.size());
+    _candidates[0]->check(srrg2b_closure_batch(ctxs.data(), (int) ctxs.size(), 1, &d, &ap, guesses.data(), &cp, _results.data()),
+                          "LoopDetectorBruteForceB200::compute");
+    for (size_t i = 0; i < live.size(); ++i) {
+      const srrg2b_closure_result& r = _results[i];
+      if (r.verdict != SRRG2B_CLOSURE_ACCEPT) continue;
+      Closure cl;
+      cl.target = live[i];
+      std::memcpy(cl.moving_in_fixed.data(), r.moving_in_fixed, sizeof(float) * EstimateType::N);
+      cl.chi_inliers = r.chi_inliers;
+      cl.num_inliers = r.num_inliers;
+      cl.num_correspondences = r.num_correspondences;
+      _detected.push_back(cl);
+    }
+  }
+
+private:
+  int _device;
+  ContextPtr _source;
+  std::vector<ContextPtr> _candidates;
+  size_t _lent = 0;
+  const CloudType* _fixed = nullptr;
+  bool _fixed_changed = false;
+  std::vector<Closure> _detected;
+  std::vector<srrg2b_closure_result> _results;
+};
+
+// ---------------------------------------------------------------------------------------------
 // Solver on a pose graph (a10): SE{2,3}PosePoseGeodesicErrorFactor between VariableSE2RightAD /
 // VariableSE3QuaternionRightAD poses (R/registration/loop_closure.h:110-111, R/mapping/local_map.h:64,75).
 // The context's dim selects the group: 3 -> 4x4 poses, 6x6 informations; 2 -> 3x3 poses, 3x3 informations.

@@ -27,6 +27,9 @@ namespace s2b {
 #define S2B_LOOP_STAGES 4
 #define S2B_LOOP_PPL 1
 #endif
+#ifndef S2B_FAIL_ROUNDS
+#define S2B_FAIL_ROUNDS 2  // failures of a check pass searched in place: at most this many rounds of the CTA's warps
+#endif
 // One CTA of 12 warps per SM: the lineariser wants registers (35 accumulators + ~90 temporaries of a pair),
 // not warps.  Measured on C2 (pass over 1M correspondences inside the loop kernel): 512 threads x 128
 // registers spill the accumulators: 30 us; 384 x 168: 19-21 us; 256 x 255: 21 us; two independent pairs
@@ -37,7 +40,7 @@ constexpr int kPPL = S2B_LOOP_PPL;         // pairs per lane and tile
 constexpr int kSubTile = 64;               // correspondences of one sub-tile: one pair per lane
 constexpr int kWTile = kSubTile * kPPL;    // correspondences per warp tile
 constexpr int kStages = S2B_LOOP_STAGES;
-constexpr int kFailInPlace = 2 * (S2B_LOOP_THREADS / 32);  // ... unless the CTA saw more failures than two rounds of its warps
+constexpr int kFailInPlace = S2B_FAIL_ROUNDS * (S2B_LOOP_THREADS / 32);  // ... unless the CTA saw more failures than two rounds of its warps
 constexpr int kFailCap = 48;               // coherence-check failures a CTA resolves in place per pass (one warp per
                                            // query); the rest go to the global work list
 

@@ -82,6 +82,34 @@ int main(int argc, char** argv) {
     for (const Correspondence& c : fc) { wr(out, &c.fixed_idx, 1); wr(out, &c.moving_idx, 1); wr(out, &c.response, 1); }
     if (aligner.numCorrespondences() != (int) nc) { fprintf(stderr, "numCorrespondences mismatch\n"); return 4; }
 
+    // --- MultiLoopDetectorBruteForce_::compute (multi_loop_detector_brute_force_impl.cpp:63-133): the source map
+    // against three hints -- the whole target map, a hint without a local map (skipped), half of the map ---
+    {
+      PointNormalCloud<3> half;
+      half.coordinates.assign(moving.coordinates.begin(), moving.coordinates.begin() + (moving.size() / 2) * 3);
+      half.normals.assign(moving.normals.begin(), moving.normals.begin() + (moving.size() / 2) * 3);
+      LoopDetectorBruteForceB200<3> detector(0);
+      detector.param_relocalize_min_inliers = 100;
+      detector.param_relocalize_min_inliers_ratio = 0.5f;
+      detector.aligner_slice = sp;
+      detector.aligner_max_iterations = 8;
+      detector.aligner_enable_inlier_only_runs = true;
+      detector.setSource(&fixed);
+      std::vector<LoopDetectorBruteForceB200<3>::Hint> hints(3);
+      hints[0].local_map = &moving;
+      hints[2].local_map = &half;
+      detector.compute(hints);
+      detector.compute(hints);  // a second call reuses the contexts and the lent index
+      const int32_t nr = (int32_t) detector.results().size(), nd = (int32_t) detector.detectedClosures().size();
+      wr(out, &nr, 1);
+      for (const srrg2b_closure_result& r : detector.results()) {
+        wr(out, &r.verdict, 1); wr(out, &r.aligner_status, 1); wr(out, &r.num_correspondences, 1); wr(out, &r.num_inliers, 1);
+        wr(out, &r.chi_inliers, 1); wr(out, r.moving_in_fixed, 16);
+      }
+      wr(out, &nd, 1);
+      for (const auto& cl : detector.detectedClosures()) { const int32_t t = cl.target; wr(out, &t, 1); wr(out, cl.moving_in_fixed.data(), 16); }
+    }
+
     // --- misconfiguration throws, like the reference (aligner_slice_processor_impl.cpp:13-16) ---
     bool threw = false;
     try {

@@ -63,7 +63,13 @@ def test_cpp_mirror_matches_oracle(binary, tmp_path, oracle):
     status, ns = struct.unpack_from("<ii", buf, off); off += 8
     stats = np.frombuffer(buf, stats_t, ns, off); off += ns * stats_t.itemsize
     nc = struct.unpack_from("<q", buf, off)[0]; off += 8
-    corr = np.frombuffer(buf, corr_t, nc, off)
+    corr = np.frombuffer(buf, corr_t, nc, off); off += nc * corr_t.itemsize
+    nr = struct.unpack_from("<i", buf, off)[0]; off += 4
+    res_t = np.dtype([("verdict", "<i4"), ("status", "<i4"), ("ncorr", "<i8"), ("ninl", "<i8"), ("chi", "<f4"), ("T", "<f4", (16,))])
+    res = np.frombuffer(buf, res_t, nr, off); off += nr * res_t.itemsize
+    nd = struct.unpack_from("<i", buf, off)[0]; off += 4
+    det_t = np.dtype([("target", "<i4"), ("T", "<f4", (16,))])
+    det = np.frombuffer(buf, det_t, nd, off)
     # oracle, same inputs
     F = O.CloudRef(d["fixed"], d["fixed_normals"])
     M = O.CloudRef(d["moving"], d["moving_normals"])
@@ -81,3 +87,20 @@ def test_cpp_mirror_matches_oracle(binary, tmp_path, oracle):
             assert got[key] == want[key], key
     ofi, omi, ors = o["correspondences"][0]
     assert np.array_equal(corr["f"], ofi) and np.array_equal(corr["m"], omi) and np.array_equal(corr["r"], ors)
+    # the loop detector's candidate loop (N3): hints 0 and 2 are live
+    half = O.CloudRef(d["moving"][: d["moving"].shape[0] // 2], d["moving_normals"][: d["moving"].shape[0] // 2])
+    fa = O.factor_params(O.FACTOR_PLANE, O.ROB_HUBER, 0.01)
+    ol = O.closure_loop(3, [[O.make_slice(F, M, None, fp, fa)], [O.make_slice(F, half, None, fp, fa)]],
+                        O.aligner_params(max_iterations=8, min_num_inliers=10, enable_inlier_only_runs=True),
+                        [np.eye(4, dtype=np.float32)] * 2, 100, 0.005, 0.5)
+    assert nr == 2
+    for got, want in zip(res, ol):
+        assert got["verdict"] == want["verdict"] and got["status"] == want["aligner_status"]
+        assert np.array_equal(got["T"].reshape(4, 4), want["T"])
+        if want["aligner_status"] == 0:
+            assert got["ncorr"] == want["num_correspondences"] and got["ninl"] == want["num_inliers"]
+            assert np.float32(got["chi"]) == np.float32(want["chi_inliers"])
+    accepted = [(0, 2)[k] for k, want in enumerate(ol) if want["verdict"] == O.CLOSURE_ACCEPT]
+    assert list(det["target"]) == accepted and len(accepted) >= 1
+    for dd in det:
+        assert np.array_equal(dd["T"].reshape(4, 4), ol[(0, 2).index(dd["target"])]["T"])
