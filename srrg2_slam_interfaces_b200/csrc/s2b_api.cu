@@ -215,6 +215,7 @@ struct srrg2b_ctx {
   bool graph_nccl = false;  // env SRRG2B_GRAPH_NCCL=1: capture the all-reduce too (experimental: failed the 2-GPU parity test)
   bool eager_index = true;  // env SRRG2B_EAGER_INDEX=0: build the NN index on first use only
   int small_shift = 6;  // env SRRG2B_SMALL_SHIFT
+  int far_sole_ctas = 2;  // CTAs per SM of the lone search kernel of a late iteration (env SRRG2B_FAR_SOLE_CTAS)
   int nn_flat = 3;  // thread-per-query searches walk their rows in chunks of 8 (env SRRG2B_NN_FLAT=0: one row at a time)
   int full_iters = 4;  // iterations of a run that launch the three-kernel search pipeline (env SRRG2B_FULL_ITERS)
   long long timeout_cycles = 4000000000ll;  // ~2 s of SM clock: the peer exchange gives up (env SRRG2B_TIMEOUT_MS)
@@ -742,7 +743,7 @@ int fill_slice_args(srrg2b_ctx* c, SliceData& sd, int state_slot, const srrg2b_f
 void launch_far(srrg2b_ctx* c, const SliceArgs& a_in, int factor, const int* skip) {
   const int threads = 256;
   SliceArgs a = a_in;
-  const int fblocks = std::max(1, std::min(blocks_for((int64_t) a.nm * 32, threads), c->sm_count * 8));
+  const int fblocks = std::max(1, std::min(blocks_for((int64_t) a.nm * 32, threads), c->sm_count * (a.sole_list ? c->far_sole_ctas : 8)));
   {  // tail mode: lane 0 of a warp linearises its share of a short (< nm / 64 + 64) work list
     const int64_t warps = (int64_t) fblocks * (threads / 32);
     const int64_t per_lane = (((int64_t) a.nm >> a.small_shift) + 64 + warps - 1) / warps;
@@ -819,7 +820,7 @@ void launch_tiles_kernel(srrg2b_ctx* c, const SliceArgs& a, int factor, K3P k3p,
 // lin_after_search_kernel -- three launches that have nothing to do in a converged iteration, yet cost 6 us of
 // every iteration in the replayed graph (measured at C2).  The first full_iters iterations of a run, which search
 // everything, keep the three-kernel pipeline.
-int launch_slice_iteration(srrg2b_ctx* c, const SliceArgs& a0, int factor, const int* skip, bool sole = false) {
+int launch_slice_iteration(srrg2b_ctx* c, const SliceArgs& a0, int factor, const int* skip, bool sole = false, bool no_check = false) {
   if (a0.nm <= 0) return SRRG2B_OK;
   if (a0.projective || skip) {  // no coherence machinery for the index-image finder / the groups in front of the loop kernel
     int rcode = launch_find(c, a0, skip);
@@ -828,8 +829,11 @@ int launch_slice_iteration(srrg2b_ctx* c, const SliceArgs& a0, int factor, const
   }
   SliceArgs a = a0;
   a.use_list = 1;  // (the work-list counters were zeroed by icp_init_kernel / the previous solve step)
-  launch_tiles_kernel(c, a, factor, check_tiles_kernel<3, SRRG2B_FACTOR_P2P>, check_tiles_kernel<3, SRRG2B_FACTOR_PLANE>,
-                      check_tiles_kernel<2, SRRG2B_FACTOR_P2P>, check_tiles_kernel<2, SRRG2B_FACTOR_PLANE>);
+  // no_check: an iteration that cannot hold certified bounds yet (the first of a fresh run; the second too unless
+  // every search certifies) -- the check kernel would read its control words and return: 2.9 us saved per launch
+  if (!no_check)
+    launch_tiles_kernel(c, a, factor, check_tiles_kernel<3, SRRG2B_FACTOR_P2P>, check_tiles_kernel<3, SRRG2B_FACTOR_PLANE>,
+                        check_tiles_kernel<2, SRRG2B_FACTOR_P2P>, check_tiles_kernel<2, SRRG2B_FACTOR_PLANE>);
   if (sole) {
     a.sole_list = 1;
     launch_far(c, a, factor, nullptr);
@@ -963,7 +967,7 @@ int allreduce_acc(srrg2b_ctx* c, int n_slices, bool in_solve_kernel) {
 
 // one _runSolver iteration (multi_aligner_impl.cpp:103-126) as a kernel sequence: full search +
 // linearisation per point slice, then the solve step.  skip: device flag that makes the whole group a no-op.
-int enqueue_iteration_group(srrg2b_ctx* c, const Plan& plan, const int* skip, bool sole = false) {
+int enqueue_iteration_group(srrg2b_ctx* c, const Plan& plan, const int* skip, bool sole = false, bool no_check = false) {
   for (int s = 0; s < plan.solve.n_slices; ++s) {
     if (!plan.is_points[s]) continue;
     if (c->time_kernels) {
@@ -974,7 +978,7 @@ int enqueue_iteration_group(srrg2b_ctx* c, const Plan& plan, const int* skip, bo
       }
       CK(c, cudaEventRecord(c->kev[c->kev_used], c->stream));
     }
-    int rcode = launch_slice_iteration(c, plan.sargs[s], plan.factor[s], skip, sole);
+    int rcode = launch_slice_iteration(c, plan.sargs[s], plan.factor[s], skip, sole, no_check);
     if (rcode) return rcode;
     if (c->time_kernels) {
       CK(c, cudaEventRecord(c->kev[c->kev_used + 1], c->stream));
@@ -990,9 +994,12 @@ int enqueue_iteration_group(srrg2b_ctx* c, const Plan& plan, const int* skip, bo
 }
 
 // enqueue `iterations` _runSolver iterations; no host sync inside
-int enqueue_iterations(srrg2b_ctx* c, const Plan& plan, int iterations) {
+int enqueue_iterations(srrg2b_ctx* c, const Plan& plan, int iterations, int keep_stats) {
   for (int it = 0; it < iterations; ++it) {
-    const int rcode = enqueue_iteration_group(c, plan, nullptr, it >= c->full_iters);
+    // a fresh run (icp_init_kernel: list_all = 1, track2 = (mode == 1)) has no bounds in its first pass, and none in
+    // its second unless the first one certified (icp_solve_serial: list_all = !track2)
+    const bool no_check = !keep_stats && (it == 0 || (it == 1 && c->track2_mode != 1));
+    const int rcode = enqueue_iteration_group(c, plan, nullptr, it >= c->full_iters, no_check);
     if (rcode) return rcode;
   }
   CK(c, cudaGetLastError());
@@ -1014,9 +1021,9 @@ int run_plan(srrg2b_ctx* c, const Plan& plan, const Mat4f& T0, int iterations, i
     icp_init_kernel<<<1, 32, 0, c->stream>>>(c->d_solve, c->d_state, c->d_T0, apply_prior_guess, reset_tc, keep_stats,
                                              iterations);
     c->launches++;
-    return enqueue_iterations(c, plan, iterations);
+    return enqueue_iterations(c, plan, iterations, keep_stats);
   }
-  const int tail[6] = {iterations, apply_prior_guess, reset_tc, keep_stats, c->full_iters, 0};
+  const int tail[6] = {iterations, apply_prior_guess, reset_tc, keep_stats, c->full_iters, c->track2_mode};
   // key = everything the launch sequence depends on (slice kernel arguments, factor kinds, counts);
   // the solve-step values are read from device memory and may change freely between replays
   const size_t nb = sizeof(plan.sargs) + sizeof(plan.factor) + sizeof(plan.is_points);
@@ -1040,7 +1047,7 @@ int run_plan(srrg2b_ctx* c, const Plan& plan, const Mat4f& T0, int iterations, i
     icp_init_kernel<<<1, 32, 0, c->stream>>>(c->d_solve, c->d_state, c->d_T0, apply_prior_guess, reset_tc, keep_stats,
                                              iterations);
     c->launches++;
-    const int rcode = enqueue_iterations(c, plan, iterations);
+    const int rcode = enqueue_iterations(c, plan, iterations, keep_stats);
     const cudaError_t e = cudaStreamEndCapture(c->stream, &g);
     const int64_t n_launch = c->launches - before;
     c->launches = before;
@@ -1293,6 +1300,7 @@ int srrg2b_ctx_create(int dim, int device, srrg2b_ctx** out) {
   }
   if (const char* env = getenv("SRRG2B_FULL_ITERS")) c->full_iters = std::max(0, atoi(env));
   if (const char* env = getenv("SRRG2B_NN_FLAT")) c->nn_flat = atoi(env);
+  if (const char* env = getenv("SRRG2B_FAR_SOLE_CTAS")) c->far_sole_ctas = std::min(8, std::max(1, atoi(env)));
   if (const char* env = getenv("SRRG2B_SMALL_SHIFT")) c->small_shift = std::min(20, std::max(0, atoi(env)));
   if (const char* env = getenv("SRRG2B_EAGER_INDEX")) c->eager_index = atoi(env) != 0;
   if (const char* env = getenv("SRRG2B_GRAPH_NCCL")) c->graph_nccl = atoi(env) != 0;

@@ -11,10 +11,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++")
-def test_adapters_instantiate_against_the_stub_surface():
+@pytest.mark.parametrize("unit", ["check_adapters.cpp", "instances_b200.cpp"])
+def test_adapters_instantiate_against_the_stub_surface(unit):
+    """check_adapters.cpp: explicit instantiations; instances_b200.cpp: the BOSS registration unit (pattern R/instances.cpp:21-85)."""
     out = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
                           "-I", os.path.join(ROOT, "adapters", "stubs"), "-I", os.path.join(ROOT, "adapters"),
-                          os.path.join(ROOT, "adapters", "check_adapters.cpp")], capture_output=True, text=True)
+                          os.path.join(ROOT, "adapters", unit)], capture_output=True, text=True)
     assert out.returncode == 0, out.stderr[-3000:]
 
 
