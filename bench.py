@@ -483,6 +483,22 @@ def run_aligner(args):
     barrier()
     gpu_launches = ctx.launch_count - launches0
     corr = [ctx.get_correspondences(s, cfg.local_moving()) for s in cfg.point_slices()]
+    # ---- the converged iterations alone (their kernel, check_tiles_kernel, is the dominant one of the run): device time
+    # of the same cold steps cut off after half of the iterations; the difference is the second half ----
+    half_ms, half_iters = 0.0, 0
+    ap_half = cfg.aligner_params(A)
+    ap_half.max_iterations = max(cfg.iters // 2, 1)
+    ctx.icp_run(sl, ap_half, T0)
+    for _ in range(args.steps):
+        for s in cfg.point_slices():
+            ctx.reset_correspondences(s)
+        flush_l2()
+        barrier()
+        ctx.icp_run(sl, ap_half, T0)
+        ms, it = ctx.last_run_timing()
+        half_ms += ms
+        half_iters += it
+    barrier()
     # ---- e2e: host buffers in, pose + stats out, every step ----
     upload_e2e()
     ctx.icp_run(sl, ap, T0)
@@ -525,10 +541,10 @@ def run_aligner(args):
     h2d_gbs = 3 * sum(x.numel() * 4 for x in srcs) / (time.perf_counter() - t0) / 1e9
     del probe
 
-    t = torch.tensor([dev_ms, e2e_s, warm_ms, -h2d_gbs, e2e_res_s], dtype=torch.float64, device="cuda")
+    t = torch.tensor([dev_ms, e2e_s, warm_ms, -h2d_gbs, e2e_res_s, half_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms_max, e2e_s_max, warm_ms_max, h2d_gbs_min, e2e_res_s_max = [float(x) for x in t.tolist()]
+    dev_ms_max, e2e_s_max, warm_ms_max, h2d_gbs_min, e2e_res_s_max, half_ms_max = [float(x) for x in t.tolist()]
     h2d_gbs_min = -h2d_gbs_min
 
     # ---- N > 1: every rank's result must be the single-process oracle's on the global clouds, bit for bit ----
@@ -563,6 +579,14 @@ def run_aligner(args):
         k_ms = dev_ms_max / max(iters_done, 1)
         abytes = cfg.algorithmic_bytes_per_iteration()
         achieved = abytes / (k_ms * 1e-3) / 1e9
+        converged = None
+        if iters_done > half_iters > 0 and dev_ms_max > half_ms_max:
+            c_ms = (dev_ms_max - half_ms_max) / (iters_done - half_iters)
+            converged = {"bound": "hbm", "achieved": abytes / (c_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": abytes / (c_ms * 1e-3) / 1e9 / peak, "kernel_ms": c_ms, "algorithmic_bytes_per_launch": abytes,
+                         "kernel": "iterations %d..%d of the same cold run (full run minus a run cut off after %d iterations, CUDA events): "
+                                   "check_tiles_kernel + the lone search kernel + icp_solve_kernel per point slice"
+                                   % (half_iters // args.steps + 1, iters_done // args.steps, half_iters // args.steps)}
         h2d = sum(host[k].nbytes for k in host if not (dev and k in dev)) + (sum(host[k].nbytes for k in dev) // world if dev else 0)
         if cfg.name == "c5":
             h2d += host["map"].nbytes + host["map_normals"].nbytes  # the map shard is uploaded once per scanner slice
@@ -580,6 +604,7 @@ def run_aligner(args):
                                        "nn_far_kernel / lin_after_search_kernel on iterations that search) + icp_solve_kernel; "
                                        "CUDA events around the graph-replayed run / iterations",
                              "kernel_ms": k_ms, "algorithmic_bytes_per_launch": abytes, "peak_source": peak_src},
+                "roofline_converged_iteration": converged,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": 1e3 * e2e_s_max / args.steps,
                         "h2d_gbs_per_rank_all_ranks_copying": h2d_gbs_min,  # slowest rank; the limiting copy of the e2e step

@@ -743,7 +743,7 @@ int fill_slice_args(srrg2b_ctx* c, SliceData& sd, int state_slot, const srrg2b_f
 void launch_far(srrg2b_ctx* c, const SliceArgs& a_in, int factor, const int* skip) {
   const int threads = 256;
   SliceArgs a = a_in;
-  const int fblocks = std::max(1, std::min(blocks_for((int64_t) a.nm * 32, threads), c->sm_count * (a.sole_list ? c->far_sole_ctas : 8)));
+  const int fblocks = std::max(1, std::min(blocks_for((int64_t) a.nm * 32, threads), c->sm_count * ((a.sole_list && a.nm <= (1 << 21)) ? c->far_sole_ctas : 8)));  // (big clouds: their late work lists are not short)
   {  // tail mode: lane 0 of a warp linearises its share of a short (< nm / 64 + 64) work list
     const int64_t warps = (int64_t) fblocks * (threads / 32);
     const int64_t per_lane = (((int64_t) a.nm >> a.small_shift) + 64 + warps - 1) / warps;
@@ -1936,6 +1936,9 @@ int srrg2b_closure_batch(srrg2b_ctx* const* ctxs, int k, int n_slices, const srr
   if (!slices || !ap || !guesses || !cp || !results) FAIL(c0, SRRG2B_ERR_INVALID, "null argument");
   for (int i = 0; i < k; ++i) {
     if (ctxs[i]->dim != c0->dim) FAIL(c0, SRRG2B_ERR_INVALID, "contexts differ in dimension");
+    // candidates are independent: several GPUs take disjoint runs of them (sharding.py: candidate_shard), they do not
+    // shard one candidate's cloud -- a context that belongs to a communicator would wait for its peers in every solve step
+    if (ctxs[i]->world > 1) FAIL(c0, SRRG2B_ERR_INVALID, "a context of the batch belongs to a multi-rank communicator");
     for (int j = 0; j < i; ++j) if (ctxs[j] == ctxs[i]) FAIL(c0, SRRG2B_ERR_INVALID, "a context appears twice in the batch");
   }
   const int D1 = c0->dim + 1, DD = D1 * D1;

@@ -863,7 +863,7 @@ __global__ void __launch_bounds__(256) nn_kernel(const SliceArgs a, const int* s
   if (small_work_list(a, all, n_work)) return;
   __shared__ float S[16];
   __shared__ int rows[16];
-  __shared__ int park_all[3 * kRowChunk * 256];
+  __shared__ int park_all[DIM == 3 ? 3 * kRowChunk * 256 : 1];  // (2D: 2 rows per ring -- the flat chunks are compiled out)
   if (threadIdx.x < 16) S[threadIdx.x] = a.S[threadIdx.x];
   if (threadIdx.x >= 32 && threadIdx.x < 32 + (DIM == 3 ? 9 : 3))
     rows[threadIdx.x - 32] = (DIM == 3) ? *reinterpret_cast<const int*>(c_rows3[threadIdx.x - 32])
@@ -874,7 +874,7 @@ __global__ void __launch_bounds__(256) nn_kernel(const SliceArgs a, const int* s
   // distance below which a point cannot lie in ring 2 or beyond (for R == 1: the covered radius)
   const float ring2 = (a.R >= 2) ? (1.f - 4e-3f) * cell : __fsqrt_rn(a.rho_s2);
   const float ring2_sq = (a.R >= 2) ? ring2 * ring2 : 3.0e38f;
-  if (a.nn_flat & 1) {
+  if (DIM == 3 && (a.nn_flat & 1)) {
     if (track2) nn_phase1_body<DIM, true, true>(a, S, cell, ring2, ring2_sq, all, n_work, rows, park);
     else nn_phase1_body<DIM, false, true>(a, S, cell, ring2, ring2_sq, all, n_work, rows, park);
   } else {
@@ -908,7 +908,7 @@ __device__ __forceinline__ void nn_far_body(const SliceArgs& a, const float* S, 
       const int p0 = slot_candidate(old_slot);
       if (a.warm && p0 >= 0) { nn_consider<DIM, TRACK2>(a, q, p0); if (TRACK2) nn_limit_bound(q, cell); }
       // (far list of phase 1, nearest point only: rings 0-1 were searched exhaustively there)
-      if (a.nn_flat & 2) {
+      if (DIM == 3 && (a.nn_flat & 2)) {
         int k = TRACK2 ? 0 : min(K, (DIM == 3 ? 9 : 3));
         if (k == 0) {
           if (q.cy >= 0 && q.cy < a.ny && q.cz >= 0 && q.cz < a.nz) nn_scan_row<DIM, TRACK2>(a, q, q.cy, q.cz, 0.f);
@@ -1278,7 +1278,7 @@ __device__ __forceinline__ void nn_full_lin_body(const SliceArgs& a, const float
     const int old_slot = __ldcg(a.c_fpos + i);
     const int p0 = slot_candidate(old_slot);
     if (a.warm && p0 >= 0) { nn_consider<DIM, TRACK2>(a, q, p0); if (TRACK2) nn_limit_bound(q, cell); }
-    if (a.nn_flat & 2) {
+    if (DIM == 3 && (a.nn_flat & 2)) {
       if (q.cy >= 0 && q.cy < a.ny && q.cz >= 0 && q.cz < a.nz) nn_scan_row<DIM, TRACK2>(a, q, q.cy, q.cz, 0.f);
       nn_scan_rings_flat<DIM, TRACK2>(a, q, rows, 1, K, cell, park, blockDim.x);
     } else
@@ -1339,7 +1339,7 @@ __global__ void __launch_bounds__(256) nn_far_kernel(const SliceArgs a, const in
   __shared__ int rows[kRowTable];
   __shared__ FlushSmem fsm;
   __shared__ LinConst lk;
-  __shared__ int park_all[3 * kRowChunk * 256];
+  __shared__ int park_all[DIM == 3 ? 3 * kRowChunk * 256 : 1];  // (2D: 2 rows per ring -- the flat chunks are compiled out)
   int* park = park_all + threadIdx.x;
   if (threadIdx.x < 16) S[threadIdx.x] = a.S[threadIdx.x];
   if (threadIdx.x == 32) make_lin_const(a, a.S, lk);

@@ -12,3 +12,12 @@ def shard_range(n, rank, world):
     base, rem = divmod(n, world)
     begin = rank * base + min(rank, rem)
     return begin, begin + base + (1 if rank < rem else 0)
+
+
+def candidate_shard(n_candidates, rank, world):
+    """Loop closing over several GPUs: the K candidate alignments of the brute-force detector are
+    independent, so they are dealt to the ranks in contiguous runs (each rank batches its own run with
+    srrg2b_closure_batch) and the per-candidate results are concatenated in rank order -- candidate order, as the
+    reference's serial loop produces them.  No data-path collective."""
+    begin, end = shard_range(n_candidates, rank, world)
+    return list(range(begin, end))

@@ -136,3 +136,72 @@ def test_sharded_pose_graph_equals_oracle():
         assert np.abs(got[:, :3, 3] - poses[:, :3, 3]).max() < 1e-4
         for (chi, _), co in zip(st, chis):
             assert abs(chi - co) <= 1e-6 * co
+
+
+# ---- loop closing over several GPUs (SURVEY 8f N3 + 8e): the detector's candidates are independent alignments; every
+# rank batches its own contiguous run of them (srrg2b_closure_batch on its GPU), results concatenated in rank order ----
+def _closure_problem(syn):
+    base = syn.make_icp2d(20000, 16, seed=9, paired=False)
+    cands = []
+    for k in range(6):
+        T_star = syn.iso2(0.02 * k, -0.015 * k, 0.004 * k)
+        d = syn.make_icp2d(20000, 4000 + 500 * k, seed=9 if k != 4 else 12, T_star=T_star, paired=False)
+        cands.append((d["moving"], d["moving_normals"]))
+    return base, cands
+
+
+def _closure_worker(rank, world, out_q):
+    sys.path.insert(0, ROOT)
+    from srrg2_slam_interfaces_b200 import capi as A
+    from srrg2_slam_interfaces_b200 import synthetic as syn
+    from srrg2_slam_interfaces_b200.sharding import candidate_shard
+    base, cands = _closure_problem(syn)
+    sl = [A.make_slice(2, 0, None, A.finder_params(0.5, 0.7), A.factor_params(A.FACTOR_PLANE, A.ROB_CAUCHY, 0.05))]
+    ap = A.aligner_params(max_iterations=10, min_num_inliers=10)
+    mine = candidate_shard(len(cands), rank, world)
+    src = A.Context(2, rank)
+    src.set_cloud(A.FIXED, 0, base["fixed"], base["fixed_normals"])
+    src.set_cloud(A.MOVING, 0, cands[0][0][:64], cands[0][1][:64])
+    src.icp_run(sl, A.aligner_params(max_iterations=1, min_num_inliers=0), np.eye(3))
+    ctxs = []
+    for k in mine:
+        x = A.Context(2, rank)
+        x.share_fixed(0, src, 0)
+        x.set_cloud(A.MOVING, 0, cands[k][0], cands[k][1])
+        ctxs.append(x)
+    res = A.closure_batch(ctxs, sl, ap, [np.eye(3, dtype=np.float32)] * len(mine), A.closure_params(500, 0.01, 0.5))
+    out_q.put((rank, [(k, r["verdict"], r["aligner_status"], r["num_correspondences"], r["num_inliers"], float(r["chi_inliers"]), r["T"])
+                      for k, r in zip(mine, res)]))
+    for x in ctxs:
+        x.close()
+    src.close()
+
+
+def test_candidates_sharded_over_gpus_equal_serial_loop(oracle):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from srrg2_slam_interfaces_b200 import synthetic as syn
+    world = 2
+    ctx = mp.get_context("spawn")
+    out_q = ctx.Queue()
+    procs = [ctx.Process(target=_closure_worker, args=(r, world, out_q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = sorted([out_q.get(timeout=300) for _ in range(world)], key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    got = [x for _, part in results for x in part]
+    base, cands = _closure_problem(syn)
+    F = oracle.CloudRef(base["fixed"], base["fixed_normals"])
+    refs = [oracle.CloudRef(m, n) for m, n in cands]
+    osl = [[oracle.make_slice(F, m, None, oracle.finder_params(0.5, 0.7), oracle.factor_params(oracle.FACTOR_PLANE, oracle.ROB_CAUCHY, 0.05), dim=2)]
+           for m in refs]
+    want = oracle.closure_loop(2, osl, oracle.aligner_params(max_iterations=10, min_num_inliers=10), [np.eye(3, dtype=np.float32)] * len(cands),
+                               500, 0.01, 0.5)
+    assert [g[0] for g in got] == list(range(len(cands)))
+    for g, w in zip(got, want):
+        assert g[1] == w["verdict"] and g[2] == w["aligner_status"], (g[:3], w["verdict"])
+        assert np.array_equal(g[6], w["T"])
+        if w["aligner_status"] == 0:
+            assert g[3] == w["num_correspondences"] and g[4] == w["num_inliers"] and np.float32(g[5]) == np.float32(w["chi_inliers"])

@@ -11,6 +11,7 @@ for cfg in c2 c5 c3 c4; do
   timeout 900 python bench.py --config $cfg $extra > $OUT/bench_$cfg.json 2> $OUT/bench_$cfg.err; echo "bench $cfg rc=$?"; cut -c1-200 $OUT/bench_$cfg.json
 done
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_reference_c2.json 2> $OUT/bench_reference_c2.err; echo "reference rc=$?"; cut -c1-200 $OUT/bench_reference_c2.json
+timeout 300 python tools/closure_bench.py 16 20000 5000 2 > $OUT/closure_bench.txt 2>&1; timeout 300 python tools/closure_bench.py 16 100000 50000 3 >> $OUT/closure_bench.txt 2>&1; cat $OUT/closure_bench.txt
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --cache-control none -c 900 --csv --log-file $OUT/launches.csv \
   python bench.py --steps 1 --warmup 2 --no-cpu-baseline > $OUT/ncu_launches.log 2>&1; echo "ncu launches rc=$?"
 python tools/launch_table.py $OUT/launches.csv > $OUT/launch_table.txt; head -8 $OUT/launch_table.txt
@@ -18,3 +19,8 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:chec
   python tools/one_run.py 1000000 20 2 > $OUT/ncu_full.log 2>&1; echo "ncu full rc=$?"
 python tools/ncu_summary.py $OUT/check_tiles.ncu-rep > $OUT/ncu_check_tiles_summary.txt 2>&1; head -12 $OUT/ncu_check_tiles_summary.txt
 rm -f $OUT/check_tiles.ncu-rep
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"nn_kernel|nn_far_kernel" -s 0 -c 6 -f -o $OUT/nn \
+  python tools/one_run.py 1000000 4 1 > $OUT/ncu_nn.log 2>&1; echo "ncu nn rc=$?"
+for k in 0 1 2; do python tools/ncu_lines2.py $OUT/nn.ncu-rep 14 $k; done > $OUT/ncu_nn_lines.txt 2>&1
+python tools/ncu_summary.py $OUT/nn.ncu-rep > $OUT/ncu_nn_summary.txt 2>&1; head -12 $OUT/ncu_nn_summary.txt
+rm -f $OUT/nn.ncu-rep

@@ -23,6 +23,19 @@ for k, sc in enumerate(m["scans"]):
     s2.append(A.make_slice(2, k, sc["robot_in_sensor"], A.finder_params(0.5, 0.7), A.factor_params(A.FACTOR_PLANE, A.ROB_CAUCHY, 0.05)))
 s2.append(A.make_slice(2, prior_measurement=syn.iso2(0.07, -0.04, 0.02), prior_info_diag=np.full(3, 100.0)))
 c2.icp_run(s2, A.aligner_params(max_iterations=8), np.eye(3)); c2.close()
+# N3: K candidates in flight on their own contexts, the fixed side lent by the source context
+src = A.Context(2)
+dd = [syn.make_icp2d(3000, 1200 + 100 * k, seed=9, T_star=syn.iso2(0.02 * k, -0.01 * k, 0.005 * k), paired=False) for k in range(4)]
+src.set_cloud(A.FIXED, 0, dd[0]["fixed"], dd[0]["fixed_normals"]); src.set_cloud(A.MOVING, 0, dd[0]["moving"], dd[0]["moving_normals"])
+sl2 = [A.make_slice(2, 0, None, A.finder_params(0.5, 0.7), A.factor_params(A.FACTOR_PLANE, A.ROB_CAUCHY, 0.05))]
+src.icp_run(sl2, A.aligner_params(max_iterations=2), np.eye(3))
+cx = []
+for x in dd:
+    q = A.Context(2); q.share_fixed(0, src, 0); q.set_cloud(A.MOVING, 0, x["moving"], x["moving_normals"]); cx.append(q)
+cb = A.closure_batch(cx, sl2, A.aligner_params(max_iterations=8, enable_inlier_only_runs=True, keep_only_inlier_correspondences=True),
+                     [np.eye(3, dtype=np.float32)] * 4, A.closure_params(100, 0.01, 0.5))
+for q in cx: q.close()
+src.close()
 g = syn.make_pose_graph3d(300, 1200, seed=4, box=(6, 6, 2))
 c3 = A.Context(3); c3.pgo_upload(g["guess"], g["fixed"], g["ij"], g["Z"], g["Omega"]); h = c3.pgo_optimize(max_iterations=8); c3.close()
 print("sanitizer case done:", r["status"], len(h))
