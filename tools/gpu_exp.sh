@@ -1,5 +1,5 @@
 #!/bin/bash
 TAG=${1:-exp}; OUT=$PWD/gpurun_out/$TAG; mkdir -p $OUT
-timeout 600 python -m pytest tests/test_gpu_pgo.py -m gpu -x -q 2>&1 | tail -2
-timeout 900 python bench.py --config c4 --no-cpu-baseline > $OUT/bench_c4.json 2> $OUT/bench_c4.err; python -c "
-import json; d=json.load(open('$OUT/bench_c4.json')); print(d['ms_per_step'], d['value'], d['result_check']['cg_iterations'], d['result_check']['solve_ms'])"
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -2
+for r in 1 2; do timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu-baseline 2> $OUT/err.txt | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['value'])"; done
+timeout 600 python bench.py --config c5 --steps 5 --warmup 3 --no-cpu-baseline 2> $OUT/err.txt | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['value'])"
