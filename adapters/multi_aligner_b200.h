@@ -26,12 +26,12 @@ public:
 
   ~MultiAlignerB200_() override { if (_ctx) srrg2b_ctx_destroy(_ctx); }
 
-  void compute() override {
+  // The aligner's configuration as the C ABI takes it: one srrg2b_slice per slice processor, in order.  No cloud is
+  // touched (the loop-detector adapter describes the slices once and runs them on its own contexts).
+  void describeSlices(std::vector<srrg2b_slice>& slices) {
     const size_t n_slices = this->param_slice_processors.size();
-    if (n_slices == 0 || n_slices > SRRG2B_MAX_SLICES) throw std::runtime_error("MultiAlignerB200_::compute|bad number of slice processors");
-    if (!_ctx) srrg2b_adapters::check(nullptr, srrg2b_ctx_create(Dim, param_device.value(), &_ctx) == SRRG2B_OK ? SRRG2B_OK : SRRG2B_ERR_CUDA,
-                                      "MultiAlignerB200_|no usable CUDA device (there is no CPU fallback)");
-    std::vector<srrg2b_slice> slices(n_slices);
+    if (n_slices == 0 || n_slices > SRRG2B_MAX_SLICES) throw std::runtime_error("MultiAlignerB200_|bad number of slice processors");
+    slices.assign(n_slices, srrg2b_slice{});
     for (size_t s = 0; s < n_slices; ++s) {
       srrg2b_slice& d = slices[s];
       std::memset(&d, 0, sizeof(d));
@@ -44,7 +44,7 @@ public:
         // motion of AlignerSliceMotionModel_ (aligner_slice_motion_model.hpp:69-78); the adapter only reads the result.
         // The library lets the priors overwrite the initial guess in slice order (multi_aligner_impl.cpp:130-141).
         auto* p = dynamic_cast<PriorSlice*>(base);
-        if (!p) throw std::runtime_error("MultiAlignerB200_::compute|unknown prior slice type");
+        if (!p) throw std::runtime_error("MultiAlignerB200_|unknown prior slice type");
         p->setupFactor();
         d.kind = SRRG2B_SLICE_PRIOR;
         srrg2b_adapters::embed16(p->measurement(), d.prior_measurement);
@@ -52,7 +52,7 @@ public:
         continue;
       }
       auto* sp = dynamic_cast<PointSlice*>(base);
-      if (!sp || !sp->fixed() || !sp->moving()) throw std::runtime_error("MultiAlignerB200_::compute|slice without fixed or moving");
+      if (!sp) throw std::runtime_error("MultiAlignerB200_|unknown point slice type");
       d.kind = SRRG2B_SLICE_POINTS;
       d.slice_id = (int) s;
       d.min_num_correspondences = sp->param_min_num_correspondences.value();
@@ -72,10 +72,11 @@ public:
         else if (dynamic_cast<srrg2_solver::RobustifierClamp*>(rob.get())) d.factor.robustifier = SRRG2B_ROB_CLAMP;
         else d.factor.robustifier = SRRG2B_ROB_SATURATED;
       }
-      if (sp->fixedChanged()) upload(SRRG2B_FIXED, (int) s, *sp->fixed());
-      if (sp->movingChanged()) upload(SRRG2B_MOVING, (int) s, *sp->moving());
-      sp->clearChanged();
     }
+  }
+
+  // AlignerBase / MultiAlignerBase_ / termination-criterion parameters (aligner.h:30-35, multi_aligner.h:45-57)
+  srrg2b_aligner_params alignerParams() const {
     srrg2b_aligner_params ap;
     std::memset(&ap, 0, sizeof(ap));
     // (dim 2 contexts use VariableSE2Right whatever this field says)
@@ -91,6 +92,27 @@ public:
     ap.num_inliers_range = tc ? tc->param_num_inliers_range.value() : 20;
     ap.num_outliers_range = tc ? tc->param_num_outliers_range.value() : 20;
     ap.chi_epsilon = tc ? tc->param_chi_epsilon.value() : 0.2f;
+    return ap;
+  }
+
+  // the point slice behind slot s (null for a prior slice): its clouds are bound by Aligner::setFixed / setMoving
+  PointSlice* pointSlice(size_t s) const { return dynamic_cast<PointSlice*>(this->param_slice_processors.value(s).get()); }
+
+  void compute() override {
+    if (!_ctx) srrg2b_adapters::check(nullptr, srrg2b_ctx_create(Dim, param_device.value(), &_ctx) == SRRG2B_OK ? SRRG2B_OK : SRRG2B_ERR_CUDA,
+                                      "MultiAlignerB200_|no usable CUDA device (there is no CPU fallback)");
+    std::vector<srrg2b_slice> slices;
+    describeSlices(slices);
+    const size_t n_slices = slices.size();
+    for (size_t s = 0; s < n_slices; ++s) {
+      if (slices[s].kind != SRRG2B_SLICE_POINTS) continue;
+      PointSlice* sp = pointSlice(s);
+      if (!sp->fixed() || !sp->moving()) throw std::runtime_error("MultiAlignerB200_::compute|slice without fixed or moving");
+      if (sp->fixedChanged()) upload(SRRG2B_FIXED, (int) s, *sp->fixed());
+      if (sp->movingChanged()) upload(SRRG2B_MOVING, (int) s, *sp->moving());
+      sp->clearChanged();
+    }
+    const srrg2b_aligner_params ap = alignerParams();
     float T[16];
     srrg2b_adapters::to_row_major(this->movingInFixed(), T);
     std::vector<srrg2b_iter_stats> st(256);

@@ -5,6 +5,7 @@
 #pragma once
 #include <array>
 #include <cstdint>
+#include <map>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -48,6 +49,18 @@ struct PropertyConfigurableVector_ {
 };
 struct Configurable { virtual ~Configurable() = default; };
 
+// PropertyContainerBase: the dynamic properties of a local map / a measurement; an aligner slice looks its cloud up by
+// name (R/registration/aligners/aligner_slice_processor_base.h:160-168 bindSlice, R/mapping/local_map.h:15-31)
+struct PropertyContainerBase {
+  std::map<std::string, void*> _properties;
+  template <typename T>
+  T* property(const std::string& name) const {
+    auto it = _properties.find(name);
+    return it == _properties.end() ? nullptr : static_cast<T*>(it->second);
+  }
+};
+using PropertyContainerDynamic = PropertyContainerBase;
+
 // Correspondence(fixed_idx, moving_idx, response) (R/registration/loop_detector/multi_loop_detector_hbst_impl.cpp:183-191)
 struct Correspondence {
   int fixed_idx = -1, moving_idx = -1;
@@ -76,6 +89,27 @@ struct IsometryStub {
   }
   const Matrix& matrix() const { return _m; }
   Matrix& matrix() { return _m; }
+  // rigid inverse and composition (Eigen::Transform::inverse / operator* upstream;
+  // R/registration/loop_detector/multi_loop_detector_brute_force_impl.cpp:115)
+  IsometryStub inverse() const {
+    IsometryStub T = Identity();
+    for (int r = 0; r < D; ++r) {
+      float t = 0.f;
+      for (int c = 0; c < D; ++c) { T._m(r, c) = _m(c, r); t -= _m(c, r) * _m(c, D); }
+      T._m(r, D) = t;
+    }
+    return T;
+  }
+  IsometryStub operator*(const IsometryStub& o) const {
+    IsometryStub T;
+    for (int r = 0; r <= D; ++r)
+      for (int c = 0; c <= D; ++c) {
+        float v = 0.f;
+        for (int k = 0; k <= D; ++k) v += _m(r, k) * o._m(k, c);
+        T._m(r, c) = v;
+      }
+    return T;
+  }
 };
 using Isometry2f = IsometryStub<2>;
 using Isometry3f = IsometryStub<3>;

@@ -36,6 +36,10 @@ class AlignerSliceProcessorBase_ : public srrg2_core::Configurable {
 public:
   using EstimateType = EstimateType_;
   srrg2_core::PropertyConfigurable_<srrg2_solver::RobustifierBase> param_robustifier;  // :34-38
+  PARAM(srrg2_core::PropertyString, fixed_slice_name, "name of the slice in the fixed scene", "", nullptr);    // :40-45
+  PARAM(srrg2_core::PropertyString, moving_slice_name, "name of the slice in the moving scene", "", nullptr);  // :46-51
+  virtual void setFixed(srrg2_core::PropertyContainerBase*) {}   // :97-101 (binds the slice's cloud by name)
+  virtual void setMoving(srrg2_core::PropertyContainerBase*) {}  // :106-110
   virtual bool isPrior() const = 0;
   virtual ~AlignerSliceProcessorBase_() = default;
 };
@@ -47,6 +51,14 @@ public:
   srrg2_core::PropertyConfigurable_<CorrespondenceFinder_<EstimateType_, CloudType_, CloudType_>> param_finder;  // :56-60
   PARAM(srrg2_core::PropertyInt, min_num_correspondences, "", 0, nullptr);                                       // :62-66
   bool isPrior() const override { return false; }
+  void setFixed(srrg2_core::PropertyContainerBase* scene) override {
+    _fixed = scene ? scene->template property<CloudType>(this->param_fixed_slice_name.value()) : nullptr;
+    _fixed_changed = true;
+  }
+  void setMoving(srrg2_core::PropertyContainerBase* scene) override {
+    _moving = scene ? scene->template property<CloudType>(this->param_moving_slice_name.value()) : nullptr;
+    _moving_changed = true;
+  }
   CloudType* fixed() const { return _fixed; }      // bound by name from the tracker slice (…_base_impl.cpp:7-51)
   CloudType* moving() const { return _moving; }
   bool fixedChanged() const { return _fixed_changed; }
@@ -88,6 +100,12 @@ public:
   PARAM(srrg2_core::PropertyInt, min_num_inliers, "", 10, nullptr);                                         // :45-46
   PARAM(srrg2_core::PropertyBool, enable_inlier_only_runs, "", false, nullptr);                             // :47-51
   PARAM(srrg2_core::PropertyBool, keep_only_inlier_correspondences, "", false, nullptr);                    // :53-57
+  void setFixed(srrg2_core::PropertyContainerBase* scene) {   // multi_aligner_impl.cpp:8-14
+    for (size_t s = 0; s < param_slice_processors.size(); ++s) param_slice_processors.value(s)->setFixed(scene);
+  }
+  void setMoving(srrg2_core::PropertyContainerBase* scene) {  // multi_aligner_impl.cpp:18-24
+    for (size_t s = 0; s < param_slice_processors.size(); ++s) param_slice_processors.value(s)->setMoving(scene);
+  }
   void setMovingInFixed(const EstimateType& T) { _moving_in_fixed = T; }  // aligner.h:62-70
   const EstimateType& movingInFixed() const { return _moving_in_fixed; }
   void compute() override {}                                              // :95 (virtual upstream)

@@ -31,3 +31,22 @@ def test_adapters_name_every_entry_point_they_bind():
             used |= set(re.findall(r"\b(srrg2b_[a-z_0-9]+)\s*\(", open(os.path.join(ROOT, "adapters", name)).read()))
     used = {u for u in used if not u.startswith("srrg2b_adapters")}
     assert used and used <= declared, used - declared
+
+
+def test_loop_detector_adapter_links_and_fails_loudly_without_a_gpu(tmp_path):
+    """adapters/multi_loop_detector_b200.h driven over the stub SLAM surface: builds, links against libsrrg2b.so, and --
+    on a machine without a CUDA device -- compute() throws instead of falling back to anything."""
+    import torch
+    import __graft_entry__ as G
+    if not os.path.exists(G.LIB):
+        G.build_cuda()
+    exe = str(tmp_path / "adapter_detector_main")
+    libdir = os.path.dirname(G.LIB)
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-I", os.path.join(ROOT, "include"),
+                           "-I", os.path.join(ROOT, "adapters", "stubs"), "-I", os.path.join(ROOT, "adapters"),
+                           os.path.join(ROOT, "tests", "cpp", "adapter_detector_main.cpp"), "-o", exe,
+                           "-L", libdir, "-lsrrg2b", "-Wl,-rpath," + libdir])
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 3 and "no usable CUDA device" in r.stderr, (r.returncode, r.stderr)
