@@ -33,20 +33,39 @@ def test_adapters_name_every_entry_point_they_bind():
     assert used and used <= declared, used - declared
 
 
-def test_loop_detector_adapter_links_and_fails_loudly_without_a_gpu(tmp_path):
-    """adapters/multi_loop_detector_b200.h driven over the stub SLAM surface: builds, links against libsrrg2b.so, and --
-    on a machine without a CUDA device -- compute() throws instead of falling back to anything."""
-    import torch
+@pytest.fixture(scope="module")
+def detector_binary(tmp_path_factory):
+    """adapters/multi_loop_detector_b200.h driven over the stub SLAM surface, linked against libsrrg2b.so."""
     import __graft_entry__ as G
     if not os.path.exists(G.LIB):
         G.build_cuda()
-    exe = str(tmp_path / "adapter_detector_main")
+    exe = str(tmp_path_factory.mktemp("adapters") / "adapter_detector_main")
     libdir = os.path.dirname(G.LIB)
     subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-I", os.path.join(ROOT, "include"),
                            "-I", os.path.join(ROOT, "adapters", "stubs"), "-I", os.path.join(ROOT, "adapters"),
                            os.path.join(ROOT, "tests", "cpp", "adapter_detector_main.cpp"), "-o", exe,
                            "-L", libdir, "-lsrrg2b", "-Wl,-rpath," + libdir])
+    return exe
+
+
+def test_loop_detector_adapter_links_and_fails_loudly_without_a_gpu(detector_binary):
+    """On a machine without a CUDA device compute() throws instead of falling back to anything."""
+    import torch
     if torch.cuda.is_available():
         pytest.skip("a CUDA device is present")
-    r = subprocess.run([exe], capture_output=True, text=True)
+    r = subprocess.run([detector_binary], capture_output=True, text=True)
     assert r.returncode == 3 and "no usable CUDA device" in r.stderr, (r.returncode, r.stderr)
+
+
+@pytest.mark.gpu
+def test_loop_detector_adapter_detects_the_matching_map(detector_binary):
+    """Source map = an L-shaped corner; candidates: the same corner 3 cm off (accepted: every point an inlier) and a
+    corner 4 m away (the aligner drops it: no correspondences).  Reference flow:
+    R/registration/loop_detector/multi_loop_detector_brute_force_impl.cpp:63-133."""
+    r = subprocess.run([detector_binary], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.strip().splitlines()
+    assert lines[0] == "attempted 2 detected 1", lines
+    assert lines[1].startswith("verdict 0 inliers 3000 correspondences 3000"), lines
+    assert lines[2].startswith("verdict 1"), lines
+    assert lines[-1] == "closure -> map 1", lines
