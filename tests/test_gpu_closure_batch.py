@@ -127,3 +127,39 @@ def test_share_fixed_contract(capi):
     assert rb2["stats"] != ra["stats"]
     b.close()
     a.close()
+
+
+def test_closure_batch_edge_cases(oracle, capi):
+    """Empty batch, a candidate with an empty cloud, a candidate whose every point is masked out, a context listed twice:
+    the reference's loop would `continue` on the aligner status for the degenerate maps (:80-84); misuse is an error."""
+    d = syn.make_icp3d(8000, 3000, seed=13)
+    sl = [capi.make_slice(3, 0, None, capi.finder_params(0.3, 0.8), capi.factor_params(capi.FACTOR_PLANE, capi.ROB_HUBER, 0.01))]
+    ap = capi.aligner_params(max_iterations=5, min_num_inliers=10)
+    cp = capi.closure_params(50, 0.01, 0.5)
+    assert capi.closure_batch([], sl, ap, [], cp) == []
+    src = capi.Context(3)
+    src.set_cloud(capi.FIXED, 0, d["fixed"], d["fixed_normals"])
+    clouds = [(d["moving"], d["moving_normals"], None),
+              (np.zeros((0, 3), np.float32), np.zeros((0, 3), np.float32), None),
+              (d["moving"][:500], d["moving_normals"][:500], np.zeros(500, np.uint8))]
+    ctxs = []
+    for m, n, v in clouds:
+        x = capi.Context(3)
+        x.share_fixed(0, src, 0)
+        x.set_cloud(capi.MOVING, 0, m, n, v)
+        ctxs.append(x)
+    res = capi.closure_batch(ctxs, sl, ap, [np.eye(4, dtype=np.float32)] * 3, cp)
+    F = oracle.CloudRef(d["fixed"], d["fixed_normals"])
+    refs = [oracle.CloudRef(m, n, v) for m, n, v in clouds]
+    osl = [[oracle.make_slice(F, r, None, oracle.finder_params(0.3, 0.8), oracle.factor_params(oracle.FACTOR_PLANE, oracle.ROB_HUBER, 0.01))]
+           for r in refs]
+    want = oracle.closure_loop(3, osl, oracle.aligner_params(max_iterations=5, min_num_inliers=10), [np.eye(4, dtype=np.float32)] * 3, 50, 0.01, 0.5)
+    for g, w in zip(res, want):
+        assert g["verdict"] == w["verdict"] and g["aligner_status"] == w["aligner_status"], (g, w)
+        assert np.array_equal(g["T"], w["T"])
+    assert res[1]["verdict"] == capi.CLOSURE_ALIGNER_DROP and res[2]["verdict"] == capi.CLOSURE_ALIGNER_DROP
+    with pytest.raises(capi.Srrg2bError):
+        capi.closure_batch([ctxs[0], ctxs[0]], sl, ap, [np.eye(4, dtype=np.float32)] * 2, cp)
+    for x in ctxs:
+        x.close()
+    src.close()
