@@ -3,6 +3,7 @@
 #include "multi_aligner_b200.h"
 #include "solver_b200.h"
 #include "multi_loop_detector_b200.h"
+#include "scene_b200.h"
 
 template class srrg2_slam_interfaces::CorrespondenceFinderB200_<srrg2_core::Isometry2f, srrg2_core::PointNormal2fVectorCloud>;
 template class srrg2_slam_interfaces::CorrespondenceFinderB200_<srrg2_core::Isometry3f, srrg2_core::PointNormal3fVectorCloud>;
@@ -20,3 +21,7 @@ using SLAM3DStub = srrg2_slam_interfaces::SLAMAlgorithmStub<srrg2_slam_interface
 }  // namespace
 template class srrg2_slam_interfaces::MultiLoopDetectorBruteForceB200_<SLAM2DStub, srrg2_slam_interfaces::MultiAligner2DB200>;
 template class srrg2_slam_interfaces::MultiLoopDetectorBruteForceB200_<SLAM3DStub, srrg2_slam_interfaces::MultiAligner3DQRB200>;
+template class srrg2_slam_interfaces::SceneClipperRangeB200_<srrg2_core::Isometry2f, srrg2_core::PointNormal2fVectorCloud, srrg2_slam_interfaces::MultiAligner2DB200>;
+template class srrg2_slam_interfaces::SceneClipperRangeB200_<srrg2_core::Isometry3f, srrg2_core::PointNormal3fVectorCloud, srrg2_slam_interfaces::MultiAligner3DQRB200>;
+template class srrg2_slam_interfaces::MergerCorrespondenceHomoB200_<srrg2_core::Isometry2f, srrg2_core::PointNormal2fVectorCloud, srrg2_slam_interfaces::MultiAligner2DB200>;
+template class srrg2_slam_interfaces::MergerCorrespondenceHomoB200_<srrg2_core::Isometry3f, srrg2_core::PointNormal3fVectorCloud, srrg2_slam_interfaces::MultiAligner3DQRB200>;

@@ -98,18 +98,33 @@ public:
   // the point slice behind slot s (null for a prior slice): its clouds are bound by Aligner::setFixed / setMoving
   PointSlice* pointSlice(size_t s) const { return dynamic_cast<PointSlice*>(this->param_slice_processors.value(s).get()); }
 
-  void compute() override {
+  // The library context of this aligner (created on first use): the scene adapters (scene_b200.h) keep the local map
+  // on the same device context, so that a clipped scene becomes a slice's moving cloud without crossing PCIe.
+  srrg2b_ctx* context() {
     if (!_ctx) srrg2b_adapters::check(nullptr, srrg2b_ctx_create(Dim, param_device.value(), &_ctx) == SRRG2B_OK ? SRRG2B_OK : SRRG2B_ERR_CUDA,
                                       "MultiAlignerB200_|no usable CUDA device (there is no CPU fallback)");
+    return _ctx;
+  }
+  // SceneClipperRangeB200_::compute() has written slice s's moving cloud on the device (n_points of them): compute()
+  // neither expects nor uploads a host cloud for it until setMovingResident(s, -1).
+  void setMovingResident(size_t s, int64_t n_points) {
+    if (_resident.size() <= s) _resident.resize(s + 1, -1);
+    _resident[s] = n_points;
+  }
+  int64_t movingResident(size_t s) const { return s < _resident.size() ? _resident[s] : -1; }
+
+  void compute() override {
+    context();
     std::vector<srrg2b_slice> slices;
     describeSlices(slices);
     const size_t n_slices = slices.size();
     for (size_t s = 0; s < n_slices; ++s) {
       if (slices[s].kind != SRRG2B_SLICE_POINTS) continue;
       PointSlice* sp = pointSlice(s);
-      if (!sp->fixed() || !sp->moving()) throw std::runtime_error("MultiAlignerB200_::compute|slice without fixed or moving");
+      const bool resident = movingResident(s) >= 0;
+      if (!sp->fixed() || (!resident && !sp->moving())) throw std::runtime_error("MultiAlignerB200_::compute|slice without fixed or moving");
       if (sp->fixedChanged()) upload(SRRG2B_FIXED, (int) s, *sp->fixed());
-      if (sp->movingChanged()) upload(SRRG2B_MOVING, (int) s, *sp->moving());
+      if (!resident && sp->movingChanged()) upload(SRRG2B_MOVING, (int) s, *sp->moving());
       sp->clearChanged();
     }
     const srrg2b_aligner_params ap = alignerParams();
@@ -136,7 +151,7 @@ public:
     for (size_t s = 0; s < n_slices; ++s) {
       if (slices[s].kind != SRRG2B_SLICE_POINTS) continue;
       auto* sp = static_cast<PointSlice*>(this->param_slice_processors.value(s).get());
-      const size_t n = sp->moving()->size();
+      const size_t n = movingResident(s) >= 0 ? (size_t) movingResident(s) : sp->moving()->size();
       _fi.resize(n); _mi.resize(n); _rs.resize(n);
       int64_t m = 0;
       srrg2b_adapters::check(_ctx, srrg2b_get_correspondences(_ctx, (int) s, _fi.data(), _mi.data(), _rs.data(), &m),
@@ -155,6 +170,7 @@ private:
     srrg2b_adapters::check(_ctx, srrg2b_set_cloud(_ctx, slot, slice, &c), "MultiAlignerB200_::upload");
   }
   srrg2b_ctx* _ctx = nullptr;
+  std::vector<int64_t> _resident;
   std::vector<int32_t> _fi, _mi;
   std::vector<float> _rs;
 };

@@ -69,3 +69,41 @@ def test_loop_detector_adapter_detects_the_matching_map(detector_binary):
     assert lines[1].startswith("verdict 0 inliers 3000 correspondences 3000"), lines
     assert lines[2].startswith("verdict 1"), lines
     assert lines[-1] == "closure -> map 1", lines
+
+
+@pytest.fixture(scope="module")
+def tracker_binary(tmp_path_factory):
+    """adapters/scene_b200.h + multi_aligner_b200.h: one tracker frame (clip -> align -> merge) over the stub surface."""
+    import __graft_entry__ as G
+    if not os.path.exists(G.LIB):
+        G.build_cuda()
+    exe = str(tmp_path_factory.mktemp("adapters") / "adapter_tracker_main")
+    libdir = os.path.dirname(G.LIB)
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-I", os.path.join(ROOT, "include"),
+                           "-I", os.path.join(ROOT, "adapters", "stubs"), "-I", os.path.join(ROOT, "adapters"),
+                           os.path.join(ROOT, "tests", "cpp", "adapter_tracker_main.cpp"), "-o", exe,
+                           "-L", libdir, "-lsrrg2b", "-Wl,-rpath," + libdir])
+    return exe
+
+
+def test_scene_adapters_link_and_fail_loudly_without_a_gpu(tracker_binary):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    r = subprocess.run([tracker_binary], capture_output=True, text=True)
+    assert r.returncode == 3 and "no usable CUDA device" in r.stderr, (r.returncode, r.stderr)
+
+
+@pytest.mark.gpu
+def test_scene_adapters_run_a_tracker_frame(tracker_binary):
+    """Local map = two 12 m walls (6000 points), scan = their first 8 m, 2.5 cm off.  The range clipper (9 m) keeps the
+    4502 map points within range, the aligner -- its moving cloud resident, only the scan uploaded -- recovers the offset
+    with every correspondence an inlier, the merger merges 1999 scan points and appends the remaining one
+    (R/trackers/multi_tracker_impl.cpp:82-138, R/trackers/tracker_slice_processor_impl.cpp:159-205)."""
+    r = subprocess.run([tracker_binary], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.strip().splitlines()
+    assert lines[0] == "clipped 4502 status 1", lines
+    assert lines[1] == "aligner status 0 correspondences 4247 inliers 4247", lines
+    assert lines[2] == "merged 1999 added 1 scene 6000 -> 6001", lines
+    assert lines[3] == "map in scan: tx 0.0200 ty -0.0150", lines
