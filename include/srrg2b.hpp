@@ -429,6 +429,15 @@ public:
   void setSource(const CloudType* source) { _fixed = source; _fixed_changed = true; }
   const std::vector<Closure>& detectedClosures() const { return _detected; }
   const std::vector<srrg2b_closure_result>& results() const { return _results; }
+  // MultiRelocalizer_::compute's choice (R/registration/relocalization/multi_relocalizer_impl.cpp:119-131): among the
+  // accepted candidates the one with the smallest chi per inlier, the first one on ties; -1: none (index into
+  // detectedClosures()).  Its correspondences stay in its context (storeCorrespondences(), :130).
+  int bestDetectedByChi() const {
+    int best = -1;
+    for (size_t k = 0; k < _detected.size(); ++k)
+      if (best < 0 || _detected[k].chi_inliers < _detected[(size_t) best].chi_inliers) best = (int) k;
+    return best;
+  }
 
   void compute(const std::vector<Hint>& hints) {
     _detected.clear();

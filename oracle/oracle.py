@@ -315,7 +315,24 @@ def closure_loop(dim, candidate_slices, ap, guesses, min_inliers=500, max_chi_in
     return out
 
 
-def scales(dim, variable, radius_bound2, fp, fa, normal_bound2=1.0):
+def relocalize_loop(dim, candidate_slices, ap, guesses, translations, max_translation, min_inliers=500, max_chi_inliers=0.005,
+                    min_inliers_ratio=0.7):
+    """MultiRelocalizer_::compute, alignment branch (R/registration/relocalization/multi_relocalizer_impl.cpp:74-138):
+    the detector's loop with a translation pre-filter (:79-83) and `best = smallest chi per inlier, first on ties` (:121-131).
+    Returns (index of the relocalisation map or None, per-candidate results with None for the pre-filtered ones)."""
+    out, best, best_chi = [], None, np.float32(np.finfo(np.float32).max)
+    for k, (slices, g) in enumerate(zip(candidate_slices, guesses)):
+        if translations[k] > max_translation:                              # :79-83
+            out.append(None)
+            continue
+        r = closure_loop(dim, [slices], ap, [g], min_inliers, max_chi_inliers, min_inliers_ratio)[0]
+        out.append(r)
+        if r["verdict"] == CLOSURE_ACCEPT and r["chi_inliers"] < best_chi:  # :119-121
+            best, best_chi = k, r["chi_inliers"]
+    return best, out
+
+
+
     s = Scales()
     lib().orc_scales(dim, variable, radius_bound2, normal_bound2, C.byref(fp), C.byref(fa), C.byref(s))
     return tuple(s.k)

@@ -231,6 +231,23 @@ def closure_batch(contexts, slices, ap, guesses, cp):
     return out
 
 
+def relocalize_select(results, pose_in_target_translations=None, max_translation=None):
+    """MultiRelocalizer_::compute's choice among the candidates (R/registration/relocalization/
+    multi_relocalizer_impl.cpp:77-131): candidates whose guess lies farther than param_max_translation are not aligned
+    at all (:79-83; pass their translation norms and the bound, their results are ignored), the others go through the
+    detector's gates (closure_batch did that), and the accepted candidate with the SMALLEST chi per inlier wins --
+    strictly smaller, so the first one on ties (:121).  Returns its index, or None."""
+    best, best_chi = None, float("inf")
+    for k, r in enumerate(results):
+        if max_translation is not None and pose_in_target_translations is not None and pose_in_target_translations[k] > max_translation:
+            continue
+        if r["verdict"] != CLOSURE_ACCEPT:
+            continue
+        if float(r["chi_inliers"]) < best_chi:
+            best, best_chi = k, float(r["chi_inliers"])
+    return best
+
+
 def _ptr(a):
     return None if a is None else a.ctypes.data
 
