@@ -8,6 +8,11 @@ iterations of the configuration over the resident clouds.
   value  device-timed (CUDA events on the context stream around the graph-replayed run), clouds resident in
          HBM, COLD: the slice's correspondences / warm-start candidates / certified bounds are forgotten before
          every timed step, as a tracker's fresh setMoving() would (the warm figure is reported beside it)
+  roofline                       algorithmic bytes of one iteration / (device time of the run / iterations): the whole
+                                 run, searching iterations included
+  roofline_converged_iteration   the same for the converged iterations alone, measured in the same run: the cold step
+                                 repeated with half of the iterations, the difference is the second half (their kernel,
+                                 check_tiles_kernel, is the dominant one of the run)
   e2e    the same step through the C ABI with HOST (pinned) buffers: H2D of the clouds, index build, all
          iterations, D2H of pose + IterationStats inside the timed region.  N > 1: the replicated fixed cloud
          crosses PCIe once IN TOTAL (every rank uploads 1/N of it) and is all-gathered over NVLink; every rank
