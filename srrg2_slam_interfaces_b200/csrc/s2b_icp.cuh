@@ -475,6 +475,9 @@ __global__ void fill_int_kernel(int* p, int n, int v) {
 //                   as the warm-start candidate of the next iteration)
 //   kSlotSuppressed externally supplied correspondence that cannot be evaluated
 constexpr int kSlotSuppressed = INT_MIN;
+#ifndef S2B_ROW_WIDTH
+#define S2B_ROW_WIDTH 4  // candidates per trip of a row walk (2 or 4)
+#endif
 constexpr int kMaxR = 4;
 constexpr int kRowTable = (2 * kMaxR + 1) * (2 * kMaxR + 1);
 
@@ -550,6 +553,19 @@ __device__ __forceinline__ void nn_scan_row(const SliceArgs& a, NNQuery& q, int 
   // walk -- examines 4x fewer candidates but is 20-35% SLOWER: the search adds dependent L2 round trips
   // to a walk whose loads are otherwise all independent.  The x order pays off in shared memory only.)
   const int last = pe - 1;
+#if S2B_ROW_WIDTH == 2
+  // (experiment, -DS2B_ROW_WIDTH=2: a CPU simulation of the walk -- tools/cell_size_study.py -- finds ~1.3 points per
+  // visited run at C2, so a four-wide trip spends most of its slots on padding; measured, two per trip is SLOWER all
+  // the same -- iterations 1 / 2 / 3: 277 / 188 / 174 us against 241 / 166 / 172 us -- the loads in flight are worth
+  // more than the padded slots cost)
+#pragma unroll 1
+  for (int p = ps; p < pe; p += 2) {
+    const float4 c0 = __ldg(a.fp + p);
+    const float4 c1 = __ldg(a.fp + min(p + 1, last));
+    nn_consider_pt<DIM, TRACK2>(q, p, c0);
+    if (p + 1 < pe) nn_consider_pt<DIM, TRACK2>(q, p + 1, c1);
+  }
+#else
 #pragma unroll 1
   for (int p = ps; p < pe; p += 4) {
     const float4 c0 = __ldg(a.fp + p);
@@ -561,6 +577,7 @@ __device__ __forceinline__ void nn_scan_row(const SliceArgs& a, NNQuery& q, int 
     if (p + 2 < pe) nn_consider_pt<DIM, TRACK2>(q, p + 2, c2);
     if (p + 3 < pe) nn_consider_pt<DIM, TRACK2>(q, p + 3, c3);
   }
+#endif
 }
 
 // Up to 8 rows of the search neighbourhood in one go, SIMT-friendly.  rows[k0..k1) are packed table entries
@@ -632,6 +649,13 @@ __device__ __forceinline__ void nn_scan_rows8(const SliceArgs& a, NNQuery& q, co
     }
     if (p < end) {
       const int last = end - 1;
+#if S2B_ROW_WIDTH == 2
+      const float4 c0 = __ldg(a.fp + p);
+      const float4 c1 = __ldg(a.fp + min(p + 1, last));
+      nn_consider_pt<DIM, TRACK2>(q, p, c0);
+      if (p + 1 < end) nn_consider_pt<DIM, TRACK2>(q, p + 1, c1);
+      p += 2;
+#else
       const float4 c0 = __ldg(a.fp + p);
       const float4 c1 = __ldg(a.fp + min(p + 1, last));
       const float4 c2 = __ldg(a.fp + min(p + 2, last));
@@ -641,6 +665,7 @@ __device__ __forceinline__ void nn_scan_rows8(const SliceArgs& a, NNQuery& q, co
       if (p + 2 < end) nn_consider_pt<DIM, TRACK2>(q, p + 2, c2);
       if (p + 3 < end) nn_consider_pt<DIM, TRACK2>(q, p + 3, c3);
       p += 4;
+#endif
     }
   }
 }

@@ -1,5 +1,6 @@
 #!/bin/bash
-TAG=${1:-exp}; OUT=$PWD/gpurun_out/$TAG; mkdir -p $OUT
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -2
-for r in 1 2; do timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu-baseline 2> $OUT/err.txt | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['value'])"; done
-timeout 600 python bench.py --config c5 --steps 5 --warmup 3 --no-cpu-baseline 2> $OUT/err.txt | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['value'])"
+# experiment: two candidates per trip of a row walk (library variant built with -DS2B_ROW_WIDTH=2)
+W2=$PWD/srrg2_slam_interfaces_b200/libsrrg2b_w2.so
+SRRG2B_LIB=$W2 python tools/iter_profile.py 1000000 4
+python tools/iter_profile.py 1000000 4
+SRRG2B_LIB=$W2 timeout 20 python -m pytest tests/test_gpu_parity_icp.py -m gpu -x -q 2>&1 | tail -2
